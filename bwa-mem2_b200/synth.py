@@ -1,0 +1,193 @@
+"""Seeded synthetic inputs for the seed-and-extend hot path.
+
+Reference genomes: several contigs, planted repeat families (diverged copies), tandem repeats,
+low-complexity runs and a few N runs (so .amb is non-trivial).  Reads: 2x151 bp pairs, insert
+N(400,40), substitutions / insertions / deletions / N, plus chimeric and garbage reads.
+Pure numpy; deterministic for a given seed.  Not part of the product path.
+"""
+from __future__ import annotations
+import numpy as np
+
+_ALPHA = np.frombuffer(b"ACGTN", dtype=np.uint8)
+_COMP = np.array([3, 2, 1, 0, 4], dtype=np.uint8)
+
+
+def make_reference(total_bp: int, seed: int = 1, n_contigs: int = 4, repeat_frac: float = 0.15,
+                   n_runs: int = 3):
+    """Returns list of (name, codes uint8 array in 0..4)."""
+    rng = np.random.default_rng(seed)
+    # contig lengths: geometric-ish split
+    w = np.array([0.5 ** i for i in range(n_contigs)], dtype=np.float64)
+    lens = np.maximum((w / w.sum() * total_bp).astype(np.int64), 1000)
+    contigs = [rng.integers(0, 4, size=int(l), dtype=np.uint8) for l in lens]
+    # repeat families
+    budget = int(total_bp * repeat_frac)
+    while budget > 0:
+        L = int(rng.integers(200, 3000))
+        copies = int(rng.integers(3, 60))
+        div = float(rng.choice([0.0, 0.005, 0.02, 0.05, 0.10]))
+        unit = rng.integers(0, 4, size=L, dtype=np.uint8)
+        for _ in range(copies):
+            c = int(rng.integers(0, n_contigs))
+            if len(contigs[c]) <= L + 10:
+                continue
+            p = int(rng.integers(0, len(contigs[c]) - L))
+            u = unit.copy()
+            if div > 0:
+                m = rng.random(L) < div
+                u[m] = (u[m] + rng.integers(1, 4, size=int(m.sum()), dtype=np.uint8)) & 3
+            if rng.random() < 0.5:
+                u = (3 - u)[::-1]
+            contigs[c][p:p + L] = u
+            budget -= L
+    # tandem repeats and low-complexity
+    for _ in range(max(4, total_bp // 500_000)):
+        c = int(rng.integers(0, n_contigs))
+        ul = int(rng.integers(1, 40))
+        tot = int(rng.integers(60, 600))
+        if len(contigs[c]) <= tot + 10:
+            continue
+        p = int(rng.integers(0, len(contigs[c]) - tot))
+        unit = rng.integers(0, 4, size=ul, dtype=np.uint8)
+        contigs[c][p:p + tot] = np.tile(unit, tot // ul + 1)[:tot]
+    # N runs
+    for _ in range(n_runs):
+        c = int(rng.integers(0, n_contigs))
+        tot = int(rng.integers(50, 800))
+        if len(contigs[c]) <= tot + 10:
+            continue
+        p = int(rng.integers(0, len(contigs[c]) - tot))
+        contigs[c][p:p + tot] = 4
+    return [(f"chr{i + 1}", contigs[i]) for i in range(n_contigs)]
+
+
+def write_fasta(path: str, contigs, width: int = 80):
+    with open(path, "wb") as f:
+        for name, codes in contigs:
+            f.write(b">" + name.encode() + b"\n")
+            s = _ALPHA[codes]
+            n = len(s)
+            full = (n // width) * width
+            if full:
+                body = np.empty((n // width, width + 1), dtype=np.uint8)
+                body[:, :width] = s[:full].reshape(-1, width)
+                body[:, width] = 10
+                f.write(body.tobytes())
+            if n > full:
+                f.write(s[full:].tobytes() + b"\n")
+
+
+def _mutate(rng, codes, sub, ins, dele, nrate, out_len):
+    """Apply errors to a template (codes longer than out_len), return exactly out_len codes."""
+    out = []
+    i = 0
+    n = len(codes)
+    r = rng.random(size=3 * out_len + 16)
+    k = 0
+    while len(out) < out_len:
+        if i >= n:
+            out.append(int(rng.integers(0, 4)))
+            continue
+        x = r[k % len(r)]; k += 1
+        if x < dele:
+            i += 1
+            continue
+        if x < dele + ins:
+            out.append(int(rng.integers(0, 4)))
+            continue
+        b = int(codes[i]); i += 1
+        if b > 3:
+            b = 4
+        elif x < dele + ins + sub:
+            b = (b + int(rng.integers(1, 4))) & 3
+        elif x < dele + ins + sub + nrate:
+            b = 4
+        out.append(b)
+    return np.array(out, dtype=np.uint8)
+
+
+def make_pairs(contigs, n_pairs: int, read_len: int = 151, seed: int = 2, ins_mean: float = 400.0,
+               ins_sd: float = 40.0, sub: float = 0.01, ins: float = 0.0015, dele: float = 0.0005,
+               nrate: float = 0.001, garbage: float = 0.02):
+    """Returns (r1, r2): arrays [n_pairs, read_len] of codes 0..4."""
+    rng = np.random.default_rng(seed)
+    lens = np.array([len(c) for _, c in contigs], dtype=np.float64)
+    prob = lens / lens.sum()
+    r1 = np.empty((n_pairs, read_len), dtype=np.uint8)
+    r2 = np.empty((n_pairs, read_len), dtype=np.uint8)
+    pad = read_len // 8 + 8
+    for p in range(n_pairs):
+        g = rng.random()
+        if g < garbage / 2:
+            r1[p] = rng.integers(0, 4, size=read_len, dtype=np.uint8)
+            r2[p] = rng.integers(0, 4, size=read_len, dtype=np.uint8)
+            continue
+        while True:
+            c = int(rng.choice(len(contigs), p=prob))
+            ref = contigs[c][1]
+            isz = max(int(rng.normal(ins_mean, ins_sd)), read_len + 5)
+            if len(ref) > isz + 2 * pad:
+                break
+        st = int(rng.integers(0, len(ref) - isz - pad))
+        frag = ref[st:st + isz + pad]
+        a = frag[:read_len + pad]
+        b = _COMP[frag[max(0, isz - read_len - pad):isz]][::-1]
+        if rng.random() < 0.5:  # fragment from the reverse strand
+            a, b = b, a
+        m1 = _mutate(rng, a, sub, ins, dele, nrate, read_len)
+        m2 = _mutate(rng, b, sub, ins, dele, nrate, read_len)
+        if g < garbage:  # chimeric: second half of read 1 from elsewhere
+            c2 = int(rng.choice(len(contigs), p=prob))
+            ref2 = contigs[c2][1]
+            s2 = int(rng.integers(0, max(1, len(ref2) - read_len)))
+            h = int(rng.integers(40, read_len - 40))
+            alt = ref2[s2:s2 + read_len - h]
+            if len(alt) == read_len - h:
+                m1[h:] = alt if rng.random() < 0.5 else _COMP[alt][::-1]
+        r1[p] = m1
+        r2[p] = m2
+    return r1, r2
+
+
+def make_long_reads(contigs, n_reads: int, read_len: int = 10000, seed: int = 3, sub: float = 0.04,
+                    ins: float = 0.03, dele: float = 0.03):
+    rng = np.random.default_rng(seed)
+    lens = np.array([len(c) for _, c in contigs], dtype=np.float64)
+    prob = lens / lens.sum()
+    out = []
+    for _ in range(n_reads):
+        while True:
+            c = int(rng.choice(len(contigs), p=prob))
+            ref = contigs[c][1]
+            if len(ref) > read_len * 1.2 + 100:
+                break
+        st = int(rng.integers(0, len(ref) - int(read_len * 1.2)))
+        t = ref[st:st + int(read_len * 1.2)]
+        if rng.random() < 0.5:
+            t = _COMP[t][::-1]
+        out.append(_mutate(rng, t, sub, ins, dele, 0.0, read_len))
+    return out
+
+
+def write_fastq(path: str, reads, prefix: str = "r", suffix: str = ""):
+    with open(path, "wb") as f:
+        for i, codes in enumerate(reads):
+            s = _ALPHA[codes].tobytes()
+            f.write(b"@" + f"{prefix}{i}{suffix}".encode() + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n")
+
+
+if __name__ == "__main__":
+    import argparse, os
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--ref-bp", type=int, default=10_000_000)
+    ap.add_argument("--pairs", type=int, default=10_000)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--contigs", type=int, default=4)
+    a = ap.parse_args()
+    os.makedirs(a.out, exist_ok=True)
+    ctg = make_reference(a.ref_bp, seed=a.seed, n_contigs=a.contigs)
+    write_fasta(os.path.join(a.out, "ref.fa"), ctg)
+    r1, r2 = make_pairs(ctg, a.pairs, seed=a.seed + 1)
+    write_fastq(os.path.join(a.out, "r1.fq"), r1, "p")
+    write_fastq(os.path.join(a.out, "r2.fq"), r2, "p")

@@ -1,0 +1,190 @@
+/* bm2_b200.h — C ABI of libbm2b200.so: the B200-native seed-and-extend hot path of bwa-mem2.
+ *
+ * Plain C, pointers and sizes only.  Every entry point names the reference interface it replaces
+ * (file:line under bwa-mem2 @ 97978f95).  The reference has no FFI; the seam is the C++ function
+ * boundary below `mem_process_seqs` (src/bwamem.cpp:1338): `kt_for(worker_bwt)` + `kt_for(worker_aln)`
+ * (src/bwamem.cpp:1359,1363), and the finer seams `BandedPairWiseSW::getScores16/getScores8/
+ * scalarBandedSWAWrapper` (src/bandedSWA.h:130-297) and `FMI_search::getSMEMs*`/
+ * `get_sa_entries_prefetch` (src/FMI_search.h:106-165).  INTEGRATION.md shows the reference-side
+ * binding.  All functions return 0 on success, non-zero on error (`bm2_last_error`); there is no
+ * CPU fallback: without a usable CUDA device every compute entry fails.
+ */
+#ifndef BM2_B200_H
+#define BM2_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BM2_ABI_VERSION 1
+
+typedef struct bm2_ctx bm2_ctx;
+
+/* Field-for-field mirror of `mem_opt_t` (src/bwamem.h:76-108) so a `const mem_opt_t*` can be
+ * passed as `const bm2_mem_opt_t*`; defaults: src/bwamem.cpp:107-143. */
+typedef struct bm2_mem_opt_t {
+    int a, b;
+    int o_del, e_del;
+    int o_ins, e_ins;
+    int pen_unpaired;
+    int pen_clip5, pen_clip3;
+    int w;
+    int zdrop;
+    uint64_t max_mem_intv;
+    int T;
+    int flag;
+    int min_seed_len;
+    int min_chain_weight;
+    int max_chain_extend;
+    float split_factor;
+    int split_width;
+    int max_occ;
+    int max_chain_gap;
+    int n_threads;
+    int64_t chunk_size;
+    float mask_level;
+    float drop_ratio;
+    float XA_drop_ratio;
+    float mask_level_redun;
+    float mapQ_coef_len;
+    int mapQ_coef_fac;
+    int max_ins;
+    int max_matesw;
+    int max_XA_hits, max_XA_hits_alt;
+    int8_t mat[25];
+} bm2_mem_opt_t;
+
+/* `mem_opt_init()` defaults (src/bwamem.cpp:107-143) incl. `bwa_fill_scmat` (src/bwa.cpp:248). */
+void bm2_opt_init(bm2_mem_opt_t *opt);
+
+/* One checkpoint of the 2bit.64 Occ table: `CP_OCC` (src/FMI_search.h:54-58). */
+typedef struct bm2_cp_occ {
+    int64_t  cp_count[4];
+    uint64_t one_hot_bwt_str[4];
+} bm2_cp_occ;
+
+/* Host view of the index the hot path reads (src/FMI_search.h:167-177, src/bntseq.h:53-61,
+ * `ref_string` src/fastmap.cpp:860-881).  All pointers are HOST memory owned by the caller;
+ * `bm2_create` copies them to HBM. */
+typedef struct bm2_index_desc {
+    int64_t reference_seq_len;      /* N = 2*l_pac + 1 (BWT length incl. sentinel)              */
+    int64_t count[5];               /* as held in memory after load: (#symbols < b) + 1         */
+    int64_t sentinel_index;
+    const bm2_cp_occ *cp_occ;       /* (N >> 6) + 1 entries                                     */
+    const int8_t   *sa_ms_byte;     /* (N >> 3) + 1 entries: bits 32..39 of sampled SA          */
+    const uint32_t *sa_ls_word;     /* (N >> 3) + 1 entries: bits 0..31                         */
+    const uint8_t  *ref_string;     /* 2*l_pac codes 0..3: forward then reverse complement      */
+    int64_t l_pac;
+    int32_t n_seqs;                 /* contigs (bntseq_t::n_seqs)                               */
+    const int64_t *ann_offset;      /* n_seqs (bntann1_t::offset)                               */
+    const int32_t *ann_len;         /* n_seqs (bntann1_t::len)                                  */
+    const int32_t *ann_is_alt;      /* n_seqs, may be NULL (bntann1_t::is_alt)                  */
+} bm2_index_desc;
+
+/* Native loader of `<prefix>.bwt.2bit.64`, `.0123`, `.ann` (+ `.alt`): replaces
+ * FMI_search::load_index (src/FMI_search.cpp:384-494), bwa_idx_load_ele (read_index_ele.cpp:60)
+ * and the ref_string read (fastmap.cpp:860-881).  The returned descriptor owns its host memory. */
+int  bm2_index_load(const char *prefix, bm2_index_desc **out);
+void bm2_index_free(bm2_index_desc *idx);
+
+/* Create a device context on CUDA device `device`: uploads the index to HBM and fixes the
+ * parameters.  `idx` may be NULL for a BSW-only context (bm2_extend_pairs). */
+int  bm2_create(bm2_ctx **out, int device, const bm2_index_desc *idx, const bm2_mem_opt_t *opt);
+void bm2_destroy(bm2_ctx *ctx);
+const char *bm2_last_error(const bm2_ctx *ctx);   /* ctx may be NULL: last create error */
+int  bm2_abi_version(void);
+
+/* ---- seam 1: batched banded-SW seed extension -------------------------------------------------
+ * Layout-compatible with `SeqPair` (src/bandedSWA.h:90-99). */
+typedef struct bm2_seqpair {
+    int32_t idr, idq, id;
+    int32_t len1, len2;
+    int32_t h0;
+    int32_t seqid, regid;
+    int32_t score, tle, gtle, qle;
+    int32_t gscore, max_off;
+} bm2_seqpair;
+
+/* Replaces BandedPairWiseSW::getScores16 / getScores8 / scalarBandedSWAWrapper
+ * (src/bandedSWA.cpp:2664, :1970, :242; AVX2 twins :1117, :412): for pair i, target = seq_buf_ref + idr (len1 codes 0..4),
+ * query = seq_buf_qer + idq (len2), start score h0, band w; writes score/tle/gtle/qle/gscore/
+ * max_off in place.  `end_bonus` is the constructor's end_bonus (pen_clip5 for left, pen_clip3 for
+ * right extensions, src/bwamem.cpp:2456-2462).  Host buffers; copies are done inside. */
+int bm2_extend_pairs(bm2_ctx *ctx, bm2_seqpair *pairs, const uint8_t *seq_buf_ref,
+                     const uint8_t *seq_buf_qer, int32_t n_pairs, int32_t w, int32_t end_bonus);
+
+/* Device-resident variant used by the throughput bench: same contract, all pointers are DEVICE
+ * memory, the launch goes to the context's stream, no host sync.  `cells_out` (device, may be
+ * NULL) accumulates the banded DP cells actually computed (sum over rows of end-beg). */
+int bm2_extend_pairs_device(bm2_ctx *ctx, bm2_seqpair *d_pairs, const uint8_t *d_ref,
+                            const uint8_t *d_qer, int32_t n_pairs, int32_t w, int32_t end_bonus,
+                            unsigned long long *d_cells_out);
+
+/* ---- seam 2: the whole hot path over a chunk of reads -----------------------------------------
+ * Output record: layout-compatible with `mem_alnreg_t` (src/bwamem.h:137-160); the pointer slot
+ * `c` is always NULL on output. */
+typedef struct bm2_alnreg_t {
+    int64_t rb, re;
+    int32_t qb, qe;
+    int32_t rid;
+    void   *c;
+    int32_t score, truesc, sub, alt_sc, csub, sub_n, w, seedcov, secondary, secondary_all, seedlen0;
+    int32_t n_comp_is_alt;          /* bit-field word: n_comp:30, is_alt:2                      */
+    float   frac_rep;
+    uint64_t hash;
+    int32_t flg;
+} bm2_alnreg_t;
+
+/* SMEM record: `SMEM` (src/FMI_search.h:75-83). */
+typedef struct bm2_smem {
+    uint32_t rid;
+    uint32_t m, n;
+    int64_t  k, l, s;
+} bm2_smem;
+
+/* Seed / chain records (src/bwamem.h:113-135) as flat arrays. */
+typedef struct bm2_seed {
+    int64_t rbeg;
+    int32_t qbeg, len, score;
+    int32_t chain;                  /* index into the chunk's chain array                       */
+} bm2_seed;
+
+typedef struct bm2_chain {
+    int64_t pos;
+    int32_t seqid, rid;
+    int32_t n_seeds, seed_off;      /* seeds [seed_off, seed_off+n_seeds) of the chunk's seeds   */
+    int32_t w, kept, first, is_alt;
+    float   frac_rep;
+    int32_t _pad;
+} bm2_chain;
+
+/* A chunk of reads: concatenated base codes (0..3 = ACGT, 4 = other; exactly what
+ * src/bwamem.cpp:992-1000 leaves in bseq1_t::seq) and n_reads+1 offsets. */
+typedef struct bm2_read_batch {
+    int32_t n_reads;
+    const uint8_t *codes;
+    const int64_t *offsets;
+} bm2_read_batch;
+
+/* Result arrays are owned by the context (pinned host memory) and stay valid until the next call
+ * on the same context. */
+typedef struct bm2_smem_result  { int64_t n; const bm2_smem *smems; const int64_t *read_off; } bm2_smem_result;
+typedef struct bm2_chain_result { int64_t n_chains, n_seeds; const bm2_chain *chains; const bm2_seed *seeds;
+                                  const int64_t *read_off; /* n_reads+1 offsets into chains */ } bm2_chain_result;
+typedef struct bm2_reg_result   { int64_t n; const bm2_alnreg_t *regs; const int64_t *read_off; } bm2_reg_result;
+
+/* Replaces mem_collect_smem (src/bwamem.cpp:626-804): three SMEM passes + ordering. */
+int bm2_collect_smems(bm2_ctx *ctx, const bm2_read_batch *reads, bm2_smem_result *out);
+/* Replaces mem_kernel1_core (src/bwamem.cpp:976-1091): SMEMs + SA lookup + chaining + filters. */
+int bm2_seed_chain(bm2_ctx *ctx, const bm2_read_batch *reads, bm2_chain_result *out);
+/* Replaces kt_for(worker_bwt) + kt_for(worker_aln) (src/bwamem.cpp:1359-1363): regs per read as
+ * left by mem_kernel2_core (src/bwamem.cpp:1093-1172). */
+int bm2_seed_chain_extend(bm2_ctx *ctx, const bm2_read_batch *reads, bm2_reg_result *out);
+
+/* Per-stage device times (ms, CUDA events) of the last seam-2 call; names in `names`. */
+int bm2_last_stage_ms(const bm2_ctx *ctx, const char *const **names, const float **ms, int *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BM2_B200_H */
