@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the B200 seed-and-extend hot path (BASELINE.json metric: paired 151 bp
+reads/s) with roofline and the reference CPU path beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload bsw|pipeline]
+
+One "step" = one pass of the hot path over one batch of synthetic reads.  See DESIGN.md §Measurement.
+"""
+from __future__ import annotations
+import argparse, json, os, subprocess, sys, tempfile, threading, time
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from __graft_entry__ import load_package  # noqa: E402
+
+
+def _isa():
+    flags = open("/proc/cpuinfo").read()
+    return "avx512bw" if "avx512bw" in flags else "avx2"
+
+
+def _refbin(name):
+    p = os.path.join(ROOT, "oracle", "_ref", _isa(), name)
+    if not os.path.exists(p):
+        raise RuntimeError(f"{p} missing: run __graft_entry__.build() where /root/reference exists")
+    return p
+
+
+def host_threads():
+    n = len(os.sched_getaffinity(0))
+    return max(1, min(n, 128))      # reference tprof[][] is 128 columns wide (src/macro.h LIM_C)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu=0):
+        self.gpu = gpu; self.rows = []; self._stop = False; self.t = None
+
+    def start(self):
+        def run():
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            while not self._stop:
+                try:
+                    o = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                       capture_output=True, text=True, timeout=5).stdout.strip()
+                    if o:
+                        self.rows.append([x.strip() for x in o.split(",")])
+                except Exception:
+                    pass
+                time.sleep(0.2)
+        self.t = threading.Thread(target=run, daemon=True); self.t.start()
+
+    def stop(self):
+        self._stop = True
+        if self.t:
+            self.t.join(timeout=6)
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i] == "Active"})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload preparation (untimed): synthetic genome + reads, reference-built index, and for the
+# BSW-only configuration the extension jobs as the reference's CPU seeding/chaining produces them
+# ------------------------------------------------------------------------------------------------
+def prepare_inputs(work, ref_bp, n_pairs, seed):
+    pkg = load_package()
+    from bwa_mem2_b200 import synth
+    os.makedirs(work, exist_ok=True)
+    fa = os.path.join(work, "ref.fa")
+    if not os.path.exists(fa + ".bwt.2bit.64"):
+        ctg = synth.make_reference(ref_bp, seed=seed, n_contigs=4)
+        synth.write_fasta(fa, ctg)
+        subprocess.check_call([_refbin("bwa-mem2"), "index", fa], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        r1, r2 = synth.make_pairs(ctg, n_pairs, seed=seed + 1)
+        synth.write_fastq(os.path.join(work, "r1.fq"), r1, "p"); synth.write_fastq(os.path.join(work, "r2.fq"), r2, "p")
+        np.save(os.path.join(work, "reads.npy"), np.stack([r1, r2], 1).reshape(-1, r1.shape[1]))
+    return fa
+
+
+def reference_bsw_jobs(work, fa):
+    """Extension jobs exactly as the reference builds them (seeds from the CPU path), via ref_driver."""
+    import refdump
+    dump = os.path.join(work, "dump")
+    stats = os.path.join(work, "stats.json")
+    if not os.path.exists(dump + ".bsw.bin"):
+        env = dict(os.environ, BM2_DUMP_PREFIX=dump, BM2_STATS=stats)
+        with open(os.path.join(work, "ref.sam"), "w") as f:
+            subprocess.check_call([_refbin("ref_driver"), "mem", "-t", "1", "-K", "100000000", fa, os.path.join(work, "r1.fq"),
+                                   os.path.join(work, "r2.fq")], stdout=f, stderr=subprocess.DEVNULL, env=env)
+    g = refdump.merge_bsw(refdump.read_bsw(dump + ".bsw.bin"))
+    g = [x for x in g if x["w"] == 100][0]
+    st = json.load(open(stats))
+    return g, st
+
+
+def run_bsw(args, rank, world):
+    import torch
+    pkg = load_package()
+    capi = pkg.capi
+    import oracle_lib as ol
+    dev = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(dev)
+    work = os.path.join(tempfile.gettempdir(), f"bm2_bench_bsw_{args.ref_mbp}_{args.pairs}")
+    if rank == 0:
+        fa = prepare_inputs(work, args.ref_mbp * 1_000_000, args.pairs, seed=11)
+        reference_bsw_jobs(work, fa)
+    if world > 1:
+        torch.distributed.barrier()
+    g, st = reference_bsw_jobs(work, os.path.join(work, "ref.fa"))
+    n0 = len(g["h0"])
+    reads_per_rep = st["reads"]
+    # replicate the job list so that one step is well above L2 (126 MB) in sequence bytes
+    rep = max(1, int(np.ceil(args.bsw_jobs / n0)))
+    n = n0 * rep
+    pairs = np.zeros(n, capi.PAIR_DT)
+    ref_len = len(g["ref"]); qer_len = len(g["qer"])
+    for r in range(rep):
+        s = slice(r * n0, (r + 1) * n0)
+        pairs["len1"][s] = g["len1"]; pairs["len2"][s] = g["len2"]; pairs["h0"][s] = g["h0"]
+        pairs["idr"][s] = g["idr"] + r * ref_len; pairs["idq"][s] = g["idq"] + r * qer_len
+    ref = np.tile(g["ref"], rep); qer = np.tile(g["qer"], rep)
+    assert int(pairs["idr"].astype(np.int64).max()) < 2 ** 31 - 70000
+    ctx = capi.Context(dev)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    int_gops = ctx.int_pipe_gops()
+    d_pairs = torch.from_numpy(pairs.view(np.uint8).reshape(-1)).cuda()
+    d_ref = torch.from_numpy(ref).cuda(); d_qer = torch.from_numpy(qer).cuda()
+    d_cells = torch.zeros(1, dtype=torch.int64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def step():
+        ctx.extend_pairs_device(d_pairs.data_ptr(), d_ref.data_ptr(), d_qer.data_ptr(), n, 100, 5, d_cells.data_ptr())
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    # parity spot check of the bench workload itself (first replica) against the reference outputs
+    got = d_pairs.cpu().numpy().view(capi.PAIR_DT)[:n0]
+    for k, f in enumerate(("score", "tle", "gtle", "qle", "gscore", "max_off")):
+        assert np.array_equal(got[f], g["out"][:, k]), f"bench workload: {f} differs from the reference"
+    d_cells.zero_()
+    sampler = ClockSampler(dev); sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for a, b in evs:
+        flush.fill_(1)                      # L2 flush between timed iterations
+        a.record(stream); step(); b.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ms = [a.elapsed_time(b) for a, b in evs]
+    ms_step = float(np.mean(ms))
+    cells = int(d_cells.item()) / args.steps
+    if world > 1:
+        t = torch.tensor([ms_step], device="cuda"); torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_step = float(t.item())
+    reads_per_step = reads_per_rep * rep
+    value = world * reads_per_step / (ms_step * 1e-3)
+    # e2e through the host C ABI: pinned host buffers, H2D + D2H inside the timed region
+    h_pairs = torch.from_numpy(pairs.view(np.uint8).reshape(-1).copy()).pin_memory()
+    h_ref = torch.from_numpy(ref).pin_memory(); h_qer = torch.from_numpy(qer).pin_memory()
+    ctx.set_stream(None)
+    hp = h_pairs.numpy().view(capi.PAIR_DT)
+    ctx.extend_pairs(hp, h_ref.numpy(), h_qer.numpy(), 100, 5)
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        ctx.extend_pairs(hp, h_ref.numpy(), h_qer.numpy(), 100, 5)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda"); torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    out = None
+    if rank == 0:
+        gcups = cells / (ms_step * 1e-3) / 1e9
+        peak_cells = int_gops / 14.0          # 14 two-input ops per cell update
+        # CPU baseline: the reference's own AVX-512 BSW calls timed by ref_driver on this host (1 thread)
+        cpu = {"value": st["reads"] / st["t_bsw"], "unit": "reads/s", "cores": 1, "kind": "reference",
+               "sample": f"{st['bsw_pairs']} extension jobs of {st['reads']} reads, reference getScores8/16 ({_isa()}), 1 thread"}
+        out = {"metric": "paired 151bp reads/s (BSW extension only, seeds from the reference CPU path)", "value": value,
+               "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+               "config": {"workload": f"config[1]-like: BSW kernel only; {reads_per_step} reads/step/GPU = {n} extension jobs "
+                                      f"(jobs of {st['reads']} synthetic 2x151 reads vs {args.ref_mbp} Mbp synthetic reference, x{rep})",
+                          "l2": "256 MB flush between steps", "band": 100},
+               "e2e": {"value": world * reads_per_step / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(pairs.nbytes + ref.nbytes + qer.nbytes),
+                       "d2h_bytes_per_step": int(pairs.nbytes)},
+               "gpu_launches": 14 * args.steps,
+               "roofline": {"bound": "int_alu", "achieved": gcups, "peak": peak_cells, "unit": "Gcell/s", "frac": gcups / peak_cells,
+                            "traffic": None, "note": f"cells = banded DP cells actually computed; peak = measured int pipe {int_gops:.0f} Gop/s / 14 ops per cell"},
+               "cpu_baseline": cpu, "clocks": clocks, "wall_s": wall}
+    ctx.close()
+    return out
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path, all host threads, bounded sample."""
+    if rank != 0:
+        return None
+    work = os.path.join(tempfile.gettempdir(), f"bm2_bench_ref_{args.ref_mbp}_{args.pairs}")
+    fa = prepare_inputs(work, args.ref_mbp * 1_000_000, args.pairs, seed=11)
+    nt = host_threads()
+    vals = []
+    for i in range(args.warmup + args.steps):
+        stats = os.path.join(work, f"stats_ref.json")
+        env = dict(os.environ, BM2_MODE="hotpath", BM2_STATS=stats)
+        subprocess.check_call([_refbin("ref_driver"), "mem", "-t", str(nt), "-K", "100000000", fa, os.path.join(work, "r1.fq"),
+                               os.path.join(work, "r2.fq")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
+        st = json.load(open(stats))
+        if i >= args.warmup:
+            vals.append(st["reads"] / (st["t_bwt"] + st["t_aln"]))
+    v = float(np.mean(vals))
+    return {"impl": "reference", "metric": "paired 151bp reads/s", "value": v, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * 2 * args.pairs / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "config": {"workload": f"worker_bwt + worker_aln of the unmodified reference ({_isa()}) on {2 * args.pairs} synthetic 2x151 reads "
+                                   f"vs {args.ref_mbp} Mbp synthetic reference"},
+            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": nt, "kind": "reference",
+                             "sample": f"{2 * args.pairs} reads per step, kt_for over {nt} threads"},
+            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bsw", choices=["bsw", "pipeline"])
+    ap.add_argument("--ref-mbp", type=int, default=10)
+    ap.add_argument("--pairs", type=int, default=50_000)
+    ap.add_argument("--bsw-jobs", type=int, default=4_000_000)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+        if rank == 0:
+            print(json.dumps(out))
+        return
+    if world > 1:
+        import torch, torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        dist.init_process_group("nccl")
+    out = run_bsw(args, rank, world)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,208 @@
+"""ctypes binding of libbm2b200.so (include/bm2_b200.h).  Fails loudly when the library or a CUDA
+device is missing: there is no CPU fallback."""
+from __future__ import annotations
+import ctypes as C, os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbm2b200.so")
+
+PAIR_DT = np.dtype([("idr", "<i4"), ("idq", "<i4"), ("id", "<i4"), ("len1", "<i4"), ("len2", "<i4"), ("h0", "<i4"),
+                    ("seqid", "<i4"), ("regid", "<i4"), ("score", "<i4"), ("tle", "<i4"), ("gtle", "<i4"),
+                    ("qle", "<i4"), ("gscore", "<i4"), ("max_off", "<i4")])
+SMEM_DT = np.dtype([("rid", "<u4"), ("m", "<u4"), ("n", "<u4"), ("_pad", "<u4"), ("k", "<i8"), ("l", "<i8"), ("s", "<i8")])
+SEED_DT = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4"), ("score", "<i4"), ("chain", "<i4")])
+CHAIN_DT = np.dtype([("pos", "<i8"), ("seqid", "<i4"), ("rid", "<i4"), ("n_seeds", "<i4"), ("seed_off", "<i4"),
+                     ("w", "<i4"), ("kept", "<i4"), ("first", "<i4"), ("is_alt", "<i4"), ("frac_rep", "<f4"), ("_pad", "<i4")])
+REG_DT = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("rid", "<i4"), ("_p0", "<i4"), ("c", "<u8"),
+                   ("score", "<i4"), ("truesc", "<i4"), ("sub", "<i4"), ("alt_sc", "<i4"), ("csub", "<i4"), ("sub_n", "<i4"),
+                   ("w", "<i4"), ("seedcov", "<i4"), ("secondary", "<i4"), ("secondary_all", "<i4"), ("seedlen0", "<i4"),
+                   ("n_comp_is_alt", "<i4"), ("frac_rep", "<f4"), ("_p1", "<i4"), ("hash", "<u8"), ("flg", "<i4"), ("_p2", "<i4")])
+
+
+class MemOpt(C.Structure):
+    _fields_ = [("a", C.c_int), ("b", C.c_int), ("o_del", C.c_int), ("e_del", C.c_int), ("o_ins", C.c_int), ("e_ins", C.c_int),
+                ("pen_unpaired", C.c_int), ("pen_clip5", C.c_int), ("pen_clip3", C.c_int), ("w", C.c_int), ("zdrop", C.c_int),
+                ("max_mem_intv", C.c_uint64), ("T", C.c_int), ("flag", C.c_int), ("min_seed_len", C.c_int),
+                ("min_chain_weight", C.c_int), ("max_chain_extend", C.c_int), ("split_factor", C.c_float),
+                ("split_width", C.c_int), ("max_occ", C.c_int), ("max_chain_gap", C.c_int), ("n_threads", C.c_int),
+                ("chunk_size", C.c_int64), ("mask_level", C.c_float), ("drop_ratio", C.c_float), ("XA_drop_ratio", C.c_float),
+                ("mask_level_redun", C.c_float), ("mapQ_coef_len", C.c_float), ("mapQ_coef_fac", C.c_int), ("max_ins", C.c_int),
+                ("max_matesw", C.c_int), ("max_XA_hits", C.c_int), ("max_XA_hits_alt", C.c_int), ("mat", C.c_int8 * 25)]
+
+
+class IndexDesc(C.Structure):
+    _fields_ = [("reference_seq_len", C.c_int64), ("count", C.c_int64 * 5), ("sentinel_index", C.c_int64),
+                ("cp_occ", C.c_void_p), ("sa_ms_byte", C.c_void_p), ("sa_ls_word", C.c_void_p), ("ref_string", C.c_void_p),
+                ("l_pac", C.c_int64), ("n_seqs", C.c_int32), ("ann_offset", C.c_void_p), ("ann_len", C.c_void_p),
+                ("ann_is_alt", C.c_void_p)]
+
+
+class ReadBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("codes", C.c_void_p), ("offsets", C.c_void_p)]
+
+
+class SmemResult(C.Structure):
+    _fields_ = [("n", C.c_int64), ("smems", C.c_void_p), ("read_off", C.c_void_p)]
+
+
+class ChainResult(C.Structure):
+    _fields_ = [("n_chains", C.c_int64), ("n_seeds", C.c_int64), ("chains", C.c_void_p), ("seeds", C.c_void_p),
+                ("read_off", C.c_void_p)]
+
+
+class RegResult(C.Structure):
+    _fields_ = [("n", C.c_int64), ("regs", C.c_void_p), ("read_off", C.c_void_p)]
+
+
+EXPORTS = ["bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
+           "bm2_last_error", "bm2_extend_pairs", "bm2_extend_pairs_device", "bm2_collect_smems", "bm2_seed_chain",
+           "bm2_seed_chain_extend", "bm2_last_stage_ms"]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() (no CPU fallback exists)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.bm2_last_error.restype = C.c_char_p
+        _lib.bm2_last_error.argtypes = [C.c_void_p]
+        _lib.bm2_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p]
+        _lib.bm2_destroy.argtypes = [C.c_void_p]
+        _lib.bm2_index_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(IndexDesc))]
+        _lib.bm2_index_free.argtypes = [C.POINTER(IndexDesc)]
+        _lib.bm2_extend_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+        _lib.bm2_extend_pairs_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                                 C.c_int32, C.c_void_p]
+        for f in ("bm2_collect_smems", "bm2_seed_chain", "bm2_seed_chain_extend"):
+            if hasattr(_lib, f):
+                getattr(_lib, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    return _lib
+
+
+def default_opt() -> MemOpt:
+    o = MemOpt()
+    lib().bm2_opt_init(C.byref(o))
+    return o
+
+
+class Bm2Error(RuntimeError):
+    pass
+
+
+class Index:
+    """Host-resident index loaded by the native loader (bm2_index_load)."""
+
+    def __init__(self, prefix: str):
+        self._p = C.POINTER(IndexDesc)()
+        rc = lib().bm2_index_load(prefix.encode(), C.byref(self._p))
+        if rc:
+            lib().bm2_index_io_error.restype = C.c_char_p
+            raise Bm2Error(f"bm2_index_load({prefix}): {lib().bm2_index_io_error().decode()}")
+        self.desc = self._p.contents
+
+    def close(self):
+        if self._p:
+            lib().bm2_index_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """bm2_ctx wrapper; mirrors the reference seams (see include/bm2_b200.h)."""
+
+    def __init__(self, device: int = 0, index=None, opt: MemOpt | None = None):
+        self._ctx = C.c_void_p()
+        self.opt = opt if opt is not None else default_opt()
+        self._index = index
+        idx_ptr = None
+        if index is not None:
+            idx_ptr = C.cast(C.byref(index.desc if isinstance(index, Index) else index), C.c_void_p)
+        rc = lib().bm2_create(C.byref(self._ctx), device, idx_ptr, C.cast(C.byref(self.opt), C.c_void_p))
+        if rc:
+            raise Bm2Error("bm2_create: " + lib().bm2_last_error(None).decode())
+
+    def close(self):
+        if self._ctx:
+            lib().bm2_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc:
+            raise Bm2Error(f"{what}: " + lib().bm2_last_error(self._ctx).decode())
+
+    # seam 1 (BandedPairWiseSW::getScores16 & co.)
+    def extend_pairs(self, pairs: np.ndarray, ref: np.ndarray, qer: np.ndarray, w: int, end_bonus: int):
+        assert pairs.dtype == PAIR_DT and pairs.flags.c_contiguous
+        ref = np.ascontiguousarray(ref, np.uint8); qer = np.ascontiguousarray(qer, np.uint8)
+        self._check(lib().bm2_extend_pairs(self._ctx, pairs.ctypes.data, ref.ctypes.data, qer.ctypes.data,
+                                           len(pairs), w, end_bonus), "bm2_extend_pairs")
+        return pairs
+
+    def extend_pairs_device(self, d_pairs_ptr, d_ref_ptr, d_qer_ptr, n, w, end_bonus, d_cells_ptr=None):
+        self._check(lib().bm2_extend_pairs_device(self._ctx, d_pairs_ptr, d_ref_ptr, d_qer_ptr, n, w, end_bonus,
+                                                  d_cells_ptr), "bm2_extend_pairs_device")
+
+    # seam 2
+    @staticmethod
+    def _batch(codes: np.ndarray, offsets: np.ndarray):
+        codes = np.ascontiguousarray(codes, np.uint8); offsets = np.ascontiguousarray(offsets, np.int64)
+        rb = ReadBatch(len(offsets) - 1, codes.ctypes.data, offsets.ctypes.data)
+        return rb, (codes, offsets)
+
+    def collect_smems(self, codes, offsets):
+        rb, keep = self._batch(codes, offsets)
+        res = SmemResult()
+        self._check(lib().bm2_collect_smems(self._ctx, C.byref(rb), C.byref(res)), "bm2_collect_smems")
+        n = res.n
+        sm = np.ctypeslib.as_array(C.cast(res.smems, C.POINTER(C.c_uint8)), shape=(n * SMEM_DT.itemsize,)).view(SMEM_DT).copy() if n else np.zeros(0, SMEM_DT)
+        off = np.ctypeslib.as_array(C.cast(res.read_off, C.POINTER(C.c_int64)), shape=(rb.n_reads + 1,)).copy()
+        return sm, off
+
+    def seed_chain(self, codes, offsets):
+        rb, keep = self._batch(codes, offsets)
+        res = ChainResult()
+        self._check(lib().bm2_seed_chain(self._ctx, C.byref(rb), C.byref(res)), "bm2_seed_chain")
+        nc, ns = res.n_chains, res.n_seeds
+        ch = np.ctypeslib.as_array(C.cast(res.chains, C.POINTER(C.c_uint8)), shape=(nc * CHAIN_DT.itemsize,)).view(CHAIN_DT).copy() if nc else np.zeros(0, CHAIN_DT)
+        sd = np.ctypeslib.as_array(C.cast(res.seeds, C.POINTER(C.c_uint8)), shape=(ns * SEED_DT.itemsize,)).view(SEED_DT).copy() if ns else np.zeros(0, SEED_DT)
+        off = np.ctypeslib.as_array(C.cast(res.read_off, C.POINTER(C.c_int64)), shape=(rb.n_reads + 1,)).copy()
+        return ch, sd, off
+
+    def seed_chain_extend(self, codes, offsets, copy=True):
+        rb, keep = self._batch(codes, offsets)
+        res = RegResult()
+        self._check(lib().bm2_seed_chain_extend(self._ctx, C.byref(rb), C.byref(res)), "bm2_seed_chain_extend")
+        n = res.n
+        regs = np.ctypeslib.as_array(C.cast(res.regs, C.POINTER(C.c_uint8)), shape=(n * REG_DT.itemsize,)).view(REG_DT) if n else np.zeros(0, REG_DT)
+        off = np.ctypeslib.as_array(C.cast(res.read_off, C.POINTER(C.c_int64)), shape=(rb.n_reads + 1,))
+        return (regs.copy(), off.copy()) if copy else (regs, off)
+
+    def set_stream(self, cuda_stream_handle):
+        lib().bm2_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        self._check(lib().bm2_set_stream(self._ctx, cuda_stream_handle), "bm2_set_stream")
+
+    def int_pipe_gops(self) -> float:
+        v = C.c_double()
+        lib().bm2_int_pipe_gops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self._check(lib().bm2_int_pipe_gops(self._ctx, C.byref(v)), "bm2_int_pipe_gops")
+        return v.value
+
+    def stage_ms(self):
+        names = C.POINTER(C.c_char_p)(); ms = C.POINTER(C.c_float)(); n = C.c_int()
+        lib().bm2_last_stage_ms(self._ctx, C.byref(names), C.byref(ms), C.byref(n))
+        return {names[i].decode(): ms[i] for i in range(n.value)}

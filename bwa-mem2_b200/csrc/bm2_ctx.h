@@ -1,0 +1,49 @@
+// bm2_ctx.h — the device context behind the opaque `bm2_ctx*` of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "bm2_b200.h"
+
+struct DevBuf  { void *p = nullptr; size_t cap = 0; };
+struct HostBuf { void *p = nullptr; size_t cap = 0; };
+
+struct DevIndex {                 // FM-index + reference resident in HBM (replicated per GPU)
+    int64_t N = 0, l_pac = 0, sentinel = 0;
+    int64_t count[5] = {0, 0, 0, 0, 0};
+    const bm2_cp_occ *cp_occ = nullptr;
+    const int8_t *sa_ms = nullptr;
+    const uint32_t *sa_ls = nullptr;
+    const uint8_t *ref = nullptr;          // 2*l_pac codes
+    int32_t n_seqs = 0;
+    const int64_t *ann_off = nullptr;
+    const int32_t *ann_len = nullptr;
+    const int32_t *ann_alt = nullptr;
+    bool loaded = false;
+};
+
+struct bm2_ctx {
+    int device = 0, n_sm = 148;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    bm2_mem_opt_t opt;
+    std::string err;
+    DevIndex idx;
+    std::vector<void *> idx_allocs;
+    // seam 1
+    DevBuf io_pairs, io_ref, io_qer, bsw_jobs, bsw_outs, bsw_scratch;
+    // seam 2 (pipeline.cu)
+    DevBuf d[32];
+    HostBuf h[16];
+    std::vector<cudaEvent_t> events;
+    std::vector<const char *> stage_names;
+    std::vector<float> stage_ms;
+
+    int ensure(DevBuf &b, size_t bytes);
+    int ensure_host(HostBuf &b, size_t bytes);
+    std::vector<DevBuf *> all_dev() {
+        std::vector<DevBuf *> v = {&io_pairs, &io_ref, &io_qer, &bsw_jobs, &bsw_outs, &bsw_scratch};
+        for (auto &x : d) v.push_back(&x);
+        return v;
+    }
+    std::vector<HostBuf *> all_host() { std::vector<HostBuf *> v; for (auto &x : h) v.push_back(&x); return v; }
+};

@@ -1,0 +1,339 @@
+// bsw.cu — banded affine-gap seed-extension (BSW) kernels for sm_100a.
+//
+// Replaces BandedPairWiseSW::{getScores8,getScores16,scalarBandedSWAWrapper}
+// (reference src/bandedSWA.cpp:1970, :2664, :242).  Semantics = ksw_extend2 / scalarBandedSWA
+// (src/bandedSWA.cpp:116-237) with the band derived as the SIMD wrappers derive it
+// (src/bandedSWA.cpp:2905-2926).
+//
+// Kernel "thread-per-job" (short queries, the 2x151 bp workload): the DP of one job is
+// row-sequential with data-dependent band / early exit, so parallelism is taken ACROSS jobs, one
+// job per thread, exactly the inter-sequence scheme of the reference's SIMD kernels but 32-wide
+// SIMT with independent control per lane.  The per-column state {H(i-1,j-1), E(i,j)} is packed
+// 16+16 bit in one shared-memory word laid out [column][thread] (bank == lane: conflict-free for
+// any per-thread column), the query is packed 4 bit/base in the same layout.  Jobs are radix-sorted
+// by (query-length class, target length) so that the 32 lanes of a warp run similar trip counts.
+// Integer-ALU bound; HBM traffic is ~(qlen+tlen+56) B per job.
+#include "bm2_common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+#define BSW_THREADS 128
+#define BSW_NCLASS 8
+// upper query-length bound of each class (state words = bound + 2)
+__constant__ int c_class_bound[BSW_NCLASS] = {32, 64, 96, 128, 160, 256, 512, 1024};
+static const int h_class_bound[BSW_NCLASS] = {32, 64, 96, 128, 160, 256, 512, 1024};
+
+struct BswSortScratch {
+    uint32_t *keys_in, *keys_out;
+    int32_t *idx_in, *idx_out;
+    int32_t *class_cnt;      // BSW_NCLASS + 2 counters (last = "global-state" class)
+    int32_t *class_off;      // BSW_NCLASS + 3 offsets
+    void *cub_tmp;
+    size_t cub_bytes;
+};
+
+__device__ __forceinline__ int bsw_class_of(int qlen, int tlen, int h0, int a) {
+    // scores must fit 15 bits for the packed state (same rule as the reference's int16 class,
+    // src/bwamem.cpp:2307); anything else goes to the wide / global-state kernel.
+    int minlen = qlen < tlen ? qlen : tlen;
+    long long maxsc = (long long) h0 + (long long) minlen * a;
+    if (maxsc >= 32768 || qlen > c_class_bound[BSW_NCLASS - 1]) return BSW_NCLASS;
+#pragma unroll
+    for (int c = 0; c < BSW_NCLASS; ++c)
+        if (qlen <= c_class_bound[c]) return c;
+    return BSW_NCLASS;
+}
+
+__global__ void bsw_keys_kernel(const BswJob *jobs, int n, int a, uint32_t *keys, int32_t *idx, int32_t *class_cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    BswJob j = jobs[i];
+    int c = bsw_class_of(j.qlen, j.tlen, j.h0, a);
+    int t = j.tlen > 0xFFFFF ? 0xFFFFF : j.tlen;
+    // ascending sort => class ascending, target length descending (long jobs first), then qlen desc
+    int q = j.qlen > 0xFF ? 0xFF : j.qlen;
+    keys[i] = ((uint32_t) c << 28) | ((uint32_t) (0xFFFFF - t) << 8) | (uint32_t) (0xFF - q);
+    idx[i] = i;
+    atomicAdd(&class_cnt[c], 1);
+}
+
+__global__ void bsw_class_off_kernel(const int32_t *class_cnt, int32_t *class_off) {
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int c = 0; c <= BSW_NCLASS; ++c) { class_off[c] = s; s += class_cnt[c]; }
+        class_off[BSW_NCLASS + 1] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The extension DP of one job (one thread).  `St` abstracts the per-column state storage.
+// ---------------------------------------------------------------------------------------------
+struct SmemPacked {            // H | E<<16 in shared memory, [column][thread]
+    uint32_t *base;            // &sh[threadIdx.x]
+    __device__ __forceinline__ void get(int j, int &h, int &e) const {
+        uint32_t w = base[j * BSW_THREADS];
+        h = (int) (w & 0xFFFFu); e = (int) (w >> 16);
+    }
+    __device__ __forceinline__ void put(int j, int h, int e) const { base[j * BSW_THREADS] = (uint32_t) h | ((uint32_t) e << 16); }
+    __device__ __forceinline__ bool zero(int j) const { return base[j * BSW_THREADS] == 0u; }
+};
+
+struct GmemWide {              // {H,E} int32 in global memory, private stripe per thread
+    int2 *base;
+    __device__ __forceinline__ void get(int j, int &h, int &e) const { int2 v = base[j]; h = v.x; e = v.y; }
+    __device__ __forceinline__ void put(int j, int h, int e) const { base[j] = make_int2(h, e); }
+    __device__ __forceinline__ bool zero(int j) const { int2 v = base[j]; return (v.x | v.y) == 0; }
+};
+
+template <class St, class QFetch>
+__device__ __forceinline__ void bsw_extend_one(const St &st, const QFetch &qf, const uint8_t *__restrict__ tptr, int tstride,
+                                               int qlen, int tlen, int h0, const BswParams &p, BswOut &o,
+                                               unsigned long long &cells)
+{
+    const int oe_del = p.o_del + p.e_del, oe_ins = p.o_ins + p.e_ins;
+    const int e_del = p.e_del, e_ins = p.e_ins, sa = p.a, sb = -p.b;
+    // first row (bandedSWA.cpp:141-144); columns 0..qlen, E = 0
+    {
+        int h = h0;
+        st.put(0, h, 0);
+        h = h0 > oe_ins ? h0 - oe_ins : 0;
+        for (int j = 1; j <= qlen; ++j) {
+            st.put(j, h, 0);
+            h = h > e_ins ? h - e_ins : 0;
+        }
+        // NB: reference stops writing when the value reaches <= e_ins and leaves zeros; identical.
+    }
+    // band (SIMD wrapper arithmetic, bandedSWA.cpp:2905-2926; == scalar :146-156 when e == 1)
+    int w = p.w;
+    {
+        unsigned t1 = ((unsigned) (qlen * sa) + (unsigned) (p.end_bonus - p.o_ins)) & 0xFFFFu;
+        int max_ins = (int) (t1 / (unsigned) e_ins) + 1; if (max_ins < 1) max_ins = 1;
+        unsigned t2 = ((unsigned) (qlen * sa) + (unsigned) (p.end_bonus - p.o_del)) & 0xFFFFu;
+        int max_del = (int) (t2 / (unsigned) e_del) + 1; if (max_del < 1) max_del = 1;
+        if (w > max_ins) w = max_ins;
+        if (w > max_del) w = max_del;
+    }
+    int best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0;
+    int beg = 0, end = qlen;
+    unsigned long long ncell = 0;
+    for (int i = 0; i < tlen; ++i) {
+        if (beg < i - w) beg = i - w;
+        if (end > i + w + 1) end = i + w + 1;
+        if (end > qlen) end = qlen;
+        int h1;
+        if (beg == 0) { h1 = h0 - (p.o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
+        else h1 = 0;
+        const int tb = tptr[(long long) i * tstride];
+        const int s_row_amb = tb > 3;
+        int f = 0, m = 0, mj = -1;
+        int j = beg;
+        typename QFetch::Cursor qc = qf.cursor(beg);
+#pragma unroll 4
+        for (; j < end; ++j) {
+            int hd, e;
+            st.get(j, hd, e);
+            int qb = qf.next(qc, j);
+            int s = (qb == tb) ? sa : sb;
+            if (s_row_amb | (qb > 3)) s = -1;
+            int M = hd ? hd + s : 0;
+            int h = max(max(M, e), f);
+            int t = max(M - oe_del, 0);
+            e = max(e - e_del, t);
+            st.put(j, h1, e);
+            t = max(M - oe_ins, 0);
+            f = max(f - e_ins, t);
+            h1 = h;
+            if (h >= m) { mj = j; m = h; }
+        }
+        if (end > beg) ncell += (unsigned) (end - beg);
+        st.put(end, h1, 0);
+        if (j == qlen) {
+            if (h1 >= gscore) best_ie = i;
+            if (h1 > gscore) gscore = h1;
+        }
+        if (m == 0) break;
+        if (m > best) {
+            best = m; best_i = i; best_j = mj;
+            int d = mj - i; d = d < 0 ? -d : d;
+            if (d > max_off) max_off = d;
+        } else if (p.zdrop > 0) {
+            int di = i - best_i, dj = mj - best_j;
+            int pen = di > dj ? di - dj : dj - di;       // SIMD z-drop: no e_del/e_ins factor (ZSCORE16)
+            if (best - m - pen > p.zdrop) break;
+        }
+        for (j = beg; j < end && st.zero(j); ++j) {}
+        beg = j;
+        for (j = end; j >= beg && st.zero(j); --j) {}
+        end = j + 2 < qlen ? j + 2 : qlen;
+    }
+    o.score = best; o.qle = best_j + 1; o.tle = best_i + 1; o.gtle = best_ie + 1; o.gscore = gscore; o.max_off = max_off;
+    cells += ncell;
+}
+
+// query packed 4 bit / base in shared memory words [word][thread]
+struct QSmem4 {
+    const uint32_t *base;      // &sh[(W)*BSW_THREADS + threadIdx.x]
+    struct Cursor { uint32_t w; };
+    __device__ __forceinline__ Cursor cursor(int j) const { Cursor c; c.w = base[(j >> 3) * BSW_THREADS] >> ((j & 7) * 4); return c; }
+    __device__ __forceinline__ int next(Cursor &c, int j) const {
+        if ((j & 7) == 0) c.w = base[(j >> 3) * BSW_THREADS];
+        int b = (int) (c.w & 0xFu);
+        c.w >>= 4;
+        return b;
+    }
+};
+
+struct QGmem {                 // query bytes straight from global memory
+    const uint8_t *ptr; int stride;
+    struct Cursor { int dummy; };
+    __device__ __forceinline__ Cursor cursor(int) const { return Cursor(); }
+    __device__ __forceinline__ int next(Cursor &, int j) const { return ptr[(long long) j * stride]; }
+};
+
+__global__ void __launch_bounds__(BSW_THREADS)
+bsw_thread_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ perm, const int32_t *__restrict__ class_off,
+                  int cls, BswOut *__restrict__ out, const uint8_t *__restrict__ tbase, const uint8_t *__restrict__ qbase,
+                  BswParams p, int W, unsigned long long *cells)
+{
+    extern __shared__ uint32_t sh[];
+    const int first = class_off[cls], last = class_off[cls + 1];
+    const int g = first + blockIdx.x * BSW_THREADS + threadIdx.x;
+    if (first + blockIdx.x * BSW_THREADS >= last) return;
+    unsigned long long ncell = 0;
+    if (g < last) {
+        const int id = perm[g];
+        const BswJob job = jobs[id];
+        // pack the query, 8 bases per word
+        const uint8_t *qp = qbase + job.qoff;
+        uint32_t *qs = sh + W * BSW_THREADS + threadIdx.x;
+        for (int k = 0; k < job.qlen; k += 8) {
+            uint32_t wv = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                int jj = k + u;
+                uint32_t b = jj < job.qlen ? (uint32_t) qp[(long long) jj * job.qstride] : 4u;
+                if (b > 4u) b = 4u;
+                wv |= b << (4 * u);
+            }
+            qs[(k >> 3) * BSW_THREADS] = wv;
+        }
+        SmemPacked st; st.base = sh + threadIdx.x;
+        QSmem4 qf; qf.base = qs;
+        BswOut o;
+        bsw_extend_one(st, qf, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
+        out[id] = o;
+    }
+    if (cells) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) ncell += __shfl_xor_sync(0xffffffffu, ncell, d);
+        if ((threadIdx.x & 31) == 0 && ncell) atomicAdd(cells, ncell);
+    }
+}
+
+// jobs whose scores need 32 bits or whose query does not fit the shared-memory classes:
+// state in a private global-memory stripe (correctness path for the rare scalar class,
+// reference src/bwamem.cpp:2310; long reads get the warp-per-job kernel in a later round).
+__global__ void __launch_bounds__(64)
+bsw_wide_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ perm, const int32_t *__restrict__ class_off,
+                BswOut *__restrict__ out, const uint8_t *__restrict__ tbase, const uint8_t *__restrict__ qbase, BswParams p,
+                int2 *state, const long long *state_off, unsigned long long *cells)
+{
+    const int first = class_off[BSW_NCLASS], last = class_off[BSW_NCLASS + 1];
+    for (int g = first + blockIdx.x * blockDim.x + threadIdx.x; g < last; g += gridDim.x * blockDim.x) {
+        const int id = perm[g];
+        const BswJob job = jobs[id];
+        GmemWide st; st.base = state + state_off[g - first];
+        QGmem qf; qf.ptr = qbase + job.qoff; qf.stride = job.qstride;
+        BswOut o; unsigned long long ncell = 0;
+        bsw_extend_one(st, qf, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
+        out[id] = o;
+        if (cells && ncell) atomicAdd(cells, ncell);
+    }
+}
+
+// exclusive prefix of (qlen+2) over the wide class, single thread block (the class is tiny)
+__global__ void bsw_wide_off_kernel(const BswJob *jobs, const int32_t *perm, const int32_t *class_off, long long *state_off,
+                                    long long *total) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int first = class_off[BSW_NCLASS], last = class_off[BSW_NCLASS + 1];
+    long long s = 0;
+    for (int g = first; g < last; ++g) { state_off[g - first] = s; s += jobs[perm[g]].qlen + 2; }
+    *total = s;
+}
+
+size_t bsw_scratch_bytes(int n) {
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint32_t *) nullptr, (uint32_t *) nullptr, (int32_t *) nullptr,
+                                    (int32_t *) nullptr, n > 0 ? n : 1);
+    size_t per = ((size_t) (n > 0 ? n : 1) * 4 + 255) / 256 * 256;
+    return 4 * per + 256 * 2 + ((cub_bytes + 255) / 256 * 256) + 256;
+}
+
+struct BswWideScratch { int2 *state; long long *state_off; long long *total; size_t cap_words; size_t cap_jobs; };
+static BswWideScratch g_wide = {nullptr, nullptr, nullptr, 0, 0};
+
+int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const BswJob *d_jobs, BswOut *d_out, int n,
+                            const uint8_t *d_tbase, const uint8_t *d_qbase, const BswParams &prm,
+                            unsigned long long *d_cells, void *scratch, size_t scratch_bytes, int wide_possible)
+{
+    if (n <= 0) return 0;
+    if (scratch_bytes < bsw_scratch_bytes(n)) { bm2_set_error(ctx_for_error, "bsw: scratch too small"); return 1; }
+    size_t per = ((size_t) n * 4 + 255) / 256 * 256;
+    char *s = (char *) scratch;
+    uint32_t *keys_in = (uint32_t *) s; s += per;
+    uint32_t *keys_out = (uint32_t *) s; s += per;
+    int32_t *idx_in = (int32_t *) s; s += per;
+    int32_t *idx_out = (int32_t *) s; s += per;
+    int32_t *class_cnt = (int32_t *) s; s += 256;
+    int32_t *class_off = (int32_t *) s; s += 256;
+    void *cub_tmp = s;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys_in, keys_out, idx_in, idx_out, n);
+
+    BM2_CUDA_OK(cudaMemsetAsync(class_cnt, 0, 256, stream));
+    bsw_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_jobs, n, prm.a, keys_in, idx_in, class_cnt);
+    BM2_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, idx_in, idx_out, n, 0, 32, stream));
+    bsw_class_off_kernel<<<1, 32, 0, stream>>>(class_cnt, class_off);
+
+    const int nblk = (n + BSW_THREADS - 1) / BSW_THREADS;
+    for (int c = 0; c < BSW_NCLASS; ++c) {
+        int W = h_class_bound[c] + 2;
+        int QW = (h_class_bound[c] + 7) / 8;
+        size_t smem = (size_t) (W + QW) * BSW_THREADS * 4;
+        static bool attr_set = false;
+        if (!attr_set) {   // one function, several dynamic sizes: raise the limit once
+            BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_set = true;
+        }
+        if (smem > 227 * 1024) { bm2_set_error(ctx_for_error, "bsw: class does not fit shared memory"); return 1; }
+        bsw_thread_kernel<<<nblk, BSW_THREADS, smem, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, W, d_cells);
+    }
+    if (wide_possible) {
+        // the wide class needs its size on the host (rare path): one small sync
+        int32_t h_off[2];
+        BM2_CUDA_OK(cudaMemcpyAsync(h_off, class_off + BSW_NCLASS, 8, cudaMemcpyDeviceToHost, stream));
+        BM2_CUDA_OK(cudaStreamSynchronize(stream));
+        int nw = h_off[1] - h_off[0];
+        if (nw > 0) {
+            if (g_wide.cap_jobs < (size_t) nw) {
+                if (g_wide.state_off) cudaFree(g_wide.state_off);
+                if (!g_wide.total) BM2_CUDA_OK(cudaMalloc(&g_wide.total, 8));
+                BM2_CUDA_OK(cudaMalloc(&g_wide.state_off, (size_t) nw * 8));
+                g_wide.cap_jobs = nw;
+            }
+            bsw_wide_off_kernel<<<1, 32, 0, stream>>>(d_jobs, idx_out, class_off, g_wide.state_off, g_wide.total);
+            long long total = 0;
+            BM2_CUDA_OK(cudaMemcpyAsync(&total, g_wide.total, 8, cudaMemcpyDeviceToHost, stream));
+            BM2_CUDA_OK(cudaStreamSynchronize(stream));
+            if (g_wide.cap_words < (size_t) total) {
+                if (g_wide.state) cudaFree(g_wide.state);
+                BM2_CUDA_OK(cudaMalloc(&g_wide.state, (size_t) total * sizeof(int2)));
+                g_wide.cap_words = total;
+            }
+            int blocks = (nw + 63) / 64; if (blocks > 148 * 8) blocks = 148 * 8;
+            bsw_wide_kernel<<<blocks, 64, 0, stream>>>(d_jobs, idx_out, class_off, d_out, d_tbase, d_qbase, prm, g_wide.state,
+                                                       g_wide.state_off, d_cells);
+        }
+    }
+    BM2_CUDA_OK(cudaGetLastError());
+    return 0;
+}

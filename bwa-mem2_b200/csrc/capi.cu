@@ -1,0 +1,257 @@
+// capi.cu — the C ABI of libbm2b200.so (include/bm2_b200.h): context, parameter handling and the
+// host side of seam 1 (bm2_extend_pairs).  Seam 2 lives in pipeline.cu.
+#include "bm2_common.cuh"
+#include "bm2_ctx.h"
+#include <cstring>
+#include <vector>
+#include <mutex>
+
+static std::string g_create_error;
+static std::mutex g_err_mu;
+
+void bm2_set_error(bm2_ctx *ctx, const std::string &msg) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+}
+
+int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const BswJob *d_jobs, BswOut *d_out, int n,
+                            const uint8_t *d_tbase, const uint8_t *d_qbase, const BswParams &prm,
+                            unsigned long long *d_cells, void *scratch, size_t scratch_bytes, int wide_possible);
+
+extern "C" int bm2_abi_version(void) { return BM2_ABI_VERSION; }
+
+extern "C" void bm2_opt_init(bm2_mem_opt_t *o) {
+    // mem_opt_init, reference src/bwamem.cpp:107-143
+    memset(o, 0, sizeof(*o));
+    o->a = 1; o->b = 4;
+    o->o_del = o->o_ins = 6;
+    o->e_del = o->e_ins = 1;
+    o->w = 100;
+    o->T = 30;
+    o->zdrop = 100;
+    o->pen_unpaired = 17;
+    o->pen_clip5 = o->pen_clip3 = 5;
+    o->max_mem_intv = 20;
+    o->min_seed_len = 19;
+    o->split_width = 10;
+    o->max_occ = 500;
+    o->max_chain_gap = 10000;
+    o->max_ins = 10000;
+    o->mask_level = 0.50f;
+    o->drop_ratio = 0.50f;
+    o->XA_drop_ratio = 0.80f;
+    o->split_factor = 1.5f;
+    o->chunk_size = 10000000;
+    o->n_threads = 1;
+    o->max_XA_hits = 5;
+    o->max_XA_hits_alt = 200;
+    o->max_matesw = 50;
+    o->mask_level_redun = 0.95f;
+    o->min_chain_weight = 0;
+    o->max_chain_extend = 1 << 30;
+    o->mapQ_coef_len = 50;
+    o->mapQ_coef_fac = 3;   // (int) log(50)
+    // bwa_fill_scmat, reference src/bwa.cpp:248-258
+    int k = 0;
+    for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 4; ++j) o->mat[k++] = i == j ? o->a : -o->b;
+        o->mat[k++] = -1;
+    }
+    for (int j = 0; j < 5; ++j) o->mat[k++] = -1;
+}
+
+int bm2_ctx::ensure(DevBuf &b, size_t bytes) {
+    bm2_ctx *ctx_for_error = this;
+    if (b.cap >= bytes) return 0;
+    if (b.p) BM2_CUDA_OK(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    BM2_CUDA_OK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+
+int bm2_ctx::ensure_host(HostBuf &b, size_t bytes) {
+    bm2_ctx *ctx_for_error = this;
+    if (b.cap >= bytes) return 0;
+    if (b.p) BM2_CUDA_OK(cudaFreeHost(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    BM2_CUDA_OK(cudaMallocHost(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+
+int bm2_upload_index(bm2_ctx *ctx, const bm2_index_desc *idx);   // pipeline.cu
+void bm2_free_index(bm2_ctx *ctx);
+
+extern "C" int bm2_create(bm2_ctx **out, int device, const bm2_index_desc *idx, const bm2_mem_opt_t *opt) {
+    bm2_ctx *ctx_for_error = nullptr;
+    if (!out) { bm2_set_error(nullptr, "bm2_create: out is NULL"); return 1; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        bm2_set_error(nullptr, std::string("bm2_create: no usable CUDA device (") + cudaGetErrorString(e) +
+                               "); this library has no CPU fallback");
+        return 2;
+    }
+    if (device < 0 || device >= ndev) { bm2_set_error(nullptr, "bm2_create: bad device ordinal"); return 1; }
+    BM2_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    BM2_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        bm2_set_error(nullptr, "bm2_create: device is not sm_100 (library is built for sm_100a only)");
+        return 2;
+    }
+    bm2_ctx *ctx = new bm2_ctx();
+    ctx->device = device;
+    ctx->n_sm = prop.multiProcessorCount;
+    if (opt) ctx->opt = *opt; else bm2_opt_init(&ctx->opt);
+    ctx_for_error = ctx;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        bm2_set_error(nullptr, "bm2_create: cudaStreamCreate failed"); delete ctx; return 1;
+    }
+    ctx->stream = ctx->own_stream;
+    if (idx) {
+        if (bm2_upload_index(ctx, idx)) { bm2_set_error(nullptr, "bm2_create: " + ctx->err); bm2_destroy(ctx); return 1; }
+    }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void bm2_destroy(bm2_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    bm2_free_index(ctx);
+    for (DevBuf *b : ctx->all_dev()) if (b->p) cudaFree(b->p);
+    for (HostBuf *b : ctx->all_host()) if (b->p) cudaFreeHost(b->p);
+    for (cudaEvent_t ev : ctx->events) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char *bm2_last_error(const bm2_ctx *ctx) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+static BswParams bsw_params_of(const bm2_ctx *ctx, int w, int end_bonus) {
+    BswParams p;
+    p.a = ctx->opt.a; p.b = ctx->opt.b;
+    p.o_del = ctx->opt.o_del; p.e_del = ctx->opt.e_del; p.o_ins = ctx->opt.o_ins; p.e_ins = ctx->opt.e_ins;
+    p.zdrop = ctx->opt.zdrop; p.end_bonus = end_bonus; p.w = w;
+    return p;
+}
+
+// ---- seam 1 ------------------------------------------------------------------------------------
+__global__ void pairs_to_jobs_kernel(const bm2_seqpair *pairs, int n, BswJob *jobs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bm2_seqpair sp = pairs[i];
+    BswJob j;
+    j.toff = sp.idr; j.qoff = sp.idq; j.tlen = sp.len1; j.qlen = sp.len2; j.h0 = sp.h0;
+    j.tstride = 1; j.qstride = 1; j._pad = 0;
+    jobs[i] = j;
+}
+
+__global__ void outs_to_pairs_kernel(const BswOut *outs, int n, bm2_seqpair *pairs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    BswOut o = outs[i];
+    pairs[i].score = o.score; pairs[i].tle = o.tle; pairs[i].gtle = o.gtle; pairs[i].qle = o.qle;
+    pairs[i].gscore = o.gscore; pairs[i].max_off = o.max_off;
+}
+
+extern "C" int bm2_extend_pairs_device(bm2_ctx *ctx, bm2_seqpair *d_pairs, const uint8_t *d_ref, const uint8_t *d_qer,
+                                       int32_t n, int32_t w, int32_t end_bonus, unsigned long long *d_cells) {
+    bm2_ctx *ctx_for_error = ctx;
+    if (!ctx) return 1;
+    if (n <= 0) return 0;
+    BM2_CUDA_OK(cudaSetDevice(ctx->device));
+    if (ctx->ensure(ctx->bsw_jobs, (size_t) n * sizeof(BswJob))) return 1;
+    if (ctx->ensure(ctx->bsw_outs, (size_t) n * sizeof(BswOut))) return 1;
+    if (ctx->ensure(ctx->bsw_scratch, bsw_scratch_bytes(n))) return 1;
+    pairs_to_jobs_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_pairs, n, (BswJob *) ctx->bsw_jobs.p);
+    BswParams p = bsw_params_of(ctx, w, end_bonus);
+    if (bsw_launch_with_scratch(ctx, ctx->stream, (const BswJob *) ctx->bsw_jobs.p, (BswOut *) ctx->bsw_outs.p, n, d_ref, d_qer,
+                                p, d_cells, ctx->bsw_scratch.p, ctx->bsw_scratch.cap, 1)) return 1;
+    outs_to_pairs_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const BswOut *) ctx->bsw_outs.p, n, d_pairs);
+    BM2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bm2_extend_pairs(bm2_ctx *ctx, bm2_seqpair *pairs, const uint8_t *ref, const uint8_t *qer, int32_t n,
+                                int32_t w, int32_t end_bonus) {
+    bm2_ctx *ctx_for_error = ctx;
+    if (!ctx) return 1;
+    if (n <= 0) return 0;
+    BM2_CUDA_OK(cudaSetDevice(ctx->device));
+    // extent of the two byte buffers actually referenced
+    int64_t ref_bytes = 0, qer_bytes = 0;
+    for (int i = 0; i < n; ++i) {
+        if (pairs[i].len1 < 0 || pairs[i].len2 < 0 || pairs[i].idr < 0 || pairs[i].idq < 0) {
+            bm2_set_error(ctx, "bm2_extend_pairs: negative length/offset"); return 1;
+        }
+        int64_t r = (int64_t) pairs[i].idr + pairs[i].len1, q = (int64_t) pairs[i].idq + pairs[i].len2;
+        if (r > ref_bytes) ref_bytes = r;
+        if (q > qer_bytes) qer_bytes = q;
+    }
+    if (ctx->ensure(ctx->io_pairs, (size_t) n * sizeof(bm2_seqpair))) return 1;
+    if (ctx->ensure(ctx->io_ref, (size_t) ref_bytes + 16)) return 1;
+    if (ctx->ensure(ctx->io_qer, (size_t) qer_bytes + 16)) return 1;
+    BM2_CUDA_OK(cudaMemcpyAsync(ctx->io_pairs.p, pairs, (size_t) n * sizeof(bm2_seqpair), cudaMemcpyHostToDevice, ctx->stream));
+    if (ref_bytes) BM2_CUDA_OK(cudaMemcpyAsync(ctx->io_ref.p, ref, ref_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (qer_bytes) BM2_CUDA_OK(cudaMemcpyAsync(ctx->io_qer.p, qer, qer_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bm2_extend_pairs_device(ctx, (bm2_seqpair *) ctx->io_pairs.p, (const uint8_t *) ctx->io_ref.p,
+                                (const uint8_t *) ctx->io_qer.p, n, w, end_bonus, nullptr)) return 1;
+    BM2_CUDA_OK(cudaMemcpyAsync(pairs, ctx->io_pairs.p, (size_t) n * sizeof(bm2_seqpair), cudaMemcpyDeviceToHost, ctx->stream));
+    BM2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int bm2_set_stream(bm2_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return 1;
+    ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
+    return 0;
+}
+
+// ---- integer-pipe micro-benchmark: 8 independent dependent-chains of add+max per thread ----------
+__global__ void int_pipe_kernel(int *out, int iters, int seed) {
+    int a0 = seed + threadIdx.x, a1 = a0 ^ 0x55, a2 = a0 + 7, a3 = a0 * 3, a4 = a0 - 11, a5 = a0 ^ 0x33, a6 = a0 + 101, a7 = a0 - 5;
+    const int d = seed | 1, z = seed >> 20;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = max(a0 - d, z); a1 = max(a1 - d, z); a2 = max(a2 - d, z); a3 = max(a3 - d, z);
+            a4 = max(a4 + d, z); a5 = max(a5 + d, z); a6 = max(a6 + d, z); a7 = max(a7 + d, z);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int bm2_int_pipe_gops(bm2_ctx *ctx, double *gops) {
+    bm2_ctx *ctx_for_error = ctx;
+    if (!ctx || !gops) return 1;
+    BM2_CUDA_OK(cudaSetDevice(ctx->device));
+    const int blocks = ctx->n_sm * 8, threads = 256, iters = 4096;
+    if (ctx->ensure(ctx->bsw_outs, (size_t) blocks * threads * 4)) return 1;
+    cudaEvent_t e0, e1;
+    BM2_CUDA_OK(cudaEventCreate(&e0)); BM2_CUDA_OK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        BM2_CUDA_OK(cudaEventRecord(e0, ctx->stream));
+        int_pipe_kernel<<<blocks, threads, 0, ctx->stream>>>((int *) ctx->bsw_outs.p, iters, 12345 + rep);
+        BM2_CUDA_OK(cudaEventRecord(e1, ctx->stream));
+        BM2_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0; BM2_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    // per loop iteration and thread: 8 unrolled x 8 chains x 2 ops (add, max)
+    double ops = (double) blocks * threads * (double) iters * 8 * 8 * 2;
+    *gops = ops / (best * 1e-3) / 1e9;
+    return 0;
+}

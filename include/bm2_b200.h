@@ -92,6 +92,12 @@ void bm2_index_free(bm2_index_desc *idx);
 int  bm2_create(bm2_ctx **out, int device, const bm2_index_desc *idx, const bm2_mem_opt_t *opt);
 void bm2_destroy(bm2_ctx *ctx);
 const char *bm2_last_error(const bm2_ctx *ctx);   /* ctx may be NULL: last create error */
+/* Launch on a caller-owned CUDA stream (cudaStream_t as void*), e.g. the caller's framework stream,
+ * so that the caller's events bracket the kernels.  NULL restores the context's own stream. */
+int  bm2_set_stream(bm2_ctx *ctx, void *cuda_stream);
+/* Measured integer-pipe throughput of this device (G lane-ops/s of dependent 32-bit add/max
+ * chains over all SMs): the denominator of the BSW cell-update roofline. */
+int  bm2_int_pipe_gops(bm2_ctx *ctx, double *gops_s32);
 int  bm2_abi_version(void);
 
 /* ---- seam 1: batched banded-SW seed extension -------------------------------------------------

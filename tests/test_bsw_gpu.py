@@ -1,0 +1,92 @@
+"""GPU parity of seam 1 (bm2_extend_pairs) through the C ABI: bit-exact against the oracle on
+seeded inputs, against the reference's golden vectors, and on edge cases."""
+import numpy as np
+import pytest
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+OUT = ("score", "tle", "gtle", "qle", "gscore", "max_off")
+
+
+def _assert_same(got, want):
+    for f in OUT:
+        bad = np.nonzero(got[f] != want[f])[0]
+        assert len(bad) == 0, (f, bad[:5], got[f][bad[:5]], want[f][bad[:5]], got["len1"][bad[:5]], got["len2"][bad[:5]], got["h0"][bad[:5]])
+
+
+def test_golden_reference_vectors(pkg, gpu_ctx, golden_dir):
+    g = np.load(golden_dir + "/bsw_c0.npz")
+    p = np.zeros(len(g["h0"]), pkg.capi.PAIR_DT)
+    for f in ("len1", "len2", "h0", "idr", "idq"):
+        p[f] = g[f]
+    gpu_ctx.extend_pairs(p, g["ref"], g["qer"], int(g["w"]), int(g["p_end_bonus"]))
+    for f in OUT:
+        assert np.array_equal(p[f], g["out_" + f]), f
+
+
+def _random_jobs(rng, n, qmax, tmax, sim=0.9, nrate=0.01, h0max=150):
+    len2 = rng.integers(1, qmax + 1, n).astype(np.int32)
+    len1 = np.minimum(np.maximum(len2 + rng.integers(-20, 120, n), 0), tmax).astype(np.int32)
+    idq = np.concatenate([[0], np.cumsum(len2[:-1])]).astype(np.int32)
+    idr = np.concatenate([[0], np.cumsum(len1[:-1])]).astype(np.int32)
+    qer = rng.integers(0, 4, int(len2.sum()), dtype=np.uint8)
+    ref = rng.integers(0, 4, int(len1.sum()) + 1, dtype=np.uint8)
+    for i in range(n):  # make the target a noisy copy of the query so that extensions go somewhere
+        m = min(len1[i], len2[i])
+        t = qer[idq[i]:idq[i] + m].copy()
+        mut = rng.random(m) > sim
+        t[mut] = rng.integers(0, 4, int(mut.sum()))
+        if m > 30 and rng.random() < 0.3:  # an indel
+            k = int(rng.integers(5, m - 5)); d = int(rng.integers(1, 6))
+            t = np.concatenate([t[:k], t[k + d:], rng.integers(0, 4, d, dtype=np.uint8)])
+        ref[idr[i]:idr[i] + m] = t
+    qer[rng.random(len(qer)) < nrate] = 4
+    h0 = rng.integers(1, h0max, n).astype(np.int32)
+    return len1, len2, h0, idr, idq, ref, qer
+
+
+@pytest.mark.parametrize("seed,qmax,tmax,w", [(1, 151, 400, 100), (2, 151, 400, 200), (3, 40, 90, 100), (4, 700, 900, 100),
+                                               (5, 1500, 1700, 100), (6, 151, 400, 10)])
+def test_random_jobs_match_oracle(pkg, gpu_ctx, seed, qmax, tmax, w):
+    rng = np.random.default_rng(seed)
+    n = 3000 if qmax <= 151 else 400
+    len1, len2, h0, idr, idq, ref, qer = _random_jobs(rng, n, qmax, tmax)
+    p = np.zeros(n, pkg.capi.PAIR_DT)
+    p["len1"] = len1; p["len2"] = len2; p["h0"] = h0; p["idr"] = idr; p["idq"] = idq
+    want = p.copy()
+    gpu_ctx.extend_pairs(p, ref, qer, w, 5)
+    ol.extend_pairs(want, ref, qer, w, ol.bsw_params(end_bonus=5))
+    _assert_same(p, want)
+
+
+def test_edge_cases(pkg, gpu_ctx):
+    # empty target, single-base query/target, all-N query, h0 near the int16 class limit, >int16 scores (wide path)
+    seq = np.array([0, 1, 2, 3] * 64, np.uint8)
+    nq = np.full(64, 4, np.uint8)
+    qer = np.concatenate([seq[:4], seq[:1], nq, seq[:200], seq[:200]])
+    ref = np.concatenate([seq[:1], seq[:64], seq[:200], seq[:200]])
+    p = np.zeros(5, pkg.capi.PAIR_DT)
+    p["len1"] = [0, 1, 64, 200, 200]; p["len2"] = [4, 1, 64, 200, 200]
+    p["idr"] = [0, 0, 1, 65, 265]; p["idq"] = [0, 4, 5, 69, 269]
+    p["h0"] = [17, 3, 9, 32000, 40000]
+    want = p.copy()
+    gpu_ctx.extend_pairs(p, ref, qer, 100, 5)
+    ol.extend_pairs(want, ref, qer, 100, ol.bsw_params(end_bonus=5))
+    _assert_same(p, want)
+    assert p["score"][0] == 17 and p["gscore"][0] == -1
+    assert p["score"][4] == 40200
+
+
+def test_non_default_scoring(pkg, golden_dir):
+    o = pkg.capi.default_opt()
+    o.a, o.b, o.o_del, o.e_del, o.o_ins, o.e_ins, o.zdrop = 1, 1, 1, 1, 1, 1, 100   # -x ont2d scoring
+    ctx = pkg.capi.Context(0, opt=o)
+    rng = np.random.default_rng(11)
+    len1, len2, h0, idr, idq, ref, qer = _random_jobs(rng, 1500, 300, 500, sim=0.85)
+    p = np.zeros(1500, pkg.capi.PAIR_DT)
+    p["len1"] = len1; p["len2"] = len2; p["h0"] = h0; p["idr"] = idr; p["idq"] = idq
+    want = p.copy()
+    ctx.extend_pairs(p, ref, qer, 100, 0)
+    ol.extend_pairs(want, ref, qer, 100, ol.bsw_params(a=1, b=1, o_del=1, e_del=1, o_ins=1, e_ins=1, zdrop=100, end_bonus=0))
+    _assert_same(p, want)
+    ctx.close()
