@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <vector>
 #include <algorithm>
+#include <cmath>
 
 /* ------------------------------------------------------------------------------------------------
  * A6. Banded affine-gap extension DP.
@@ -118,4 +119,817 @@ extern "C" int64_t bm2o_extend_pairs(bm2_seqpair *pairs, const uint8_t *seq_buf_
         sp->score = o[0]; sp->qle = o[1]; sp->tle = o[2]; sp->gtle = o[3]; sp->gscore = o[4]; sp->max_off = o[5];
     }
     return cells;
+}
+
+/* ================================================================================================
+ * FM-index stages
+ * ============================================================================================== */
+extern "C" void bm2o_free(void *p) { free(p); }
+
+namespace {
+
+struct Fm {
+    const bm2_index_desc *x;
+    /* A1. Occ(b, pp): checkpoint count + popcount of the one-hot word masked to the first pp&63
+     * symbols (GET_OCC, src/FMI_search.h:66-73; mask table src/FMI_search.cpp:386-394). */
+    inline int64_t occ(int b, int64_t pp) const {
+        const bm2_cp_occ &c = x->cp_occ[pp >> 6];
+        int y = (int)(pp & 63);
+        uint64_t mask = y ? ~0ULL << (64 - y) : 0ULL;
+        return c.cp_count[b] + __builtin_popcountll(c.one_hot_bwt_str[b] & mask);
+    }
+};
+
+struct Iv { int64_t k, l, s; };
+
+/* backwardExt (src/FMI_search.cpp:1025-1052) */
+static Iv backward_ext(const Fm &fm, Iv in, int a) {
+    int64_t kk[4], ss[4], ll[4];
+    for (int b = 0; b < 4; ++b) {
+        int64_t o1 = fm.occ(b, in.k), o2 = fm.occ(b, in.k + in.s);
+        kk[b] = fm.x->count[b] + o1;
+        ss[b] = o2 - o1;
+    }
+    int64_t sent = (in.k <= fm.x->sentinel_index && in.k + in.s > fm.x->sentinel_index) ? 1 : 0;
+    ll[3] = in.l + sent; ll[2] = ll[3] + ss[3]; ll[1] = ll[2] + ss[2]; ll[0] = ll[1] + ss[1];
+    Iv out = { kk[a], ll[a], ss[a] };
+    return out;
+}
+/* forward extension = backward extension of the swapped interval with the complement base
+ * (src/FMI_search.cpp:544-553) */
+static Iv forward_ext(const Fm &fm, Iv in, int a) {
+    Iv sw = { in.l, in.k, in.s };
+    Iv r = backward_ext(fm, sw, 3 - a);
+    Iv out = { r.l, r.k, r.s };
+    return out;
+}
+static Iv init_iv(const Fm &fm, int a) {
+    Iv v = { fm.x->count[a], fm.x->count[3 - a], fm.x->count[a + 1] - fm.x->count[a] };
+    return v;
+}
+
+struct Sm { int32_t m, n; Iv v; };
+
+/* A2. one (read, x, min_intv) SMEM search (getSMEMsOnePosOneThread, src/FMI_search.cpp:496-670);
+ * appends to out, returns next_x. */
+static int smem_one_pos(const Fm &fm, const uint8_t *q, int len, int x, int min_intv, int min_seed_len,
+                        uint32_t rid, std::vector<bm2_smem> &out)
+{
+    int next_x = x + 1;
+    if (q[x] > 3) return next_x;
+    std::vector<Sm> prev;
+    Sm cur = { x, x, init_iv(fm, q[x]) };
+    int j;
+    for (j = x + 1; j < len; ++j) {
+        next_x = j + 1;
+        if (q[j] > 3) break;
+        Iv nv = forward_ext(fm, cur.v, q[j]);
+        if (nv.s != cur.v.s) prev.push_back(cur);
+        if (nv.s < min_intv) { next_x = j; break; }
+        cur.v = nv; cur.n = j;
+    }
+    if (cur.v.s >= min_intv) prev.push_back(cur);
+    std::reverse(prev.begin(), prev.end());
+    auto emit = [&](const Sm &s) {
+        bm2_smem o; o.rid = rid; o.m = s.m; o.n = s.n; o.k = s.v.k; o.l = s.v.l; o.s = s.v.s; out.push_back(o);
+    };
+    for (j = x - 1; j >= 0; --j) {
+        if (q[j] > 3) break;
+        std::vector<Sm> curr;
+        int curr_s = -1;
+        size_t p = 0;
+        for (; p < prev.size(); ++p) {
+            Iv nv = backward_ext(fm, prev[p].v, q[j]);
+            if (nv.s < min_intv && prev[p].n - prev[p].m + 1 >= min_seed_len) { emit(prev[p]); break; }
+            if (nv.s >= min_intv && nv.s != curr_s) {
+                curr_s = (int) nv.s;
+                Sm t = { j, prev[p].n, nv }; curr.push_back(t);
+                break;
+            }
+        }
+        for (++p; p < prev.size(); ++p) {
+            Iv nv = backward_ext(fm, prev[p].v, q[j]);
+            if (nv.s >= min_intv && nv.s != curr_s) {
+                curr_s = (int) nv.s;
+                Sm t = { j, prev[p].n, nv }; curr.push_back(t);
+            }
+        }
+        prev.swap(curr);
+        if (prev.empty()) break;
+    }
+    if (!prev.empty() && prev[0].n - prev[0].m + 1 >= min_seed_len) emit(prev[0]);
+    return next_x;
+}
+
+/* pass 3 (bwtSeedStrategyAllPosOneThread, src/FMI_search.cpp:726-812) */
+static void seed_strategy(const Fm &fm, const uint8_t *q, int len, int max_intv, int min_len, uint32_t rid,
+                          std::vector<bm2_smem> &out)
+{
+    int x = 0;
+    while (x < len) {
+        int next_x = x + 1;
+        if (q[x] < 4) {
+            Iv v = init_iv(fm, q[x]);
+            for (int j = x + 1; j < len; ++j) {
+                next_x = j + 1;
+                if (q[j] > 3) break;
+                v = forward_ext(fm, v, q[j]);
+                if (v.s < max_intv && j - x + 1 >= min_len) {
+                    if (v.s > 0) { bm2_smem o; o.rid = rid; o.m = x; o.n = j; o.k = v.k; o.l = v.l; o.s = v.s; out.push_back(o); }
+                    break;
+                }
+            }
+        }
+        x = next_x;
+    }
+}
+
+/* all three passes for one read, ordered (m asc, n asc) (src/bwamem.cpp:626-804,
+ * sortSMEMs src/FMI_search.cpp:987-1022) */
+static void collect_read(const Fm &fm, const bm2_mem_opt_t *opt, const uint8_t *q, int len, uint32_t rid,
+                         std::vector<bm2_smem> &out)
+{
+    size_t first = out.size();
+    if (len <= 0) return;
+    int split_len = (int)(opt->min_seed_len * opt->split_factor + .499);
+    for (int x = 0; x < len;) x = smem_one_pos(fm, q, len, x, 1, opt->min_seed_len, rid, out);
+    size_t n1 = out.size();
+    for (size_t i = first; i < n1; ++i) {
+        bm2_smem p = out[i];
+        int start = p.m, end = p.n + 1;
+        if (end - start < split_len || p.s > opt->split_width) continue;
+        smem_one_pos(fm, q, len, (end + start) >> 1, (int)(p.s + 1), opt->min_seed_len, rid, out);
+    }
+    if (opt->max_mem_intv > 0) seed_strategy(fm, q, len, (int) opt->max_mem_intv, opt->min_seed_len + 1, rid, out);
+    std::stable_sort(out.begin() + first, out.end(), [](const bm2_smem &a, const bm2_smem &b) {
+        return (((uint64_t) a.m << 32) | a.n) < (((uint64_t) b.m << 32) | b.n);
+    });
+}
+
+/* A3. SA of one BWT row: LF-walk to a sampled row (call_one_step, src/FMI_search.cpp:1202-1255);
+ * the walk returns 0 when it meets the sentinel (:1230-1233). */
+static int64_t sa_of_row(const Fm &fm, int64_t r) {
+    int64_t steps = 0;
+    while (r & 7) {
+        const bm2_cp_occ &c = fm.x->cp_occ[r >> 6];
+        int y = 63 - (int)(r & 63);
+        int b = 4;
+        for (int t = 0; t < 4; ++t) if ((c.one_hot_bwt_str[t] >> y) & 1) { b = t; break; }
+        if (b == 4) return 0;
+        r = fm.x->count[b] + fm.occ(b, r);
+        ++steps;
+    }
+    int64_t sa = ((int64_t) fm.x->sa_ms_byte[r >> 3] << 32) + (int64_t) fm.x->sa_ls_word[r >> 3];
+    return sa + steps;
+}
+
+/* bns_depos / bns_pos2rid / bns_intv2rid (src/bntseq.h:87-90, src/bntseq.cpp:378-402) */
+static int pos2rid(const bm2_index_desc *x, int64_t pos_f) {
+    if (pos_f >= x->l_pac) return -1;
+    int left = 0, mid = 0, right = x->n_seqs;
+    while (left < right) {
+        mid = (left + right) >> 1;
+        if (pos_f >= x->ann_offset[mid]) {
+            if (mid == x->n_seqs - 1) break;
+            if (pos_f < x->ann_offset[mid + 1]) break;
+            left = mid + 1;
+        } else right = mid;
+    }
+    return mid;
+}
+static int64_t depos(const bm2_index_desc *x, int64_t pos) { return pos >= x->l_pac ? (x->l_pac << 1) - 1 - pos : pos; }
+static int intv2rid(const bm2_index_desc *x, int64_t rb, int64_t re) {
+    if (rb < x->l_pac && re > x->l_pac) return -2;
+    int rid_b = pos2rid(x, depos(x, rb));
+    int rid_e = rb < re ? pos2rid(x, depos(x, re - 1)) : rid_b;
+    return rid_b == rid_e ? rid_b : -1;
+}
+
+/* ks_introsort (src/ksort.h:185-232) restated on indices: same comparisons, same swaps, hence the
+ * same order among ties.  lt(a,b) is the reference's __sort_lt. */
+template <class T, class LT> static void ks_insertsort(T *a, long s, long t, LT lt) {   /* [s,t) */
+    for (long i = s + 1; i < t; ++i)
+        for (long j = i; j > s && lt(a[j], a[j - 1]); --j) std::swap(a[j], a[j - 1]);
+}
+template <class T, class LT> static void ks_combsort(T *a, long n, LT lt) {
+    const double shrink = 1.2473309501039786540366528676643;
+    long gap = n; bool swapped;
+    do {
+        if (gap > 2) { gap = (long)(gap / shrink); if (gap == 9 || gap == 10) gap = 11; }
+        swapped = false;
+        for (long i = 0; i + gap < n; ++i) if (lt(a[i + gap], a[i])) { std::swap(a[i], a[i + gap]); swapped = true; }
+    } while (swapped || gap > 2);
+    if (gap != 1) ks_insertsort(a, 0, n, lt);
+}
+template <class T, class LT> static void ks_introsort(T *a, long n, LT lt) {
+    if (n < 1) return;
+    if (n == 2) { if (lt(a[1], a[0])) std::swap(a[0], a[1]); return; }
+    int d; for (d = 2; (1ul << d) < (unsigned long) n; ++d) {}
+    struct Fr { long l, r; int d; };
+    std::vector<Fr> stack;
+    long s = 0, t = n - 1; d <<= 1;
+    for (;;) {
+        if (s < t) {
+            if (--d == 0) { ks_combsort(a + s, t - s + 1, lt); t = s; continue; }
+            long i = s, j = t, k = i + ((j - i) >> 1) + 1;
+            if (lt(a[k], a[i])) { if (lt(a[k], a[j])) k = j; }
+            else k = lt(a[j], a[i]) ? i : j;
+            T rp = a[k];
+            if (k != t) std::swap(a[k], a[t]);
+            for (;;) {
+                do ++i; while (lt(a[i], rp));
+                do --j; while (i <= j && lt(rp, a[j]));
+                if (j <= i) break;
+                std::swap(a[i], a[j]);
+            }
+            std::swap(a[i], a[t]);
+            if (i - s > t - i) {
+                if (i - s > 16) { Fr f = { s, i - 1, d }; stack.push_back(f); }
+                s = t - i > 16 ? i + 1 : t;
+            } else {
+                if (t - i > 16) { Fr f = { i + 1, t, d }; stack.push_back(f); }
+                t = i - s > 16 ? i - 1 : s;
+            }
+        } else {
+            if (stack.empty()) { ks_insertsort(a, 0, n, lt); return; }
+            Fr f = stack.back(); stack.pop_back(); s = f.l; t = f.r; d = f.d;
+        }
+    }
+}
+
+struct OSeed { int64_t rbeg; int32_t qbeg, len, score; };
+struct OChain {
+    int64_t pos; int32_t rid, seqid, is_alt; int32_t w, kept, first; float frac_rep;
+    std::vector<OSeed> seeds;
+};
+
+/* test_and_merge (src/bwamem.cpp:357-399) */
+static bool test_and_merge(const bm2_mem_opt_t *opt, int64_t l_pac, OChain &c, const OSeed &p, int seed_rid) {
+    const OSeed &last = c.seeds.back(), &first = c.seeds.front();
+    int64_t qend = last.qbeg + last.len, rend = last.rbeg + last.len;
+    if (seed_rid != c.rid) return false;
+    if (p.qbeg >= first.qbeg && p.qbeg + p.len <= qend && p.rbeg >= first.rbeg && p.rbeg + p.len <= rend) return true;
+    if ((last.rbeg < l_pac || first.rbeg < l_pac) && p.rbeg >= l_pac) return false;
+    int64_t x = p.qbeg - last.qbeg, y = p.rbeg - last.rbeg;
+    if (y >= 0 && x - y <= opt->w && y - x <= opt->w && x - last.len < opt->max_chain_gap && y - last.len < opt->max_chain_gap) {
+        c.seeds.push_back(p);
+        return true;
+    }
+    return false;
+}
+
+/* mem_chain_weight (src/bwamem.cpp:429-448) */
+static int chain_weight(const OChain &c) {
+    int64_t end = 0; int w = 0, tmp;
+    for (const OSeed &s : c.seeds) {
+        if (s.qbeg >= end) w += s.len; else if (s.qbeg + s.len > end) w += (int)(s.qbeg + s.len - end);
+        end = end > s.qbeg + s.len ? end : s.qbeg + s.len;
+    }
+    tmp = w; w = 0; end = 0;
+    for (const OSeed &s : c.seeds) {
+        if (s.rbeg >= end) w += s.len; else if (s.rbeg + s.len > end) w += (int)(s.rbeg + s.len - end);
+        end = end > s.rbeg + s.len ? end : s.rbeg + s.len;
+    }
+    w = w < tmp ? w : tmp;
+    return w < (1 << 30) ? w : (1 << 30) - 1;
+}
+
+/* mem_chain_flt (src/bwamem.cpp:506-624) for the chains of one read */
+static void chain_filter(const bm2_mem_opt_t *opt, std::vector<OChain> &a) {
+    if (a.empty()) return;
+    std::vector<OChain> kept0;
+    for (OChain &c : a) { c.first = -1; c.kept = 0; c.w = chain_weight(c); }
+    for (OChain &c : a) if (c.w >= opt->min_chain_weight) kept0.push_back(c);
+    if (kept0.empty()) kept0.push_back(a[0]);     /* reference quirk: range (0,1) is processed even when k == 0 */
+    a.swap(kept0);
+    int n = (int) a.size();
+    ks_introsort(a.data(), n, [](const OChain &x, const OChain &y) { return x.w > y.w; });
+    std::vector<int> chains;
+    a[0].kept = 3; chains.push_back(0);
+    auto cbeg = [](const OChain &c) { return c.seeds.front().qbeg; };
+    auto cend = [](const OChain &c) { return c.seeds.back().qbeg + c.seeds.back().len; };
+    for (int i = 1; i < n; ++i) {
+        int large_ovlp = 0; size_t k;
+        for (k = 0; k < chains.size(); ++k) {
+            int j = chains[k];
+            int b_max = cbeg(a[j]) > cbeg(a[i]) ? cbeg(a[j]) : cbeg(a[i]);
+            int e_min = cend(a[j]) < cend(a[i]) ? cend(a[j]) : cend(a[i]);
+            if (e_min > b_max && (!a[j].is_alt || a[i].is_alt)) {
+                int li = cend(a[i]) - cbeg(a[i]), lj = cend(a[j]) - cbeg(a[j]);
+                int min_l = li < lj ? li : lj;
+                if (e_min - b_max >= min_l * opt->mask_level && min_l < opt->max_chain_gap) {
+                    large_ovlp = 1;
+                    if (a[j].first < 0) a[j].first = i;
+                    if (a[i].w < a[j].w * opt->drop_ratio && a[j].w - a[i].w >= opt->min_seed_len << 1) break;
+                }
+            }
+        }
+        if (k == chains.size()) { chains.push_back(i); a[i].kept = large_ovlp ? 2 : 3; }
+    }
+    for (int idx : chains) if (a[idx].first >= 0) a[a[idx].first].kept = 1;
+    int i, k;
+    for (i = k = 0; i < n; ++i) {
+        if (a[i].kept == 0 || a[i].kept == 3) continue;
+        if (++k >= opt->max_chain_extend) break;
+    }
+    for (; i < n; ++i) if (a[i].kept < 3) a[i].kept = 0;
+    std::vector<OChain> out;
+    for (OChain &c : a) if (c.kept) out.push_back(c);
+    a.swap(out);
+}
+
+/* A4. chains of one read from its ordered SMEMs (mem_chain_seeds, src/bwamem.cpp:806-974).  The
+ * B-tree is restated as an array ordered by pos; a new chain whose pos equals an existing one
+ * is placed right after the first equal element (leaf insertion rule, src/kbtree.h:219-225). */
+static void chain_read(const Fm &fm, const bm2_mem_opt_t *opt, const bm2_smem *sm, int64_t nsm, int l_seq, int seqid,
+                       std::vector<OChain> &chains)
+{
+    const bm2_index_desc *x = fm.x;
+    int b = 0, e = 0, l_rep = 0;
+    for (int64_t i = 0; i < nsm; ++i) {
+        int sb = sm[i].m, se = sm[i].n + 1;
+        if (sm[i].s <= opt->max_occ) continue;
+        if (sb > e) { l_rep += e - b; b = sb; e = se; }
+        else e = e > se ? e : se;
+    }
+    l_rep += e - b;
+    for (int64_t i = 0; i < nsm; ++i) {
+        const bm2_smem &p = sm[i];
+        int slen = p.n + 1 - p.m;
+        int64_t step = p.s > opt->max_occ ? p.s / opt->max_occ : 1;
+        int64_t k; int count;
+        for (k = 0, count = 0; k < p.s && count < opt->max_occ; k += step, ++count) {
+            OSeed s; s.rbeg = sa_of_row(fm, p.k + k); s.qbeg = p.m; s.len = s.score = slen;
+            int rid = intv2rid(x, s.rbeg, s.rbeg + s.len);
+            if (rid < 0) continue;
+            bool to_add = true;
+            long lower = -1;
+            if (!chains.empty()) {
+                /* first element with pos >= rbeg; equal -> lower = it, else the one before */
+                long lo = 0, hi = (long) chains.size();
+                while (lo < hi) { long mid = (lo + hi) >> 1; if (chains[mid].pos < s.rbeg) lo = mid + 1; else hi = mid; }
+                if (lo < (long) chains.size() && chains[lo].pos == s.rbeg) lower = lo; else lower = lo - 1;
+                if (lower >= 0 && test_and_merge(opt, x->l_pac, chains[lower], s, rid)) to_add = false;
+            }
+            if (to_add) {
+                OChain c; c.pos = s.rbeg; c.rid = rid; c.seqid = seqid; c.is_alt = x->ann_is_alt ? !!x->ann_is_alt[rid] : 0;
+                c.w = 0; c.kept = 0; c.first = -1; c.frac_rep = 0; c.seeds.push_back(s);
+                chains.insert(chains.begin() + (lower + 1), c);
+            }
+        }
+    }
+    for (OChain &c : chains) c.frac_rep = (float) l_rep / l_seq;
+}
+
+}  // namespace
+
+static const int BLOCK_READS = 512;   /* BATCH_SIZE, src/macro.h:48 */
+
+static void collect_all(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads,
+                        std::vector<bm2_smem> &all)
+{
+    Fm fm = { idx };
+    for (int b0 = 0; b0 < reads->n_reads; b0 += BLOCK_READS) {
+        size_t first = all.size();
+        int b1 = std::min(reads->n_reads, b0 + BLOCK_READS);
+        for (int r = b0; r < b1; ++r)
+            collect_read(fm, opt, reads->codes + reads->offsets[r], (int)(reads->offsets[r + 1] - reads->offsets[r]), r, all);
+        (void) first;
+    }
+}
+
+extern "C" int64_t bm2o_collect_smems(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads,
+                                      bm2_smem **out)
+{
+    std::vector<bm2_smem> all;
+    collect_all(idx, opt, reads, all);
+    *out = (bm2_smem *) malloc(sizeof(bm2_smem) * (all.size() + 1));
+    memcpy(*out, all.data(), sizeof(bm2_smem) * all.size());
+    return (int64_t) all.size();
+}
+
+extern "C" void bm2o_sa_lookup(const bm2_index_desc *idx, const int64_t *rows, int64_t n, int64_t *out) {
+    Fm fm = { idx };
+    for (int64_t i = 0; i < n; ++i) out[i] = sa_of_row(fm, rows[i]);
+}
+
+extern "C" int bm2o_seed_chain(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads,
+                               bm2_chain **chains, int64_t *n_chains, bm2_seed **seeds, int64_t *n_seeds, int64_t **read_off)
+{
+    Fm fm = { idx };
+    std::vector<bm2_chain> oc; std::vector<bm2_seed> os;
+    int64_t *off = (int64_t *) malloc(sizeof(int64_t) * (reads->n_reads + 1));
+    off[0] = 0;
+    for (int b0 = 0; b0 < reads->n_reads; b0 += BLOCK_READS) {
+        int b1 = std::min(reads->n_reads, b0 + BLOCK_READS);
+        std::vector<bm2_smem> sm;
+        for (int r = b0; r < b1; ++r)
+            collect_read(fm, opt, reads->codes + reads->offsets[r], (int)(reads->offsets[r + 1] - reads->offsets[r]), r, sm);
+        /* reference quirk: a 512-read block whose SMEM total is exactly 1 yields no chain
+         * (loop guards `pos < num_smem - 1`, src/bwamem.cpp:835) */
+        bool skip_block = sm.size() <= 1;
+        size_t p = 0;
+        for (int r = b0; r < b1; ++r) {
+            size_t q = p;
+            while (q < sm.size() && (int) sm[q].rid == r) ++q;
+            std::vector<OChain> ch;
+            int l_seq = (int)(reads->offsets[r + 1] - reads->offsets[r]);
+            if (!skip_block && q > p && l_seq >= opt->min_seed_len) {
+                chain_read(fm, opt, sm.data() + p, (int64_t)(q - p), l_seq, r, ch);
+                chain_filter(opt, ch);
+            }
+            for (OChain &c : ch) {
+                bm2_chain o; memset(&o, 0, sizeof(o));
+                o.pos = c.pos; o.seqid = c.seqid; o.rid = c.rid; o.n_seeds = (int32_t) c.seeds.size(); o.seed_off = (int32_t) os.size();
+                o.w = c.w; o.kept = c.kept; o.first = c.first; o.is_alt = c.is_alt; o.frac_rep = c.frac_rep;
+                for (OSeed &s : c.seeds) { bm2_seed t; t.rbeg = s.rbeg; t.qbeg = s.qbeg; t.len = s.len; t.score = s.score; t.chain = (int32_t) oc.size(); os.push_back(t); }
+                oc.push_back(o);
+            }
+            off[r + 1] = (int64_t) oc.size();
+            p = q;
+        }
+    }
+    *chains = (bm2_chain *) malloc(sizeof(bm2_chain) * (oc.size() + 1)); memcpy(*chains, oc.data(), sizeof(bm2_chain) * oc.size());
+    *seeds = (bm2_seed *) malloc(sizeof(bm2_seed) * (os.size() + 1)); memcpy(*seeds, os.data(), sizeof(bm2_seed) * os.size());
+    *n_chains = (int64_t) oc.size(); *n_seeds = (int64_t) os.size(); *read_off = off;
+    return 0;
+}
+
+/* ================================================================================================
+ * Extension stage (A5-A8) and the tail of mem_kernel2_core
+ * ============================================================================================== */
+namespace {
+
+/* cal_max_gap (src/bwamem.cpp:66-76) */
+static int cal_max_gap(const bm2_mem_opt_t *opt, int qlen) {
+    int l_del = (int)((double)(qlen * opt->a - opt->o_del) / opt->e_del + 1.);
+    int l_ins = (int)((double)(qlen * opt->a - opt->o_ins) / opt->e_ins + 1.);
+    int l = l_del > l_ins ? l_del : l_ins;
+    l = l > 1 ? l : 1;
+    return l < opt->w << 1 ? l : opt->w << 1;
+}
+
+/* ksw_global2, score only (src/ksw.cpp:558-668) */
+static int global_score(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat,
+                        int o_del, int e_del, int o_ins, int e_ins, int w)
+{
+    const int MINUS_INF = -0x40000000;
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    std::vector<int32_t> H(qlen + 1), E(qlen + 1);
+    H[0] = 0; E[0] = MINUS_INF;
+    int j;
+    for (j = 1; j <= qlen && j <= w; ++j) { H[j] = -(o_ins + e_ins * j); E[j] = MINUS_INF; }
+    for (; j <= qlen; ++j) H[j] = E[j] = MINUS_INF;
+    for (int i = 0; i < tlen; ++i) {
+        int32_t f = MINUS_INF, h1;
+        int beg = i > w ? i - w : 0;
+        int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+        h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : MINUS_INF;
+        for (j = beg; j < end; ++j) {
+            int32_t m = H[j], e = E[j];
+            H[j] = h1;
+            m += mat[target[i] * 5 + query[j]];
+            int32_t h = m >= e ? m : e;
+            h = h >= f ? h : f;
+            h1 = h;
+            int32_t t = m - oe_del;
+            e -= e_del; e = e > t ? e : t;
+            E[j] = e;
+            t = m - oe_ins;
+            f -= e_ins; f = f > t ? f : t;
+        }
+        H[end] = h1; E[end] = MINUS_INF;
+    }
+    return H[qlen];
+}
+
+/* bwa_gen_cigar2 with n_cigar == NM == NULL: score of the banded global alignment of
+ * query[0..l_query) against T[rb..re) (src/bwa.cpp:260-347); returns false when rejected. */
+static bool gen_score(const bm2_index_desc *x, const bm2_mem_opt_t *opt, int w_, int l_query, const uint8_t *query,
+                      int64_t rb, int64_t re, int *score)
+{
+    int64_t l_pac = x->l_pac;
+    if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) return false;
+    if (re > (l_pac << 1)) return false;       /* bns_get_seq clips -> re-rb != rlen -> no score */
+    if (rb < 0) return false;
+    int64_t rlen = re - rb;
+    std::vector<uint8_t> rs(x->ref_string + rb, x->ref_string + re), qs(query, query + l_query);
+    if (rb >= l_pac) { std::reverse(rs.begin(), rs.end()); std::reverse(qs.begin(), qs.end()); }
+    if (l_query == re - rb && w_ == 0) {
+        int sc = 0;
+        for (int i = 0; i < l_query; ++i) sc += opt->mat[rs[i] * 5 + qs[i]];
+        *score = sc;
+    } else {
+        int max_ins = (int)((double)(((l_query + 1) >> 1) * opt->mat[0] - opt->o_ins) / opt->e_ins + 1.);
+        int max_del = (int)((double)(((l_query + 1) >> 1) * opt->mat[0] - opt->o_del) / opt->e_del + 1.);
+        int max_gap = max_ins > max_del ? max_ins : max_del;
+        max_gap = max_gap > 1 ? max_gap : 1;
+        int diff = (int)(rlen - l_query); if (diff < 0) diff = -diff;
+        int w = (max_gap + diff + 1) >> 1;
+        w = w < w_ ? w : w_;
+        int min_w = diff + 3;
+        w = w > min_w ? w : min_w;
+        *score = global_score(l_query, qs.data(), (int) rlen, rs.data(), opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, w);
+    }
+    return true;
+}
+
+/* mem_patch_reg (src/bwamem.cpp:175-234) */
+static int patch_reg(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const uint8_t *query, const bm2_alnreg_t *a,
+                     const bm2_alnreg_t *b, int *_w)
+{
+    int w, score = 0, q_s, r_s;
+    double r;
+    if (a->rb < x->l_pac && b->rb >= x->l_pac) return 0;
+    if (a->qb >= b->qb || a->qe >= b->qe || a->re >= b->re) return 0;
+    w = (int)((a->re - b->rb) - (a->qe - b->qb));
+    w = w > 0 ? w : -w;
+    r = (double)(a->re - b->rb) / (b->re - a->rb) - (double)(a->qe - b->qb) / (b->qe - a->qb);
+    r = r > 0. ? r : -r;
+    if (a->re < b->rb || a->qe < b->qb) {
+        if (w > opt->w << 1 || r >= 0.05f) return 0;
+    } else if (w > opt->w << 2 || r >= 0.05f * 2) return 0;
+    w += a->w + b->w;
+    w = w < opt->w << 2 ? w : opt->w << 2;
+    if (!gen_score(x, opt, w, b->qe - a->qb, query + a->qb, a->rb, b->re, &score)) score = 0;
+    q_s = (int)((double)(b->qe - a->qb) / ((b->qe - b->qb) + (a->qe - a->qb)) * (b->score + a->score) + .499);
+    r_s = (int)((double)(b->re - a->rb) / ((b->re - b->rb) + (a->re - a->rb)) * (b->score + a->score) + .499);
+    if ((double) score / (q_s > r_s ? q_s : r_s) < 0.90f) return 0;
+    *_w = w;
+    return score;
+}
+
+static inline int reg_n_comp(const bm2_alnreg_t &a) { return (a.n_comp_is_alt << 2) >> 2; }
+static inline void reg_set_n_comp(bm2_alnreg_t &a, int v) { a.n_comp_is_alt = (a.n_comp_is_alt & ~0x3FFFFFFF) | (v & 0x3FFFFFFF); }
+static inline void reg_set_is_alt(bm2_alnreg_t &a, int v) { a.n_comp_is_alt = (a.n_comp_is_alt & 0x3FFFFFFF) | ((v & 3) << 30); }
+
+/* mem_sort_dedup_patch (src/bwamem.cpp:292-353) */
+static int sort_dedup_patch(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const uint8_t *query, int n, bm2_alnreg_t *a) {
+    int m, i, j;
+    if (n <= 1) return n;
+    ks_introsort(a, n, [](const bm2_alnreg_t &p, const bm2_alnreg_t &q) { return p.re < q.re; });
+    for (i = 0; i < n; ++i) reg_set_n_comp(a[i], 1);
+    for (i = 1; i < n; ++i) {
+        bm2_alnreg_t *p = &a[i];
+        if (p->rid != a[i - 1].rid || p->rb >= a[i - 1].re + opt->max_chain_gap) continue;
+        for (j = i - 1; j >= 0 && p->rid == a[j].rid && p->rb < a[j].re + opt->max_chain_gap; --j) {
+            bm2_alnreg_t *q = &a[j];
+            int64_t or_, oq, mr, mq;
+            int score, w;
+            if (q->qe == q->qb) continue;
+            or_ = q->re - p->rb;
+            oq = q->qb < p->qb ? q->qe - p->qb : p->qe - q->qb;
+            mr = q->re - q->rb < p->re - p->rb ? q->re - q->rb : p->re - p->rb;
+            mq = q->qe - q->qb < p->qe - p->qb ? q->qe - q->qb : p->qe - p->qb;
+            if (or_ > opt->mask_level_redun * mr && oq > opt->mask_level_redun * mq) {
+                if (p->score < q->score) { p->qe = p->qb; break; }
+                else q->qe = q->qb;
+            } else if (q->rb < p->rb && (score = patch_reg(x, opt, query, q, p, &w)) > 0) {
+                reg_set_n_comp(*p, reg_n_comp(*p) + reg_n_comp(*q) + 1);
+                p->seedcov = p->seedcov > q->seedcov ? p->seedcov : q->seedcov;
+                p->sub = p->sub > q->sub ? p->sub : q->sub;
+                p->csub = p->csub > q->csub ? p->csub : q->csub;
+                p->qb = q->qb; p->rb = q->rb;
+                p->truesc = p->score = score;
+                p->w = w;
+                q->qb = q->qe;
+            }
+        }
+    }
+    for (i = 0, m = 0; i < n; ++i)
+        if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
+    n = m;
+    ks_introsort(a, n, [](const bm2_alnreg_t &p, const bm2_alnreg_t &q) {
+        return p.score > q.score || (p.score == q.score && (p.rb < q.rb || (p.rb == q.rb && p.qb < q.qb)));
+    });
+    for (i = 1; i < n; ++i)
+        if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
+    for (i = 1, m = 1; i < n; ++i)
+        if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
+    return m;
+}
+
+struct ExtJob { int reg; int qlen, tlen; int64_t toff; int qoff; int dir; };   /* dir -1: left (reversed), +1: right */
+
+/* mem_chain2aln_across_reads_V2 for one read (src/bwamem.cpp:2069-2994) */
+static void extend_read(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const uint8_t *query, int l_query,
+                        std::vector<OChain> &chains, std::vector<bm2_alnreg_t> &av, int64_t *cells)
+{
+    const int64_t l_pac = x->l_pac;
+    const int H0_ = -99;
+    struct SeedRef { int chain, seed, aln; };
+    std::vector<SeedRef> order;              /* replay order (A5) */
+    std::vector<ExtJob> left, right;
+    std::vector<int> reg_chain;
+    for (size_t ci = 0; ci < chains.size(); ++ci) {
+        OChain &c = chains[ci];
+        if (c.seeds.empty()) continue;
+        int64_t rmax0 = l_pac << 1, rmax1 = 0;
+        for (const OSeed &t : c.seeds) {
+            int64_t b = t.rbeg - (t.qbeg + cal_max_gap(opt, t.qbeg));
+            int64_t e = t.rbeg + t.len + ((l_query - t.qbeg - t.len) + cal_max_gap(opt, l_query - t.qbeg - t.len));
+            rmax0 = rmax0 < b ? rmax0 : b;
+            rmax1 = rmax1 > e ? rmax1 : e;
+        }
+        rmax0 = rmax0 > 0 ? rmax0 : 0;
+        rmax1 = rmax1 < l_pac << 1 ? rmax1 : l_pac << 1;
+        if (rmax0 < l_pac && l_pac < rmax1) { if (c.seeds[0].rbeg < l_pac) rmax1 = l_pac; else rmax0 = l_pac; }
+        {   /* bns_fetch_seq_v2: clip to the contig of seeds[0].rbeg (src/bwamem.cpp:1890-1924) */
+            int64_t mid = c.seeds[0].rbeg;
+            int is_rev = mid >= l_pac;
+            int rid = pos2rid(x, depos(x, mid));
+            int64_t far_beg = x->ann_offset[rid], far_end = far_beg + x->ann_len[rid];
+            if (is_rev) { int64_t tmp = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - tmp; }
+            rmax0 = rmax0 > far_beg ? rmax0 : far_beg;
+            rmax1 = rmax1 < far_end ? rmax1 : far_end;
+        }
+        int n = (int) c.seeds.size();
+        std::vector<uint64_t> srt(n);
+        for (int i = 0; i < n; ++i) srt[i] = (uint64_t) c.seeds[i].score << 32 | (uint32_t) i;
+        std::sort(srt.begin(), srt.end());       /* keys are unique: ks_introsort_64 gives the same order */
+        for (int k = n - 1; k >= 0; --k) {
+            int si = (int)(uint32_t) srt[k];
+            const OSeed &s = c.seeds[si];
+            bm2_alnreg_t a; memset(&a, 0, sizeof(a));
+            int ai = (int) av.size();
+            a.w = opt->w; a.score = a.truesc = -1; a.rid = c.rid; a.frac_rep = c.frac_rep; a.seedlen0 = s.len;
+            a.rb = a.re = H0_; a.qb = a.qe = H0_;
+            if (s.qbeg) {
+                ExtJob j; j.reg = ai; j.qlen = s.qbeg; j.tlen = (int)(s.rbeg - rmax0); j.toff = s.rbeg - 1; j.qoff = s.qbeg - 1; j.dir = -1;
+                left.push_back(j);
+                a.qb = s.qbeg; a.rb = s.rbeg;
+            } else { a.score = a.truesc = s.len * opt->a; a.qb = 0; a.rb = s.rbeg; }
+            bool has_right = false;
+            if (s.qbeg + s.len != l_query) {
+                int64_t qe = s.qbeg + s.len, re = s.rbeg + s.len - rmax0;
+                ExtJob j; j.reg = ai; j.qlen = (int)(l_query - qe); j.tlen = (int)(rmax1 - rmax0 - re); j.toff = rmax0 + re; j.qoff = (int) qe; j.dir = 1;
+                right.push_back(j);
+                a.qe = (int) qe; a.re = rmax0 + re;
+                has_right = true;
+            } else { a.qe = l_query; a.re = s.rbeg + s.len; }
+            av.push_back(a); reg_chain.push_back((int) ci);
+            if (!has_right && av[ai].rb != H0_ && av[ai].qb != H0_) {
+                int cov = 0;
+                for (const OSeed &t : c.seeds)
+                    if (t.qbeg >= av[ai].qb && t.qbeg + t.len <= av[ai].qe && t.rbeg >= av[ai].rb && t.rbeg + t.len <= av[ai].re) cov += t.len;
+                av[ai].seedcov = cov;
+            }
+            SeedRef sr = { (int) ci, si, ai }; order.push_back(sr);
+        }
+    }
+    auto seedcov = [&](bm2_alnreg_t &a, const OChain &c) {
+        if (a.rb != H0_ && a.qb != H0_ && a.qe != H0_ && a.re != H0_) {
+            int cov = 0;
+            for (const OSeed &t : c.seeds)
+                if (t.qbeg >= a.qb && t.qbeg + t.len <= a.qe && t.rbeg >= a.rb && t.rbeg + t.len <= a.re) cov += t.len;
+            a.seedcov = cov;
+        }
+    };
+    auto run = [&](const ExtJob &j, int h0, int w, int end_bonus, int32_t *o) {
+        std::vector<uint8_t> q(j.qlen), t(j.tlen);
+        for (int i = 0; i < j.qlen; ++i) q[i] = query[j.qoff + (int64_t) i * j.dir];
+        for (int i = 0; i < j.tlen; ++i) t[i] = x->ref_string[j.toff + (int64_t) i * j.dir];
+        bm2o_bsw_params p = { opt->a, opt->b, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, opt->zdrop, end_bonus, 1 };
+        /* the reference routes jobs with 32-bit scores to the scalar kernel (src/bwamem.cpp:2304-2313) */
+        int minlen = j.qlen < j.tlen ? j.qlen : j.tlen;
+        if (!(j.tlen < 32768 && j.qlen < 32768 && h0 + minlen * opt->a < 32768)) p.vector_quirks = 0;
+        *cells += bm2o_bsw_extend(q.data(), j.qlen, t.data(), j.tlen, w, h0, &p, o);
+    };
+    /* A7 left */
+    for (const ExtJob &j : left) {
+        bm2_alnreg_t &a = av[j.reg];
+        const OChain &c = chains[reg_chain[j.reg]];
+        int h0 = a.seedlen0 * opt->a;
+        for (int i = 0; i < 2; ++i) {
+            int w = opt->w << i; int32_t o[6];
+            run(j, h0, w, opt->pen_clip5, o);
+            int score = o[0], qle = o[1], tle = o[2], gtle = o[3], gscore = o[4], max_off = o[5];
+            int prev = a.score; a.score = score;
+            if (a.score == prev || max_off < (w >> 1) + (w >> 2) || i + 1 == 2) {
+                if (gscore <= 0 || gscore <= a.score - opt->pen_clip5) { a.qb -= qle; a.rb -= tle; a.truesc = a.score; }
+                else { a.qb = 0; a.rb -= gtle; a.truesc = gscore; }
+                a.w = a.w > w ? a.w : w;
+                seedcov(a, c);
+                break;
+            }
+        }
+    }
+    /* A7 right */
+    for (const ExtJob &j : right) {
+        bm2_alnreg_t &a = av[j.reg];
+        const OChain &c = chains[reg_chain[j.reg]];
+        int h0 = a.score;
+        for (int i = 0; i < 2; ++i) {
+            int w = opt->w << i; int32_t o[6];
+            run(j, h0, w, opt->pen_clip3, o);
+            int score = o[0], qle = o[1], tle = o[2], gtle = o[3], gscore = o[4], max_off = o[5];
+            int prev = a.score; a.score = score;
+            if (a.score == prev || max_off < (w >> 1) + (w >> 2) || i + 1 == 2) {
+                if (gscore <= 0 || gscore <= a.score - opt->pen_clip3) { a.qe += qle; a.re += tle; a.truesc += a.score - h0; }
+                else { a.qe = l_query; a.re += gtle; a.truesc += gscore - h0; }
+                a.w = a.w > w ? a.w : w;
+                seedcov(a, c);
+                break;
+            }
+        }
+    }
+    /* A8 post-filter (src/bwamem.cpp:2895-2989) */
+    int lim = 0;
+    size_t pos = 0;
+    for (size_t ci = 0; ci < chains.size(); ++ci) {
+        OChain &c = chains[ci];
+        int n = (int) c.seeds.size();
+        if (n == 0) continue;
+        /* srt2[k] for k = n-1..0 is order[pos + (n-1-k)] */
+        std::vector<int> srt2(n); std::vector<int> aln_of(n);
+        for (int k = n - 1; k >= 0; --k) { srt2[k] = order[pos + (n - 1 - k)].seed; aln_of[k] = order[pos + (n - 1 - k)].aln; }
+        pos += n;
+        for (int k = n - 1; k >= 0; --k) {
+            const OSeed &s = c.seeds[srt2[k]];
+            int i, v = 0;
+            for (i = 0; i < (int) av.size() && v < lim; ++i) {
+                bm2_alnreg_t *p = &av[i];
+                if (p->qb == -1 && p->qe == -1) continue;
+                int64_t rd; int qd, w, max_gap;
+                if (s.rbeg < p->rb || s.rbeg + s.len > p->re || s.qbeg < p->qb || s.qbeg + s.len > p->qe) { v++; continue; }
+                if (s.len - p->seedlen0 > .1 * l_query) { v++; continue; }
+                qd = s.qbeg - p->qb; rd = s.rbeg - p->rb;
+                max_gap = cal_max_gap(opt, qd < rd ? qd : (int) rd);
+                w = max_gap < p->w ? max_gap : p->w;
+                if (qd - rd < w && rd - qd < w) break;
+                qd = p->qe - (s.qbeg + s.len); rd = p->re - (s.rbeg + s.len);
+                max_gap = cal_max_gap(opt, qd < rd ? qd : (int) rd);
+                w = max_gap < p->w ? max_gap : p->w;
+                if (qd - rd < w && rd - qd < w) break;
+                v++;
+            }
+            if (v < lim) {
+                int vv;
+                for (vv = k + 1; vv < n; ++vv) {
+                    if (srt2[vv] < 0) continue;
+                    const OSeed &t = c.seeds[srt2[vv]];
+                    if (t.len < s.len * .95) continue;
+                    if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
+                    if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
+                }
+                if (vv == n) {
+                    av[aln_of[k]].qb = av[aln_of[k]].qe = -1;
+                    srt2[k] = -1;
+                    continue;
+                }
+            }
+            lim++;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int bm2o_seed_chain_extend(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads,
+                                      bm2_alnreg_t **regs, int64_t *n_regs, int64_t **read_off, int64_t *bsw_cells)
+{
+    Fm fm = { idx };
+    std::vector<bm2_alnreg_t> all;
+    int64_t *off = (int64_t *) malloc(sizeof(int64_t) * (reads->n_reads + 1));
+    off[0] = 0;
+    int64_t cells = 0;
+    int rc = 0;
+    for (int b0 = 0; b0 < reads->n_reads; b0 += BLOCK_READS) {
+        int b1 = std::min(reads->n_reads, b0 + BLOCK_READS);
+        std::vector<bm2_smem> sm;
+        for (int r = b0; r < b1; ++r)
+            collect_read(fm, opt, reads->codes + reads->offsets[r], (int)(reads->offsets[r + 1] - reads->offsets[r]), r, sm);
+        bool skip_block = sm.size() <= 1;
+        size_t p = 0;
+        for (int r = b0; r < b1; ++r) {
+            size_t q = p;
+            while (q < sm.size() && (int) sm[q].rid == r) ++q;
+            std::vector<OChain> ch;
+            const uint8_t *query = reads->codes + reads->offsets[r];
+            int l_seq = (int)(reads->offsets[r + 1] - reads->offsets[r]);
+            if (!skip_block && q > p && l_seq >= opt->min_seed_len) {
+                chain_read(fm, opt, sm.data() + p, (int64_t)(q - p), l_seq, r, ch);
+                chain_filter(opt, ch);
+                /* mem_flt_chained_seeds (src/bwamem.cpp:472-504) is a no-op unless min_l <= 0.05 * l_query */
+                double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log((double) l_seq);
+                if (!(min_l > 0.05f * l_seq) && !ch.empty()) rc = 2;
+            }
+            std::vector<bm2_alnreg_t> av;
+            extend_read(idx, opt, query, l_seq, ch, av, &cells);
+            int m = 0;
+            for (size_t i = 0; i < av.size(); ++i) if (av[i].qe > av[i].qb) av[m++] = av[i];
+            m = sort_dedup_patch(idx, opt, query, m, av.data());
+            for (int i = 0; i < m; ++i) {
+                if (av[i].rid >= 0 && idx->ann_is_alt && idx->ann_is_alt[av[i].rid]) reg_set_is_alt(av[i], 1);
+                all.push_back(av[i]);
+            }
+            off[r + 1] = (int64_t) all.size();
+            p = q;
+        }
+    }
+    *regs = (bm2_alnreg_t *) malloc(sizeof(bm2_alnreg_t) * (all.size() + 1));
+    memcpy(*regs, all.data(), sizeof(bm2_alnreg_t) * all.size());
+    *n_regs = (int64_t) all.size(); *read_off = off;
+    if (bsw_cells) *bsw_cells = cells;
+    return rc;
 }

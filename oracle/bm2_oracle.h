@@ -29,6 +29,28 @@ int64_t bm2o_bsw_extend(const uint8_t *query, int32_t qlen, const uint8_t *targe
 int64_t bm2o_extend_pairs(bm2_seqpair *pairs, const uint8_t *seq_buf_ref, const uint8_t *seq_buf_qer,
                           int32_t n_pairs, int32_t w, const bm2o_bsw_params *p);
 
+/* ---- FM-index stages (A1-A4).  Results are malloc'd arrays the caller frees with bm2o_free. ---- */
+void bm2o_free(void *p);
+
+/* three SMEM passes + ordering == mem_collect_smem (src/bwamem.cpp:626-804); reads are processed
+ * in blocks of `block` reads (BATCH_SIZE = 512, src/macro.h:48) like kt_for does. */
+int64_t bm2o_collect_smems(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads,
+                           bm2_smem **out);
+
+/* SA lookup of rows == FMI_search::get_sa_entries_prefetch (src/FMI_search.cpp:1257-1375) */
+void bm2o_sa_lookup(const bm2_index_desc *idx, const int64_t *rows, int64_t n, int64_t *out);
+
+/* SMEM + SA + chaining + chain filter == mem_kernel1_core (src/bwamem.cpp:976-1091), without
+ * mem_flt_chained_seeds.  read_off has n_reads+1 entries. */
+int bm2o_seed_chain(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads,
+                    bm2_chain **chains, int64_t *n_chains, bm2_seed **seeds, int64_t *n_seeds, int64_t **read_off);
+
+/* the whole hot path == worker_bwt + worker_aln (src/bwamem.cpp:1193-1214, :1175-1191): regs per
+ * read as mem_kernel2_core leaves them (src/bwamem.cpp:1093-1172).  Returns non-zero if a read
+ * needs mem_flt_chained_seeds' local SW (long reads; not restated yet). */
+int bm2o_seed_chain_extend(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads,
+                           bm2_alnreg_t **regs, int64_t *n_regs, int64_t **read_off, int64_t *bsw_cells);
+
 #ifdef __cplusplus
 }
 #endif

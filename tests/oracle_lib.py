@@ -43,3 +43,86 @@ def extend_pairs(pairs, ref, qer, w, params):
     assert pairs.flags.c_contiguous
     return lib().bm2o_extend_pairs(pairs.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p),
                                    qer.ctypes.data_as(C.c_void_p), C.c_int32(len(pairs)), C.c_int32(w), C.byref(params))
+
+
+# ---- FM-index stages ----------------------------------------------------------------------------
+def _capi():
+    import sys
+    from __graft_entry__ import load_package
+    return load_package().capi
+
+
+def collect_smems(index, opt, codes, offsets):
+    capi = _capi()
+    codes = np.ascontiguousarray(codes, np.uint8); offsets = np.ascontiguousarray(offsets, np.int64)
+    rb = capi.ReadBatch(len(offsets) - 1, codes.ctypes.data, offsets.ctypes.data)
+    out = C.c_void_p()
+    L = lib()
+    L.bm2o_collect_smems.restype = C.c_int64
+    n = L.bm2o_collect_smems(C.byref(index.desc), C.byref(opt), C.byref(rb), C.byref(out))
+    a = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(max(n, 1) * capi.SMEM_DT.itemsize,))[:n * capi.SMEM_DT.itemsize].view(capi.SMEM_DT).copy()
+    L.bm2o_free(out)
+    return a
+
+
+def sa_lookup(index, rows):
+    rows = np.ascontiguousarray(rows, np.int64)
+    out = np.empty_like(rows)
+    lib().bm2o_sa_lookup(C.byref(index.desc), rows.ctypes.data_as(C.c_void_p), C.c_int64(len(rows)), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def seed_chain(index, opt, codes, offsets):
+    capi = _capi()
+    codes = np.ascontiguousarray(codes, np.uint8); offsets = np.ascontiguousarray(offsets, np.int64)
+    rb = capi.ReadBatch(len(offsets) - 1, codes.ctypes.data, offsets.ctypes.data)
+    ch = C.c_void_p(); sd = C.c_void_p(); off = C.c_void_p(); nc = C.c_int64(); ns = C.c_int64()
+    L = lib()
+    rc = L.bm2o_seed_chain(C.byref(index.desc), C.byref(opt), C.byref(rb), C.byref(ch), C.byref(nc), C.byref(sd), C.byref(ns), C.byref(off))
+    assert rc == 0
+    def arr(p, n, dt):
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(n, 1) * dt.itemsize,))[:n * dt.itemsize].view(dt).copy()
+        return a
+    chains = arr(ch, nc.value, capi.CHAIN_DT); seeds = arr(sd, ns.value, capi.SEED_DT)
+    offs = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_int64)), shape=(rb.n_reads + 1,)).copy()
+    for p in (ch, sd, off):
+        L.bm2o_free(p)
+    return chains, seeds, offs
+
+
+def seed_chain_extend(index, opt, codes, offsets):
+    """-> (regs REG_DT array, read_off, bsw_cells, rc)"""
+    capi = _capi()
+    codes = np.ascontiguousarray(codes, np.uint8); offsets = np.ascontiguousarray(offsets, np.int64)
+    rb = capi.ReadBatch(len(offsets) - 1, codes.ctypes.data, offsets.ctypes.data)
+    regs = C.c_void_p(); off = C.c_void_p(); n = C.c_int64(); cells = C.c_int64()
+    L = lib()
+    rc = L.bm2o_seed_chain_extend(C.byref(index.desc), C.byref(opt), C.byref(rb), C.byref(regs), C.byref(n), C.byref(off), C.byref(cells))
+    dt = capi.REG_DT
+    a = np.ctypeslib.as_array(C.cast(regs, C.POINTER(C.c_uint8)), shape=(max(n.value, 1) * dt.itemsize,))[:n.value * dt.itemsize].view(dt).copy()
+    offs = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_int64)), shape=(rb.n_reads + 1,)).copy()
+    L.bm2o_free(regs); L.bm2o_free(off)
+    return a, offs, cells.value, rc
+
+
+REG_CMP_FIELDS = ("rb", "re", "qb", "qe", "rid", "score", "truesc", "sub", "alt_sc", "csub", "sub_n", "w", "seedcov",
+                  "secondary", "secondary_all", "seedlen0", "frac_rep", "hash")
+
+
+def regs_equal_to_dump(regs, off, dump_regs, dump_off):
+    """Compare REG_DT regs (ours) with refdump.REG_DT regs (reference dump). Returns list of differing reads."""
+    bad = []
+    if not np.array_equal(off, dump_off):
+        bad = list(np.nonzero(np.diff(off) != np.diff(dump_off))[0][:20])
+    same = len(regs) == len(dump_regs)
+    if same:
+        ok = np.ones(len(regs), bool)
+        for f in REG_CMP_FIELDS:
+            ok &= regs[f] == dump_regs[f]
+        ok &= ((regs["n_comp_is_alt"] << 2) >> 2) == dump_regs["n_comp"]
+        ok &= ((regs["n_comp_is_alt"] >> 30) & 3) == (dump_regs["is_alt"] & 3)
+        if not ok.all():
+            idx = np.nonzero(~ok)[0]
+            rd = np.searchsorted(off, idx, side="right") - 1
+            bad = sorted(set(bad) | set(rd.tolist()))
+    return bad
