@@ -69,12 +69,13 @@ __global__ void bsw_class_off_kernel(const int32_t *class_cnt, int32_t *class_of
 // ---------------------------------------------------------------------------------------------
 struct SmemPacked {            // H | E<<16 in shared memory, [column][thread]
     uint32_t *base;            // &sh[threadIdx.x]
+    int stride;                // blockDim.x
     __device__ __forceinline__ void get(int j, int &h, int &e) const {
-        uint32_t w = base[j * BSW_THREADS];
+        uint32_t w = base[j * stride];
         h = (int) (w & 0xFFFFu); e = (int) (w >> 16);
     }
-    __device__ __forceinline__ void put(int j, int h, int e) const { base[j * BSW_THREADS] = (uint32_t) h | ((uint32_t) e << 16); }
-    __device__ __forceinline__ bool zero(int j) const { return base[j * BSW_THREADS] == 0u; }
+    __device__ __forceinline__ void put(int j, int h, int e) const { base[j * stride] = (uint32_t) h | ((uint32_t) e << 16); }
+    __device__ __forceinline__ bool zero(int j) const { return base[j * stride] == 0u; }
 };
 
 struct GmemWide {              // {H,E} int32 in global memory, private stripe per thread
@@ -171,11 +172,12 @@ __device__ __forceinline__ void bsw_extend_one(const St &st, const QFetch &qf, c
 
 // query packed 4 bit / base in shared memory words [word][thread]
 struct QSmem4 {
-    const uint32_t *base;      // &sh[(W)*BSW_THREADS + threadIdx.x]
+    const uint32_t *base;      // &sh[W * blockDim.x + threadIdx.x]
+    int stride;
     struct Cursor { uint32_t w; };
-    __device__ __forceinline__ Cursor cursor(int j) const { Cursor c; c.w = base[(j >> 3) * BSW_THREADS] >> ((j & 7) * 4); return c; }
+    __device__ __forceinline__ Cursor cursor(int j) const { Cursor c; c.w = base[(j >> 3) * stride] >> ((j & 7) * 4); return c; }
     __device__ __forceinline__ int next(Cursor &c, int j) const {
-        if ((j & 7) == 0) c.w = base[(j >> 3) * BSW_THREADS];
+        if ((j & 7) == 0) c.w = base[(j >> 3) * stride];
         int b = (int) (c.w & 0xFu);
         c.w >>= 4;
         return b;
@@ -196,15 +198,16 @@ bsw_thread_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ p
 {
     extern __shared__ uint32_t sh[];
     const int first = class_off[cls], last = class_off[cls + 1];
-    const int g = first + blockIdx.x * BSW_THREADS + threadIdx.x;
-    if (first + blockIdx.x * BSW_THREADS >= last) return;
+    const int nthr = blockDim.x;
+    const int g = first + blockIdx.x * nthr + threadIdx.x;
+    if (first + blockIdx.x * nthr >= last) return;
     unsigned long long ncell = 0;
     if (g < last) {
         const int id = perm[g];
         const BswJob job = jobs[id];
         // pack the query, 8 bases per word
         const uint8_t *qp = qbase + job.qoff;
-        uint32_t *qs = sh + W * BSW_THREADS + threadIdx.x;
+        uint32_t *qs = sh + W * nthr + threadIdx.x;
         for (int k = 0; k < job.qlen; k += 8) {
             uint32_t wv = 0;
 #pragma unroll
@@ -214,10 +217,10 @@ bsw_thread_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ p
                 if (b > 4u) b = 4u;
                 wv |= b << (4 * u);
             }
-            qs[(k >> 3) * BSW_THREADS] = wv;
+            qs[(k >> 3) * nthr] = wv;
         }
-        SmemPacked st; st.base = sh + threadIdx.x;
-        QSmem4 qf; qf.base = qs;
+        SmemPacked st; st.base = sh + threadIdx.x; st.stride = nthr;
+        QSmem4 qf; qf.base = qs; qf.stride = nthr;
         BswOut o;
         bsw_extend_one(st, qf, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
         out[id] = o;
@@ -294,18 +297,21 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     BM2_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, idx_in, idx_out, n, 0, 32, stream));
     bsw_class_off_kernel<<<1, 32, 0, stream>>>(class_cnt, class_off);
 
-    const int nblk = (n + BSW_THREADS - 1) / BSW_THREADS;
     for (int c = 0; c < BSW_NCLASS; ++c) {
         int W = h_class_bound[c] + 2;
         int QW = (h_class_bound[c] + 7) / 8;
-        size_t smem = (size_t) (W + QW) * BSW_THREADS * 4;
+        // threads per CTA: as many as fit ~150 KB (>= 1 CTA/SM), capped at BSW_THREADS
+        int nthr = BSW_THREADS;
+        while (nthr > 32 && (size_t) (W + QW) * nthr * 4 > 150 * 1024) nthr >>= 1;
+        const int nblk = (n + nthr - 1) / nthr;
+        size_t smem = (size_t) (W + QW) * nthr * 4;
         static bool attr_set = false;
         if (!attr_set) {   // one function, several dynamic sizes: raise the limit once
             BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr_set = true;
         }
         if (smem > 227 * 1024) { bm2_set_error(ctx_for_error, "bsw: class does not fit shared memory"); return 1; }
-        bsw_thread_kernel<<<nblk, BSW_THREADS, smem, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, W, d_cells);
+        bsw_thread_kernel<<<nblk, nthr, smem, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, W, d_cells);
     }
     if (wide_possible) {
         // the wide class needs its size on the host (rare path): one small sync

@@ -1,0 +1,272 @@
+// chain_device.cuh — seed chaining and chain filtering of ONE read (device logic, one read per thread).
+//
+// Replaces mem_chain_seeds + test_and_merge (reference src/bwamem.cpp:806-974, :357-399),
+// mem_chain_weight (:429-448), mem_chain_flt (:506-624) and bns_intv2rid (src/bntseq.cpp:378-402).
+// The reference's per-read B-tree of chains becomes an index array ordered by chain position inside
+// the read's private stripe of the flat seed arrays; chains hold their seeds as linked lists until
+// the filter has decided which chains survive, then the survivors are written out contiguously.
+#pragma once
+#include "hd.h"
+#include "bm2_b200.h"
+
+struct ContigView { int64_t l_pac; int32_t n_seqs; const int64_t *ann_off; const int32_t *ann_len; const int32_t *ann_alt; };
+
+BM2_HD int64_t bns_depos_d(const ContigView &c, int64_t pos) { return pos >= c.l_pac ? (c.l_pac << 1) - 1 - pos : pos; }
+BM2_HD int bns_pos2rid_d(const ContigView &c, int64_t pos_f) {
+    if (pos_f >= c.l_pac) return -1;
+    int left = 0, mid = 0, right = c.n_seqs;
+    while (left < right) {
+        mid = (left + right) >> 1;
+        if (pos_f >= c.ann_off[mid]) {
+            if (mid == c.n_seqs - 1) break;
+            if (pos_f < c.ann_off[mid + 1]) break;
+            left = mid + 1;
+        } else right = mid;
+    }
+    return mid;
+}
+BM2_HD int bns_intv2rid_d(const ContigView &c, int64_t rb, int64_t re) {
+    if (rb < c.l_pac && re > c.l_pac) return -2;
+    int rid_b = bns_pos2rid_d(c, bns_depos_d(c, rb));
+    int rid_e = rb < re ? bns_pos2rid_d(c, bns_depos_d(c, re - 1)) : rid_b;
+    return rid_b == rid_e ? rid_b : -1;
+}
+
+// ks_introsort (src/ksort.h:185-232) restated over an index array: identical comparison/swap
+// sequence, hence the identical order among ties.  lt(i, j) compares ELEMENTS i and j.
+template <class T, class LT> BM2_HD void ks_insertsort_d(T *a, long s, long t, LT &lt) {
+    for (long i = s + 1; i < t; ++i)
+        for (long j = i; j > s && lt(a[j], a[j - 1]); --j) bm2_swap(a[j], a[j - 1]);
+}
+template <class T, class LT> BM2_HD void ks_combsort_d(T *a, long n, LT &lt) {
+    const double shrink = 1.2473309501039786540366528676643;
+    long gap = n; bool swapped;
+    do {
+        if (gap > 2) { gap = (long) (gap / shrink); if (gap == 9 || gap == 10) gap = 11; }
+        swapped = false;
+        for (long i = 0; i + gap < n; ++i) if (lt(a[i + gap], a[i])) { bm2_swap(a[i], a[i + gap]); swapped = true; }
+    } while (swapped || gap > 2);
+    if (gap != 1) ks_insertsort_d(a, 0, n, lt);
+}
+template <class T, class LT> BM2_HD void ks_introsort_d(T *a, long n, LT lt) {
+    if (n < 1) return;
+    if (n == 2) { if (lt(a[1], a[0])) bm2_swap(a[0], a[1]); return; }
+    int d; for (d = 2; (1ul << d) < (unsigned long) n; ++d) {}
+    long st_l[72], st_r[72]; int st_d[72]; int top = 0;
+    long s = 0, t = n - 1; d <<= 1;
+    for (;;) {
+        if (s < t) {
+            if (--d == 0) { ks_combsort_d(a + s, t - s + 1, lt); t = s; continue; }
+            long i = s, j = t, k = i + ((j - i) >> 1) + 1;
+            if (lt(a[k], a[i])) { if (lt(a[k], a[j])) k = j; }
+            else k = lt(a[j], a[i]) ? i : j;
+            T rp = a[k];
+            if (k != t) bm2_swap(a[k], a[t]);
+            for (;;) {
+                do ++i; while (lt(a[i], rp));
+                do --j; while (i <= j && lt(rp, a[j]));
+                if (j <= i) break;
+                bm2_swap(a[i], a[j]);
+            }
+            bm2_swap(a[i], a[t]);
+            if (i - s > t - i) {
+                if (i - s > 16) { st_l[top] = s; st_r[top] = i - 1; st_d[top] = d; ++top; }
+                s = t - i > 16 ? i + 1 : t;
+            } else {
+                if (t - i > 16) { st_l[top] = i + 1; st_r[top] = t; st_d[top] = d; ++top; }
+                t = i - s > 16 ? i - 1 : s;
+            }
+        } else {
+            if (top == 0) { ks_insertsort_d(a, 0, n, lt); return; }
+            --top; s = st_l[top]; t = st_r[top]; d = st_d[top];
+        }
+    }
+}
+
+struct ChainParams {
+    int w, max_chain_gap, max_occ, min_chain_weight, max_chain_extend, min_seed_len;
+    float mask_level, drop_ratio;
+};
+
+// working records inside the read's stripe
+struct WSeed { int64_t rbeg; int32_t qbeg, len, next; int32_t _pad; };
+struct WChain {
+    int64_t pos;
+    int64_t first_rbeg, last_rbeg;
+    int32_t first_qbeg, last_qbeg, last_len;
+    int32_t head, tail, n;          // linked list of WSeed
+    int32_t rid, is_alt;
+    int32_t w, kept, first;
+};
+
+struct ChainStripe {               // all arrays have >= n_slots entries, private to the read
+    WSeed *seeds;
+    WChain *chains;
+    int32_t *ord;                  // chain ids ordered by pos (the B-tree's in-order sequence)
+    int32_t *srt;                  // filter: chain ids sorted by weight
+    int32_t *kv;                   // filter: kept non-overlapping chains
+};
+
+// test_and_merge (src/bwamem.cpp:357-399) on the cached first/last seed of the chain
+BM2_HD bool chain_test_and_merge(const ChainParams &p, int64_t l_pac, WChain &c, WSeed *seeds, int seed_id, int seed_rid) {
+    const WSeed &s = seeds[seed_id];
+    const int64_t qend = c.last_qbeg + c.last_len, rend = c.last_rbeg + c.last_len;
+    if (seed_rid != c.rid) return false;
+    if (s.qbeg >= c.first_qbeg && s.qbeg + s.len <= qend && s.rbeg >= c.first_rbeg && s.rbeg + s.len <= rend) return true;
+    if ((c.last_rbeg < l_pac || c.first_rbeg < l_pac) && s.rbeg >= l_pac) return false;
+    const int64_t x = s.qbeg - c.last_qbeg, y = s.rbeg - c.last_rbeg;
+    if (y >= 0 && x - y <= p.w && y - x <= p.w && x - c.last_len < p.max_chain_gap && y - c.last_len < p.max_chain_gap) {
+        seeds[c.tail].next = seed_id; c.tail = seed_id; ++c.n;
+        c.last_qbeg = s.qbeg; c.last_rbeg = s.rbeg; c.last_len = s.len;
+        return true;
+    }
+    return false;
+}
+
+BM2_HD int chain_weight_d(const WChain &c, const WSeed *seeds) {
+    int64_t end = 0; int w = 0, tmp;
+    for (int i = c.head, k = 0; k < c.n; ++k, i = seeds[i].next) {
+        const WSeed &s = seeds[i];
+        if (s.qbeg >= end) w += s.len; else if (s.qbeg + s.len > end) w += (int) (s.qbeg + s.len - end);
+        end = end > s.qbeg + s.len ? end : s.qbeg + s.len;
+    }
+    tmp = w; w = 0; end = 0;
+    for (int i = c.head, k = 0; k < c.n; ++k, i = seeds[i].next) {
+        const WSeed &s = seeds[i];
+        if (s.rbeg >= end) w += s.len; else if (s.rbeg + s.len > end) w += (int) (s.rbeg + s.len - end);
+        end = end > s.rbeg + s.len ? end : s.rbeg + s.len;
+    }
+    w = w < tmp ? w : tmp;
+    return w < (1 << 30) ? w : (1 << 30) - 1;
+}
+
+// Chains of one read.  smems[0..n_smem) ordered (m asc, n asc); sa[] holds, SMEM after SMEM, the
+// reference positions of its sampled rows (count = min(s, max_occ)).  On return srt[0..n_kept) lists
+// the surviving chains in the reference's output order (weight-sorted, kept != 0); returns n_kept.
+// *frac_rep receives l_rep / l_seq.
+BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_smem *smems, int n_smem, const int64_t *sa,
+                        int l_seq, ChainStripe &ws, float *frac_rep)
+{
+    int b = 0, e = 0, l_rep = 0;
+    for (int i = 0; i < n_smem; ++i) {
+        const int sb = (int) smems[i].m, se = (int) smems[i].n + 1;
+        if (smems[i].s <= p.max_occ) continue;
+        if (sb > e) { l_rep += e - b; b = sb; e = se; }
+        else e = e > se ? e : se;
+    }
+    l_rep += e - b;
+    *frac_rep = (float) l_rep / l_seq;
+
+    int n_ch = 0, n_sd = 0;
+    int64_t slot = 0;
+    for (int i = 0; i < n_smem; ++i) {
+        const bm2_smem &sm = smems[i];
+        const int slen = (int) sm.n + 1 - (int) sm.m;
+        const int64_t cnt = sm.s < p.max_occ ? sm.s : p.max_occ;
+        for (int64_t t = 0; t < cnt; ++t, ++slot) {
+            const int64_t rbeg = sa[slot];
+            const int rid = bns_intv2rid_d(cv, rbeg, rbeg + slen);
+            if (rid < 0) continue;
+            const int sid = n_sd;
+            WSeed &s = ws.seeds[sid]; s.rbeg = rbeg; s.qbeg = (int) sm.m; s.len = slen; s.next = -1; s._pad = 0;
+            int lower = -1;
+            if (n_ch) {
+                int lo = 0, hi = n_ch;            // first chain with pos >= rbeg
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (ws.chains[ws.ord[mid]].pos < rbeg) lo = mid + 1; else hi = mid; }
+                lower = (lo < n_ch && ws.chains[ws.ord[lo]].pos == rbeg) ? lo : lo - 1;
+                if (lower >= 0) {
+                    WChain &lc = ws.chains[ws.ord[lower]];
+                    if (chain_test_and_merge(p, cv.l_pac, lc, ws.seeds, sid, rid)) {
+                        if (lc.tail == sid) ++n_sd;      // appended: keeps its slot; contained: slot is reused
+                        continue;
+                    }
+                }
+            }
+            ++n_sd;
+            WChain &c = ws.chains[n_ch];
+            c.pos = rbeg; c.first_rbeg = c.last_rbeg = rbeg; c.first_qbeg = c.last_qbeg = s.qbeg; c.last_len = slen;
+            c.head = c.tail = sid; c.n = 1; c.rid = rid; c.is_alt = cv.ann_alt ? (cv.ann_alt[rid] != 0) : 0;
+            c.w = 0; c.kept = 0; c.first = -1;
+            for (int k = n_ch; k > lower + 1; --k) ws.ord[k] = ws.ord[k - 1];
+            ws.ord[lower + 1] = n_ch;
+            ++n_ch;
+        }
+    }
+    if (n_ch == 0) return 0;
+
+    // ---- mem_chain_flt (src/bwamem.cpp:506-624) -------------------------------------------------------------
+    int n = 0;
+    for (int i = 0; i < n_ch; ++i) {
+        WChain &c = ws.chains[ws.ord[i]];
+        c.first = -1; c.kept = 0; c.w = chain_weight_d(c, ws.seeds);
+        if (c.w >= p.min_chain_weight) ws.srt[n++] = ws.ord[i];
+    }
+    if (n == 0) ws.srt[n++] = ws.ord[0];     // reference quirk: range (0,1) is processed even when all were dropped
+    {
+        const WChain *chs = ws.chains;
+        ks_introsort_d(ws.srt, (long) n, [chs](int x, int y) { return chs[x].w > chs[y].w; });
+    }
+#define CHN_BEG(c) ((c).first_qbeg)
+#define CHN_END(c) ((c).last_qbeg + (c).last_len)
+    int n_kv = 0;
+    ws.chains[ws.srt[0]].kept = 3; ws.kv[n_kv++] = 0;
+    for (int i = 1; i < n; ++i) {
+        WChain &ai = ws.chains[ws.srt[i]];
+        int large_ovlp = 0, k;
+        for (k = 0; k < n_kv; ++k) {
+            const int j = ws.kv[k];
+            WChain &aj = ws.chains[ws.srt[j]];
+            const int b_max = CHN_BEG(aj) > CHN_BEG(ai) ? CHN_BEG(aj) : CHN_BEG(ai);
+            const int e_min = CHN_END(aj) < CHN_END(ai) ? CHN_END(aj) : CHN_END(ai);
+            if (e_min > b_max && (!aj.is_alt || ai.is_alt)) {
+                const int li = CHN_END(ai) - CHN_BEG(ai), lj = CHN_END(aj) - CHN_BEG(aj);
+                const int min_l = li < lj ? li : lj;
+                if ((float) (e_min - b_max) >= (float) min_l * p.mask_level && min_l < p.max_chain_gap) {
+                    large_ovlp = 1;
+                    if (aj.first < 0) aj.first = i;
+                    if ((float) ai.w < (float) aj.w * p.drop_ratio && aj.w - ai.w >= p.min_seed_len << 1) break;
+                }
+            }
+        }
+        if (k == n_kv) { ws.kv[n_kv++] = i; ai.kept = large_ovlp ? 2 : 3; }
+    }
+#undef CHN_BEG
+#undef CHN_END
+    for (int k = 0; k < n_kv; ++k) {
+        const WChain &c = ws.chains[ws.srt[ws.kv[k]]];
+        if (c.first >= 0) ws.chains[ws.srt[c.first]].kept = 1;
+    }
+    int i, k;
+    for (i = k = 0; i < n; ++i) {
+        const int kept = ws.chains[ws.srt[i]].kept;
+        if (kept == 0 || kept == 3) continue;
+        if (++k >= p.max_chain_extend) break;
+    }
+    for (; i < n; ++i) if (ws.chains[ws.srt[i]].kept < 3) ws.chains[ws.srt[i]].kept = 0;
+    int n_kept = 0;
+    for (i = 0; i < n; ++i) if (ws.chains[ws.srt[i]].kept) ws.srt[n_kept++] = ws.srt[i];
+    return n_kept;
+}
+
+// Writes the surviving chains of one read contiguously (reference order) and counts the extension
+// work they imply: one reg per seed, a left job iff qbeg > 0, a right job iff the seed does not
+// reach the read end (src/bwamem.cpp:2229, :2324).
+BM2_HD void chain_finalize_d(const ChainStripe &ws, int n_kept, float frac_rep, int seqid, int l_seq, bm2_chain *out_chain,
+                             bm2_seed *out_seed, int *n_seed_out, int *n_left, int *n_right)
+{
+    int ns = 0, nl = 0, nr = 0;
+    for (int k = 0; k < n_kept; ++k) {
+        const WChain &c = ws.chains[ws.srt[k]];
+        bm2_chain &o = out_chain[k];
+        o.pos = c.pos; o.seqid = seqid; o.rid = c.rid; o.n_seeds = c.n; o.seed_off = ns;
+        o.w = c.w; o.kept = c.kept; o.first = c.first; o.is_alt = c.is_alt; o.frac_rep = frac_rep; o._pad = 0;
+        for (int i = c.head, t = 0; t < c.n; ++t, i = ws.seeds[i].next) {
+            const WSeed &s = ws.seeds[i];
+            bm2_seed &d = out_seed[ns++];
+            d.rbeg = s.rbeg; d.qbeg = s.qbeg; d.len = s.len; d.score = s.len; d.chain = k;
+            if (s.qbeg) ++nl;
+            if (s.qbeg + s.len != l_seq) ++nr;
+        }
+    }
+    *n_seed_out = ns; *n_left = nl; *n_right = nr;
+}

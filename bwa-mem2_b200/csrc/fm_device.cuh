@@ -1,0 +1,220 @@
+// fm_device.cuh — FM-index search over the 2bit.64 Occ table (device logic, one read per thread).
+//
+// Replaces FMI_search::backwardExt (reference src/FMI_search.cpp:1025-1052), the three SMEM passes
+// getSMEMsAllPosOneThread / getSMEMsOnePosOneThread / bwtSeedStrategyAllPosOneThread
+// (src/FMI_search.cpp:496-812) as orchestrated by mem_collect_smem (src/bwamem.cpp:626-804), and
+// the compressed-SA walk call_one_step (src/FMI_search.cpp:1202-1255).
+//
+// GPU shape: the search of one read is a chain of ~600 dependent interval extensions, each touching
+// two random 64-byte checkpoints of a multi-GB table, so it is HBM-latency/sector bound.  One read
+// per thread; the whole three-pass search is ONE state machine with a SINGLE extension call site, so
+// the 32 lanes of a warp stay converged at the two checkpoint loads no matter which pass / direction
+// each lane is in (a straight port of the nested loops would serialise the lanes).
+#pragma once
+#include "hd.h"
+#include "bm2_b200.h"
+
+struct FmIndexView {
+    const bm2_cp_occ *cp_occ;
+    const int8_t *sa_ms;
+    const uint32_t *sa_ls;
+    int64_t count[5];
+    int64_t sentinel;
+};
+
+struct FmIv { int64_t k, l, s; };
+
+struct FmOcc4 { int64_t c[4]; };
+
+// Occ(b, pp) for the four bases from one 64-byte checkpoint (GET_OCC, src/FMI_search.h:66-73).
+BM2_HD FmOcc4 fm_occ4(const FmIndexView &fm, int64_t pp) {
+    const bm2_cp_occ *e = fm.cp_occ + (pp >> 6);
+    FmOcc4 r;
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(e);
+    ulonglong2 c01 = __ldg(p), c23 = __ldg(p + 1), b01 = __ldg(p + 2), b23 = __ldg(p + 3);
+    uint64_t cnt[4] = {c01.x, c01.y, c23.x, c23.y}, bits[4] = {b01.x, b01.y, b23.x, b23.y};
+#else
+    uint64_t cnt[4], bits[4];
+    for (int b = 0; b < 4; ++b) { cnt[b] = (uint64_t) e->cp_count[b]; bits[b] = e->one_hot_bwt_str[b]; }
+#endif
+    const int y = (int) (pp & 63);
+    const uint64_t mask = y ? ~0ULL << (64 - y) : 0ULL;      // top y bits (src/FMI_search.cpp:386-394)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) r.c[b] = (int64_t) cnt[b] + BM2_POPC64(bits[b] & mask);
+    return r;
+}
+
+// backwardExt (src/FMI_search.cpp:1025-1052): 2 checkpoints = 128 algorithmic bytes.
+BM2_HD FmIv fm_backward_ext(const FmIndexView &fm, const FmIv &in, int a) {
+    FmOcc4 o1 = fm_occ4(fm, in.k), o2 = fm_occ4(fm, in.k + in.s);
+    int64_t s0 = o2.c[0] - o1.c[0], s1 = o2.c[1] - o1.c[1], s2 = o2.c[2] - o1.c[2], s3 = o2.c[3] - o1.c[3];
+    int64_t l3 = in.l + ((in.k <= fm.sentinel && in.k + in.s > fm.sentinel) ? 1 : 0);
+    int64_t l2 = l3 + s3, l1 = l2 + s2, l0 = l1 + s1;
+    FmIv r;
+    r.k = fm.count[a] + o1.c[a];
+    r.l = a == 0 ? l0 : a == 1 ? l1 : a == 2 ? l2 : l3;
+    r.s = a == 0 ? s0 : a == 1 ? s1 : a == 2 ? s2 : s3;
+    return r;
+}
+
+// SA of one BWT row: LF-walk to a sampled row (call_one_step; returns 0 on the sentinel, :1230-1233)
+BM2_HD int64_t fm_sa_of_row(const FmIndexView &fm, int64_t r, int *lf_steps) {
+    int64_t steps = 0;
+    while (r & 7) {
+        const bm2_cp_occ *e = fm.cp_occ + (r >> 6);
+        const int y = 63 - (int) (r & 63);
+#if defined(__CUDA_ARCH__)
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(e);
+        ulonglong2 c01 = __ldg(p), c23 = __ldg(p + 1), b01 = __ldg(p + 2), b23 = __ldg(p + 3);
+        uint64_t cnt[4] = {c01.x, c01.y, c23.x, c23.y}, bits[4] = {b01.x, b01.y, b23.x, b23.y};
+#else
+        uint64_t cnt[4], bits[4];
+        for (int b = 0; b < 4; ++b) { cnt[b] = (uint64_t) e->cp_count[b]; bits[b] = e->one_hot_bwt_str[b]; }
+#endif
+        int b = ((bits[0] >> y) & 1) ? 0 : ((bits[1] >> y) & 1) ? 1 : ((bits[2] >> y) & 1) ? 2 : ((bits[3] >> y) & 1) ? 3 : 4;
+        if (b == 4) { if (lf_steps) *lf_steps += (int) steps; return 0; }
+        const int yy = (int) (r & 63);
+        const uint64_t mask = yy ? ~0ULL << (64 - yy) : 0ULL;
+        uint64_t cb = b == 0 ? cnt[0] : b == 1 ? cnt[1] : b == 2 ? cnt[2] : cnt[3];
+        uint64_t bb = b == 0 ? bits[0] : b == 1 ? bits[1] : b == 2 ? bits[2] : bits[3];
+        r = fm.count[b] + (int64_t) cb + BM2_POPC64(bb & mask);
+        ++steps;
+    }
+    if (lf_steps) *lf_steps += (int) steps;
+#if defined(__CUDA_ARCH__)
+    int64_t sa = ((int64_t) __ldg(fm.sa_ms + (r >> 3)) << 32) + (int64_t) __ldg(fm.sa_ls + (r >> 3));
+#else
+    int64_t sa = ((int64_t) fm.sa_ms[r >> 3] << 32) + (int64_t) fm.sa_ls[r >> 3];
+#endif
+    return sa + steps;
+}
+
+// One entry of the per-read interval list of the SMEM search (prevArray, src/FMI_search.cpp:510).
+struct FmPrev { int64_t k, l, s; int32_t m, n; };
+
+struct SmemParams {
+    int min_seed_len;        // opt->min_seed_len
+    int split_len;           // (int)(min_seed_len * split_factor + .499)   (src/bwamem.cpp:640)
+    int split_width;         // opt->split_width
+    int max_mem_intv;        // opt->max_mem_intv (0 disables pass 3)
+};
+
+// The three-pass SMEM search of ONE read as a state machine with a single extension call site.
+//   q[0..len): base codes;  prev: scratch of >= len+1 entries;  reseed: scratch of >= len int2-like
+//   entries (x, min_intv) for pass 2;  emit(m, n, k, l, s) appends one SMEM (any order: the caller
+//   sorts by (rid, m, n) afterwards, as sortSMEMs + the per-read introsort do);
+//   n_ext counts extensions (128 algorithmic bytes each).
+template <class Emit>
+BM2_HD void fm_smem_read(const FmIndexView &fm, const uint8_t *q, int len, const SmemParams &sp, FmPrev *prev,
+                         int32_t *reseed, Emit &emit, unsigned &n_ext)
+{
+    enum { ST_SEARCH_BEGIN, ST_FWD, ST_FWD_END, ST_BWD_ROW, ST_BWD_ITEM, ST_SEARCH_END, ST_P3_BEGIN, ST_P3_FWD, ST_DONE };
+    if (len <= 0) return;
+    int pass = 1;
+    int x = 0, min_intv = 1, next_x = 0, j = 0, num_prev = 0, num_curr = 0, p = 0, curr_s = -1;
+    bool first_phase = true;
+    int n_reseed = 0, i_reseed = 0;
+    FmPrev cur; cur.k = cur.l = cur.s = 0; cur.m = cur.n = 0;
+    int st = ST_SEARCH_BEGIN;
+    for (;;) {
+        // ---- run the control automaton until it needs one interval extension -----------------------
+        FmIv req; int req_base = 0; bool req_fwd = false;
+        bool need = false;
+        while (!need) {
+            if (st == ST_SEARCH_BEGIN) {
+                // getSMEMsOnePosOneThread entry (src/FMI_search.cpp:513-533)
+                next_x = x + 1;
+                const int a = q[x];
+                if (a > 3) { st = ST_SEARCH_END; num_prev = 0; continue; }
+                cur.m = x; cur.n = x; cur.k = fm.count[a]; cur.l = fm.count[3 - a]; cur.s = fm.count[a + 1] - fm.count[a];
+                num_prev = 0; j = x + 1; st = ST_FWD;
+            } else if (st == ST_FWD) {
+                if (j >= len) { st = ST_FWD_END; continue; }
+                next_x = j + 1;
+                const int a = q[j];
+                if (a > 3) { st = ST_FWD_END; continue; }
+                req.k = cur.l; req.l = cur.k; req.s = cur.s; req_base = 3 - a; req_fwd = true; need = true;
+            } else if (st == ST_FWD_END) {
+                if (cur.s >= min_intv) prev[num_prev++] = cur;
+                for (int a = 0, b = num_prev - 1; a < b; ++a, --b) { FmPrev t = prev[a]; prev[a] = prev[b]; prev[b] = t; }
+                j = x - 1; st = ST_BWD_ROW;
+            } else if (st == ST_BWD_ROW) {
+                if (j < 0 || q[j] > 3 || num_prev == 0) { st = ST_SEARCH_END; continue; }
+                num_curr = 0; curr_s = -1; p = 0; first_phase = true; st = ST_BWD_ITEM;
+            } else if (st == ST_BWD_ITEM) {
+                if (p >= num_prev) { num_prev = num_curr; if (num_curr == 0) { st = ST_SEARCH_END; continue; } --j; st = ST_BWD_ROW; continue; }
+                req.k = prev[p].k; req.l = prev[p].l; req.s = prev[p].s; req_base = q[j]; req_fwd = false; need = true;
+            } else if (st == ST_SEARCH_END) {
+                // tail of one search (src/FMI_search.cpp:656-667), then the pass drivers
+                if (num_prev != 0) {
+                    const FmPrev &s0 = prev[0];
+                    if (s0.n - s0.m + 1 >= sp.min_seed_len) {
+                        emit(s0.m, s0.n, s0.k, s0.l, s0.s);
+                        if (pass == 1 && s0.n + 1 - s0.m >= sp.split_len && s0.s <= sp.split_width) {
+                            reseed[2 * n_reseed] = (s0.n + 1 + s0.m) >> 1; reseed[2 * n_reseed + 1] = (int32_t) (s0.s + 1); ++n_reseed;
+                        }
+                    }
+                    num_prev = 0;
+                }
+                if (pass == 1) {            // getSMEMsAllPosOneThread (src/FMI_search.cpp:672-724)
+                    x = next_x;
+                    if (x < len) { min_intv = 1; st = ST_SEARCH_BEGIN; continue; }
+                    pass = 2; i_reseed = 0;
+                }
+                if (pass == 2) {            // re-seeding (src/bwamem.cpp:695-753)
+                    if (i_reseed < n_reseed) { x = reseed[2 * i_reseed]; min_intv = reseed[2 * i_reseed + 1]; ++i_reseed; st = ST_SEARCH_BEGIN; continue; }
+                    pass = 3; x = 0;
+                    if (sp.max_mem_intv <= 0) { st = ST_DONE; continue; }
+                    st = ST_P3_BEGIN;
+                }
+            } else if (st == ST_P3_BEGIN) {   // bwtSeedStrategyAllPosOneThread (src/FMI_search.cpp:726-812)
+                if (x >= len) { st = ST_DONE; continue; }
+                next_x = x + 1;
+                const int a = q[x];
+                if (a > 3) { x = next_x; continue; }
+                cur.m = x; cur.n = x; cur.k = fm.count[a]; cur.l = fm.count[3 - a]; cur.s = fm.count[a + 1] - fm.count[a];
+                j = x + 1; st = ST_P3_FWD;
+            } else if (st == ST_P3_FWD) {
+                if (j >= len) { x = next_x; st = ST_P3_BEGIN; continue; }
+                next_x = j + 1;
+                const int a = q[j];
+                if (a > 3) { x = next_x; st = ST_P3_BEGIN; continue; }
+                req.k = cur.l; req.l = cur.k; req.s = cur.s; req_base = 3 - a; req_fwd = true; need = true;
+            } else {  // ST_DONE
+                return;
+            }
+        }
+        // ---- the single extension call site -----------------------------------------------------------
+        FmIv r = fm_backward_ext(fm, req, req_base);
+        ++n_ext;
+        if (req_fwd) { int64_t t = r.k; r.k = r.l; r.l = t; }
+        // ---- consume the result ---------------------------------------------------------------------------
+        if (st == ST_FWD) {
+            if (r.s != cur.s) prev[num_prev++] = cur;
+            if (r.s < min_intv) { next_x = j; st = ST_FWD_END; }
+            else { cur.k = r.k; cur.l = r.l; cur.s = r.s; cur.n = j; ++j; }
+        } else if (st == ST_BWD_ITEM) {
+            const FmPrev old = prev[p];
+            if (first_phase && r.s < min_intv && old.n - old.m + 1 >= sp.min_seed_len) {
+                emit(old.m, old.n, old.k, old.l, old.s);
+                if (pass == 1 && old.n + 1 - old.m >= sp.split_len && old.s <= sp.split_width) {
+                    reseed[2 * n_reseed] = (old.n + 1 + old.m) >> 1; reseed[2 * n_reseed + 1] = (int32_t) (old.s + 1); ++n_reseed;
+                }
+                first_phase = false;
+            } else if (r.s >= min_intv && r.s != curr_s) {
+                curr_s = (int) r.s;
+                FmPrev t; t.k = r.k; t.l = r.l; t.s = r.s; t.m = j; t.n = old.n;
+                prev[num_curr++] = t;
+                first_phase = false;
+            }
+            ++p;
+        } else {  // ST_P3_FWD
+            cur.k = r.k; cur.l = r.l; cur.s = r.s; cur.n = j;
+            if (cur.s < sp.max_mem_intv && cur.n - cur.m + 1 >= sp.min_seed_len + 1) {
+                if (cur.s > 0) emit(cur.m, cur.n, cur.k, cur.l, cur.s);
+                x = next_x; st = ST_P3_BEGIN;
+            } else ++j;
+        }
+    }
+}

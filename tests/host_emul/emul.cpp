@@ -1,0 +1,192 @@
+// emul.cpp — TEST-ONLY host emulation of the seam-2 GPU pipeline.
+//
+// Compiles the per-thread device logic of bwa-mem2_b200/csrc/{fm,chain,ext}_device.cuh with g++ and
+// runs it read after read with the SAME flat data layout and stage order as pipeline.cu, so that the
+// kernels' control logic can be checked against the oracle on a machine without a GPU.  The banded
+// extension DP itself is NOT emulated here (its CUDA kernel is checked on the GPU by
+// tests/test_bsw_gpu.py); this harness calls the oracle's DP for that step.  Never part of the product.
+#include <vector>
+#include <algorithm>
+#include <cstring>
+#include <cstdlib>
+#include <cmath>
+#include "fm_device.cuh"
+#include "chain_device.cuh"
+#include "ext_device.cuh"
+#include "../../oracle/bm2_oracle.h"
+
+namespace {
+struct Views { FmIndexView fm; ContigView cv; SmemParams sp; ChainParams cp; ExtParams ep; };
+
+Views make_views(const bm2_index_desc *idx, const bm2_mem_opt_t *o) {
+    Views v;
+    v.fm.cp_occ = idx->cp_occ; v.fm.sa_ms = idx->sa_ms_byte; v.fm.sa_ls = idx->sa_ls_word; v.fm.sentinel = idx->sentinel_index;
+    for (int i = 0; i < 5; ++i) v.fm.count[i] = idx->count[i];
+    v.cv.l_pac = idx->l_pac; v.cv.n_seqs = idx->n_seqs; v.cv.ann_off = idx->ann_offset; v.cv.ann_len = idx->ann_len; v.cv.ann_alt = idx->ann_is_alt;
+    v.sp.min_seed_len = o->min_seed_len; v.sp.split_len = (int) (o->min_seed_len * o->split_factor + .499);
+    v.sp.split_width = o->split_width; v.sp.max_mem_intv = (int) o->max_mem_intv;
+    v.cp.w = o->w; v.cp.max_chain_gap = o->max_chain_gap; v.cp.max_occ = o->max_occ; v.cp.min_chain_weight = o->min_chain_weight;
+    v.cp.max_chain_extend = o->max_chain_extend; v.cp.min_seed_len = o->min_seed_len; v.cp.mask_level = o->mask_level; v.cp.drop_ratio = o->drop_ratio;
+    v.ep.a = o->a; v.ep.b = o->b; v.ep.o_del = o->o_del; v.ep.e_del = o->e_del; v.ep.o_ins = o->o_ins; v.ep.e_ins = o->e_ins; v.ep.w = o->w;
+    v.ep.pen_clip5 = o->pen_clip5; v.ep.pen_clip3 = o->pen_clip3; v.ep.max_chain_gap = o->max_chain_gap; v.ep.mask_level_redun = o->mask_level_redun;
+    memcpy(v.ep.mat, o->mat, 25);
+    return v;
+}
+
+struct Stage1 {      // sorted SMEMs + per-read ranges + SA of every seed slot
+    std::vector<bm2_smem> smems; std::vector<int64_t> read_smem_off; std::vector<int64_t> slot_off; std::vector<int64_t> sa;
+    int64_t n_ext = 0, n_lf = 0;
+};
+
+void stage_smem_sa(const Views &v, const bm2_mem_opt_t *o, const bm2_read_batch *rb, Stage1 &s) {
+    int max_len = 0;
+    for (int r = 0; r < rb->n_reads; ++r) max_len = std::max<int>(max_len, (int) (rb->offsets[r + 1] - rb->offsets[r]));
+    std::vector<FmPrev> prev(max_len + 2); std::vector<int32_t> reseed(2 * max_len + 2);
+    for (int r = 0; r < rb->n_reads; ++r) {
+        const uint8_t *q = rb->codes + rb->offsets[r]; int len = (int) (rb->offsets[r + 1] - rb->offsets[r]);
+        unsigned n_ext = 0;
+        auto emit = [&](int m, int n, int64_t k, int64_t l, int64_t ss) {
+            bm2_smem x; x.rid = r; x.m = m; x.n = n; x.k = k; x.l = l; x.s = ss; s.smems.push_back(x);
+        };
+        fm_smem_read(v.fm, q, len, v.sp, prev.data(), reseed.data(), emit, n_ext);
+        s.n_ext += n_ext;
+    }
+    std::stable_sort(s.smems.begin(), s.smems.end(), [](const bm2_smem &a, const bm2_smem &b) {
+        uint64_t ka = (uint64_t) a.rid << 32 | (uint64_t) a.m << 16 | a.n, kb = (uint64_t) b.rid << 32 | (uint64_t) b.m << 16 | b.n;
+        return ka < kb;
+    });
+    s.read_smem_off.assign(rb->n_reads + 1, 0);
+    for (auto &x : s.smems) s.read_smem_off[x.rid + 1]++;
+    for (int r = 0; r < rb->n_reads; ++r) s.read_smem_off[r + 1] += s.read_smem_off[r];
+    s.slot_off.assign(s.smems.size() + 1, 0);
+    for (size_t i = 0; i < s.smems.size(); ++i) s.slot_off[i + 1] = s.slot_off[i] + std::min<int64_t>(s.smems[i].s, o->max_occ);
+    s.sa.resize(s.slot_off.back());
+    for (size_t i = 0; i < s.smems.size(); ++i) {
+        const bm2_smem &x = s.smems[i];
+        int64_t step = x.s > o->max_occ ? x.s / o->max_occ : 1;
+        for (int64_t t = 0; t < s.slot_off[i + 1] - s.slot_off[i]; ++t) { int lf = 0; s.sa[s.slot_off[i] + t] = fm_sa_of_row(v.fm, x.k + t * step, &lf); s.n_lf += lf; }
+    }
+}
+
+struct Stage2 {      // finalized chains per read (flat, per-read stripes compacted here)
+    std::vector<bm2_chain> chains; std::vector<bm2_seed> seeds; std::vector<int64_t> read_chain_off;
+    std::vector<int> n_left, n_right;
+};
+
+void stage_chain(const Views &v, const bm2_read_batch *rb, const Stage1 &s1, Stage2 &s2) {
+    s2.read_chain_off.assign(rb->n_reads + 1, 0); s2.n_left.assign(rb->n_reads, 0); s2.n_right.assign(rb->n_reads, 0);
+    for (int r = 0; r < rb->n_reads; ++r) {
+        int len = (int) (rb->offsets[r + 1] - rb->offsets[r]);
+        int64_t sb = s1.read_smem_off[r], se = s1.read_smem_off[r + 1];
+        // reference quirk: a 512-read block with exactly one SMEM yields no chain (src/bwamem.cpp:835)
+        int b0 = (r / 512) * 512, b1 = std::min(rb->n_reads, b0 + 512);
+        bool skip = (s1.read_smem_off[b1] - s1.read_smem_off[b0]) <= 1;
+        if (se > sb && !skip && len >= v.sp.min_seed_len) {
+            int64_t slots = s1.slot_off[se] - s1.slot_off[sb];
+            std::vector<WSeed> ws(slots + 1); std::vector<WChain> wc(slots + 1); std::vector<int32_t> ord(slots + 1), srt(slots + 1), kv(slots + 1);
+            ChainStripe st = { ws.data(), wc.data(), ord.data(), srt.data(), kv.data() };
+            float frac = 0;
+            int nk = chain_read_d(v.cv, v.cp, s1.smems.data() + sb, (int) (se - sb), s1.sa.data() + s1.slot_off[sb], len, st, &frac);
+            std::vector<bm2_chain> oc(nk + 1); std::vector<bm2_seed> os(slots + 1);
+            int ns = 0, nl = 0, nr = 0;
+            chain_finalize_d(st, nk, frac, r, len, oc.data(), os.data(), &ns, &nl, &nr);
+            int64_t seed_base = (int64_t) s2.seeds.size();
+            for (int k = 0; k < nk; ++k) { oc[k].seed_off += (int32_t) seed_base; s2.chains.push_back(oc[k]); }
+            for (int k = 0; k < ns; ++k) { os[k].chain += (int32_t) s2.read_chain_off[r]; s2.seeds.push_back(os[k]); }
+            s2.n_left[r] = nl; s2.n_right[r] = nr;
+        }
+        s2.read_chain_off[r + 1] = (int64_t) s2.chains.size();
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int64_t emul_collect_smems(const bm2_index_desc *idx, const bm2_mem_opt_t *o, const bm2_read_batch *rb, bm2_smem **out, int64_t *n_ext) {
+    Views v = make_views(idx, o); Stage1 s1; stage_smem_sa(v, o, rb, s1);
+    *out = (bm2_smem *) malloc(sizeof(bm2_smem) * (s1.smems.size() + 1));
+    memcpy(*out, s1.smems.data(), sizeof(bm2_smem) * s1.smems.size());
+    if (n_ext) *n_ext = s1.n_ext;
+    return (int64_t) s1.smems.size();
+}
+
+int emul_seed_chain(const bm2_index_desc *idx, const bm2_mem_opt_t *o, const bm2_read_batch *rb, bm2_chain **chains, int64_t *n_chains,
+                    bm2_seed **seeds, int64_t *n_seeds, int64_t **read_off) {
+    Views v = make_views(idx, o); Stage1 s1; stage_smem_sa(v, o, rb, s1); Stage2 s2; stage_chain(v, rb, s1, s2);
+    *chains = (bm2_chain *) malloc(sizeof(bm2_chain) * (s2.chains.size() + 1)); memcpy(*chains, s2.chains.data(), sizeof(bm2_chain) * s2.chains.size());
+    *seeds = (bm2_seed *) malloc(sizeof(bm2_seed) * (s2.seeds.size() + 1)); memcpy(*seeds, s2.seeds.data(), sizeof(bm2_seed) * s2.seeds.size());
+    *read_off = (int64_t *) malloc(8 * (rb->n_reads + 1)); memcpy(*read_off, s2.read_chain_off.data(), 8 * (rb->n_reads + 1));
+    *n_chains = (int64_t) s2.chains.size(); *n_seeds = (int64_t) s2.seeds.size();
+    return 0;
+}
+
+int emul_seed_chain_extend(const bm2_index_desc *idx, const bm2_mem_opt_t *o, const bm2_read_batch *rb, bm2_alnreg_t **regs_out,
+                           int64_t *n_regs, int64_t **read_off) {
+    Views v = make_views(idx, o); Stage1 s1; stage_smem_sa(v, o, rb, s1); Stage2 s2; stage_chain(v, rb, s1, s2);
+    const int n = rb->n_reads;
+    // reg / job offsets (device: exclusive scans)
+    std::vector<int64_t> reg_off(n + 1, 0), left_off(n + 1, 0), right_off(n + 1, 0);
+    int max_chain = 1, max_len = 1;
+    for (int r = 0; r < n; ++r) {
+        int64_t nr = 0;
+        for (int64_t c = s2.read_chain_off[r]; c < s2.read_chain_off[r + 1]; ++c) { nr += s2.chains[c].n_seeds; max_chain = std::max(max_chain, s2.chains[c].n_seeds); }
+        reg_off[r + 1] = reg_off[r] + nr; left_off[r + 1] = left_off[r] + s2.n_left[r]; right_off[r + 1] = right_off[r] + s2.n_right[r];
+        max_len = std::max<int>(max_len, (int) (rb->offsets[r + 1] - rb->offsets[r]));
+    }
+    std::vector<bm2_alnreg_t> regs(reg_off[n] + 1); std::vector<int32_t> reg_chain(reg_off[n] + 1), reg_seed(reg_off[n] + 1);
+    std::vector<ExtJobRec> left(left_off[n] + 1), right(right_off[n] + 1); std::vector<int32_t> left_reg(left_off[n] + 1), right_reg(right_off[n] + 1);
+    std::vector<uint64_t> srt(max_chain + 1);
+    for (int r = 0; r < n; ++r) {
+        int64_t cb = s2.read_chain_off[r], ce = s2.read_chain_off[r + 1];
+        if (ce == cb) continue;
+        // chains of the read address seeds through absolute seed_off: pass seeds base 0
+        ext_build_read_d(v.cv, v.ep, s2.chains.data() + cb, (int) (ce - cb), s2.seeds.data(), (int) (rb->offsets[r + 1] - rb->offsets[r]),
+                         rb->offsets[r], cb, reg_off[r], regs.data() + reg_off[r], reg_chain.data() + reg_off[r], reg_seed.data() + reg_off[r],
+                         left.data() + left_off[r], left_reg.data() + left_off[r], right.data() + right_off[r], right_reg.data() + right_off[r], srt.data());
+    }
+    auto run_phase = [&](std::vector<ExtJobRec> &jobs, std::vector<int32_t> &job_reg, int64_t nj, int is_right) {
+        std::vector<int> todo(nj); for (int64_t i = 0; i < nj; ++i) todo[i] = (int) i;
+        for (int t = 0; t < 2 && !todo.empty(); ++t) {
+            int w = o->w << t;
+            std::vector<int> retry;
+            for (int ji : todo) {
+                ExtJobRec &j = jobs[ji];
+                bm2_alnreg_t &a = regs[job_reg[ji]];
+                if (is_right && t == 0) j.h0 = a.score;
+                std::vector<uint8_t> q(j.qlen), tg(j.tlen);
+                for (int i = 0; i < j.qlen; ++i) q[i] = rb->codes[j.qoff + (int64_t) i * j.qstride];
+                for (int i = 0; i < j.tlen; ++i) tg[i] = idx->ref_string[j.toff + (int64_t) i * j.tstride];
+                bm2o_bsw_params bp = { o->a, o->b, o->o_del, o->e_del, o->o_ins, o->e_ins, o->zdrop, is_right ? o->pen_clip3 : o->pen_clip5, 1 };
+                int32_t out[6];
+                bm2o_bsw_extend(q.data(), j.qlen, tg.data(), j.tlen, w, j.h0, &bp, out);
+                const bm2_chain &c = s2.chains[reg_chain[job_reg[ji]]];
+                int rd = c.seqid; int l_query = (int) (rb->offsets[rd + 1] - rb->offsets[rd]);
+                bool ok = ext_fold_d(v.ep, a, is_right, j.h0, out[0], out[1], out[2], out[3], out[4], out[5], w, t == 1, l_query,
+                                     s2.seeds.data() + c.seed_off, c.n_seeds);
+                if (!ok) retry.push_back(ji);
+            }
+            todo.swap(retry);
+        }
+    };
+    run_phase(left, left_reg, left_off[n], 0);
+    run_phase(right, right_reg, right_off[n], 1);
+    std::vector<bm2_alnreg_t> out; std::vector<int64_t> off(n + 1, 0);
+    std::vector<int32_t> srt2(max_chain + 1), he(2 * (max_len + 2));
+    for (int r = 0; r < n; ++r) {
+        int64_t cb = s2.read_chain_off[r], ce = s2.read_chain_off[r + 1];
+        int nreg = (int) (reg_off[r + 1] - reg_off[r]);
+        int l_query = (int) (rb->offsets[r + 1] - rb->offsets[r]);
+        if (ce > cb) {
+            ext_postfilter_read_d(v.ep, s2.chains.data() + cb, (int) (ce - cb), s2.seeds.data(), l_query, regs.data() + reg_off[r], nreg,
+                                  reg_seed.data() + reg_off[r], srt2.data());
+            int m = ext_tail_read_d(v.cv, v.ep, idx->ref_string, rb->codes + rb->offsets[r], regs.data() + reg_off[r], nreg, he.data());
+            for (int i = 0; i < m; ++i) out.push_back(regs[reg_off[r] + i]);
+        }
+        off[r + 1] = (int64_t) out.size();
+    }
+    *regs_out = (bm2_alnreg_t *) malloc(sizeof(bm2_alnreg_t) * (out.size() + 1)); memcpy(*regs_out, out.data(), sizeof(bm2_alnreg_t) * out.size());
+    *read_off = (int64_t *) malloc(8 * (n + 1)); memcpy(*read_off, off.data(), 8 * (n + 1));
+    *n_regs = (int64_t) out.size();
+    return 0;
+}
+}
