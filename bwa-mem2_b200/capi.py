@@ -55,7 +55,7 @@ class RegResult(C.Structure):
     _fields_ = [("n", C.c_int64), ("regs", C.c_void_p), ("read_off", C.c_void_p)]
 
 
-EXPORTS = ["bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
+EXPORTS = ["bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
            "bm2_last_error", "bm2_extend_pairs", "bm2_extend_pairs_device", "bm2_collect_smems", "bm2_seed_chain",
            "bm2_seed_chain_extend", "bm2_last_stage_ms"]
 
@@ -201,6 +201,12 @@ class Context:
         lib().bm2_int_pipe_gops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         self._check(lib().bm2_int_pipe_gops(self._ctx, C.byref(v)), "bm2_int_pipe_gops")
         return v.value
+
+    def counters(self):
+        v = (C.c_ulonglong * 5)()
+        lib().bm2_last_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib().bm2_last_counters(self._ctx, v, 5)
+        return dict(n_ext=v[0], n_lf=v[1], cells=v[2], retry_left=v[3], retry_right=v[4])
 
     def stage_ms(self):
         names = C.POINTER(C.c_char_p)(); ms = C.POINTER(C.c_float)(); n = C.c_int()

@@ -37,6 +37,7 @@ struct bm2_ctx {
     std::vector<cudaEvent_t> events;
     std::vector<const char *> stage_names;
     std::vector<float> stage_ms;
+    unsigned long long last_n_ext = 0, last_n_lf = 0, last_cells = 0, last_n_retry[2] = {0, 0};
 
     int ensure(DevBuf &b, size_t bytes);
     int ensure_host(HostBuf &b, size_t bytes);

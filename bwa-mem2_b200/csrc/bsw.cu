@@ -44,16 +44,22 @@ __device__ __forceinline__ int bsw_class_of(int qlen, int tlen, int h0, int a) {
 }
 
 __global__ void bsw_keys_kernel(const BswJob *jobs, int n, int a, uint32_t *keys, int32_t *idx, int32_t *class_cnt) {
+    __shared__ int hist[BSW_NCLASS + 1];
+    if (threadIdx.x <= BSW_NCLASS) hist[threadIdx.x] = 0;
+    __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    BswJob j = jobs[i];
-    int c = bsw_class_of(j.qlen, j.tlen, j.h0, a);
-    int t = j.tlen > 0xFFFFF ? 0xFFFFF : j.tlen;
-    // ascending sort => class ascending, target length descending (long jobs first), then qlen desc
-    int q = j.qlen > 0xFF ? 0xFF : j.qlen;
-    keys[i] = ((uint32_t) c << 28) | ((uint32_t) (0xFFFFF - t) << 8) | (uint32_t) (0xFF - q);
-    idx[i] = i;
-    atomicAdd(&class_cnt[c], 1);
+    if (i < n) {
+        BswJob j = jobs[i];
+        int c = bsw_class_of(j.qlen, j.tlen, j.h0, a);
+        int t = j.tlen > 0xFFFFF ? 0xFFFFF : j.tlen;
+        // ascending sort => class ascending, target length descending (long jobs first), then qlen desc
+        int q = j.qlen > 0xFF ? 0xFF : j.qlen;
+        keys[i] = ((uint32_t) c << 28) | ((uint32_t) (0xFFFFF - t) << 8) | (uint32_t) (0xFF - q);
+        idx[i] = i;
+        atomicAdd(&hist[c], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x <= BSW_NCLASS && hist[threadIdx.x]) atomicAdd(&class_cnt[threadIdx.x], hist[threadIdx.x]);
 }
 
 __global__ void bsw_class_off_kernel(const int32_t *class_cnt, int32_t *class_off) {
@@ -299,7 +305,7 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
 
     for (int c = 0; c < BSW_NCLASS; ++c) {
         int W = h_class_bound[c] + 2;
-        int QW = (h_class_bound[c] + 7) / 8;
+        int QW = h_class_bound[c] / 8 + 1;       // +1: cursor(beg) may touch word qlen>>3 when beg == qlen
         // threads per CTA: as many as fit ~150 KB (>= 1 CTA/SM), capped at BSW_THREADS
         int nthr = BSW_THREADS;
         while (nthr > 32 && (size_t) (W + QW) * nthr * 4 > 150 * 1024) nthr >>= 1;

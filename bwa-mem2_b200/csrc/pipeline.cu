@@ -1,7 +1,41 @@
-// pipeline.cu — seam 2: index upload and the seed -> chain -> extend pipeline (under construction).
+// pipeline.cu — seam 2: the seed -> SA -> chain -> extend pipeline on the GPU.
+//
+// Replaces kt_for(worker_bwt) + kt_for(worker_aln) of mem_process_seqs (reference
+// src/bwamem.cpp:1359-1363), i.e. mem_kernel1_core (:976-1091) and mem_kernel2_core (:1093-1172),
+// and the 512-read/thread batching of kthread.cpp:81-115: the whole chunk is one batch, every stage
+// is one kernel over all reads (or all SMEMs / seed slots / extension jobs) of the chunk.
+//
+// Stage list (each a kernel or a cub primitive on ctx->stream):
+//   A  smem_kernel         one read per thread, 3 SMEM passes (fm_device.cuh)       HBM random 64 B
+//   B  radix sort of SMEMs by (read, m, n)  == sortSMEMs + per-read introsort
+//   C  sa_kernel           one seed slot per thread, compressed-SA LF walk          HBM random 64 B
+//   D  chain_kernel        one read per thread: chaining + chain filter (chain_device.cuh)
+//   E  scans + compaction  flat chain / seed / reg / job arrays
+//   F  ext_build_kernel    one read per thread: regs + left/right extension jobs
+//   G  BSW left  (bsw.cu) + fold + doubled-band retry
+//   H  BSW right (bsw.cu) + fold + doubled-band retry
+//   I  tail_kernel         one read per thread: post-filter, dedup/patch, ALT marking
+//   J  gather of the final regs, D2H
 #include "bm2_common.cuh"
 #include "bm2_ctx.h"
+#include "fm_device.cuh"
+#include "chain_device.cuh"
+#include "ext_device.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <vector>
+#include <cstring>
+#include <cmath>
 
+static_assert(sizeof(ExtJobRec) == sizeof(BswJob), "ExtJobRec must alias BswJob");
+
+int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const BswJob *d_jobs, BswOut *d_out, int n,
+                            const uint8_t *d_tbase, const uint8_t *d_qbase, const BswParams &prm,
+                            unsigned long long *d_cells, void *scratch, size_t scratch_bytes, int wide_possible);
+
+// ------------------------------------------------------------------------------------------------
+// index upload
+// ------------------------------------------------------------------------------------------------
 int bm2_upload_index(bm2_ctx *ctx, const bm2_index_desc *idx) {
     bm2_ctx *ctx_for_error = ctx;
     auto up = [&](const void *src, size_t bytes, const void **dst) -> int {
@@ -37,18 +71,572 @@ void bm2_free_index(bm2_ctx *ctx) {
     ctx->idx.loaded = false;
 }
 
-// ---- seam 2 entry points (filled in stage by stage) ---------------------------------------------
-extern "C" int bm2_collect_smems(bm2_ctx *ctx, const bm2_read_batch *, bm2_smem_result *) {
-    bm2_set_error(ctx, "bm2_collect_smems: not implemented in this build"); return 1;
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+struct Counters {                 // device-side counters of one batch
+    unsigned long long n_smem, n_ext, n_lf, n_retry, cells;
+    unsigned long long pad[3];
+};
+
+struct SmemAppend {
+    bm2_smem *out; unsigned long long cap; unsigned long long *count; uint32_t rid;
+    __device__ __forceinline__ void operator()(int m, int n, int64_t k, int64_t l, int64_t s) {
+        unsigned long long i = atomicAdd(count, 1ULL);
+        if (i < cap) { bm2_smem x; x.rid = rid; x.m = (uint32_t) m; x.n = (uint32_t) n; x.k = k; x.l = l; x.s = s; out[i] = x; }
+    }
+};
+
+// A. one read per thread (grid-stride), private prev/reseed stripes per THREAD
+__global__ void __launch_bounds__(128)
+smem_kernel(FmIndexView fm, SmemParams sp, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, int n_reads, int stripe,
+            FmPrev *prev_all, int32_t *reseed_all, bm2_smem *out, unsigned long long cap, Counters *cnt)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    FmPrev *prev = prev_all + (size_t) tid * stripe;
+    int32_t *reseed = reseed_all + (size_t) tid * 2 * stripe;
+    unsigned n_ext = 0;
+    for (int r = tid; r < n_reads; r += nthr) {
+        const int64_t o = offs[r];
+        const int len = (int) (offs[r + 1] - o);
+        SmemAppend emit = { out, cap, &cnt->n_smem, (uint32_t) r };
+        fm_smem_read(fm, codes + o, len, sp, prev, reseed, emit, n_ext);
+    }
+    if (n_ext) atomicAdd(&cnt->n_ext, (unsigned long long) n_ext);
 }
-extern "C" int bm2_seed_chain(bm2_ctx *ctx, const bm2_read_batch *, bm2_chain_result *) {
-    bm2_set_error(ctx, "bm2_seed_chain: not implemented in this build"); return 1;
+
+// B. sort keys: (rid, m, n) -> the order of sortSMEMs + ks_introsort(mem_intv1) (src/bwamem.cpp:785-799)
+__global__ void smem_keys_kernel(const bm2_smem *sm, int64_t n, uint64_t *keys, uint32_t *vals) {
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = (uint64_t) sm[i].rid << 32 | (uint64_t) (sm[i].m & 0xFFFFu) << 16 | (uint64_t) (sm[i].n & 0xFFFFu);
+    vals[i] = (uint32_t) i;
 }
-extern "C" int bm2_seed_chain_extend(bm2_ctx *ctx, const bm2_read_batch *, bm2_reg_result *) {
-    bm2_set_error(ctx, "bm2_seed_chain_extend: not implemented in this build"); return 1;
+
+__global__ void smem_gather_kernel(const bm2_smem *in, const uint32_t *perm, int64_t n, int max_occ, bm2_smem *out, int64_t *slot_cnt) {
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bm2_smem x = in[perm[i]];
+    out[i] = x;
+    slot_cnt[i] = x.s < max_occ ? x.s : max_occ;          // rows sampled per SMEM (src/bwamem.cpp:892-893)
 }
+
+__global__ void read_smem_off_kernel(const uint64_t *keys_sorted, int64_t n_smem, int n_reads, int64_t *read_smem_off) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_reads) return;
+    const uint64_t key = (uint64_t) r << 32;               // first SMEM with rid >= r
+    int64_t lo = 0, hi = n_smem;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (keys_sorted[mid] < key) lo = mid + 1; else hi = mid; }
+    read_smem_off[r] = lo;
+}
+
+// C. one seed slot per thread
+__global__ void __launch_bounds__(256)
+sa_kernel(FmIndexView fm, const bm2_smem *__restrict__ sm, const int64_t *__restrict__ slot_off, int64_t n_smem, int64_t n_slots, int max_occ,
+          int64_t *sa, Counters *cnt)
+{
+    int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    int lf = 0;
+    if (t < n_slots) {
+        int64_t lo = 0, hi = n_smem;                        // last SMEM with slot_off <= t
+        while (lo + 1 < hi) { int64_t mid = (lo + hi) >> 1; if (slot_off[mid] <= t) lo = mid; else hi = mid; }
+        const bm2_smem x = sm[lo];
+        const int64_t step = x.s > max_occ ? x.s / max_occ : 1;
+        sa[t] = fm_sa_of_row(fm, x.k + (t - slot_off[lo]) * step, &lf);
+    }
+    if (lf) atomicAdd(&cnt->n_lf, (unsigned long long) lf);
+}
+
+// D. one read per thread
+struct ChainBufs {
+    WSeed *wseed; WChain *wchain; int32_t *ord, *srt, *kv;
+    bm2_chain *fin_chain; bm2_seed *fin_seed;
+    int32_t *n_chain, *n_seed, *n_left, *n_right;
+};
+
+__global__ void __launch_bounds__(128)
+chain_kernel(ContigView cv, ChainParams cp, const bm2_smem *__restrict__ sm, const int64_t *__restrict__ read_smem_off,
+             const int64_t *__restrict__ slot_off, const int64_t *__restrict__ sa, const int64_t *__restrict__ offs, int n_reads, ChainBufs b)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    int nk = 0, ns = 0, nl = 0, nr = 0;
+    const int64_t sb = read_smem_off[r], se = read_smem_off[r + 1];
+    const int len = (int) (offs[r + 1] - offs[r]);
+    // reference quirk: a 512-read block whose SMEM total is exactly 1 yields no chain (src/bwamem.cpp:835)
+    const int b0 = (r / 512) * 512, b1 = min(n_reads, b0 + 512);
+    const bool skip = (read_smem_off[b1] - read_smem_off[b0]) <= 1;
+    if (se > sb && !skip && len >= cp.min_seed_len) {
+        const int64_t base = slot_off[sb];
+        ChainStripe ws = { b.wseed + base, b.wchain + base, b.ord + base, b.srt + base, b.kv + base };
+        float frac = 0.f;
+        nk = chain_read_d(cv, cp, sm + sb, (int) (se - sb), sa + base, len, ws, &frac);
+        chain_finalize_d(ws, nk, frac, r, len, b.fin_chain + base, b.fin_seed + base, &ns, &nl, &nr);
+    }
+    b.n_chain[r] = nk; b.n_seed[r] = ns; b.n_left[r] = nl; b.n_right[r] = nr;
+}
+
+// E. compaction of the per-read stripes into flat arrays
+__global__ void chain_compact_kernel(const int64_t *__restrict__ read_smem_off, const int64_t *__restrict__ slot_off, int n_reads,
+                                     const bm2_chain *fin_chain, const bm2_seed *fin_seed, const int64_t *chain_off, const int64_t *reg_off,
+                                     bm2_chain *chains, bm2_seed *seeds)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int64_t c0 = chain_off[r], c1 = chain_off[r + 1];
+    if (c1 == c0) return;
+    const int64_t base = slot_off[read_smem_off[r]];
+    const int64_t s0 = reg_off[r], s1 = reg_off[r + 1];
+    for (int64_t k = 0; k < c1 - c0; ++k) { bm2_chain c = fin_chain[base + k]; c.seed_off += (int32_t) s0; chains[c0 + k] = c; }
+    for (int64_t k = 0; k < s1 - s0; ++k) { bm2_seed s = fin_seed[base + k]; s.chain += (int32_t) c0; seeds[s0 + k] = s; }
+}
+
+// F. one read per thread
+struct ExtBufs {
+    bm2_alnreg_t *regs; int32_t *reg_chain, *reg_seed; uint64_t *srt;
+    ExtJobRec *left, *right; int32_t *left_reg, *right_reg;
+};
+
+__global__ void __launch_bounds__(128)
+ext_build_kernel(ContigView cv, ExtParams ep, const bm2_chain *__restrict__ chains, const bm2_seed *__restrict__ seeds,
+                 const int64_t *__restrict__ chain_off, const int64_t *__restrict__ reg_off, const int64_t *__restrict__ left_off,
+                 const int64_t *__restrict__ right_off, const int64_t *__restrict__ offs, int n_reads, ExtBufs b)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int64_t c0 = chain_off[r], c1 = chain_off[r + 1];
+    if (c1 == c0) return;
+    const int64_t g0 = reg_off[r];
+    ext_build_read_d(cv, ep, chains + c0, (int) (c1 - c0), seeds, (int) (offs[r + 1] - offs[r]), offs[r], c0, g0, b.regs + g0,
+                     b.reg_chain + g0, b.reg_seed + g0, b.left + left_off[r], b.left_reg + left_off[r], b.right + right_off[r],
+                     b.right_reg + right_off[r], b.srt + g0);
+}
+
+// G/H. fold one finished job into its reg; rejected jobs are appended to the retry list
+__global__ void right_h0_kernel(ExtJobRec *jobs, const int32_t *job_reg, int n, const bm2_alnreg_t *regs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) jobs[i].h0 = regs[job_reg[i]].score;       // src/bwamem.cpp:2672-2677
+}
+
+__global__ void fold_kernel(ExtParams ep, const ExtJobRec *jobs, const int32_t *job_reg, const BswOut *outs, const int32_t *sel, int n,
+                            int is_right, int w, int last_try, bm2_alnreg_t *regs, const int32_t *reg_chain, const bm2_chain *chains,
+                            const bm2_seed *seeds, const int64_t *offs, int32_t *retry, Counters *cnt)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int j = sel ? sel[t] : t;                        // job index; outs[] is indexed like the launch (t)
+    const BswOut o = outs[t];
+    const int g = job_reg[j];
+    const bm2_chain c = chains[reg_chain[g]];
+    const int l_query = (int) (offs[c.seqid + 1] - offs[c.seqid]);
+    bm2_alnreg_t a = regs[g];
+    const bool ok = ext_fold_d(ep, a, is_right, jobs[j].h0, o.score, o.qle, o.tle, o.gtle, o.gscore, o.max_off, w, last_try, l_query,
+                               seeds + c.seed_off, c.n_seeds);
+    regs[g] = a;
+    if (!ok) { unsigned long long k = atomicAdd(&cnt->n_retry, 1ULL); retry[k] = j; }
+}
+
+__global__ void gather_jobs_kernel(const ExtJobRec *jobs, const int32_t *sel, int n, ExtJobRec *out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = jobs[sel[t]];
+}
+
+// I. one read per thread (grid-stride: the NW scratch `he` is per thread)
+__global__ void __launch_bounds__(128)
+tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs,
+            const bm2_chain *__restrict__ chains, const bm2_seed *__restrict__ seeds, const int64_t *__restrict__ chain_off,
+            const int64_t *__restrict__ reg_off, int n_reads, bm2_alnreg_t *regs, const int32_t *reg_seed, int32_t *srt2_all, int32_t *he_all,
+            int he_stride, int32_t *n_final)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    int32_t *he = he_all + (size_t) tid * he_stride;
+    for (int r = tid; r < n_reads; r += nthr) {
+        const int64_t c0 = chain_off[r], c1 = chain_off[r + 1], g0 = reg_off[r];
+        const int n_reg = (int) (reg_off[r + 1] - g0);
+        int m = 0;
+        if (c1 > c0) {
+            const int l_query = (int) (offs[r + 1] - offs[r]);
+            ext_postfilter_read_d(ep, chains + c0, (int) (c1 - c0), seeds, l_query, regs + g0, n_reg, reg_seed + g0, srt2_all + g0);
+            m = ext_tail_read_d(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he);
+        }
+        n_final[r] = m;
+    }
+}
+
+__global__ void regs_gather_kernel(const bm2_alnreg_t *regs, const int64_t *reg_off, const int64_t *out_off, int n_reads, bm2_alnreg_t *out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int64_t o0 = out_off[r], o1 = out_off[r + 1], g0 = reg_off[r];
+    for (int64_t k = 0; k < o1 - o0; ++k) out[o0 + k] = regs[g0 + k];
+}
+
+__global__ void widen_kernel(const int32_t *in, int n, int64_t *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+    if (i == n) out[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+namespace {
+enum Buf {
+    B_CODES, B_OFFS, B_CNT, B_PREV, B_RESEED, B_SMEM_RAW, B_KEYS_IN, B_KEYS_OUT, B_VALS_IN, B_VALS_OUT, B_CUB, B_SMEM, B_SLOT_CNT,
+    B_SLOT_OFF, B_READ_SMEM_OFF, B_SA, B_WSEED, B_WCHAIN, B_ORD, B_SRT, B_KV, B_FIN_CHAIN, B_FIN_SEED, B_PER_READ, B_SCAN, B_CHAINS,
+    B_SEEDS, B_REGS, B_REG_AUX, B_JOBS, B_NW, B_OUT
+};
+enum HBuf { H_OUT_REGS, H_OUT_OFF, H_SMEM, H_CHAINS, H_SEEDS, H_MISC };
+
+struct Stages {
+    bm2_ctx *ctx; std::vector<cudaEvent_t> &ev; std::vector<const char *> &names;
+    int n = 0;
+    int mark(const char *name) {
+        bm2_ctx *ctx_for_error = ctx;
+        if ((int) ev.size() <= n) { cudaEvent_t e; BM2_CUDA_OK(cudaEventCreate(&e)); ev.push_back(e); }
+        BM2_CUDA_OK(cudaEventRecord(ev[n], ctx->stream));
+        if ((int) names.size() <= n) names.push_back(name); else names[n] = name;
+        ++n;
+        return 0;
+    }
+};
+
+template <class T> T *P(bm2_ctx *ctx, int b) { return (T *) ctx->d[b].p; }
+
+}  // namespace
+
+namespace {
+
+struct Params { FmIndexView fm; ContigView cv; SmemParams sp; ChainParams cp; ExtParams ep; };
+
+Params make_params(const bm2_ctx *ctx) {
+    Params v;
+    const DevIndex &d = ctx->idx; const bm2_mem_opt_t &o = ctx->opt;
+    v.fm.cp_occ = d.cp_occ; v.fm.sa_ms = d.sa_ms; v.fm.sa_ls = d.sa_ls; v.fm.sentinel = d.sentinel;
+    for (int i = 0; i < 5; ++i) v.fm.count[i] = d.count[i];
+    v.cv.l_pac = d.l_pac; v.cv.n_seqs = d.n_seqs; v.cv.ann_off = d.ann_off; v.cv.ann_len = d.ann_len; v.cv.ann_alt = d.ann_alt;
+    v.sp.min_seed_len = o.min_seed_len; v.sp.split_len = (int) (o.min_seed_len * o.split_factor + .499);
+    v.sp.split_width = o.split_width; v.sp.max_mem_intv = (int) o.max_mem_intv;
+    v.cp.w = o.w; v.cp.max_chain_gap = o.max_chain_gap; v.cp.max_occ = o.max_occ; v.cp.min_chain_weight = o.min_chain_weight;
+    v.cp.max_chain_extend = o.max_chain_extend; v.cp.min_seed_len = o.min_seed_len; v.cp.mask_level = o.mask_level; v.cp.drop_ratio = o.drop_ratio;
+    v.ep.a = o.a; v.ep.b = o.b; v.ep.o_del = o.o_del; v.ep.e_del = o.e_del; v.ep.o_ins = o.o_ins; v.ep.e_ins = o.e_ins; v.ep.w = o.w;
+    v.ep.pen_clip5 = o.pen_clip5; v.ep.pen_clip3 = o.pen_clip3; v.ep.max_chain_gap = o.max_chain_gap; v.ep.mask_level_redun = o.mask_level_redun;
+    memcpy(v.ep.mat, o.mat, 25);
+    return v;
+}
+
+inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+// exclusive scan of n int64 counts into n+1 offsets (last = total)
+int scan64(bm2_ctx *ctx, const int64_t *in, int64_t *out, int64_t n) {
+    bm2_ctx *ctx_for_error = ctx;
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int) (n + 1));
+    if (ctx->ensure(ctx->d[B_CUB], bytes)) return 1;
+    BM2_CUDA_OK(cub::DeviceScan::ExclusiveSum(ctx->d[B_CUB].p, bytes, in, out, (int) (n + 1), ctx->stream));
+    return 0;
+}
+
+enum UpTo { UPTO_SMEM, UPTO_CHAIN, UPTO_REGS };
+
+struct BatchState {       // host-visible sizes of the batch in flight
+    int n = 0, max_len = 0; int64_t n_smem = 0, n_slots = 0, n_chains = 0, n_regs = 0, n_left = 0, n_right = 0, n_out = 0;
+};
+
+int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &bs) {
+    bm2_ctx *ctx_for_error = ctx;
+    if (!ctx->idx.loaded) { bm2_set_error(ctx, "seam 2 needs a context created with an index"); return 1; }
+    BM2_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = rb->n_reads;
+    bs = BatchState(); bs.n = n;
+    if (n <= 0) return 0;
+    const int64_t total = rb->offsets[n];
+    int max_len = 1;
+    for (int r = 0; r < n; ++r) {
+        int64_t l = rb->offsets[r + 1] - rb->offsets[r];
+        if (l < 0 || l > 32767) { bm2_set_error(ctx, "read length out of range (0..32767)"); return 1; }
+        if (l > max_len) max_len = (int) l;
+        // mem_flt_chained_seeds (src/bwamem.cpp:472-504) needs ksw_align2: only reads this long trigger it
+        double min_l = ctx->opt.min_chain_weight ? 1.1f * ctx->opt.min_chain_weight : 5.5f * log((double) (l > 0 ? l : 1));
+        if (l > 0 && !(min_l > 0.05f * l)) { bm2_set_error(ctx, "long reads (mem_flt_chained_seeds path) are not supported by this build"); return 1; }
+    }
+    bs.max_len = max_len;
+    Params pv = make_params(ctx);
+    Stages sg = { ctx, ctx->events, ctx->stage_names };
+    if (sg.mark("h2d")) return 1;
+
+    if (ctx->ensure(ctx->d[B_CODES], (size_t) total + 16) || ctx->ensure(ctx->d[B_OFFS], (size_t) (n + 1) * 8) ||
+        ctx->ensure(ctx->d[B_CNT], sizeof(Counters))) return 1;
+    BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[B_CODES].p, rb->codes, (size_t) total, cudaMemcpyHostToDevice, st));
+    BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[B_OFFS].p, rb->offsets, (size_t) (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    BM2_CUDA_OK(cudaMemsetAsync(ctx->d[B_CNT].p, 0, sizeof(Counters), st));
+    const uint8_t *d_codes = P<uint8_t>(ctx, B_CODES); const int64_t *d_offs = P<int64_t>(ctx, B_OFFS);
+    Counters *d_cnt = P<Counters>(ctx, B_CNT);
+    Counters h_cnt;
+
+    // ---- A. SMEMs -------------------------------------------------------------------------------------------
+    if (sg.mark("smem")) return 1;
+    const int stripe = max_len + 2;
+    int blocks_a = (n + 127) / 128; const int max_blocks_a = ctx->n_sm * 16; if (blocks_a > max_blocks_a) blocks_a = max_blocks_a;
+    const size_t thr_a = (size_t) blocks_a * 128;
+    if (ctx->ensure(ctx->d[B_PREV], thr_a * stripe * sizeof(FmPrev)) || ctx->ensure(ctx->d[B_RESEED], thr_a * 2 * stripe * 4)) return 1;
+    unsigned long long cap = (unsigned long long) n * 16 + 4096;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (ctx->ensure(ctx->d[B_SMEM_RAW], cap * sizeof(bm2_smem))) return 1;
+        BM2_CUDA_OK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), st));
+        smem_kernel<<<blocks_a, 128, 0, st>>>(pv.fm, pv.sp, d_codes, d_offs, n, stripe, P<FmPrev>(ctx, B_PREV), P<int32_t>(ctx, B_RESEED),
+                                               P<bm2_smem>(ctx, B_SMEM_RAW), cap, d_cnt);
+        BM2_CUDA_OK(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        BM2_CUDA_OK(cudaStreamSynchronize(st));
+        if (h_cnt.n_smem <= cap) break;
+        if (attempt == 1) { bm2_set_error(ctx, "SMEM buffer overflow"); return 1; }
+        cap = h_cnt.n_smem + 1024;
+    }
+    const int64_t n_smem = (int64_t) h_cnt.n_smem;
+    bs.n_smem = n_smem;
+    ctx->last_n_ext = h_cnt.n_ext;
+
+    // ---- B. order SMEMs -----------------------------------------------------------------------------------
+    if (sg.mark("sort")) return 1;
+    const int64_t ns1 = n_smem > 0 ? n_smem : 1;
+    if (ctx->ensure(ctx->d[B_KEYS_IN], ns1 * 8) || ctx->ensure(ctx->d[B_KEYS_OUT], ns1 * 8) || ctx->ensure(ctx->d[B_VALS_IN], ns1 * 4) ||
+        ctx->ensure(ctx->d[B_VALS_OUT], ns1 * 4) || ctx->ensure(ctx->d[B_SMEM], (ns1 + 1) * sizeof(bm2_smem)) ||
+        ctx->ensure(ctx->d[B_SLOT_CNT], (ns1 + 1) * 8) || ctx->ensure(ctx->d[B_SLOT_OFF], (ns1 + 2) * 8) ||
+        ctx->ensure(ctx->d[B_READ_SMEM_OFF], (size_t) (n + 2) * 8)) return 1;
+    if (n_smem > 0) {
+        const int gb = (int) ((n_smem + 255) / 256);
+        smem_keys_kernel<<<gb, 256, 0, st>>>(P<bm2_smem>(ctx, B_SMEM_RAW), n_smem, P<uint64_t>(ctx, B_KEYS_IN), P<uint32_t>(ctx, B_VALS_IN));
+        size_t cub_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, P<uint64_t>(ctx, B_KEYS_IN), P<uint64_t>(ctx, B_KEYS_OUT), P<uint32_t>(ctx, B_VALS_IN),
+                                        P<uint32_t>(ctx, B_VALS_OUT), (int) n_smem);
+        if (ctx->ensure(ctx->d[B_CUB], cub_bytes)) return 1;
+        BM2_CUDA_OK(cub::DeviceRadixSort::SortPairs(ctx->d[B_CUB].p, cub_bytes, P<uint64_t>(ctx, B_KEYS_IN), P<uint64_t>(ctx, B_KEYS_OUT),
+                                                    P<uint32_t>(ctx, B_VALS_IN), P<uint32_t>(ctx, B_VALS_OUT), (int) n_smem, 0, 64, st));
+        BM2_CUDA_OK(cudaMemsetAsync(P<int64_t>(ctx, B_SLOT_CNT) + n_smem, 0, 8, st));
+        smem_gather_kernel<<<gb, 256, 0, st>>>(P<bm2_smem>(ctx, B_SMEM_RAW), P<uint32_t>(ctx, B_VALS_OUT), n_smem, ctx->opt.max_occ,
+                                               P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_SLOT_CNT));
+    } else {
+        BM2_CUDA_OK(cudaMemsetAsync(P<int64_t>(ctx, B_SLOT_CNT), 0, 8, st));
+    }
+    read_smem_off_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(P<uint64_t>(ctx, B_KEYS_OUT), n_smem, n, P<int64_t>(ctx, B_READ_SMEM_OFF));
+    if (scan64(ctx, P<int64_t>(ctx, B_SLOT_CNT), P<int64_t>(ctx, B_SLOT_OFF), n_smem)) return 1;
+    if (upto == UPTO_SMEM) { if (sg.mark("end")) return 1; BM2_CUDA_OK(cudaStreamSynchronize(st)); return 0; }
+    int64_t n_slots = 0;
+    BM2_CUDA_OK(cudaMemcpyAsync(&n_slots, P<int64_t>(ctx, B_SLOT_OFF) + n_smem, 8, cudaMemcpyDeviceToHost, st));
+    BM2_CUDA_OK(cudaStreamSynchronize(st));
+    bs.n_slots = n_slots;
+    if (n_slots > (int64_t) 1500000000) { bm2_set_error(ctx, "too many seed occurrences in one batch: use smaller chunks"); return 1; }
+
+    // ---- C. SA lookup -------------------------------------------------------------------------------------
+    if (sg.mark("sal")) return 1;
+    const size_t sl1 = (size_t) (n_slots > 0 ? n_slots : 1) + 1;
+    if (ctx->ensure(ctx->d[B_SA], sl1 * 8)) return 1;
+    if (n_slots > 0)
+        sa_kernel<<<(unsigned) ((n_slots + 255) / 256), 256, 0, st>>>(pv.fm, P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_SLOT_OFF), n_smem, n_slots,
+                                                                        ctx->opt.max_occ, P<int64_t>(ctx, B_SA), d_cnt);
+
+    // ---- D. chaining --------------------------------------------------------------------------------------
+    if (sg.mark("chain")) return 1;
+    if (ctx->ensure(ctx->d[B_WSEED], sl1 * sizeof(WSeed)) || ctx->ensure(ctx->d[B_WCHAIN], sl1 * sizeof(WChain)) ||
+        ctx->ensure(ctx->d[B_ORD], sl1 * 4) || ctx->ensure(ctx->d[B_SRT], sl1 * 4) || ctx->ensure(ctx->d[B_KV], sl1 * 4) ||
+        ctx->ensure(ctx->d[B_FIN_CHAIN], sl1 * sizeof(bm2_chain)) || ctx->ensure(ctx->d[B_FIN_SEED], sl1 * sizeof(bm2_seed)) ||
+        ctx->ensure(ctx->d[B_PER_READ], al((size_t) (n + 1) * 4) * 5) || ctx->ensure(ctx->d[B_SCAN], al((size_t) (n + 2) * 8) * 10)) return 1;
+    const size_t pr = al((size_t) (n + 1) * 4);
+    char *prb = (char *) ctx->d[B_PER_READ].p;
+    int32_t *d_nchain = (int32_t *) prb, *d_nseed = (int32_t *) (prb + pr), *d_nleft = (int32_t *) (prb + 2 * pr),
+            *d_nright = (int32_t *) (prb + 3 * pr), *d_nfinal = (int32_t *) (prb + 4 * pr);
+    ChainBufs cb = { P<WSeed>(ctx, B_WSEED), P<WChain>(ctx, B_WCHAIN), P<int32_t>(ctx, B_ORD), P<int32_t>(ctx, B_SRT), P<int32_t>(ctx, B_KV),
+                     P<bm2_chain>(ctx, B_FIN_CHAIN), P<bm2_seed>(ctx, B_FIN_SEED), d_nchain, d_nseed, d_nleft, d_nright };
+    chain_kernel<<<(n + 127) / 128, 128, 0, st>>>(pv.cv, pv.cp, P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_READ_SMEM_OFF),
+                                                  P<int64_t>(ctx, B_SLOT_OFF), P<int64_t>(ctx, B_SA), d_offs, n, cb);
+
+    // ---- E. scans + compaction ------------------------------------------------------------------------------
+    if (sg.mark("compact")) return 1;
+    const size_t sc = al((size_t) (n + 2) * 8);
+    char *scb = (char *) ctx->d[B_SCAN].p;
+    int64_t *w_tmp = (int64_t *) scb, *d_chain_off = (int64_t *) (scb + sc), *d_reg_off = (int64_t *) (scb + 2 * sc),
+            *d_left_off = (int64_t *) (scb + 3 * sc), *d_right_off = (int64_t *) (scb + 4 * sc), *d_out_off = (int64_t *) (scb + 5 * sc);
+    const int gw = (n + 1 + 255) / 256;
+    widen_kernel<<<gw, 256, 0, st>>>(d_nchain, n, w_tmp); if (scan64(ctx, w_tmp, d_chain_off, n)) return 1;
+    widen_kernel<<<gw, 256, 0, st>>>(d_nseed, n, w_tmp);  if (scan64(ctx, w_tmp, d_reg_off, n)) return 1;
+    widen_kernel<<<gw, 256, 0, st>>>(d_nleft, n, w_tmp);  if (scan64(ctx, w_tmp, d_left_off, n)) return 1;
+    widen_kernel<<<gw, 256, 0, st>>>(d_nright, n, w_tmp); if (scan64(ctx, w_tmp, d_right_off, n)) return 1;
+    int64_t tot[4];
+    BM2_CUDA_OK(cudaMemcpyAsync(&tot[0], d_chain_off + n, 8, cudaMemcpyDeviceToHost, st));
+    BM2_CUDA_OK(cudaMemcpyAsync(&tot[1], d_reg_off + n, 8, cudaMemcpyDeviceToHost, st));
+    BM2_CUDA_OK(cudaMemcpyAsync(&tot[2], d_left_off + n, 8, cudaMemcpyDeviceToHost, st));
+    BM2_CUDA_OK(cudaMemcpyAsync(&tot[3], d_right_off + n, 8, cudaMemcpyDeviceToHost, st));
+    BM2_CUDA_OK(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    BM2_CUDA_OK(cudaStreamSynchronize(st));
+    ctx->last_n_lf = h_cnt.n_lf;
+    const int64_t n_chains = tot[0], n_regs = tot[1], n_left = tot[2], n_right = tot[3];
+    bs.n_chains = n_chains; bs.n_regs = n_regs; bs.n_left = n_left; bs.n_right = n_right;
+    if (n_regs > 2000000000LL) { bm2_set_error(ctx, "too many seeds in one batch"); return 1; }
+    if (ctx->ensure(ctx->d[B_CHAINS], (size_t) (n_chains + 1) * sizeof(bm2_chain)) || ctx->ensure(ctx->d[B_SEEDS], (size_t) (n_regs + 1) * sizeof(bm2_seed))) return 1;
+    chain_compact_kernel<<<(n + 127) / 128, 128, 0, st>>>(P<int64_t>(ctx, B_READ_SMEM_OFF), P<int64_t>(ctx, B_SLOT_OFF), n, P<bm2_chain>(ctx, B_FIN_CHAIN),
+                                                          P<bm2_seed>(ctx, B_FIN_SEED), d_chain_off, d_reg_off, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS));
+    if (upto == UPTO_CHAIN) { if (sg.mark("end")) return 1; BM2_CUDA_OK(cudaStreamSynchronize(st)); return 0; }
+
+    // ---- F. regs + jobs -----------------------------------------------------------------------------------
+    if (sg.mark("extbuild")) return 1;
+    const size_t nr1 = (size_t) n_regs + 1, nl1 = (size_t) n_left + 1, nrt1 = (size_t) n_right + 1;
+    const size_t aux_bytes = al(nr1 * 4) * 3 + al(nr1 * 8) + al(nl1 * 4) * 2 + al(nrt1 * 4) * 2;
+    const size_t njmax = nl1 > nrt1 ? nl1 : nrt1;
+    if (ctx->ensure(ctx->d[B_REGS], nr1 * sizeof(bm2_alnreg_t)) || ctx->ensure(ctx->d[B_REG_AUX], aux_bytes) ||
+        ctx->ensure(ctx->d[B_JOBS], al(nl1 * sizeof(ExtJobRec)) + al(nrt1 * sizeof(ExtJobRec)) + al(njmax * sizeof(ExtJobRec)) + al(njmax * sizeof(BswOut))) ||
+        ctx->ensure(ctx->bsw_scratch, bsw_scratch_bytes((int) njmax))) return 1;
+    char *ab = (char *) ctx->d[B_REG_AUX].p;
+    int32_t *d_reg_chain = (int32_t *) ab; ab += al(nr1 * 4);
+    int32_t *d_reg_seed = (int32_t *) ab; ab += al(nr1 * 4);
+    int32_t *d_srt2 = (int32_t *) ab; ab += al(nr1 * 4);
+    uint64_t *d_srt = (uint64_t *) ab; ab += al(nr1 * 8);
+    int32_t *d_left_reg = (int32_t *) ab; ab += al(nl1 * 4);
+    int32_t *d_left_retry = (int32_t *) ab; ab += al(nl1 * 4);
+    int32_t *d_right_reg = (int32_t *) ab; ab += al(nrt1 * 4);
+    int32_t *d_right_retry = (int32_t *) ab; ab += al(nrt1 * 4);
+    char *jb = (char *) ctx->d[B_JOBS].p;
+    ExtJobRec *d_left = (ExtJobRec *) jb; jb += al(nl1 * sizeof(ExtJobRec));
+    ExtJobRec *d_right = (ExtJobRec *) jb; jb += al(nrt1 * sizeof(ExtJobRec));
+    ExtJobRec *d_retry_jobs = (ExtJobRec *) jb; jb += al(njmax * sizeof(ExtJobRec));
+    BswOut *d_outs = (BswOut *) jb;
+    bm2_alnreg_t *d_regs = P<bm2_alnreg_t>(ctx, B_REGS);
+    ExtBufs eb = { d_regs, d_reg_chain, d_reg_seed, d_srt, d_left, d_right, d_left_reg, d_right_reg };
+    ext_build_kernel<<<(n + 127) / 128, 128, 0, st>>>(pv.cv, pv.ep, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off, d_reg_off,
+                                                      d_left_off, d_right_off, d_offs, n, eb);
+
+    // ---- G/H. extension -----------------------------------------------------------------------------------
+    auto phase = [&](const char *name, ExtJobRec *jobs, int32_t *job_reg, int32_t *retry, int64_t nj, int is_right) -> int {
+        if (sg.mark(name)) return 1;
+        if (nj <= 0) return 0;
+        BswParams bp; bp.a = ctx->opt.a; bp.b = ctx->opt.b; bp.o_del = ctx->opt.o_del; bp.e_del = ctx->opt.e_del; bp.o_ins = ctx->opt.o_ins;
+        bp.e_ins = ctx->opt.e_ins; bp.zdrop = ctx->opt.zdrop; bp.end_bonus = is_right ? ctx->opt.pen_clip3 : ctx->opt.pen_clip5; bp.w = ctx->opt.w;
+        if (is_right) right_h0_kernel<<<(unsigned) ((nj + 255) / 256), 256, 0, st>>>(jobs, job_reg, (int) nj, d_regs);
+        BM2_CUDA_OK(cudaMemsetAsync(&d_cnt->n_retry, 0, 8, st));
+        if (bsw_launch_with_scratch(ctx, st, (const BswJob *) jobs, d_outs, (int) nj, ctx->idx.ref, d_codes, bp, &d_cnt->cells, ctx->bsw_scratch.p,
+                                    ctx->bsw_scratch.cap, 1)) return 1;
+        fold_kernel<<<(unsigned) ((nj + 255) / 256), 256, 0, st>>>(pv.ep, jobs, job_reg, d_outs, nullptr, (int) nj, is_right, bp.w, 0, d_regs, d_reg_chain,
+                                                                   P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_offs, retry, d_cnt);
+        unsigned long long n_retry = 0;
+        BM2_CUDA_OK(cudaMemcpyAsync(&n_retry, &d_cnt->n_retry, 8, cudaMemcpyDeviceToHost, st));
+        BM2_CUDA_OK(cudaStreamSynchronize(st));
+        if (n_retry > 0) {   // MAX_BAND_TRY = 2: re-run the rejected jobs once with the doubled band (src/bwamem.cpp:2472)
+            gather_jobs_kernel<<<(unsigned) ((n_retry + 255) / 256), 256, 0, st>>>(jobs, retry, (int) n_retry, d_retry_jobs);
+            bp.w = ctx->opt.w << 1;
+            if (bsw_launch_with_scratch(ctx, st, (const BswJob *) d_retry_jobs, d_outs, (int) n_retry, ctx->idx.ref, d_codes, bp, &d_cnt->cells,
+                                        ctx->bsw_scratch.p, ctx->bsw_scratch.cap, 1)) return 1;
+            // `retry` is read as the selection list while the kernel appends nothing new (last_try = 1)
+            fold_kernel<<<(unsigned) ((n_retry + 255) / 256), 256, 0, st>>>(pv.ep, jobs, job_reg, d_outs, retry, (int) n_retry, is_right, bp.w, 1, d_regs,
+                                                                            d_reg_chain, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_offs,
+                                                                            retry, d_cnt);
+        }
+        ctx->last_n_retry[is_right] = n_retry;
+        return 0;
+    };
+    if (phase("bsw_left", d_left, d_left_reg, d_left_retry, n_left, 0)) return 1;
+    if (phase("bsw_right", d_right, d_right_reg, d_right_retry, n_right, 1)) return 1;
+
+    // ---- I. post-filter + tail ----------------------------------------------------------------------------
+    if (sg.mark("tail")) return 1;
+    int blocks_i = (n + 127) / 128; const int max_blocks_i = ctx->n_sm * 8; if (blocks_i > max_blocks_i) blocks_i = max_blocks_i;
+    const int he_stride = 2 * (max_len + 2);
+    if (ctx->ensure(ctx->d[B_NW], (size_t) blocks_i * 128 * he_stride * 4)) return 1;
+    tail_kernel<<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
+                                          d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_nfinal);
+
+    // ---- J. output ---------------------------------------------------------------------------------------
+    if (sg.mark("output")) return 1;
+    widen_kernel<<<gw, 256, 0, st>>>(d_nfinal, n, w_tmp); if (scan64(ctx, w_tmp, d_out_off, n)) return 1;
+    if (ctx->ensure(ctx->d[B_OUT], nr1 * sizeof(bm2_alnreg_t))) return 1;
+    regs_gather_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_regs, d_reg_off, d_out_off, n, P<bm2_alnreg_t>(ctx, B_OUT));
+    if (ctx->ensure_host(ctx->h[H_OUT_OFF], (size_t) (n + 1) * 8)) return 1;
+    BM2_CUDA_OK(cudaMemcpyAsync(ctx->h[H_OUT_OFF].p, d_out_off, (size_t) (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    BM2_CUDA_OK(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    BM2_CUDA_OK(cudaStreamSynchronize(st));
+    ctx->last_cells = h_cnt.cells;
+    const int64_t n_out = ((const int64_t *) ctx->h[H_OUT_OFF].p)[n];
+    bs.n_out = n_out;
+    if (ctx->ensure_host(ctx->h[H_OUT_REGS], (size_t) (n_out + 1) * sizeof(bm2_alnreg_t))) return 1;
+    if (n_out) BM2_CUDA_OK(cudaMemcpyAsync(ctx->h[H_OUT_REGS].p, ctx->d[B_OUT].p, (size_t) n_out * sizeof(bm2_alnreg_t), cudaMemcpyDeviceToHost, st));
+    if (sg.mark("end")) return 1;
+    BM2_CUDA_OK(cudaStreamSynchronize(st));
+    BM2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int finish_stage_times(bm2_ctx *ctx) {
+    bm2_ctx *ctx_for_error = ctx;
+    ctx->stage_ms.clear();
+    size_t n = ctx->stage_names.size();
+    // the names vector may be longer than this run's marks when an earlier run went further
+    size_t marks = 0;
+    for (; marks < n; ++marks) if (strcmp(ctx->stage_names[marks], "end") == 0) { ++marks; break; }
+    for (size_t i = 0; i + 1 < marks; ++i) {
+        float ms = 0; BM2_CUDA_OK(cudaEventElapsedTime(&ms, ctx->events[i], ctx->events[i + 1]));
+        ctx->stage_ms.push_back(ms);
+    }
+    ctx->stage_ms.push_back(0.f);
+    ctx->stage_names.resize(marks);
+    return 0;
+}
+
+}  // namespace
+
+// ---- seam 2 entry points -----------------------------------------------------------------------------------
+extern "C" int bm2_collect_smems(bm2_ctx *ctx, const bm2_read_batch *reads, bm2_smem_result *out) {
+    bm2_ctx *ctx_for_error = ctx;
+    if (!ctx || !reads || !out) return 1;
+    BatchState bs;
+    if (run_pipeline(ctx, reads, UPTO_SMEM, bs)) return 1;
+    finish_stage_times(ctx);
+    if (ctx->ensure_host(ctx->h[H_SMEM], (size_t) (bs.n_smem + 1) * sizeof(bm2_smem)) || ctx->ensure_host(ctx->h[H_OUT_OFF], (size_t) (bs.n + 2) * 8)) return 1;
+    if (bs.n_smem) BM2_CUDA_OK(cudaMemcpy(ctx->h[H_SMEM].p, ctx->d[B_SMEM].p, (size_t) bs.n_smem * sizeof(bm2_smem), cudaMemcpyDeviceToHost));
+    if (bs.n > 0) BM2_CUDA_OK(cudaMemcpy(ctx->h[H_OUT_OFF].p, ctx->d[B_READ_SMEM_OFF].p, (size_t) (bs.n + 1) * 8, cudaMemcpyDeviceToHost));
+    else ((int64_t *) ctx->h[H_OUT_OFF].p)[0] = 0;
+    out->n = bs.n_smem; out->smems = (const bm2_smem *) ctx->h[H_SMEM].p; out->read_off = (const int64_t *) ctx->h[H_OUT_OFF].p;
+    return 0;
+}
+
+extern "C" int bm2_seed_chain(bm2_ctx *ctx, const bm2_read_batch *reads, bm2_chain_result *out) {
+    bm2_ctx *ctx_for_error = ctx;
+    if (!ctx || !reads || !out) return 1;
+    BatchState bs;
+    if (run_pipeline(ctx, reads, UPTO_CHAIN, bs)) return 1;
+    finish_stage_times(ctx);
+    if (ctx->ensure_host(ctx->h[H_CHAINS], (size_t) (bs.n_chains + 1) * sizeof(bm2_chain)) ||
+        ctx->ensure_host(ctx->h[H_SEEDS], (size_t) (bs.n_regs + 1) * sizeof(bm2_seed)) || ctx->ensure_host(ctx->h[H_OUT_OFF], (size_t) (bs.n + 2) * 8)) return 1;
+    if (bs.n_chains) BM2_CUDA_OK(cudaMemcpy(ctx->h[H_CHAINS].p, ctx->d[B_CHAINS].p, (size_t) bs.n_chains * sizeof(bm2_chain), cudaMemcpyDeviceToHost));
+    if (bs.n_regs) BM2_CUDA_OK(cudaMemcpy(ctx->h[H_SEEDS].p, ctx->d[B_SEEDS].p, (size_t) bs.n_regs * sizeof(bm2_seed), cudaMemcpyDeviceToHost));
+    if (bs.n > 0) {
+        const size_t sc = al((size_t) (bs.n + 2) * 8);
+        BM2_CUDA_OK(cudaMemcpy(ctx->h[H_OUT_OFF].p, (char *) ctx->d[B_SCAN].p + sc, (size_t) (bs.n + 1) * 8, cudaMemcpyDeviceToHost));
+    } else ((int64_t *) ctx->h[H_OUT_OFF].p)[0] = 0;
+    out->n_chains = bs.n_chains; out->n_seeds = bs.n_regs; out->chains = (const bm2_chain *) ctx->h[H_CHAINS].p;
+    out->seeds = (const bm2_seed *) ctx->h[H_SEEDS].p; out->read_off = (const int64_t *) ctx->h[H_OUT_OFF].p;
+    return 0;
+}
+
+extern "C" int bm2_seed_chain_extend(bm2_ctx *ctx, const bm2_read_batch *reads, bm2_reg_result *out) {
+    if (!ctx || !reads || !out) return 1;
+    BatchState bs;
+    if (run_pipeline(ctx, reads, UPTO_REGS, bs)) return 1;
+    finish_stage_times(ctx);
+    if (bs.n <= 0) {
+        if (ctx->ensure_host(ctx->h[H_OUT_OFF], 16) || ctx->ensure_host(ctx->h[H_OUT_REGS], sizeof(bm2_alnreg_t))) return 1;
+        ((int64_t *) ctx->h[H_OUT_OFF].p)[0] = 0;
+    }
+    out->n = bs.n_out; out->regs = (const bm2_alnreg_t *) ctx->h[H_OUT_REGS].p; out->read_off = (const int64_t *) ctx->h[H_OUT_OFF].p;
+    return 0;
+}
+
 extern "C" int bm2_last_stage_ms(const bm2_ctx *ctx, const char *const **names, const float **ms, int *n) {
     if (!ctx) return 1;
-    *names = ctx->stage_names.data(); *ms = ctx->stage_ms.data(); *n = (int) ctx->stage_ms.size();
+    *names = ctx->stage_names.data(); *ms = ctx->stage_ms.data();
+    *n = (int) (ctx->stage_ms.size() < ctx->stage_names.size() ? ctx->stage_ms.size() : ctx->stage_names.size());
+    return 0;
+}
+
+extern "C" int bm2_last_counters(const bm2_ctx *ctx, unsigned long long *v, int n) {
+    if (!ctx || n < 5) return 1;
+    v[0] = ctx->last_n_ext; v[1] = ctx->last_n_lf; v[2] = ctx->last_cells; v[3] = ctx->last_n_retry[0]; v[4] = ctx->last_n_retry[1];
     return 0;
 }

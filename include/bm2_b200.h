@@ -189,6 +189,10 @@ int bm2_seed_chain_extend(bm2_ctx *ctx, const bm2_read_batch *reads, bm2_reg_res
 
 /* Per-stage device times (ms, CUDA events) of the last seam-2 call; names in `names`. */
 int bm2_last_stage_ms(const bm2_ctx *ctx, const char *const **names, const float **ms, int *n);
+/* Work counters of the last seam-2 call: v[0] interval extensions (128 algorithmic bytes each),
+ * v[1] LF steps of the SA walk (64 B each), v[2] banded DP cells, v[3]/v[4] left/right jobs re-run
+ * with the doubled band.  n >= 5. */
+int bm2_last_counters(const bm2_ctx *ctx, unsigned long long *v, int n);
 
 #ifdef __cplusplus
 }
