@@ -100,6 +100,17 @@ def reference_bsw_jobs(work, fa):
     return g, st
 
 
+def bsw_check(got, ref_out):
+    """score/qle/tle/max_off exact; gscore/gtle exact where the reference's gscore > 0.  With gscore <= 0 the
+    reference's SIMD kernels return 0 or -1 depending on the lane neighbours (3 of 906 530 jobs here) and its
+    only consumer tests `gscore <= 0` (src/bwamem.cpp:2498, :2715)."""
+    for k, f in ((0, "score"), (1, "tle"), (3, "qle"), (5, "max_off")):
+        assert np.array_equal(got[f], ref_out[:, k]), f"bench workload: {f} differs from the reference"
+    pos = ref_out[:, 4] > 0
+    assert np.array_equal(got["gscore"][pos], ref_out[pos, 4]) and np.array_equal(got["gtle"][pos], ref_out[pos, 2])
+    assert np.all(got["gscore"][~pos] <= 0)
+
+
 def run_bsw(args, rank, world):
     import torch
     pkg = load_package()
@@ -144,8 +155,7 @@ def run_bsw(args, rank, world):
     torch.cuda.synchronize()
     # parity spot check of the bench workload itself (first replica) against the reference outputs
     got = d_pairs.cpu().numpy().view(capi.PAIR_DT)[:n0]
-    for k, f in enumerate(("score", "tle", "gtle", "qle", "gscore", "max_off")):
-        assert np.array_equal(got[f], g["out"][:, k]), f"bench workload: {f} differs from the reference"
+    bsw_check(got, g["out"])
     d_cells.zero_()
     sampler = ClockSampler(dev); sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -204,6 +214,173 @@ def run_bsw(args, rank, world):
     return out
 
 
+def prepare_pipeline_inputs(work, ref_bp, n_pairs, seed):
+    """Synthetic genome indexed by the reference binary + vectorised 2x151 read pairs (cached in `work`)."""
+    load_package()
+    from bwa_mem2_b200 import synth
+    os.makedirs(work, exist_ok=True)
+    fa = os.path.join(work, "ref.fa")
+    if not os.path.exists(os.path.join(work, "reads.npy")):
+        ctg = synth.make_reference(ref_bp, seed=seed, n_contigs=max(4, min(24, ref_bp // 25_000_000)))
+        synth.write_fasta(fa, ctg)
+        t0 = time.time()
+        subprocess.check_call([_refbin("bwa-mem2"), "index", fa], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        sys.stderr.write(f"[bench] reference index of {ref_bp} bp built in {time.time() - t0:.1f}s\n")
+        r1, r2 = synth.make_pairs_fast(ctg, n_pairs, seed=seed + 1)
+        reads = np.empty((2 * n_pairs, r1.shape[1]), np.uint8); reads[0::2] = r1; reads[1::2] = r2
+        synth.write_fastq_fast(os.path.join(work, "r1.fq"), r1); synth.write_fastq_fast(os.path.join(work, "r2.fq"), r2)
+        np.save(os.path.join(work, "reads.npy"), reads)
+    return fa
+
+
+def reference_hotpath(work, fa, n_pairs_sample, threads, steps=1, warmup=0):
+    """reads/s of the unmodified reference's worker_bwt + worker_aln (ref_driver BM2_MODE=hotpath) on the first
+    n_pairs_sample pairs."""
+    r1 = os.path.join(work, "r1.fq"); r2 = os.path.join(work, "r2.fq")
+    s1 = os.path.join(work, f"s1_{n_pairs_sample}.fq"); s2 = os.path.join(work, f"s2_{n_pairs_sample}.fq")
+    if not os.path.exists(s1):
+        rec = os.path.getsize(r1) // (np.load(os.path.join(work, "reads.npy"), mmap_mode="r").shape[0] // 2)
+        for src, dst in ((r1, s1), (r2, s2)):
+            with open(src, "rb") as f, open(dst, "wb") as o:
+                o.write(f.read(rec * n_pairs_sample))
+    vals = []
+    for i in range(warmup + steps):
+        stats = os.path.join(work, "stats_ref.json")
+        env = dict(os.environ, BM2_MODE="hotpath", BM2_STATS=stats)
+        subprocess.check_call([_refbin("ref_driver"), "mem", "-t", str(threads), "-K", "1000000000", fa, s1, s2],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
+        st = json.load(open(stats))
+        if i >= warmup:
+            vals.append(st["reads"] / (st["t_bwt"] + st["t_aln"]))
+    return float(np.mean(vals)), st
+
+
+def run_pipeline(args, rank, world):
+    import torch
+    pkg = load_package()
+    capi = pkg.capi
+    import oracle_lib as ol
+    dev = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(dev)
+    work = os.path.join(tempfile.gettempdir(), f"bm2_bench_pipe_{args.ref_mbp}_{args.pairs}")
+    if rank == 0:
+        prepare_pipeline_inputs(work, args.ref_mbp * 1_000_000, args.pairs, seed=21)
+    if world > 1:
+        torch.distributed.barrier()
+    fa = os.path.join(work, "ref.fa")
+    reads = np.load(os.path.join(work, "reads.npy"))
+    if rank:   # weak scaling: every rank aligns its own batch (a rotation of the same read set)
+        reads = np.roll(reads, 2 * 1000 * rank, axis=0)
+    n = reads.shape[0]
+    codes = reads.reshape(-1); offs = (np.arange(n + 1, dtype=np.int64) * reads.shape[1])
+    index = capi.Index(fa)
+    ctx = capi.Context(dev, index=index)
+    # parity of the bench workload itself: a slice against the oracle, every field of every reg
+    ns = 4000
+    got, go = ctx.seed_chain_extend(codes[:ns * reads.shape[1]], offs[:ns + 1])
+    want, wo, _, rc = ol.seed_chain_extend(index, ctx.opt, codes[:ns * reads.shape[1]], offs[:ns + 1])
+    assert rc == 0 and np.array_equal(go, wo) and got.tobytes() == want.tobytes(), "bench workload differs from the oracle"
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    d_codes = torch.from_numpy(codes).cuda(); d_offs = torch.from_numpy(offs).cuda()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(args.warmup):
+        ctx.seed_chain_extend_resident(codes, offs, d_codes.data_ptr(), d_offs.data_ptr(), False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev); sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_acc = {}; cnt = None
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for a, b in evs:
+        flush.fill_(1)
+        a.record(stream)
+        n_regs = ctx.seed_chain_extend_resident(codes, offs, d_codes.data_ptr(), d_offs.data_ptr(), False)
+        b.record(stream)
+        for k, v in ctx.stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / args.steps
+        cnt = ctx.counters()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ms_step = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    if world > 1:
+        t = torch.tensor([ms_step], device="cuda"); torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_step = float(t.item())
+    value = world * n / (ms_step * 1e-3)
+    # e2e through the host C ABI (pinned host reads in, regs out to pinned host memory)
+    ctx.set_stream(None)
+    h_codes = torch.from_numpy(codes.copy()).pin_memory(); h_offs = torch.from_numpy(offs.copy()).pin_memory()
+    regs, ro = ctx.seed_chain_extend(h_codes.numpy(), h_offs.numpy(), copy=False)
+    n_out = len(regs)
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        regs, ro = ctx.seed_chain_extend(h_codes.numpy(), h_offs.numpy(), copy=False)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda"); torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        smem_ms = stage_acc.get("smem", 0.0)
+        alg_bytes = cnt["n_ext"] * 128.0
+        achieved = alg_bytes / (smem_ms * 1e-3) / 1e9 if smem_ms > 0 else 0.0
+        bsw_ms = stage_acc.get("bsw_left", 0.0) + stage_acc.get("bsw_right", 0.0)
+        nt = host_threads()
+        sample_pairs = min(args.pairs, 100_000)
+        cpu_v, cpu_st = reference_hotpath(work, fa, sample_pairs, nt)
+        out = {"metric": "paired 151bp reads/s (seed+chain+extend hot path: SMEM, SA lookup, chaining, BSW, post-filter)", "value": value,
+               "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/int16", "data": "synthetic",
+               "config": {"workload": f"config[2]-like: full GPU pipeline, {n} reads/step/GPU (2x151 bp pairs, 1% subs, 25% reads with an indel, "
+                                      f"1% garbage) vs {args.ref_mbp} Mbp synthetic reference (repeat families, N runs; index built by the reference "
+                                      f"binary inside the bench, which bounds the genome size)",
+                          "l2": "256 MB flush between steps; FM-index %d MB" % (index.desc.reference_seq_len // 64 * 64 // 1_000_000),
+                          "regs_per_step": int(n_regs)},
+               "e2e": {"value": world * n / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(codes.nbytes + offs.nbytes),
+                       "d2h_bytes_per_step": int(n_out * capi.REG_DT.itemsize + offs.nbytes)},
+               "gpu_launches": 42 * args.steps,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                            "kernel": "smem_kernel", "note": "algorithmic bytes = 128 B (two 64-B Occ checkpoints) x interval extensions counted by the kernel; "
+                                                             "peak = MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "of fallback",
+                            "extensions_per_read": cnt["n_ext"] / n, "kernel_ms": smem_ms},
+               "stages_ms": {k: round(v, 3) for k, v in stage_acc.items()},
+               "bsw": {"gcups": cnt["cells"] / (bsw_ms * 1e-3) / 1e9 if bsw_ms > 0 else None, "cells_per_step": int(cnt["cells"]),
+                       "retry_left": int(cnt["retry_left"]), "retry_right": int(cnt["retry_right"])},
+               "cpu_baseline": {"value": cpu_v, "unit": "reads/s", "cores": nt, "kind": "reference",
+                                "sample": f"first {2 * sample_pairs} reads of the same workload, worker_bwt+worker_aln of the unmodified reference "
+                                          f"({_isa()}), {nt} threads"},
+               "clocks": clocks, "wall_s": wall}
+    ctx.close(); index.close()
+    return out
+
+
+def run_reference_pipeline(args, rank, world):
+    if rank != 0:
+        return None
+    work = os.path.join(tempfile.gettempdir(), f"bm2_bench_pipe_{args.ref_mbp}_{args.pairs}")
+    fa = prepare_pipeline_inputs(work, args.ref_mbp * 1_000_000, args.pairs, seed=21)
+    nt = host_threads()
+    v, st = reference_hotpath(work, fa, args.pairs, nt, steps=args.steps, warmup=args.warmup)
+    n = 2 * args.pairs
+    return {"impl": "reference", "metric": "paired 151bp reads/s (seed+chain+extend hot path)", "value": v, "unit": "reads/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64/int16", "data": "synthetic",
+            "config": {"workload": f"worker_bwt + worker_aln of the unmodified reference ({_isa()}) on {n} synthetic 2x151 reads vs {args.ref_mbp} Mbp "
+                                   f"synthetic reference (same inputs as the GPU arm)"},
+            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": nt, "kind": "reference", "sample": f"{n} reads per step, kt_for over {nt} threads"},
+            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path, all host threads, bounded sample."""
     if rank != 0:
@@ -237,14 +414,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bsw", choices=["bsw", "pipeline"])
-    ap.add_argument("--ref-mbp", type=int, default=10)
-    ap.add_argument("--pairs", type=int, default=50_000)
+    ap.add_argument("--workload", default="pipeline", choices=["bsw", "pipeline"])
+    ap.add_argument("--ref-mbp", type=int, default=100)
+    ap.add_argument("--pairs", type=int, default=500_000)
     ap.add_argument("--bsw-jobs", type=int, default=4_000_000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
-        out = run_reference(args, rank, world)
+        out = run_reference_pipeline(args, rank, world) if args.workload == "pipeline" else run_reference(args, rank, world)
         if rank == 0:
             print(json.dumps(out))
         return
@@ -252,7 +429,7 @@ def main():
         import torch, torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         dist.init_process_group("nccl")
-    out = run_bsw(args, rank, world)
+    out = run_pipeline(args, rank, world) if args.workload == "pipeline" else run_bsw(args, rank, world)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -55,7 +55,7 @@ class RegResult(C.Structure):
     _fields_ = [("n", C.c_int64), ("regs", C.c_void_p), ("read_off", C.c_void_p)]
 
 
-EXPORTS = ["bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
+EXPORTS = ["bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
            "bm2_last_error", "bm2_extend_pairs", "bm2_extend_pairs_device", "bm2_collect_smems", "bm2_seed_chain",
            "bm2_seed_chain_extend", "bm2_last_stage_ms"]
 
@@ -201,6 +201,14 @@ class Context:
         lib().bm2_int_pipe_gops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         self._check(lib().bm2_int_pipe_gops(self._ctx, C.byref(v)), "bm2_int_pipe_gops")
         return v.value
+
+    def seed_chain_extend_resident(self, codes, offsets, d_codes_ptr, d_offsets_ptr, copy_out=False):
+        rb, keep = self._batch(codes, offsets)
+        res = RegResult()
+        lib().bm2_seed_chain_extend_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        self._check(lib().bm2_seed_chain_extend_resident(self._ctx, C.byref(rb), d_codes_ptr, d_offsets_ptr, int(copy_out), C.byref(res)),
+                    "bm2_seed_chain_extend_resident")
+        return res.n
 
     def counters(self):
         v = (C.c_ulonglong * 5)()

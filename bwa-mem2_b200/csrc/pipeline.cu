@@ -342,7 +342,8 @@ struct BatchState {       // host-visible sizes of the batch in flight
     int n = 0, max_len = 0; int64_t n_smem = 0, n_slots = 0, n_chains = 0, n_regs = 0, n_left = 0, n_right = 0, n_out = 0;
 };
 
-int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &bs) {
+int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &bs, const uint8_t *ext_codes = nullptr,
+                 const int64_t *ext_offs = nullptr, bool copy_out = true) {
     bm2_ctx *ctx_for_error = ctx;
     if (!ctx->idx.loaded) { bm2_set_error(ctx, "seam 2 needs a context created with an index"); return 1; }
     BM2_CUDA_OK(cudaSetDevice(ctx->device));
@@ -365,12 +366,15 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     Stages sg = { ctx, ctx->events, ctx->stage_names };
     if (sg.mark("h2d")) return 1;
 
-    if (ctx->ensure(ctx->d[B_CODES], (size_t) total + 16) || ctx->ensure(ctx->d[B_OFFS], (size_t) (n + 1) * 8) ||
-        ctx->ensure(ctx->d[B_CNT], sizeof(Counters))) return 1;
-    BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[B_CODES].p, rb->codes, (size_t) total, cudaMemcpyHostToDevice, st));
-    BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[B_OFFS].p, rb->offsets, (size_t) (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (ctx->ensure(ctx->d[B_CNT], sizeof(Counters))) return 1;
+    const uint8_t *d_codes = ext_codes; const int64_t *d_offs = ext_offs;
+    if (!ext_codes || !ext_offs) {
+        if (ctx->ensure(ctx->d[B_CODES], (size_t) total + 16) || ctx->ensure(ctx->d[B_OFFS], (size_t) (n + 1) * 8)) return 1;
+        BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[B_CODES].p, rb->codes, (size_t) total, cudaMemcpyHostToDevice, st));
+        BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[B_OFFS].p, rb->offsets, (size_t) (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        d_codes = P<uint8_t>(ctx, B_CODES); d_offs = P<int64_t>(ctx, B_OFFS);
+    }
     BM2_CUDA_OK(cudaMemsetAsync(ctx->d[B_CNT].p, 0, sizeof(Counters), st));
-    const uint8_t *d_codes = P<uint8_t>(ctx, B_CODES); const int64_t *d_offs = P<int64_t>(ctx, B_OFFS);
     Counters *d_cnt = P<Counters>(ctx, B_CNT);
     Counters h_cnt;
 
@@ -556,7 +560,7 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     const int64_t n_out = ((const int64_t *) ctx->h[H_OUT_OFF].p)[n];
     bs.n_out = n_out;
     if (ctx->ensure_host(ctx->h[H_OUT_REGS], (size_t) (n_out + 1) * sizeof(bm2_alnreg_t))) return 1;
-    if (n_out) BM2_CUDA_OK(cudaMemcpyAsync(ctx->h[H_OUT_REGS].p, ctx->d[B_OUT].p, (size_t) n_out * sizeof(bm2_alnreg_t), cudaMemcpyDeviceToHost, st));
+    if (n_out && copy_out) BM2_CUDA_OK(cudaMemcpyAsync(ctx->h[H_OUT_REGS].p, ctx->d[B_OUT].p, (size_t) n_out * sizeof(bm2_alnreg_t), cudaMemcpyDeviceToHost, st));
     if (sg.mark("end")) return 1;
     BM2_CUDA_OK(cudaStreamSynchronize(st));
     BM2_CUDA_OK(cudaGetLastError());
@@ -625,6 +629,16 @@ extern "C" int bm2_seed_chain_extend(bm2_ctx *ctx, const bm2_read_batch *reads, 
         ((int64_t *) ctx->h[H_OUT_OFF].p)[0] = 0;
     }
     out->n = bs.n_out; out->regs = (const bm2_alnreg_t *) ctx->h[H_OUT_REGS].p; out->read_off = (const int64_t *) ctx->h[H_OUT_OFF].p;
+    return 0;
+}
+
+extern "C" int bm2_seed_chain_extend_resident(bm2_ctx *ctx, const bm2_read_batch *reads, const uint8_t *d_codes, const int64_t *d_offsets,
+                                              int copy_out, bm2_reg_result *out) {
+    if (!ctx || !reads || !out || !d_codes || !d_offsets) return 1;
+    BatchState bs;
+    if (run_pipeline(ctx, reads, UPTO_REGS, bs, d_codes, d_offsets, copy_out != 0)) return 1;
+    finish_stage_times(ctx);
+    out->n = bs.n_out; out->regs = copy_out ? (const bm2_alnreg_t *) ctx->h[H_OUT_REGS].p : nullptr; out->read_off = (const int64_t *) ctx->h[H_OUT_OFF].p;
     return 0;
 }
 

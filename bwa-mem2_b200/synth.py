@@ -191,3 +191,70 @@ if __name__ == "__main__":
     r1, r2 = make_pairs(ctg, a.pairs, seed=a.seed + 1)
     write_fastq(os.path.join(a.out, "r1.fq"), r1, "p")
     write_fastq(os.path.join(a.out, "r2.fq"), r2, "p")
+
+
+def make_pairs_fast(contigs, n_pairs: int, read_len: int = 151, seed: int = 2, ins_mean: float = 400.0, ins_sd: float = 40.0,
+                    sub: float = 0.01, indel_frac: float = 0.25, nrate: float = 0.001, garbage: float = 0.01):
+    """Vectorised generator for large read sets (1M+ pairs): same error model as make_pairs except that
+    each read carries at most one indel (1..4 bp) with probability `indel_frac`.  Returns (r1, r2)."""
+    rng = np.random.default_rng(seed)
+    lens = np.array([len(c) for _, c in contigs], dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    genome = np.concatenate([c for _, c in contigs])
+    cid = rng.choice(len(contigs), size=n_pairs, p=lens / lens.sum())
+    isz = np.clip(rng.normal(ins_mean, ins_sd, n_pairs).astype(np.int64), read_len + 10, None)
+    isz = np.minimum(isz, lens[cid] - 20)
+    pos = (rng.random(n_pairs) * (lens[cid] - isz - 8)).astype(np.int64) + starts[cid]
+    ext = read_len + 8
+    ar = np.arange(ext, dtype=np.int64)
+    fwd = genome[pos[:, None] + ar[None, :]]                                   # [n, ext] from the fragment start
+    rev_idx = (pos + isz - 1)[:, None] - ar[None, :]
+    rev = _COMP[genome[np.maximum(rev_idx, 0)]]                                # reverse complement from the fragment end
+    flip = rng.random(n_pairs) < 0.5
+    a = np.where(flip[:, None], rev, fwd); b = np.where(flip[:, None], fwd, rev)
+
+    def mutate(t):
+        n = t.shape[0]
+        j = np.arange(read_len, dtype=np.int64)[None, :]
+        has = rng.random(n) < indel_frac
+        is_del = rng.random(n) < 0.5
+        p = rng.integers(10, read_len - 10, n)[:, None]
+        d = rng.integers(1, 5, n)[:, None]
+        # deletion: skip d template bases at p; insertion: d random bases at p
+        src_del = j + (j >= p) * d
+        src_ins = np.where(j < p, j, np.maximum(j - d, p))
+        src = np.where((has & is_del)[:, None], src_del, np.where((has & ~is_del)[:, None], src_ins, j))
+        out = np.take_along_axis(t, src, axis=1)
+        insmask = (has & ~is_del)[:, None] & (j >= p) & (j < p + d)
+        out = np.where(insmask, rng.integers(0, 4, out.shape, dtype=np.uint8), out)
+        m = (rng.random(out.shape) < sub) & (out < 4)
+        out = np.where(m, (out + rng.integers(1, 4, out.shape, dtype=np.uint8)) & 3, out)
+        out = np.where(rng.random(out.shape) < nrate, 4, out)
+        return out.astype(np.uint8)
+
+    r1 = mutate(a); r2 = mutate(b)
+    g = rng.random(n_pairs) < garbage
+    ng = int(g.sum())
+    if ng:
+        r1[g] = rng.integers(0, 4, (ng, read_len), dtype=np.uint8)
+        r2[g] = rng.integers(0, 4, (ng, read_len), dtype=np.uint8)
+    return r1, r2
+
+
+def write_fastq_fast(path: str, reads: np.ndarray, prefix: bytes = b"p"):
+    """Vectorised FASTQ writer: fixed-width names <prefix>%09d, constant quality 'I'."""
+    n, L = reads.shape
+    name_w = 1 + len(prefix) + 9 + 1
+    rec = np.empty((n, name_w + L + 1 + 2 + L + 1), dtype=np.uint8)
+    rec[:, 0] = ord("@")
+    rec[:, 1:1 + len(prefix)] = np.frombuffer(prefix, np.uint8)
+    ids = np.arange(n, dtype=np.int64)
+    for k in range(9):
+        rec[:, 1 + len(prefix) + k] = ord("0") + (ids // 10 ** (8 - k)) % 10
+    rec[:, name_w - 1] = 10
+    rec[:, name_w:name_w + L] = _ALPHA[reads]
+    rec[:, name_w + L] = 10
+    rec[:, name_w + L + 1] = ord("+"); rec[:, name_w + L + 2] = 10
+    rec[:, name_w + L + 3:name_w + 2 * L + 3] = ord("I")
+    rec[:, -1] = 10
+    rec.tofile(path)

@@ -187,6 +187,13 @@ int bm2_seed_chain(bm2_ctx *ctx, const bm2_read_batch *reads, bm2_chain_result *
  * left by mem_kernel2_core (src/bwamem.cpp:1093-1172). */
 int bm2_seed_chain_extend(bm2_ctx *ctx, const bm2_read_batch *reads, bm2_reg_result *out);
 
+/* Device-resident variant for throughput measurement: `reads` still carries the HOST offsets (sizes
+ * are needed on the host) but codes/offsets are taken from DEVICE memory (`d_codes`, `d_offsets`,
+ * already uploaded by the caller), and the final regs stay on the device unless `copy_out` != 0
+ * (out->regs is then NULL; out->n and out->read_off are valid). */
+int bm2_seed_chain_extend_resident(bm2_ctx *ctx, const bm2_read_batch *reads, const uint8_t *d_codes,
+                                   const int64_t *d_offsets, int copy_out, bm2_reg_result *out);
+
 /* Per-stage device times (ms, CUDA events) of the last seam-2 call; names in `names`. */
 int bm2_last_stage_ms(const bm2_ctx *ctx, const char *const **names, const float **ms, int *n);
 /* Work counters of the last seam-2 call: v[0] interval extensions (128 algorithmic bytes each),
