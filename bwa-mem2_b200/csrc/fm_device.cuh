@@ -24,6 +24,11 @@ struct FmIndexView {
 
 struct FmIv { int64_t k, l, s; };
 
+// count[] lives in kernel-parameter space: select instead of indexing dynamically (no local-memory copy)
+BM2_HD int64_t fm_count(const FmIndexView &fm, int a) {
+    return a == 0 ? fm.count[0] : a == 1 ? fm.count[1] : a == 2 ? fm.count[2] : a == 3 ? fm.count[3] : fm.count[4];
+}
+
 struct FmOcc4 { int64_t c[4]; };
 
 // Occ(b, pp) for the four bases from one 64-byte checkpoint (GET_OCC, src/FMI_search.h:66-73).
@@ -46,15 +51,26 @@ BM2_HD FmOcc4 fm_occ4(const FmIndexView &fm, int64_t pp) {
 }
 
 // backwardExt (src/FMI_search.cpp:1025-1052): 2 checkpoints = 128 algorithmic bytes.
+// Only base `a` and ONE other base are counted: the four per-base interval sizes and the sentinel sum
+// to s (every BWT row of [k, k+s) holds one of the four bases or the sentinel), so
+//   l_0 = l + s - s_0,  l_1 = l + s - s_0 - s_1,  l_2 = l + [sentinel] + s_3,  l_3 = l + [sentinel]
+// are the reference's l[a] exactly, with half the popcounts and 8-byte instead of 16-byte loads.
 BM2_HD FmIv fm_backward_ext(const FmIndexView &fm, const FmIv &in, int a) {
-    FmOcc4 o1 = fm_occ4(fm, in.k), o2 = fm_occ4(fm, in.k + in.s);
-    int64_t s0 = o2.c[0] - o1.c[0], s1 = o2.c[1] - o1.c[1], s2 = o2.c[2] - o1.c[2], s3 = o2.c[3] - o1.c[3];
-    int64_t l3 = in.l + ((in.k <= fm.sentinel && in.k + in.s > fm.sentinel) ? 1 : 0);
-    int64_t l2 = l3 + s3, l1 = l2 + s2, l0 = l1 + s1;
+    const int64_t p1 = in.k, p2 = in.k + in.s;
+    const bm2_cp_occ *e1 = fm.cp_occ + (p1 >> 6), *e2 = fm.cp_occ + (p2 >> 6);
+    const int b2 = a == 1 ? 0 : (a == 2 ? 3 : a);                  // the one other base that is needed
+    const int y1 = (int) (p1 & 63), y2 = (int) (p2 & 63);
+    const uint64_t m1 = y1 ? ~0ULL << (64 - y1) : 0ULL, m2 = y2 ? ~0ULL << (64 - y2) : 0ULL;
+    const int64_t o1a = (int64_t) BM2_LDG64(&e1->cp_count[a]) + BM2_POPC64(BM2_LDG64(&e1->one_hot_bwt_str[a]) & m1);
+    const int64_t o2a = (int64_t) BM2_LDG64(&e2->cp_count[a]) + BM2_POPC64(BM2_LDG64(&e2->one_hot_bwt_str[a]) & m2);
+    const int64_t o1b = (int64_t) BM2_LDG64(&e1->cp_count[b2]) + BM2_POPC64(BM2_LDG64(&e1->one_hot_bwt_str[b2]) & m1);
+    const int64_t o2b = (int64_t) BM2_LDG64(&e2->cp_count[b2]) + BM2_POPC64(BM2_LDG64(&e2->one_hot_bwt_str[b2]) & m2);
+    const int64_t sa = o2a - o1a, sb = o2b - o1b;
+    const int64_t sent = (in.k <= fm.sentinel && in.k + in.s > fm.sentinel) ? 1 : 0;
     FmIv r;
-    r.k = fm.count[a] + o1.c[a];
-    r.l = a == 0 ? l0 : a == 1 ? l1 : a == 2 ? l2 : l3;
-    r.s = a == 0 ? s0 : a == 1 ? s1 : a == 2 ? s2 : s3;
+    r.k = fm_count(fm, a) + o1a;
+    r.s = sa;
+    r.l = a == 0 ? in.l + in.s - sa : a == 1 ? in.l + in.s - sb - sa : a == 2 ? in.l + sent + sb : in.l + sent;
     return r;
 }
 
@@ -78,7 +94,7 @@ BM2_HD int64_t fm_sa_of_row(const FmIndexView &fm, int64_t r, int *lf_steps) {
         const uint64_t mask = yy ? ~0ULL << (64 - yy) : 0ULL;
         uint64_t cb = b == 0 ? cnt[0] : b == 1 ? cnt[1] : b == 2 ? cnt[2] : cnt[3];
         uint64_t bb = b == 0 ? bits[0] : b == 1 ? bits[1] : b == 2 ? bits[2] : bits[3];
-        r = fm.count[b] + (int64_t) cb + BM2_POPC64(bb & mask);
+        r = fm_count(fm, b) + (int64_t) cb + BM2_POPC64(bb & mask);
         ++steps;
     }
     if (lf_steps) *lf_steps += (int) steps;
@@ -127,7 +143,7 @@ BM2_HD void fm_smem_read(const FmIndexView &fm, const uint8_t *q, int len, const
                 next_x = x + 1;
                 const int a = q[x];
                 if (a > 3) { st = ST_SEARCH_END; num_prev = 0; continue; }
-                cur.m = x; cur.n = x; cur.k = fm.count[a]; cur.l = fm.count[3 - a]; cur.s = fm.count[a + 1] - fm.count[a];
+                cur.m = x; cur.n = x; cur.k = fm_count(fm, a); cur.l = fm_count(fm, 3 - a); cur.s = fm_count(fm, a + 1) - cur.k;
                 num_prev = 0; j = x + 1; st = ST_FWD;
             } else if (st == ST_FWD) {
                 if (j >= len) { st = ST_FWD_END; continue; }
@@ -173,7 +189,7 @@ BM2_HD void fm_smem_read(const FmIndexView &fm, const uint8_t *q, int len, const
                 next_x = x + 1;
                 const int a = q[x];
                 if (a > 3) { x = next_x; continue; }
-                cur.m = x; cur.n = x; cur.k = fm.count[a]; cur.l = fm.count[3 - a]; cur.s = fm.count[a + 1] - fm.count[a];
+                cur.m = x; cur.n = x; cur.k = fm_count(fm, a); cur.l = fm_count(fm, 3 - a); cur.s = fm_count(fm, a + 1) - cur.k;
                 j = x + 1; st = ST_P3_FWD;
             } else if (st == ST_P3_FWD) {
                 if (j >= len) { x = next_x; st = ST_P3_BEGIN; continue; }
@@ -186,6 +202,7 @@ BM2_HD void fm_smem_read(const FmIndexView &fm, const uint8_t *q, int len, const
             }
         }
         // ---- the single extension call site -----------------------------------------------------------
+        BM2_SYNCWARP();                          // re-converge the warp: all lanes take the two checkpoint loads together
         FmIv r = fm_backward_ext(fm, req, req_base);
         ++n_ext;
         if (req_fwd) { int64_t t = r.k; r.k = r.l; r.l = t; }

@@ -88,7 +88,7 @@ struct SmemAppend {
 };
 
 // A. one read per thread (grid-stride), private prev/reseed stripes per THREAD
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 smem_kernel(FmIndexView fm, SmemParams sp, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, int n_reads, int stripe,
             FmPrev *prev_all, int32_t *reseed_all, bm2_smem *out, unsigned long long cap, Counters *cnt)
 {
@@ -156,10 +156,12 @@ struct ChainBufs {
 
 __global__ void __launch_bounds__(128)
 chain_kernel(ContigView cv, ChainParams cp, const bm2_smem *__restrict__ sm, const int64_t *__restrict__ read_smem_off,
-             const int64_t *__restrict__ slot_off, const int64_t *__restrict__ sa, const int64_t *__restrict__ offs, int n_reads, ChainBufs b)
+             const int64_t *__restrict__ slot_off, const int64_t *__restrict__ sa, const int64_t *__restrict__ offs, int n_reads,
+             const int32_t *__restrict__ perm, ChainBufs b)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_reads) return;
+    const int r = perm[t];          // reads ordered by work so that the lanes of a warp run similar trip counts
     int nk = 0, ns = 0, nl = 0, nr = 0;
     const int64_t sb = read_smem_off[r], se = read_smem_off[r + 1];
     const int len = (int) (offs[r + 1] - offs[r]);
@@ -200,10 +202,11 @@ struct ExtBufs {
 __global__ void __launch_bounds__(128)
 ext_build_kernel(ContigView cv, ExtParams ep, const bm2_chain *__restrict__ chains, const bm2_seed *__restrict__ seeds,
                  const int64_t *__restrict__ chain_off, const int64_t *__restrict__ reg_off, const int64_t *__restrict__ left_off,
-                 const int64_t *__restrict__ right_off, const int64_t *__restrict__ offs, int n_reads, ExtBufs b)
+                 const int64_t *__restrict__ right_off, const int64_t *__restrict__ offs, int n_reads, const int32_t *__restrict__ perm, ExtBufs b)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_reads) return;
+    const int r = perm[t];
     const int64_t c0 = chain_off[r], c1 = chain_off[r + 1];
     if (c1 == c0) return;
     const int64_t g0 = reg_off[r];
@@ -246,11 +249,12 @@ __global__ void __launch_bounds__(128)
 tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs,
             const bm2_chain *__restrict__ chains, const bm2_seed *__restrict__ seeds, const int64_t *__restrict__ chain_off,
             const int64_t *__restrict__ reg_off, int n_reads, bm2_alnreg_t *regs, const int32_t *reg_seed, int32_t *srt2_all, int32_t *he_all,
-            int he_stride, int32_t *n_final)
+            int he_stride, const int32_t *__restrict__ perm, int32_t *n_final)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     int32_t *he = he_all + (size_t) tid * he_stride;
-    for (int r = tid; r < n_reads; r += nthr) {
+    for (int t = tid; t < n_reads; t += nthr) {
+        const int r = perm[t];
         const int64_t c0 = chain_off[r], c1 = chain_off[r + 1], g0 = reg_off[r];
         const int n_reg = (int) (reg_off[r + 1] - g0);
         int m = 0;
@@ -270,6 +274,22 @@ __global__ void regs_gather_kernel(const bm2_alnreg_t *regs, const int64_t *reg_
     for (int64_t k = 0; k < o1 - o0; ++k) out[o0 + k] = regs[g0 + k];
 }
 
+// reads ordered by decreasing work (heavy reads first, similar reads share a warp)
+__global__ void work_keys_slots_kernel(const int64_t *read_smem_off, const int64_t *slot_off, int n, uint32_t *keys, int32_t *vals) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int64_t w = slot_off[read_smem_off[r + 1]] - slot_off[read_smem_off[r]];
+    keys[r] = 0xFFFFFFFFu - (uint32_t) (w > 0x7FFFFFFF ? 0x7FFFFFFF : w);
+    vals[r] = r;
+}
+__global__ void work_keys_off_kernel(const int64_t *off, int n, uint32_t *keys, int32_t *vals) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int64_t w = off[r + 1] - off[r];
+    keys[r] = 0xFFFFFFFFu - (uint32_t) (w > 0x7FFFFFFF ? 0x7FFFFFFF : w);
+    vals[r] = r;
+}
+
 __global__ void widen_kernel(const int32_t *in, int n, int64_t *out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];
@@ -283,7 +303,7 @@ namespace {
 enum Buf {
     B_CODES, B_OFFS, B_CNT, B_PREV, B_RESEED, B_SMEM_RAW, B_KEYS_IN, B_KEYS_OUT, B_VALS_IN, B_VALS_OUT, B_CUB, B_SMEM, B_SLOT_CNT,
     B_SLOT_OFF, B_READ_SMEM_OFF, B_SA, B_WSEED, B_WCHAIN, B_ORD, B_SRT, B_KV, B_FIN_CHAIN, B_FIN_SEED, B_PER_READ, B_SCAN, B_CHAINS,
-    B_SEEDS, B_REGS, B_REG_AUX, B_JOBS, B_NW, B_OUT
+    B_SEEDS, B_REGS, B_REG_AUX, B_JOBS, B_NW, B_OUT, B_PERM
 };
 enum HBuf { H_OUT_REGS, H_OUT_OFF, H_SMEM, H_CHAINS, H_SEEDS, H_MISC };
 
@@ -333,6 +353,16 @@ int scan64(bm2_ctx *ctx, const int64_t *in, int64_t *out, int64_t n) {
     cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int) (n + 1));
     if (ctx->ensure(ctx->d[B_CUB], bytes)) return 1;
     BM2_CUDA_OK(cub::DeviceScan::ExclusiveSum(ctx->d[B_CUB].p, bytes, in, out, (int) (n + 1), ctx->stream));
+    return 0;
+}
+
+// sorts (keys, vals) of n reads; result permutation in vals_out
+int sort_work(bm2_ctx *ctx, uint32_t *keys_in, uint32_t *keys_out, int32_t *vals_in, int32_t *vals_out, int n) {
+    bm2_ctx *ctx_for_error = ctx;
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in, keys_out, vals_in, vals_out, n);
+    if (ctx->ensure(ctx->d[B_CUB], bytes)) return 1;
+    BM2_CUDA_OK(cub::DeviceRadixSort::SortPairs(ctx->d[B_CUB].p, bytes, keys_in, keys_out, vals_in, vals_out, n, 0, 32, ctx->stream));
     return 0;
 }
 
@@ -451,8 +481,13 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
             *d_nright = (int32_t *) (prb + 3 * pr), *d_nfinal = (int32_t *) (prb + 4 * pr);
     ChainBufs cb = { P<WSeed>(ctx, B_WSEED), P<WChain>(ctx, B_WCHAIN), P<int32_t>(ctx, B_ORD), P<int32_t>(ctx, B_SRT), P<int32_t>(ctx, B_KV),
                      P<bm2_chain>(ctx, B_FIN_CHAIN), P<bm2_seed>(ctx, B_FIN_SEED), d_nchain, d_nseed, d_nleft, d_nright };
+    if (ctx->ensure(ctx->d[B_PERM], al((size_t) n * 4) * 4)) return 1;
+    uint32_t *wk_in = (uint32_t *) ctx->d[B_PERM].p, *wk_out = (uint32_t *) ((char *) ctx->d[B_PERM].p + al((size_t) n * 4));
+    int32_t *wv_in = (int32_t *) ((char *) ctx->d[B_PERM].p + 2 * al((size_t) n * 4)), *d_perm = (int32_t *) ((char *) ctx->d[B_PERM].p + 3 * al((size_t) n * 4));
+    work_keys_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(P<int64_t>(ctx, B_READ_SMEM_OFF), P<int64_t>(ctx, B_SLOT_OFF), n, wk_in, wv_in);
+    if (sort_work(ctx, wk_in, wk_out, wv_in, d_perm, n)) return 1;
     chain_kernel<<<(n + 127) / 128, 128, 0, st>>>(pv.cv, pv.cp, P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_READ_SMEM_OFF),
-                                                  P<int64_t>(ctx, B_SLOT_OFF), P<int64_t>(ctx, B_SA), d_offs, n, cb);
+                                                  P<int64_t>(ctx, B_SLOT_OFF), P<int64_t>(ctx, B_SA), d_offs, n, d_perm, cb);
 
     // ---- E. scans + compaction ------------------------------------------------------------------------------
     if (sg.mark("compact")) return 1;
@@ -505,8 +540,10 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     BswOut *d_outs = (BswOut *) jb;
     bm2_alnreg_t *d_regs = P<bm2_alnreg_t>(ctx, B_REGS);
     ExtBufs eb = { d_regs, d_reg_chain, d_reg_seed, d_srt, d_left, d_right, d_left_reg, d_right_reg };
+    work_keys_off_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_reg_off, n, wk_in, wv_in);       // work ~ regs of the read
+    if (sort_work(ctx, wk_in, wk_out, wv_in, d_perm, n)) return 1;
     ext_build_kernel<<<(n + 127) / 128, 128, 0, st>>>(pv.cv, pv.ep, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off, d_reg_off,
-                                                      d_left_off, d_right_off, d_offs, n, eb);
+                                                      d_left_off, d_right_off, d_offs, n, d_perm, eb);
 
     // ---- G/H. extension -----------------------------------------------------------------------------------
     auto phase = [&](const char *name, ExtJobRec *jobs, int32_t *job_reg, int32_t *retry, int64_t nj, int is_right) -> int {
@@ -545,7 +582,7 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     const int he_stride = 2 * (max_len + 2);
     if (ctx->ensure(ctx->d[B_NW], (size_t) blocks_i * 128 * he_stride * 4)) return 1;
     tail_kernel<<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
-                                          d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_nfinal);
+                                          d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_nfinal);
 
     // ---- J. output ---------------------------------------------------------------------------------------
     if (sg.mark("output")) return 1;

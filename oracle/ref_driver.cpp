@@ -254,10 +254,14 @@ static void bsw_dump(int kind, BandedPairWiseSW *self, SeqPair *p, const std::ve
         if (f_bsw) before.assign(p, p + n);                                                                 \
         double t0 = now_s();                                                                                \
         if (g_mode == M_GPU_BSW) {                                                                          \
+            /* one bm2_ctx: calls are serialised by the caller (contract in INTEGRATION.md) */             \
+            static pthread_mutex_t gpu_mu = PTHREAD_MUTEX_INITIALIZER;                                      \
+            pthread_mutex_lock(&gpu_mu);                                                                    \
             make_ctx(NULL, NULL, NULL);                                                                     \
             /* bm2_create(opt=NULL) takes defaults; scoring comes from the reference object */             \
             int rc = p_extend_pairs(g_ctx, (bm2_seqpair *) p, ref, qer, n, w, self->end_bonus);             \
             if (rc) { fprintf(stderr, "[ref_driver] bm2_extend_pairs: %s\n", p_last_error(g_ctx)); exit(3); } \
+            pthread_mutex_unlock(&gpu_mu);                                                                  \
         } else {                                                                                            \
             __real_##MANGLED(self, p, ref, qer, n, nt, w);                                                  \
         }                                                                                                   \
