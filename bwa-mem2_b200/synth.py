@@ -258,3 +258,47 @@ def write_fastq_fast(path: str, reads: np.ndarray, prefix: bytes = b"p"):
     rec[:, name_w + L + 3:name_w + 2 * L + 3] = ord("I")
     rec[:, -1] = 10
     rec.tofile(path)
+
+
+def make_pairs_torch(genome, contig_lens, n_pairs: int, read_len: int = 151, seed: int = 2, ins_mean: float = 400.0, ins_sd: float = 40.0,
+                     sub: float = 0.01, indel_frac: float = 0.25, nrate: float = 0.001, garbage: float = 0.01):
+    """make_pairs_fast on a torch device (multi-Gbp genomes): `genome` uint8 tensor of all contigs concatenated."""
+    import torch
+    dev = genome.device
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    lens = torch.as_tensor(np.asarray(contig_lens, dtype=np.int64), device=dev)
+    starts = torch.cumsum(lens, 0) - lens
+    cid = torch.multinomial(lens.to(torch.float64) / lens.sum(), n_pairs, replacement=True, generator=g)
+    isz = torch.clamp((torch.randn(n_pairs, device=dev, generator=g) * ins_sd + ins_mean).to(torch.int64), min=read_len + 10)
+    isz = torch.minimum(isz, lens[cid] - 20)
+    pos = (torch.rand(n_pairs, device=dev, generator=g, dtype=torch.float64) * (lens[cid] - isz - 8).to(torch.float64)).to(torch.int64) + starts[cid]
+    ext = read_len + 8
+    ar = torch.arange(ext, device=dev)
+    fwd = genome[pos[:, None] + ar[None, :]]
+    rev = 3 - genome[torch.clamp((pos + isz - 1)[:, None] - ar[None, :], min=0)]
+    flip = torch.rand(n_pairs, device=dev, generator=g) < 0.5
+    a = torch.where(flip[:, None], rev, fwd); b = torch.where(flip[:, None], fwd, rev)
+
+    def mutate(t):
+        n = t.shape[0]
+        j = torch.arange(read_len, device=dev)[None, :]
+        has = torch.rand(n, device=dev, generator=g) < indel_frac
+        is_del = torch.rand(n, device=dev, generator=g) < 0.5
+        p = torch.randint(10, read_len - 10, (n, 1), device=dev, generator=g)
+        d = torch.randint(1, 5, (n, 1), device=dev, generator=g)
+        src_del = j + (j >= p) * d
+        src_ins = torch.where(j < p, j.expand(n, -1), torch.maximum(j - d, p))
+        src = torch.where((has & is_del)[:, None], src_del, torch.where((has & ~is_del)[:, None], src_ins, j.expand(n, -1)))
+        out = torch.gather(t, 1, src)
+        insmask = (has & ~is_del)[:, None] & (j >= p) & (j < p + d)
+        out = torch.where(insmask, torch.randint(0, 4, out.shape, dtype=torch.uint8, device=dev, generator=g), out)
+        m = torch.rand(out.shape, device=dev, generator=g) < sub
+        out = torch.where(m, (out + torch.randint(1, 4, out.shape, dtype=torch.uint8, device=dev, generator=g)) & 3, out)
+        out = torch.where(torch.rand(out.shape, device=dev, generator=g) < nrate, torch.full_like(out, 4), out)
+        return out
+
+    r1 = mutate(a); r2 = mutate(b)
+    gb = torch.rand(n_pairs, device=dev, generator=g) < garbage
+    r1 = torch.where(gb[:, None], torch.randint(0, 4, r1.shape, dtype=torch.uint8, device=dev, generator=g), r1)
+    r2 = torch.where(gb[:, None], torch.randint(0, 4, r2.shape, dtype=torch.uint8, device=dev, generator=g), r2)
+    return r1.cpu().numpy(), r2.cpu().numpy()
