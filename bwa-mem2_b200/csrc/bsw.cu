@@ -73,15 +73,23 @@ __global__ void bsw_class_off_kernel(const int32_t *class_cnt, int32_t *class_of
 // ---------------------------------------------------------------------------------------------
 // The extension DP of one job (one thread).  `St` abstracts the per-column state storage.
 // ---------------------------------------------------------------------------------------------
-struct SmemPacked {            // H | E<<16 in shared memory, [column][thread]
-    uint32_t *base;            // &sh[threadIdx.x]
-    int stride;                // blockDim.x
-    __device__ __forceinline__ void get(int j, int &h, int &e) const {
-        uint32_t w = base[j * stride];
-        h = (int) (w & 0xFFFFu); e = (int) (w >> 16);
+struct SmemPacked {            // H | E<<16 in shared memory, [column][thread]; explicit shared-space accesses
+    unsigned base;             // shared-window address of &sh[threadIdx.x]
+    unsigned stride;           // blockDim.x * 4 bytes
+    __device__ __forceinline__ uint32_t ldw(int j) const {
+        uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + (unsigned) j * stride)); return w;
     }
-    __device__ __forceinline__ void put(int j, int h, int e) const { base[j * stride] = (uint32_t) h | ((uint32_t) e << 16); }
-    __device__ __forceinline__ bool zero(int j) const { return base[j * stride] == 0u; }
+    __device__ __forceinline__ void stw(int j, uint32_t w) const {
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(base + (unsigned) j * stride), "r"(w) : "memory");
+    }
+    __device__ __forceinline__ void get(int j, int &h, int &e) const { uint32_t w = ldw(j); h = (int) (w & 0xFFFFu); e = (int) (w >> 16); }
+    __device__ __forceinline__ void put(int j, int h, int e) const { stw(j, __byte_perm((uint32_t) h, (uint32_t) e, 0x5410)); }
+    __device__ __forceinline__ bool zero(int j) const { return ldw(j) == 0u; }
+    // row maximum as one signed key: (h << 16) | j  (h < 2^15, j < 2^16)
+    typedef int key_t;
+    static __device__ __forceinline__ key_t key(int h, int j) { return (h << 16) | j; }
+    static __device__ __forceinline__ int key_h(key_t k) { return k >> 16; }
+    static __device__ __forceinline__ int key_j(key_t k) { return k & 0xFFFF; }
 };
 
 struct GmemWide {              // {H,E} int32 in global memory, private stripe per thread
@@ -89,6 +97,10 @@ struct GmemWide {              // {H,E} int32 in global memory, private stripe p
     __device__ __forceinline__ void get(int j, int &h, int &e) const { int2 v = base[j]; h = v.x; e = v.y; }
     __device__ __forceinline__ void put(int j, int h, int e) const { base[j] = make_int2(h, e); }
     __device__ __forceinline__ bool zero(int j) const { int2 v = base[j]; return (v.x | v.y) == 0; }
+    typedef long long key_t;     // 32-bit scores: (h << 32) | j
+    static __device__ __forceinline__ key_t key(int h, int j) { return ((long long) h << 32) | (unsigned) j; }
+    static __device__ __forceinline__ int key_h(key_t k) { return (int) (k >> 32); }
+    static __device__ __forceinline__ int key_j(key_t k) { return (int) (k & 0xFFFFFFFFLL); }
 };
 
 template <class St, class QFetch>
@@ -130,27 +142,34 @@ __device__ __forceinline__ void bsw_extend_one(const St &st, const QFetch &qf, c
         if (beg == 0) { h1 = h0 - (p.o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
         else h1 = 0;
         const int tb = tptr[(long long) i * tstride];
-        const int s_row_amb = tb > 3;
-        int f = 0, m = 0, mj = -1;
+        // score of target base tb against query base q = 0..3 as four signed bytes; q = 4 (or tb > 3) -> -1
+        const uint32_t sb8 = (uint32_t) sb & 0xFFu, sa8 = (uint32_t) sa & 0xFFu;
+        uint32_t tbl = sb8 * 0x01010101u;
+        tbl = tb > 3 ? 0xFFFFFFFFu : ((tbl & ~(0xFFu << (8 * tb))) | (sa8 << (8 * tb)));
+        int f = 0;
+        typename St::key_t mkey = -1;                // (h, j) packed; signed max => last column attaining the row maximum
         int j = beg;
         typename QFetch::Cursor qc = qf.cursor(beg);
 #pragma unroll 4
         for (; j < end; ++j) {
             int hd, e;
             st.get(j, hd, e);
-            int qb = qf.next(qc, j);
-            int s = (qb == tb) ? sa : sb;
-            if (s_row_amb | (qb > 3)) s = -1;
-            int M = hd ? hd + s : 0;
-            int h = max(max(M, e), f);
+            const uint32_t qb = (uint32_t) qf.next(qc, j);
+            // PRMT: byte 0 = tbl[qb] (qb = 4 selects the 0xFF byte of the second operand), bytes 1..3 = its sign
+            int s;     // (inline PTX: the __byte_perm intrinsic masks the sign-replicate bit of the selector nibbles)
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(s) : "r"(tbl), "r"(0xFFFFFFFFu), "r"(qb * 0x1111u + 0x8880u));
+            const int M = hd ? hd + s : 0;
+            const int h = max(max(M, e), f);
             int t = max(M - oe_del, 0);
             e = max(e - e_del, t);
             st.put(j, h1, e);
             t = max(M - oe_ins, 0);
             f = max(f - e_ins, t);
             h1 = h;
-            if (h >= m) { mj = j; m = h; }
+            mkey = max(mkey, St::key(h, j));
         }
+        const int m = mkey < 0 ? 0 : St::key_h(mkey);
+        const int mj = mkey < 0 ? -1 : St::key_j(mkey);
         if (end > beg) ncell += (unsigned) (end - beg);
         st.put(end, h1, 0);
         if (j == qlen) {
@@ -177,13 +196,16 @@ __device__ __forceinline__ void bsw_extend_one(const St &st, const QFetch &qf, c
 }
 
 // query packed 4 bit / base in shared memory words [word][thread]
-struct QSmem4 {
-    const uint32_t *base;      // &sh[W * blockDim.x + threadIdx.x]
-    int stride;
+struct QSmem4 {                // query packed 4 bit / base, [word][thread]
+    unsigned base;             // shared-window address of &sh[W * blockDim.x + threadIdx.x]
+    unsigned stride;
     struct Cursor { uint32_t w; };
-    __device__ __forceinline__ Cursor cursor(int j) const { Cursor c; c.w = base[(j >> 3) * stride] >> ((j & 7) * 4); return c; }
+    __device__ __forceinline__ uint32_t ldw(int k) const {
+        uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + (unsigned) k * stride)); return w;
+    }
+    __device__ __forceinline__ Cursor cursor(int j) const { Cursor c; c.w = ldw(j >> 3) >> ((j & 7) * 4); return c; }
     __device__ __forceinline__ int next(Cursor &c, int j) const {
-        if ((j & 7) == 0) c.w = base[(j >> 3) * stride];
+        if ((j & 7) == 0) c.w = ldw(j >> 3);
         int b = (int) (c.w & 0xFu);
         c.w >>= 4;
         return b;
@@ -225,8 +247,8 @@ bsw_thread_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ p
             }
             qs[(k >> 3) * nthr] = wv;
         }
-        SmemPacked st; st.base = sh + threadIdx.x; st.stride = nthr;
-        QSmem4 qf; qf.base = qs; qf.stride = nthr;
+        SmemPacked st; st.base = (unsigned) __cvta_generic_to_shared(sh + threadIdx.x); st.stride = (unsigned) nthr * 4u;
+        QSmem4 qf; qf.base = (unsigned) __cvta_generic_to_shared(qs); qf.stride = (unsigned) nthr * 4u;
         BswOut o;
         bsw_extend_one(st, qf, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
         out[id] = o;
