@@ -358,8 +358,17 @@ int scan64(bm2_ctx *ctx, const int64_t *in, int64_t *out, int64_t n) {
 }
 
 // sorts (keys, vals) of n reads; result permutation in vals_out
+// Measured (profiles/r1b_chain_tail_r1b.md): grouping heavy reads into the same warps makes the thread-per-read
+// chain/tail kernels 2-7x SLOWER (32 private n^2 scans per warp thrash L1/L2), so until those kernels are
+// warp-cooperative the reads keep their input order (the permutation is the identity).
+static const bool kSortReadsByWork = false;
+
 int sort_work(bm2_ctx *ctx, uint32_t *keys_in, uint32_t *keys_out, int32_t *vals_in, int32_t *vals_out, int n) {
     bm2_ctx *ctx_for_error = ctx;
+    if (!kSortReadsByWork) {
+        BM2_CUDA_OK(cudaMemcpyAsync(vals_out, vals_in, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        return 0;
+    }
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in, keys_out, vals_in, vals_out, n);
     if (ctx->ensure(ctx->d[B_CUB], bytes)) return 1;
