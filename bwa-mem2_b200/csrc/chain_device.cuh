@@ -99,12 +99,16 @@ struct WChain {
     int32_t w, kept, first;
 };
 
+struct FltRec { int32_t beg, end, w, is_alt, first, kept; };   // what mem_chain_flt scans, by sorted position
+
 struct ChainStripe {               // all arrays have >= n_slots entries, private to the read
     WSeed *seeds;
     WChain *chains;
     int32_t *ord;                  // chain ids ordered by pos (the B-tree's in-order sequence)
+    int64_t *ordpos;               // pos of ord[i] (contiguous copy for the binary search)
     int32_t *srt;                  // filter: chain ids sorted by weight
     int32_t *kv;                   // filter: kept non-overlapping chains
+    FltRec *flt;                   // filter: compact records by sorted position
 };
 
 // test_and_merge (src/bwamem.cpp:357-399) on the cached first/last seed of the chain
@@ -172,8 +176,8 @@ BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_sm
             int lower = -1;
             if (n_ch) {
                 int lo = 0, hi = n_ch;            // first chain with pos >= rbeg
-                while (lo < hi) { int mid = (lo + hi) >> 1; if (ws.chains[ws.ord[mid]].pos < rbeg) lo = mid + 1; else hi = mid; }
-                lower = (lo < n_ch && ws.chains[ws.ord[lo]].pos == rbeg) ? lo : lo - 1;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (ws.ordpos[mid] < rbeg) lo = mid + 1; else hi = mid; }
+                lower = (lo < n_ch && ws.ordpos[lo] == rbeg) ? lo : lo - 1;
                 if (lower >= 0) {
                     WChain &lc = ws.chains[ws.ord[lower]];
                     if (chain_test_and_merge(p, cv.l_pac, lc, ws.seeds, sid, rid)) {
@@ -187,8 +191,8 @@ BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_sm
             c.pos = rbeg; c.first_rbeg = c.last_rbeg = rbeg; c.first_qbeg = c.last_qbeg = s.qbeg; c.last_len = slen;
             c.head = c.tail = sid; c.n = 1; c.rid = rid; c.is_alt = cv.ann_alt ? (cv.ann_alt[rid] != 0) : 0;
             c.w = 0; c.kept = 0; c.first = -1;
-            for (int k = n_ch; k > lower + 1; --k) ws.ord[k] = ws.ord[k - 1];
-            ws.ord[lower + 1] = n_ch;
+            for (int k = n_ch; k > lower + 1; --k) { ws.ord[k] = ws.ord[k - 1]; ws.ordpos[k] = ws.ordpos[k - 1]; }
+            ws.ord[lower + 1] = n_ch; ws.ordpos[lower + 1] = rbeg;
             ++n_ch;
         }
     }
@@ -206,43 +210,45 @@ BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_sm
         const WChain *chs = ws.chains;
         ks_introsort_d(ws.srt, (long) n, [chs](int x, int y) { return chs[x].w > chs[y].w; });
     }
-#define CHN_BEG(c) ((c).first_qbeg)
-#define CHN_END(c) ((c).last_qbeg + (c).last_len)
+    for (int i = 0; i < n; ++i) {
+        const WChain &c = ws.chains[ws.srt[i]];
+        FltRec f; f.beg = c.first_qbeg; f.end = c.last_qbeg + c.last_len; f.w = c.w; f.is_alt = c.is_alt; f.first = -1; f.kept = 0;
+        ws.flt[i] = f;
+    }
     int n_kv = 0;
-    ws.chains[ws.srt[0]].kept = 3; ws.kv[n_kv++] = 0;
+    ws.flt[0].kept = 3; ws.kv[n_kv++] = 0;
     for (int i = 1; i < n; ++i) {
-        WChain &ai = ws.chains[ws.srt[i]];
+        const FltRec ai = ws.flt[i];
         int large_ovlp = 0, k;
         for (k = 0; k < n_kv; ++k) {
             const int j = ws.kv[k];
-            WChain &aj = ws.chains[ws.srt[j]];
-            const int b_max = CHN_BEG(aj) > CHN_BEG(ai) ? CHN_BEG(aj) : CHN_BEG(ai);
-            const int e_min = CHN_END(aj) < CHN_END(ai) ? CHN_END(aj) : CHN_END(ai);
+            const FltRec aj = ws.flt[j];
+            const int b_max = aj.beg > ai.beg ? aj.beg : ai.beg;
+            const int e_min = aj.end < ai.end ? aj.end : ai.end;
             if (e_min > b_max && (!aj.is_alt || ai.is_alt)) {
-                const int li = CHN_END(ai) - CHN_BEG(ai), lj = CHN_END(aj) - CHN_BEG(aj);
+                const int li = ai.end - ai.beg, lj = aj.end - aj.beg;
                 const int min_l = li < lj ? li : lj;
                 if ((float) (e_min - b_max) >= (float) min_l * p.mask_level && min_l < p.max_chain_gap) {
                     large_ovlp = 1;
-                    if (aj.first < 0) aj.first = i;
+                    if (aj.first < 0) ws.flt[j].first = i;
                     if ((float) ai.w < (float) aj.w * p.drop_ratio && aj.w - ai.w >= p.min_seed_len << 1) break;
                 }
             }
         }
-        if (k == n_kv) { ws.kv[n_kv++] = i; ai.kept = large_ovlp ? 2 : 3; }
+        if (k == n_kv) { ws.kv[n_kv++] = i; ws.flt[i].kept = large_ovlp ? 2 : 3; }
     }
-#undef CHN_BEG
-#undef CHN_END
     for (int k = 0; k < n_kv; ++k) {
-        const WChain &c = ws.chains[ws.srt[ws.kv[k]]];
-        if (c.first >= 0) ws.chains[ws.srt[c.first]].kept = 1;
+        const int f = ws.flt[ws.kv[k]].first;
+        if (f >= 0) ws.flt[f].kept = 1;
     }
     int i, k;
     for (i = k = 0; i < n; ++i) {
-        const int kept = ws.chains[ws.srt[i]].kept;
+        const int kept = ws.flt[i].kept;
         if (kept == 0 || kept == 3) continue;
         if (++k >= p.max_chain_extend) break;
     }
-    for (; i < n; ++i) if (ws.chains[ws.srt[i]].kept < 3) ws.chains[ws.srt[i]].kept = 0;
+    for (; i < n; ++i) if (ws.flt[i].kept < 3) ws.flt[i].kept = 0;
+    for (i = 0; i < n; ++i) { WChain &c = ws.chains[ws.srt[i]]; c.kept = ws.flt[i].kept; c.first = ws.flt[i].first; }
     int n_kept = 0;
     for (i = 0; i < n; ++i) if (ws.chains[ws.srt[i]].kept) ws.srt[n_kept++] = ws.srt[i];
     return n_kept;

@@ -135,11 +135,20 @@ BM2_HD bool ext_fold_d(const ExtParams &p, bm2_alnreg_t &a, int is_right, int h0
     return true;
 }
 
+// The fields of a reg the post-filter scans, 32 B instead of the 112-B mem_alnreg_t (the scan is O(regs x seeds)).
+struct PfBox { int64_t rb, re; int32_t qb, qe, seedlen0, w; };
+
 // Post-filter of one read (src/bwamem.cpp:2895-2989).  regs[0..n_reg) in creation order;
-// reg_seed[i] = seed index (within its chain) of reg i; srt2: int scratch of >= max chain length.
+// reg_seed[i] = seed index (within its chain) of reg i; srt2: int scratch of >= max chain length;
+// box: scratch of n_reg entries.
 BM2_HD void ext_postfilter_read_d(const ExtParams &p, const bm2_chain *chains, int n_chain, const bm2_seed *seeds, int l_query,
-                                  bm2_alnreg_t *regs, int n_reg, const int32_t *reg_seed, int32_t *srt2)
+                                  bm2_alnreg_t *regs, int n_reg, const int32_t *reg_seed, int32_t *srt2, PfBox *box)
 {
+    for (int i = 0; i < n_reg; ++i) {
+        const bm2_alnreg_t &a = regs[i];
+        PfBox b; b.rb = a.rb; b.re = a.re; b.qb = a.qb; b.qe = a.qe; b.seedlen0 = a.seedlen0; b.w = a.w;
+        box[i] = b;
+    }
     int lim = 0, base = 0;
     for (int ci = 0; ci < n_chain; ++ci) {
         const bm2_chain &c = chains[ci];
@@ -148,21 +157,21 @@ BM2_HD void ext_postfilter_read_d(const ExtParams &p, const bm2_chain *chains, i
         if (n == 0) continue;
         for (int k = n - 1; k >= 0; --k) srt2[k] = reg_seed[base + (n - 1 - k)];
         for (int k = n - 1; k >= 0; --k) {
-            const bm2_seed &s = cs[srt2[k]];
+            const bm2_seed s = cs[srt2[k]];
             int i, v = 0;
             for (i = 0; i < n_reg && v < lim; ++i) {
-                const bm2_alnreg_t *q = &regs[i];
-                if (q->qb == -1 && q->qe == -1) continue;
+                const PfBox q = box[i];
+                if (q.qb == -1 && q.qe == -1) continue;
                 int64_t rd; int qd, w, max_gap;
-                if (s.rbeg < q->rb || s.rbeg + s.len > q->re || s.qbeg < q->qb || s.qbeg + s.len > q->qe) { v++; continue; }
-                if (s.len - q->seedlen0 > .1 * l_query) { v++; continue; }
-                qd = s.qbeg - q->qb; rd = s.rbeg - q->rb;
+                if (s.rbeg < q.rb || s.rbeg + s.len > q.re || s.qbeg < q.qb || s.qbeg + s.len > q.qe) { v++; continue; }
+                if (s.len - q.seedlen0 > .1 * l_query) { v++; continue; }
+                qd = s.qbeg - q.qb; rd = s.rbeg - q.rb;
                 max_gap = cal_max_gap_d(p, qd < rd ? qd : (int) rd);
-                w = max_gap < q->w ? max_gap : q->w;
+                w = max_gap < q.w ? max_gap : q.w;
                 if (qd - rd < w && rd - qd < w) break;
-                qd = q->qe - (s.qbeg + s.len); rd = q->re - (s.rbeg + s.len);
+                qd = q.qe - (s.qbeg + s.len); rd = q.re - (s.rbeg + s.len);
                 max_gap = cal_max_gap_d(p, qd < rd ? qd : (int) rd);
-                w = max_gap < q->w ? max_gap : q->w;
+                w = max_gap < q.w ? max_gap : q.w;
                 if (qd - rd < w && rd - qd < w) break;
                 v++;
             }
@@ -176,8 +185,9 @@ BM2_HD void ext_postfilter_read_d(const ExtParams &p, const bm2_chain *chains, i
                     if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
                 }
                 if (vv == n) {
-                    bm2_alnreg_t &ar = regs[base + (n - 1 - k)];
-                    ar.qb = ar.qe = -1;
+                    const int ai = base + (n - 1 - k);
+                    regs[ai].qb = regs[ai].qe = -1;
+                    box[ai].qb = box[ai].qe = -1;
                     srt2[k] = -1;
                     continue;
                 }
@@ -279,13 +289,36 @@ BM2_HD int patch_reg_d(const ContigView &cv, const ExtParams &p, const uint8_t *
     return score;
 }
 
-// mem_sort_dedup_patch (src/bwamem.cpp:292-353) on the regs of one read; he: 2*(l_query+1) ints
+// a[i] <- a[idx[i]] in place (cycle following: every 112-byte record moves once); idx is destroyed
+BM2_HD void permute_regs_d(bm2_alnreg_t *a, int32_t *idx, int n) {
+    for (int i = 0; i < n; ++i) {
+        if (idx[i] < 0 || idx[i] == i) { continue; }
+        bm2_alnreg_t tmp = a[i];
+        int j = i;
+        for (;;) {
+            const int src = idx[j];
+            idx[j] = -1;
+            if (src == i) { a[j] = tmp; break; }
+            a[j] = a[src];
+            j = src;
+        }
+    }
+}
+
+// mem_sort_dedup_patch (src/bwamem.cpp:292-353) on the regs of one read; he: 2*(l_query+1) ints; idx: n ints.
+// The two ks_introsort calls run on an index array (same comparisons, same swaps => same permutation as sorting
+// the records) and the records are permuted once.
 BM2_HD int sort_dedup_patch_d(const ContigView &cv, const ExtParams &p, const uint8_t *ref, const uint8_t *query, int n,
-                              bm2_alnreg_t *a, int32_t *he)
+                              bm2_alnreg_t *a, int32_t *he, int32_t *idx)
 {
     int m, i, j;
     if (n <= 1) return n;
-    ks_introsort_d(a, (long) n, [](const bm2_alnreg_t &x, const bm2_alnreg_t &y) { return x.re < y.re; });
+    for (i = 0; i < n; ++i) idx[i] = i;
+    {
+        const bm2_alnreg_t *ra = a;
+        ks_introsort_d(idx, (long) n, [ra](int x, int y) { return ra[x].re < ra[y].re; });
+    }
+    permute_regs_d(a, idx, n);
     for (i = 0; i < n; ++i) reg_set_n_comp_d(a[i], 1);
     for (i = 1; i < n; ++i) {
         bm2_alnreg_t *pp = &a[i];
@@ -317,9 +350,15 @@ BM2_HD int sort_dedup_patch_d(const ContigView &cv, const ExtParams &p, const ui
     for (i = 0, m = 0; i < n; ++i)
         if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
     n = m;
-    ks_introsort_d(a, (long) n, [](const bm2_alnreg_t &x, const bm2_alnreg_t &y) {
-        return x.score > y.score || (x.score == y.score && (x.rb < y.rb || (x.rb == y.rb && x.qb < y.qb)));
-    });
+    for (i = 0; i < n; ++i) idx[i] = i;
+    {
+        const bm2_alnreg_t *ra = a;
+        ks_introsort_d(idx, (long) n, [ra](int xi, int yi) {
+            const bm2_alnreg_t &x = ra[xi], &y = ra[yi];
+            return x.score > y.score || (x.score == y.score && (x.rb < y.rb || (x.rb == y.rb && x.qb < y.qb)));
+        });
+    }
+    permute_regs_d(a, idx, n);
     for (i = 1; i < n; ++i)
         if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
     for (i = 1, m = 1; i < n; ++i)
@@ -330,12 +369,12 @@ BM2_HD int sort_dedup_patch_d(const ContigView &cv, const ExtParams &p, const ui
 // Tail of mem_kernel2_core for one read (src/bwamem.cpp:1141-1169): drop purged regs, sort/dedup/
 // patch, ALT marking.  Returns the final reg count (regs compacted in place).
 BM2_HD int ext_tail_read_d(const ContigView &cv, const ExtParams &p, const uint8_t *ref, const uint8_t *query, bm2_alnreg_t *regs,
-                           int n_reg, int32_t *he)
+                           int n_reg, int32_t *he, int32_t *idx)
 {
     int m = 0;
     for (int i = 0; i < n_reg; ++i)
         if (regs[i].qe > regs[i].qb) { if (m != i) regs[m++] = regs[i]; else ++m; }
-    m = sort_dedup_patch_d(cv, p, ref, query, m, regs, he);
+    m = sort_dedup_patch_d(cv, p, ref, query, m, regs, he, idx);
     for (int i = 0; i < m; ++i)
         if (regs[i].rid >= 0 && cv.ann_alt && cv.ann_alt[regs[i].rid]) reg_set_is_alt_d(regs[i], 1);
     return m;

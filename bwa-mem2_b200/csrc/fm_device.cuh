@@ -117,18 +117,27 @@ struct SmemParams {
 };
 
 // The three-pass SMEM search of ONE read as a state machine with a single extension call site.
-//   q[0..len): base codes;  prev: scratch of >= len+1 entries;  reseed: scratch of >= len int2-like
+//   q(j), j in [0,len): base codes;  prev: scratch of >= len+1 entries (filled from the top downwards during
+//   the forward phase, so the longest-first order of the backward phase needs no reversal);  reseed: scratch of >= len int2-like
 //   entries (x, min_intv) for pass 2;  emit(m, n, k, l, s) appends one SMEM (any order: the caller
 //   sorts by (rid, m, n) afterwards, as sortSMEMs + the per-read introsort do);
 //   n_ext counts extensions (128 algorithmic bytes each).
-template <class Emit>
-BM2_HD void fm_smem_read(const FmIndexView &fm, const uint8_t *q, int len, const SmemParams &sp, FmPrev *prev,
+struct QPlain {                    // read codes straight from memory
+    const uint8_t *p;
+    BM2_HD int operator()(int j) const { return p[j]; }
+};
+
+template <class Emit, class Q>
+BM2_HD void fm_smem_read(const FmIndexView &fm, const Q &q, int len, const SmemParams &sp, FmPrev *prev,
                          int32_t *reseed, Emit &emit, unsigned &n_ext)
 {
     enum { ST_SEARCH_BEGIN, ST_FWD, ST_FWD_END, ST_BWD_ROW, ST_BWD_ITEM, ST_SEARCH_END, ST_P3_BEGIN, ST_P3_FWD, ST_DONE };
     if (len <= 0) return;
     int pass = 1;
     int x = 0, min_intv = 1, next_x = 0, j = 0, num_prev = 0, num_curr = 0, p = 0, curr_s = -1;
+    const int cap = len + 1;
+    int top = cap;
+    FmPrev *pv = prev;
     bool first_phase = true;
     int n_reseed = 0, i_reseed = 0;
     FmPrev cur; cur.k = cur.l = cur.s = 0; cur.m = cur.n = 0;
@@ -141,30 +150,30 @@ BM2_HD void fm_smem_read(const FmIndexView &fm, const uint8_t *q, int len, const
             if (st == ST_SEARCH_BEGIN) {
                 // getSMEMsOnePosOneThread entry (src/FMI_search.cpp:513-533)
                 next_x = x + 1;
-                const int a = q[x];
+                const int a = q(x);
                 if (a > 3) { st = ST_SEARCH_END; num_prev = 0; continue; }
                 cur.m = x; cur.n = x; cur.k = fm_count(fm, a); cur.l = fm_count(fm, 3 - a); cur.s = fm_count(fm, a + 1) - cur.k;
-                num_prev = 0; j = x + 1; st = ST_FWD;
+                num_prev = 0; top = cap; j = x + 1; st = ST_FWD;
             } else if (st == ST_FWD) {
                 if (j >= len) { st = ST_FWD_END; continue; }
                 next_x = j + 1;
-                const int a = q[j];
+                const int a = q(j);
                 if (a > 3) { st = ST_FWD_END; continue; }
                 req.k = cur.l; req.l = cur.k; req.s = cur.s; req_base = 3 - a; req_fwd = true; need = true;
             } else if (st == ST_FWD_END) {
-                if (cur.s >= min_intv) prev[num_prev++] = cur;
-                for (int a = 0, b = num_prev - 1; a < b; ++a, --b) { FmPrev t = prev[a]; prev[a] = prev[b]; prev[b] = t; }
+                if (cur.s >= min_intv) prev[--top] = cur;
+                pv = prev + top; num_prev = cap - top;          // last pushed (longest) first
                 j = x - 1; st = ST_BWD_ROW;
             } else if (st == ST_BWD_ROW) {
-                if (j < 0 || q[j] > 3 || num_prev == 0) { st = ST_SEARCH_END; continue; }
+                if (j < 0 || q(j) > 3 || num_prev == 0) { st = ST_SEARCH_END; continue; }
                 num_curr = 0; curr_s = -1; p = 0; first_phase = true; st = ST_BWD_ITEM;
             } else if (st == ST_BWD_ITEM) {
                 if (p >= num_prev) { num_prev = num_curr; if (num_curr == 0) { st = ST_SEARCH_END; continue; } --j; st = ST_BWD_ROW; continue; }
-                req.k = prev[p].k; req.l = prev[p].l; req.s = prev[p].s; req_base = q[j]; req_fwd = false; need = true;
+                req.k = pv[p].k; req.l = pv[p].l; req.s = pv[p].s; req_base = q(j); req_fwd = false; need = true;
             } else if (st == ST_SEARCH_END) {
                 // tail of one search (src/FMI_search.cpp:656-667), then the pass drivers
                 if (num_prev != 0) {
-                    const FmPrev &s0 = prev[0];
+                    const FmPrev &s0 = pv[0];
                     if (s0.n - s0.m + 1 >= sp.min_seed_len) {
                         emit(s0.m, s0.n, s0.k, s0.l, s0.s);
                         if (pass == 1 && s0.n + 1 - s0.m >= sp.split_len && s0.s <= sp.split_width) {
@@ -187,14 +196,14 @@ BM2_HD void fm_smem_read(const FmIndexView &fm, const uint8_t *q, int len, const
             } else if (st == ST_P3_BEGIN) {   // bwtSeedStrategyAllPosOneThread (src/FMI_search.cpp:726-812)
                 if (x >= len) { st = ST_DONE; continue; }
                 next_x = x + 1;
-                const int a = q[x];
+                const int a = q(x);
                 if (a > 3) { x = next_x; continue; }
                 cur.m = x; cur.n = x; cur.k = fm_count(fm, a); cur.l = fm_count(fm, 3 - a); cur.s = fm_count(fm, a + 1) - cur.k;
                 j = x + 1; st = ST_P3_FWD;
             } else if (st == ST_P3_FWD) {
                 if (j >= len) { x = next_x; st = ST_P3_BEGIN; continue; }
                 next_x = j + 1;
-                const int a = q[j];
+                const int a = q(j);
                 if (a > 3) { x = next_x; st = ST_P3_BEGIN; continue; }
                 req.k = cur.l; req.l = cur.k; req.s = cur.s; req_base = 3 - a; req_fwd = true; need = true;
             } else {  // ST_DONE
@@ -208,11 +217,11 @@ BM2_HD void fm_smem_read(const FmIndexView &fm, const uint8_t *q, int len, const
         if (req_fwd) { int64_t t = r.k; r.k = r.l; r.l = t; }
         // ---- consume the result ---------------------------------------------------------------------------
         if (st == ST_FWD) {
-            if (r.s != cur.s) prev[num_prev++] = cur;
+            if (r.s != cur.s) prev[--top] = cur;
             if (r.s < min_intv) { next_x = j; st = ST_FWD_END; }
             else { cur.k = r.k; cur.l = r.l; cur.s = r.s; cur.n = j; ++j; }
         } else if (st == ST_BWD_ITEM) {
-            const FmPrev old = prev[p];
+            const FmPrev old = pv[p];
             if (first_phase && r.s < min_intv && old.n - old.m + 1 >= sp.min_seed_len) {
                 emit(old.m, old.n, old.k, old.l, old.s);
                 if (pass == 1 && old.n + 1 - old.m >= sp.split_len && old.s <= sp.split_width) {
@@ -222,7 +231,7 @@ BM2_HD void fm_smem_read(const FmIndexView &fm, const uint8_t *q, int len, const
             } else if (r.s >= min_intv && r.s != curr_s) {
                 curr_s = (int) r.s;
                 FmPrev t; t.k = r.k; t.l = r.l; t.s = r.s; t.m = j; t.n = old.n;
-                prev[num_curr++] = t;
+                pv[num_curr++] = t;
                 first_phase = false;
             }
             ++p;

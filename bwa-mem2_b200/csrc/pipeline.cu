@@ -87,11 +87,23 @@ struct SmemAppend {
     }
 };
 
-// A. one read per thread (grid-stride), private prev/reseed stripes per THREAD
+// A. one read per thread (grid-stride), private prev/reseed stripes per THREAD.  USE_SMEM: the read is packed
+// 4 bit/base into shared memory [word][thread] (bank = lane) so that the base fetch in front of every interval
+// extension never waits on L1/L2 (22 % of the stall samples before, profiles/r1b_smem_r1b.md).
+struct QShared4 {
+    unsigned base, stride;
+    __device__ __forceinline__ int operator()(int j) const {
+        uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + (unsigned) (j >> 3) * stride));
+        return (int) ((w >> ((j & 7) * 4)) & 0xFu);
+    }
+};
+
+template <bool USE_SMEM>
 __global__ void __launch_bounds__(128, 8)
 smem_kernel(FmIndexView fm, SmemParams sp, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, int n_reads, int stripe,
             FmPrev *prev_all, int32_t *reseed_all, bm2_smem *out, unsigned long long cap, Counters *cnt)
 {
+    extern __shared__ uint32_t qsh[];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     FmPrev *prev = prev_all + (size_t) tid * stripe;
     int32_t *reseed = reseed_all + (size_t) tid * 2 * stripe;
@@ -100,7 +112,20 @@ smem_kernel(FmIndexView fm, SmemParams sp, const uint8_t *__restrict__ codes, co
         const int64_t o = offs[r];
         const int len = (int) (offs[r + 1] - o);
         SmemAppend emit = { out, cap, &cnt->n_smem, (uint32_t) r };
-        fm_smem_read(fm, codes + o, len, sp, prev, reseed, emit, n_ext);
+        if (USE_SMEM) {
+            const uint8_t *qp = codes + o;
+            for (int k = 0; k < len; k += 8) {
+                uint32_t wv = 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { uint32_t b = k + u < len ? (uint32_t) qp[k + u] : 4u; wv |= (b > 4u ? 4u : b) << (4 * u); }
+                qsh[(k >> 3) * blockDim.x + threadIdx.x] = wv;
+            }
+            QShared4 q = { (unsigned) __cvta_generic_to_shared(qsh + threadIdx.x), (unsigned) blockDim.x * 4u };
+            fm_smem_read(fm, q, len, sp, prev, reseed, emit, n_ext);
+        } else {
+            QPlain q = { codes + o };
+            fm_smem_read(fm, q, len, sp, prev, reseed, emit, n_ext);
+        }
     }
     if (n_ext) atomicAdd(&cnt->n_ext, (unsigned long long) n_ext);
 }
@@ -149,7 +174,7 @@ sa_kernel(FmIndexView fm, const bm2_smem *__restrict__ sm, const int64_t *__rest
 
 // D. one read per thread
 struct ChainBufs {
-    WSeed *wseed; WChain *wchain; int32_t *ord, *srt, *kv;
+    WSeed *wseed; WChain *wchain; int32_t *ord, *srt, *kv; int64_t *ordpos; FltRec *flt;
     bm2_chain *fin_chain; bm2_seed *fin_seed;
     int32_t *n_chain, *n_seed, *n_left, *n_right;
 };
@@ -170,7 +195,7 @@ chain_kernel(ContigView cv, ChainParams cp, const bm2_smem *__restrict__ sm, con
     const bool skip = (read_smem_off[b1] - read_smem_off[b0]) <= 1;
     if (se > sb && !skip && len >= cp.min_seed_len) {
         const int64_t base = slot_off[sb];
-        ChainStripe ws = { b.wseed + base, b.wchain + base, b.ord + base, b.srt + base, b.kv + base };
+        ChainStripe ws = { b.wseed + base, b.wchain + base, b.ord + base, b.ordpos + base, b.srt + base, b.kv + base, b.flt + base };
         float frac = 0.f;
         nk = chain_read_d(cv, cp, sm + sb, (int) (se - sb), sa + base, len, ws, &frac);
         chain_finalize_d(ws, nk, frac, r, len, b.fin_chain + base, b.fin_seed + base, &ns, &nl, &nr);
@@ -249,7 +274,7 @@ __global__ void __launch_bounds__(128)
 tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs,
             const bm2_chain *__restrict__ chains, const bm2_seed *__restrict__ seeds, const int64_t *__restrict__ chain_off,
             const int64_t *__restrict__ reg_off, int n_reads, bm2_alnreg_t *regs, const int32_t *reg_seed, int32_t *srt2_all, int32_t *he_all,
-            int he_stride, const int32_t *__restrict__ perm, int32_t *n_final)
+            int he_stride, const int32_t *__restrict__ perm, PfBox *box_all, int32_t *n_final)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     int32_t *he = he_all + (size_t) tid * he_stride;
@@ -260,8 +285,8 @@ tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const 
         int m = 0;
         if (c1 > c0) {
             const int l_query = (int) (offs[r + 1] - offs[r]);
-            ext_postfilter_read_d(ep, chains + c0, (int) (c1 - c0), seeds, l_query, regs + g0, n_reg, reg_seed + g0, srt2_all + g0);
-            m = ext_tail_read_d(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he);
+            ext_postfilter_read_d(ep, chains + c0, (int) (c1 - c0), seeds, l_query, regs + g0, n_reg, reg_seed + g0, srt2_all + g0, box_all + g0);
+            m = ext_tail_read_d(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he, srt2_all + g0);
         }
         n_final[r] = m;
     }
@@ -303,7 +328,7 @@ namespace {
 enum Buf {
     B_CODES, B_OFFS, B_CNT, B_PREV, B_RESEED, B_SMEM_RAW, B_KEYS_IN, B_KEYS_OUT, B_VALS_IN, B_VALS_OUT, B_CUB, B_SMEM, B_SLOT_CNT,
     B_SLOT_OFF, B_READ_SMEM_OFF, B_SA, B_WSEED, B_WCHAIN, B_ORD, B_SRT, B_KV, B_FIN_CHAIN, B_FIN_SEED, B_PER_READ, B_SCAN, B_CHAINS,
-    B_SEEDS, B_REGS, B_REG_AUX, B_JOBS, B_NW, B_OUT, B_PERM, B_COUNT_
+    B_SEEDS, B_REGS, B_REG_AUX, B_JOBS, B_NW, B_OUT, B_PERM, B_ORDPOS, B_FLT, B_COUNT_
 };
 static_assert(B_COUNT_ <= 64, "bm2_ctx::d[] too small");
 enum HBuf { H_OUT_REGS, H_OUT_OFF, H_SMEM, H_CHAINS, H_SEEDS, H_MISC };
@@ -428,8 +453,14 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (ctx->ensure(ctx->d[B_SMEM_RAW], cap * sizeof(bm2_smem))) return 1;
         BM2_CUDA_OK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), st));
-        smem_kernel<<<blocks_a, 128, 0, st>>>(pv.fm, pv.sp, d_codes, d_offs, n, stripe, P<FmPrev>(ctx, B_PREV), P<int32_t>(ctx, B_RESEED),
-                                               P<bm2_smem>(ctx, B_SMEM_RAW), cap, d_cnt);
+        if (max_len <= 256) {
+            const size_t qsm = (size_t) ((max_len + 7) / 8) * 128 * 4;
+            smem_kernel<true><<<blocks_a, 128, qsm, st>>>(pv.fm, pv.sp, d_codes, d_offs, n, stripe, P<FmPrev>(ctx, B_PREV), P<int32_t>(ctx, B_RESEED),
+                                                           P<bm2_smem>(ctx, B_SMEM_RAW), cap, d_cnt);
+        } else {
+            smem_kernel<false><<<blocks_a, 128, 0, st>>>(pv.fm, pv.sp, d_codes, d_offs, n, stripe, P<FmPrev>(ctx, B_PREV), P<int32_t>(ctx, B_RESEED),
+                                                          P<bm2_smem>(ctx, B_SMEM_RAW), cap, d_cnt);
+        }
         BM2_CUDA_OK(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         BM2_CUDA_OK(cudaStreamSynchronize(st));
         if (h_cnt.n_smem <= cap) break;
@@ -483,6 +514,7 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     if (sg.mark("chain")) return 1;
     if (ctx->ensure(ctx->d[B_WSEED], sl1 * sizeof(WSeed)) || ctx->ensure(ctx->d[B_WCHAIN], sl1 * sizeof(WChain)) ||
         ctx->ensure(ctx->d[B_ORD], sl1 * 4) || ctx->ensure(ctx->d[B_SRT], sl1 * 4) || ctx->ensure(ctx->d[B_KV], sl1 * 4) ||
+        ctx->ensure(ctx->d[B_ORDPOS], sl1 * 8) || ctx->ensure(ctx->d[B_FLT], sl1 * sizeof(FltRec)) ||
         ctx->ensure(ctx->d[B_FIN_CHAIN], sl1 * sizeof(bm2_chain)) || ctx->ensure(ctx->d[B_FIN_SEED], sl1 * sizeof(bm2_seed)) ||
         ctx->ensure(ctx->d[B_PER_READ], al((size_t) (n + 1) * 4) * 5) || ctx->ensure(ctx->d[B_SCAN], al((size_t) (n + 2) * 8) * 10)) return 1;
     const size_t pr = al((size_t) (n + 1) * 4);
@@ -490,6 +522,7 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     int32_t *d_nchain = (int32_t *) prb, *d_nseed = (int32_t *) (prb + pr), *d_nleft = (int32_t *) (prb + 2 * pr),
             *d_nright = (int32_t *) (prb + 3 * pr), *d_nfinal = (int32_t *) (prb + 4 * pr);
     ChainBufs cb = { P<WSeed>(ctx, B_WSEED), P<WChain>(ctx, B_WCHAIN), P<int32_t>(ctx, B_ORD), P<int32_t>(ctx, B_SRT), P<int32_t>(ctx, B_KV),
+                     P<int64_t>(ctx, B_ORDPOS), P<FltRec>(ctx, B_FLT),
                      P<bm2_chain>(ctx, B_FIN_CHAIN), P<bm2_seed>(ctx, B_FIN_SEED), d_nchain, d_nseed, d_nleft, d_nright };
     if (ctx->ensure(ctx->d[B_PERM], al((size_t) n * 4) * 4)) return 1;
     uint32_t *wk_in = (uint32_t *) ctx->d[B_PERM].p, *wk_out = (uint32_t *) ((char *) ctx->d[B_PERM].p + al((size_t) n * 4));
@@ -529,7 +562,7 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     // ---- F. regs + jobs -----------------------------------------------------------------------------------
     if (sg.mark("extbuild")) return 1;
     const size_t nr1 = (size_t) n_regs + 1, nl1 = (size_t) n_left + 1, nrt1 = (size_t) n_right + 1;
-    const size_t aux_bytes = al(nr1 * 4) * 3 + al(nr1 * 8) + al(nl1 * 4) * 2 + al(nrt1 * 4) * 2;
+    const size_t aux_bytes = al(nr1 * 4) * 3 + al(nr1 * 8) + al(nl1 * 4) * 2 + al(nrt1 * 4) * 2 + al(nr1 * sizeof(PfBox));
     const size_t njmax = nl1 > nrt1 ? nl1 : nrt1;
     if (ctx->ensure(ctx->d[B_REGS], nr1 * sizeof(bm2_alnreg_t)) || ctx->ensure(ctx->d[B_REG_AUX], aux_bytes) ||
         ctx->ensure(ctx->d[B_JOBS], al(nl1 * sizeof(ExtJobRec)) + al(nrt1 * sizeof(ExtJobRec)) + al(njmax * sizeof(ExtJobRec)) + al(njmax * sizeof(BswOut))) ||
@@ -543,6 +576,7 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     int32_t *d_left_retry = (int32_t *) ab; ab += al(nl1 * 4);
     int32_t *d_right_reg = (int32_t *) ab; ab += al(nrt1 * 4);
     int32_t *d_right_retry = (int32_t *) ab; ab += al(nrt1 * 4);
+    PfBox *d_box = (PfBox *) ab; ab += al(nr1 * sizeof(PfBox));
     char *jb = (char *) ctx->d[B_JOBS].p;
     ExtJobRec *d_left = (ExtJobRec *) jb; jb += al(nl1 * sizeof(ExtJobRec));
     ExtJobRec *d_right = (ExtJobRec *) jb; jb += al(nrt1 * sizeof(ExtJobRec));
@@ -592,7 +626,7 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     const int he_stride = 2 * (max_len + 2);
     if (ctx->ensure(ctx->d[B_NW], (size_t) blocks_i * 128 * he_stride * 4)) return 1;
     tail_kernel<<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
-                                          d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_nfinal);
+                                          d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal);
 
     // ---- J. output ---------------------------------------------------------------------------------------
     if (sg.mark("output")) return 1;

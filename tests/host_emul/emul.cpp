@@ -48,7 +48,8 @@ void stage_smem_sa(const Views &v, const bm2_mem_opt_t *o, const bm2_read_batch 
         auto emit = [&](int m, int n, int64_t k, int64_t l, int64_t ss) {
             bm2_smem x; x.rid = r; x.m = m; x.n = n; x.k = k; x.l = l; x.s = ss; s.smems.push_back(x);
         };
-        fm_smem_read(v.fm, q, len, v.sp, prev.data(), reseed.data(), emit, n_ext);
+        QPlain qq = { q };
+        fm_smem_read(v.fm, qq, len, v.sp, prev.data(), reseed.data(), emit, n_ext);
         s.n_ext += n_ext;
     }
     std::stable_sort(s.smems.begin(), s.smems.end(), [](const bm2_smem &a, const bm2_smem &b) {
@@ -83,8 +84,8 @@ void stage_chain(const Views &v, const bm2_read_batch *rb, const Stage1 &s1, Sta
         bool skip = (s1.read_smem_off[b1] - s1.read_smem_off[b0]) <= 1;
         if (se > sb && !skip && len >= v.sp.min_seed_len) {
             int64_t slots = s1.slot_off[se] - s1.slot_off[sb];
-            std::vector<WSeed> ws(slots + 1); std::vector<WChain> wc(slots + 1); std::vector<int32_t> ord(slots + 1), srt(slots + 1), kv(slots + 1);
-            ChainStripe st = { ws.data(), wc.data(), ord.data(), srt.data(), kv.data() };
+            std::vector<WSeed> ws(slots + 1); std::vector<WChain> wc(slots + 1); std::vector<int32_t> ord(slots + 1), srt(slots + 1), kv(slots + 1); std::vector<int64_t> ordpos(slots + 1); std::vector<FltRec> flt(slots + 1);
+            ChainStripe st = { ws.data(), wc.data(), ord.data(), ordpos.data(), srt.data(), kv.data(), flt.data() };
             float frac = 0;
             int nk = chain_read_d(v.cv, v.cp, s1.smems.data() + sb, (int) (se - sb), s1.sa.data() + s1.slot_off[sb], len, st, &frac);
             std::vector<bm2_chain> oc(nk + 1); std::vector<bm2_seed> os(slots + 1);
@@ -171,15 +172,15 @@ int emul_seed_chain_extend(const bm2_index_desc *idx, const bm2_mem_opt_t *o, co
     run_phase(left, left_reg, left_off[n], 0);
     run_phase(right, right_reg, right_off[n], 1);
     std::vector<bm2_alnreg_t> out; std::vector<int64_t> off(n + 1, 0);
-    std::vector<int32_t> srt2(max_chain + 1), he(2 * (max_len + 2));
+    std::vector<int32_t> srt2(reg_off[n] + max_chain + 1), he(2 * (max_len + 2)); std::vector<PfBox> box(reg_off[n] + 1);
     for (int r = 0; r < n; ++r) {
         int64_t cb = s2.read_chain_off[r], ce = s2.read_chain_off[r + 1];
         int nreg = (int) (reg_off[r + 1] - reg_off[r]);
         int l_query = (int) (rb->offsets[r + 1] - rb->offsets[r]);
         if (ce > cb) {
             ext_postfilter_read_d(v.ep, s2.chains.data() + cb, (int) (ce - cb), s2.seeds.data(), l_query, regs.data() + reg_off[r], nreg,
-                                  reg_seed.data() + reg_off[r], srt2.data());
-            int m = ext_tail_read_d(v.cv, v.ep, idx->ref_string, rb->codes + rb->offsets[r], regs.data() + reg_off[r], nreg, he.data());
+                                  reg_seed.data() + reg_off[r], srt2.data() + reg_off[r], box.data() + reg_off[r]);
+            int m = ext_tail_read_d(v.cv, v.ep, idx->ref_string, rb->codes + rb->offsets[r], regs.data() + reg_off[r], nreg, he.data(), srt2.data() + reg_off[r]);
             for (int i = 0; i < m; ++i) out.push_back(regs[reg_off[r] + i]);
         }
         off[r + 1] = (int64_t) out.size();
