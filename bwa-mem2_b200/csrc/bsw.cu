@@ -17,10 +17,11 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #define BSW_THREADS 128
-#define BSW_NCLASS 8
+#define BSW_NBOUND 8
+#define BSW_NCLASS 16          // class = 2 * bound index + (needs 16-bit state)
 // upper query-length bound of each class (state words = bound + 2)
-__constant__ int c_class_bound[BSW_NCLASS] = {32, 64, 96, 128, 160, 256, 512, 1024};
-static const int h_class_bound[BSW_NCLASS] = {32, 64, 96, 128, 160, 256, 512, 1024};
+__constant__ int c_class_bound[BSW_NBOUND] = {32, 64, 96, 128, 160, 256, 512, 1024};
+static const int h_class_bound[BSW_NBOUND] = {32, 64, 96, 128, 160, 256, 512, 1024};
 
 struct BswSortScratch {
     uint32_t *keys_in, *keys_out;
@@ -36,10 +37,11 @@ __device__ __forceinline__ int bsw_class_of(int qlen, int tlen, int h0, int a) {
     // src/bwamem.cpp:2307); anything else goes to the wide / global-state kernel.
     int minlen = qlen < tlen ? qlen : tlen;
     long long maxsc = (long long) h0 + (long long) minlen * a;
-    if (maxsc >= 32768 || qlen > c_class_bound[BSW_NCLASS - 1]) return BSW_NCLASS;
+    if (maxsc >= 32768 || qlen > c_class_bound[BSW_NBOUND - 1]) return BSW_NCLASS;
+    const int wide16 = maxsc > 255 ? 1 : 0;
 #pragma unroll
-    for (int c = 0; c < BSW_NCLASS; ++c)
-        if (qlen <= c_class_bound[c]) return c;
+    for (int c = 0; c < BSW_NBOUND; ++c)
+        if (qlen <= c_class_bound[c]) return 2 * c + wide16;
     return BSW_NCLASS;
 }
 
@@ -51,10 +53,10 @@ __global__ void bsw_keys_kernel(const BswJob *jobs, int n, int a, uint32_t *keys
     if (i < n) {
         BswJob j = jobs[i];
         int c = bsw_class_of(j.qlen, j.tlen, j.h0, a);
-        int t = j.tlen > 0xFFFFF ? 0xFFFFF : j.tlen;
+        int t = j.tlen > 0x7FFFF ? 0x7FFFF : j.tlen;
         // ascending sort => class ascending, target length descending (long jobs first), then qlen desc
         int q = j.qlen > 0xFF ? 0xFF : j.qlen;
-        keys[i] = ((uint32_t) c << 28) | ((uint32_t) (0xFFFFF - t) << 8) | (uint32_t) (0xFF - q);
+        keys[i] = ((uint32_t) c << 27) | ((uint32_t) (0x7FFFF - t) << 8) | (uint32_t) (0xFF - q);   // c <= 16: 5 bits
         idx[i] = i;
         atomicAdd(&hist[c], 1);
     }
@@ -87,6 +89,26 @@ struct SmemPacked {            // H | E<<16 in shared memory, [column][thread]; 
     __device__ __forceinline__ bool zero(int j) const { return ldw(j) == 0u; }
     // row maximum as one signed key: (h << 16) | j  (h < 2^15, j < 2^16)
     typedef int key_t;
+    static constexpr unsigned kStateBytes = 4;
+    static __device__ __forceinline__ key_t key(int h, int j) { return (h << 16) | j; }
+    static __device__ __forceinline__ int key_h(key_t k) { return k >> 16; }
+    static __device__ __forceinline__ int key_j(key_t k) { return k & 0xFFFF; }
+};
+
+struct SmemPacked8 {           // H | E<<8 in 16 bits: jobs whose best possible score fits 8 bits (the 2x151 bp workload)
+    unsigned base;             // shared-window address of the thread's column 0
+    unsigned stride;           // blockDim.x * 2 bytes
+    __device__ __forceinline__ uint32_t ldw(int j) const {
+        uint16_t w; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w) : "r"(base + (unsigned) j * stride)); return (uint32_t) w;
+    }
+    __device__ __forceinline__ void stw(int j, uint32_t w) const {
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(base + (unsigned) j * stride), "h"((uint16_t) w) : "memory");
+    }
+    __device__ __forceinline__ void get(int j, int &h, int &e) const { uint32_t w = ldw(j); h = (int) (w & 0xFFu); e = (int) (w >> 8); }
+    __device__ __forceinline__ void put(int j, int h, int e) const { stw(j, (uint32_t) h | ((uint32_t) e << 8)); }
+    __device__ __forceinline__ bool zero(int j) const { return ldw(j) == 0u; }
+    typedef int key_t;
+    static constexpr unsigned kStateBytes = 2;
     static __device__ __forceinline__ key_t key(int h, int j) { return (h << 16) | j; }
     static __device__ __forceinline__ int key_h(key_t k) { return k >> 16; }
     static __device__ __forceinline__ int key_j(key_t k) { return k & 0xFFFF; }
@@ -219,6 +241,7 @@ struct QGmem {                 // query bytes straight from global memory
     __device__ __forceinline__ int next(Cursor &, int j) const { return ptr[(long long) j * stride]; }
 };
 
+template <class St>
 __global__ void __launch_bounds__(BSW_THREADS)
 bsw_thread_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ perm, const int32_t *__restrict__ class_off,
                   int cls, BswOut *__restrict__ out, const uint8_t *__restrict__ tbase, const uint8_t *__restrict__ qbase,
@@ -227,31 +250,34 @@ bsw_thread_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ p
     extern __shared__ uint32_t sh[];
     const int first = class_off[cls], last = class_off[cls + 1];
     const int nthr = blockDim.x;
-    const int g = first + blockIdx.x * nthr + threadIdx.x;
-    if (first + blockIdx.x * nthr >= last) return;
+    const unsigned state_bytes = St::kStateBytes;
+    // state columns first (W entries of state_bytes per thread), then the packed query words
+    const unsigned q_off_words = ((unsigned) W * nthr * state_bytes + 3u) / 4u;
     unsigned long long ncell = 0;
-    if (g < last) {
-        const int id = perm[g];
-        const BswJob job = jobs[id];
-        // pack the query, 8 bases per word
-        const uint8_t *qp = qbase + job.qoff;
-        uint32_t *qs = sh + W * nthr + threadIdx.x;
-        for (int k = 0; k < job.qlen; k += 8) {
-            uint32_t wv = 0;
+    for (int blk = blockIdx.x; first + blk * nthr < last; blk += gridDim.x) {      // persistent CTAs: long jobs first
+        const int g = first + blk * nthr + threadIdx.x;
+        if (g < last) {
+            const int id = perm[g];
+            const BswJob job = jobs[id];
+            const uint8_t *qp = qbase + job.qoff;
+            uint32_t *qs = sh + q_off_words + threadIdx.x;
+            for (int k = 0; k < job.qlen; k += 8) {
+                uint32_t wv = 0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                int jj = k + u;
-                uint32_t b = jj < job.qlen ? (uint32_t) qp[(long long) jj * job.qstride] : 4u;
-                if (b > 4u) b = 4u;
-                wv |= b << (4 * u);
+                for (int u = 0; u < 8; ++u) {
+                    int jj = k + u;
+                    uint32_t b = jj < job.qlen ? (uint32_t) qp[(long long) jj * job.qstride] : 4u;
+                    if (b > 4u) b = 4u;
+                    wv |= b << (4 * u);
+                }
+                qs[(k >> 3) * nthr] = wv;
             }
-            qs[(k >> 3) * nthr] = wv;
+            St st; st.base = (unsigned) __cvta_generic_to_shared(sh) + threadIdx.x * state_bytes; st.stride = (unsigned) nthr * state_bytes;
+            QSmem4 qf; qf.base = (unsigned) __cvta_generic_to_shared(qs); qf.stride = (unsigned) nthr * 4u;
+            BswOut o;
+            bsw_extend_one(st, qf, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
+            out[id] = o;
         }
-        SmemPacked st; st.base = (unsigned) __cvta_generic_to_shared(sh + threadIdx.x); st.stride = (unsigned) nthr * 4u;
-        QSmem4 qf; qf.base = (unsigned) __cvta_generic_to_shared(qs); qf.stride = (unsigned) nthr * 4u;
-        BswOut o;
-        bsw_extend_one(st, qf, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
-        out[id] = o;
     }
     if (cells) {
 #pragma unroll
@@ -325,21 +351,31 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     BM2_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, idx_in, idx_out, n, 0, 32, stream));
     bsw_class_off_kernel<<<1, 32, 0, stream>>>(class_cnt, class_off);
 
+    static bool attr_set = false;
+    if (!attr_set) {   // one function, several dynamic sizes: raise the limit once
+        BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    int n_sm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     for (int c = 0; c < BSW_NCLASS; ++c) {
-        int W = h_class_bound[c] + 2;
-        int QW = h_class_bound[c] / 8 + 1;       // +1: cursor(beg) may touch word qlen>>3 when beg == qlen
-        // threads per CTA: as many as fit ~150 KB (>= 1 CTA/SM), capped at BSW_THREADS
+        const int bound = h_class_bound[c >> 1];
+        const int is16 = c & 1;
+        const int W = bound + 2;
+        const int QW = bound / 8 + 1;            // +1: cursor(beg) may touch word qlen>>3 when beg == qlen
+        const size_t per_thread = (size_t) W * (is16 ? 4 : 2) + (size_t) QW * 4 + 4;
+        // threads per CTA: as many as fit ~112 KB (2 CTAs/SM), capped at BSW_THREADS
         int nthr = BSW_THREADS;
-        while (nthr > 32 && (size_t) (W + QW) * nthr * 4 > 150 * 1024) nthr >>= 1;
-        const int nblk = (n + nthr - 1) / nthr;
-        size_t smem = (size_t) (W + QW) * nthr * 4;
-        static bool attr_set = false;
-        if (!attr_set) {   // one function, several dynamic sizes: raise the limit once
-            BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_set = true;
-        }
+        while (nthr > 32 && per_thread * nthr > 112 * 1024) nthr >>= 1;
+        const size_t smem = per_thread * nthr;
         if (smem > 227 * 1024) { bm2_set_error(ctx_for_error, "bsw: class does not fit shared memory"); return 1; }
-        bsw_thread_kernel<<<nblk, nthr, smem, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, W, d_cells);
+        int ctas_per_sm = (int) ((227 * 1024) / (smem + 1024)); if (ctas_per_sm < 1) ctas_per_sm = 1; if (ctas_per_sm > 16) ctas_per_sm = 16;
+        int nblk = (n + nthr - 1) / nthr;
+        const int cap_blk = n_sm * ctas_per_sm;
+        if (nblk > cap_blk) nblk = cap_blk;
+        if (is16) bsw_thread_kernel<SmemPacked><<<nblk, nthr, smem, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, W, d_cells);
+        else bsw_thread_kernel<SmemPacked8><<<nblk, nthr, smem, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, W, d_cells);
     }
     if (wide_possible) {
         // the wide class needs its size on the host (rare path): one small sync
