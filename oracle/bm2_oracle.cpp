@@ -483,6 +483,8 @@ static void chain_read(const Fm &fm, const bm2_mem_opt_t *opt, const bm2_smem *s
 
 }  // namespace
 
+namespace { void flt_chained_seeds(const bm2_index_desc *x, const bm2_mem_opt_t *opt, int l_query, const uint8_t *query, std::vector<OChain> &chains); }
+
 static const int BLOCK_READS = 512;   /* BATCH_SIZE, src/macro.h:48 */
 
 static void collect_all(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads,
@@ -537,6 +539,7 @@ extern "C" int bm2o_seed_chain(const bm2_index_desc *idx, const bm2_mem_opt_t *o
             if (!skip_block && q > p && l_seq >= opt->min_seed_len) {
                 chain_read(fm, opt, sm.data() + p, (int64_t)(q - p), l_seq, r, ch);
                 chain_filter(opt, ch);
+                flt_chained_seeds(idx, opt, l_seq, reads->codes + reads->offsets[r], ch);
             }
             for (OChain &c : ch) {
                 bm2_chain o; memset(&o, 0, sizeof(o));
@@ -883,6 +886,80 @@ static void extend_read(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const
     }
 }
 
+
+/* local Smith-Waterman score == kswr_t::score of ksw_align2 / ksw_i16 (src/ksw.cpp:234-345): H floored at 0,
+ * E(i+1,j) = max(E - e_del, H - oe_del), F(i,j+1) = max(F - e_ins, H - oe_ins) with unsigned saturation.
+ * (Farrar's lazy-F pass does not feed F-corrected H back into E; that only matters for scoring systems
+ * where an insertion next to a deletion beats a mismatch, which bwa's presets exclude.) */
+static int local_sw_score(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat,
+                          int o_del, int e_del, int o_ins, int e_ins)
+{
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    std::vector<int> H(qlen + 1, 0), E(qlen + 1, 0);
+    int gmax = 0;
+    for (int i = 0; i < tlen; ++i) {
+        int f = 0, diag = 0;                       /* H(i-1, -1) = 0 */
+        for (int j = 0; j < qlen; ++j) {
+            int h = diag + mat[target[i] * 5 + query[j]];
+            diag = H[j + 1];
+            int e = E[j + 1];
+            if (e > h) h = e;
+            if (f > h) h = f;
+            if (h < 0) h = 0;
+            if (h > gmax) gmax = h;
+            H[j + 1] = h;
+            int t = h - oe_del; if (t < 0) t = 0;
+            e -= e_del; if (e < 0) e = 0;
+            E[j + 1] = e > t ? e : t;
+            t = h - oe_ins; if (t < 0) t = 0;
+            f -= e_ins; if (f < 0) f = 0;
+            f = f > t ? f : t;
+        }
+    }
+    return gmax;
+}
+
+/* mem_seed_sw (src/bwamem.cpp:401-427) */
+static int seed_sw(const bm2_index_desc *x, const bm2_mem_opt_t *opt, int l_query, const uint8_t *query, const OSeed &s) {
+    const int64_t l_pac = x->l_pac;
+    if (s.len >= 200) return -1;                               /* MEM_SHORT_LEN */
+    int qb = s.qbeg, qe = s.qbeg + s.len;
+    int64_t rb = s.rbeg, re = s.rbeg + s.len, mid = (rb + re) >> 1;
+    qb -= 50; qb = qb > 0 ? qb : 0;                             /* MEM_SHORT_EXT */
+    qe += 50; qe = qe < l_query ? qe : l_query;
+    rb -= 50; rb = rb > 0 ? rb : 0;
+    re += 50; re = re < l_pac << 1 ? re : l_pac << 1;
+    if (rb < l_pac && l_pac < re) { if (mid < l_pac) re = l_pac; else rb = l_pac; }
+    if (qe - qb >= 200 || re - rb >= 200) return -1;
+    {   /* bns_fetch_seq (src/bntseq.cpp:453-482): clip to the contig of mid */
+        int is_rev = mid >= l_pac;
+        int rid = pos2rid(x, depos(x, mid));
+        int64_t far_beg = x->ann_offset[rid], far_end = far_beg + x->ann_len[rid];
+        if (is_rev) { int64_t tmp = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - tmp; }
+        rb = rb > far_beg ? rb : far_beg;
+        re = re < far_end ? re : far_end;
+    }
+    return local_sw_score(qe - qb, query + qb, (int)(re - rb), x->ref_string + rb, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins);
+}
+
+/* mem_flt_chained_seeds (src/bwamem.cpp:472-504) for the chains of one read */
+void flt_chained_seeds(const bm2_index_desc *x, const bm2_mem_opt_t *opt, int l_query, const uint8_t *query, std::vector<OChain> &chains) {
+    double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log((double) l_query);
+    int min_HSP_score = (int)(opt->a * min_l + .499);
+    if (min_l > 0.05f * l_query) return;
+    for (OChain &c : chains) {
+        std::vector<OSeed> kept;
+        for (OSeed s : c.seeds) {
+            s.score = seed_sw(x, opt, l_query, query, s);
+            if (s.score < 0 || s.score >= min_HSP_score) {
+                s.score = s.score < 0 ? s.len * opt->a : s.score;
+                kept.push_back(s);
+            }
+        }
+        c.seeds.swap(kept);
+    }
+}
+
 }  // namespace
 
 extern "C" int bm2o_seed_chain_extend(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads,
@@ -910,9 +987,7 @@ extern "C" int bm2o_seed_chain_extend(const bm2_index_desc *idx, const bm2_mem_o
             if (!skip_block && q > p && l_seq >= opt->min_seed_len) {
                 chain_read(fm, opt, sm.data() + p, (int64_t)(q - p), l_seq, r, ch);
                 chain_filter(opt, ch);
-                /* mem_flt_chained_seeds (src/bwamem.cpp:472-504) is a no-op unless min_l <= 0.05 * l_query */
-                double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log((double) l_seq);
-                if (!(min_l > 0.05f * l_seq) && !ch.empty()) rc = 2;
+                flt_chained_seeds(idx, opt, l_seq, query, ch);
             }
             std::vector<bm2_alnreg_t> av;
             extend_read(idx, opt, query, l_seq, ch, av, &cells);
