@@ -89,7 +89,7 @@ struct ChainParams {
 };
 
 // working records inside the read's stripe
-struct WSeed { int64_t rbeg; int32_t qbeg, len, next; int32_t _pad; };
+struct WSeed { int64_t rbeg; int32_t qbeg, len, next; int32_t score; };
 struct WChain {
     int64_t pos;
     int64_t first_rbeg, last_rbeg;
@@ -172,7 +172,7 @@ BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_sm
             const int rid = bns_intv2rid_d(cv, rbeg, rbeg + slen);
             if (rid < 0) continue;
             const int sid = n_sd;
-            WSeed &s = ws.seeds[sid]; s.rbeg = rbeg; s.qbeg = (int) sm.m; s.len = slen; s.next = -1; s._pad = 0;
+            WSeed &s = ws.seeds[sid]; s.rbeg = rbeg; s.qbeg = (int) sm.m; s.len = slen; s.next = -1; s.score = slen;
             int lower = -1;
             if (n_ch) {
                 int lo = 0, hi = n_ch;            // first chain with pos >= rbeg
@@ -254,6 +254,86 @@ BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_sm
     return n_kept;
 }
 
+// ---- mem_flt_chained_seeds (src/bwamem.cpp:472-504): only for reads long enough (>= 725 bp by default) ----------
+struct SwParams { int a, o_del, e_del, o_ins, e_ins; int8_t mat[25]; };
+
+// local Smith-Waterman score == kswr_t::score of ksw_align2/ksw_i16 (src/ksw.cpp:234-345); qlen, tlen < 200
+BM2_HD int local_sw_score_d(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const SwParams &p) {
+    const int oe_del = p.o_del + p.e_del, oe_ins = p.o_ins + p.e_ins;
+    int H[201], E[201];
+    for (int j = 0; j <= qlen; ++j) { H[j] = 0; E[j] = 0; }
+    int gmax = 0;
+    for (int i = 0; i < tlen; ++i) {
+        int f = 0, diag = 0;
+        const int tb = target[i];
+        for (int j = 0; j < qlen; ++j) {
+            int h = diag + p.mat[tb * 5 + query[j]];
+            diag = H[j + 1];
+            int e = E[j + 1];
+            if (e > h) h = e;
+            if (f > h) h = f;
+            if (h < 0) h = 0;
+            if (h > gmax) gmax = h;
+            H[j + 1] = h;
+            int t = h - oe_del; if (t < 0) t = 0;
+            e -= p.e_del; if (e < 0) e = 0;
+            E[j + 1] = e > t ? e : t;
+            t = h - oe_ins; if (t < 0) t = 0;
+            f -= p.e_ins; if (f < 0) f = 0;
+            f = f > t ? f : t;
+        }
+    }
+    return gmax;
+}
+
+// mem_seed_sw (src/bwamem.cpp:401-427)
+BM2_HD int seed_sw_d(const ContigView &cv, const SwParams &p, const uint8_t *ref, int l_query, const uint8_t *query, const WSeed &s) {
+    const int64_t l_pac = cv.l_pac;
+    if (s.len >= 200) return -1;
+    int qb = s.qbeg, qe = s.qbeg + s.len;
+    int64_t rb = s.rbeg, re = s.rbeg + s.len;
+    const int64_t mid = (rb + re) >> 1;
+    qb -= 50; qb = qb > 0 ? qb : 0;
+    qe += 50; qe = qe < l_query ? qe : l_query;
+    rb -= 50; rb = rb > 0 ? rb : 0;
+    re += 50; re = re < l_pac << 1 ? re : l_pac << 1;
+    if (rb < l_pac && l_pac < re) { if (mid < l_pac) re = l_pac; else rb = l_pac; }
+    if (qe - qb >= 200 || re - rb >= 200) return -1;
+    {
+        const int is_rev = mid >= l_pac;
+        const int rid = bns_pos2rid_d(cv, bns_depos_d(cv, mid));
+        int64_t far_beg = cv.ann_off[rid], far_end = far_beg + cv.ann_len[rid];
+        if (is_rev) { const int64_t tmp = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - tmp; }
+        rb = rb > far_beg ? rb : far_beg;
+        re = re < far_end ? re : far_end;
+    }
+    return local_sw_score_d(qe - qb, query + qb, (int) (re - rb), ref + rb, p);
+}
+
+// drops the seeds of the surviving chains whose local SW score is below min_hsp (computed on the host with the
+// reference's double arithmetic); seeds keep their order, survivors get score = SW score (or len*a when skipped)
+BM2_HD void chain_flt_seeds_d(const ContigView &cv, const SwParams &p, const uint8_t *ref, int l_query, const uint8_t *query,
+                              int min_hsp, const ChainStripe &ws, int n_kept)
+{
+    for (int k = 0; k < n_kept; ++k) {
+        WChain &c = ws.chains[ws.srt[k]];
+        int prev = -1, kept = 0, i = c.head;
+        for (int t = 0; t < c.n; ++t) {
+            WSeed &s = ws.seeds[i];
+            const int nxt = s.next;
+            const int sc = seed_sw_d(cv, p, ref, l_query, query, s);
+            if (sc < 0 || sc >= min_hsp) {
+                s.score = sc < 0 ? s.len * p.a : sc;
+                if (prev < 0) c.head = i; else ws.seeds[prev].next = i;
+                prev = i; ++kept;
+            }
+            i = nxt;
+        }
+        c.n = kept;
+        if (prev >= 0) { ws.seeds[prev].next = -1; c.tail = prev; }
+    }
+}
+
 // Writes the surviving chains of one read contiguously (reference order) and counts the extension
 // work they imply: one reg per seed, a left job iff qbeg > 0, a right job iff the seed does not
 // reach the read end (src/bwamem.cpp:2229, :2324).
@@ -269,7 +349,7 @@ BM2_HD void chain_finalize_d(const ChainStripe &ws, int n_kept, float frac_rep, 
         for (int i = c.head, t = 0; t < c.n; ++t, i = ws.seeds[i].next) {
             const WSeed &s = ws.seeds[i];
             bm2_seed &d = out_seed[ns++];
-            d.rbeg = s.rbeg; d.qbeg = s.qbeg; d.len = s.len; d.score = s.len; d.chain = k;
+            d.rbeg = s.rbeg; d.qbeg = s.qbeg; d.len = s.len; d.score = s.score; d.chain = k;
             if (s.qbeg) ++nl;
             if (s.qbeg + s.len != l_seq) ++nr;
         }

@@ -182,7 +182,8 @@ struct ChainBufs {
 __global__ void __launch_bounds__(128)
 chain_kernel(ContigView cv, ChainParams cp, const bm2_smem *__restrict__ sm, const int64_t *__restrict__ read_smem_off,
              const int64_t *__restrict__ slot_off, const int64_t *__restrict__ sa, const int64_t *__restrict__ offs, int n_reads,
-             const int32_t *__restrict__ perm, ChainBufs b)
+             const int32_t *__restrict__ perm, ChainBufs b, SwParams sw, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ codes,
+             const int32_t *__restrict__ min_hsp)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_reads) return;
@@ -198,6 +199,7 @@ chain_kernel(ContigView cv, ChainParams cp, const bm2_smem *__restrict__ sm, con
         ChainStripe ws = { b.wseed + base, b.wchain + base, b.ord + base, b.ordpos + base, b.srt + base, b.kv + base, b.flt + base };
         float frac = 0.f;
         nk = chain_read_d(cv, cp, sm + sb, (int) (se - sb), sa + base, len, ws, &frac);
+        if (min_hsp && min_hsp[r] >= 0) chain_flt_seeds_d(cv, sw, ref, len, codes + offs[r], min_hsp[r], ws, nk);
         chain_finalize_d(ws, nk, frac, r, len, b.fin_chain + base, b.fin_seed + base, &ns, &nl, &nr);
     }
     b.n_chain[r] = nk; b.n_seed[r] = ns; b.n_left[r] = nl; b.n_right[r] = nr;
@@ -328,7 +330,7 @@ namespace {
 enum Buf {
     B_CODES, B_OFFS, B_CNT, B_PREV, B_RESEED, B_SMEM_RAW, B_KEYS_IN, B_KEYS_OUT, B_VALS_IN, B_VALS_OUT, B_CUB, B_SMEM, B_SLOT_CNT,
     B_SLOT_OFF, B_READ_SMEM_OFF, B_SA, B_WSEED, B_WCHAIN, B_ORD, B_SRT, B_KV, B_FIN_CHAIN, B_FIN_SEED, B_PER_READ, B_SCAN, B_CHAINS,
-    B_SEEDS, B_REGS, B_REG_AUX, B_JOBS, B_NW, B_OUT, B_PERM, B_ORDPOS, B_FLT, B_COUNT_
+    B_SEEDS, B_REGS, B_REG_AUX, B_JOBS, B_NW, B_OUT, B_PERM, B_ORDPOS, B_FLT, B_MINHSP, B_COUNT_
 };
 static_assert(B_COUNT_ <= 64, "bm2_ctx::d[] too small");
 enum HBuf { H_OUT_REGS, H_OUT_OFF, H_SMEM, H_CHAINS, H_SEEDS, H_MISC };
@@ -352,7 +354,7 @@ template <class T> T *P(bm2_ctx *ctx, int b) { return (T *) ctx->d[b].p; }
 
 namespace {
 
-struct Params { FmIndexView fm; ContigView cv; SmemParams sp; ChainParams cp; ExtParams ep; };
+struct Params { FmIndexView fm; ContigView cv; SmemParams sp; ChainParams cp; ExtParams ep; SwParams sw; };
 
 Params make_params(const bm2_ctx *ctx) {
     Params v;
@@ -367,6 +369,7 @@ Params make_params(const bm2_ctx *ctx) {
     v.ep.a = o.a; v.ep.b = o.b; v.ep.o_del = o.o_del; v.ep.e_del = o.e_del; v.ep.o_ins = o.o_ins; v.ep.e_ins = o.e_ins; v.ep.w = o.w;
     v.ep.pen_clip5 = o.pen_clip5; v.ep.pen_clip3 = o.pen_clip3; v.ep.max_chain_gap = o.max_chain_gap; v.ep.mask_level_redun = o.mask_level_redun;
     memcpy(v.ep.mat, o.mat, 25);
+    v.sw.a = o.a; v.sw.o_del = o.o_del; v.sw.e_del = o.e_del; v.sw.o_ins = o.o_ins; v.sw.e_ins = o.e_ins; memcpy(v.sw.mat, o.mat, 25);
     return v;
 }
 
@@ -418,13 +421,18 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     if (n <= 0) return 0;
     const int64_t total = rb->offsets[n];
     int max_len = 1;
+    bool any_flt = false;
+    std::vector<int32_t> min_hsp_host((size_t) n);
     for (int r = 0; r < n; ++r) {
         int64_t l = rb->offsets[r + 1] - rb->offsets[r];
         if (l < 0 || l > 32767) { bm2_set_error(ctx, "read length out of range (0..32767)"); return 1; }
         if (l > max_len) max_len = (int) l;
-        // mem_flt_chained_seeds (src/bwamem.cpp:472-504) needs ksw_align2: only reads this long trigger it
-        double min_l = ctx->opt.min_chain_weight ? 1.1f * ctx->opt.min_chain_weight : 5.5f * log((double) (l > 0 ? l : 1));
-        if (l > 0 && !(min_l > 0.05f * l)) { bm2_set_error(ctx, "long reads (mem_flt_chained_seeds path) are not supported by this build"); return 1; }
+        // mem_flt_chained_seeds (src/bwamem.cpp:472-504) applies to reads with min_l <= 0.05 * l (>= 725 bp by default):
+        // min_HSP_score is computed here with the reference's double arithmetic (log() on the host)
+        const double min_l = ctx->opt.min_chain_weight ? 1.1f * ctx->opt.min_chain_weight : 5.5f * log((double) (l > 0 ? l : 1));
+        int hsp = -1;
+        if (l > 0 && !(min_l > 0.05f * l)) { hsp = (int) (ctx->opt.a * min_l + .499); any_flt = true; }
+        min_hsp_host[r] = hsp;
     }
     bs.max_len = max_len;
     Params pv = make_params(ctx);
@@ -439,6 +447,10 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
         BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[B_OFFS].p, rb->offsets, (size_t) (n + 1) * 8, cudaMemcpyHostToDevice, st));
         d_codes = P<uint8_t>(ctx, B_CODES); d_offs = P<int64_t>(ctx, B_OFFS);
     }
+    if (any_flt) {
+        if (ctx->ensure(ctx->d[B_MINHSP], (size_t) n * 4)) return 1;
+        BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[B_MINHSP].p, min_hsp_host.data(), (size_t) n * 4, cudaMemcpyHostToDevice, st));
+    }
     BM2_CUDA_OK(cudaMemsetAsync(ctx->d[B_CNT].p, 0, sizeof(Counters), st));
     Counters *d_cnt = P<Counters>(ctx, B_CNT);
     Counters h_cnt;
@@ -446,7 +458,13 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     // ---- A. SMEMs -------------------------------------------------------------------------------------------
     if (sg.mark("smem")) return 1;
     const int stripe = max_len + 2;
-    int blocks_a = (n + 127) / 128; const int max_blocks_a = ctx->n_sm * 16; if (blocks_a > max_blocks_a) blocks_a = max_blocks_a;
+    int blocks_a = (n + 127) / 128; int max_blocks_a = ctx->n_sm * 16;
+    {   // per-thread scratch = stripe * (32 + 8) bytes: keep it under ~8 GB for long reads
+        const size_t per_block = (size_t) 128 * stripe * (sizeof(FmPrev) + 8);
+        const size_t fit = ((size_t) 8 << 30) / per_block;
+        if ((size_t) max_blocks_a > fit) max_blocks_a = (int) (fit > (size_t) ctx->n_sm ? fit : (size_t) ctx->n_sm);
+    }
+    if (blocks_a > max_blocks_a) blocks_a = max_blocks_a;
     const size_t thr_a = (size_t) blocks_a * 128;
     if (ctx->ensure(ctx->d[B_PREV], thr_a * stripe * sizeof(FmPrev)) || ctx->ensure(ctx->d[B_RESEED], thr_a * 2 * stripe * 4)) return 1;
     unsigned long long cap = (unsigned long long) n * 16 + 4096;
@@ -530,7 +548,8 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     work_keys_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(P<int64_t>(ctx, B_READ_SMEM_OFF), P<int64_t>(ctx, B_SLOT_OFF), n, wk_in, wv_in);
     if (sort_work(ctx, wk_in, wk_out, wv_in, d_perm, n)) return 1;
     chain_kernel<<<(n + 127) / 128, 128, 0, st>>>(pv.cv, pv.cp, P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_READ_SMEM_OFF),
-                                                  P<int64_t>(ctx, B_SLOT_OFF), P<int64_t>(ctx, B_SA), d_offs, n, d_perm, cb);
+                                                  P<int64_t>(ctx, B_SLOT_OFF), P<int64_t>(ctx, B_SA), d_offs, n, d_perm, cb, pv.sw, ctx->idx.ref, d_codes,
+                                                  any_flt ? P<int32_t>(ctx, B_MINHSP) : nullptr);
 
     // ---- E. scans + compaction ------------------------------------------------------------------------------
     if (sg.mark("compact")) return 1;

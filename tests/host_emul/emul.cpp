@@ -16,7 +16,7 @@
 #include "../../oracle/bm2_oracle.h"
 
 namespace {
-struct Views { FmIndexView fm; ContigView cv; SmemParams sp; ChainParams cp; ExtParams ep; };
+struct Views { FmIndexView fm; ContigView cv; SmemParams sp; ChainParams cp; ExtParams ep; SwParams sw; const bm2_index_desc *idx; const bm2_mem_opt_t *opt; };
 
 Views make_views(const bm2_index_desc *idx, const bm2_mem_opt_t *o) {
     Views v;
@@ -30,6 +30,8 @@ Views make_views(const bm2_index_desc *idx, const bm2_mem_opt_t *o) {
     v.ep.a = o->a; v.ep.b = o->b; v.ep.o_del = o->o_del; v.ep.e_del = o->e_del; v.ep.o_ins = o->o_ins; v.ep.e_ins = o->e_ins; v.ep.w = o->w;
     v.ep.pen_clip5 = o->pen_clip5; v.ep.pen_clip3 = o->pen_clip3; v.ep.max_chain_gap = o->max_chain_gap; v.ep.mask_level_redun = o->mask_level_redun;
     memcpy(v.ep.mat, o->mat, 25);
+    v.sw.a = o->a; v.sw.o_del = o->o_del; v.sw.e_del = o->e_del; v.sw.o_ins = o->o_ins; v.sw.e_ins = o->e_ins; memcpy(v.sw.mat, o->mat, 25);
+    v.idx = idx; v.opt = o;
     return v;
 }
 
@@ -88,6 +90,11 @@ void stage_chain(const Views &v, const bm2_read_batch *rb, const Stage1 &s1, Sta
             ChainStripe st = { ws.data(), wc.data(), ord.data(), ordpos.data(), srt.data(), kv.data(), flt.data() };
             float frac = 0;
             int nk = chain_read_d(v.cv, v.cp, s1.smems.data() + sb, (int) (se - sb), s1.sa.data() + s1.slot_off[sb], len, st, &frac);
+            {
+                const double min_l = v.opt->min_chain_weight ? 1.1f * v.opt->min_chain_weight : 5.5f * log((double) len);
+                if (!(min_l > 0.05f * len))
+                    chain_flt_seeds_d(v.cv, v.sw, v.idx->ref_string, len, rb->codes + rb->offsets[r], (int) (v.opt->a * min_l + .499), st, nk);
+            }
             std::vector<bm2_chain> oc(nk + 1); std::vector<bm2_seed> os(slots + 1);
             int ns = 0, nl = 0, nr = 0;
             chain_finalize_d(st, nk, frac, r, len, oc.data(), os.data(), &ns, &nl, &nr);
