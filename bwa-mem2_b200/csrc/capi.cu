@@ -113,6 +113,11 @@ extern "C" int bm2_create(bm2_ctx **out, int device, const bm2_index_desc *idx, 
         bm2_set_error(nullptr, "bm2_create: cudaStreamCreate failed"); delete ctx; return 1;
     }
     ctx->stream = ctx->own_stream;
+    if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        bm2_set_error(nullptr, "bm2_create: side stream/events failed"); delete ctx; return 1;
+    }
     if (idx) {
         if (bm2_upload_index(ctx, idx)) { bm2_set_error(nullptr, "bm2_create: " + ctx->err); bm2_destroy(ctx); return 1; }
     }
@@ -129,6 +134,9 @@ extern "C" void bm2_destroy(bm2_ctx *ctx) {
     for (HostBuf *b : ctx->all_host()) if (b->p) cudaFreeHost(b->p);
     for (cudaEvent_t ev : ctx->events) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
 }
 

@@ -127,9 +127,49 @@ struct QPlain {                    // read codes straight from memory
     BM2_HD int operator()(int j) const { return p[j]; }
 };
 
+// Pass 3 alone (bwtSeedStrategyAllPosOneThread, src/FMI_search.cpp:726-812): forward-only, no interval list, so it
+// runs as its own lean kernel (few registers, one hot loop) next to the pass-1/2 automaton.
+template <class Emit, class Q>
+BM2_HD void fm_smem_pass3(const FmIndexView &fm, const Q &q, int len, const SmemParams &sp, Emit &emit, unsigned &n_ext)
+{
+    if (len <= 0 || sp.max_mem_intv <= 0) return;
+    int x = 0, j = 0, next_x = 0;
+    bool searching = false;
+    FmIv cur; cur.k = cur.l = cur.s = 0;
+    for (;;) {
+        // control: find the next extension to do
+        bool need = false;
+        int base = 0;
+        while (!need) {
+            if (!searching) {
+                if (x >= len) return;
+                next_x = x + 1;
+                const int a = q(x);
+                if (a > 3) { x = next_x; continue; }
+                cur.k = fm_count(fm, a); cur.l = fm_count(fm, 3 - a); cur.s = fm_count(fm, a + 1) - cur.k;
+                j = x + 1; searching = true;
+            }
+            if (j >= len) { x = next_x; searching = false; continue; }
+            next_x = j + 1;
+            const int a = q(j);
+            if (a > 3) { x = next_x; searching = false; continue; }
+            base = 3 - a; need = true;
+        }
+        BM2_SYNCWARP();
+        FmIv req; req.k = cur.l; req.l = cur.k; req.s = cur.s;
+        FmIv r = fm_backward_ext(fm, req, base);
+        ++n_ext;
+        cur.k = r.l; cur.l = r.k; cur.s = r.s;
+        if (cur.s < sp.max_mem_intv && j - x + 1 >= sp.min_seed_len + 1) {
+            if (cur.s > 0) emit(x, j, cur.k, cur.l, cur.s);
+            x = next_x; searching = false;
+        } else ++j;
+    }
+}
+
 template <class Emit, class Q>
 BM2_HD void fm_smem_read(const FmIndexView &fm, const Q &q, int len, const SmemParams &sp, FmPrev *prev,
-                         int32_t *reseed, Emit &emit, unsigned &n_ext)
+                         int32_t *reseed, Emit &emit, unsigned &n_ext, bool with_pass3 = true)
 {
     enum { ST_SEARCH_BEGIN, ST_FWD, ST_FWD_END, ST_BWD_ROW, ST_BWD_ITEM, ST_SEARCH_END, ST_P3_BEGIN, ST_P3_FWD, ST_DONE };
     if (len <= 0) return;
@@ -190,7 +230,7 @@ BM2_HD void fm_smem_read(const FmIndexView &fm, const Q &q, int len, const SmemP
                 if (pass == 2) {            // re-seeding (src/bwamem.cpp:695-753)
                     if (i_reseed < n_reseed) { x = reseed[2 * i_reseed]; min_intv = reseed[2 * i_reseed + 1]; ++i_reseed; st = ST_SEARCH_BEGIN; continue; }
                     pass = 3; x = 0;
-                    if (sp.max_mem_intv <= 0) { st = ST_DONE; continue; }
+                    if (sp.max_mem_intv <= 0 || !with_pass3) { st = ST_DONE; continue; }
                     st = ST_P3_BEGIN;
                 }
             } else if (st == ST_P3_BEGIN) {   // bwtSeedStrategyAllPosOneThread (src/FMI_search.cpp:726-812)

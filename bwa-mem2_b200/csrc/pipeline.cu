@@ -121,10 +121,41 @@ smem_kernel(FmIndexView fm, SmemParams sp, const uint8_t *__restrict__ codes, co
                 qsh[(k >> 3) * blockDim.x + threadIdx.x] = wv;
             }
             QShared4 q = { (unsigned) __cvta_generic_to_shared(qsh + threadIdx.x), (unsigned) blockDim.x * 4u };
-            fm_smem_read(fm, q, len, sp, prev, reseed, emit, n_ext);
+            fm_smem_read(fm, q, len, sp, prev, reseed, emit, n_ext, false);
         } else {
             QPlain q = { codes + o };
-            fm_smem_read(fm, q, len, sp, prev, reseed, emit, n_ext);
+            fm_smem_read(fm, q, len, sp, prev, reseed, emit, n_ext, false);
+        }
+    }
+    if (n_ext) atomicAdd(&cnt->n_ext, (unsigned long long) n_ext);
+}
+
+// A'. pass 3 (forward-only seeding) as its own kernel on a second stream: lean state, high occupancy
+template <bool USE_SMEM>
+__global__ void __launch_bounds__(128, 12)
+smem_pass3_kernel(FmIndexView fm, SmemParams sp, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, int n_reads,
+                  bm2_smem *out, unsigned long long cap, Counters *cnt)
+{
+    extern __shared__ uint32_t qsh[];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    unsigned n_ext = 0;
+    for (int r = tid; r < n_reads; r += nthr) {
+        const int64_t o = offs[r];
+        const int len = (int) (offs[r + 1] - o);
+        SmemAppend emit = { out, cap, &cnt->n_smem, (uint32_t) r };
+        if (USE_SMEM) {
+            const uint8_t *qp = codes + o;
+            for (int k = 0; k < len; k += 8) {
+                uint32_t wv = 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { uint32_t b = k + u < len ? (uint32_t) qp[k + u] : 4u; wv |= (b > 4u ? 4u : b) << (4 * u); }
+                qsh[(k >> 3) * blockDim.x + threadIdx.x] = wv;
+            }
+            QShared4 q = { (unsigned) __cvta_generic_to_shared(qsh + threadIdx.x), (unsigned) blockDim.x * 4u };
+            fm_smem_pass3(fm, q, len, sp, emit, n_ext);
+        } else {
+            QPlain q = { codes + o };
+            fm_smem_pass3(fm, q, len, sp, emit, n_ext);
         }
     }
     if (n_ext) atomicAdd(&cnt->n_ext, (unsigned long long) n_ext);
@@ -155,19 +186,25 @@ __global__ void read_smem_off_kernel(const uint64_t *keys_sorted, int64_t n_smem
     read_smem_off[r] = lo;
 }
 
-// C. one seed slot per thread
+// C. one seed slot per thread.  owner[slot] = index of the SMEM the slot belongs to, by a scatter of the SMEM
+// indices to their first slot followed by an inclusive max-scan (no per-thread binary search over slot_off).
+__global__ void slot_head_kernel(const int64_t *__restrict__ slot_off, int64_t n_smem, int32_t *owner) {
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_smem) return;
+    if (slot_off[i + 1] > slot_off[i]) owner[slot_off[i]] = (int32_t) i;
+}
+
 __global__ void __launch_bounds__(256)
-sa_kernel(FmIndexView fm, const bm2_smem *__restrict__ sm, const int64_t *__restrict__ slot_off, int64_t n_smem, int64_t n_slots, int max_occ,
-          int64_t *sa, Counters *cnt)
+sa_kernel(FmIndexView fm, const bm2_smem *__restrict__ sm, const int64_t *__restrict__ slot_off, const int32_t *__restrict__ owner,
+          int64_t n_slots, int max_occ, int64_t *sa, Counters *cnt)
 {
     int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     int lf = 0;
     if (t < n_slots) {
-        int64_t lo = 0, hi = n_smem;                        // last SMEM with slot_off <= t
-        while (lo + 1 < hi) { int64_t mid = (lo + hi) >> 1; if (slot_off[mid] <= t) lo = mid; else hi = mid; }
-        const bm2_smem x = sm[lo];
+        const int32_t o = owner[t];
+        const bm2_smem x = sm[o];
         const int64_t step = x.s > max_occ ? x.s / max_occ : 1;
-        sa[t] = fm_sa_of_row(fm, x.k + (t - slot_off[lo]) * step, &lf);
+        sa[t] = fm_sa_of_row(fm, x.k + (t - slot_off[o]) * step, &lf);
     }
     if (lf) atomicAdd(&cnt->n_lf, (unsigned long long) lf);
 }
@@ -330,7 +367,7 @@ namespace {
 enum Buf {
     B_CODES, B_OFFS, B_CNT, B_PREV, B_RESEED, B_SMEM_RAW, B_KEYS_IN, B_KEYS_OUT, B_VALS_IN, B_VALS_OUT, B_CUB, B_SMEM, B_SLOT_CNT,
     B_SLOT_OFF, B_READ_SMEM_OFF, B_SA, B_WSEED, B_WCHAIN, B_ORD, B_SRT, B_KV, B_FIN_CHAIN, B_FIN_SEED, B_PER_READ, B_SCAN, B_CHAINS,
-    B_SEEDS, B_REGS, B_REG_AUX, B_JOBS, B_NW, B_OUT, B_PERM, B_ORDPOS, B_FLT, B_MINHSP, B_COUNT_
+    B_SEEDS, B_REGS, B_REG_AUX, B_JOBS, B_NW, B_OUT, B_PERM, B_ORDPOS, B_FLT, B_MINHSP, B_OWNER, B_COUNT_
 };
 static_assert(B_COUNT_ <= 64, "bm2_ctx::d[] too small");
 enum HBuf { H_OUT_REGS, H_OUT_OFF, H_SMEM, H_CHAINS, H_SEEDS, H_MISC };
@@ -471,6 +508,19 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (ctx->ensure(ctx->d[B_SMEM_RAW], cap * sizeof(bm2_smem))) return 1;
         BM2_CUDA_OK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), st));
+        // fork: pass 3 on the side stream, passes 1+2 on the main stream (both only append to the SMEM buffer)
+        BM2_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
+        BM2_CUDA_OK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+        {
+            int blocks_p3 = (n + 127) / 128; if (blocks_p3 > ctx->n_sm * 12) blocks_p3 = ctx->n_sm * 12;
+            if (max_len <= 256) {
+                const size_t qsm = (size_t) ((max_len + 7) / 8) * 128 * 4;
+                smem_pass3_kernel<true><<<blocks_p3, 128, qsm, ctx->side_stream>>>(pv.fm, pv.sp, d_codes, d_offs, n, P<bm2_smem>(ctx, B_SMEM_RAW), cap, d_cnt);
+            } else {
+                smem_pass3_kernel<false><<<blocks_p3, 128, 0, ctx->side_stream>>>(pv.fm, pv.sp, d_codes, d_offs, n, P<bm2_smem>(ctx, B_SMEM_RAW), cap, d_cnt);
+            }
+            BM2_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        }
         if (max_len <= 256) {
             const size_t qsm = (size_t) ((max_len + 7) / 8) * 128 * 4;
             smem_kernel<true><<<blocks_a, 128, qsm, st>>>(pv.fm, pv.sp, d_codes, d_offs, n, stripe, P<FmPrev>(ctx, B_PREV), P<int32_t>(ctx, B_RESEED),
@@ -479,6 +529,7 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
             smem_kernel<false><<<blocks_a, 128, 0, st>>>(pv.fm, pv.sp, d_codes, d_offs, n, stripe, P<FmPrev>(ctx, B_PREV), P<int32_t>(ctx, B_RESEED),
                                                           P<bm2_smem>(ctx, B_SMEM_RAW), cap, d_cnt);
         }
+        BM2_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_join, 0));          // join
         BM2_CUDA_OK(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         BM2_CUDA_OK(cudaStreamSynchronize(st));
         if (h_cnt.n_smem <= cap) break;
@@ -524,9 +575,18 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     if (sg.mark("sal")) return 1;
     const size_t sl1 = (size_t) (n_slots > 0 ? n_slots : 1) + 1;
     if (ctx->ensure(ctx->d[B_SA], sl1 * 8)) return 1;
-    if (n_slots > 0)
-        sa_kernel<<<(unsigned) ((n_slots + 255) / 256), 256, 0, st>>>(pv.fm, P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_SLOT_OFF), n_smem, n_slots,
+    if (n_slots > 0) {
+        if (ctx->ensure(ctx->d[B_OWNER], sl1 * 4 * 2)) return 1;
+        int32_t *own_in = P<int32_t>(ctx, B_OWNER), *own = own_in + sl1;
+        BM2_CUDA_OK(cudaMemsetAsync(own_in, 0, sl1 * 4, st));
+        slot_head_kernel<<<(unsigned) ((n_smem + 255) / 256), 256, 0, st>>>(P<int64_t>(ctx, B_SLOT_OFF), n_smem, own_in);
+        size_t sbytes = 0;
+        cub::DeviceScan::InclusiveScan(nullptr, sbytes, own_in, own, cub::Max(), (int) n_slots);
+        if (ctx->ensure(ctx->d[B_CUB], sbytes)) return 1;
+        BM2_CUDA_OK(cub::DeviceScan::InclusiveScan(ctx->d[B_CUB].p, sbytes, own_in, own, cub::Max(), (int) n_slots, st));
+        sa_kernel<<<(unsigned) ((n_slots + 255) / 256), 256, 0, st>>>(pv.fm, P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_SLOT_OFF), own, n_slots,
                                                                         ctx->opt.max_occ, P<int64_t>(ctx, B_SA), d_cnt);
+    }
 
     // ---- D. chaining --------------------------------------------------------------------------------------
     if (sg.mark("chain")) return 1;

@@ -51,7 +51,8 @@ void stage_smem_sa(const Views &v, const bm2_mem_opt_t *o, const bm2_read_batch 
             bm2_smem x; x.rid = r; x.m = m; x.n = n; x.k = k; x.l = l; x.s = ss; s.smems.push_back(x);
         };
         QPlain qq = { q };
-        fm_smem_read(v.fm, qq, len, v.sp, prev.data(), reseed.data(), emit, n_ext);
+        fm_smem_read(v.fm, qq, len, v.sp, prev.data(), reseed.data(), emit, n_ext, false);
+        fm_smem_pass3(v.fm, qq, len, v.sp, emit, n_ext);
         s.n_ext += n_ext;
     }
     std::stable_sort(s.smems.begin(), s.smems.end(), [](const bm2_smem &a, const bm2_smem &b) {
