@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q 2>&1 | tail -6
+python bench.py --steps 3 --warmup 2 > gpurun_out/bench_pipe_3g.json 2> gpurun_out/bench_pipe_3g.err; tail -2 gpurun_out/bench_pipe_3g.err; cat gpurun_out/bench_pipe_3g.json
+ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 500 --csv --log-file gpurun_out/launches_r1d_3g.csv python bench.py --steps 1 --warmup 2 > gpurun_out/ncu_bench.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:smem_kernel|smem_pass3_kernel" -s 6 -c 2 -o gpurun_out/prof_smem_r1d python bench.py --steps 1 --warmup 2 > gpurun_out/ncu_full_smem.log 2>&1
+ls -la gpurun_out
