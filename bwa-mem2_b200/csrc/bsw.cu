@@ -280,6 +280,164 @@ bsw_thread_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ p
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-per-job kernel for long queries (the wide class: qlen > 1024 or 32-bit scores; long reads).
+// A row of the band (<= 2w+1 columns) is split over the 32 lanes, CMAX columns per lane.  F, the only state
+// that runs along the row, depends on M(k), k < j only:
+//     F(j) = max(0, max_{beg<=k<j} (max(M(k) - oe_ins, 0) - (j-1-k) e_ins))
+// so one exclusive max-scan per row (5 shuffles) replaces the sequential sweep; everything else is per column.
+// State {H(i-1,j-1), E(i,j)} lives in a per-warp circular buffer of WCAP >= 2w+8 columns in shared memory;
+// columns the band has never reached are initialised on demand with the first-row values, which reproduces the
+// reference's "stale eh[] entries" exactly (tests/host_emul/bsw_rowscan.cpp is the CPU model of this kernel).
+// ---------------------------------------------------------------------------------------------
+#define BSWW_WARPS 4
+template <int CMAX>
+__global__ void __launch_bounds__(BSWW_WARPS * 32)
+bsw_warp_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ perm, const int32_t *__restrict__ class_off,
+                BswOut *__restrict__ out, const uint8_t *__restrict__ tbase, const uint8_t *__restrict__ qbase, BswParams p,
+                int *next_job, unsigned long long *cells)
+{
+    constexpr int WCAP = 32 * CMAX + 8;
+    __shared__ int shH[BSWW_WARPS][WCAP], shE[BSWW_WARPS][WCAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int *H = shH[wid], *E = shE[wid];
+    const int first = class_off[BSW_NCLASS], last = class_off[BSW_NCLASS + 1];
+    const int oe_del = p.o_del + p.e_del, oe_ins = p.o_ins + p.e_ins, e_del = p.e_del, e_ins = p.e_ins;
+    const int NEG = -(1 << 29);
+    unsigned long long ncell = 0;
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = first + atomicAdd(next_job, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= last) break;
+        const int id = perm[g];
+        const BswJob job = jobs[id];
+        const uint8_t *qp = qbase + job.qoff, *tp = tbase + job.toff;
+        const int qlen = job.qlen, tlen = job.tlen, h0 = job.h0;
+        int w = p.w;
+        {
+            unsigned t1 = ((unsigned) (qlen * p.a) + (unsigned) (p.end_bonus - p.o_ins)) & 0xFFFFu;
+            int max_ins = (int) (t1 / (unsigned) e_ins) + 1; if (max_ins < 1) max_ins = 1;
+            unsigned t2 = ((unsigned) (qlen * p.a) + (unsigned) (p.end_bonus - p.o_del)) & 0xFFFFu;
+            int max_del = (int) (t2 / (unsigned) e_del) + 1; if (max_del < 1) max_del = 1;
+            if (w > max_ins) w = max_ins;
+            if (w > max_del) w = max_del;
+        }
+        // the launcher guarantees 2*w+2 <= 32*CMAX for this instantiation
+        int max_init = -1;
+        int best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0;
+        int beg = 0, end = qlen;
+        for (int i = 0; i < tlen; ++i) {
+            if (beg < i - w) beg = i - w;
+            if (end > i + w + 1) end = i + w + 1;
+            if (end > qlen) end = qlen;
+            // first visit of columns (max_init, end]: first-row values  H(-1, j-1), E = 0
+            for (int j = max_init + 1 + lane; j <= end; j += 32) {
+                int v = j == 0 ? h0 : h0 - oe_ins - (j - 1) * e_ins;
+                H[j % WCAP] = v > 0 ? v : 0; E[j % WCAP] = 0;
+            }
+            if (end > max_init) max_init = end;
+            __syncwarp();
+            int h1_init = 0;
+            if (beg == 0) { h1_init = h0 - (p.o_del + e_del * (i + 1)); if (h1_init < 0) h1_init = 0; }
+            const int n = end - beg;
+            const int c = (n + 31) >> 5;
+            const int tb = tp[(long long) i * job.tstride];
+            const int j0 = beg + lane * c;
+            int Mr[CMAX], Er[CMAX], Pl[CMAX];
+            int run = NEG;
+#pragma unroll
+            for (int k = 0; k < CMAX; ++k) {
+                const int j = j0 + k;
+                Mr[k] = 0; Er[k] = 0; Pl[k] = NEG;
+                if (k < c && j < end) {
+                    const int hd = H[j % WCAP];
+                    Er[k] = E[j % WCAP];
+                    const int qb = qp[(long long) j * job.qstride];
+                    const int s = (qb > 3 || tb > 3) ? -1 : (qb == tb ? p.a : -p.b);
+                    const int m = hd ? hd + s : 0;
+                    Mr[k] = m;
+                    Pl[k] = run;
+                    run = max(run, max(m - oe_ins, 0) + j * e_ins);
+                }
+            }
+            // exclusive max-scan of the lane aggregates
+            int incl = run;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl = max(incl, o); }
+            int lp = __shfl_up_sync(0xffffffffu, incl, 1); if (lane == 0) lp = NEG;
+            __syncwarp();
+            // finish the cells, write the next row's state
+            int lm = -1, lmj = -1, hlast = 0;                // (m, mj) per lane: 32-bit scores do not fit one packed key
+#pragma unroll
+            for (int k = 0; k < CMAX; ++k) {
+                const int j = j0 + k;
+                if (k < c && j < end) {
+                    const int P = max(lp, Pl[k]);
+                    int f = P - (j - 1) * e_ins; if (f < 0 || P == NEG) f = 0;
+                    const int h = max(max(Mr[k], Er[k]), f);
+                    E[j % WCAP] = max(Er[k] - e_del, max(Mr[k] - oe_del, 0));
+                    if (k > 0) H[j % WCAP] = hlast;           // H(i, j-1) = h of the previous column of this lane
+                    hlast = h;
+                    if (h >= lm) { lm = h; lmj = j; }
+                }
+            }
+            // first column of each lane takes the last h of the previous lane (or h1_init at column beg)
+            const int ncols_lane = max(0, min(c, end - j0));
+            int carry = __shfl_up_sync(0xffffffffu, hlast, 1);
+            if (ncols_lane > 0) H[j0 % WCAP] = (lane == 0) ? h1_init : carry;
+            // h1 = h of column end-1 (owner: lane (n-1)/c), H[end] = h1, E[end] = 0
+            int h1 = h1_init;
+            if (n > 0) h1 = __shfl_sync(0xffffffffu, hlast, (n - 1) / c);
+            if (lane == 0) { H[end % WCAP] = h1; E[end % WCAP] = 0; }
+            ncell += (lane == 0 && n > 0) ? (unsigned) n : 0u;
+            // row maximum: largest h, among equals the largest column
+            int m = lm, mj = lmj;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const int om = __shfl_xor_sync(0xffffffffu, m, d), oj = __shfl_xor_sync(0xffffffffu, mj, d);
+                if (om > m || (om == m && oj > mj)) { m = om; mj = oj; }
+            }
+            if (m < 0) { m = 0; mj = -1; }
+            __syncwarp();
+            if (end == qlen) {
+                if (h1 >= gscore) best_ie = i;
+                if (h1 > gscore) gscore = h1;
+            }
+            if (m == 0) break;
+            if (m > best) {
+                best = m; best_i = i; best_j = mj;
+                int dd = mj - i; dd = dd < 0 ? -dd : dd;
+                if (dd > max_off) max_off = dd;
+            } else if (p.zdrop > 0) {
+                const int di = i - best_i, dj = mj - best_j;
+                const int pen = di > dj ? di - dj : dj - di;
+                if (best - m - pen > p.zdrop) break;
+            }
+            // shrink the band to the non-zero support of the row just written
+            int fz = end, lz = beg - 1;                       // first / last non-zero column in [beg, end]
+            for (int j = beg + lane; j <= end; j += 32) {
+                if ((H[j % WCAP] | E[j % WCAP]) != 0) { if (j < end && j < fz) fz = j; if (j > lz) lz = j; }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                fz = min(fz, __shfl_xor_sync(0xffffffffu, fz, d));
+                lz = max(lz, __shfl_xor_sync(0xffffffffu, lz, d));
+            }
+            if (lz < fz) lz = fz - 1;                          // (all zero: cannot happen after m > 0; scalar semantics anyway)
+            beg = fz;                                          // == end when the whole row is zero
+            end = lz + 2 < qlen ? lz + 2 : qlen;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            BswOut o; o.score = best; o.qle = best_j + 1; o.tle = best_i + 1; o.gtle = best_ie + 1; o.gscore = gscore; o.max_off = max_off;
+            out[id] = o;
+        }
+        __syncwarp();
+    }
+    if (cells && lane == 0 && ncell) atomicAdd(cells, ncell);
+}
+
 // jobs whose scores need 32 bits or whose query does not fit the shared-memory classes:
 // state in a private global-memory stripe (correctness path for the rare scalar class,
 // reference src/bwamem.cpp:2310; long reads get the warp-per-job kernel in a later round).
@@ -372,7 +530,16 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
         else bsw_thread_kernel<SmemPacked8><<<nblk, nthr, smem, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, W, d_cells);
     }
     if (wide_possible) {
-        // the wide class needs its size on the host (rare path): one small sync
+        int *next_job = class_cnt + 48;                    // zeroed with class_cnt above
+        const int wblocks = n_sm * 4;
+        if (2 * prm.w + 2 <= 32 * 7)
+            bsw_warp_kernel<7><<<wblocks, BSWW_WARPS * 32, 0, stream>>>(d_jobs, idx_out, class_off, d_out, d_tbase, d_qbase, prm, next_job, d_cells);
+        else if (2 * prm.w + 2 <= 32 * 13)
+            bsw_warp_kernel<13><<<wblocks, BSWW_WARPS * 32, 0, stream>>>(d_jobs, idx_out, class_off, d_out, d_tbase, d_qbase, prm, next_job, d_cells);
+        else if (2 * prm.w + 2 <= 32 * 32)
+            bsw_warp_kernel<32><<<wblocks, BSWW_WARPS * 32, 0, stream>>>(d_jobs, idx_out, class_off, d_out, d_tbase, d_qbase, prm, next_job, d_cells);
+        else {
+        // very wide bands: state in global memory, one job per thread; the class size is needed on the host
         int32_t h_off[2];
         BM2_CUDA_OK(cudaMemcpyAsync(h_off, class_off + BSW_NCLASS, 8, cudaMemcpyDeviceToHost, stream));
         BM2_CUDA_OK(cudaStreamSynchronize(stream));
@@ -396,6 +563,7 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
             int blocks = (nw + 63) / 64; if (blocks > 148 * 8) blocks = 148 * 8;
             bsw_wide_kernel<<<blocks, 64, 0, stream>>>(d_jobs, idx_out, class_off, d_out, d_tbase, d_qbase, prm, g_wide.state,
                                                        g_wide.state_off, d_cells);
+        }
         }
     }
     BM2_CUDA_OK(cudaGetLastError());

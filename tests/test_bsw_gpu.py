@@ -46,10 +46,12 @@ def _random_jobs(rng, n, qmax, tmax, sim=0.9, nrate=0.01, h0max=150):
 
 
 @pytest.mark.parametrize("seed,qmax,tmax,w", [(1, 151, 400, 100), (2, 151, 400, 200), (3, 40, 90, 100), (4, 700, 900, 100),
-                                               (5, 1500, 1700, 100), (6, 151, 400, 10)])
+                                               (5, 1500, 1700, 100), (6, 151, 400, 10),
+                                               # long queries: the warp-per-job kernel (row-parallel scan), three band widths
+                                               (7, 4000, 4300, 100), (8, 3000, 3300, 200), (9, 2500, 2800, 300), (10, 2000, 2200, 600)])
 def test_random_jobs_match_oracle(pkg, gpu_ctx, seed, qmax, tmax, w):
     rng = np.random.default_rng(seed)
-    n = 3000 if qmax <= 151 else 400
+    n = 3000 if qmax <= 151 else (400 if qmax <= 1500 else 120)
     len1, len2, h0, idr, idq, ref, qer = _random_jobs(rng, n, qmax, tmax)
     p = np.zeros(n, pkg.capi.PAIR_DT)
     p["len1"] = len1; p["len2"] = len2; p["h0"] = h0; p["idr"] = idr; p["idq"] = idq
