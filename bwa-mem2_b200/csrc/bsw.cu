@@ -75,35 +75,46 @@ __global__ void bsw_class_off_kernel(const int32_t *class_cnt, int32_t *class_of
 // ---------------------------------------------------------------------------------------------
 // The extension DP of one job (one thread).  `St` abstracts the per-column state storage.
 // ---------------------------------------------------------------------------------------------
-// Per-column DP state {H(i-1,j-1), E(i,j)} in shared memory as two separate arrays laid out [column][thread]
-// (bank conflict free for any per-thread column): narrow loads/stores zero-extend for free on the LSU pipe, so no
-// integer-ALU instructions are spent on packing/unpacking (the kernel is ALU-pipe bound, profiles/r1b_bsw_r1b.md).
-template <int BYTES>              // 1: scores < 256 (the 2x151 bp workload), 2: scores < 32768
-struct SmemState {
-    unsigned hbase, ebase;        // shared-window addresses of the thread's column 0 in the H and the E array
-    unsigned stride;              // blockDim.x * BYTES
-    static constexpr unsigned kStateBytes = 2 * BYTES;
-    __device__ __forceinline__ uint32_t ld(unsigned a) const {
-        uint32_t w;
-        if (BYTES == 1) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(w) : "r"(a));
-        else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w) : "r"(a));
-        return w;
+// (Measured: splitting H and E into separate narrow arrays - 2 LDS + 2 STS per cell instead of pack/unpack ALU
+// ops - made the kernel 6 % slower, profiles/r1d notes; the packed word stays.)
+struct SmemPacked {            // H | E<<16 in shared memory, [column][thread]; explicit shared-space accesses
+    unsigned base;             // shared-window address of &sh[threadIdx.x]
+    unsigned stride;           // blockDim.x * 4 bytes
+    __device__ __forceinline__ uint32_t ldw(int j) const {
+        uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + (unsigned) j * stride)); return w;
     }
-    __device__ __forceinline__ void st(unsigned a, uint32_t w) const {
-        if (BYTES == 1) asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(w) : "memory");
-        else asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(w) : "memory");
+    __device__ __forceinline__ void stw(int j, uint32_t w) const {
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(base + (unsigned) j * stride), "r"(w) : "memory");
     }
-    __device__ __forceinline__ void get(int j, int &h, int &e) const { const unsigned o = (unsigned) j * stride; h = (int) ld(hbase + o); e = (int) ld(ebase + o); }
-    __device__ __forceinline__ void put(int j, int h, int e) const { const unsigned o = (unsigned) j * stride; st(hbase + o, (uint32_t) h); st(ebase + o, (uint32_t) e); }
-    __device__ __forceinline__ bool zero(int j) const { const unsigned o = (unsigned) j * stride; return (ld(hbase + o) | ld(ebase + o)) == 0u; }
+    __device__ __forceinline__ void get(int j, int &h, int &e) const { uint32_t w = ldw(j); h = (int) (w & 0xFFFFu); e = (int) (w >> 16); }
+    __device__ __forceinline__ void put(int j, int h, int e) const { stw(j, __byte_perm((uint32_t) h, (uint32_t) e, 0x5410)); }
+    __device__ __forceinline__ bool zero(int j) const { return ldw(j) == 0u; }
     // row maximum as one signed key: (h << 16) | j  (h < 2^15, j < 2^16)
     typedef int key_t;
+    static constexpr unsigned kStateBytes = 4;
     static __device__ __forceinline__ key_t key(int h, int j) { return (h << 16) | j; }
     static __device__ __forceinline__ int key_h(key_t k) { return k >> 16; }
     static __device__ __forceinline__ int key_j(key_t k) { return k & 0xFFFF; }
 };
-typedef SmemState<2> SmemPacked;
-typedef SmemState<1> SmemPacked8;
+
+struct SmemPacked8 {           // H | E<<8 in 16 bits: jobs whose best possible score fits 8 bits (the 2x151 bp workload)
+    unsigned base;             // shared-window address of the thread's column 0
+    unsigned stride;           // blockDim.x * 2 bytes
+    __device__ __forceinline__ uint32_t ldw(int j) const {
+        uint16_t w; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w) : "r"(base + (unsigned) j * stride)); return (uint32_t) w;
+    }
+    __device__ __forceinline__ void stw(int j, uint32_t w) const {
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(base + (unsigned) j * stride), "h"((uint16_t) w) : "memory");
+    }
+    __device__ __forceinline__ void get(int j, int &h, int &e) const { uint32_t w = ldw(j); h = (int) (w & 0xFFu); e = (int) (w >> 8); }
+    __device__ __forceinline__ void put(int j, int h, int e) const { stw(j, (uint32_t) h | ((uint32_t) e << 8)); }
+    __device__ __forceinline__ bool zero(int j) const { return ldw(j) == 0u; }
+    typedef int key_t;
+    static constexpr unsigned kStateBytes = 2;
+    static __device__ __forceinline__ key_t key(int h, int j) { return (h << 16) | j; }
+    static __device__ __forceinline__ int key_h(key_t k) { return k >> 16; }
+    static __device__ __forceinline__ int key_j(key_t k) { return k & 0xFFFF; }
+};
 
 struct GmemWide {              // {H,E} int32 in global memory, private stripe per thread
     int2 *base;
@@ -263,10 +274,7 @@ bsw_thread_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ p
                 }
                 qs[(k >> 3) * nthr] = wv;
             }
-            St st;
-            st.stride = (unsigned) nthr * (state_bytes / 2);
-            st.hbase = (unsigned) __cvta_generic_to_shared(sh) + threadIdx.x * (state_bytes / 2);
-            st.ebase = st.hbase + (unsigned) W * st.stride;
+            St st; st.base = (unsigned) __cvta_generic_to_shared(sh) + threadIdx.x * state_bytes; st.stride = (unsigned) nthr * state_bytes;
             QSmem4 qf; qf.base = (unsigned) __cvta_generic_to_shared(qs); qf.stride = (unsigned) nthr * 4u;
             BswOut o;
             bsw_extend_one(st, qf, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);

@@ -116,12 +116,6 @@ struct SmemParams {
     int max_mem_intv;        // opt->max_mem_intv (0 disables pass 3)
 };
 
-// The three-pass SMEM search of ONE read as a state machine with a single extension call site.
-//   q(j), j in [0,len): base codes;  prev: scratch of >= len+1 entries (filled from the top downwards during
-//   the forward phase, so the longest-first order of the backward phase needs no reversal);  reseed: scratch of >= len int2-like
-//   entries (x, min_intv) for pass 2;  emit(m, n, k, l, s) appends one SMEM (any order: the caller
-//   sorts by (rid, m, n) afterwards, as sortSMEMs + the per-read introsort do);
-//   n_ext counts extensions (128 algorithmic bytes each).
 struct QPlain {                    // read codes straight from memory
     const uint8_t *p;
     BM2_HD int operator()(int j) const { return p[j]; }
@@ -167,120 +161,100 @@ BM2_HD void fm_smem_pass3(const FmIndexView &fm, const Q &q, int len, const Smem
     }
 }
 
-template <class Emit, class Q>
-BM2_HD void fm_smem_read(const FmIndexView &fm, const Q &q, int len, const SmemParams &sp, FmPrev *prev,
-                         int32_t *reseed, Emit &emit, unsigned &n_ext, bool with_pass3 = true)
+// ---- passes 1 and 2, split into HOMOGENEOUS phases ---------------------------------------------------------------
+// getSMEMsOnePosOneThread (src/FMI_search.cpp:496-670) is a forward phase (extend right from x, remember the
+// interval whenever its size changes) followed by a backward phase (extend all remembered intervals to the left,
+// longest first, emitting SMEMs).  The start of the NEXT search of pass 1 depends on the forward phase only
+// (next_x), so all forward phases of a read form one chain and every backward phase is an independent task.
+// Running them as separate kernels keeps the lanes of a warp in the same loop (measured: the forward-only pass-3
+// kernel does 2.6x more extensions per second than the mixed automaton, profiles/r1d_smem_split_3gbp.md).
+
+// Forward phase(s).  single == false: pass 1, all searches of the read from x = 0 with min_intv 1
+// (getSMEMsAllPosOneThread, src/FMI_search.cpp:672-724); single == true: one search from (x0, min_intv), pass 2
+// (src/bwamem.cpp:695-753).  scratch: >= len+1 entries, filled from the top down so that the list handed to
+// sink(x, min_intv, list, n) is already longest-first (no reversal, :587-592).
+template <class Q, class Sink>
+BM2_HD void fm_forward(const FmIndexView &fm, const Q &q, int len, int x0, int min_intv, bool single, FmPrev *scratch, Sink &sink,
+                       unsigned &n_ext)
 {
-    enum { ST_SEARCH_BEGIN, ST_FWD, ST_FWD_END, ST_BWD_ROW, ST_BWD_ITEM, ST_SEARCH_END, ST_P3_BEGIN, ST_P3_FWD, ST_DONE };
     if (len <= 0) return;
-    int pass = 1;
-    int x = 0, min_intv = 1, next_x = 0, j = 0, num_prev = 0, num_curr = 0, p = 0, curr_s = -1;
     const int cap = len + 1;
-    int top = cap;
-    FmPrev *pv = prev;
-    bool first_phase = true;
-    int n_reseed = 0, i_reseed = 0;
+    int x = x0, j = 0, next_x = 0, top = cap;
+    bool searching = false;
     FmPrev cur; cur.k = cur.l = cur.s = 0; cur.m = cur.n = 0;
-    int st = ST_SEARCH_BEGIN;
     for (;;) {
-        // ---- run the control automaton until it needs one interval extension -----------------------
-        FmIv req; int req_base = 0; bool req_fwd = false;
         bool need = false;
+        int base = 0;
         while (!need) {
-            if (st == ST_SEARCH_BEGIN) {
-                // getSMEMsOnePosOneThread entry (src/FMI_search.cpp:513-533)
+            if (!searching) {
+                if (x >= len) return;
                 next_x = x + 1;
                 const int a = q(x);
-                if (a > 3) { st = ST_SEARCH_END; num_prev = 0; continue; }
+                if (a > 3) { if (single) return; x = next_x; continue; }
                 cur.m = x; cur.n = x; cur.k = fm_count(fm, a); cur.l = fm_count(fm, 3 - a); cur.s = fm_count(fm, a + 1) - cur.k;
-                num_prev = 0; top = cap; j = x + 1; st = ST_FWD;
-            } else if (st == ST_FWD) {
-                if (j >= len) { st = ST_FWD_END; continue; }
-                next_x = j + 1;
-                const int a = q(j);
-                if (a > 3) { st = ST_FWD_END; continue; }
-                req.k = cur.l; req.l = cur.k; req.s = cur.s; req_base = 3 - a; req_fwd = true; need = true;
-            } else if (st == ST_FWD_END) {
-                if (cur.s >= min_intv) prev[--top] = cur;
-                pv = prev + top; num_prev = cap - top;          // last pushed (longest) first
-                j = x - 1; st = ST_BWD_ROW;
-            } else if (st == ST_BWD_ROW) {
-                if (j < 0 || q(j) > 3 || num_prev == 0) { st = ST_SEARCH_END; continue; }
-                num_curr = 0; curr_s = -1; p = 0; first_phase = true; st = ST_BWD_ITEM;
-            } else if (st == ST_BWD_ITEM) {
-                if (p >= num_prev) { num_prev = num_curr; if (num_curr == 0) { st = ST_SEARCH_END; continue; } --j; st = ST_BWD_ROW; continue; }
-                req.k = pv[p].k; req.l = pv[p].l; req.s = pv[p].s; req_base = q(j); req_fwd = false; need = true;
-            } else if (st == ST_SEARCH_END) {
-                // tail of one search (src/FMI_search.cpp:656-667), then the pass drivers
-                if (num_prev != 0) {
-                    const FmPrev &s0 = pv[0];
-                    if (s0.n - s0.m + 1 >= sp.min_seed_len) {
-                        emit(s0.m, s0.n, s0.k, s0.l, s0.s);
-                        if (pass == 1 && s0.n + 1 - s0.m >= sp.split_len && s0.s <= sp.split_width) {
-                            reseed[2 * n_reseed] = (s0.n + 1 + s0.m) >> 1; reseed[2 * n_reseed + 1] = (int32_t) (s0.s + 1); ++n_reseed;
-                        }
-                    }
-                    num_prev = 0;
-                }
-                if (pass == 1) {            // getSMEMsAllPosOneThread (src/FMI_search.cpp:672-724)
-                    x = next_x;
-                    if (x < len) { min_intv = 1; st = ST_SEARCH_BEGIN; continue; }
-                    pass = 2; i_reseed = 0;
-                }
-                if (pass == 2) {            // re-seeding (src/bwamem.cpp:695-753)
-                    if (i_reseed < n_reseed) { x = reseed[2 * i_reseed]; min_intv = reseed[2 * i_reseed + 1]; ++i_reseed; st = ST_SEARCH_BEGIN; continue; }
-                    pass = 3; x = 0;
-                    if (sp.max_mem_intv <= 0 || !with_pass3) { st = ST_DONE; continue; }
-                    st = ST_P3_BEGIN;
-                }
-            } else if (st == ST_P3_BEGIN) {   // bwtSeedStrategyAllPosOneThread (src/FMI_search.cpp:726-812)
-                if (x >= len) { st = ST_DONE; continue; }
-                next_x = x + 1;
-                const int a = q(x);
-                if (a > 3) { x = next_x; continue; }
-                cur.m = x; cur.n = x; cur.k = fm_count(fm, a); cur.l = fm_count(fm, 3 - a); cur.s = fm_count(fm, a + 1) - cur.k;
-                j = x + 1; st = ST_P3_FWD;
-            } else if (st == ST_P3_FWD) {
-                if (j >= len) { x = next_x; st = ST_P3_BEGIN; continue; }
-                next_x = j + 1;
-                const int a = q(j);
-                if (a > 3) { x = next_x; st = ST_P3_BEGIN; continue; }
-                req.k = cur.l; req.l = cur.k; req.s = cur.s; req_base = 3 - a; req_fwd = true; need = true;
-            } else {  // ST_DONE
-                return;
+                top = cap; j = x + 1; searching = true;
+            }
+            bool stop = j >= len;
+            if (!stop) { next_x = j + 1; const int a = q(j); if (a > 3) stop = true; else { base = 3 - a; need = true; } }
+            if (stop) {
+                if (cur.s >= min_intv) scratch[--top] = cur;
+                sink(x, min_intv, scratch + top, cap - top);
+                if (single) return;
+                x = next_x; searching = false;
             }
         }
-        // ---- the single extension call site -----------------------------------------------------------
-        BM2_SYNCWARP();                          // re-converge the warp: all lanes take the two checkpoint loads together
-        FmIv r = fm_backward_ext(fm, req, req_base);
+        BM2_SYNCWARP();
+        FmIv req; req.k = cur.l; req.l = cur.k; req.s = cur.s;
+        const FmIv r = fm_backward_ext(fm, req, base);
         ++n_ext;
-        if (req_fwd) { int64_t t = r.k; r.k = r.l; r.l = t; }
-        // ---- consume the result ---------------------------------------------------------------------------
-        if (st == ST_FWD) {
-            if (r.s != cur.s) prev[--top] = cur;
-            if (r.s < min_intv) { next_x = j; st = ST_FWD_END; }
-            else { cur.k = r.k; cur.l = r.l; cur.s = r.s; cur.n = j; ++j; }
-        } else if (st == ST_BWD_ITEM) {
-            const FmPrev old = pv[p];
-            if (first_phase && r.s < min_intv && old.n - old.m + 1 >= sp.min_seed_len) {
-                emit(old.m, old.n, old.k, old.l, old.s);
-                if (pass == 1 && old.n + 1 - old.m >= sp.split_len && old.s <= sp.split_width) {
-                    reseed[2 * n_reseed] = (old.n + 1 + old.m) >> 1; reseed[2 * n_reseed + 1] = (int32_t) (old.s + 1); ++n_reseed;
-                }
-                first_phase = false;
-            } else if (r.s >= min_intv && r.s != curr_s) {
-                curr_s = (int) r.s;
-                FmPrev t; t.k = r.k; t.l = r.l; t.s = r.s; t.m = j; t.n = old.n;
-                pv[num_curr++] = t;
-                first_phase = false;
-            }
-            ++p;
-        } else {  // ST_P3_FWD
-            cur.k = r.k; cur.l = r.l; cur.s = r.s; cur.n = j;
-            if (cur.s < sp.max_mem_intv && cur.n - cur.m + 1 >= sp.min_seed_len + 1) {
-                if (cur.s > 0) emit(cur.m, cur.n, cur.k, cur.l, cur.s);
-                x = next_x; st = ST_P3_BEGIN;
-            } else ++j;
+        if (r.s != cur.s) scratch[--top] = cur;
+        if (r.s < min_intv) {
+            next_x = j;
+            if (cur.s >= min_intv) scratch[--top] = cur;
+            sink(x, min_intv, scratch + top, cap - top);
+            if (single) return;
+            x = next_x; searching = false;
+        } else { cur.k = r.l; cur.l = r.k; cur.s = r.s; cur.n = j; ++j; }
+    }
+}
+
+// Backward phase of one search (src/FMI_search.cpp:594-667): pv[0..num_prev) longest first, compacted in place.
+template <class Q, class Emit>
+BM2_HD void fm_backward(const FmIndexView &fm, const Q &q, int x, int min_intv, int min_seed_len, FmPrev *pv, int num_prev, Emit &emit,
+                        unsigned &n_ext)
+{
+    int j = x - 1, p = 0, num_curr = 0, curr_s = -1;
+    bool first_phase = true;
+    for (;;) {
+        // next (row, item) that needs an extension
+        bool done = false;
+        for (;;) {
+            if (num_prev == 0 || j < 0) { done = true; break; }
+            if (p == 0 && num_curr == 0 && first_phase && q(j) > 3) { done = true; break; }    // row start: stop at an ambiguous base
+            if (p < num_prev) break;
+            num_prev = num_curr;                                        // row finished
+            if (num_curr == 0) { done = true; break; }
+            --j; p = 0; num_curr = 0; curr_s = -1; first_phase = true;
         }
+        if (done) break;
+        BM2_SYNCWARP();
+        const FmPrev old = pv[p];
+        FmIv req; req.k = old.k; req.l = old.l; req.s = old.s;
+        const FmIv r = fm_backward_ext(fm, req, q(j));
+        ++n_ext;
+        if (first_phase && r.s < min_intv && old.n - old.m + 1 >= min_seed_len) {
+            emit(old.m, old.n, old.k, old.l, old.s);
+            first_phase = false;
+        } else if (r.s >= min_intv && r.s != curr_s) {
+            curr_s = (int) r.s;
+            FmPrev t; t.k = r.k; t.l = r.l; t.s = r.s; t.m = j; t.n = old.n;
+            pv[num_curr++] = t;
+            first_phase = false;
+        }
+        ++p;
+    }
+    if (num_prev != 0) {
+        const FmPrev &s0 = pv[0];
+        if (s0.n - s0.m + 1 >= min_seed_len) emit(s0.m, s0.n, s0.k, s0.l, s0.s);
     }
 }

@@ -76,20 +76,17 @@ void bm2_free_index(bm2_ctx *ctx) {
 // ------------------------------------------------------------------------------------------------
 struct Counters {                 // device-side counters of one batch
     unsigned long long n_smem, n_ext, n_lf, n_retry, cells;
+    unsigned long long n_pool, n_task, n_task1, n_rtask;     // SMEM stage: interval-list pool, search tasks, re-seed tasks
     unsigned long long pad[3];
 };
 
-struct SmemAppend {
-    bm2_smem *out; unsigned long long cap; unsigned long long *count; uint32_t rid;
-    __device__ __forceinline__ void operator()(int m, int n, int64_t k, int64_t l, int64_t s) {
-        unsigned long long i = atomicAdd(count, 1ULL);
-        if (i < cap) { bm2_smem x; x.rid = rid; x.m = (uint32_t) m; x.n = (uint32_t) n; x.k = k; x.l = l; x.s = s; out[i] = x; }
-    }
-};
+struct SearchTask { int32_t read, x, min_intv, n; int64_t off; };     // one backward phase: list pool[off .. off+n)
+struct ReseedTask { int32_t read, x, min_intv; };                    // one pass-2 forward search
 
-// A. one read per thread (grid-stride), private prev/reseed stripes per THREAD.  USE_SMEM: the read is packed
-// 4 bit/base into shared memory [word][thread] (bank = lane) so that the base fetch in front of every interval
-// extension never waits on L1/L2 (22 % of the stall samples before, profiles/r1b_smem_r1b.md).
+
+// A. SMEM passes 1+2 as homogeneous phases (fm_device.cuh): forward chains (one read per thread), backward tasks
+// (one search per thread), pass-2 forward searches (one re-seed task per thread), backward tasks again.  The read is
+// packed 4 bit/base into shared memory [word][thread] (bank = lane) for the read-per-thread kernels.
 struct QShared4 {
     unsigned base, stride;
     __device__ __forceinline__ int operator()(int j) const {
@@ -98,37 +95,104 @@ struct QShared4 {
     }
 };
 
+struct PoolSink {                 // hands the interval list of one finished forward phase to the backward kernel
+    FmPrev *pool; unsigned long long pool_cap; SearchTask *tasks; unsigned long long task_cap; Counters *cnt; int read;
+    __device__ __forceinline__ void operator()(int x, int min_intv, const FmPrev *list, int n) {
+        if (n <= 0) return;
+        const unsigned long long off = atomicAdd(&cnt->n_pool, (unsigned long long) n);
+        const unsigned long long t = atomicAdd(&cnt->n_task, 1ULL);
+        if (off + n <= pool_cap) for (int i = 0; i < n; ++i) pool[off + i] = list[i];
+        if (t < task_cap) { SearchTask k; k.read = read; k.x = x; k.min_intv = min_intv; k.n = n; k.off = (int64_t) off; tasks[t] = k; }
+    }
+};
+
+__device__ __forceinline__ void pack_read_smem(uint32_t *qsh, const uint8_t *qp, int len) {
+    for (int k = 0; k < len; k += 8) {
+        uint32_t wv = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { uint32_t b = k + u < len ? (uint32_t) qp[k + u] : 4u; wv |= (b > 4u ? 4u : b) << (4 * u); }
+        qsh[(k >> 3) * blockDim.x + threadIdx.x] = wv;
+    }
+}
+
 template <bool USE_SMEM>
-__global__ void __launch_bounds__(128, 8)
-smem_kernel(FmIndexView fm, SmemParams sp, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, int n_reads, int stripe,
-            FmPrev *prev_all, int32_t *reseed_all, bm2_smem *out, unsigned long long cap, Counters *cnt)
+__global__ void __launch_bounds__(128, 10)
+smem_fwd1_kernel(FmIndexView fm, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, int n_reads, int stripe,
+                 FmPrev *scratch_all, FmPrev *pool, unsigned long long pool_cap, SearchTask *tasks, unsigned long long task_cap, Counters *cnt)
 {
     extern __shared__ uint32_t qsh[];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
-    FmPrev *prev = prev_all + (size_t) tid * stripe;
-    int32_t *reseed = reseed_all + (size_t) tid * 2 * stripe;
+    FmPrev *scratch = scratch_all + (size_t) tid * stripe;
     unsigned n_ext = 0;
     for (int r = tid; r < n_reads; r += nthr) {
         const int64_t o = offs[r];
         const int len = (int) (offs[r + 1] - o);
-        SmemAppend emit = { out, cap, &cnt->n_smem, (uint32_t) r };
+        PoolSink sink = { pool, pool_cap, tasks, task_cap, cnt, r };
         if (USE_SMEM) {
-            const uint8_t *qp = codes + o;
-            for (int k = 0; k < len; k += 8) {
-                uint32_t wv = 0;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { uint32_t b = k + u < len ? (uint32_t) qp[k + u] : 4u; wv |= (b > 4u ? 4u : b) << (4 * u); }
-                qsh[(k >> 3) * blockDim.x + threadIdx.x] = wv;
-            }
+            pack_read_smem(qsh, codes + o, len);
             QShared4 q = { (unsigned) __cvta_generic_to_shared(qsh + threadIdx.x), (unsigned) blockDim.x * 4u };
-            fm_smem_read(fm, q, len, sp, prev, reseed, emit, n_ext, false);
+            fm_forward(fm, q, len, 0, 1, false, scratch, sink, n_ext);
         } else {
             QPlain q = { codes + o };
-            fm_smem_read(fm, q, len, sp, prev, reseed, emit, n_ext, false);
+            fm_forward(fm, q, len, 0, 1, false, scratch, sink, n_ext);
         }
     }
     if (n_ext) atomicAdd(&cnt->n_ext, (unsigned long long) n_ext);
 }
+
+__global__ void __launch_bounds__(128, 10)
+smem_fwd2_kernel(FmIndexView fm, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, int stripe, FmPrev *scratch_all,
+                 const ReseedTask *__restrict__ rtasks, unsigned long long rtask_cap, FmPrev *pool, unsigned long long pool_cap,
+                 SearchTask *tasks, unsigned long long task_cap, Counters *cnt)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    FmPrev *scratch = scratch_all + (size_t) tid * stripe;
+    const unsigned long long n = cnt->n_rtask < rtask_cap ? cnt->n_rtask : rtask_cap;
+    unsigned n_ext = 0;
+    for (unsigned long long t = tid; t < n; t += nthr) {
+        const ReseedTask rt = rtasks[t];
+        const int64_t o = offs[rt.read];
+        const int len = (int) (offs[rt.read + 1] - o);
+        PoolSink sink = { pool, pool_cap, tasks, task_cap, cnt, rt.read };
+        QPlain q = { codes + o };
+        fm_forward(fm, q, len, rt.x, rt.min_intv, true, scratch, sink, n_ext);
+    }
+    if (n_ext) atomicAdd(&cnt->n_ext, (unsigned long long) n_ext);
+}
+
+struct SmemAppend {
+    bm2_smem *out; unsigned long long cap; Counters *cnt; uint32_t rid;
+    ReseedTask *rtasks; unsigned long long rtask_cap; int split_len, split_width;      // rtasks == nullptr: no re-seeding (pass 2, 3)
+    __device__ __forceinline__ void operator()(int m, int n, int64_t k, int64_t l, int64_t s) {
+        unsigned long long i = atomicAdd(&cnt->n_smem, 1ULL);
+        if (i < cap) { bm2_smem x; x.rid = rid; x.m = (uint32_t) m; x.n = (uint32_t) n; x.k = k; x.l = l; x.s = s; out[i] = x; }
+        if (rtasks && n + 1 - m >= split_len && s <= split_width) {                 // src/bwamem.cpp:695-714
+            unsigned long long t = atomicAdd(&cnt->n_rtask, 1ULL);
+            if (t < rtask_cap) { ReseedTask r; r.read = (int32_t) rid; r.x = (n + 1 + m) >> 1; r.min_intv = (int32_t) (s + 1); rtasks[t] = r; }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(128, 10)
+smem_bwd_kernel(FmIndexView fm, SmemParams sp, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, int round,
+                const SearchTask *__restrict__ tasks, unsigned long long task_cap, FmPrev *pool, unsigned long long pool_cap,
+                bm2_smem *out, unsigned long long cap, ReseedTask *rtasks, unsigned long long rtask_cap, Counters *cnt)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const unsigned long long t0 = round ? cnt->n_task1 : 0ULL;
+    const unsigned long long t1 = cnt->n_task < task_cap ? cnt->n_task : task_cap;
+    unsigned n_ext = 0;
+    for (unsigned long long t = t0 + tid; t < t1; t += nthr) {
+        const SearchTask k = tasks[t];
+        if ((unsigned long long) k.off + k.n > pool_cap) continue;                     // overflowed pool: the stage is re-run
+        SmemAppend emit = { out, cap, cnt, (uint32_t) k.read, round ? nullptr : rtasks, rtask_cap, sp.split_len, sp.split_width };
+        QPlain q = { codes + offs[k.read] };
+        fm_backward(fm, q, k.x, k.min_intv, sp.min_seed_len, pool + k.off, k.n, emit, n_ext);
+    }
+    if (n_ext) atomicAdd(&cnt->n_ext, (unsigned long long) n_ext);
+}
+
+__global__ void mark_task1_kernel(Counters *cnt) { if (threadIdx.x == 0 && blockIdx.x == 0) cnt->n_task1 = cnt->n_task; }
 
 // A'. pass 3 (forward-only seeding) as its own kernel on a second stream: lean state, high occupancy
 template <bool USE_SMEM>
@@ -142,15 +206,9 @@ smem_pass3_kernel(FmIndexView fm, SmemParams sp, const uint8_t *__restrict__ cod
     for (int r = tid; r < n_reads; r += nthr) {
         const int64_t o = offs[r];
         const int len = (int) (offs[r + 1] - o);
-        SmemAppend emit = { out, cap, &cnt->n_smem, (uint32_t) r };
+        SmemAppend emit = { out, cap, cnt, (uint32_t) r, nullptr, 0, 0, 0 };
         if (USE_SMEM) {
-            const uint8_t *qp = codes + o;
-            for (int k = 0; k < len; k += 8) {
-                uint32_t wv = 0;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { uint32_t b = k + u < len ? (uint32_t) qp[k + u] : 4u; wv |= (b > 4u ? 4u : b) << (4 * u); }
-                qsh[(k >> 3) * blockDim.x + threadIdx.x] = wv;
-            }
+            pack_read_smem(qsh, codes + o, len);
             QShared4 q = { (unsigned) __cvta_generic_to_shared(qsh + threadIdx.x), (unsigned) blockDim.x * 4u };
             fm_smem_pass3(fm, q, len, sp, emit, n_ext);
         } else {
@@ -206,7 +264,9 @@ sa_kernel(FmIndexView fm, const bm2_smem *__restrict__ sm, const int64_t *__rest
         const int64_t step = x.s > max_occ ? x.s / max_occ : 1;
         sa[t] = fm_sa_of_row(fm, x.k + (t - slot_off[o]) * step, &lf);
     }
-    if (lf) atomicAdd(&cnt->n_lf, (unsigned long long) lf);
+    // one atomic per warp (12 M same-address atomics cost ~6 ms, profiles/r1d)
+    lf = __reduce_add_sync(0xffffffffu, lf);
+    if ((threadIdx.x & 31) == 0 && lf) atomicAdd(&cnt->n_lf, (unsigned long long) lf);
 }
 
 // D. one read per thread
@@ -367,7 +427,7 @@ namespace {
 enum Buf {
     B_CODES, B_OFFS, B_CNT, B_PREV, B_RESEED, B_SMEM_RAW, B_KEYS_IN, B_KEYS_OUT, B_VALS_IN, B_VALS_OUT, B_CUB, B_SMEM, B_SLOT_CNT,
     B_SLOT_OFF, B_READ_SMEM_OFF, B_SA, B_WSEED, B_WCHAIN, B_ORD, B_SRT, B_KV, B_FIN_CHAIN, B_FIN_SEED, B_PER_READ, B_SCAN, B_CHAINS,
-    B_SEEDS, B_REGS, B_REG_AUX, B_JOBS, B_NW, B_OUT, B_PERM, B_ORDPOS, B_FLT, B_MINHSP, B_OWNER, B_COUNT_
+    B_SEEDS, B_REGS, B_REG_AUX, B_JOBS, B_NW, B_OUT, B_PERM, B_ORDPOS, B_FLT, B_MINHSP, B_OWNER, B_POOL, B_TASKS, B_RTASKS, B_COUNT_
 };
 static_assert(B_COUNT_ <= 64, "bm2_ctx::d[] too small");
 enum HBuf { H_OUT_REGS, H_OUT_OFF, H_SMEM, H_CHAINS, H_SEEDS, H_MISC };
@@ -495,46 +555,57 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     // ---- A. SMEMs -------------------------------------------------------------------------------------------
     if (sg.mark("smem")) return 1;
     const int stripe = max_len + 2;
-    int blocks_a = (n + 127) / 128; int max_blocks_a = ctx->n_sm * 16;
-    {   // per-thread scratch = stripe * (32 + 8) bytes: keep it under ~8 GB for long reads
-        const size_t per_block = (size_t) 128 * stripe * (sizeof(FmPrev) + 8);
+    int blocks_a = (n + 127) / 128; int max_blocks_a = ctx->n_sm * 10;
+    {   // per-thread forward scratch = stripe * 32 bytes: keep it under ~8 GB for long reads
+        const size_t per_block = (size_t) 128 * stripe * sizeof(FmPrev);
         const size_t fit = ((size_t) 8 << 30) / per_block;
         if ((size_t) max_blocks_a > fit) max_blocks_a = (int) (fit > (size_t) ctx->n_sm ? fit : (size_t) ctx->n_sm);
     }
     if (blocks_a > max_blocks_a) blocks_a = max_blocks_a;
     const size_t thr_a = (size_t) blocks_a * 128;
-    if (ctx->ensure(ctx->d[B_PREV], thr_a * stripe * sizeof(FmPrev)) || ctx->ensure(ctx->d[B_RESEED], thr_a * 2 * stripe * 4)) return 1;
+    if (ctx->ensure(ctx->d[B_PREV], thr_a * stripe * sizeof(FmPrev))) return 1;
+    // capacities grow from the counters when a batch overflows them (then the stage is re-run)
+    const double rl = (double) total / n;                                  // mean read length
     unsigned long long cap = (unsigned long long) n * 16 + 4096;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        if (ctx->ensure(ctx->d[B_SMEM_RAW], cap * sizeof(bm2_smem))) return 1;
+    unsigned long long pool_cap = (unsigned long long) (n * (rl * 1.7 + 64)) + 65536;
+    unsigned long long task_cap = (unsigned long long) (n * (rl / 12 + 8)) + 4096;
+    unsigned long long rtask_cap = (unsigned long long) n * 8 + 4096;
+    const bool q_smem = max_len <= 256;
+    const size_t qsm = q_smem ? (size_t) ((max_len + 7) / 8) * 128 * 4 : 0;
+    const int blocks_b = ctx->n_sm * 10;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if (ctx->ensure(ctx->d[B_SMEM_RAW], cap * sizeof(bm2_smem)) || ctx->ensure(ctx->d[B_POOL], pool_cap * sizeof(FmPrev)) ||
+            ctx->ensure(ctx->d[B_TASKS], task_cap * sizeof(SearchTask)) || ctx->ensure(ctx->d[B_RTASKS], rtask_cap * sizeof(ReseedTask))) return 1;
         BM2_CUDA_OK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), st));
-        // fork: pass 3 on the side stream, passes 1+2 on the main stream (both only append to the SMEM buffer)
+        bm2_smem *d_raw = P<bm2_smem>(ctx, B_SMEM_RAW); FmPrev *d_pool = P<FmPrev>(ctx, B_POOL);
+        SearchTask *d_tasks = P<SearchTask>(ctx, B_TASKS); ReseedTask *d_rt = P<ReseedTask>(ctx, B_RTASKS);
+        // fork: pass 3 on the side stream (it only appends to the SMEM buffer)
         BM2_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
         BM2_CUDA_OK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
         {
             int blocks_p3 = (n + 127) / 128; if (blocks_p3 > ctx->n_sm * 12) blocks_p3 = ctx->n_sm * 12;
-            if (max_len <= 256) {
-                const size_t qsm = (size_t) ((max_len + 7) / 8) * 128 * 4;
-                smem_pass3_kernel<true><<<blocks_p3, 128, qsm, ctx->side_stream>>>(pv.fm, pv.sp, d_codes, d_offs, n, P<bm2_smem>(ctx, B_SMEM_RAW), cap, d_cnt);
-            } else {
-                smem_pass3_kernel<false><<<blocks_p3, 128, 0, ctx->side_stream>>>(pv.fm, pv.sp, d_codes, d_offs, n, P<bm2_smem>(ctx, B_SMEM_RAW), cap, d_cnt);
-            }
+            if (q_smem) smem_pass3_kernel<true><<<blocks_p3, 128, qsm, ctx->side_stream>>>(pv.fm, pv.sp, d_codes, d_offs, n, d_raw, cap, d_cnt);
+            else smem_pass3_kernel<false><<<blocks_p3, 128, 0, ctx->side_stream>>>(pv.fm, pv.sp, d_codes, d_offs, n, d_raw, cap, d_cnt);
             BM2_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
         }
-        if (max_len <= 256) {
-            const size_t qsm = (size_t) ((max_len + 7) / 8) * 128 * 4;
-            smem_kernel<true><<<blocks_a, 128, qsm, st>>>(pv.fm, pv.sp, d_codes, d_offs, n, stripe, P<FmPrev>(ctx, B_PREV), P<int32_t>(ctx, B_RESEED),
-                                                           P<bm2_smem>(ctx, B_SMEM_RAW), cap, d_cnt);
-        } else {
-            smem_kernel<false><<<blocks_a, 128, 0, st>>>(pv.fm, pv.sp, d_codes, d_offs, n, stripe, P<FmPrev>(ctx, B_PREV), P<int32_t>(ctx, B_RESEED),
-                                                          P<bm2_smem>(ctx, B_SMEM_RAW), cap, d_cnt);
-        }
+        // pass 1: forward chains, then one backward task per search (emits SMEMs and re-seed tasks)
+        if (q_smem) smem_fwd1_kernel<true><<<blocks_a, 128, qsm, st>>>(pv.fm, d_codes, d_offs, n, stripe, P<FmPrev>(ctx, B_PREV), d_pool, pool_cap, d_tasks, task_cap, d_cnt);
+        else smem_fwd1_kernel<false><<<blocks_a, 128, 0, st>>>(pv.fm, d_codes, d_offs, n, stripe, P<FmPrev>(ctx, B_PREV), d_pool, pool_cap, d_tasks, task_cap, d_cnt);
+        smem_bwd_kernel<<<blocks_b, 128, 0, st>>>(pv.fm, pv.sp, d_codes, d_offs, 0, d_tasks, task_cap, d_pool, pool_cap, d_raw, cap, d_rt, rtask_cap, d_cnt);
+        mark_task1_kernel<<<1, 32, 0, st>>>(d_cnt);
+        // pass 2: one forward search per re-seed task, then its backward task
+        smem_fwd2_kernel<<<blocks_a, 128, 0, st>>>(pv.fm, d_codes, d_offs, stripe, P<FmPrev>(ctx, B_PREV), d_rt, rtask_cap, d_pool, pool_cap, d_tasks, task_cap, d_cnt);
+        smem_bwd_kernel<<<blocks_b, 128, 0, st>>>(pv.fm, pv.sp, d_codes, d_offs, 1, d_tasks, task_cap, d_pool, pool_cap, d_raw, cap, d_rt, rtask_cap, d_cnt);
         BM2_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_join, 0));          // join
         BM2_CUDA_OK(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         BM2_CUDA_OK(cudaStreamSynchronize(st));
-        if (h_cnt.n_smem <= cap) break;
-        if (attempt == 1) { bm2_set_error(ctx, "SMEM buffer overflow"); return 1; }
-        cap = h_cnt.n_smem + 1024;
+        if (h_cnt.n_smem <= cap && h_cnt.n_pool <= pool_cap && h_cnt.n_task <= task_cap && h_cnt.n_rtask <= rtask_cap) break;
+        if (attempt == 2) { bm2_set_error(ctx, "SMEM stage buffers overflow"); return 1; }
+        // an overflow truncates the later phases, so the counters are lower bounds: grow generously
+        if (h_cnt.n_smem > cap) cap = h_cnt.n_smem * 2 + 1024;
+        if (h_cnt.n_pool > pool_cap) pool_cap = h_cnt.n_pool * 2 + 65536;
+        if (h_cnt.n_task > task_cap) task_cap = h_cnt.n_task * 2 + 4096;
+        if (h_cnt.n_rtask > rtask_cap) rtask_cap = h_cnt.n_rtask * 2 + 4096;
     }
     const int64_t n_smem = (int64_t) h_cnt.n_smem;
     bs.n_smem = n_smem;

@@ -43,15 +43,28 @@ struct Stage1 {      // sorted SMEMs + per-read ranges + SA of every seed slot
 void stage_smem_sa(const Views &v, const bm2_mem_opt_t *o, const bm2_read_batch *rb, Stage1 &s) {
     int max_len = 0;
     for (int r = 0; r < rb->n_reads; ++r) max_len = std::max<int>(max_len, (int) (rb->offsets[r + 1] - rb->offsets[r]));
-    std::vector<FmPrev> prev(max_len + 2); std::vector<int32_t> reseed(2 * max_len + 2);
+    std::vector<FmPrev> scratch(max_len + 2);
+    struct Search { int x, min_intv; std::vector<FmPrev> list; };
     for (int r = 0; r < rb->n_reads; ++r) {
         const uint8_t *q = rb->codes + rb->offsets[r]; int len = (int) (rb->offsets[r + 1] - rb->offsets[r]);
         unsigned n_ext = 0;
+        QPlain qq = { q };
+        // same phase order as the kernels: forward chain of pass 1, backward tasks, re-seed forward, backward, pass 3
+        std::vector<Search> tasks;
+        auto sink = [&](int x, int min_intv, const FmPrev *list, int nl) { Search t; t.x = x; t.min_intv = min_intv; t.list.assign(list, list + nl); tasks.push_back(t); };
+        fm_forward(v.fm, qq, len, 0, 1, false, scratch.data(), sink, n_ext);
+        std::vector<std::pair<int, int>> reseeds;
+        bool pass1 = true;
         auto emit = [&](int m, int n, int64_t k, int64_t l, int64_t ss) {
             bm2_smem x; x.rid = r; x.m = m; x.n = n; x.k = k; x.l = l; x.s = ss; s.smems.push_back(x);
+            if (pass1 && n + 1 - m >= v.sp.split_len && ss <= v.sp.split_width) reseeds.push_back(std::make_pair((n + 1 + m) >> 1, (int) (ss + 1)));
         };
-        QPlain qq = { q };
-        fm_smem_read(v.fm, qq, len, v.sp, prev.data(), reseed.data(), emit, n_ext, false);
+        for (Search &t : tasks) fm_backward(v.fm, qq, t.x, t.min_intv, v.sp.min_seed_len, t.list.data(), (int) t.list.size(), emit, n_ext);
+        pass1 = false;
+        std::vector<Search> tasks2;
+        auto sink2 = [&](int x, int min_intv, const FmPrev *list, int nl) { Search t; t.x = x; t.min_intv = min_intv; t.list.assign(list, list + nl); tasks2.push_back(t); };
+        for (auto &rs : reseeds) fm_forward(v.fm, qq, len, rs.first, rs.second, true, scratch.data(), sink2, n_ext);
+        for (Search &t : tasks2) fm_backward(v.fm, qq, t.x, t.min_intv, v.sp.min_seed_len, t.list.data(), (int) t.list.size(), emit, n_ext);
         fm_smem_pass3(v.fm, qq, len, v.sp, emit, n_ext);
         s.n_ext += n_ext;
     }
