@@ -258,3 +258,44 @@ BM2_HD void fm_backward(const FmIndexView &fm, const Q &q, int x, int min_intv, 
         if (s0.n - s0.m + 1 >= min_seed_len) emit(s0.m, s0.n, s0.k, s0.l, s0.s);
     }
 }
+
+// Row-wise form of the backward phase: all intervals of the list are extended by the same base q[j]
+// INDEPENDENTLY (one DRAM round trip per row when the lanes of a lane group take one entry each), then the
+// sequential keep/emit rule of src/FMI_search.cpp:607-649 is applied to the extended sizes.  Because entry p+1 is
+// a proper prefix of entry p (same start j+1, shorter end), the extended sizes ext_s[p] are non-decreasing in p
+// and the lengths strictly decreasing, so the rule collapses to:
+//   b = first p with ext_s[p] >= min_intv;  if b > 0 and entry 0 is long enough: emit entry 0 (un-extended);
+//   keep p >= b iff p == b or ext_s[p] != ext_s[p-1].
+// fm_backward_rows applies the rule with plain loops (host model and fallback); the kernel in pipeline.cu applies
+// it with ballots.  Returns through emit exactly what fm_backward emits.
+template <class Q, class Emit>
+BM2_HD void fm_backward_rows(const FmIndexView &fm, const Q &q, int x, int min_intv, int min_seed_len, FmPrev *pv, int num_prev,
+                             Emit &emit, unsigned &n_ext)
+{
+    for (int j = x - 1; j >= 0 && num_prev > 0; --j) {
+        const int a = q(j);
+        if (a > 3) break;
+        // phase 1: independent extensions (results overwrite k,l,s in place; m,n of the old entry are still needed)
+        int b = num_prev;
+        const FmPrev first = pv[0];
+        for (int p = 0; p < num_prev; ++p) {
+            FmIv req; req.k = pv[p].k; req.l = pv[p].l; req.s = pv[p].s;
+            const FmIv r = fm_backward_ext(fm, req, a);
+            ++n_ext;
+            pv[p].k = r.k; pv[p].l = r.l; pv[p].s = r.s;
+            if (r.s >= min_intv && b == num_prev) b = p;
+        }
+        // phase 2: the keep/emit rule
+        if (b > 0 && first.n - first.m + 1 >= min_seed_len) emit(first.m, first.n, first.k, first.l, first.s);
+        int num_curr = 0;
+        int64_t last_s = -1;
+        for (int p = b; p < num_prev; ++p) {
+            if (pv[p].s != last_s) { last_s = pv[p].s; FmPrev t = pv[p]; t.m = j; pv[num_curr++] = t; }
+        }
+        num_prev = num_curr;
+    }
+    if (num_prev != 0) {
+        const FmPrev &s0 = pv[0];
+        if (s0.n - s0.m + 1 >= min_seed_len) emit(s0.m, s0.n, s0.k, s0.l, s0.s);
+    }
+}

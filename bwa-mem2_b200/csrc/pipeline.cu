@@ -173,23 +173,77 @@ struct SmemAppend {
     }
 };
 
-__global__ void __launch_bounds__(128, 10)
+// Backward phases: one search task per group of BWD_G lanes.  Per row (one base to the left) the lanes extend the
+// entries of the interval list INDEPENDENTLY (one DRAM round trip per row instead of one per entry), then apply the
+// collapsed keep/emit rule of fm_backward_rows with a ballot.  Lists of up to BWD_CAP entries live in shared memory.
+#define BWD_G 8
+#define BWD_CAP 32
+__global__ void __launch_bounds__(128, 8)
 smem_bwd_kernel(FmIndexView fm, SmemParams sp, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, int round,
                 const SearchTask *__restrict__ tasks, unsigned long long task_cap, FmPrev *pool, unsigned long long pool_cap,
                 bm2_smem *out, unsigned long long cap, ReseedTask *rtasks, unsigned long long rtask_cap, Counters *cnt)
 {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    __shared__ FmPrev shl[128 / BWD_G][BWD_CAP];
+    const int lane = threadIdx.x & 31, gl = lane & (BWD_G - 1), gw = lane / BWD_G;      // lane in group, group in warp
+    const unsigned gmask = ((1u << BWD_G) - 1u) << (gw * BWD_G);
+    const int grp = (blockIdx.x * blockDim.x + threadIdx.x) / BWD_G, ngrp = gridDim.x * blockDim.x / BWD_G;
     const unsigned long long t0 = round ? cnt->n_task1 : 0ULL;
     const unsigned long long t1 = cnt->n_task < task_cap ? cnt->n_task : task_cap;
     unsigned n_ext = 0;
-    for (unsigned long long t = t0 + tid; t < t1; t += nthr) {
+    for (unsigned long long t = t0 + grp; t < t1; t += ngrp) {
         const SearchTask k = tasks[t];
         if ((unsigned long long) k.off + k.n > pool_cap) continue;                     // overflowed pool: the stage is re-run
         SmemAppend emit = { out, cap, cnt, (uint32_t) k.read, round ? nullptr : rtasks, rtask_cap, sp.split_len, sp.split_width };
-        QPlain q = { codes + offs[k.read] };
-        fm_backward(fm, q, k.x, k.min_intv, sp.min_seed_len, pool + k.off, k.n, emit, n_ext);
+        const uint8_t *q = codes + offs[k.read];
+        FmPrev *lst = pool + k.off;
+        int num_prev = k.n;
+        if (num_prev <= BWD_CAP) {
+            FmPrev *sl = shl[threadIdx.x / BWD_G];
+            for (int p = gl; p < num_prev; p += BWD_G) sl[p] = lst[p];
+            lst = sl;
+        }
+        __syncwarp(gmask);
+        for (int j = k.x - 1; j >= 0 && num_prev > 0; --j) {
+            const int a = q[j];
+            if (a > 3) break;
+            const FmPrev first = lst[0];
+            __syncwarp(gmask);                                            // everyone has read entry 0 before it is overwritten
+            // phase 1: independent extensions, results written back in place (k, l, s)
+            int b = num_prev;
+            for (int p = gl; p < num_prev; p += BWD_G) {
+                FmIv req; req.k = lst[p].k; req.l = lst[p].l; req.s = lst[p].s;
+                const FmIv r = fm_backward_ext(fm, req, a);
+                ++n_ext;
+                lst[p].k = r.k; lst[p].l = r.l; lst[p].s = r.s;
+                if (r.s >= k.min_intv && p < b) b = p;
+            }
+#pragma unroll
+            for (int d = BWD_G / 2; d > 0; d >>= 1) b = min(b, __shfl_xor_sync(gmask, b, d));
+            __syncwarp(gmask);
+            // phase 2: emit entry 0 if it died long enough; keep p >= b iff p == b or s[p] != s[p-1]; compact in place
+            if (gl == 0 && b > 0 && first.n - first.m + 1 >= sp.min_seed_len) emit(first.m, first.n, first.k, first.l, first.s);
+            int num_curr = 0;
+            for (int base = b; base < num_prev; base += BWD_G) {
+                const int p = base + gl;
+                bool keep = false;
+                FmPrev e;
+                if (p < num_prev) { e = lst[p]; keep = (p == b) || (lst[p - 1].s != e.s); }
+                const unsigned km = __ballot_sync(gmask, keep) >> (gw * BWD_G);
+                __syncwarp(gmask);                                        // all reads of this round before any write
+                if (keep) { e.m = j; lst[num_curr + __popc(km & ((1u << gl) - 1u))] = e; }
+                num_curr += __popc(km);
+                __syncwarp(gmask);
+            }
+            num_prev = num_curr;
+        }
+        if (gl == 0 && num_prev != 0) {
+            const FmPrev s0 = lst[0];
+            if (s0.n - s0.m + 1 >= sp.min_seed_len) emit(s0.m, s0.n, s0.k, s0.l, s0.s);
+        }
+        __syncwarp(gmask);
     }
-    if (n_ext) atomicAdd(&cnt->n_ext, (unsigned long long) n_ext);
+    n_ext = __reduce_add_sync(0xffffffffu, n_ext);
+    if (lane == 0 && n_ext) atomicAdd(&cnt->n_ext, (unsigned long long) n_ext);
 }
 
 __global__ void mark_task1_kernel(Counters *cnt) { if (threadIdx.x == 0 && blockIdx.x == 0) cnt->n_task1 = cnt->n_task; }

@@ -59,12 +59,12 @@ void stage_smem_sa(const Views &v, const bm2_mem_opt_t *o, const bm2_read_batch 
             bm2_smem x; x.rid = r; x.m = m; x.n = n; x.k = k; x.l = l; x.s = ss; s.smems.push_back(x);
             if (pass1 && n + 1 - m >= v.sp.split_len && ss <= v.sp.split_width) reseeds.push_back(std::make_pair((n + 1 + m) >> 1, (int) (ss + 1)));
         };
-        for (Search &t : tasks) fm_backward(v.fm, qq, t.x, t.min_intv, v.sp.min_seed_len, t.list.data(), (int) t.list.size(), emit, n_ext);
+        for (Search &t : tasks) fm_backward_rows(v.fm, qq, t.x, t.min_intv, v.sp.min_seed_len, t.list.data(), (int) t.list.size(), emit, n_ext);
         pass1 = false;
         std::vector<Search> tasks2;
         auto sink2 = [&](int x, int min_intv, const FmPrev *list, int nl) { Search t; t.x = x; t.min_intv = min_intv; t.list.assign(list, list + nl); tasks2.push_back(t); };
         for (auto &rs : reseeds) fm_forward(v.fm, qq, len, rs.first, rs.second, true, scratch.data(), sink2, n_ext);
-        for (Search &t : tasks2) fm_backward(v.fm, qq, t.x, t.min_intv, v.sp.min_seed_len, t.list.data(), (int) t.list.size(), emit, n_ext);
+        for (Search &t : tasks2) fm_backward_rows(v.fm, qq, t.x, t.min_intv, v.sp.min_seed_len, t.list.data(), (int) t.list.size(), emit, n_ext);
         fm_smem_pass3(v.fm, qq, len, v.sp, emit, n_ext);
         s.n_ext += n_ext;
     }
