@@ -77,6 +77,12 @@ __global__ void bsw_class_off_kernel(const int32_t *class_cnt, int32_t *class_of
 // ---------------------------------------------------------------------------------------------
 // (Measured: splitting H and E into separate narrow arrays - 2 LDS + 2 STS per cell instead of pack/unpack ALU
 // ops - made the kernel 6 % slower, profiles/r1d notes; the packed word stays.)
+// The kernel is bound by the integer-ALU pipe (LOP3/SHF/VIMNMX/SEL/PRMT); the FMA pipe (IMAD) idles.  Field
+// extraction and packing are therefore written as multiply-adds so that they issue on the FMA pipe:
+//   x >> s == umulhi(x, 2^(32-s)),  x & (2^s-1) == x - (x >> s) * 2^s,  (a << s) | b == a * 2^s + b  (b < 2^s).
+__device__ __forceinline__ uint32_t fma_shr(uint32_t x, uint32_t two_pow_32_minus_s) { return __umulhi(x, two_pow_32_minus_s); }
+__device__ __forceinline__ int fma_mad(int a, int b, int c) { int d; asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+
 struct SmemPacked {            // H | E<<16 in shared memory, [column][thread]; explicit shared-space accesses
     unsigned base;             // shared-window address of &sh[threadIdx.x]
     unsigned stride;           // blockDim.x * 4 bytes
@@ -86,13 +92,13 @@ struct SmemPacked {            // H | E<<16 in shared memory, [column][thread]; 
     __device__ __forceinline__ void stw(int j, uint32_t w) const {
         asm volatile("st.shared.u32 [%0], %1;" :: "r"(base + (unsigned) j * stride), "r"(w) : "memory");
     }
-    __device__ __forceinline__ void get(int j, int &h, int &e) const { uint32_t w = ldw(j); h = (int) (w & 0xFFFFu); e = (int) (w >> 16); }
-    __device__ __forceinline__ void put(int j, int h, int e) const { stw(j, __byte_perm((uint32_t) h, (uint32_t) e, 0x5410)); }
+    __device__ __forceinline__ void get(int j, int &h, int &e) const { uint32_t w = ldw(j); e = (int) fma_shr(w, 1u << 16); h = fma_mad(e, -65536, (int) w); }
+    __device__ __forceinline__ void put(int j, int h, int e) const { stw(j, (uint32_t) fma_mad(e, 65536, h)); }
     __device__ __forceinline__ bool zero(int j) const { return ldw(j) == 0u; }
     // row maximum as one signed key: (h << 16) | j  (h < 2^15, j < 2^16)
     typedef int key_t;
     static constexpr unsigned kStateBytes = 4;
-    static __device__ __forceinline__ key_t key(int h, int j) { return (h << 16) | j; }
+    static __device__ __forceinline__ key_t key(int h, int j) { return fma_mad(h, 65536, j); }
     static __device__ __forceinline__ int key_h(key_t k) { return k >> 16; }
     static __device__ __forceinline__ int key_j(key_t k) { return k & 0xFFFF; }
 };
@@ -106,12 +112,12 @@ struct SmemPacked8 {           // H | E<<8 in 16 bits: jobs whose best possible 
     __device__ __forceinline__ void stw(int j, uint32_t w) const {
         asm volatile("st.shared.u16 [%0], %1;" :: "r"(base + (unsigned) j * stride), "h"((uint16_t) w) : "memory");
     }
-    __device__ __forceinline__ void get(int j, int &h, int &e) const { uint32_t w = ldw(j); h = (int) (w & 0xFFu); e = (int) (w >> 8); }
-    __device__ __forceinline__ void put(int j, int h, int e) const { stw(j, (uint32_t) h | ((uint32_t) e << 8)); }
+    __device__ __forceinline__ void get(int j, int &h, int &e) const { uint32_t w = ldw(j); e = (int) fma_shr(w, 1u << 24); h = fma_mad(e, -256, (int) w); }
+    __device__ __forceinline__ void put(int j, int h, int e) const { stw(j, (uint32_t) fma_mad(e, 256, h)); }
     __device__ __forceinline__ bool zero(int j) const { return ldw(j) == 0u; }
     typedef int key_t;
     static constexpr unsigned kStateBytes = 2;
-    static __device__ __forceinline__ key_t key(int h, int j) { return (h << 16) | j; }
+    static __device__ __forceinline__ key_t key(int h, int j) { return fma_mad(h, 65536, j); }
     static __device__ __forceinline__ int key_h(key_t k) { return k >> 16; }
     static __device__ __forceinline__ int key_j(key_t k) { return k & 0xFFFF; }
 };
@@ -230,8 +236,9 @@ struct QSmem4 {                // query packed 4 bit / base, [word][thread]
     __device__ __forceinline__ Cursor cursor(int j) const { Cursor c; c.w = ldw(j >> 3) >> ((j & 7) * 4); return c; }
     __device__ __forceinline__ int next(Cursor &c, int j) const {
         if ((j & 7) == 0) c.w = ldw(j >> 3);
-        int b = (int) (c.w & 0xFu);
-        c.w >>= 4;
+        const uint32_t nxt = fma_shr(c.w, 1u << 28);           // c.w >> 4 on the FMA pipe
+        const int b = fma_mad((int) nxt, -16, (int) c.w);          // c.w & 15
+        c.w = nxt;
         return b;
     }
 };
