@@ -334,11 +334,20 @@ __global__ void __launch_bounds__(128)
 chain_kernel(ContigView cv, ChainParams cp, const bm2_smem *__restrict__ sm, const int64_t *__restrict__ read_smem_off,
              const int64_t *__restrict__ slot_off, const int64_t *__restrict__ sa, const int64_t *__restrict__ offs, int n_reads,
              const int32_t *__restrict__ perm, ChainBufs b, SwParams sw, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ codes,
-             const int32_t *__restrict__ min_hsp)
+             const int32_t *__restrict__ min_hsp, int mode, int heavy_thr)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_reads) return;
-    const int r = perm[t];          // reads ordered by work so that the lanes of a warp run similar trip counts
+    // mode 0: light reads, one per thread; mode 1: heavy reads (many seed occurrences: O(n^2) chain insertion and
+    // filtering), one per WARP with lane 0 working, taken from the list sorted by decreasing work
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode && (threadIdx.x & 31)) return;
+    const int stride = mode ? (gridDim.x * blockDim.x) >> 5 : gridDim.x * blockDim.x;
+    for (int t = mode ? tid >> 5 : tid; t < n_reads; t += stride) {
+    const int r = mode ? perm[t] : t;
+    {
+        const int64_t nslot = slot_off[read_smem_off[r + 1]] - slot_off[read_smem_off[r]];
+        if (mode) { if (nslot <= heavy_thr) break; }                  // perm is sorted by decreasing work
+        else if (nslot > heavy_thr) continue;
+    }
     int nk = 0, ns = 0, nl = 0, nr = 0;
     const int64_t sb = read_smem_off[r], se = read_smem_off[r + 1];
     const int len = (int) (offs[r + 1] - offs[r]);
@@ -354,7 +363,9 @@ chain_kernel(ContigView cv, ChainParams cp, const bm2_smem *__restrict__ sm, con
         chain_finalize_d(ws, nk, frac, r, len, b.fin_chain + base, b.fin_seed + base, &ns, &nl, &nr);
     }
     b.n_chain[r] = nk; b.n_seed[r] = ns; b.n_left[r] = nl; b.n_right[r] = nr;
+    }
 }
+
 
 // E. compaction of the per-read stripes into flat arrays
 __global__ void chain_compact_kernel(const int64_t *__restrict__ read_smem_off, const int64_t *__restrict__ slot_off, int n_reads,
@@ -427,14 +438,21 @@ __global__ void __launch_bounds__(128)
 tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs,
             const bm2_chain *__restrict__ chains, const bm2_seed *__restrict__ seeds, const int64_t *__restrict__ chain_off,
             const int64_t *__restrict__ reg_off, int n_reads, bm2_alnreg_t *regs, const int32_t *reg_seed, int32_t *srt2_all, int32_t *he_all,
-            int he_stride, const int32_t *__restrict__ perm, PfBox *box_all, int32_t *n_final)
+            int he_stride, const int32_t *__restrict__ perm, PfBox *box_all, int32_t *n_final, int mode, int heavy_thr)
 {
+    // Heavy reads (many regs: O(regs^2) post-filter, sorts, patch DP) would serialise with the 31 other reads of their
+    // warp (ncu: 1.9 active lanes per instruction), so they get a WARP each (mode 1: reads in decreasing-work order,
+    // lane 0 works); light reads run one per thread (mode 0).
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
-    int32_t *he = he_all + (size_t) tid * he_stride;
-    for (int t = tid; t < n_reads; t += nthr) {
-        const int r = perm[t];
+    int32_t *he = he_all + (size_t) (mode ? tid >> 5 : tid) * he_stride;
+    const int unit = mode ? tid >> 5 : tid, nunit = mode ? nthr >> 5 : nthr;
+    if (mode && (threadIdx.x & 31)) return;
+    for (int t = unit; t < n_reads; t += nunit) {
+        const int r = mode ? perm[t] : t;
         const int64_t c0 = chain_off[r], c1 = chain_off[r + 1], g0 = reg_off[r];
         const int n_reg = (int) (reg_off[r + 1] - g0);
+        if (mode) { if (n_reg <= heavy_thr) break; }       // perm is sorted by decreasing n_reg
+        else if (n_reg > heavy_thr) continue;
         int m = 0;
         if (c1 > c0) {
             const int l_query = (int) (offs[r + 1] - offs[r]);
@@ -542,9 +560,9 @@ int scan64(bm2_ctx *ctx, const int64_t *in, int64_t *out, int64_t n) {
 // warp-cooperative the reads keep their input order (the permutation is the identity).
 static const bool kSortReadsByWork = false;
 
-int sort_work(bm2_ctx *ctx, uint32_t *keys_in, uint32_t *keys_out, int32_t *vals_in, int32_t *vals_out, int n) {
+int sort_work(bm2_ctx *ctx, uint32_t *keys_in, uint32_t *keys_out, int32_t *vals_in, int32_t *vals_out, int n, bool force = false) {
     bm2_ctx *ctx_for_error = ctx;
-    if (!kSortReadsByWork) {
+    if (!kSortReadsByWork && !force) {
         BM2_CUDA_OK(cudaMemcpyAsync(vals_out, vals_in, (size_t) n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         return 0;
     }
@@ -731,10 +749,17 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     uint32_t *wk_in = (uint32_t *) ctx->d[B_PERM].p, *wk_out = (uint32_t *) ((char *) ctx->d[B_PERM].p + al((size_t) n * 4));
     int32_t *wv_in = (int32_t *) ((char *) ctx->d[B_PERM].p + 2 * al((size_t) n * 4)), *d_perm = (int32_t *) ((char *) ctx->d[B_PERM].p + 3 * al((size_t) n * 4));
     work_keys_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(P<int64_t>(ctx, B_READ_SMEM_OFF), P<int64_t>(ctx, B_SLOT_OFF), n, wk_in, wv_in);
-    if (sort_work(ctx, wk_in, wk_out, wv_in, d_perm, n)) return 1;
+    if (sort_work(ctx, wk_in, wk_out, wv_in, d_perm, n, true)) return 1;             // decreasing number of seed slots
+    const int chain_heavy = 64;
     chain_kernel<<<(n + 127) / 128, 128, 0, st>>>(pv.cv, pv.cp, P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_READ_SMEM_OFF),
                                                   P<int64_t>(ctx, B_SLOT_OFF), P<int64_t>(ctx, B_SA), d_offs, n, d_perm, cb, pv.sw, ctx->idx.ref, d_codes,
-                                                  any_flt ? P<int32_t>(ctx, B_MINHSP) : nullptr);
+                                                  any_flt ? P<int32_t>(ctx, B_MINHSP) : nullptr, 0, chain_heavy);
+    {   // heavy reads: one warp each; the sorted list ends the grid early (warps whose read is light return at once)
+        int heavy_warps = n < ctx->n_sm * 256 ? n : ctx->n_sm * 256;
+        chain_kernel<<<(heavy_warps * 32 + 127) / 128, 128, 0, st>>>(pv.cv, pv.cp, P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_READ_SMEM_OFF),
+                                                                      P<int64_t>(ctx, B_SLOT_OFF), P<int64_t>(ctx, B_SA), d_offs, n, d_perm, cb, pv.sw,
+                                                                      ctx->idx.ref, d_codes, any_flt ? P<int32_t>(ctx, B_MINHSP) : nullptr, 1, chain_heavy);
+    }
 
     // ---- E. scans + compaction ------------------------------------------------------------------------------
     if (sg.mark("compact")) return 1;
@@ -829,8 +854,13 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     int blocks_i = (n + 127) / 128; const int max_blocks_i = ctx->n_sm * 8; if (blocks_i > max_blocks_i) blocks_i = max_blocks_i;
     const int he_stride = 2 * (max_len + 2);
     if (ctx->ensure(ctx->d[B_NW], (size_t) blocks_i * 128 * he_stride * 4)) return 1;
+    const int heavy_thr = 24;
+    work_keys_off_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_reg_off, n, wk_in, wv_in);
+    if (sort_work(ctx, wk_in, wk_out, wv_in, d_perm, n, true)) return 1;          // decreasing number of regs
     tail_kernel<<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
-                                          d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal);
+                                          d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, 0, heavy_thr);
+    tail_kernel<<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
+                                          d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, 1, heavy_thr);
 
     // ---- J. output ---------------------------------------------------------------------------------------
     if (sg.mark("output")) return 1;
