@@ -179,24 +179,42 @@ __device__ __forceinline__ void bsw_extend_one(const St &st, const QFetch &qf, c
         int f = 0;
         typename St::key_t mkey = -1;                // (h, j) packed; signed max => last column attaining the row maximum
         int j = beg;
-        typename QFetch::Cursor qc = qf.cursor(beg);
-#pragma unroll 4
-        for (; j < end; ++j) {
+        auto cell = [&](const int jj, const uint32_t qb) {
             int hd, e;
-            st.get(j, hd, e);
-            const uint32_t qb = (uint32_t) qf.next(qc, j);
+            st.get(jj, hd, e);
             // PRMT: byte 0 = tbl[qb] (qb = 4 selects the 0xFF byte of the second operand), bytes 1..3 = its sign
             int s;     // (inline PTX: the __byte_perm intrinsic masks the sign-replicate bit of the selector nibbles)
             asm("prmt.b32 %0, %1, %2, %3;" : "=r"(s) : "r"(tbl), "r"(0xFFFFFFFFu), "r"(qb * 0x1111u + 0x8880u));
-            const int M = hd ? hd + s : 0;
-            const int h = max(max(M, e), f);
+            // hd ? hd + s : 0, clamped at 0 (h, e and f are >= 0, so a negative M never shows): min against hd * 1024 is the hd == 0 test
+            const int M = max(min(hd + s, hd * 1024), 0);
+            const int h = (int) max(max((unsigned) M, (unsigned) e), (unsigned) f);     // all three are >= 0
             int t = max(M - oe_del, 0);
             e = max(e - e_del, t);
-            st.put(j, h1, e);
+            st.put(jj, h1, e);
             t = max(M - oe_ins, 0);
             f = max(f - e_ins, t);
             h1 = h;
-            mkey = max(mkey, St::key(h, j));
+            mkey = max(mkey, St::key(h, jj));
+        };
+        if (QFetch::kPacked) {
+            // head (to the next multiple of 8 columns), 8-column groups with one query word each, tail
+            if (j < end && (j & 7)) {
+                uint32_t qw = qf.word(j >> 3) >> ((j & 7) * 4);
+                const int he = min(end, (j + 7) & ~7);
+                for (; j < he; ++j) { const uint32_t nx = fma_shr(qw, 1u << 28); cell(j, (uint32_t) fma_mad((int) nx, -16, (int) qw)); qw = nx; }
+            }
+            for (; j + 8 <= end; j += 8) {
+                uint32_t qw = qf.word(j >> 3);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const uint32_t nx = fma_shr(qw, 1u << 28); cell(j + u, (uint32_t) fma_mad((int) nx, -16, (int) qw)); qw = nx; }
+            }
+            if (j < end) {
+                uint32_t qw = qf.word(j >> 3);
+                for (; j < end; ++j) { const uint32_t nx = fma_shr(qw, 1u << 28); cell(j, (uint32_t) fma_mad((int) nx, -16, (int) qw)); qw = nx; }
+            }
+        } else {
+            typename QFetch::Cursor qc = qf.cursor(beg);
+            for (; j < end; ++j) cell(j, (uint32_t) qf.next(qc, j));
         }
         const int m = mkey < 0 ? 0 : St::key_h(mkey);
         const int mj = mkey < 0 ? -1 : St::key_j(mkey);
@@ -229,7 +247,9 @@ __device__ __forceinline__ void bsw_extend_one(const St &st, const QFetch &qf, c
 struct QSmem4 {                // query packed 4 bit / base, [word][thread]
     unsigned base;             // shared-window address of &sh[W * blockDim.x + threadIdx.x]
     unsigned stride;
+    static constexpr bool kPacked = true;
     struct Cursor { uint32_t w; };
+    __device__ __forceinline__ uint32_t word(int k) const { return ldw(k); }
     __device__ __forceinline__ uint32_t ldw(int k) const {
         uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + (unsigned) k * stride)); return w;
     }
@@ -245,6 +265,8 @@ struct QSmem4 {                // query packed 4 bit / base, [word][thread]
 
 struct QGmem {                 // query bytes straight from global memory
     const uint8_t *ptr; int stride;
+    static constexpr bool kPacked = false;
+    __device__ __forceinline__ uint32_t word(int) const { return 0; }
     struct Cursor { int dummy; };
     __device__ __forceinline__ Cursor cursor(int) const { return Cursor(); }
     __device__ __forceinline__ int next(Cursor &, int j) const { return ptr[(long long) j * stride]; }
