@@ -16,6 +16,17 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from __graft_entry__ import load_package  # noqa: E402
 
 
+def _smem_traffic(args):
+    """DRAM bytes per step of the SMEM-stage kernels from the committed ncu capture, when it was taken on this workload."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "smem_traffic.json")))
+        if t["ref_mbp"] == args.ref_mbp and t["pairs"] == args.pairs:
+            return t["dram_bytes_per_step"]
+    except Exception:
+        pass
+    return None
+
+
 def _isa():
     flags = open("/proc/cpuinfo").read()
     return "avx512bw" if "avx512bw" in flags else "avx2"
@@ -306,6 +317,7 @@ def run_pipeline(args, rank, world):
     got, go = ctx.seed_chain_extend(codes[:ns * reads.shape[1]], offs[:ns + 1])
     want, wo, _, rc = ol.seed_chain_extend(index, ctx.opt, codes[:ns * reads.shape[1]], offs[:ns + 1])
     assert rc == 0 and np.array_equal(go, wo) and got.tobytes() == want.tobytes(), "bench workload differs from the oracle"
+    int_gops = ctx.int_pipe_gops()
     index_how = "built by the reference binary" if args.ref_mbp <= 400 else "built on the GPU by bwa_mem2_b200.index_build, byte-identical format"
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
@@ -375,11 +387,19 @@ def run_pipeline(args, rank, world):
                           "regs_per_step": int(n_regs)},
                "e2e": {"value": world * n / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(codes.nbytes + offs.nbytes),
                        "d2h_bytes_per_step": int(n_out * capi.REG_DT.itemsize + offs.nbytes)},
-               "gpu_launches": 56 * args.steps,      # our own kernels per step (cub sort/scan kernels not counted)
-               "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                            "kernel": "smem_kernel", "note": "algorithmic bytes = 128 B (two 64-B Occ checkpoints) x interval extensions counted by the kernel; "
-                                                             "peak = MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "of fallback",
+               "gpu_launches": 62 * args.steps,      # our own kernels per step (profiles/r1h_kernel_traffic_3gbp.md; cub sort/scan kernels not counted)
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                            "traffic": _smem_traffic(args),
+                            "kernel": "SMEM stage: smem_fwd1_kernel + smem_bwd_kernel + smem_fwd2_kernel + smem_bwd_kernel (+ smem_pass3_kernel on a side stream)",
+                            "note": "algorithmic bytes = 128 B (two 64-B Occ checkpoints) x interval extensions counted by the kernels; peak = "
+                                    + ("MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback of B200_PROFILING.md")
+                                    + "; traffic = DRAM read+write bytes of those kernels per step from profiles/ (ncu), null when the workload differs",
                             "extensions_per_read": cnt["n_ext"] / n, "kernel_ms": smem_ms},
+               "roofline_bsw": {"bound": "int-alu", "achieved": cnt["cells"] / (bsw_ms * 1e-3) / 1e9 if bsw_ms > 0 else None,
+                                "peak": int_gops / 14.0, "unit": "Gcell/s",
+                                "frac": (cnt["cells"] / (bsw_ms * 1e-3) / 1e9) / (int_gops / 14.0) if bsw_ms > 0 else None,
+                                "note": f"banded DP cells counted by the kernels / (bsw_left + bsw_right stage time); peak = {int_gops:.0f} G two-input "
+                                        "int32 op/s measured in-library (bm2_int_pipe_gops) / 14 ops per cell (SURVEY 8d)"},
                "stages_ms": {k: round(v, 3) for k, v in stage_acc.items()},
                "bsw": {"gcups": cnt["cells"] / (bsw_ms * 1e-3) / 1e9 if bsw_ms > 0 else None, "cells_per_step": int(cnt["cells"]),
                        "retry_left": int(cnt["retry_left"]), "retry_right": int(cnt["retry_right"])},

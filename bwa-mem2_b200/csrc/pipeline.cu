@@ -433,6 +433,89 @@ __global__ void gather_jobs_kernel(const ExtJobRec *jobs, const int32_t *sel, in
     if (t < n) out[t] = jobs[sel[t]];
 }
 
+// Post-filter of one read by a whole warp (same result as ext_postfilter_read_d, src/bwamem.cpp:2895-2989): the scan of
+// the earlier alignments - O(regs) per seed, O(regs^2) per read - is split over the lanes, 32 boxes per step.  Each lane
+// classifies its box as skipped / counted (v++) / hit (break); the sequential loop `for (i = 0; i < n_reg && v < lim; ++i)`
+// ends at the first hit whose preceding count is still below lim, which a ballot pair decides per 32 boxes.
+__device__ void ext_postfilter_read_warp(const ExtParams &p, const bm2_chain *chains, int n_chain, const bm2_seed *seeds, int l_query,
+                                         bm2_alnreg_t *regs, int n_reg, const int32_t *reg_seed, int32_t *srt2, PfBox *box)
+{
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < n_reg; i += 32) {
+        const bm2_alnreg_t &a = regs[i];
+        PfBox b; b.rb = a.rb; b.re = a.re; b.qb = a.qb; b.qe = a.qe; b.seedlen0 = a.seedlen0; b.w = a.w;
+        box[i] = b;
+    }
+    __syncwarp();
+    int lim = 0, base = 0;
+    for (int ci = 0; ci < n_chain; ++ci) {
+        const bm2_chain &c = chains[ci];
+        const bm2_seed *cs = seeds + c.seed_off;
+        const int n = c.n_seeds;
+        if (n == 0) continue;
+        for (int k = n - 1 - lane; k >= 0; k -= 32) srt2[k] = reg_seed[base + (n - 1 - k)];
+        __syncwarp();
+        for (int k = n - 1; k >= 0; --k) {
+            const bm2_seed s = cs[srt2[k]];
+            int v = 0;
+            for (int i0 = 0; i0 < n_reg && v < lim; i0 += 32) {
+                const int i = i0 + lane;
+                int kind = 0;                                   // 0 skipped, 1 counted, 2 hit
+                if (i < n_reg) {
+                    const PfBox q = box[i];
+                    if (!(q.qb == -1 && q.qe == -1)) {
+                        kind = 1;
+                        if (!(s.rbeg < q.rb || s.rbeg + s.len > q.re || s.qbeg < q.qb || s.qbeg + s.len > q.qe) &&
+                            !(s.len - q.seedlen0 > .1 * l_query)) {
+                            int64_t rd; int qd, w, max_gap;
+                            qd = s.qbeg - q.qb; rd = s.rbeg - q.rb;
+                            max_gap = cal_max_gap_d(p, qd < rd ? qd : (int) rd);
+                            w = max_gap < q.w ? max_gap : q.w;
+                            if (qd - rd < w && rd - qd < w) kind = 2;
+                            else {
+                                qd = q.qe - (s.qbeg + s.len); rd = q.re - (s.rbeg + s.len);
+                                max_gap = cal_max_gap_d(p, qd < rd ? qd : (int) rd);
+                                w = max_gap < q.w ? max_gap : q.w;
+                                if (qd - rd < w && rd - qd < w) kind = 2;
+                            }
+                        }
+                    }
+                }
+                const unsigned cm = __ballot_sync(0xFFFFFFFFu, kind == 1), hm = __ballot_sync(0xFFFFFFFFu, kind == 2);
+                if (hm) {
+                    const int at = v + __popc(cm & ((1u << (__ffs(hm) - 1)) - 1u));
+                    if (at < lim) { v = at; break; }
+                }
+                v += __popc(cm);
+            }
+            if (v < lim) {
+                int vv;
+                for (vv = k + 1; vv < n; ++vv) {
+                    if (srt2[vv] < 0) continue;
+                    const bm2_seed &t = cs[srt2[vv]];
+                    if (t.len < s.len * .95) continue;
+                    if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
+                    if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
+                }
+                if (vv == n) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int ai = base + (n - 1 - k);
+                        regs[ai].qb = regs[ai].qe = -1;
+                        box[ai].qb = box[ai].qe = -1;
+                        srt2[k] = -1;
+                    }
+                    __syncwarp();
+                    continue;
+                }
+            }
+            lim++;
+        }
+        __syncwarp();
+        base += n;
+    }
+}
+
 // I. one read per thread (grid-stride: the NW scratch `he` is per thread)
 __global__ void __launch_bounds__(128)
 tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs,
@@ -441,12 +524,11 @@ tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const 
             int he_stride, const int32_t *__restrict__ perm, PfBox *box_all, int32_t *n_final, int mode, int heavy_thr)
 {
     // Heavy reads (many regs: O(regs^2) post-filter, sorts, patch DP) would serialise with the 31 other reads of their
-    // warp (ncu: 1.9 active lanes per instruction), so they get a WARP each (mode 1: reads in decreasing-work order,
-    // lane 0 works); light reads run one per thread (mode 0).
+    // warp (ncu: 1.9 active lanes per instruction), so they get a WARP each (mode 1: reads in decreasing-work order; the
+    // post-filter scan runs on all lanes, the rest on lane 0); light reads run one per thread (mode 0).
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     int32_t *he = he_all + (size_t) (mode ? tid >> 5 : tid) * he_stride;
     const int unit = mode ? tid >> 5 : tid, nunit = mode ? nthr >> 5 : nthr;
-    if (mode && (threadIdx.x & 31)) return;
     for (int t = unit; t < n_reads; t += nunit) {
         const int r = mode ? perm[t] : t;
         const int64_t c0 = chain_off[r], c1 = chain_off[r + 1], g0 = reg_off[r];
@@ -456,10 +538,17 @@ tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const 
         int m = 0;
         if (c1 > c0) {
             const int l_query = (int) (offs[r + 1] - offs[r]);
-            ext_postfilter_read_d(ep, chains + c0, (int) (c1 - c0), seeds, l_query, regs + g0, n_reg, reg_seed + g0, srt2_all + g0, box_all + g0);
-            m = ext_tail_read_d(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he, srt2_all + g0);
+            if (mode) {
+                ext_postfilter_read_warp(ep, chains + c0, (int) (c1 - c0), seeds, l_query, regs + g0, n_reg, reg_seed + g0, srt2_all + g0, box_all + g0);
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) m = ext_tail_read_d(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he, srt2_all + g0);
+                __syncwarp();
+            } else {
+                ext_postfilter_read_d(ep, chains + c0, (int) (c1 - c0), seeds, l_query, regs + g0, n_reg, reg_seed + g0, srt2_all + g0, box_all + g0);
+                m = ext_tail_read_d(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he, srt2_all + g0);
+            }
         }
-        n_final[r] = m;
+        if (!mode || (threadIdx.x & 31) == 0) n_final[r] = m;
     }
 }
 
