@@ -14,11 +14,15 @@
 // by (query-length class, target length) so that the 32 lanes of a warp run similar trip counts.
 // Integer-ALU bound; HBM traffic is ~(qlen+tlen+56) B per job.
 #include "bm2_common.cuh"
+#include "bsw_pair.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 #define BSW_THREADS 128
 #define BSW_NBOUND 8
-#define BSW_NCLASS 16          // class = 2 * bound index + (needs 16-bit state)
+#define BSW_NCLASS 16          // class = 2 * bound index + (needs 16-bit state); class 16 = wide (warp / global-state kernels)
+#define BSW_NPAIR 5            // pair classes 17..21: two jobs per thread in packed 16-bit halves (bsw_pair.cuh), bounds 32..160
+#define BSW_PAIR0 (BSW_NCLASS + 1)
+#define BSW_NALL (BSW_PAIR0 + BSW_NPAIR)
 // upper query-length bound of each class (state words = bound + 2)
 __constant__ int c_class_bound[BSW_NBOUND] = {32, 64, 96, 128, 160, 256, 512, 1024};
 static const int h_class_bound[BSW_NBOUND] = {32, 64, 96, 128, 160, 256, 512, 1024};
@@ -45,30 +49,38 @@ __device__ __forceinline__ int bsw_class_of(int qlen, int tlen, int h0, int a) {
     return BSW_NCLASS;
 }
 
-__global__ void bsw_keys_kernel(const BswJob *jobs, int n, int a, uint32_t *keys, int32_t *idx, int32_t *class_cnt) {
-    __shared__ int hist[BSW_NCLASS + 1];
-    if (threadIdx.x <= BSW_NCLASS) hist[threadIdx.x] = 0;
+__global__ void bsw_keys_kernel(const BswJob *jobs, int n, int a, int pair_ok, const uint8_t *__restrict__ qbase, uint32_t *keys, int32_t *idx,
+                                int32_t *class_cnt) {
+    __shared__ int hist[BSW_NALL];
+    if (threadIdx.x < BSW_NALL) hist[threadIdx.x] = 0;
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         BswJob j = jobs[i];
         int c = bsw_class_of(j.qlen, j.tlen, j.h0, a);
+        // 8-bit-score jobs with a short N-free query run two per thread (bsw_pair_kernel)
+        if (pair_ok && !(c & 1) && c < 2 * BSW_NPAIR) {
+            const uint8_t *qp = qbase + j.qoff;
+            bool has_n = false;
+            for (int k = 0; k < j.qlen && !has_n; ++k) has_n = qp[(long long) k * j.qstride] > 3;
+            if (!has_n) c = BSW_PAIR0 + (c >> 1);
+        }
         int t = j.tlen > 0x7FFFF ? 0x7FFFF : j.tlen;
         // ascending sort => class ascending, target length descending (long jobs first), then qlen desc
         int q = j.qlen > 0xFF ? 0xFF : j.qlen;
-        keys[i] = ((uint32_t) c << 27) | ((uint32_t) (0x7FFFF - t) << 8) | (uint32_t) (0xFF - q);   // c <= 16: 5 bits
+        keys[i] = ((uint32_t) c << 27) | ((uint32_t) (0x7FFFF - t) << 8) | (uint32_t) (0xFF - q);   // c <= 21: 5 bits
         idx[i] = i;
         atomicAdd(&hist[c], 1);
     }
     __syncthreads();
-    if (threadIdx.x <= BSW_NCLASS && hist[threadIdx.x]) atomicAdd(&class_cnt[threadIdx.x], hist[threadIdx.x]);
+    if (threadIdx.x < BSW_NALL && hist[threadIdx.x]) atomicAdd(&class_cnt[threadIdx.x], hist[threadIdx.x]);
 }
 
 __global__ void bsw_class_off_kernel(const int32_t *class_cnt, int32_t *class_off) {
     if (threadIdx.x == 0) {
         int s = 0;
-        for (int c = 0; c <= BSW_NCLASS; ++c) { class_off[c] = s; s += class_cnt[c]; }
-        class_off[BSW_NCLASS + 1] = s;
+        for (int c = 0; c < BSW_NALL; ++c) { class_off[c] = s; s += class_cnt[c]; }
+        class_off[BSW_NALL] = s;
     }
 }
 
@@ -318,6 +330,72 @@ bsw_thread_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ p
 }
 
 // ---------------------------------------------------------------------------------------------
+// Two jobs per thread (bsw_pair.cuh): consecutive jobs of the sorted pair class share a thread, job A in the low
+// halves, job B in the high halves.  Shared memory: packed state {H_A, E_A, H_B, E_B} one word per column
+// [column][thread], then the PRMT selectors of the query pair, 16 bit per column [column][thread].
+// ---------------------------------------------------------------------------------------------
+struct PairMemShared {
+    unsigned st_base, st_stride;        // shared-window byte address of the thread's column 0, nthr * 4
+    unsigned sel_base, sel_stride;      // selectors: nthr * 2
+    __device__ __forceinline__ uint32_t ld(int j) const {
+        uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(st_base + (unsigned) j * st_stride)); return w;
+    }
+    __device__ __forceinline__ void st(int j, uint32_t w) const {
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(st_base + (unsigned) j * st_stride), "r"(w) : "memory");
+    }
+    __device__ __forceinline__ uint32_t ld_half(int j, int l) const {
+        uint16_t w; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w) : "r"(st_base + (unsigned) j * st_stride + 2u * (unsigned) l)); return (uint32_t) w;
+    }
+    __device__ __forceinline__ void st_half(int j, int l, uint32_t v) const {
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(st_base + (unsigned) j * st_stride + 2u * (unsigned) l), "h"((uint16_t) v) : "memory");
+    }
+    __device__ __forceinline__ uint32_t sel(int j) const {
+        uint16_t w; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w) : "r"(sel_base + (unsigned) j * sel_stride)); return (uint32_t) w;
+    }
+    __device__ __forceinline__ void set_sel(int j, uint32_t v) const {
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(sel_base + (unsigned) j * sel_stride), "h"((uint16_t) v) : "memory");
+    }
+};
+
+__global__ void __launch_bounds__(BSW_THREADS)
+bsw_pair_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ perm, const int32_t *__restrict__ class_off,
+                int cls, BswOut *__restrict__ out, const uint8_t *__restrict__ tbase, const uint8_t *__restrict__ qbase,
+                BswParams p, int W, unsigned long long *cells)
+{
+    extern __shared__ uint32_t sh[];
+    const int first = class_off[cls], last = class_off[cls + 1];
+    const int nthr = blockDim.x;
+    PairMemShared mem;
+    mem.st_base = (unsigned) __cvta_generic_to_shared(sh) + threadIdx.x * 4u; mem.st_stride = (unsigned) nthr * 4u;
+    mem.sel_base = (unsigned) __cvta_generic_to_shared(sh) + (unsigned) W * nthr * 4u + threadIdx.x * 2u; mem.sel_stride = (unsigned) nthr * 2u;
+    unsigned long long ncell = 0;
+    for (int blk = blockIdx.x; first + 2 * blk * nthr < last; blk += gridDim.x) {      // persistent CTAs: long jobs first
+        const int g = first + 2 * (blk * nthr + threadIdx.x);
+        if (g < last) {
+            const int nj = g + 1 < last ? 2 : 1;
+            const int idA = perm[g], idB = nj == 2 ? perm[g + 1] : idA;
+            const BswJob ja = jobs[idA], jb = jobs[idB];
+            const int qlen[2] = {ja.qlen, nj == 2 ? jb.qlen : 0}, tlen[2] = {ja.tlen, nj == 2 ? jb.tlen : 0}, h0[2] = {ja.h0, nj == 2 ? jb.h0 : 0};
+            const uint8_t *qa = qbase + ja.qoff, *qb = qbase + jb.qoff;
+            const int qmax = qlen[0] > qlen[1] ? qlen[0] : qlen[1];
+            for (int j = 0; j <= qmax; ++j) {
+                const int ba = j < qlen[0] ? (int) qa[(long long) j * ja.qstride] : 0, bb = j < qlen[1] ? (int) qb[(long long) j * jb.qstride] : 0;
+                mem.set_sel(j, p2_selector(ba & 3, bb & 3));
+            }
+            BswOut o[2];
+            bsw_pair_extend(mem, tbase + ja.toff, (int) ja.tstride, tbase + jb.toff, (int) jb.tstride, qlen, tlen, h0, nj, p, o, ncell);
+            out[idA] = o[0];
+            if (nj == 2) out[idB] = o[1];
+        }
+    }
+    if (cells) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) ncell += __shfl_xor_sync(0xffffffffu, ncell, d);
+        if ((threadIdx.x & 31) == 0 && ncell) atomicAdd(cells, ncell);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Warp-per-job kernel for long queries (the wide class: qlen > 1024 or 32-bit scores; long reads).
 // A row of the band (<= 2w+1 columns) is split over the 32 lanes, CMAX columns per lane.  F, the only state
 // that runs along the row, depends on M(k), k < j only:
@@ -536,7 +614,8 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys_in, keys_out, idx_in, idx_out, n);
 
     BM2_CUDA_OK(cudaMemsetAsync(class_cnt, 0, 256, stream));
-    bsw_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_jobs, n, prm.a, keys_in, idx_in, class_cnt);
+    const int pair_ok = p2_params_ok(prm) ? 1 : 0;
+    bsw_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_jobs, n, prm.a, pair_ok, d_qbase, keys_in, idx_in, class_cnt);
     BM2_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, idx_in, idx_out, n, 0, 32, stream));
     bsw_class_off_kernel<<<1, 32, 0, stream>>>(class_cnt, class_off);
 
@@ -544,6 +623,7 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     if (!attr_set) {   // one function, several dynamic sizes: raise the limit once
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     int n_sm = 148;
@@ -565,6 +645,22 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
         if (nblk > cap_blk) nblk = cap_blk;
         if (is16) bsw_thread_kernel<SmemPacked><<<nblk, nthr, smem, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, W, d_cells);
         else bsw_thread_kernel<SmemPacked8><<<nblk, nthr, smem, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, W, d_cells);
+    }
+    for (int c = 0; pair_ok && c < BSW_NPAIR; ++c) {
+        const int W = h_class_bound[c] + 2;
+        const size_t per_thread = (size_t) W * 6;
+        // threads per CTA: the size that keeps the most threads resident per SM
+        int nthr = 32, best_res = 0;
+        for (int t = 128; t >= 32; t -= 32) {
+            const int ctas = (int) ((227 * 1024) / (per_thread * t + 1024));
+            const int res = (ctas > 16 ? 16 : ctas) * t;
+            if (res > best_res) { best_res = res; nthr = t; }
+        }
+        const size_t smem = per_thread * nthr;
+        int ctas_per_sm = (int) ((227 * 1024) / (smem + 1024)); if (ctas_per_sm < 1) ctas_per_sm = 1; if (ctas_per_sm > 16) ctas_per_sm = 16;
+        int nblk = (n + 2 * nthr - 1) / (2 * nthr);
+        if (nblk > n_sm * ctas_per_sm) nblk = n_sm * ctas_per_sm;
+        bsw_pair_kernel<<<nblk, nthr, smem, stream>>>(d_jobs, idx_out, class_off, BSW_PAIR0 + c, d_out, d_tbase, d_qbase, prm, W, d_cells);
     }
     if (wide_possible) {
         int *next_job = class_cnt + 48;                    // zeroed with class_cnt above
