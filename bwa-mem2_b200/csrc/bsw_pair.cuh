@@ -21,7 +21,10 @@ BM2_D uint32_t p2_addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return __via
 BM2_D uint32_t p2_max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 BM2_D uint32_t p2_maxu(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
 BM2_D uint32_t p2_add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+// a * b + c as ONE multiply-add on the FMA pipe (the compiler would turn constant multiplies into ALU-pipe shift/mask pairs)
+BM2_D uint32_t p2_mad(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 #else
+inline uint32_t p2_mad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
 inline uint32_t p2_prmt(uint32_t a, uint32_t b, uint32_t s) {            // PTX prmt.b32, default mode
     const uint64_t src = ((uint64_t) b << 32) | a;
     uint32_t d = 0;
@@ -84,14 +87,14 @@ BM2_HD void p2_cells(const Mem &mem, int j0, int j1, uint32_t tblA, uint32_t tbl
         const uint32_t hd = w & (MODE == 0 ? 0x00FF00FFu : MODE == 1 ? 0x000000FFu : 0x00FF0000u);
         const uint32_t e = p2_prmt(w, 0u, MODE == 0 ? 0x4341u : MODE == 1 ? 0x4441u : 0x4344u);
         const uint32_t s = p2_prmt(tblA, tblB, mem.sel(j));
-        const uint32_t M = p2_addmin_relu(hd, s, hd * 128u);          // hd ? max(hd + s, 0) : 0   (s <= 127)
+        const uint32_t M = p2_addmin_relu(hd, s, p2_mad(hd, 128u, 0u));          // hd ? max(hd + s, 0) : 0   (s <= 127)
         const uint32_t h = p2_max3(M, e, f);
         const uint32_t en = p2_addmax_relu(e, c.n_e_del, p2_add(M, c.n_oe_del));
-        const uint32_t wn = h1 + en * 256u;
+        const uint32_t wn = p2_mad(en, 256u, h1);
         if (MODE == 0) mem.st(j, wn); else if (MODE == 1) mem.st_half(j, 0, wn & 0xFFFFu); else mem.st_half(j, 1, wn >> 16);
         f = p2_addmax_relu(f, c.n_e_ins, p2_add(M, c.n_oe_ins));
         h1 = h;
-        mkey = p2_maxu(mkey, h * 256u + jj);
+        mkey = p2_maxu(mkey, p2_mad(h, 256u, jj));
         jj += 0x10001u;
     }
 }
@@ -139,11 +142,10 @@ BM2_HD void bsw_pair_extend(const Mem &mem, const uint8_t *tptrA, int tstrideA, 
         }
     }
     for (int i = 0; alive[0] || alive[1]; ++i) {
-        int b[2], e[2];
-        uint32_t tbl[2], h1 = 0;
+        int b0 = 0, e0 = 0, b1 = 0, e1 = 0;
+        uint32_t tbl0 = 0xFFFFFFFFu, tbl1 = 0xFFFFFFFFu, h1 = 0;
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
-            tbl[l] = 0xFFFFFFFFu; b[l] = e[l] = 0;
             if (alive[l]) {
                 if (beg[l] < i - w[l]) beg[l] = i - w[l];
                 if (end[l] > i + w[l] + 1) end[l] = i + w[l] + 1;
@@ -152,37 +154,39 @@ BM2_HD void bsw_pair_extend(const Mem &mem, const uint8_t *tptrA, int tstrideA, 
                 if (beg[l] == 0) { hi = h0[l] - (p.o_del + e_del * (i + 1)); if (hi < 0) hi = 0; }
                 h1 |= (uint32_t) hi << (16 * l);
                 const int tb = l == 0 ? tptrA[(long long) i * tstrideA] : tptrB[(long long) i * tstrideB];
-                tbl[l] = p2_score_table(tb, p.a, p.b);
-                b[l] = beg[l]; e[l] = end[l] > beg[l] ? end[l] : beg[l];
+                const uint32_t tv = p2_score_table(tb, p.a, p.b);
+                const int bv = beg[l], ev = end[l] > beg[l] ? end[l] : beg[l];
+                if (l == 0) { tbl0 = tv; b0 = bv; e0 = ev; } else { tbl1 = tv; b1 = bv; e1 = ev; }
             }
         }
-        if (!alive[0]) b[0] = e[0] = e[1];             // an idle job contributes an empty interval at the other's end
-        if (!alive[1]) b[1] = e[1] = e[0];
+        if (!alive[0]) b0 = e0 = e1;                   // an idle job contributes an empty interval at the other's end
+        if (!alive[1]) b1 = e1 = e0;
         uint32_t f = 0, mkey = 0;
         {
-            const int first = b[0] <= b[1] ? 0 : 1, second = first ^ 1;
-            const int bmax = b[second], emin = e[0] < e[1] ? e[0] : e[1];
-            const int lastl = e[0] >= e[1] ? 0 : 1;
+            // (selects, no dynamic indexing: everything stays in registers)
+            const bool a_first = b0 <= b1, a_last = e0 >= e1;
+            const int bmin = a_first ? b0 : b1, bmax = a_first ? b1 : b0, e_first = a_first ? e0 : e1;
+            const int emin = a_last ? e1 : e0, emax = a_last ? e0 : e1;
             // 1. only the job that starts first
-            const int s1e = bmax < e[first] ? bmax : e[first];
-            if (b[first] < s1e) {
-                const uint32_t keep = first == 0 ? 0xFFFF0000u : 0x0000FFFFu;
+            const int s1e = bmax < e_first ? bmax : e_first;
+            if (bmin < s1e) {
+                const uint32_t keep = a_first ? 0xFFFF0000u : 0x0000FFFFu;
                 const uint32_t sf = f & keep, sh = h1 & keep, sk = mkey & keep;
                 f &= ~keep; h1 &= ~keep; mkey &= ~keep;
-                if (first == 0) p2_cells<1>(mem, b[first], s1e, tbl[0], tbl[1], c, f, h1, mkey);
-                else p2_cells<2>(mem, b[first], s1e, tbl[0], tbl[1], c, f, h1, mkey);
+                if (a_first) p2_cells<1>(mem, bmin, s1e, tbl0, tbl1, c, f, h1, mkey);
+                else p2_cells<2>(mem, bmin, s1e, tbl0, tbl1, c, f, h1, mkey);
                 f = (f & ~keep) | sf; h1 = (h1 & ~keep) | sh; mkey = (mkey & ~keep) | sk;
             }
             // 2. both
-            if (bmax < emin) p2_cells<0>(mem, bmax, emin, tbl[0], tbl[1], c, f, h1, mkey);
+            if (bmax < emin) p2_cells<0>(mem, bmax, emin, tbl0, tbl1, c, f, h1, mkey);
             // 3. only the job that ends last
             const int s3b = emin > bmax ? emin : bmax;
-            if (s3b < e[lastl]) {
-                const uint32_t keep = lastl == 0 ? 0xFFFF0000u : 0x0000FFFFu;
+            if (s3b < emax) {
+                const uint32_t keep = a_last ? 0xFFFF0000u : 0x0000FFFFu;
                 const uint32_t sf = f & keep, sh = h1 & keep, sk = mkey & keep;
                 f &= ~keep; h1 &= ~keep; mkey &= ~keep;
-                if (lastl == 0) p2_cells<1>(mem, s3b, e[lastl], tbl[0], tbl[1], c, f, h1, mkey);
-                else p2_cells<2>(mem, s3b, e[lastl], tbl[0], tbl[1], c, f, h1, mkey);
+                if (a_last) p2_cells<1>(mem, s3b, emax, tbl0, tbl1, c, f, h1, mkey);
+                else p2_cells<2>(mem, s3b, emax, tbl0, tbl1, c, f, h1, mkey);
                 f = (f & ~keep) | sf; h1 = (h1 & ~keep) | sh; mkey = (mkey & ~keep) | sk;
             }
         }

@@ -41,6 +41,20 @@ def test_random_jobs_match_oracle(pkg, gpu_ctx, seed, qmax, tmax, w):
     _assert_same(p, want)
 
 
+@pytest.mark.parametrize("seed,qmax,tmax,w", [(21, 151, 400, 100), (22, 60, 200, 100), (23, 151, 300, 7)])
+def test_random_low_score_jobs_match_oracle(pkg, gpu_ctx, seed, qmax, tmax, w):
+    # small h0, almost no N: most jobs take the two-jobs-per-thread kernel (8-bit scores, bsw_pair_kernel)
+    rng = np.random.default_rng(seed)
+    n = 6001
+    len1, len2, h0, idr, idq, ref, qer = _random_jobs(rng, n, qmax, tmax, nrate=0.001, h0max=60)
+    p = np.zeros(n, pkg.capi.PAIR_DT)
+    p["len1"] = len1; p["len2"] = len2; p["h0"] = h0; p["idr"] = idr; p["idq"] = idq
+    want = p.copy()
+    gpu_ctx.extend_pairs(p, ref, qer, w, 5)
+    ol.extend_pairs(want, ref, qer, w, ol.bsw_params(end_bonus=5))
+    _assert_same(p, want)
+
+
 def test_edge_cases(pkg, gpu_ctx):
     # empty target, single-base query/target, all-N query, h0 near the int16 class limit, >int16 scores (wide path)
     seq = np.array([0, 1, 2, 3] * 64, np.uint8)
