@@ -334,9 +334,10 @@ bsw_thread_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ p
 // halves, job B in the high halves.  Shared memory: packed state {H_A, E_A, H_B, E_B} one word per column
 // [column][thread], then the PRMT selectors of the query pair, 16 bit per column [column][thread].
 // ---------------------------------------------------------------------------------------------
+template <int NTHR>                     // compile-time strides: the unrolled cell loop addresses columns as [base + immediate]
 struct PairMemShared {
-    unsigned st_base, st_stride;        // shared-window byte address of the thread's column 0, nthr * 4
-    unsigned sel_base, sel_stride;      // selectors: nthr * 2
+    unsigned st_base, sel_base;         // shared-window byte addresses of the thread's column 0 (state words, selectors)
+    static constexpr unsigned st_stride = NTHR * 4u, sel_stride = NTHR * 2u;
     __device__ __forceinline__ uint32_t ld(int j) const {
         uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(st_base + (unsigned) j * st_stride)); return w;
     }
@@ -357,17 +358,18 @@ struct PairMemShared {
     }
 };
 
-__global__ void __launch_bounds__(BSW_THREADS)
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR)
 bsw_pair_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ perm, const int32_t *__restrict__ class_off,
                 int cls, BswOut *__restrict__ out, const uint8_t *__restrict__ tbase, const uint8_t *__restrict__ qbase,
                 BswParams p, int W, unsigned long long *cells)
 {
     extern __shared__ uint32_t sh[];
     const int first = class_off[cls], last = class_off[cls + 1];
-    const int nthr = blockDim.x;
-    PairMemShared mem;
-    mem.st_base = (unsigned) __cvta_generic_to_shared(sh) + threadIdx.x * 4u; mem.st_stride = (unsigned) nthr * 4u;
-    mem.sel_base = (unsigned) __cvta_generic_to_shared(sh) + (unsigned) W * nthr * 4u + threadIdx.x * 2u; mem.sel_stride = (unsigned) nthr * 2u;
+    constexpr int nthr = NTHR;
+    PairMemShared<NTHR> mem;
+    mem.st_base = (unsigned) __cvta_generic_to_shared(sh) + threadIdx.x * 4u;
+    mem.sel_base = (unsigned) __cvta_generic_to_shared(sh) + (unsigned) W * nthr * 4u + threadIdx.x * 2u;
     unsigned long long ncell = 0;
     for (int blk = blockIdx.x; first + 2 * blk * nthr < last; blk += gridDim.x) {      // persistent CTAs: long jobs first
         const int g = first + 2 * (blk * nthr + threadIdx.x);
@@ -623,7 +625,10 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     if (!attr_set) {   // one function, several dynamic sizes: raise the limit once
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     int n_sm = 148;
@@ -660,7 +665,9 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
         int ctas_per_sm = (int) ((227 * 1024) / (smem + 1024)); if (ctas_per_sm < 1) ctas_per_sm = 1; if (ctas_per_sm > 16) ctas_per_sm = 16;
         int nblk = (n + 2 * nthr - 1) / (2 * nthr);
         if (nblk > n_sm * ctas_per_sm) nblk = n_sm * ctas_per_sm;
-        bsw_pair_kernel<<<nblk, nthr, smem, stream>>>(d_jobs, idx_out, class_off, BSW_PAIR0 + c, d_out, d_tbase, d_qbase, prm, W, d_cells);
+#define BM2_PAIR_LAUNCH(T) bsw_pair_kernel<T><<<nblk, T, smem, stream>>>(d_jobs, idx_out, class_off, BSW_PAIR0 + c, d_out, d_tbase, d_qbase, prm, W, d_cells)
+        if (nthr == 128) BM2_PAIR_LAUNCH(128); else if (nthr == 96) BM2_PAIR_LAUNCH(96); else if (nthr == 64) BM2_PAIR_LAUNCH(64); else BM2_PAIR_LAUNCH(32);
+#undef BM2_PAIR_LAUNCH
     }
     if (wide_possible) {
         int *next_job = class_cnt + 48;                    // zeroed with class_cnt above

@@ -4,8 +4,7 @@
 // :2905-2926) for jobs whose scores fit 8 bits (h0 + min(qlen, tlen) * a <= 255: every job of a 2x151 bp read),
 // whose query has no N and is at most 255 columns long.  Job A lives in the low half of every packed register,
 // job B in the high half; each keeps its OWN band [beg, end), exit row and outputs - a row is run as up to three
-// column segments (only the job that starts first / both / only the job that ends last), so nothing is masked per
-// cell.  Per pair of cells: 1 LDS + 1 STS of the packed state {H_A, E_A, H_B, E_B} (4 x 8 bit), one PRMT for both
+// column segments (only the job that starts first / both / only the job that ends last) through one cell loop.  Per pair of cells: 1 LDS + 1 STS of the packed state {H_A, E_A, H_B, E_B} (4 x 8 bit), one PRMT for both
 // substitution scores (the per-column selector is precomputed from the two queries), 3 VIADDMNMX.S16x2, 1 VIMNMX3,
 // and the row maximum + its last column as one unsigned key (h << 8 | j) per half.
 //
@@ -76,22 +75,35 @@ BM2_HD bool p2_params_ok(const BswParams &p) {
 
 struct PairConsts { uint32_t n_oe_del, n_e_del, n_oe_ins, n_e_ins; };     // negated penalties in both halves
 
-// Columns [j0, j1) of one row.  MODE 0: both jobs; 1: job A only; 2: job B only (the other half is forced to 0 so
-// that no carry crosses the halves, and its state is not written).
-template <int MODE, class Mem>
-BM2_HD void p2_cells(const Mem &mem, int j0, int j1, uint32_t tblA, uint32_t tblB, const PairConsts &c, uint32_t &f, uint32_t &h1, uint32_t &mkey)
+// Columns [j0, j1) of one row for the jobs selected by `act` (0xFFFF per active half).  ONE code path for "both",
+// "A only" and "B only" (the lanes of a warp are in different situations; separate loops would serialise them): the
+// idle half is forced to 0 on input (hmask / esel) so that no carry crosses the halves, and its state is written back
+// unchanged (one LOP3 blend).
+struct PairMode { uint32_t hmask, esel, act; };
+BM2_HD PairMode p2_mode(bool a_on, bool b_on) {
+    PairMode m;
+    m.hmask = (a_on ? 0x000000FFu : 0u) | (b_on ? 0x00FF0000u : 0u);
+    m.esel = (a_on ? 0x0001u : 0x0004u) | 0x0040u | (b_on ? 0x0300u : 0x0400u) | 0x4000u;     // E bytes 1 / 3 or the zero byte
+    m.act = (a_on ? 0x0000FFFFu : 0u) | (b_on ? 0xFFFF0000u : 0u);
+    return m;
+}
+
+template <class Mem>
+BM2_HD void p2_cells(const Mem &mem, int j0, int j1, const PairMode md, uint32_t tblA, uint32_t tblB, const PairConsts &c,
+                     uint32_t &f, uint32_t &h1, uint32_t &mkey)
 {
     uint32_t jj = (uint32_t) j0 * 0x10001u;
+#pragma unroll 4
     for (int j = j0; j < j1; ++j) {
         const uint32_t w = mem.ld(j);
-        const uint32_t hd = w & (MODE == 0 ? 0x00FF00FFu : MODE == 1 ? 0x000000FFu : 0x00FF0000u);
-        const uint32_t e = p2_prmt(w, 0u, MODE == 0 ? 0x4341u : MODE == 1 ? 0x4441u : 0x4344u);
+        const uint32_t hd = w & md.hmask;
+        const uint32_t e = p2_prmt(w, 0u, md.esel);
         const uint32_t s = p2_prmt(tblA, tblB, mem.sel(j));
         const uint32_t M = p2_addmin_relu(hd, s, p2_mad(hd, 128u, 0u));          // hd ? max(hd + s, 0) : 0   (s <= 127)
         const uint32_t h = p2_max3(M, e, f);
         const uint32_t en = p2_addmax_relu(e, c.n_e_del, p2_add(M, c.n_oe_del));
         const uint32_t wn = p2_mad(en, 256u, h1);
-        if (MODE == 0) mem.st(j, wn); else if (MODE == 1) mem.st_half(j, 0, wn & 0xFFFFu); else mem.st_half(j, 1, wn >> 16);
+        mem.st(j, (wn & md.act) | (w & ~md.act));
         f = p2_addmax_relu(f, c.n_e_ins, p2_add(M, c.n_oe_ins));
         h1 = h;
         mkey = p2_maxu(mkey, p2_mad(h, 256u, jj));
@@ -163,31 +175,22 @@ BM2_HD void bsw_pair_extend(const Mem &mem, const uint8_t *tptrA, int tstrideA, 
         if (!alive[1]) b1 = e1 = e0;
         uint32_t f = 0, mkey = 0;
         {
-            // (selects, no dynamic indexing: everything stays in registers)
+            // three column segments: only the job that starts first / both / only the job that ends last
             const bool a_first = b0 <= b1, a_last = e0 >= e1;
             const int bmin = a_first ? b0 : b1, bmax = a_first ? b1 : b0, e_first = a_first ? e0 : e1;
             const int emin = a_last ? e1 : e0, emax = a_last ? e0 : e1;
-            // 1. only the job that starts first
             const int s1e = bmax < e_first ? bmax : e_first;
-            if (bmin < s1e) {
-                const uint32_t keep = a_first ? 0xFFFF0000u : 0x0000FFFFu;
-                const uint32_t sf = f & keep, sh = h1 & keep, sk = mkey & keep;
-                f &= ~keep; h1 &= ~keep; mkey &= ~keep;
-                if (a_first) p2_cells<1>(mem, bmin, s1e, tbl0, tbl1, c, f, h1, mkey);
-                else p2_cells<2>(mem, bmin, s1e, tbl0, tbl1, c, f, h1, mkey);
-                f = (f & ~keep) | sf; h1 = (h1 & ~keep) | sh; mkey = (mkey & ~keep) | sk;
-            }
-            // 2. both
-            if (bmax < emin) p2_cells<0>(mem, bmax, emin, tbl0, tbl1, c, f, h1, mkey);
-            // 3. only the job that ends last
             const int s3b = emin > bmax ? emin : bmax;
-            if (s3b < emax) {
-                const uint32_t keep = a_last ? 0xFFFF0000u : 0x0000FFFFu;
-                const uint32_t sf = f & keep, sh = h1 & keep, sk = mkey & keep;
-                f &= ~keep; h1 &= ~keep; mkey &= ~keep;
-                if (a_last) p2_cells<1>(mem, s3b, emax, tbl0, tbl1, c, f, h1, mkey);
-                else p2_cells<2>(mem, s3b, emax, tbl0, tbl1, c, f, h1, mkey);
-                f = (f & ~keep) | sf; h1 = (h1 & ~keep) | sh; mkey = (mkey & ~keep) | sk;
+#pragma unroll 1
+            for (int sg = 0; sg < 3; ++sg) {
+                const int j0 = sg == 0 ? bmin : sg == 1 ? bmax : s3b, j1 = sg == 0 ? s1e : sg == 1 ? emin : emax;
+                if (j0 >= j1) continue;
+                const bool a_on = sg == 1 || (sg == 0 ? a_first : a_last), b_on = sg == 1 || (sg == 0 ? !a_first : !a_last);
+                const PairMode md = p2_mode(a_on, b_on);
+                const uint32_t sf = f & ~md.act, sh = h1 & ~md.act, sk = mkey & ~md.act;     // the idle half keeps its running values
+                f &= md.act; h1 &= md.act; mkey &= md.act;
+                p2_cells(mem, j0, j1, md, tbl0, tbl1, c, f, h1, mkey);
+                f = (f & md.act) | sf; h1 = (h1 & md.act) | sh; mkey = (mkey & md.act) | sk;
             }
         }
 #pragma unroll
