@@ -15,6 +15,7 @@
 // Integer-ALU bound; HBM traffic is ~(qlen+tlen+56) B per job.
 #include "bm2_common.cuh"
 #include "bsw_pair.cuh"
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
 #define BSW_THREADS 128
@@ -616,7 +617,11 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys_in, keys_out, idx_in, idx_out, n);
 
     BM2_CUDA_OK(cudaMemsetAsync(class_cnt, 0, 256, stream));
-    const int pair_ok = p2_params_ok(prm) ? 1 : 0;
+    // Two-jobs-per-thread kernel (bsw_pair.cuh): bit-exact, but measured SLOWER than the thread-per-job kernel on B200
+    // (115 vs 89 ms per 1 M reads: the lanes of a warp spend the pre/post column segments of their pairs apart,
+    // profiles/r1k_bsw_pair_3gbp.md), so it is off unless BM2_BSW_PAIR=1 asks for it (experiments, tests).
+    const char *pair_env = getenv("BM2_BSW_PAIR");
+    const int pair_ok = (pair_env && pair_env[0] == '1' && p2_params_ok(prm)) ? 1 : 0;
     bsw_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_jobs, n, prm.a, pair_ok, d_qbase, keys_in, idx_in, class_cnt);
     BM2_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, idx_in, idx_out, n, 0, 32, stream));
     bsw_class_off_kernel<<<1, 32, 0, stream>>>(class_cnt, class_off);

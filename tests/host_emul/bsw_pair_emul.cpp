@@ -4,6 +4,11 @@
 #include <vector>
 #include <cstdint>
 #include <cstring>
+static std::vector<int> *g_trace = nullptr;       // optional: the three column segments of every row (for lane-utilisation studies)
+static inline void pair_trace(int a, int b, int c, int d, int e, int f) {
+    if (g_trace) { int v[6] = {a, b, c, d, e, f}; g_trace->insert(g_trace->end(), v, v + 6); }
+}
+#define BM2_PAIR_TRACE pair_trace
 #include "bsw_pair.cuh"
 
 struct HostPairMem {
@@ -17,9 +22,23 @@ struct HostPairMem {
 
 // jobs 2k and 2k+1 of the given order share a thread; out = 6 ints per job; returns the number of DP cells.
 // eligible[i] == 0 jobs must not be passed.  Sequences: query[qoff + k], target[toff + k] (stride +1).
+// per thread (pair) k: trace_off[k]..trace_off[k+1] rows of 6 ints in trace (call with out_trace = null to skip)
+extern "C" long long pair_extend_trace(int n, const int64_t *qoff, const int64_t *toff, const int32_t *qlen, const int32_t *tlen,
+                                       const int32_t *h0, const uint8_t *qbuf, const uint8_t *tbuf, const int32_t *prm, int32_t *out,
+                                       int32_t *trace, long long trace_cap, int64_t *trace_off);
+
 extern "C" long long pair_extend_all(int n, const int64_t *qoff, const int64_t *toff, const int32_t *qlen, const int32_t *tlen,
                                      const int32_t *h0, const uint8_t *qbuf, const uint8_t *tbuf, const int32_t *prm /*9*/, int32_t *out)
 {
+    return pair_extend_trace(n, qoff, toff, qlen, tlen, h0, qbuf, tbuf, prm, out, nullptr, 0, nullptr);
+}
+
+extern "C" long long pair_extend_trace(int n, const int64_t *qoff, const int64_t *toff, const int32_t *qlen, const int32_t *tlen,
+                                       const int32_t *h0, const uint8_t *qbuf, const uint8_t *tbuf, const int32_t *prm, int32_t *out,
+                                       int32_t *trace, long long trace_cap, int64_t *trace_off)
+{
+    std::vector<int> tr;
+    g_trace = trace ? &tr : nullptr;
     BswParams p; p.a = prm[0]; p.b = prm[1]; p.o_del = prm[2]; p.e_del = prm[3]; p.o_ins = prm[4]; p.e_ins = prm[5];
     p.zdrop = prm[6]; p.end_bonus = prm[7]; p.w = prm[8];
     if (!p2_params_ok(p)) return -1;
@@ -38,11 +57,15 @@ extern "C" long long pair_extend_all(int n, const int64_t *qoff, const int64_t *
         }
         HostPairMem mem{state.data(), sel.data()};
         BswOut o[2];
+        if (trace_off) trace_off[k / 2] = (int64_t) tr.size() / 6;
         bsw_pair_extend(mem, tbuf + toff[k], 1, tbuf + (nj == 2 ? toff[k + 1] : toff[k]), 1, ql, tl, hh, nj, p, o, cells);
         for (int l = 0; l < nj; ++l) {
             int32_t *d = out + 6 * (size_t) (k + l);
             d[0] = o[l].score; d[1] = o[l].tle; d[2] = o[l].gtle; d[3] = o[l].qle; d[4] = o[l].gscore; d[5] = o[l].max_off;
         }
     }
+    if (trace_off) trace_off[(n + 1) / 2] = (int64_t) tr.size() / 6;
+    if (trace) { if ((long long) tr.size() > trace_cap) return -2; memcpy(trace, tr.data(), tr.size() * sizeof(int)); }
+    g_trace = nullptr;
     return (long long) cells;
 }

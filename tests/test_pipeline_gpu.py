@@ -59,6 +59,14 @@ def test_regs_match_reference(c0):
     assert "smem" in ms and "bsw_left" in ms
 
 
+def test_regs_match_reference_with_pair_bsw_kernel(c0, monkeypatch):
+    # same batch with the experimental two-jobs-per-thread extension kernel routed in (off by default)
+    monkeypatch.setenv("BM2_BSW_PAIR", "1")
+    idx, ctx, codes, offs, st = c0
+    regs, ro = ctx.seed_chain_extend(codes, offs)
+    assert ol.regs_equal_to_dump(regs, ro, st["regs"], st["reg_off"]) == []
+
+
 def test_ragged_and_degenerate_reads(pkg, c0):
     idx, ctx, codes, offs, st = c0
     reads = codes.reshape(-1, 151)
