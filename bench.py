@@ -152,6 +152,7 @@ def run_bsw(args, rank, world):
     ctx = capi.Context(dev)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
+    ctx.set_sub_batches(args.sub_batches)
     int_gops = ctx.int_pipe_gops()
     d_pairs = torch.from_numpy(pairs.view(np.uint8).reshape(-1)).cuda()
     d_ref = torch.from_numpy(ref).cuda(); d_qer = torch.from_numpy(qer).cuda()
@@ -349,6 +350,19 @@ def run_pipeline(args, rank, world):
         t = torch.tensor([ms_step], device="cuda"); torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms_step = float(t.item())
     value = world * n / (ms_step * 1e-3)
+    # the stages alone: one more pass of the same batch UNSPLIT, so that every kernel is timed without another sub-batch's
+    # kernels beside it (the roofline figures below; the timed steps above run args.sub_batches sub-batches in flight,
+    # whose per-stage times are sums over sub-batches and overlap each other)
+    stage_split = dict(stage_acc)
+    if args.sub_batches > 1:
+        ctx.set_sub_batches(1)
+        flush.fill_(1)
+        ctx.seed_chain_extend_resident(codes, offs, d_codes.data_ptr(), d_offs.data_ptr(), False)     # buffers of the unsplit path
+        flush.fill_(1)
+        ctx.seed_chain_extend_resident(codes, offs, d_codes.data_ptr(), d_offs.data_ptr(), False)
+        torch.cuda.synchronize()
+        stage_acc = dict(ctx.stage_ms()); cnt = ctx.counters()
+        ctx.set_sub_batches(args.sub_batches)
     # e2e through the host C ABI (pinned host reads in, regs out to pinned host memory)
     ctx.set_stream(None)
     h_codes = torch.from_numpy(codes.copy()).pin_memory(); h_offs = torch.from_numpy(offs.copy()).pin_memory()
@@ -384,23 +398,28 @@ def run_pipeline(args, rank, world):
                                       f"1% garbage) vs {args.ref_mbp} Mbp synthetic reference (planted repeat families; index files "
                                       f"{index_how})",
                           "l2": "256 MB flush between steps; FM-index %d MB" % (index.desc.reference_seq_len // 64 * 64 // 1_000_000),
+                          "sub_batches_in_flight": args.sub_batches,
                           "regs_per_step": int(n_regs)},
                "e2e": {"value": world * n / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(codes.nbytes + offs.nbytes),
                        "d2h_bytes_per_step": int(n_out * capi.REG_DT.itemsize + offs.nbytes)},
-               "gpu_launches": 62 * args.steps,      # our own kernels per step (profiles/r1h_kernel_traffic_3gbp.md; cub sort/scan kernels not counted)
+               # our own kernels per step and sub-batch (profiles/r1h_kernel_traffic_3gbp.md; cub sort/scan kernels not counted)
+               "gpu_launches": 62 * args.steps * max(1, args.sub_batches),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                             "traffic": _smem_traffic(args),
                             "kernel": "SMEM stage: smem_fwd1_kernel + smem_bwd_kernel + smem_fwd2_kernel + smem_bwd_kernel (+ smem_pass3_kernel on a side stream)",
                             "note": "algorithmic bytes = 128 B (two 64-B Occ checkpoints) x interval extensions counted by the kernels; peak = "
                                     + ("MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback of B200_PROFILING.md")
                                     + "; traffic = DRAM read+write bytes of those kernels per step from profiles/ (ncu), null when the workload differs",
-                            "extensions_per_read": cnt["n_ext"] / n, "kernel_ms": smem_ms},
+                            "extensions_per_read": cnt["n_ext"] / n, "kernel_ms": smem_ms,
+                            "timed": "one extra pass of the same batch, unsplit (stage timed alone, CUDA events inside the library)" if args.sub_batches > 1
+                                     else "timed steps"},
                "roofline_bsw": {"bound": "int-alu", "achieved": cnt["cells"] / (bsw_ms * 1e-3) / 1e9 if bsw_ms > 0 else None,
                                 "peak": int_gops / 14.0, "unit": "Gcell/s",
                                 "frac": (cnt["cells"] / (bsw_ms * 1e-3) / 1e9) / (int_gops / 14.0) if bsw_ms > 0 else None,
                                 "note": f"banded DP cells counted by the kernels / (bsw_left + bsw_right stage time); peak = {int_gops:.0f} G two-input "
                                         "int32 op/s measured in-library (bm2_int_pipe_gops) / 14 ops per cell (SURVEY 8d)"},
                "stages_ms": {k: round(v, 3) for k, v in stage_acc.items()},
+               "stages_ms_sum_over_sub_batches_in_timed_steps": {k: round(v, 3) for k, v in stage_split.items()},
                "bsw": {"gcups": cnt["cells"] / (bsw_ms * 1e-3) / 1e9 if bsw_ms > 0 else None, "cells_per_step": int(cnt["cells"]),
                        "retry_left": int(cnt["retry_left"]), "retry_right": int(cnt["retry_right"])},
                "cpu_baseline": {"value": cpu_v, "unit": "reads/s", "cores": nt, "kind": "reference",
@@ -465,6 +484,7 @@ def main():
     ap.add_argument("--ref-mbp", type=int, default=3000)
     ap.add_argument("--pairs", type=int, default=500_000)
     ap.add_argument("--bsw-jobs", type=int, default=4_000_000)
+    ap.add_argument("--sub-batches", type=int, default=4, help="sub-batches in flight per GPU (bm2_set_sub_batches); 1 = unsplit")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

@@ -55,7 +55,7 @@ class RegResult(C.Structure):
     _fields_ = [("n", C.c_int64), ("regs", C.c_void_p), ("read_off", C.c_void_p)]
 
 
-EXPORTS = ["bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
+EXPORTS = ["bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
            "bm2_last_error", "bm2_extend_pairs", "bm2_extend_pairs_device", "bm2_collect_smems", "bm2_seed_chain",
            "bm2_seed_chain_extend", "bm2_last_stage_ms"]
 
@@ -196,19 +196,29 @@ class Context:
         lib().bm2_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         self._check(lib().bm2_set_stream(self._ctx, cuda_stream_handle), "bm2_set_stream")
 
+    def set_sub_batches(self, k: int, min_reads: int = 16384):
+        """Seam 2 runs a batch as k sub-batches in flight (bm2_set_sub_batches); k = 1 turns the split off."""
+        lib().bm2_set_sub_batches.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self._check(lib().bm2_set_sub_batches(self._ctx, int(k), int(min_reads)), "bm2_set_sub_batches")
+
     def int_pipe_gops(self) -> float:
         v = C.c_double()
         lib().bm2_int_pipe_gops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         self._check(lib().bm2_int_pipe_gops(self._ctx, C.byref(v)), "bm2_int_pipe_gops")
         return v.value
 
-    def seed_chain_extend_resident(self, codes, offsets, d_codes_ptr, d_offsets_ptr, copy_out=False):
+    def seed_chain_extend_resident(self, codes, offsets, d_codes_ptr, d_offsets_ptr, copy_out=False, return_arrays=False):
         rb, keep = self._batch(codes, offsets)
         res = RegResult()
         lib().bm2_seed_chain_extend_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         self._check(lib().bm2_seed_chain_extend_resident(self._ctx, C.byref(rb), d_codes_ptr, d_offsets_ptr, int(copy_out), C.byref(res)),
                     "bm2_seed_chain_extend_resident")
-        return res.n
+        if not return_arrays:
+            return res.n
+        n = res.n
+        regs = np.ctypeslib.as_array(C.cast(res.regs, C.POINTER(C.c_uint8)), shape=(n * REG_DT.itemsize,)).view(REG_DT).copy() if n else np.zeros(0, REG_DT)
+        off = np.ctypeslib.as_array(C.cast(res.read_off, C.POINTER(C.c_int64)), shape=(rb.n_reads + 1,)).copy()
+        return regs, off
 
     def counters(self):
         v = (C.c_ulonglong * 5)()

@@ -39,6 +39,11 @@ struct bm2_ctx {
     std::vector<const char *> stage_names;
     std::vector<float> stage_ms;
     unsigned long long last_n_ext = 0, last_n_lf = 0, last_cells = 0, last_n_retry[2] = {0, 0};
+    // seam 2 sub-batches in flight (pipeline.cu run_regs): child contexts with their own streams, events and scratch;
+    // they share this context's index (their idx_allocs stay empty)
+    int n_lanes = 4, lane_min_reads = 16384;
+    std::vector<bm2_ctx *> lanes;
+    cudaEvent_t ev_entry = nullptr;
 
     int ensure(DevBuf &b, size_t bytes);
     int ensure_host(HostBuf &b, size_t bytes);

@@ -2,6 +2,7 @@
 // host side of seam 1 (bm2_extend_pairs).  Seam 2 lives in pipeline.cu.
 #include "bm2_common.cuh"
 #include "bm2_ctx.h"
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include <mutex>
@@ -108,6 +109,7 @@ extern "C" int bm2_create(bm2_ctx **out, int device, const bm2_index_desc *idx, 
     ctx->device = device;
     ctx->n_sm = prop.multiProcessorCount;
     if (opt) ctx->opt = *opt; else bm2_opt_init(&ctx->opt);
+    if (const char *e = getenv("BM2_SUB_BATCHES")) { int k = atoi(e); if (k >= 1 && k <= 16) ctx->n_lanes = k; }
     ctx_for_error = ctx;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         bm2_set_error(nullptr, "bm2_create: cudaStreamCreate failed"); delete ctx; return 1;
@@ -125,10 +127,37 @@ extern "C" int bm2_create(bm2_ctx **out, int device, const bm2_index_desc *idx, 
     return 0;
 }
 
+// A lane: a child context for one sub-batch in flight (own streams, events and scratch; the parent's index by reference).
+bm2_ctx *bm2_make_lane(bm2_ctx *parent) {
+    bm2_ctx *c = new bm2_ctx();
+    c->device = parent->device; c->n_sm = parent->n_sm; c->opt = parent->opt;
+    c->idx = parent->idx;                      // device pointers only; idx_allocs stays empty: the parent owns the memory
+    c->n_lanes = 1;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        bm2_set_error(parent, "sub-batch lane: stream/event creation failed");
+        bm2_destroy(c);
+        return nullptr;
+    }
+    c->stream = c->own_stream;
+    return c;
+}
+
+extern "C" int bm2_set_sub_batches(bm2_ctx *ctx, int k, int min_reads) {
+    if (!ctx || k < 1 || k > 16 || min_reads < 512) { if (ctx) bm2_set_error(ctx, "bm2_set_sub_batches: k in 1..16, min_reads >= 512"); return 1; }
+    ctx->n_lanes = k; ctx->lane_min_reads = min_reads;
+    return 0;
+}
+
 extern "C" void bm2_destroy(bm2_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (bm2_ctx *l : ctx->lanes) bm2_destroy(l);
+    ctx->lanes.clear();
+    if (ctx->ev_entry) cudaEventDestroy(ctx->ev_entry);
     bm2_free_index(ctx);
     for (DevBuf *b : ctx->all_dev()) if (b->p) cudaFree(b->p);
     for (HostBuf *b : ctx->all_host()) if (b->p) cudaFreeHost(b->p);

@@ -24,6 +24,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <vector>
+#include <thread>
+#include <string>
 #include <cstring>
 #include <cmath>
 
@@ -680,17 +682,24 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     const int64_t total = rb->offsets[n];
     int max_len = 1;
     bool any_flt = false;
-    std::vector<int32_t> min_hsp_host((size_t) n);
-    for (int r = 0; r < n; ++r) {
-        int64_t l = rb->offsets[r + 1] - rb->offsets[r];
-        if (l < 0 || l > 32767) { bm2_set_error(ctx, "read length out of range (0..32767)"); return 1; }
-        if (l > max_len) max_len = (int) l;
+    std::vector<int32_t> min_hsp_host;
+    {
         // mem_flt_chained_seeds (src/bwamem.cpp:472-504) applies to reads with min_l <= 0.05 * l (>= 725 bp by default):
-        // min_HSP_score is computed here with the reference's double arithmetic (log() on the host)
-        const double min_l = ctx->opt.min_chain_weight ? 1.1f * ctx->opt.min_chain_weight : 5.5f * log((double) (l > 0 ? l : 1));
-        int hsp = -1;
-        if (l > 0 && !(min_l > 0.05f * l)) { hsp = (int) (ctx->opt.a * min_l + .499); any_flt = true; }
-        min_hsp_host[r] = hsp;
+        // min_HSP_score is computed here with the reference's double arithmetic (log() on the host), once per distinct
+        // consecutive length (a batch of equal-length reads costs one log(), not a million)
+        int64_t memo_l = -1; int memo_hsp = -1;
+        for (int r = 0; r < n; ++r) {
+            const int64_t l = rb->offsets[r + 1] - rb->offsets[r];
+            if (l < 0 || l > 32767) { bm2_set_error(ctx, "read length out of range (0..32767)"); return 1; }
+            if (l > max_len) max_len = (int) l;
+            if (l != memo_l) {
+                const double min_l = ctx->opt.min_chain_weight ? 1.1f * ctx->opt.min_chain_weight : 5.5f * log((double) (l > 0 ? l : 1));
+                memo_l = l; memo_hsp = -1;
+                if (l > 0 && !(min_l > 0.05f * l)) memo_hsp = (int) (ctx->opt.a * min_l + .499);
+            }
+            if (memo_hsp >= 0 && !any_flt) { any_flt = true; min_hsp_host.assign((size_t) n, -1); }
+            if (any_flt) min_hsp_host[r] = memo_hsp;
+        }
     }
     bs.max_len = max_len;
     Params pv = make_params(ctx);
@@ -699,11 +708,15 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
 
     if (ctx->ensure(ctx->d[B_CNT], sizeof(Counters))) return 1;
     const uint8_t *d_codes = ext_codes; const int64_t *d_offs = ext_offs;
-    if (!ext_codes || !ext_offs) {
-        if (ctx->ensure(ctx->d[B_CODES], (size_t) total + 16) || ctx->ensure(ctx->d[B_OFFS], (size_t) (n + 1) * 8)) return 1;
+    if (!ext_codes) {
+        if (ctx->ensure(ctx->d[B_CODES], (size_t) total + 16)) return 1;
         BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[B_CODES].p, rb->codes, (size_t) total, cudaMemcpyHostToDevice, st));
+        d_codes = P<uint8_t>(ctx, B_CODES);
+    }
+    if (!ext_offs) {     // (a sub-batch of a device-resident batch brings its codes pointer but re-based offsets from the host)
+        if (ctx->ensure(ctx->d[B_OFFS], (size_t) (n + 1) * 8)) return 1;
         BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[B_OFFS].p, rb->offsets, (size_t) (n + 1) * 8, cudaMemcpyHostToDevice, st));
-        d_codes = P<uint8_t>(ctx, B_CODES); d_offs = P<int64_t>(ctx, B_OFFS);
+        d_offs = P<int64_t>(ctx, B_OFFS);
     }
     if (any_flt) {
         if (ctx->ensure(ctx->d[B_MINHSP], (size_t) n * 4)) return 1;
@@ -963,7 +976,7 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     ctx->last_cells = h_cnt.cells;
     const int64_t n_out = ((const int64_t *) ctx->h[H_OUT_OFF].p)[n];
     bs.n_out = n_out;
-    if (ctx->ensure_host(ctx->h[H_OUT_REGS], (size_t) (n_out + 1) * sizeof(bm2_alnreg_t))) return 1;
+    if (copy_out && ctx->ensure_host(ctx->h[H_OUT_REGS], (size_t) (n_out + 1) * sizeof(bm2_alnreg_t))) return 1;
     if (n_out && copy_out) BM2_CUDA_OK(cudaMemcpyAsync(ctx->h[H_OUT_REGS].p, ctx->d[B_OUT].p, (size_t) n_out * sizeof(bm2_alnreg_t), cudaMemcpyDeviceToHost, st));
     if (sg.mark("end")) return 1;
     BM2_CUDA_OK(cudaStreamSynchronize(st));
@@ -1023,27 +1036,108 @@ extern "C" int bm2_seed_chain(bm2_ctx *ctx, const bm2_read_batch *reads, bm2_cha
     return 0;
 }
 
+bm2_ctx *bm2_make_lane(bm2_ctx *parent);   // capi.cu
+
+// mem_kernel1_core + mem_kernel2_core of one batch, as up to n_lanes sub-batches in flight (bm2_set_sub_batches).
+// d_codes / d_offs: device-resident inputs (may be null: host inputs are uploaded); results into the context's pinned buffers.
+static int run_regs(bm2_ctx *ctx, const bm2_read_batch *rb, const uint8_t *d_codes, const int64_t *d_offs, bool copy_out, bm2_reg_result *out)
+{
+    bm2_ctx *ctx_for_error = ctx;
+    const int n = rb->n_reads;
+    int K = ctx->n_lanes;
+    if (K > 1 && (int64_t) n < (int64_t) K * ctx->lane_min_reads) K = n / ctx->lane_min_reads;
+    if (K <= 1) {
+        BatchState bs;
+        if (run_pipeline(ctx, rb, UPTO_REGS, bs, d_codes, d_offs, copy_out)) return 1;
+        finish_stage_times(ctx);
+        if (bs.n <= 0) {
+            if (ctx->ensure_host(ctx->h[H_OUT_OFF], 16) || ctx->ensure_host(ctx->h[H_OUT_REGS], sizeof(bm2_alnreg_t))) return 1;
+            ((int64_t *) ctx->h[H_OUT_OFF].p)[0] = 0;
+        }
+        out->n = bs.n_out; out->regs = copy_out ? (const bm2_alnreg_t *) ctx->h[H_OUT_REGS].p : nullptr; out->read_off = (const int64_t *) ctx->h[H_OUT_OFF].p;
+        return 0;
+    }
+    BM2_CUDA_OK(cudaSetDevice(ctx->device));
+    while ((int) ctx->lanes.size() < K) {
+        bm2_ctx *l = bm2_make_lane(ctx);
+        if (!l) return 1;
+        ctx->lanes.push_back(l);
+    }
+    if (!ctx->ev_entry) BM2_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_entry, cudaEventDisableTiming));
+    // the sub-batches start after whatever the caller queued on the context's stream (its inputs, its start event)
+    BM2_CUDA_OK(cudaEventRecord(ctx->ev_entry, ctx->stream));
+    struct Job { int first = 0, n = 0; std::vector<int64_t> offs; bm2_read_batch rb; BatchState bs; int rc = 0; };
+    std::vector<Job> jobs((size_t) K);
+    for (int k = 0; k < K; ++k) {
+        Job &j = jobs[k];
+        j.first = (int) (((int64_t) n * k / K) / 512 * 512);
+        const int next = k + 1 < K ? (int) (((int64_t) n * (k + 1) / K) / 512 * 512) : n;
+        j.n = next - j.first;
+        bm2_ctx *l = ctx->lanes[k];
+        l->opt = ctx->opt;
+        BM2_CUDA_OK(cudaStreamWaitEvent(l->stream, ctx->ev_entry, 0));
+    }
+    auto work = [&](int k) {
+        Job &j = jobs[k];
+        bm2_ctx *l = ctx->lanes[k];
+        const int64_t base = rb->offsets[j.first];
+        j.offs.resize((size_t) j.n + 1);
+        for (int i = 0; i <= j.n; ++i) j.offs[i] = rb->offsets[j.first + i] - base;
+        j.rb.n_reads = j.n; j.rb.codes = rb->codes ? rb->codes + base : nullptr; j.rb.offsets = j.offs.data();
+        // (the device offsets of a resident batch mirror the host offsets: the sub-batch's codes start at `base`)
+        j.rc = run_pipeline(l, &j.rb, UPTO_REGS, j.bs, d_codes ? d_codes + base : nullptr, nullptr, false);
+        if (!j.rc) finish_stage_times(l);
+    };
+    {
+        std::vector<std::thread> th;
+        for (int k = 1; k < K; ++k) th.emplace_back(work, k);
+        work(0);
+        for (auto &t : th) t.join();
+    }
+    for (int k = 0; k < K; ++k)
+        if (jobs[k].rc) { bm2_set_error(ctx, "sub-batch " + std::to_string(k) + ": " + ctx->lanes[k]->err); return 1; }
+    // gather: per-read offsets on the host, regs device -> the context's pinned buffer, one copy per lane on its own stream
+    int64_t n_out = 0;
+    for (int k = 0; k < K; ++k) n_out += jobs[k].bs.n_out;
+    if (ctx->ensure_host(ctx->h[H_OUT_OFF], (size_t) (n + 1) * 8) || ctx->ensure_host(ctx->h[H_OUT_REGS], (size_t) (n_out + 1) * sizeof(bm2_alnreg_t))) return 1;
+    int64_t *off = (int64_t *) ctx->h[H_OUT_OFF].p;
+    bm2_alnreg_t *regs = (bm2_alnreg_t *) ctx->h[H_OUT_REGS].p;
+    int64_t pos = 0;
+    for (int k = 0; k < K; ++k) {
+        const Job &j = jobs[k];
+        bm2_ctx *l = ctx->lanes[k];
+        const int64_t *lo = (const int64_t *) l->h[H_OUT_OFF].p;
+        if (copy_out && j.bs.n_out)
+            BM2_CUDA_OK(cudaMemcpyAsync(regs + pos, l->d[B_OUT].p, (size_t) j.bs.n_out * sizeof(bm2_alnreg_t), cudaMemcpyDeviceToHost, l->stream));
+        for (int i = 0; i < j.n; ++i) off[j.first + i] = lo[i] + pos;
+        pos += j.bs.n_out;
+    }
+    off[n] = n_out;
+    for (int k = 0; k < K; ++k) BM2_CUDA_OK(cudaStreamSynchronize(ctx->lanes[k]->stream));
+    // bookkeeping: stage times are summed over the sub-batches (GPU time per stage; the stages of different
+    // sub-batches overlap, so they no longer add up to the wall time), counters are totals
+    ctx->stage_names = ctx->lanes[0]->stage_names;
+    ctx->stage_ms.assign(ctx->lanes[0]->stage_ms.size(), 0.f);
+    ctx->last_n_ext = ctx->last_n_lf = ctx->last_cells = 0; ctx->last_n_retry[0] = ctx->last_n_retry[1] = 0;
+    for (int k = 0; k < K; ++k) {
+        const bm2_ctx *l = ctx->lanes[k];
+        for (size_t i = 0; i < ctx->stage_ms.size() && i < l->stage_ms.size(); ++i) ctx->stage_ms[i] += l->stage_ms[i];
+        ctx->last_n_ext += l->last_n_ext; ctx->last_n_lf += l->last_n_lf; ctx->last_cells += l->last_cells;
+        ctx->last_n_retry[0] += l->last_n_retry[0]; ctx->last_n_retry[1] += l->last_n_retry[1];
+    }
+    out->n = n_out; out->regs = copy_out ? regs : nullptr; out->read_off = off;
+    return 0;
+}
+
 extern "C" int bm2_seed_chain_extend(bm2_ctx *ctx, const bm2_read_batch *reads, bm2_reg_result *out) {
     if (!ctx || !reads || !out) return 1;
-    BatchState bs;
-    if (run_pipeline(ctx, reads, UPTO_REGS, bs)) return 1;
-    finish_stage_times(ctx);
-    if (bs.n <= 0) {
-        if (ctx->ensure_host(ctx->h[H_OUT_OFF], 16) || ctx->ensure_host(ctx->h[H_OUT_REGS], sizeof(bm2_alnreg_t))) return 1;
-        ((int64_t *) ctx->h[H_OUT_OFF].p)[0] = 0;
-    }
-    out->n = bs.n_out; out->regs = (const bm2_alnreg_t *) ctx->h[H_OUT_REGS].p; out->read_off = (const int64_t *) ctx->h[H_OUT_OFF].p;
-    return 0;
+    return run_regs(ctx, reads, nullptr, nullptr, true, out);
 }
 
 extern "C" int bm2_seed_chain_extend_resident(bm2_ctx *ctx, const bm2_read_batch *reads, const uint8_t *d_codes, const int64_t *d_offsets,
                                               int copy_out, bm2_reg_result *out) {
     if (!ctx || !reads || !out || !d_codes || !d_offsets) return 1;
-    BatchState bs;
-    if (run_pipeline(ctx, reads, UPTO_REGS, bs, d_codes, d_offsets, copy_out != 0)) return 1;
-    finish_stage_times(ctx);
-    out->n = bs.n_out; out->regs = copy_out ? (const bm2_alnreg_t *) ctx->h[H_OUT_REGS].p : nullptr; out->read_off = (const int64_t *) ctx->h[H_OUT_OFF].p;
-    return 0;
+    return run_regs(ctx, reads, d_codes, d_offsets, copy_out != 0, out);
 }
 
 extern "C" int bm2_last_stage_ms(const bm2_ctx *ctx, const char *const **names, const float **ms, int *n) {

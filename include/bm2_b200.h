@@ -95,6 +95,13 @@ const char *bm2_last_error(const bm2_ctx *ctx);   /* ctx may be NULL: last creat
 /* Launch on a caller-owned CUDA stream (cudaStream_t as void*), e.g. the caller's framework stream,
  * so that the caller's events bracket the kernels.  NULL restores the context's own stream. */
 int  bm2_set_stream(bm2_ctx *ctx, void *cuda_stream);
+/* Seam 2 runs a batch as `k` sub-batches in flight (own CUDA streams and scratch, shared index): the SMEM stage is
+ * bound by memory latency and the extension stage by the integer pipe, so sub-batches at different stages fill
+ * each other's stalls (measured +17 % reads/s at k = 4 on B200).  A batch is only split when every sub-batch gets
+ * at least `min_reads` reads; cuts are multiples of 512 reads so that results do not depend on k (the reference's
+ * kt_for works in 512-read blocks, src/kthread.cpp:41-115).  Defaults: k = 4, min_reads = 16384; k = 1 turns it off.
+ * The mem_collect_smem / mem_kernel1_core stage entries (bm2_collect_smems, bm2_seed_chain) always run unsplit. */
+int  bm2_set_sub_batches(bm2_ctx *ctx, int k, int min_reads);
 /* Measured integer-pipe throughput of this device (G lane-ops/s of dependent 32-bit add/max
  * chains over all SMs): the denominator of the BSW cell-update roofline. */
 int  bm2_int_pipe_gops(bm2_ctx *ctx, double *gops_s32);

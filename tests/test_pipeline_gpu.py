@@ -107,4 +107,17 @@ def test_second_dataset_against_oracle(pkg):
     # idempotence: a second call on the same context gives the same bytes
     regs2, ro2 = ctx.seed_chain_extend(codes, offs)
     assert regs.tobytes() == regs2.tobytes() and np.array_equal(ro, ro2)
+    # sub-batches in flight (bm2_set_sub_batches): 6000 reads as 4 / 3 / 11 concurrent sub-batches cut at multiples of 512
+    # reads give the same bytes as the unsplit batch, through the host entry and through the device-resident entry
+    import torch
+    for k in (4, 3, 11):
+        ctx.set_sub_batches(k, 512)
+        regs3, ro3 = ctx.seed_chain_extend(codes, offs)
+        assert regs.tobytes() == regs3.tobytes() and np.array_equal(ro, ro3), k
+    d_codes = torch.from_numpy(codes).cuda(); d_offs = torch.from_numpy(offs).cuda()
+    torch.cuda.synchronize()
+    regs4, ro4 = ctx.seed_chain_extend_resident(codes, offs, d_codes.data_ptr(), d_offs.data_ptr(), True, return_arrays=True)
+    assert regs.tobytes() == regs4.tobytes() and np.array_equal(ro, ro4)
+    assert ctx.counters()["cells"] > 0 and ctx.stage_ms()["smem"] > 0
+    ctx.set_sub_batches(1)
     ctx.close(); idx.close()
