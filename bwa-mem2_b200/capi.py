@@ -55,7 +55,7 @@ class RegResult(C.Structure):
     _fields_ = [("n", C.c_int64), ("regs", C.c_void_p), ("read_off", C.c_void_p)]
 
 
-EXPORTS = ["bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
+EXPORTS = ["bm2_gather64_gbs", "bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
            "bm2_last_error", "bm2_extend_pairs", "bm2_extend_pairs_device", "bm2_collect_smems", "bm2_seed_chain",
            "bm2_seed_chain_extend", "bm2_last_stage_ms"]
 
@@ -195,6 +195,12 @@ class Context:
     def set_stream(self, cuda_stream_handle):
         lib().bm2_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         self._check(lib().bm2_set_stream(self._ctx, cuda_stream_handle), "bm2_set_stream")
+
+    def gather64_gbs(self) -> float:
+        v = C.c_double()
+        lib().bm2_gather64_gbs.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self._check(lib().bm2_gather64_gbs(self._ctx, C.byref(v)), "bm2_gather64_gbs")
+        return v.value
 
     def set_sub_batches(self, k: int, min_reads: int = 16384):
         """Seam 2 runs a batch as k sub-batches in flight (bm2_set_sub_batches); k = 1 turns the split off."""

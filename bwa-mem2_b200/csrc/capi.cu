@@ -292,3 +292,54 @@ extern "C" int bm2_int_pipe_gops(bm2_ctx *ctx, double *gops) {
     *gops = ops / (best * 1e-3) / 1e9;
     return 0;
 }
+
+// ---- random 64-byte gather micro-benchmark over the Occ checkpoint table --------------------------------------------------
+// The SMEM stage reads two random 64-byte checkpoints per interval extension; this measures what the memory system
+// delivers for exactly that access shape when nothing else limits it: every thread keeps `MLP` independent 64-byte
+// (4 x 16 B) loads of pseudo-random checkpoints in flight, no dependent address chain, trivial arithmetic.
+template <int MLP>
+__global__ void __launch_bounds__(256) gather64_kernel(const uint4 *__restrict__ tab, unsigned long long n_entries, int iters, unsigned long long seed,
+                                                       unsigned *out) {
+    unsigned long long x = seed + (unsigned long long) (blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull;
+    unsigned acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        uint4 v[MLP][4];
+#pragma unroll
+        for (int m = 0; m < MLP; ++m) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;                 // xorshift64
+            const unsigned long long e = (unsigned long long) (((unsigned __int128) x * n_entries) >> 64);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[m][q] = __ldg(tab + e * 4 + q);
+        }
+#pragma unroll
+        for (int m = 0; m < MLP; ++m)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc += v[m][q].x ^ v[m][q].y ^ v[m][q].z ^ v[m][q].w;
+    }
+    if (acc == 0x12345678u) out[0] = acc;                            // keeps the loads alive
+}
+
+extern "C" int bm2_gather64_gbs(bm2_ctx *ctx, double *gbs) {
+    bm2_ctx *ctx_for_error = ctx;
+    if (!ctx || !gbs) return 1;
+    if (!ctx->idx.loaded) { bm2_set_error(ctx, "bm2_gather64_gbs needs a context created with an index"); return 1; }
+    BM2_CUDA_OK(cudaSetDevice(ctx->device));
+    const unsigned long long n_entries = (unsigned long long) (ctx->idx.N >> 6) + 1;
+    const int blocks = ctx->n_sm * 8, threads = 256, iters = 64;
+    constexpr int MLP = 4;
+    if (ctx->ensure(ctx->bsw_outs, 256)) return 1;
+    cudaEvent_t e0, e1;
+    BM2_CUDA_OK(cudaEventCreate(&e0)); BM2_CUDA_OK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        BM2_CUDA_OK(cudaEventRecord(e0, ctx->stream));
+        gather64_kernel<MLP><<<blocks, threads, 0, ctx->stream>>>((const uint4 *) ctx->idx.cp_occ, n_entries, iters, 777 + rep, (unsigned *) ctx->bsw_outs.p);
+        BM2_CUDA_OK(cudaEventRecord(e1, ctx->stream));
+        BM2_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0; BM2_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *gbs = (double) blocks * threads * (double) iters * MLP * 64.0 / (best * 1e-3) / 1e9;
+    return 0;
+}

@@ -205,6 +205,9 @@ BM2_HD int global_score_d(int qlen, const uint8_t *qp, int qstride, int tlen, co
 {
     const int MINUS_INF = -0x40000000;
     const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+#if defined(BM2_TRACE_GLOBAL_SCORE) && !defined(__CUDA_ARCH__)
+    BM2_TRACE_GLOBAL_SCORE(qlen, tlen, w);
+#endif
     int32_t *H = he, *E = he + (qlen + 1);
     H[0] = 0; E[0] = MINUS_INF;
     int j;

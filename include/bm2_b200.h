@@ -105,6 +105,10 @@ int  bm2_set_sub_batches(bm2_ctx *ctx, int k, int min_reads);
 /* Measured integer-pipe throughput of this device (G lane-ops/s of dependent 32-bit add/max
  * chains over all SMs): the denominator of the BSW cell-update roofline. */
 int  bm2_int_pipe_gops(bm2_ctx *ctx, double *gops_s32);
+/* Measured throughput (GB/s) of independent random 64-byte reads over this context's Occ checkpoint table: what the
+ * memory system delivers for the SMEM stage's access shape (two random 64-B checkpoints per interval extension) when
+ * no dependent address chain limits it.  Reported next to the HBM copy peak in bench.py. */
+int  bm2_gather64_gbs(bm2_ctx *ctx, double *gbs);
 int  bm2_abi_version(void);
 
 /* ---- seam 1: batched banded-SW seed extension -------------------------------------------------

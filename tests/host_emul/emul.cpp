@@ -6,12 +6,17 @@
 // extension DP itself is NOT emulated here (its CUDA kernel is checked on the GPU by
 // tests/test_bsw_gpu.py); this harness calls the oracle's DP for that step.  Never part of the product.
 #include <vector>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
 #include <cmath>
 #include "fm_device.cuh"
 #include "chain_device.cuh"
+static long long g_gs_calls = 0, g_gs_cells = 0;      // statistics of the score-only global alignment inside the tail
+#define BM2_TRACE_GLOBAL_SCORE(qlen, tlen, w) do { ++g_gs_calls; g_gs_cells += (long long) (tlen) * ((2 * (w) + 1) < (qlen) ? (2 * (w) + 1) : (qlen)); } while (0)
 #include "ext_device.cuh"
 #include "../../oracle/bm2_oracle.h"
 
@@ -199,9 +204,16 @@ int emul_seed_chain_extend(const bm2_index_desc *idx, const bm2_mem_opt_t *o, co
         int nreg = (int) (reg_off[r + 1] - reg_off[r]);
         int l_query = (int) (rb->offsets[r + 1] - rb->offsets[r]);
         if (ce > cb) {
+            g_gs_calls = 0; g_gs_cells = 0;
+            const auto t0 = std::chrono::steady_clock::now();
             ext_postfilter_read_d(v.ep, s2.chains.data() + cb, (int) (ce - cb), s2.seeds.data(), l_query, regs.data() + reg_off[r], nreg,
                                   reg_seed.data() + reg_off[r], srt2.data() + reg_off[r], box.data() + reg_off[r]);
+            const auto t1 = std::chrono::steady_clock::now();
             int m = ext_tail_read_d(v.cv, v.ep, idx->ref_string, rb->codes + rb->offsets[r], regs.data() + reg_off[r], nreg, he.data(), srt2.data() + reg_off[r]);
+            const auto t2 = std::chrono::steady_clock::now();
+            if (getenv("BM2_EMUL_TAIL_STATS") && nreg > 24)
+                fprintf(stderr, "TAILSTAT %d nreg %d final %d pf_us %.1f tail_us %.1f gs_calls %lld gs_cells %lld\n", r, nreg, m,
+                        std::chrono::duration<double, std::micro>(t1 - t0).count(), std::chrono::duration<double, std::micro>(t2 - t1).count(), g_gs_calls, g_gs_cells);
             for (int i = 0; i < m; ++i) out.push_back(regs[reg_off[r] + i]);
         }
         off[r + 1] = (int64_t) out.size();
