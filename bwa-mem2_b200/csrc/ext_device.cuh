@@ -7,6 +7,7 @@
 // mem_patch_reg (:175-234), bwa_gen_cigar2's score path (src/bwa.cpp:260-347) and the score-only
 // ksw_global2 (src/ksw.cpp:558-668).
 #pragma once
+#include <string.h>
 #include "hd.h"
 #include "bm2_b200.h"
 #include "chain_device.cuh"
@@ -34,6 +35,23 @@ BM2_HD int cal_max_gap_d(const ExtParams &p, int qlen) {
 BM2_HD int reg_n_comp_d(const bm2_alnreg_t &a) { return (a.n_comp_is_alt << 2) >> 2; }
 BM2_HD void reg_set_n_comp_d(bm2_alnreg_t &a, int v) { a.n_comp_is_alt = (a.n_comp_is_alt & ~0x3FFFFFFF) | (v & 0x3FFFFFFF); }
 BM2_HD void reg_set_is_alt_d(bm2_alnreg_t &a, int v) { a.n_comp_is_alt = (a.n_comp_is_alt & 0x3FFFFFFF) | ((v & 3) << 30); }
+
+// Whole-record copy as seven 16-byte words: a member-wise struct assignment may skip the padding bytes, which are part of
+// the output (callers compare / checksum records as bytes).  Records are 16-byte aligned (112 = 7 x 16, buffers from cudaMalloc).
+static_assert(sizeof(bm2_alnreg_t) == 112, "bm2_alnreg_t layout");
+BM2_HD void reg_copy(bm2_alnreg_t *dst, const bm2_alnreg_t *src) {
+#if defined(__CUDA_ARCH__)
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    uint4 v[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) v[k] = s4[k];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) d4[k] = v[k];
+#else
+    memcpy(dst, src, sizeof(bm2_alnreg_t));
+#endif
+}
 
 BM2_HD void seedcov_d(bm2_alnreg_t &a, const bm2_seed *seeds, int n) {
     if (a.rb != BM2_H0 && a.qb != BM2_H0 && a.qe != BM2_H0 && a.re != BM2_H0) {
@@ -88,7 +106,7 @@ BM2_HD void ext_build_read_d(const ContigView &cv, const ExtParams &p, const bm2
         for (int k = n - 1; k >= 0; --k) {
             const int si = (int) (uint32_t) srt[k];
             const bm2_seed &s = cs[si];
-            bm2_alnreg_t a;
+            alignas(16) bm2_alnreg_t a = bm2_alnreg_t();   // value-initialised: the padding bytes are part of the output too
             a.rb = a.re = BM2_H0; a.qb = a.qe = BM2_H0; a.rid = c.rid; a.c = 0;
             a.score = a.truesc = -1; a.sub = a.alt_sc = a.csub = a.sub_n = 0; a.w = p.w; a.seedcov = 0;
             a.secondary = a.secondary_all = 0; a.seedlen0 = s.len; a.n_comp_is_alt = 0; a.frac_rep = c.frac_rep; a.hash = 0; a.flg = 0;
@@ -109,7 +127,7 @@ BM2_HD void ext_build_read_d(const ContigView &cv, const ExtParams &p, const bm2
                 a.qe = l_query; a.re = s.rbeg + s.len;
                 seedcov_d(a, cs, n);
             }
-            regs[ai] = a; reg_chain[ai] = (int32_t) (chain_base + ci); reg_seed[ai] = si;
+            reg_copy(&regs[ai], &a); reg_chain[ai] = (int32_t) (chain_base + ci); reg_seed[ai] = si;
             ++n_reg;
         }
     }
@@ -296,13 +314,14 @@ BM2_HD int patch_reg_d(const ContigView &cv, const ExtParams &p, const uint8_t *
 BM2_HD void permute_regs_d(bm2_alnreg_t *a, int32_t *idx, int n) {
     for (int i = 0; i < n; ++i) {
         if (idx[i] < 0 || idx[i] == i) { continue; }
-        bm2_alnreg_t tmp = a[i];
+        alignas(16) bm2_alnreg_t tmp;
+        reg_copy(&tmp, &a[i]);
         int j = i;
         for (;;) {
             const int src = idx[j];
             idx[j] = -1;
-            if (src == i) { a[j] = tmp; break; }
-            a[j] = a[src];
+            if (src == i) { reg_copy(&a[j], &tmp); break; }
+            reg_copy(&a[j], &a[src]);
             j = src;
         }
     }
@@ -351,7 +370,7 @@ BM2_HD int sort_dedup_patch_d(const ContigView &cv, const ExtParams &p, const ui
         }
     }
     for (i = 0, m = 0; i < n; ++i)
-        if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
+        if (a[i].qe > a[i].qb) { if (m != i) reg_copy(&a[m++], &a[i]); else ++m; }
     n = m;
     for (i = 0; i < n; ++i) idx[i] = i;
     {
@@ -365,7 +384,7 @@ BM2_HD int sort_dedup_patch_d(const ContigView &cv, const ExtParams &p, const ui
     for (i = 1; i < n; ++i)
         if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
     for (i = 1, m = 1; i < n; ++i)
-        if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
+        if (a[i].qe > a[i].qb) { if (m != i) reg_copy(&a[m++], &a[i]); else ++m; }
     return m;
 }
 
@@ -376,7 +395,7 @@ BM2_HD int ext_tail_read_d(const ContigView &cv, const ExtParams &p, const uint8
 {
     int m = 0;
     for (int i = 0; i < n_reg; ++i)
-        if (regs[i].qe > regs[i].qb) { if (m != i) regs[m++] = regs[i]; else ++m; }
+        if (regs[i].qe > regs[i].qb) { if (m != i) reg_copy(&regs[m++], &regs[i]); else ++m; }
     m = sort_dedup_patch_d(cv, p, ref, query, m, regs, he, idx);
     for (int i = 0; i < m; ++i)
         if (regs[i].rid >= 0 && cv.ann_alt && cv.ann_alt[regs[i].rid]) reg_set_is_alt_d(regs[i], 1);

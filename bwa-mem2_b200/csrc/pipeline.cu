@@ -27,6 +27,7 @@
 #include <thread>
 #include <string>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 
 static_assert(sizeof(ExtJobRec) == sizeof(BswJob), "ExtJobRec must alias BswJob");
@@ -558,7 +559,7 @@ __global__ void regs_gather_kernel(const bm2_alnreg_t *regs, const int64_t *reg_
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     const int64_t o0 = out_off[r], o1 = out_off[r + 1], g0 = reg_off[r];
-    for (int64_t k = 0; k < o1 - o0; ++k) out[o0 + k] = regs[g0 + k];
+    for (int64_t k = 0; k < o1 - o0; ++k) reg_copy(&out[o0 + k], &regs[g0 + k]);
 }
 
 // reads ordered by decreasing work (heavy reads first, similar reads share a warp)
@@ -1088,7 +1089,9 @@ static int run_regs(bm2_ctx *ctx, const bm2_read_batch *rb, const uint8_t *d_cod
         j.rc = run_pipeline(l, &j.rb, UPTO_REGS, j.bs, d_codes ? d_codes + base : nullptr, nullptr, false);
         if (!j.rc) finish_stage_times(l);
     };
-    {
+    if (getenv("BM2_SUB_BATCHES_SERIAL")) {        // debugging aid: the same split, one sub-batch after the other
+        for (int k = 0; k < K; ++k) work(k);
+    } else {
         std::vector<std::thread> th;
         for (int k = 1; k < K; ++k) th.emplace_back(work, k);
         work(0);
