@@ -318,8 +318,18 @@ def run_pipeline(args, rank, world):
     got, go = ctx.seed_chain_extend(codes[:ns * reads.shape[1]], offs[:ns + 1])
     want, wo, _, rc = ol.seed_chain_extend(index, ctx.opt, codes[:ns * reads.shape[1]], offs[:ns + 1])
     assert rc == 0 and np.array_equal(go, wo) and got.tobytes() == want.tobytes(), "bench workload differs from the oracle"
+    # ... and of the sub-batch path the timed steps use: the same reads split into sub-batches in flight give the same bytes
+    nsb = min(n, 65536)
+    if args.sub_batches > 1 and nsb >= 2 * 16384:
+        ctx.set_sub_batches(1)
+        r_one, o_one = ctx.seed_chain_extend(codes[:nsb * reads.shape[1]], offs[:nsb + 1])
+        ctx.set_sub_batches(args.sub_batches)
+        r_sub, o_sub = ctx.seed_chain_extend(codes[:nsb * reads.shape[1]], offs[:nsb + 1])
+        assert np.array_equal(o_one, o_sub) and r_one.tobytes() == r_sub.tobytes(), "sub-batches in flight differ from the unsplit batch"
+        del r_one, r_sub
     int_gops = ctx.int_pipe_gops()
     gather_gbs = ctx.gather64_gbs()
+    gather_by_span = {f"{mb}MB": round(ctx.gather64_gbs(mb << 20), 1) for mb in (32, 256, 1024, 4096)}
     index_how = "built by the reference binary" if args.ref_mbp <= 400 else "built on the GPU by bwa_mem2_b200.index_build, byte-identical format"
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
@@ -412,7 +422,7 @@ def run_pipeline(args, rank, world):
                                     + ("MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback of B200_PROFILING.md")
                                     + "; traffic = DRAM read+write bytes of those kernels per step from profiles/ (ncu), null when the workload differs",
                             "extensions_per_read": cnt["n_ext"] / n, "kernel_ms": smem_ms,
-                            "random_64B_gather_gbs": gather_gbs, "frac_of_random_gather": achieved / gather_gbs if gather_gbs > 0 else None,
+                            "random_64B_gather_gbs": gather_gbs, "random_64B_gather_gbs_by_span": gather_by_span, "frac_of_random_gather": achieved / gather_gbs if gather_gbs > 0 else None,
                             "timed": "one extra pass of the same batch, unsplit (stage timed alone, CUDA events inside the library)" if args.sub_batches > 1
                                      else "timed steps"},
                "roofline_bsw": {"bound": "int-alu", "achieved": cnt["cells"] / (bsw_ms * 1e-3) / 1e9 if bsw_ms > 0 else None,

@@ -196,10 +196,10 @@ class Context:
         lib().bm2_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         self._check(lib().bm2_set_stream(self._ctx, cuda_stream_handle), "bm2_set_stream")
 
-    def gather64_gbs(self) -> float:
+    def gather64_gbs(self, span_bytes: int = 0) -> float:
         v = C.c_double()
-        lib().bm2_gather64_gbs.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
-        self._check(lib().bm2_gather64_gbs(self._ctx, C.byref(v)), "bm2_gather64_gbs")
+        lib().bm2_gather64_gbs.argtypes = [C.c_void_p, C.c_ulonglong, C.POINTER(C.c_double)]
+        self._check(lib().bm2_gather64_gbs(self._ctx, int(span_bytes), C.byref(v)), "bm2_gather64_gbs")
         return v.value
 
     def set_sub_batches(self, k: int, min_reads: int = 16384):

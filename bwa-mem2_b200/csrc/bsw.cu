@@ -638,6 +638,10 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     }
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    // shared memory the persistent CTAs of one launch may occupy per SM: the rest stays free for the kernels of the other
+    // sub-batches in flight (latency-bound SMEM / chain / tail kernels co-resident with the ALU-bound extension)
+    size_t smem_budget = 227 * 1024;
+    if (const char *e = getenv("BM2_BSW_SMEM_KB")) { int kb = atoi(e); if (kb >= 48 && kb <= 227) smem_budget = (size_t) kb * 1024; }
     for (int c = 0; c < BSW_NCLASS; ++c) {
         const int bound = h_class_bound[c >> 1];
         const int is16 = c & 1;
@@ -649,7 +653,7 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
         while (nthr > 32 && per_thread * nthr > 112 * 1024) nthr >>= 1;
         const size_t smem = per_thread * nthr;
         if (smem > 227 * 1024) { bm2_set_error(ctx_for_error, "bsw: class does not fit shared memory"); return 1; }
-        int ctas_per_sm = (int) ((227 * 1024) / (smem + 1024)); if (ctas_per_sm < 1) ctas_per_sm = 1; if (ctas_per_sm > 16) ctas_per_sm = 16;
+        int ctas_per_sm = (int) (smem_budget / (smem + 1024)); if (ctas_per_sm < 1) ctas_per_sm = 1; if (ctas_per_sm > 16) ctas_per_sm = 16;
         int nblk = (n + nthr - 1) / nthr;
         const int cap_blk = n_sm * ctas_per_sm;
         if (nblk > cap_blk) nblk = cap_blk;

@@ -319,12 +319,13 @@ __global__ void __launch_bounds__(256) gather64_kernel(const uint4 *__restrict__
     if (acc == 0x12345678u) out[0] = acc;                            // keeps the loads alive
 }
 
-extern "C" int bm2_gather64_gbs(bm2_ctx *ctx, double *gbs) {
+extern "C" int bm2_gather64_gbs(bm2_ctx *ctx, unsigned long long span_bytes, double *gbs) {
     bm2_ctx *ctx_for_error = ctx;
     if (!ctx || !gbs) return 1;
     if (!ctx->idx.loaded) { bm2_set_error(ctx, "bm2_gather64_gbs needs a context created with an index"); return 1; }
     BM2_CUDA_OK(cudaSetDevice(ctx->device));
-    const unsigned long long n_entries = (unsigned long long) (ctx->idx.N >> 6) + 1;
+    unsigned long long n_entries = (unsigned long long) (ctx->idx.N >> 6) + 1;
+    if (span_bytes && span_bytes / 64 < n_entries) n_entries = span_bytes / 64 ? span_bytes / 64 : 1;     // only the first span_bytes of the table
     const int blocks = ctx->n_sm * 8, threads = 256, iters = 64;
     constexpr int MLP = 4;
     if (ctx->ensure(ctx->bsw_outs, 256)) return 1;

@@ -110,6 +110,7 @@ BM2_HD void ext_build_read_d(const ContigView &cv, const ExtParams &p, const bm2
             a.rb = a.re = BM2_H0; a.qb = a.qe = BM2_H0; a.rid = c.rid; a.c = 0;
             a.score = a.truesc = -1; a.sub = a.alt_sc = a.csub = a.sub_n = 0; a.w = p.w; a.seedcov = 0;
             a.secondary = a.secondary_all = 0; a.seedlen0 = s.len; a.n_comp_is_alt = 0; a.frac_rep = c.frac_rep; a.hash = 0; a.flg = 0;
+            a.pad0_ = a.pad1_ = a.pad2_ = 0;
             const int ai = n_reg;
             if (s.qbeg) {
                 ExtJobRec j; j.qlen = s.qbeg; j.tlen = (int) (s.rbeg - rmax0); j.toff = s.rbeg - 1; j.qoff = read_code_off + s.qbeg - 1;

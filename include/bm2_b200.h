@@ -105,10 +105,10 @@ int  bm2_set_sub_batches(bm2_ctx *ctx, int k, int min_reads);
 /* Measured integer-pipe throughput of this device (G lane-ops/s of dependent 32-bit add/max
  * chains over all SMs): the denominator of the BSW cell-update roofline. */
 int  bm2_int_pipe_gops(bm2_ctx *ctx, double *gops_s32);
-/* Measured throughput (GB/s) of independent random 64-byte reads over this context's Occ checkpoint table: what the
- * memory system delivers for the SMEM stage's access shape (two random 64-B checkpoints per interval extension) when
- * no dependent address chain limits it.  Reported next to the HBM copy peak in bench.py. */
-int  bm2_gather64_gbs(bm2_ctx *ctx, double *gbs);
+/* Measured throughput (GB/s) of independent random 64-byte reads over the first `span_bytes` (0 = all) of this context's
+ * Occ checkpoint table: what the memory system delivers for the SMEM stage's access shape (two random 64-B checkpoints
+ * per interval extension) when no dependent address chain limits it.  Reported next to the HBM copy peak in bench.py. */
+int  bm2_gather64_gbs(bm2_ctx *ctx, unsigned long long span_bytes, double *gbs);
 int  bm2_abi_version(void);
 
 /* ---- seam 1: batched banded-SW seed extension -------------------------------------------------
@@ -144,12 +144,15 @@ typedef struct bm2_alnreg_t {
     int64_t rb, re;
     int32_t qb, qe;
     int32_t rid;
+    int32_t pad0_;                  /* the compiler's padding of mem_alnreg_t, named so that it is written (0) */
     void   *c;
     int32_t score, truesc, sub, alt_sc, csub, sub_n, w, seedcov, secondary, secondary_all, seedlen0;
     int32_t n_comp_is_alt;          /* bit-field word: n_comp:30, is_alt:2                      */
     float   frac_rep;
+    int32_t pad1_;
     uint64_t hash;
     int32_t flg;
+    int32_t pad2_;
 } bm2_alnreg_t;
 
 /* SMEM record: `SMEM` (src/FMI_search.h:75-83). */
