@@ -15,6 +15,7 @@
 // Integer-ALU bound; HBM traffic is ~(qlen+tlen+56) B per job.
 #include "bm2_common.cuh"
 #include "bsw_pair.cuh"
+#include "bsw_col2.cuh"
 #include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -331,6 +332,74 @@ bsw_thread_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ p
 }
 
 // ---------------------------------------------------------------------------------------------
+// One job per thread, two adjacent columns per packed instruction (bsw_col2.cuh): the 8-bit-score classes with at most
+// 256 query columns, i.e. every job of a 2x151 bp read.  Shared memory: state words {H, E} x 2 columns [pair][thread],
+// then the query as one PRMT selector byte per column, 4 columns per word [word][thread].
+// ---------------------------------------------------------------------------------------------
+template <int NTHR>                     // compile-time strides: the unrolled pair loop addresses columns as [base + immediate]
+struct Col2MemShared {
+    unsigned st_base, q_base;           // shared-window byte addresses of the thread's pair 0 / selector word 0
+    static constexpr unsigned stride = NTHR * 4u;
+    __device__ __forceinline__ uint32_t ldw(int q) const {
+        uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(st_base + (unsigned) q * stride)); return w;
+    }
+    __device__ __forceinline__ void stw(int q, uint32_t w) const {
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(st_base + (unsigned) q * stride), "r"(w) : "memory");
+    }
+    __device__ __forceinline__ uint32_t ldh(int j) const {
+        uint16_t w; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w) : "r"(st_base + (unsigned) (j >> 1) * stride + 2u * (unsigned) (j & 1))); return (uint32_t) w;
+    }
+    __device__ __forceinline__ void sth(int j, uint32_t v) const {
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(st_base + (unsigned) (j >> 1) * stride + 2u * (unsigned) (j & 1)), "h"((uint16_t) v) : "memory");
+    }
+    __device__ __forceinline__ uint32_t qsel(int k) const {
+        uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(q_base + (unsigned) k * stride)); return w;
+    }
+};
+
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR)
+bsw_col2_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ perm, const int32_t *__restrict__ class_off,
+                int cls, BswOut *__restrict__ out, const uint8_t *__restrict__ tbase, const uint8_t *__restrict__ qbase,
+                BswParams p, int NP, unsigned long long *cells)
+{
+    extern __shared__ uint32_t sh[];
+    const int first = class_off[cls], last = class_off[cls + 1];
+    Col2MemShared<NTHR> mem;
+    mem.st_base = (unsigned) __cvta_generic_to_shared(sh) + threadIdx.x * 4u;
+    mem.q_base = mem.st_base + (unsigned) NP * NTHR * 4u;
+    const bool same_oe = p.o_del + p.e_del == p.o_ins + p.e_ins;
+    unsigned long long ncell = 0;
+    for (int blk = blockIdx.x; first + blk * NTHR < last; blk += gridDim.x) {      // persistent CTAs: long jobs first
+        const int g = first + blk * NTHR + threadIdx.x;
+        if (g < last) {
+            const int id = perm[g];
+            const BswJob job = jobs[id];
+            const uint8_t *qp = qbase + job.qoff;
+            for (int k = 0; k < job.qlen; k += 4) {
+                uint32_t wv = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int jj = k + u;
+                    const int b = jj < job.qlen ? (int) qp[(long long) jj * job.qstride] : 4;
+                    wv |= c2_selector_byte(b) << (8 * u);
+                }
+                asm volatile("st.shared.u32 [%0], %1;" :: "r"(mem.q_base + (unsigned) (k >> 2) * (NTHR * 4u)), "r"(wv) : "memory");
+            }
+            BswOut o;
+            if (same_oe) bsw_col2_extend<true>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
+            else bsw_col2_extend<false>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
+            out[id] = o;
+        }
+    }
+    if (cells) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) ncell += __shfl_xor_sync(0xffffffffu, ncell, d);
+        if ((threadIdx.x & 31) == 0 && ncell) atomicAdd(cells, ncell);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Two jobs per thread (bsw_pair.cuh): consecutive jobs of the sorted pair class share a thread, job A in the low
 // halves, job B in the high halves.  Shared memory: packed state {H_A, E_A, H_B, E_B} one word per column
 // [column][thread], then the PRMT selectors of the query pair, 16 bit per column [column][thread].
@@ -630,18 +699,25 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     if (!attr_set) {   // one function, several dynamic sizes: raise the limit once
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BM2_CUDA_OK(cudaFuncSetAttribute(bsw_col2_kernel<BSW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
+    // Two columns of one job per packed instruction (bsw_col2.cuh) for the 8-bit-score classes; BM2_BSW_COL2=0 keeps the
+    // one-cell-per-instruction kernel for them (A/B measurements, tests of both kernels).
+    const char *col2_env = getenv("BM2_BSW_COL2");
+    const int col2_ok = (!(col2_env && col2_env[0] == '0') && c2_params_ok(prm)) ? 1 : 0;
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     // shared memory the persistent CTAs of one launch may occupy per SM: the rest stays free for the kernels of the other
     // sub-batches in flight (latency-bound SMEM / chain / tail kernels co-resident with the ALU-bound extension)
     size_t smem_budget = 227 * 1024;
     if (const char *e = getenv("BM2_BSW_SMEM_KB")) { int kb = atoi(e); if (kb >= 48 && kb <= 227) smem_budget = (size_t) kb * 1024; }
+    int max_ctas = 16;            // ... and a plain cap on its CTAs per SM (warp slots / registers left for the others)
+    if (const char *e = getenv("BM2_BSW_MAX_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 16) max_ctas = v; }
     for (int c = 0; c < BSW_NCLASS; ++c) {
         const int bound = h_class_bound[c >> 1];
         const int is16 = c & 1;
@@ -653,10 +729,19 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
         while (nthr > 32 && per_thread * nthr > 112 * 1024) nthr >>= 1;
         const size_t smem = per_thread * nthr;
         if (smem > 227 * 1024) { bm2_set_error(ctx_for_error, "bsw: class does not fit shared memory"); return 1; }
-        int ctas_per_sm = (int) (smem_budget / (smem + 1024)); if (ctas_per_sm < 1) ctas_per_sm = 1; if (ctas_per_sm > 16) ctas_per_sm = 16;
+        int ctas_per_sm = (int) (smem_budget / (smem + 1024)); if (ctas_per_sm < 1) ctas_per_sm = 1; if (ctas_per_sm > max_ctas) ctas_per_sm = max_ctas;
         int nblk = (n + nthr - 1) / nthr;
         const int cap_blk = n_sm * ctas_per_sm;
         if (nblk > cap_blk) nblk = cap_blk;
+        if (col2_ok && !is16 && bound <= 256) {
+            // two columns per packed instruction (bsw_col2.cuh): state 2 B per column in pair words, selectors 1 B per column
+            const int NP = (W + 1) / 2, NQ = (bound + 3) / 4;
+            const size_t smem2 = (size_t) (NP + NQ) * 4 * BSW_THREADS;
+            int cps = (int) (smem_budget / (smem2 + 1024)); if (cps < 1) cps = 1; if (cps > max_ctas) cps = max_ctas;
+            int nb = (n + BSW_THREADS - 1) / BSW_THREADS; if (nb > n_sm * cps) nb = n_sm * cps;
+            bsw_col2_kernel<BSW_THREADS><<<nb, BSW_THREADS, smem2, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, NP, d_cells);
+            continue;
+        }
         if (is16) bsw_thread_kernel<SmemPacked><<<nblk, nthr, smem, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, W, d_cells);
         else bsw_thread_kernel<SmemPacked8><<<nblk, nthr, smem, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, W, d_cells);
     }

@@ -636,6 +636,14 @@ Params make_params(const bm2_ctx *ctx) {
 
 inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
+// tuning knobs read from the environment at every batch (experiments toggle them between calls of one process)
+inline int env_int(const char *name, int def, int lo, int hi) {
+    const char *e = getenv(name);
+    if (!e || !*e) return def;
+    const int v = atoi(e);
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
 // exclusive scan of n int64 counts into n+1 offsets (last = total)
 int scan64(bm2_ctx *ctx, const int64_t *in, int64_t *out, int64_t n) {
     bm2_ctx *ctx_for_error = ctx;
@@ -730,7 +738,10 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     // ---- A. SMEMs -------------------------------------------------------------------------------------------
     if (sg.mark("smem")) return 1;
     const int stripe = max_len + 2;
-    int blocks_a = (n + 127) / 128; int max_blocks_a = ctx->n_sm * 10;
+    // CTAs per SM the SMEM kernels' grids may occupy (BM2_SMEM_CTAS): fewer leave room for the extension kernels of
+    // the other sub-batches in flight (memory-latency-bound search next to ALU-bound DP on the same SM)
+    const int smem_ctas = env_int("BM2_SMEM_CTAS", 10, 1, 16);
+    int blocks_a = (n + 127) / 128; int max_blocks_a = ctx->n_sm * smem_ctas;
     {   // per-thread forward scratch = stripe * 32 bytes: keep it under ~8 GB for long reads
         const size_t per_block = (size_t) 128 * stripe * sizeof(FmPrev);
         const size_t fit = ((size_t) 8 << 30) / per_block;
@@ -747,7 +758,7 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     unsigned long long rtask_cap = (unsigned long long) n * 8 + 4096;
     const bool q_smem = max_len <= 256;
     const size_t qsm = q_smem ? (size_t) ((max_len + 7) / 8) * 128 * 4 : 0;
-    const int blocks_b = ctx->n_sm * 10;
+    const int blocks_b = ctx->n_sm * smem_ctas;
     for (int attempt = 0; attempt < 3; ++attempt) {
         if (ctx->ensure(ctx->d[B_SMEM_RAW], cap * sizeof(bm2_smem)) || ctx->ensure(ctx->d[B_POOL], pool_cap * sizeof(FmPrev)) ||
             ctx->ensure(ctx->d[B_TASKS], task_cap * sizeof(SearchTask)) || ctx->ensure(ctx->d[B_RTASKS], rtask_cap * sizeof(ReseedTask))) return 1;
@@ -758,7 +769,8 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
         BM2_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
         BM2_CUDA_OK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
         {
-            int blocks_p3 = (n + 127) / 128; if (blocks_p3 > ctx->n_sm * 12) blocks_p3 = ctx->n_sm * 12;
+            const int p3_ctas = env_int("BM2_SMEM_P3_CTAS", smem_ctas + 2, 1, 16);
+            int blocks_p3 = (n + 127) / 128; if (blocks_p3 > ctx->n_sm * p3_ctas) blocks_p3 = ctx->n_sm * p3_ctas;
             if (q_smem) smem_pass3_kernel<true><<<blocks_p3, 128, qsm, ctx->side_stream>>>(pv.fm, pv.sp, d_codes, d_offs, n, d_raw, cap, d_cnt);
             else smem_pass3_kernel<false><<<blocks_p3, 128, 0, ctx->side_stream>>>(pv.fm, pv.sp, d_codes, d_offs, n, d_raw, cap, d_cnt);
             BM2_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->side_stream));

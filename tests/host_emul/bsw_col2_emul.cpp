@@ -1,0 +1,44 @@
+// bsw_col2_emul.cpp — TEST-ONLY host build of the two-columns-per-instruction BSW DP (bwa-mem2_b200/csrc/bsw_col2.cuh,
+// the code bsw_col2_kernel runs per thread) so that it can be checked against the oracle on a machine without a GPU.
+// The packed-halfword instructions are replaced by the portable definitions in bsw_pair.cuh.
+#include <vector>
+#include <cstdint>
+#include <cstring>
+#include "bsw_col2.cuh"
+
+struct HostCol2Mem {
+    uint16_t *state; uint8_t *selb;
+    uint32_t ldw(int p) const { return (uint32_t) state[2 * p] | ((uint32_t) state[2 * p + 1] << 16); }
+    void stw(int p, uint32_t w) const { state[2 * p] = (uint16_t) (w & 0xFFFFu); state[2 * p + 1] = (uint16_t) (w >> 16); }
+    uint32_t ldh(int j) const { return state[j]; }
+    void sth(int j, uint32_t v) const { state[j] = (uint16_t) v; }
+    uint32_t qsel(int k) const { uint32_t w; memcpy(&w, selb + 4 * k, 4); return w; }
+};
+
+// out = 6 ints per job (score, tle, gtle, qle, gscore, max_off); returns the number of DP cells, -1 for unsupported scoring.
+// Sequences: query[qoff + k * qstride], target[toff + k * tstride].
+extern "C" long long col2_extend_all(int n, const int64_t *qoff, const int64_t *toff, const int32_t *qlen, const int32_t *tlen,
+                                     const int32_t *h0, const int32_t *qstride, const int32_t *tstride, const uint8_t *qbuf, const uint8_t *tbuf,
+                                     const int32_t *prm /*9*/, int32_t *out)
+{
+    BswParams p; p.a = prm[0]; p.b = prm[1]; p.o_del = prm[2]; p.e_del = prm[3]; p.o_ins = prm[4]; p.e_ins = prm[5];
+    p.zdrop = prm[6]; p.end_bonus = prm[7]; p.w = prm[8];
+    if (!c2_params_ok(p)) return -1;
+    unsigned long long cells = 0;
+    std::vector<uint16_t> state(264);
+    std::vector<uint8_t> sel(268);
+    for (int k = 0; k < n; ++k) {
+        if (qlen[k] > 256) return -2;
+        // stale garbage on purpose: the kernel's shared memory is not cleared between jobs either
+        for (size_t x = 0; x < state.size(); ++x) state[x] = (uint16_t) (0xA5A5u * (unsigned) (k + 1) + x * 7u);
+        for (size_t x = 0; x < sel.size(); ++x) sel[x] = (uint8_t) c2_selector_byte(4);
+        for (int j = 0; j < qlen[k]; ++j) sel[j] = (uint8_t) c2_selector_byte(qbuf[qoff[k] + (int64_t) j * qstride[k]]);
+        HostCol2Mem mem{state.data(), sel.data()};
+        BswOut o;
+        if (p.o_del + p.e_del == p.o_ins + p.e_ins && !(k & 1)) bsw_col2_extend<true>(mem, tbuf + toff[k], tstride[k], qlen[k], tlen[k], h0[k], p, o, cells);
+        else bsw_col2_extend<false>(mem, tbuf + toff[k], tstride[k], qlen[k], tlen[k], h0[k], p, o, cells);      // (odd jobs: the general form also under equal penalties)
+        int32_t *d = out + 6 * (size_t) k;
+        d[0] = o.score; d[1] = o.tle; d[2] = o.gtle; d[3] = o.qle; d[4] = o.gscore; d[5] = o.max_off;
+    }
+    return (long long) cells;
+}

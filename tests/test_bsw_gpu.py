@@ -9,6 +9,14 @@ pytestmark = pytest.mark.gpu
 OUT = ("score", "tle", "gtle", "qle", "gscore", "max_off")
 
 
+@pytest.fixture(autouse=True, params=["col2", "cell"])
+def bsw_kernel(request, monkeypatch):
+    """Every test runs twice: 8-bit-score jobs on the two-columns-per-instruction kernel (bsw_col2_kernel, the default)
+    and on the one-cell-per-instruction kernel (BM2_BSW_COL2=0); the library reads the variable at every launch."""
+    monkeypatch.setenv("BM2_BSW_COL2", "1" if request.param == "col2" else "0")
+    return request.param
+
+
 def _assert_same(got, want):
     for f in OUT:
         bad = np.nonzero(got[f] != want[f])[0]
@@ -57,6 +65,21 @@ def test_random_low_score_jobs_match_oracle(pkg, gpu_ctx, seed, qmax, tmax, w, m
     _assert_same(p, want)
 
 
+@pytest.mark.parametrize("seed,qmax,tmax,w,nrate,h0max", [(31, 151, 400, 100, 0.05, 100), (32, 256, 500, 100, 0.01, 40), (33, 9, 40, 100, 0.1, 30),
+                                                           (34, 151, 300, 1, 0.01, 60), (35, 130, 400, 40, 0.0, 120)])
+def test_random_8bit_jobs_match_oracle(pkg, gpu_ctx, seed, qmax, tmax, w, nrate, h0max):
+    # the 8-bit-score classes up to 256 columns (bsw_col2_kernel's domain): N-rich queries, tiny jobs, narrow bands
+    rng = np.random.default_rng(seed)
+    n = 5003
+    len1, len2, h0, idr, idq, ref, qer = _random_jobs(rng, n, qmax, tmax, nrate=nrate, h0max=h0max)
+    p = np.zeros(n, pkg.capi.PAIR_DT)
+    p["len1"] = len1; p["len2"] = len2; p["h0"] = h0; p["idr"] = idr; p["idq"] = idq
+    want = p.copy()
+    gpu_ctx.extend_pairs(p, ref, qer, w, 5)
+    ol.extend_pairs(want, ref, qer, w, ol.bsw_params(end_bonus=5))
+    _assert_same(p, want)
+
+
 def test_edge_cases(pkg, gpu_ctx):
     # empty target, single-base query/target, all-N query, h0 near the int16 class limit, >int16 scores (wide path)
     seq = np.array([0, 1, 2, 3] * 64, np.uint8)
@@ -75,16 +98,18 @@ def test_edge_cases(pkg, gpu_ctx):
     assert p["score"][4] == 40200
 
 
-def test_non_default_scoring(pkg, golden_dir):
+@pytest.mark.parametrize("sc", [dict(a=1, b=1, o_del=1, e_del=1, o_ins=1, e_ins=1, zdrop=100),     # -x ont2d scoring
+                                dict(a=2, b=3, o_del=4, e_del=2, o_ins=5, e_ins=1, zdrop=30)])     # o_del+e_del != o_ins+e_ins
+def test_non_default_scoring(pkg, golden_dir, sc):
     o = pkg.capi.default_opt()
-    o.a, o.b, o.o_del, o.e_del, o.o_ins, o.e_ins, o.zdrop = 1, 1, 1, 1, 1, 1, 100   # -x ont2d scoring
+    o.a, o.b, o.o_del, o.e_del, o.o_ins, o.e_ins, o.zdrop = sc["a"], sc["b"], sc["o_del"], sc["e_del"], sc["o_ins"], sc["e_ins"], sc["zdrop"]
     ctx = pkg.capi.Context(0, opt=o)
     rng = np.random.default_rng(11)
-    len1, len2, h0, idr, idq, ref, qer = _random_jobs(rng, 1500, 300, 500, sim=0.85)
+    len1, len2, h0, idr, idq, ref, qer = _random_jobs(rng, 1500, 300, 500, sim=0.85, h0max=60)
     p = np.zeros(1500, pkg.capi.PAIR_DT)
     p["len1"] = len1; p["len2"] = len2; p["h0"] = h0; p["idr"] = idr; p["idq"] = idq
     want = p.copy()
     ctx.extend_pairs(p, ref, qer, 100, 0)
-    ol.extend_pairs(want, ref, qer, 100, ol.bsw_params(a=1, b=1, o_del=1, e_del=1, o_ins=1, e_ins=1, zdrop=100, end_bonus=0))
+    ol.extend_pairs(want, ref, qer, 100, ol.bsw_params(end_bonus=0, **sc))
     _assert_same(p, want)
     ctx.close()

@@ -67,6 +67,14 @@ def test_regs_match_reference_with_pair_bsw_kernel(c0, monkeypatch):
     assert ol.regs_equal_to_dump(regs, ro, st["regs"], st["reg_off"]) == []
 
 
+def test_regs_match_reference_with_cell_bsw_kernel(c0, monkeypatch):
+    # same batch with the one-cell-per-instruction extension kernel for the 8-bit classes (the default is bsw_col2_kernel)
+    monkeypatch.setenv("BM2_BSW_COL2", "0")
+    idx, ctx, codes, offs, st = c0
+    regs, ro = ctx.seed_chain_extend(codes, offs)
+    assert ol.regs_equal_to_dump(regs, ro, st["regs"], st["reg_off"]) == []
+
+
 def test_ragged_and_degenerate_reads(pkg, c0):
     idx, ctx, codes, offs, st = c0
     reads = codes.reshape(-1, 151)
