@@ -6,8 +6,8 @@
 // whose query is at most 256 columns long.  Columns 2p (low half) and 2p+1 (high half) of a row share every packed
 // register.  M, E, and the row maximum are independent per column; only F runs along the row,
 //     F(j+1) = max(F(j) - e_ins, M(j) - oe_ins, 0),
-// and crosses from the low to the high half inside a pair (one PRMT) and from the high half of a pair to the low half
-// of the next (one shift on the FMA pipe).  Both columns belong to the SAME job, so - unlike two jobs per thread
+// and crosses from the low to the high half inside a pair and from the high half of a pair to the low half of the
+// next (shifts written as multiplies: FMA pipe).  Both columns belong to the SAME job, so - unlike two jobs per thread
 // (bsw_pair.cuh) - the band, the exit row and the trip count are shared: the lanes of a warp diverge no more than in
 // the one-cell-per-instruction kernel.  Odd band edges are single cells (at most two per row).
 //
@@ -65,6 +65,7 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
     int best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0;
     int beg = 0, end = qlen;
     unsigned long long ncell = 0;
+    int tb_next = tlen > 0 ? (int) tptr[0] : 0;           // the target base of a row is fetched one row ahead (global-memory latency)
     for (int i = 0; i < tlen; ++i) {
         if (beg < i - w) beg = i - w;
         if (end > i + w + 1) end = i + w + 1;
@@ -72,7 +73,8 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
         int h1;
         if (beg == 0) { h1 = h0 - (p.o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
         else h1 = 0;
-        const int tb = tptr[(long long) i * tstride];
+        const int tb = tb_next;
+        if (i + 1 < tlen) tb_next = (int) tptr[(long long) (i + 1) * tstride];
         const uint32_t tbl = p2_score_table(tb, p.a, p.b);
         int f = 0, key1 = 0;
         uint32_t key2 = 0;

@@ -276,6 +276,9 @@ BM2_HD void fm_backward_rows(const FmIndexView &fm, const Q &q, int x, int min_i
         const int a = q(j);
         if (a > 3) break;
         // phase 1: independent extensions (results overwrite k,l,s in place; m,n of the old entry are still needed)
+#ifdef BM2_TRACE_BWD_ROW
+        BM2_TRACE_BWD_ROW(num_prev);
+#endif
         int b = num_prev;
         const FmPrev first = pv[0];
         for (int p = 0; p < num_prev; ++p) {
