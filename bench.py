@@ -413,8 +413,8 @@ def run_pipeline(args, rank, world):
                           "regs_per_step": int(n_regs)},
                "e2e": {"value": world * n / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(codes.nbytes + offs.nbytes),
                        "d2h_bytes_per_step": int(n_out * capi.REG_DT.itemsize + offs.nbytes)},
-               # our own kernels per step and sub-batch (profiles/r1h_kernel_traffic_3gbp.md; cub sort/scan kernels not counted)
-               "gpu_launches": 62 * args.steps * max(1, args.sub_batches),
+               # our own kernels per step and sub-batch (profiles/r1n_kernel_traffic_3gbp.md: 115 launches, 48 of them cub sort/scan)
+               "gpu_launches": 67 * args.steps * max(1, args.sub_batches),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                             "traffic": _smem_traffic(args),
                             "kernel": "SMEM stage: smem_fwd1_kernel + smem_bwd_kernel + smem_fwd2_kernel + smem_bwd_kernel (+ smem_pass3_kernel on a side stream)",

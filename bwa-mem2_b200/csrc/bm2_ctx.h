@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <string>
 #include <vector>
+#include <mutex>
 #include "bm2_b200.h"
 
 struct DevBuf  { void *p = nullptr; size_t cap = 0; };
@@ -43,6 +44,10 @@ struct bm2_ctx {
     // they share this context's index (their idx_allocs stay empty)
     int n_lanes = 4, lane_min_reads = 16384;
     std::vector<bm2_ctx *> lanes;
+    bm2_ctx *parent = nullptr;                 // set in a lane
+    // stage tokens (held by one lane at a time): the sub-batches take turns in the DRAM-bound SMEM stage and in the
+    // ALU-bound extension stage, so that at any time DIFFERENT kinds of stages overlap instead of four copies of the same
+    std::mutex tok_smem, tok_bsw;
     cudaEvent_t ev_entry = nullptr;
 
     int ensure(DevBuf &b, size_t bytes);

@@ -166,7 +166,8 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
         }
         for (j = beg; j < end && mem.ldh(j) == 0u; ++j) {}
         beg = j;
-        for (j = end; j >= beg && mem.ldh(j) == 0u; --j) {}
+        j = end;                                               // column `end` holds {h1, 0} (written above): no load for the usual case
+        if (h1 == 0) for (--j; j >= beg && mem.ldh(j) == 0u; --j) {}
         end = j + 2 < qlen ? j + 2 : qlen;
     }
     o.score = best; o.qle = best_j + 1; o.tle = best_i + 1; o.gtle = best_ie + 1; o.gscore = gscore; o.max_off = max_off;

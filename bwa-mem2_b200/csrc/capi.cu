@@ -133,6 +133,7 @@ bm2_ctx *bm2_make_lane(bm2_ctx *parent) {
     c->device = parent->device; c->n_sm = parent->n_sm; c->opt = parent->opt;
     c->idx = parent->idx;                      // device pointers only; idx_allocs stays empty: the parent owns the memory
     c->n_lanes = 1;
+    c->parent = parent;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||

@@ -25,10 +25,20 @@ BM2_HD int bns_pos2rid_d(const ContigView &c, int64_t pos_f) {
     }
     return mid;
 }
-BM2_HD int bns_intv2rid_d(const ContigView &c, int64_t rb, int64_t re) {
+// is pos_f (forward-strand coordinate) inside contig rid?  (the answer bns_pos2rid_d would give, without the search)
+BM2_HD bool bns_pos_in_rid_d(const ContigView &c, int64_t pos_f, int rid) {
+    return rid >= 0 && pos_f < c.l_pac && pos_f >= c.ann_off[rid] && (rid == c.n_seqs - 1 || pos_f < c.ann_off[rid + 1]);
+}
+// bns_intv2rid (src/bntseq.cpp:378-402).  *hint: contig of the caller's previous interval (most seeds of a read fall into the
+// same contig), tried before the binary search; the second end is tested against the contig of the first.
+BM2_HD int bns_intv2rid_d(const ContigView &c, int64_t rb, int64_t re, int *hint = nullptr) {
     if (rb < c.l_pac && re > c.l_pac) return -2;
-    int rid_b = bns_pos2rid_d(c, bns_depos_d(c, rb));
-    int rid_e = rb < re ? bns_pos2rid_d(c, bns_depos_d(c, re - 1)) : rid_b;
+    const int64_t pb = bns_depos_d(c, rb);
+    int rid_b = (hint && bns_pos_in_rid_d(c, pb, *hint)) ? *hint : bns_pos2rid_d(c, pb);
+    if (hint && rid_b >= 0) *hint = rid_b;
+    if (!(rb < re)) return rid_b;
+    const int64_t pe = bns_depos_d(c, re - 1);
+    const int rid_e = bns_pos_in_rid_d(c, pe, rid_b) ? rid_b : bns_pos2rid_d(c, pe);
     return rid_b == rid_e ? rid_b : -1;
 }
 
@@ -161,7 +171,7 @@ BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_sm
     l_rep += e - b;
     *frac_rep = (float) l_rep / l_seq;
 
-    int n_ch = 0, n_sd = 0;
+    int n_ch = 0, n_sd = 0, rid_hint = -1;
     int64_t slot = 0;
     for (int i = 0; i < n_smem; ++i) {
         const bm2_smem &sm = smems[i];
@@ -169,7 +179,7 @@ BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_sm
         const int64_t cnt = sm.s < p.max_occ ? sm.s : p.max_occ;
         for (int64_t t = 0; t < cnt; ++t, ++slot) {
             const int64_t rbeg = sa[slot];
-            const int rid = bns_intv2rid_d(cv, rbeg, rbeg + slen);
+            const int rid = bns_intv2rid_d(cv, rbeg, rbeg + slen, &rid_hint);
             if (rid < 0) continue;
             const int sid = n_sd;
             WSeed &s = ws.seeds[sid]; s.rbeg = rbeg; s.qbeg = (int) sm.m; s.len = slen; s.next = -1; s.score = slen;

@@ -331,15 +331,17 @@ BM2_HD void permute_regs_d(bm2_alnreg_t *a, int32_t *idx, int n) {
 // mem_sort_dedup_patch (src/bwamem.cpp:292-353) on the regs of one read; he: 2*(l_query+1) ints; idx: n ints.
 // The two ks_introsort calls run on an index array (same comparisons, same swaps => same permutation as sorting
 // the records) and the records are permuted once.
+// keys: n entries of 16 bytes; the comparators read these compact copies of the sort fields instead of the 112-byte records.
+struct TailSortKey { int64_t r; int32_t score, qb; };
 BM2_HD int sort_dedup_patch_d(const ContigView &cv, const ExtParams &p, const uint8_t *ref, const uint8_t *query, int n,
-                              bm2_alnreg_t *a, int32_t *he, int32_t *idx)
+                              bm2_alnreg_t *a, int32_t *he, int32_t *idx, TailSortKey *keys)
 {
     int m, i, j;
     if (n <= 1) return n;
-    for (i = 0; i < n; ++i) idx[i] = i;
+    for (i = 0; i < n; ++i) { idx[i] = i; keys[i].r = a[i].re; }
     {
-        const bm2_alnreg_t *ra = a;
-        ks_introsort_d(idx, (long) n, [ra](int x, int y) { return ra[x].re < ra[y].re; });
+        const TailSortKey *rk = keys;
+        ks_introsort_d(idx, (long) n, [rk](int x, int y) { return rk[x].r < rk[y].r; });
     }
     permute_regs_d(a, idx, n);
     for (i = 0; i < n; ++i) reg_set_n_comp_d(a[i], 1);
@@ -373,12 +375,12 @@ BM2_HD int sort_dedup_patch_d(const ContigView &cv, const ExtParams &p, const ui
     for (i = 0, m = 0; i < n; ++i)
         if (a[i].qe > a[i].qb) { if (m != i) reg_copy(&a[m++], &a[i]); else ++m; }
     n = m;
-    for (i = 0; i < n; ++i) idx[i] = i;
+    for (i = 0; i < n; ++i) { idx[i] = i; keys[i].r = a[i].rb; keys[i].score = a[i].score; keys[i].qb = a[i].qb; }
     {
-        const bm2_alnreg_t *ra = a;
-        ks_introsort_d(idx, (long) n, [ra](int xi, int yi) {
-            const bm2_alnreg_t &x = ra[xi], &y = ra[yi];
-            return x.score > y.score || (x.score == y.score && (x.rb < y.rb || (x.rb == y.rb && x.qb < y.qb)));
+        const TailSortKey *rk = keys;
+        ks_introsort_d(idx, (long) n, [rk](int xi, int yi) {
+            const TailSortKey x = rk[xi], y = rk[yi];
+            return x.score > y.score || (x.score == y.score && (x.r < y.r || (x.r == y.r && x.qb < y.qb)));
         });
     }
     permute_regs_d(a, idx, n);
@@ -392,12 +394,12 @@ BM2_HD int sort_dedup_patch_d(const ContigView &cv, const ExtParams &p, const ui
 // Tail of mem_kernel2_core for one read (src/bwamem.cpp:1141-1169): drop purged regs, sort/dedup/
 // patch, ALT marking.  Returns the final reg count (regs compacted in place).
 BM2_HD int ext_tail_read_d(const ContigView &cv, const ExtParams &p, const uint8_t *ref, const uint8_t *query, bm2_alnreg_t *regs,
-                           int n_reg, int32_t *he, int32_t *idx)
+                           int n_reg, int32_t *he, int32_t *idx, TailSortKey *keys)
 {
     int m = 0;
     for (int i = 0; i < n_reg; ++i)
         if (regs[i].qe > regs[i].qb) { if (m != i) reg_copy(&regs[m++], &regs[i]); else ++m; }
-    m = sort_dedup_patch_d(cv, p, ref, query, m, regs, he, idx);
+    m = sort_dedup_patch_d(cv, p, ref, query, m, regs, he, idx, keys);
     for (int i = 0; i < m; ++i)
         if (regs[i].rid >= 0 && cv.ann_alt && cv.ann_alt[regs[i].rid]) reg_set_is_alt_d(regs[i], 1);
     return m;

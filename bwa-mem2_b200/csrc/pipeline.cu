@@ -544,11 +544,11 @@ tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const 
             if (mode) {
                 ext_postfilter_read_warp(ep, chains + c0, (int) (c1 - c0), seeds, l_query, regs + g0, n_reg, reg_seed + g0, srt2_all + g0, box_all + g0);
                 __syncwarp();
-                if ((threadIdx.x & 31) == 0) m = ext_tail_read_d(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he, srt2_all + g0);
+                if ((threadIdx.x & 31) == 0) m = ext_tail_read_d(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he, srt2_all + g0, reinterpret_cast<TailSortKey *>(box_all + g0));
                 __syncwarp();
             } else {
                 ext_postfilter_read_d(ep, chains + c0, (int) (c1 - c0), seeds, l_query, regs + g0, n_reg, reg_seed + g0, srt2_all + g0, box_all + g0);
-                m = ext_tail_read_d(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he, srt2_all + g0);
+                m = ext_tail_read_d(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he, srt2_all + g0, reinterpret_cast<TailSortKey *>(box_all + g0));
             }
         }
         if (!mode || (threadIdx.x & 31) == 0) n_final[r] = m;
@@ -675,6 +675,15 @@ int sort_work(bm2_ctx *ctx, uint32_t *keys_in, uint32_t *keys_out, int32_t *vals
 
 enum UpTo { UPTO_SMEM, UPTO_CHAIN, UPTO_REGS };
 
+// A stage token of the parent context, held while a lane's stage is enqueued and until its closing host sync.
+struct StageToken {
+    std::mutex *m;
+    explicit StageToken(std::mutex *mu) : m(mu) { if (m) m->lock(); }
+    ~StageToken() { release(); }
+    void release() { if (m) { m->unlock(); m = nullptr; } }
+    StageToken(const StageToken &) = delete; StageToken &operator=(const StageToken &) = delete;
+};
+
 struct BatchState {       // host-visible sizes of the batch in flight
     int n = 0, max_len = 0; int64_t n_smem = 0, n_slots = 0, n_chains = 0, n_regs = 0, n_left = 0, n_right = 0, n_out = 0;
 };
@@ -759,6 +768,11 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     const bool q_smem = max_len <= 256;
     const size_t qsm = q_smem ? (size_t) ((max_len + 7) / 8) * 128 * 4 : 0;
     const int blocks_b = ctx->n_sm * smem_ctas;
+    // BM2_STAGE_TOKENS: bit 0 = SMEM-stage token, bit 1 = extension-stage token (sub-batch lanes only).  Off by default:
+    // measured SLOWER (149-160 ms against 138 ms per 1 M-read step, profiles/r1o_exp_stage_tokens.log) - taking turns in
+    // a stage leaves the other lanes' host threads waiting at the token instead of queueing work.
+    const int use_tokens = ctx->parent ? env_int("BM2_STAGE_TOKENS", 0, 0, 3) : 0;
+    StageToken tok_smem((use_tokens & 1) ? &ctx->parent->tok_smem : nullptr);
     for (int attempt = 0; attempt < 3; ++attempt) {
         if (ctx->ensure(ctx->d[B_SMEM_RAW], cap * sizeof(bm2_smem)) || ctx->ensure(ctx->d[B_POOL], pool_cap * sizeof(FmPrev)) ||
             ctx->ensure(ctx->d[B_TASKS], task_cap * sizeof(SearchTask)) || ctx->ensure(ctx->d[B_RTASKS], rtask_cap * sizeof(ReseedTask))) return 1;
@@ -794,6 +808,7 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
         if (h_cnt.n_task > task_cap) task_cap = h_cnt.n_task * 2 + 4096;
         if (h_cnt.n_rtask > rtask_cap) rtask_cap = h_cnt.n_rtask * 2 + 4096;
     }
+    tok_smem.release();
     const int64_t n_smem = (int64_t) h_cnt.n_smem;
     bs.n_smem = n_smem;
     ctx->last_n_ext = h_cnt.n_ext;
@@ -937,6 +952,7 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     auto phase = [&](const char *name, ExtJobRec *jobs, int32_t *job_reg, int32_t *retry, int64_t nj, int is_right) -> int {
         if (sg.mark(name)) return 1;
         if (nj <= 0) return 0;
+        StageToken tok_bsw((use_tokens & 2) ? &ctx->parent->tok_bsw : nullptr);
         BswParams bp; bp.a = ctx->opt.a; bp.b = ctx->opt.b; bp.o_del = ctx->opt.o_del; bp.e_del = ctx->opt.e_del; bp.o_ins = ctx->opt.o_ins;
         bp.e_ins = ctx->opt.e_ins; bp.zdrop = ctx->opt.zdrop; bp.end_bonus = is_right ? ctx->opt.pen_clip3 : ctx->opt.pen_clip5; bp.w = ctx->opt.w;
         if (is_right) right_h0_kernel<<<(unsigned) ((nj + 255) / 256), 256, 0, st>>>(jobs, job_reg, (int) nj, d_regs);

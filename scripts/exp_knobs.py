@@ -8,25 +8,30 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package
 
-KNOBS = ("BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS")
+KNOBS = ("BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
 CONFIGS = [
-    dict(name="col2 off, sub 4 (r1l baseline)", sub=4, BM2_BSW_COL2="0"),
-    dict(name="col2 off, sub 1", sub=1, BM2_BSW_COL2="0"),
-    dict(name="col2 on, sub 1", sub=1),
-    dict(name="col2 on, sub 4 (default)", sub=4),
-    dict(name="col2 on, sub 2", sub=2),
-    dict(name="col2 on, sub 8", sub=8),
-    dict(name="col2, sub 4, bsw<=4 ctas, smem 6", sub=4, BM2_BSW_MAX_CTAS="4", BM2_SMEM_CTAS="6"),
-    dict(name="col2, sub 4, bsw<=3 ctas, smem 6", sub=4, BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="6"),
-    dict(name="col2, sub 4, bsw<=4 ctas, smem 4", sub=4, BM2_BSW_MAX_CTAS="4", BM2_SMEM_CTAS="4"),
-    dict(name="col2, sub 4, bsw<=5 ctas, smem 5", sub=4, BM2_BSW_MAX_CTAS="5", BM2_SMEM_CTAS="5"),
-    dict(name="col2, sub 8, bsw<=4 ctas, smem 6", sub=8, BM2_BSW_MAX_CTAS="4", BM2_SMEM_CTAS="6"),
-    dict(name="col2, sub 8, bsw<=3 ctas, smem 5", sub=8, BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5"),
-    dict(name="col2, sub 4, smem 6 only", sub=4, BM2_SMEM_CTAS="6"),
-    dict(name="col2, sub 4, bsw<=4 only", sub=4, BM2_BSW_MAX_CTAS="4"),
-    dict(name="col2, sub 4, smem 14", sub=4, BM2_SMEM_CTAS="14", BM2_SMEM_P3_CTAS="16"),
-    dict(name="col2, sub 1, smem 14", sub=1, BM2_SMEM_CTAS="14", BM2_SMEM_P3_CTAS="16"),
-    dict(name="col2, sub 1, smem 6", sub=1, BM2_SMEM_CTAS="6"),
+    dict(name="default, sub 4", sub=4),
+    dict(name="default, sub 1", sub=1),
+    dict(name="sub 1, smem 3", sub=1, BM2_SMEM_CTAS="3"),
+    dict(name="sub 1, smem 4", sub=1, BM2_SMEM_CTAS="4"),
+    dict(name="sub 1, smem 5", sub=1, BM2_SMEM_CTAS="5"),
+    dict(name="sub 1, smem 6", sub=1, BM2_SMEM_CTAS="6"),
+    dict(name="sub 1, smem 7", sub=1, BM2_SMEM_CTAS="7"),
+    dict(name="sub 1, smem 8", sub=1, BM2_SMEM_CTAS="8"),
+    dict(name="sub 1, smem 6, p3 4", sub=1, BM2_SMEM_CTAS="6", BM2_SMEM_P3_CTAS="4"),
+    dict(name="sub 1, smem 6, p3 12", sub=1, BM2_SMEM_CTAS="6", BM2_SMEM_P3_CTAS="12"),
+    dict(name="sub 1, smem 4, p3 4", sub=1, BM2_SMEM_CTAS="4", BM2_SMEM_P3_CTAS="4"),
+    dict(name="sub 4, smem 2", sub=4, BM2_SMEM_CTAS="2"),
+    dict(name="sub 4, smem 3", sub=4, BM2_SMEM_CTAS="3"),
+    dict(name="sub 4, smem 4", sub=4, BM2_SMEM_CTAS="4"),
+    dict(name="sub 4, smem 3, p3 3", sub=4, BM2_SMEM_CTAS="3", BM2_SMEM_P3_CTAS="3"),
+    dict(name="sub 4, smem 2, p3 2", sub=4, BM2_SMEM_CTAS="2", BM2_SMEM_P3_CTAS="2"),
+    dict(name="sub 4, smem 4, bsw<=4", sub=4, BM2_SMEM_CTAS="4", BM2_BSW_MAX_CTAS="4"),
+    dict(name="sub 4, smem 3, bsw<=4", sub=4, BM2_SMEM_CTAS="3", BM2_BSW_MAX_CTAS="4"),
+    dict(name="sub 3, smem 4", sub=3, BM2_SMEM_CTAS="4"),
+    dict(name="sub 2, smem 5", sub=2, BM2_SMEM_CTAS="5"),
+    dict(name="sub 2, smem 4", sub=2, BM2_SMEM_CTAS="4"),
+    dict(name="default, sub 4 (again)", sub=4),
 ]
 
 
@@ -71,7 +76,7 @@ def main():
     # parity of one knob setting against another on a slice (regs must be byte-identical whatever the knobs)
     ns = 65536
     outs = []
-    for env in (dict(BM2_BSW_COL2="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5")):
+    for env in (dict(BM2_BSW_COL2="0", BM2_STAGE_TOKENS="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5")):
         for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update(env)

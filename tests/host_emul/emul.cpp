@@ -209,7 +209,7 @@ int emul_seed_chain_extend(const bm2_index_desc *idx, const bm2_mem_opt_t *o, co
             ext_postfilter_read_d(v.ep, s2.chains.data() + cb, (int) (ce - cb), s2.seeds.data(), l_query, regs.data() + reg_off[r], nreg,
                                   reg_seed.data() + reg_off[r], srt2.data() + reg_off[r], box.data() + reg_off[r]);
             const auto t1 = std::chrono::steady_clock::now();
-            int m = ext_tail_read_d(v.cv, v.ep, idx->ref_string, rb->codes + rb->offsets[r], regs.data() + reg_off[r], nreg, he.data(), srt2.data() + reg_off[r]);
+            int m = ext_tail_read_d(v.cv, v.ep, idx->ref_string, rb->codes + rb->offsets[r], regs.data() + reg_off[r], nreg, he.data(), srt2.data() + reg_off[r], reinterpret_cast<TailSortKey *>(box.data() + reg_off[r]));
             const auto t2 = std::chrono::steady_clock::now();
             if (getenv("BM2_EMUL_TAIL_STATS") && nreg > 24)
                 fprintf(stderr, "TAILSTAT %d nreg %d final %d pf_us %.1f tail_us %.1f gs_calls %lld gs_cells %lld\n", r, nreg, m,
