@@ -442,6 +442,53 @@ def run_pipeline(args, rank, world):
     return out
 
 
+def run_cigar(args, rank, world):
+    """Seam 3 (the first widening step): CIGAR / NM / MD of the final alignment regions of a slice of the
+    default workload through bm2_gen_cigar (host requests in, host results out), next to the reference's own bwa_gen_cigar2
+    (ref_driver cigar, one host thread) on a sample of the same requests.  Not the headline line: `--workload cigar`."""
+    import torch
+    pkg = load_package(); capi = pkg.capi
+    import oracle_lib as ol, cigar_util as cu
+    dev = int(os.environ.get("LOCAL_RANK", 0)); torch.cuda.set_device(dev)
+    work = os.path.join(tempfile.gettempdir(), f"bm2_bench_pipe_{args.ref_mbp}_{args.pairs}")
+    fa = prepare_pipeline_inputs(work, args.ref_mbp * 1_000_000, args.pairs, seed=21)
+    reads = np.load(os.path.join(work, "reads.npy"))[:min(2 * args.pairs, 200_000)]
+    n, L = reads.shape
+    codes = np.ascontiguousarray(reads.reshape(-1)); offs = np.arange(n + 1, dtype=np.int64) * L
+    index = capi.Index(fa); ctx = capi.Context(dev, index=index)
+    regs, ro = ctx.seed_chain_extend(codes, offs)
+    rd = np.searchsorted(ro, np.arange(len(regs)), side="right") - 1
+    reqs = np.zeros(len(regs), capi.CIGAR_REQ_DT)
+    reqs["rb"] = regs["rb"]; reqs["re"] = regs["re"]; reqs["read"] = rd; reqs["qb"] = regs["qb"]; reqs["qe"] = regs["qe"]
+    reqs["w"] = np.minimum(np.maximum(regs["w"], 1), 4 * ctx.opt.w)
+    ns = min(len(reqs), 20_000)
+    got = ctx.gen_cigar(codes, offs, reqs[:ns]); want = ol.gen_cigar(index, ctx.opt, codes, offs, reqs[:ns])
+    assert want[3] == 0 and cu.same(got, want[:3]) == [], "bm2_gen_cigar differs from the oracle on the bench workload"
+    for _ in range(max(1, args.warmup)):
+        ctx.gen_cigar(codes, offs, reqs)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        recs, ops, md = ctx.gen_cigar(codes, offs, reqs)
+    dt = (time.perf_counter() - t0) / args.steps
+    sample = reqs[:min(len(reqs), 100_000)]
+    t0 = time.perf_counter(); cu.reference_gen_cigar(capi, fa, codes, offs, sample[:1]); t_load = time.perf_counter() - t0     # index load + process start
+    t0 = time.perf_counter(); cu.reference_gen_cigar(capi, fa, codes, offs, sample); t_ref = max(time.perf_counter() - t0 - t_load, 1e-6)
+    out = {"metric": "alignments/s through bwa_gen_cigar2's replacement (CIGAR + NM + MD, seam 3)", "value": len(reqs) / dt, "unit": "alignments/s",
+           "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+           "config": {"workload": f"final alignment regions of {n} reads of the default workload ({len(reqs)} requests per step, {args.ref_mbp} Mbp reference), "
+                                  "host requests in / host CIGAR, NM, MD out (timed end to end, wall clock)",
+                      "mean_ops": float(recs["n_cigar"].mean()), "with_indels": int((recs["n_cigar"] > 1).sum())},
+           "e2e": {"value": len(reqs) / dt, "unit": "alignments/s", "h2d_bytes_per_step": int(codes.nbytes + offs.nbytes + reqs.nbytes),
+                   "d2h_bytes_per_step": int(recs.nbytes + ops.nbytes + md.nbytes)},
+           "gpu_launches": 2 * args.steps,
+           "cpu_baseline": {"value": len(sample) / t_ref, "unit": "alignments/s", "cores": 1, "kind": "reference",
+                            "sample": f"the reference's bwa_gen_cigar2 (ref_driver cigar) on the first {len(sample)} requests, one host thread, index load subtracted"}}
+    ctx.close(); index.close()
+    return out
+
+
 def run_reference_pipeline(args, rank, world):
     if rank != 0:
         return None
@@ -492,7 +539,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="pipeline", choices=["bsw", "pipeline"])
+    ap.add_argument("--workload", default="pipeline", choices=["bsw", "pipeline", "cigar"])
     ap.add_argument("--ref-mbp", type=int, default=3000)
     ap.add_argument("--pairs", type=int, default=500_000)
     ap.add_argument("--bsw-jobs", type=int, default=4_000_000)
@@ -508,7 +555,7 @@ def main():
         import torch, torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         dist.init_process_group("nccl")
-    out = run_pipeline(args, rank, world) if args.workload == "pipeline" else run_bsw(args, rank, world)
+    out = run_pipeline(args, rank, world) if args.workload == "pipeline" else (run_cigar(args, rank, world) if args.workload == "cigar" else run_bsw(args, rank, world))
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

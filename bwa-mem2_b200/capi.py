@@ -38,6 +38,15 @@ class IndexDesc(C.Structure):
                 ("ann_is_alt", C.c_void_p)]
 
 
+# seam 3 (bm2_gen_cigar): request / record layouts of include/bm2_b200.h
+CIGAR_REQ_DT = np.dtype([("rb", "<i8"), ("re", "<i8"), ("read", "<i4"), ("qb", "<i4"), ("qe", "<i4"), ("w", "<i4")])
+CIGAR_REC_DT = np.dtype([("score", "<i4"), ("n_cigar", "<i4"), ("nm", "<i4"), ("n_md", "<i4"), ("cigar_off", "<i8"), ("md_off", "<i8")])
+
+
+class CigarResult(C.Structure):
+    _fields_ = [("n", C.c_int64), ("recs", C.c_void_p), ("n_ops", C.c_int64), ("cigar", C.c_void_p), ("n_md", C.c_int64), ("md", C.c_void_p)]
+
+
 class ReadBatch(C.Structure):
     _fields_ = [("n_reads", C.c_int32), ("codes", C.c_void_p), ("offsets", C.c_void_p)]
 
@@ -57,7 +66,7 @@ class RegResult(C.Structure):
 
 EXPORTS = ["bm2_gather64_gbs", "bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
            "bm2_last_error", "bm2_extend_pairs", "bm2_extend_pairs_device", "bm2_collect_smems", "bm2_seed_chain",
-           "bm2_seed_chain_extend", "bm2_last_stage_ms"]
+           "bm2_seed_chain_extend", "bm2_last_stage_ms", "bm2_gen_cigar"]
 
 _lib = None
 
@@ -191,6 +200,18 @@ class Context:
         regs = np.ctypeslib.as_array(C.cast(res.regs, C.POINTER(C.c_uint8)), shape=(n * REG_DT.itemsize,)).view(REG_DT) if n else np.zeros(0, REG_DT)
         off = np.ctypeslib.as_array(C.cast(res.read_off, C.POINTER(C.c_int64)), shape=(rb.n_reads + 1,))
         return (regs.copy(), off.copy()) if copy else (regs, off)
+
+    def gen_cigar(self, codes, offsets, reqs):
+        """bm2_gen_cigar: reqs is a CIGAR_REQ_DT array -> (recs CIGAR_REC_DT, cigar uint32[], md bytes)."""
+        rb, keep = self._batch(codes, offsets)
+        reqs = np.ascontiguousarray(reqs, CIGAR_REQ_DT)
+        res = CigarResult()
+        lib().bm2_gen_cigar.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        self._check(lib().bm2_gen_cigar(self._ctx, C.byref(rb), reqs.ctypes.data_as(C.c_void_p), len(reqs), C.byref(res)), "bm2_gen_cigar")
+        def arr(p, n, dt):
+            dt = np.dtype(dt)
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * dt.itemsize,)).view(dt).copy() if n else np.zeros(0, dt)
+        return arr(res.recs, res.n, CIGAR_REC_DT), arr(res.cigar, res.n_ops, "<u4"), arr(res.md, res.n_md, "u1")
 
     def set_stream(self, cuda_stream_handle):
         lib().bm2_set_stream.argtypes = [C.c_void_p, C.c_void_p]

@@ -149,6 +149,9 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
         }
         const int m = key1 >> 8, mj = key1 & 0xFF;
         if (end > beg) ncell += (unsigned) (end - beg);
+#ifdef BM2_COL2_TRACE
+        BM2_COL2_TRACE(beg, end);                              // lane-utilisation studies (tests/host_emul/bsw_col2_emul.cpp)
+#endif
         mem.sth(end, (uint32_t) h1);
         if (j == qlen) {
             if (h1 >= gscore) best_ie = i;

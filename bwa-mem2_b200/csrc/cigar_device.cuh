@@ -1,0 +1,177 @@
+// cigar_device.cuh — CIGAR / NM / MD of one alignment whose end points are known (device logic, one alignment per thread).
+//
+// Replaces bwa_gen_cigar2 (reference src/bwa.cpp:260-347) with its banded global alignment + backtrack ksw_global2
+// (src/ksw.cpp:558-668, push_cigar :545-556) as mem_reg2aln calls them (src/bwamem.cpp:1732-1805): SURVEY §8(f) item 2,
+// the first widening step after the seed-chain-extend path.  Same band arithmetic (double), same direction bytes
+// (f << 4 | e << 2 | h), same tie rules, reverse-strand hits aligned on the reversed sequences so that indels are placed
+// leftmost.  Sequences are read through base + k * stride (no reversed copies).
+//
+// Written as BM2_HD: tests/host_emul/cigar_emul.cpp runs the same code on the CPU against the oracle.
+#pragma once
+#include "hd.h"
+#include "chain_device.cuh"       // ContigView
+
+struct CigarParams {
+    int8_t mat[25];
+    int o_del, e_del, o_ins, e_ins;
+};
+
+// Backtrack matrix of one thread: cell c lives at base[c * stride] (stride = threads of the launch: the lanes of a warp
+// touch neighbouring bytes when they are at the same cell index; stride 1 on the host).
+struct CigarZ {
+    uint8_t *base; long long stride;
+    BM2_HD void put(long long c, uint8_t v) const { base[c * stride] = v; }
+    BM2_HD uint8_t get(long long c) const { return base[c * stride]; }
+};
+
+// push_cigar (src/ksw.cpp:545-556) into a caller-provided array
+BM2_HD void cigar_push_d(uint32_t *cigar, int &n, int op, int len) {
+    if (n == 0 || op != (int) (cigar[n - 1] & 0xf)) cigar[n++] = (uint32_t) len << 4 | (uint32_t) op;
+    else cigar[n - 1] += (uint32_t) len << 4;
+}
+
+// ksw_global2 with backtrack (src/ksw.cpp:558-668).  he: 2*(qlen+1) ints; z: n_col*tlen cells, n_col = min(qlen, 2w+1);
+// cigar: room for qlen + tlen + 2 operations.  Returns the score; *n_cigar operations in cigar[].
+BM2_HD int global_align_d(int qlen, const uint8_t *qp, int qstride, int tlen, const uint8_t *tp, int tstride, const int8_t *mat,
+                          int o_del, int e_del, int o_ins, int e_ins, int w, int32_t *he, const CigarZ &z, uint32_t *cigar, int *n_cigar)
+{
+    const int MINUS_INF = -0x40000000;
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+    int32_t *H = he, *E = he + (qlen + 1);
+    H[0] = 0; E[0] = MINUS_INF;
+    int j;
+    for (j = 1; j <= qlen && j <= w; ++j) { H[j] = -(o_ins + e_ins * j); E[j] = MINUS_INF; }
+    for (; j <= qlen; ++j) H[j] = E[j] = MINUS_INF;
+    for (int i = 0; i < tlen; ++i) {
+        int32_t f = MINUS_INF, h1;
+        const int beg = i > w ? i - w : 0;
+        const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+        const int tb = tp[(long long) i * tstride];
+        h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : MINUS_INF;
+        const long long zi = (long long) i * n_col;
+        for (j = beg; j < end; ++j) {
+            int32_t m = H[j], e = E[j];
+            H[j] = h1;
+            m += mat[tb * 5 + qp[(long long) j * qstride]];
+            uint8_t d = m >= e ? 0 : 1;
+            int32_t h = m >= e ? m : e;
+            d = h >= f ? d : 2;
+            h = h >= f ? h : f;
+            h1 = h;
+            int32_t t = m - oe_del;
+            e -= e_del;
+            d |= e > t ? 1 << 2 : 0;
+            e = e > t ? e : t;
+            E[j] = e;
+            t = m - oe_ins;
+            f -= e_ins;
+            d |= f > t ? 2 << 4 : 0;
+            f = f > t ? f : t;
+            z.put(zi + (j - beg), d);
+        }
+        H[end] = h1; E[end] = MINUS_INF;
+    }
+    const int score = H[qlen];
+    // backtrack
+    int n = 0, which = 0;
+    int i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
+    while (i >= 0 && k >= 0) {
+        which = z.get((long long) i * n_col + (k - (i > w ? i - w : 0))) >> (which << 1) & 3;
+        if (which == 0) { cigar_push_d(cigar, n, 0, 1); --i; --k; }
+        else if (which == 1) { cigar_push_d(cigar, n, 2, 1); --i; }
+        else { cigar_push_d(cigar, n, 1, 1); --k; }
+    }
+    if (i >= 0) cigar_push_d(cigar, n, 2, i + 1);
+    if (k >= 0) cigar_push_d(cigar, n, 1, k + 1);
+    for (i = 0; i < n >> 1; ++i) { const uint32_t tmp = cigar[i]; cigar[i] = cigar[n - 1 - i]; cigar[n - 1 - i] = tmp; }
+    *n_cigar = n;
+    return score;
+}
+
+// band of the global alignment (src/bwa.cpp:292-300; double arithmetic as the reference)
+BM2_HD int cigar_band_d(const CigarParams &p, int w_, int l_query, long long rlen) {
+    int max_ins = (int) ((double) (((l_query + 1) >> 1) * p.mat[0] - p.o_ins) / p.e_ins + 1.);
+    int max_del = (int) ((double) (((l_query + 1) >> 1) * p.mat[0] - p.o_del) / p.e_del + 1.);
+    int max_gap = max_ins > max_del ? max_ins : max_del;
+    max_gap = max_gap > 1 ? max_gap : 1;
+    int diff = (int) (rlen - l_query); if (diff < 0) diff = -diff;
+    int w = (max_gap + diff + 1) >> 1;
+    w = w < w_ ? w : w_;
+    const int min_w = diff + 3;
+    return w > min_w ? w : min_w;
+}
+
+// cells of the backtrack matrix a request needs (0: no DP)
+BM2_HD long long cigar_z_cells_d(const CigarParams &p, int64_t l_pac, int w_, int l_query, int64_t rb, int64_t re) {
+    if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac) || re > (l_pac << 1) || rb < 0) return 0;
+    const long long rlen = re - rb;
+    if (l_query == rlen && w_ == 0) return 0;
+    const int w = cigar_band_d(p, w_, l_query, rlen);
+    const long long n_col = l_query < 2 * w + 1 ? l_query : 2 * w + 1;
+    return n_col * rlen;
+}
+
+// decimal digits of a non-negative int appended to md (kputw)
+BM2_HD void md_putw_d(char *md, int &n, int v) {
+    char buf[12]; int l = 0;
+    if (v == 0) buf[l++] = '0';
+    while (v > 0) { buf[l++] = (char) ('0' + v % 10); v /= 10; }
+    while (l > 0) md[n++] = buf[--l];
+}
+
+// bwa_gen_cigar2 (src/bwa.cpp:260-347).  query: the read's codes (0-4), l_query of them; ref: 2*l_pac codes (fwd || revcomp).
+// Outputs: *score (untouched when the request is rejected, as in the reference), cigar[0..*n_cigar), *nm (-1 when rejected),
+// md[0..*n_md) (NUL-terminated, the terminator counted as the reference appends it).  Returns false when rejected.
+// Capacities: cigar l_query + rlen + 2 operations, md 2*l_query + 7*rlen + 16 bytes, he 2*(l_query+1) ints.
+BM2_HD bool gen_cigar_d(const CigarParams &p, int64_t l_pac, const uint8_t *ref, int w_, int l_query, const uint8_t *query, int64_t rb, int64_t re,
+                        int32_t *he, const CigarZ &z, int *score, uint32_t *cigar, int *n_cigar, int *nm, char *md, int *n_md)
+{
+    *n_cigar = 0; *nm = -1; *n_md = 0;
+    if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) return false;
+    if (re > (l_pac << 1) || rb < 0) return false;                       // bns_get_seq clips: rlen != re - rb
+    const long long rlen = re - rb;
+    const bool rev = rb >= l_pac;
+    const uint8_t *qp = rev ? query + (l_query - 1) : query; const int qs = rev ? -1 : 1;
+    const uint8_t *tp = rev ? ref + (re - 1) : ref + rb;      const int ts = rev ? -1 : 1;
+    int n = 0;
+    if (l_query == rlen && w_ == 0) {
+        cigar[0] = (uint32_t) l_query << 4 | 0; n = 1;
+        int sc = 0;
+        for (int i = 0; i < l_query; ++i) sc += p.mat[tp[(long long) i * ts] * 5 + qp[(long long) i * qs]];
+        *score = sc;
+    } else {
+        const int w = cigar_band_d(p, w_, l_query, rlen);
+        *score = global_align_d(l_query, qp, qs, (int) rlen, tp, ts, p.mat, p.o_del, p.e_del, p.o_ins, p.e_ins, w, he, z, cigar, &n);
+    }
+    *n_cigar = n;
+    // NM and MD (src/bwa.cpp:305-337)
+    {
+        int x = 0, y = 0, u = 0, n_mm = 0, n_gap = 0, m = 0;
+        for (int k = 0; k < n; ++k) {
+            const int op = (int) (cigar[k] & 0xf), len = (int) (cigar[k] >> 4);
+            if (op == 0) {
+                for (int i = 0; i < len; ++i) {
+                    const int qb = qp[(long long) (x + i) * qs], tb = tp[(long long) (y + i) * ts];
+                    if (qb != tb) {
+                        md_putw_d(md, m, u);
+                        md[m++] = rev ? "TGCAN"[tb] : "ACGTN"[tb];
+                        ++n_mm; u = 0;
+                    } else ++u;
+                }
+                x += len; y += len;
+            } else if (op == 2) {
+                if (k > 0 && k < n - 1) {
+                    md_putw_d(md, m, u); md[m++] = '^';
+                    for (int i = 0; i < len; ++i) { const int tb = tp[(long long) (y + i) * ts]; md[m++] = rev ? "TGCAN"[tb] : "ACGTN"[tb]; }
+                    u = 0; n_gap += len;
+                }
+                y += len;
+            } else if (op == 1) { x += len; n_gap += len; }
+        }
+        md_putw_d(md, m, u); md[m++] = 0;
+        *nm = n_mm + n_gap;
+        *n_md = m;
+    }
+    return true;
+}

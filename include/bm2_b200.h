@@ -215,6 +215,35 @@ int bm2_last_stage_ms(const bm2_ctx *ctx, const char *const **names, const float
  * with the doubled band.  n >= 5. */
 int bm2_last_counters(const bm2_ctx *ctx, unsigned long long *v, int n);
 
+/* ---------------------------------------------------------------------------------------------
+ * Seam 3 (first widening step): CIGAR, NM and MD of alignments whose end points are
+ * known.  Replaces bwa_gen_cigar2 (src/bwa.cpp:260-347) with its banded global alignment + backtrack
+ * ksw_global2 (src/ksw.cpp:558-668), called per output alignment by mem_reg2aln (src/bwamem.cpp:1757-1768):
+ *     cigar = bwa_gen_cigar2(opt->mat, o_del, e_del, o_ins, e_ins, w2, bns->l_pac, pac, qe - qb, &query[qb], rb, re,
+ *                            &score, &n_cigar, &NM);
+ * One request = one such call; the query is reads[read][qb, qe), the scoring comes from the context's mem_opt_t.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct bm2_cigar_req {
+    int64_t rb, re;            /* reference interval in the [0, 2*l_pac) coordinate (mem_alnreg_t / mem_aln_t) */
+    int32_t read;              /* index of the read in the batch                                               */
+    int32_t qb, qe;            /* query interval of the read                                                   */
+    int32_t w;                 /* band limit (the w_ argument)                                                 */
+} bm2_cigar_req;
+typedef struct bm2_cigar_rec {
+    int32_t score;             /* INT32_MIN when the reference returns without setting *score (rejected)      */
+    int32_t n_cigar;           /* operations: len << 4 | op (0 M, 1 I, 2 D), as the reference's uint32_t cigar */
+    int32_t nm;                /* NM (-1 when rejected)                                                        */
+    int32_t n_md;              /* bytes of the MD string incl. its NUL (the block appended after the cigar)    */
+    int64_t cigar_off, md_off; /* offsets into bm2_cigar_result::cigar / ::md                                  */
+} bm2_cigar_rec;
+typedef struct bm2_cigar_result {
+    int64_t n; const bm2_cigar_rec *recs;
+    int64_t n_ops; const uint32_t *cigar;
+    int64_t n_md; const char *md;
+} bm2_cigar_result;
+/* Needs a context created with an index.  Result arrays are owned by the context (valid until its next call). */
+int bm2_gen_cigar(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_cigar_req *reqs, int64_t n, bm2_cigar_result *out);
+
 #ifdef __cplusplus
 }
 #endif

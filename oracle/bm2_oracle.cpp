@@ -8,6 +8,8 @@
 #include <vector>
 #include <algorithm>
 #include <cmath>
+#include <string>
+#include <climits>
 
 /* ------------------------------------------------------------------------------------------------
  * A6. Banded affine-gap extension DP.
@@ -1007,4 +1009,143 @@ extern "C" int bm2o_seed_chain_extend(const bm2_index_desc *idx, const bm2_mem_o
     *n_regs = (int64_t) all.size(); *read_off = off;
     if (bsw_cells) *bsw_cells = cells;
     return rc;
+}
+
+
+/* ================================================================================================
+ * CIGAR / NM / MD: bwa_gen_cigar2 (src/bwa.cpp:260-347) over ksw_global2 with the
+ * backtrack matrix (src/ksw.cpp:558-668) and push_cigar (:545-556).  Plain restatement: sequences are
+ * copied (and reversed for reverse-strand hits), the matrix is a vector.
+ * ============================================================================================== */
+static void o_push_cigar(std::vector<uint32_t> &c, int op, int len) {
+    if (c.empty() || op != (int) (c.back() & 0xf)) c.push_back((uint32_t) len << 4 | (uint32_t) op);
+    else c.back() += (uint32_t) len << 4;
+}
+
+static int o_global_align(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat,
+                          int o_del, int e_del, int o_ins, int e_ins, int w, std::vector<uint32_t> &cigar)
+{
+    const int MINUS_INF = -0x40000000;
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+    std::vector<uint8_t> z((size_t) n_col * (size_t) tlen + 1);
+    std::vector<int32_t> H(qlen + 1), E(qlen + 1);
+    H[0] = 0; E[0] = MINUS_INF;
+    int i, j, k;
+    for (j = 1; j <= qlen && j <= w; ++j) { H[j] = -(o_ins + e_ins * j); E[j] = MINUS_INF; }
+    for (; j <= qlen; ++j) H[j] = E[j] = MINUS_INF;
+    for (i = 0; i < tlen; ++i) {
+        int32_t f = MINUS_INF, h1;
+        const int beg = i > w ? i - w : 0;
+        const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+        h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : MINUS_INF;
+        uint8_t *zi = &z[(size_t) i * n_col];
+        for (j = beg; j < end; ++j) {
+            int32_t m = H[j], e = E[j], h, t;
+            uint8_t d;
+            H[j] = h1;
+            m += mat[target[i] * 5 + query[j]];
+            d = m >= e ? 0 : 1;
+            h = m >= e ? m : e;
+            d = h >= f ? d : 2;
+            h = h >= f ? h : f;
+            h1 = h;
+            t = m - oe_del; e -= e_del;
+            d |= e > t ? 1 << 2 : 0;
+            e = e > t ? e : t;
+            E[j] = e;
+            t = m - oe_ins; f -= e_ins;
+            d |= f > t ? 2 << 4 : 0;
+            f = f > t ? f : t;
+            zi[j - beg] = d;
+        }
+        H[end] = h1; E[end] = MINUS_INF;
+    }
+    const int score = H[qlen];
+    int which = 0;
+    cigar.clear();
+    i = tlen - 1; k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
+    while (i >= 0 && k >= 0) {
+        which = z[(size_t) i * n_col + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
+        if (which == 0) { o_push_cigar(cigar, 0, 1); --i; --k; }
+        else if (which == 1) { o_push_cigar(cigar, 2, 1); --i; }
+        else { o_push_cigar(cigar, 1, 1); --k; }
+    }
+    if (i >= 0) o_push_cigar(cigar, 2, i + 1);
+    if (k >= 0) o_push_cigar(cigar, 1, k + 1);
+    std::reverse(cigar.begin(), cigar.end());
+    return score;
+}
+
+extern "C" int bm2o_gen_cigar(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const bm2_cigar_req *reqs,
+                              int64_t n, bm2_cigar_rec **recs_out, uint32_t **cigar_out, int64_t *n_ops_out, char **md_out, int64_t *n_md_out)
+{
+    std::vector<bm2_cigar_rec> recs((size_t) n);
+    std::vector<uint32_t> all_ops; std::string all_md;
+    const int64_t l_pac = x->l_pac;
+    for (int64_t r = 0; r < n; ++r) {
+        const bm2_cigar_req &q = reqs[r];
+        bm2_cigar_rec &o = recs[(size_t) r];
+        o.score = INT32_MIN; o.n_cigar = 0; o.nm = -1; o.n_md = 0; o.cigar_off = (int64_t) all_ops.size(); o.md_off = (int64_t) all_md.size();
+        if (q.read < 0 || q.read >= reads->n_reads) return 1;
+        const int64_t ro = reads->offsets[q.read], rl = reads->offsets[q.read + 1] - ro;
+        if (q.qb < 0 || q.qe > rl) return 1;
+        const int l_query = q.qe - q.qb;
+        const int64_t rb = q.rb, re = q.re;
+        if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) continue;       /* src/bwa.cpp:272 */
+        if (re > (l_pac << 1) || rb < 0) continue;                                   /* bns_get_seq clips: rlen != re - rb, :274 */
+        const int64_t rlen = re - rb;
+        std::vector<uint8_t> rs(x->ref_string + rb, x->ref_string + re), qs(reads->codes + ro + q.qb, reads->codes + ro + q.qe);
+        const bool rev = rb >= l_pac;
+        if (rev) { std::reverse(rs.begin(), rs.end()); std::reverse(qs.begin(), qs.end()); }      /* :275-280 */
+        std::vector<uint32_t> cig;
+        if (l_query == rlen && q.w == 0) {                                                          /* :281-290 */
+            cig.push_back((uint32_t) l_query << 4 | 0);
+            int sc = 0;
+            for (int i = 0; i < l_query; ++i) sc += opt->mat[rs[i] * 5 + qs[i]];
+            o.score = sc;
+        } else {                                                                                    /* :291-304 */
+            int max_ins = (int)((double)(((l_query + 1) >> 1) * opt->mat[0] - opt->o_ins) / opt->e_ins + 1.);
+            int max_del = (int)((double)(((l_query + 1) >> 1) * opt->mat[0] - opt->o_del) / opt->e_del + 1.);
+            int max_gap = max_ins > max_del ? max_ins : max_del;
+            max_gap = max_gap > 1 ? max_gap : 1;
+            int diff = (int)(rlen - l_query); if (diff < 0) diff = -diff;
+            int w = (max_gap + diff + 1) >> 1;
+            w = w < q.w ? w : q.w;
+            int min_w = diff + 3;
+            w = w > min_w ? w : min_w;
+            o.score = o_global_align(l_query, qs.data(), (int) rlen, rs.data(), opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, w, cig);
+        }
+        /* NM and MD (:305-337) */
+        std::string md;
+        int xq = 0, y = 0, u = 0, n_mm = 0, n_gap = 0;
+        const char *int2base = rev ? "TGCAN" : "ACGTN";
+        const int nc = (int) cig.size();
+        for (int k = 0; k < nc; ++k) {
+            const int op = (int) (cig[k] & 0xf), len = (int) (cig[k] >> 4);
+            if (op == 0) {
+                for (int i = 0; i < len; ++i) {
+                    if (qs[xq + i] != rs[y + i]) { md += std::to_string(u); md += int2base[rs[y + i]]; ++n_mm; u = 0; }
+                    else ++u;
+                }
+                xq += len; y += len;
+            } else if (op == 2) {
+                if (k > 0 && k < nc - 1) {
+                    md += std::to_string(u); md += '^';
+                    for (int i = 0; i < len; ++i) md += int2base[rs[y + i]];
+                    u = 0; n_gap += len;
+                }
+                y += len;
+            } else if (op == 1) { xq += len; n_gap += len; }
+        }
+        md += std::to_string(u);
+        o.n_cigar = nc; o.nm = n_mm + n_gap; o.n_md = (int32_t) md.size() + 1;
+        all_ops.insert(all_ops.end(), cig.begin(), cig.end());
+        all_md += md; all_md.push_back('\0');
+    }
+    *recs_out = (bm2_cigar_rec *) malloc(sizeof(bm2_cigar_rec) * (size_t) (n + 1)); memcpy(*recs_out, recs.data(), sizeof(bm2_cigar_rec) * (size_t) n);
+    *cigar_out = (uint32_t *) malloc(4 * (all_ops.size() + 1)); memcpy(*cigar_out, all_ops.data(), 4 * all_ops.size());
+    *md_out = (char *) malloc(all_md.size() + 1); memcpy(*md_out, all_md.data(), all_md.size());
+    *n_ops_out = (int64_t) all_ops.size(); *n_md_out = (int64_t) all_md.size();
+    return 0;
 }

@@ -51,6 +51,11 @@ int bm2o_seed_chain(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const b
 int bm2o_seed_chain_extend(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads,
                            bm2_alnreg_t **regs, int64_t *n_regs, int64_t **read_off, int64_t *bsw_cells);
 
+/* CIGAR / NM / MD of alignments with known end points == bwa_gen_cigar2 (src/bwa.cpp:260-347) + ksw_global2 with backtrack
+ * (src/ksw.cpp:545-668); same request / record layout as bm2_gen_cigar.  Arrays are malloc'd (bm2o_free). */
+int bm2o_gen_cigar(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const bm2_cigar_req *reqs,
+                   int64_t n, bm2_cigar_rec **recs, uint32_t **cigar, int64_t *n_ops, char **md, int64_t *n_md);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,12 @@
  *   BM2_LIB=<path to libbm2b200.so>       (gpu modes)
  *   BM2_DUMP_PREFIX=<p>   write <p>.smem.bin <p>.chains.bin <p>.regs.bin <p>.bsw.bin  (use -t 1)
  *   BM2_STATS=<file>      JSON with wall seconds of the phases
+ *
+ * `ref_driver cigar <index prefix> <requests.bin> <out.bin>` calls the reference's own bwa_gen_cigar2 (src/bwa.cpp:260)
+ * on every request of a binary file (pins the CIGAR/NM/MD restatement of the oracle):
+ *   requests.bin: int64 n; then per request int64 rb, re; int32 w, l_query; uint8 query[l_query]
+ *   out.bin:      per request int32 score, n_cigar, nm, n_md; uint32 cigar[n_cigar]; char md[n_md]
+ *                 (score = INT32_MIN when the reference returns without setting it)
  */
 #include <cstdio>
 #include <cstdlib>
@@ -43,6 +49,8 @@
 #include "fastmap.h"
 #include "kthread.h"
 #include "main.h"
+#include "bwa.h"
+#include "bntseq.h"
 #undef private
 #undef protected
 
@@ -273,7 +281,43 @@ BSW_HOOK(_ZN16BandedPairWiseSW11getScores16EP10dnaSeqPairPhS2_iti, 16, uint16_t)
 BSW_HOOK(_ZN16BandedPairWiseSW10getScores8EP10dnaSeqPairPhS2_iti, 8, uint16_t)
 BSW_HOOK(_ZN16BandedPairWiseSW22scalarBandedSWAWrapperEP10dnaSeqPairPhS2_iii, 1, int)
 
+static int cigar_mode(int argc, char *argv[]) {
+    if (argc < 5) { fprintf(stderr, "usage: ref_driver cigar <index prefix> <requests.bin> <out.bin>\n"); return 1; }
+    bntseq_t *bns = bns_restore(argv[2]);
+    if (!bns) return 1;
+    std::vector<uint8_t> pac((size_t) (bns->l_pac / 4 + 1));
+    if (fread(pac.data(), 1, pac.size(), bns->fp_pac) == 0) return 1;
+    mem_opt_t *opt = mem_opt_init();
+    FILE *fi = fopen(argv[3], "rb"), *fo = fopen(argv[4], "wb");
+    if (!fi || !fo) return 1;
+    int64_t n = 0;
+    if (fread(&n, 8, 1, fi) != 1) return 1;
+    std::vector<uint8_t> q;
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t rb, re; int32_t w, lq;
+        if (fread(&rb, 8, 1, fi) != 1 || fread(&re, 8, 1, fi) != 1 || fread(&w, 4, 1, fi) != 1 || fread(&lq, 4, 1, fi) != 1) return 1;
+        q.resize((size_t) (lq > 0 ? lq : 0) + 1);
+        if (lq > 0 && fread(q.data(), 1, (size_t) lq, fi) != (size_t) lq) return 1;
+        int score = INT32_MIN, n_cigar = 0, nm = 0;
+        uint32_t *cigar = bwa_gen_cigar2(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, w, bns->l_pac, pac.data(), lq, q.data(), rb, re,
+                                         &score, &n_cigar, &nm);
+        /* the MD string follows the n_cigar operations in the returned block (src/bwa.cpp:307, :334) */
+        int32_t n_md = 0;
+        const char *md = nullptr;
+        if (cigar && nm >= 0) { md = (const char *) (cigar + n_cigar); n_md = (int32_t) strlen(md) + 1; }
+        int32_t hdr[4] = { score, n_cigar, nm, n_md };
+        fwrite(hdr, 4, 4, fo);
+        if (n_cigar) fwrite(cigar, 4, (size_t) n_cigar, fo);
+        if (n_md) fwrite(md, 1, (size_t) n_md, fo);
+        free(cigar);
+    }
+    fclose(fi); fclose(fo);
+    free(opt); bns_destroy(bns);
+    return 0;
+}
+
 int main(int argc, char *argv[]) {
+    if (argc >= 2 && strcmp(argv[1], "cigar") == 0) return cigar_mode(argc, argv);
     const char *m = getenv("BM2_MODE");
     if (m) {
         if (!strcmp(m, "hotpath")) g_mode = M_HOTPATH;

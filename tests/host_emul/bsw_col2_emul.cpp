@@ -4,6 +4,9 @@
 #include <vector>
 #include <cstdint>
 #include <cstring>
+static std::vector<int> *g_trace = nullptr;       // optional: the band [beg, end) of every row (lane-utilisation studies)
+static inline void col2_trace(int b, int e) { if (g_trace) { g_trace->push_back(b); g_trace->push_back(e); } }
+#define BM2_COL2_TRACE col2_trace
 #include "bsw_col2.cuh"
 
 struct HostCol2Mem {
@@ -17,13 +20,27 @@ struct HostCol2Mem {
 
 // out = 6 ints per job (score, tle, gtle, qle, gscore, max_off); returns the number of DP cells, -1 for unsupported scoring.
 // Sequences: query[qoff + k * qstride], target[toff + k * tstride].
+// rows[k] = number of rows job k ran; widths: per job and row the band width end - beg (concatenated, cap entries)
+extern "C" long long col2_extend_trace(int n, const int64_t *qoff, const int64_t *toff, const int32_t *qlen, const int32_t *tlen,
+                                       const int32_t *h0, const int32_t *qstride, const int32_t *tstride, const uint8_t *qbuf, const uint8_t *tbuf,
+                                       const int32_t *prm, int32_t *out, int32_t *rows, int16_t *widths, long long cap);
+
 extern "C" long long col2_extend_all(int n, const int64_t *qoff, const int64_t *toff, const int32_t *qlen, const int32_t *tlen,
                                      const int32_t *h0, const int32_t *qstride, const int32_t *tstride, const uint8_t *qbuf, const uint8_t *tbuf,
                                      const int32_t *prm /*9*/, int32_t *out)
 {
+    return col2_extend_trace(n, qoff, toff, qlen, tlen, h0, qstride, tstride, qbuf, tbuf, prm, out, nullptr, nullptr, 0);
+}
+
+extern "C" long long col2_extend_trace(int n, const int64_t *qoff, const int64_t *toff, const int32_t *qlen, const int32_t *tlen,
+                                       const int32_t *h0, const int32_t *qstride, const int32_t *tstride, const uint8_t *qbuf, const uint8_t *tbuf,
+                                       const int32_t *prm, int32_t *out, int32_t *rows, int16_t *widths, long long cap)
+{
     BswParams p; p.a = prm[0]; p.b = prm[1]; p.o_del = prm[2]; p.e_del = prm[3]; p.o_ins = prm[4]; p.e_ins = prm[5];
     p.zdrop = prm[6]; p.end_bonus = prm[7]; p.w = prm[8];
     if (!c2_params_ok(p)) return -1;
+    std::vector<int> tr;
+    long long wpos = 0;
     unsigned long long cells = 0;
     std::vector<uint16_t> state(264);
     std::vector<uint8_t> sel(268);
@@ -35,8 +52,14 @@ extern "C" long long col2_extend_all(int n, const int64_t *qoff, const int64_t *
         for (int j = 0; j < qlen[k]; ++j) sel[j] = (uint8_t) c2_selector_byte(qbuf[qoff[k] + (int64_t) j * qstride[k]]);
         HostCol2Mem mem{state.data(), sel.data()};
         BswOut o;
+        tr.clear(); g_trace = rows ? &tr : nullptr;
         if (p.o_del + p.e_del == p.o_ins + p.e_ins && !(k & 1)) bsw_col2_extend<true>(mem, tbuf + toff[k], tstride[k], qlen[k], tlen[k], h0[k], p, o, cells);
         else bsw_col2_extend<false>(mem, tbuf + toff[k], tstride[k], qlen[k], tlen[k], h0[k], p, o, cells);      // (odd jobs: the general form also under equal penalties)
+        g_trace = nullptr;
+        if (rows) {
+            rows[k] = (int32_t) (tr.size() / 2);
+            for (size_t r = 0; r < tr.size() / 2; ++r) { if (wpos >= cap) return -3; widths[wpos++] = (int16_t) (tr[2 * r + 1] > tr[2 * r] ? tr[2 * r + 1] - tr[2 * r] : 0); }
+        }
         int32_t *d = out + 6 * (size_t) k;
         d[0] = o.score; d[1] = o.tle; d[2] = o.gtle; d[3] = o.qle; d[4] = o.gscore; d[5] = o.max_off;
     }

@@ -105,6 +105,27 @@ def seed_chain_extend(index, opt, codes, offsets):
     return a, offs, cells.value, rc
 
 
+def gen_cigar(index, opt, codes, offsets, reqs):
+    """Oracle's bwa_gen_cigar2 restatement -> (recs CIGAR_REC_DT, cigar uint32[], md bytes, rc)."""
+    capi = _capi()
+    codes = np.ascontiguousarray(codes, np.uint8); offsets = np.ascontiguousarray(offsets, np.int64)
+    reqs = np.ascontiguousarray(reqs, capi.CIGAR_REQ_DT)
+    rb = capi.ReadBatch(len(offsets) - 1, codes.ctypes.data, offsets.ctypes.data)
+    recs = C.c_void_p(); cig = C.c_void_p(); md = C.c_void_p(); n_ops = C.c_int64(); n_md = C.c_int64()
+    L = lib()
+    rc = L.bm2o_gen_cigar(C.byref(index.desc), C.byref(opt), C.byref(rb), reqs.ctypes.data_as(C.c_void_p), C.c_int64(len(reqs)),
+                          C.byref(recs), C.byref(cig), C.byref(n_ops), C.byref(md), C.byref(n_md))
+    if rc:
+        return None, None, None, rc
+    def arr(p, n, dt):
+        dt = np.dtype(dt)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(n, 1) * dt.itemsize,))[:n * dt.itemsize].view(dt).copy()
+    out = arr(recs, len(reqs), capi.CIGAR_REC_DT), arr(cig, n_ops.value, "<u4"), arr(md, n_md.value, "u1"), 0
+    for p in (recs, cig, md):
+        L.bm2o_free(p)
+    return out
+
+
 REG_CMP_FIELDS = ("rb", "re", "qb", "qe", "rid", "score", "truesc", "sub", "alt_sc", "csub", "sub_n", "w", "seedcov",
                   "secondary", "secondary_all", "seedlen0", "frac_rep", "hash")
 
