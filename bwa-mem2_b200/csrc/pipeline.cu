@@ -749,7 +749,10 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     const int stripe = max_len + 2;
     // CTAs per SM the SMEM kernels' grids may occupy (BM2_SMEM_CTAS): fewer leave room for the extension kernels of
     // the other sub-batches in flight (memory-latency-bound search next to ALU-bound DP on the same SM)
-    const int smem_ctas = env_int("BM2_SMEM_CTAS", 10, 1, 16);
+    // Measured (profiles/r1q_exp_smem_ctas.log, 1 M reads, 3 Gbp): unsplit batch 8 CTAs/SM: SMEM stage 47 ms against 55 ms with 10
+    // and 50 ms with 6 (the stage sits on the random-access roofline of HBM: more searches in flight only thrash L2 / the DRAM
+    // pages); four sub-batch lanes with 3-4 CTAs/SM each: 126.5-127.3 ms per step against 129.2-129.8 ms with 10.
+    const int smem_ctas = env_int("BM2_SMEM_CTAS", ctx->parent ? 4 : 8, 1, 16);
     int blocks_a = (n + 127) / 128; int max_blocks_a = ctx->n_sm * smem_ctas;
     {   // per-thread forward scratch = stripe * 32 bytes: keep it under ~8 GB for long reads
         const size_t per_block = (size_t) 128 * stripe * sizeof(FmPrev);
