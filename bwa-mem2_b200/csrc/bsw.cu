@@ -167,10 +167,11 @@ __device__ __forceinline__ void bsw_extend_one(const St &st, const QFetch &qf, c
     }
     // band (SIMD wrapper arithmetic, bandedSWA.cpp:2905-2926; == scalar :146-156 when e == 1)
     int w = p.w;
+    const BswQuirk qk = bsw_quirk(qlen, tlen, h0, p);
     {
-        unsigned t1 = ((unsigned) (qlen * sa) + (unsigned) (p.end_bonus - p.o_ins)) & 0xFFFFu;
+        unsigned t1 = ((unsigned) (qlen * sa) + (unsigned) (p.end_bonus - p.o_ins)) & qk.band_mask;
         int max_ins = (int) (t1 / (unsigned) e_ins) + 1; if (max_ins < 1) max_ins = 1;
-        unsigned t2 = ((unsigned) (qlen * sa) + (unsigned) (p.end_bonus - p.o_del)) & 0xFFFFu;
+        unsigned t2 = ((unsigned) (qlen * sa) + (unsigned) (p.end_bonus - p.o_del)) & qk.band_mask;
         int max_del = (int) (t2 / (unsigned) e_del) + 1; if (max_del < 1) max_del = 1;
         if (w > max_ins) w = max_ins;
         if (w > max_del) w = max_del;
@@ -243,10 +244,11 @@ __device__ __forceinline__ void bsw_extend_one(const St &st, const QFetch &qf, c
             best = m; best_i = i; best_j = mj;
             int d = mj - i; d = d < 0 ? -d : d;
             if (d > max_off) max_off = d;
-        } else if (p.zdrop > 0) {
+            if (0 > qk.zthr) break;
+        } else {
             int di = i - best_i, dj = mj - best_j;
-            int pen = di > dj ? di - dj : dj - di;       // SIMD z-drop: no e_del/e_ins factor (ZSCORE16)
-            if (best - m - pen > p.zdrop) break;
+            int pen = di > dj ? di - dj : dj - di;       // SIMD z-drop: no e_del/e_ins factor, no `zdrop > 0` guard (ZSCORE8/16)
+            if (best - m - pen > qk.zthr) break;
         }
         for (j = beg; j < end && st.zero(j); ++j) {}
         beg = j;
@@ -510,6 +512,7 @@ bsw_warp_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ per
             if (w > max_ins) w = max_ins;
             if (w > max_del) w = max_del;
         }
+        const int zthr = bsw_quirk(qlen, tlen, h0, p).zthr;      // (never the 8-bit class here: 16-bit threshold, no guard)
         // the launcher guarantees 2*w+2 <= 32*CMAX for this instantiation
         int max_init = -1;
         int best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0;
@@ -596,10 +599,11 @@ bsw_warp_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ per
                 best = m; best_i = i; best_j = mj;
                 int dd = mj - i; dd = dd < 0 ? -dd : dd;
                 if (dd > max_off) max_off = dd;
-            } else if (p.zdrop > 0) {
+                if (0 > zthr) break;
+            } else {
                 const int di = i - best_i, dj = mj - best_j;
                 const int pen = di > dj ? di - dj : dj - di;
-                if (best - m - pen > p.zdrop) break;
+                if (best - m - pen > zthr) break;
             }
             // shrink the band to the non-zero support of the row just written
             int fz = end, lz = beg - 1;                       // first / last non-zero column in [beg, end]

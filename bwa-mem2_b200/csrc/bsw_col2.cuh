@@ -54,10 +54,11 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
     }
     // band (SIMD wrapper arithmetic, bandedSWA.cpp:2905-2926)
     int w = p.w;
+    const BswQuirk qk = bsw_quirk(qlen, tlen, h0, p);
     {
-        unsigned t1 = ((unsigned) (qlen * p.a) + (unsigned) (p.end_bonus - p.o_ins)) & 0xFFFFu;
+        unsigned t1 = ((unsigned) (qlen * p.a) + (unsigned) (p.end_bonus - p.o_ins)) & qk.band_mask;
         int max_ins = (int) (t1 / (unsigned) e_ins) + 1; if (max_ins < 1) max_ins = 1;
-        unsigned t2 = ((unsigned) (qlen * p.a) + (unsigned) (p.end_bonus - p.o_del)) & 0xFFFFu;
+        unsigned t2 = ((unsigned) (qlen * p.a) + (unsigned) (p.end_bonus - p.o_del)) & qk.band_mask;
         int max_del = (int) (t2 / (unsigned) e_del) + 1; if (max_del < 1) max_del = 1;
         if (w > max_ins) w = max_ins;
         if (w > max_del) w = max_del;
@@ -162,10 +163,11 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
             best = m; best_i = i; best_j = mj;
             int d = mj - i; d = d < 0 ? -d : d;
             if (d > max_off) max_off = d;
-        } else if (p.zdrop > 0) {
+            if (0 > qk.zthr) break;
+        } else {
             const int di = i - best_i, dj = mj - best_j;
-            const int pen = di > dj ? di - dj : dj - di;       // SIMD z-drop: no e_del/e_ins factor (ZSCORE16)
-            if (best - m - pen > p.zdrop) break;
+            const int pen = di > dj ? di - dj : dj - di;       // SIMD z-drop: no e_del/e_ins factor, no `zdrop > 0` guard (ZSCORE8/16)
+            if (best - m - pen > qk.zthr) break;
         }
         for (j = beg; j < end && mem.ldh(j) == 0u; ++j) {}
         beg = j;

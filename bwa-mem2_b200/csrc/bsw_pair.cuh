@@ -101,7 +101,7 @@ BM2_HD void bsw_pair_extend(const Mem &mem, const uint8_t *tptrA, int tstrideA, 
     c.n_e_del = ((uint32_t) (-p.e_del) & 0xFFFFu) * 0x10001u;
     c.n_oe_ins = ((uint32_t) (-oe_ins) & 0xFFFFu) * 0x10001u;
     c.n_e_ins = ((uint32_t) (-p.e_ins) & 0xFFFFu) * 0x10001u;
-    int qlen[2], tlen[2], h0[2], w[2], beg[2], end[2], best[2], best_i[2], best_j[2], best_ie[2], gscore[2], max_off[2];
+    int qlen[2], tlen[2], h0[2], w[2], beg[2], end[2], best[2], best_i[2], best_j[2], best_ie[2], gscore[2], max_off[2], zthr[2];
     bool alive[2];
     unsigned long long ncell = 0;
 #pragma unroll
@@ -112,9 +112,11 @@ BM2_HD void bsw_pair_extend(const Mem &mem, const uint8_t *tptrA, int tstrideA, 
         beg[l] = 0; end[l] = qlen[l];
         // band (SIMD wrapper arithmetic, bandedSWA.cpp:2905-2926)
         int ww = p.w;
-        unsigned t1 = ((unsigned) (qlen[l] * p.a) + (unsigned) (p.end_bonus - p.o_ins)) & 0xFFFFu;
+        const BswQuirk qk = bsw_quirk(qlen[l], tlen[l], h0[l], p);
+        zthr[l] = qk.zthr;
+        unsigned t1 = ((unsigned) (qlen[l] * p.a) + (unsigned) (p.end_bonus - p.o_ins)) & qk.band_mask;
         int max_ins = (int) (t1 / (unsigned) e_ins) + 1; if (max_ins < 1) max_ins = 1;
-        unsigned t2 = ((unsigned) (qlen[l] * p.a) + (unsigned) (p.end_bonus - p.o_del)) & 0xFFFFu;
+        unsigned t2 = ((unsigned) (qlen[l] * p.a) + (unsigned) (p.end_bonus - p.o_del)) & qk.band_mask;
         int max_del = (int) (t2 / (unsigned) e_del) + 1; if (max_del < 1) max_del = 1;
         if (ww > max_ins) ww = max_ins;
         if (ww > max_del) ww = max_del;
@@ -228,10 +230,11 @@ BM2_HD void bsw_pair_extend(const Mem &mem, const uint8_t *tptrA, int tstrideA, 
                 best[l] = m; best_i[l] = i; best_j[l] = mj;
                 int d = mj - i; d = d < 0 ? -d : d;
                 if (d > max_off[l]) max_off[l] = d;
-            } else if (p.zdrop > 0) {
+                if (0 > zthr[l]) { alive[l] = false; continue; }
+            } else {
                 const int di = i - best_i[l], dj = mj - best_j[l];
-                const int pen = di > dj ? di - dj : dj - di;       // SIMD z-drop: no gap-extension factor (ZSCORE16)
-                if (best[l] - m - pen > p.zdrop) { alive[l] = false; continue; }
+                const int pen = di > dj ? di - dj : dj - di;       // SIMD z-drop: no gap-extension factor, no `zdrop > 0` guard (ZSCORE8/16)
+                if (best[l] - m - pen > zthr[l]) { alive[l] = false; continue; }
             }
             int j;
             for (j = beg[l]; j < end[l] && mem.ld_half(j, l) == 0u; ++j) {}

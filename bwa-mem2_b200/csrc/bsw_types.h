@@ -27,3 +27,24 @@ struct BswOut {               // as SeqPair's result fields (src/bandedSWA.h:96-
     int32_t score, tle, gtle, qle, gscore, max_off;
 };
 
+
+// How the reference's SIMD class of a job bends its arithmetic (results must equal the reference's for every mem_opt_t):
+// jobs that sortPairsLenExt (src/bwamem.cpp:1944-1952) sends to the 8-bit kernel - len1, len2 < 128 and
+// h0 + min(len1, len2) * a < 128 - keep the band operands and the z-drop threshold in 8 bits (src/bandedSWA.cpp:2195-2216,
+// :2347), the 16-bit kernel in 16 bits (:2905-2926, :3044); neither kernel guards the z-drop test with `zdrop > 0`
+// (ZSCORE8/16 run on every row, :1826-1839, :1868-1880), so -d 0 drops at the first non-improving row and a threshold that
+// went negative (-d 128..255 in the 8-bit class) ends the job at its first row.
+struct BswQuirk { unsigned band_mask; int zthr; };
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+BswQuirk bsw_quirk(int qlen, int tlen, int h0, const BswParams &p) {
+    const int minlen = qlen < tlen ? qlen : tlen;
+    const bool k8 = tlen < 128 && qlen < 128 && h0 + minlen * p.a < 128;
+    BswQuirk q;
+    q.band_mask = k8 ? 0xFFu : 0xFFFFu;
+    q.zthr = k8 ? (int) (int8_t) p.zdrop : (int) (int16_t) p.zdrop;
+    return q;
+}

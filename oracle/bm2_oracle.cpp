@@ -39,10 +39,16 @@ extern "C" int64_t bm2o_bsw_extend(const uint8_t *query, int32_t qlen, const uin
     /* band clipping (bandedSWA.cpp:146-156) */
     int maxsc = p->a;                                   /* max of mat[] for bwa_fill_scmat matrices */
     int max_ins, max_del;
+    /* the SIMD class of the job (sortPairsLenExt, src/bwamem.cpp:1944-1952): the 8-bit kernel keeps the band operands, the
+     * z-drop threshold and the z-drop arithmetic in 8 bits (src/bandedSWA.cpp:2195-2216, :1826-1839, :2347), the 16-bit one in 16 */
+    const int minlen = qlen < tlen ? qlen : tlen;
+    const bool k8 = p->vector_quirks && tlen < 128 && qlen < 128 && h0 + minlen * p->a < 128;
+    const int zthr = !p->vector_quirks ? p->zdrop : (k8 ? (int) (int8_t) p->zdrop : (int) (int16_t) p->zdrop);
     if (p->vector_quirks) {
-        uint16_t t1 = (uint16_t)((uint16_t)(qlen * maxsc) + (uint16_t)(int16_t)(p->end_bonus - p->o_ins));
+        const unsigned mask = k8 ? 0xFFu : 0xFFFFu;
+        unsigned t1 = ((unsigned) (qlen * maxsc) + (unsigned) (p->end_bonus - p->o_ins)) & mask;
         max_ins = (int)((double)(t1 / p->e_ins) + 1.0);
-        uint16_t t2 = (uint16_t)((uint16_t)(qlen * maxsc) + (uint16_t)(int16_t)(p->end_bonus - p->o_del));
+        unsigned t2 = ((unsigned) (qlen * maxsc) + (unsigned) (p->end_bonus - p->o_del)) & mask;
         max_del = (int)((double)(t2 / p->e_del) + 1.0);
     } else {
         max_ins = (int)((double)(qlen * maxsc + p->end_bonus - p->o_ins) / p->e_ins + 1.);
@@ -90,14 +96,17 @@ extern "C" int64_t bm2o_bsw_extend(const uint8_t *query, int32_t qlen, const uin
             best = row_max; best_i = i; best_j = row_arg;
             int d = row_arg - i; if (d < 0) d = -d;
             if (d > max_off) max_off = d;
-        } else if (p->zdrop > 0) {
+            /* the SIMD kernels evaluate the z-drop test on every row (ZSCORE8/16 after the best-score update: 0 > zdrop),
+             * which fires for a threshold that went negative in 8 / 16 bits (-d 128..255 in the 8-bit class) */
+            if (p->vector_quirks && 0 > zthr) break;
+        } else if (p->vector_quirks || p->zdrop > 0) {     /* no `zdrop > 0` guard in the SIMD kernels: -d 0 drops at once */
             int di = i - best_i, dj = row_arg - best_j;
             if (di > dj) {
                 int pen = p->vector_quirks ? (di - dj) : (di - dj) * p->e_del;
-                if (best - row_max - pen > p->zdrop) break;
+                if (best - row_max - pen > zthr) break;
             } else {
                 int pen = p->vector_quirks ? (dj - di) : (dj - di) * p->e_ins;
-                if (best - row_max - pen > p->zdrop) break;
+                if (best - row_max - pen > zthr) break;
             }
         }
         /* shrink the band to the non-zero support of the row just written (:218-221) */

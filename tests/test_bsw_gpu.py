@@ -113,3 +113,26 @@ def test_non_default_scoring(pkg, golden_dir, sc):
     ol.extend_pairs(want, ref, qer, 100, ol.bsw_params(end_bonus=0, **sc))
     _assert_same(p, want)
     ctx.close()
+
+
+@pytest.mark.parametrize("sc", [dict(zdrop=0), dict(zdrop=128), dict(zdrop=200), dict(a=2, b=8, o_del=12, e_del=2, o_ins=12, e_ins=2, zdrop=200),
+                                dict(a=3, b=12, o_del=18, e_del=3, o_ins=18, e_ins=3, zdrop=90)])
+def test_zdrop_and_band_quirks_of_the_simd_classes(pkg, sc):
+    # the reference's SIMD kernels test z-drop on every row without a `zdrop > 0` guard, and its 8-bit class (len < 128,
+    # h0 + min(len) * a < 128) keeps the threshold and the band operands in 8 bits: -d 0, -d 128.., -A 2 (which scales -d to 200)
+    o = pkg.capi.default_opt()
+    for k, v in sc.items():
+        setattr(o, k, v)
+    ctx = pkg.capi.Context(0, opt=o)
+    rng = np.random.default_rng(77)
+    n = 4000
+    len1, len2, h0, idr, idq, ref, qer = _random_jobs(rng, n, 151, 300, sim=0.9, nrate=0.005, h0max=70)
+    p = np.zeros(n, pkg.capi.PAIR_DT)
+    p["len1"] = len1; p["len2"] = len2; p["h0"] = h0; p["idr"] = idr; p["idq"] = idq
+    want = p.copy()
+    ctx.extend_pairs(p, ref, qer, 100, 5 * o.a)
+    prm = ol.bsw_params(a=o.a, b=o.b, o_del=o.o_del, e_del=o.e_del, o_ins=o.o_ins, e_ins=o.e_ins, zdrop=o.zdrop, end_bonus=5 * o.a)
+    ol.extend_pairs(want, ref, qer, 100, prm)
+    _assert_same(p, want)
+    assert ((len1 < 128) & (len2 < 128) & (h0 + np.minimum(len1, len2) * o.a < 128)).sum() > 200      # the 8-bit class is covered
+    ctx.close()

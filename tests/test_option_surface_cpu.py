@@ -22,7 +22,10 @@ CASES = [
     ("c20_D0.3_r1.0", ["-c", "20", "-D", "0.3", "-r", "1.0"]),
     ("s5_G500_N30_W10", ["-s", "5", "-G", "500", "-N", "30", "-W", "10"]),
     ("y5_X0.3", ["-y", "5", "-X", "0.3"]),
-    ("k25_w10_d200_B8", ["-k", "25", "-w", "10", "-d", "200", "-B", "8"]),
+    ("k25_w10_d200_B8", ["-k", "25", "-w", "10", "-d", "200", "-B", "8"]),   # -d >= 128: the 8-bit SIMD class sees a negative threshold
+    ("d0", ["-d", "0"]),                                             # the SIMD kernels have no `zdrop > 0` guard
+    ("d128", ["-d", "128"]),
+    ("A3_d90", ["-A", "3", "-d", "90"]),                             # 8-bit band operands wrap (qlen * a)
 ]
 
 

@@ -75,6 +75,26 @@ def test_regs_match_reference_with_cell_bsw_kernel(c0, monkeypatch):
     assert ol.regs_equal_to_dump(regs, ro, st["regs"], st["reg_off"]) == []
 
 
+@pytest.mark.parametrize("sc", [dict(zdrop=0), dict(a=2, b=8, o_del=12, e_del=2, o_ins=12, e_ins=2, zdrop=200, pen_clip5=10, pen_clip3=10, T=60, pen_unpaired=34)])
+def test_regs_match_oracle_with_non_default_options(pkg, c0, sc):
+    # -d 0 and -A 2 (update_a of src/fastmap.cpp scales B, O, E, L, T, d, U): the oracle is pinned to the reference run with these
+    # options by tests/test_option_surface_cpu.py
+    idx, ctx0, codes, offs, st = c0
+    o = pkg.capi.default_opt()
+    for k, v in sc.items():
+        setattr(o, k, v)
+    k = 0
+    for i in range(4):
+        for j in range(4):
+            o.mat[k] = o.a if i == j else -o.b; k += 1
+        o.mat[k] = -1; k += 1
+    ctx = pkg.capi.Context(0, index=idx, opt=o)
+    regs, ro = ctx.seed_chain_extend(codes, offs)
+    want, wo, _, rc = ol.seed_chain_extend(idx, o, codes, offs)
+    assert rc == 0 and np.array_equal(ro, wo) and regs.tobytes() == want.tobytes()
+    ctx.close()
+
+
 def test_ragged_and_degenerate_reads(pkg, c0):
     idx, ctx, codes, offs, st = c0
     reads = codes.reshape(-1, 151)
