@@ -1,0 +1,2 @@
+set -x
+timeout 240 python -m pytest tests -m gpu -q 2>&1 | tail -8

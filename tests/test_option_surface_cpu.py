@@ -26,6 +26,10 @@ CASES = [
     ("d0", ["-d", "0"]),                                             # the SIMD kernels have no `zdrop > 0` guard
     ("d128", ["-d", "128"]),
     ("A3_d90", ["-A", "3", "-d", "90"]),                             # 8-bit band operands wrap (qlen * a)
+    ("x_intractg", ["-x", "intractg"]),                              # B9 O16 L5
+    # (-x pacbio on these 2x151 pairs makes the reference itself abort inside worker_sam; -x ont2d covers the same preset code)
+    ("x_ont2d_k19", ["-x", "ont2d", "-k", "19"]),
+    ("w150_c5", ["-w", "150", "-c", "5"]),
 ]
 
 
@@ -37,8 +41,10 @@ def opt_from_cli(capi, args):
     def two(v):
         a = v.replace(",", " ").split()
         return int(a[0]), int(a[1]) if len(a) > 1 else int(a[0])
+    mode = None
     for k in it:
         v = next(it)
+        if k == "-x": mode = v; continue
         if k == "-k": o.min_seed_len = int(v); set_.add("min_seed_len")
         elif k == "-w": o.w = int(v)
         elif k == "-A": o.a = int(v); set_.add("a")
@@ -48,16 +54,27 @@ def opt_from_cli(capi, args):
         elif k == "-L": o.pen_clip5, o.pen_clip3 = two(v); set_.add("pen_clip5"); set_.add("pen_clip3")
         elif k == "-c": o.max_occ = int(v)
         elif k == "-d": o.zdrop = int(v); set_.add("zdrop")
-        elif k == "-r": o.split_factor = float(v)
+        elif k == "-r": o.split_factor = float(v); set_.add("split_factor")
         elif k == "-D": o.drop_ratio = float(v)
         elif k == "-s": o.split_width = int(v)
         elif k == "-G": o.max_chain_gap = int(v)
         elif k == "-N": o.max_chain_extend = int(v)
-        elif k == "-W": o.min_chain_weight = int(v)
+        elif k == "-W": o.min_chain_weight = int(v); set_.add("min_chain_weight")
         elif k == "-y": o.max_mem_intv = int(v)
         elif k == "-X": o.mask_level = float(v)
         else: raise ValueError(k)
-    if "a" in set_:                                                  # update_a (src/fastmap.cpp:547-561)
+    if mode == "intractg":                                           # src/fastmap.cpp:803-811
+        for f, v in (("o_del", 16), ("o_ins", 16), ("b", 9), ("pen_clip5", 5), ("pen_clip3", 5)):
+            if f not in set_: setattr(o, f, v)
+    elif mode in ("pacbio", "pbref", "ont2d"):                       # :812-835
+        for f, v in (("o_del", 1), ("e_del", 1), ("o_ins", 1), ("e_ins", 1), ("b", 1)):
+            if f not in set_: setattr(o, f, v)
+        if "split_factor" not in set_: o.split_factor = 10.0
+        for f, v in (("min_chain_weight", 20 if mode == "ont2d" else 40), ("min_seed_len", 14 if mode == "ont2d" else 17), ("pen_clip5", 0), ("pen_clip3", 0)):
+            if f not in set_: setattr(o, f, v)
+    elif mode is not None:
+        raise ValueError(mode)
+    if mode is None and "a" in set_:                                 # update_a (src/fastmap.cpp:547-561), only without -x (:843)
         for f in ("b", "T", "o_del", "e_del", "o_ins", "e_ins", "zdrop", "pen_clip5", "pen_clip3", "pen_unpaired"):
             if f not in set_:
                 setattr(o, f, getattr(o, f) * o.a)
