@@ -120,3 +120,28 @@ def test_reference_oracle_and_device_logic_agree(pkg, c0, name, args):
     eregs, ero = el.seed_chain_extend(idx, opt, codes, offs)
     assert np.array_equal(ero, ro) and eregs.tobytes() == regs.tobytes(), "device logic differs from the oracle"
     assert len(regs) > 1000
+
+
+def test_alt_contigs(pkg, c0, golden_dir):
+    """ALT-aware chaining / marking (src/bwamem.cpp:506-624, :1164-1168): the C0 index with a .alt file naming two of its four contigs."""
+    import shutil
+    idx0, codes, offs, work, prefix0 = c0
+    d = os.path.join(work, "altidx"); os.makedirs(d, exist_ok=True)
+    for f in os.listdir(os.path.dirname(prefix0)):
+        shutil.copy(os.path.join(os.path.dirname(prefix0), f), os.path.join(d, f))
+    with open(os.path.join(d, "ref.fa.alt"), "w") as f:
+        f.write("chr3\t0\tchr1\t1\t60\t100M\t*\t0\t0\t*\t*\nchr4\t0\tchr1\t1\t60\t100M\t*\t0\t0\t*\t*\n")
+    prefix = os.path.join(d, "ref.fa")
+    env = dict(os.environ, BM2_DUMP_PREFIX=os.path.join(work, "alt"))
+    with open(os.path.join(work, "alt.sam"), "w") as f:
+        subprocess.check_call([cu.refbin(), "mem", "-t", "1", "-K", "100000000", prefix, os.path.join(work, "r1.fq"), os.path.join(work, "r2.fq")],
+                              stdout=f, stderr=subprocess.DEVNULL, env=env)
+    ref_regs, ref_off = refdump.read_regs(os.path.join(work, "alt.regs.bin"))
+    idx = pkg.capi.Index(prefix)
+    opt = pkg.capi.default_opt()
+    regs, ro, cells, rc = ol.seed_chain_extend(idx, opt, codes, offs)
+    assert rc == 0 and (ref_regs["is_alt"] != 0).sum() > 1000
+    assert ol.regs_equal_to_dump(regs, ro, ref_regs, ref_off) == []
+    eregs, ero = el.seed_chain_extend(idx, opt, codes, offs)
+    assert np.array_equal(ero, ro) and eregs.tobytes() == regs.tobytes()
+    idx.close()
