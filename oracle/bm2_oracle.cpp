@@ -1158,3 +1158,127 @@ extern "C" int bm2o_gen_cigar(const bm2_index_desc *x, const bm2_mem_opt_t *opt,
     *n_ops_out = (int64_t) all_ops.size(); *n_md_out = (int64_t) all_md.size();
     return 0;
 }
+
+
+/* ================================================================================================
+ * Mate-rescue local alignment: ksw_align2 (src/ksw.cpp:324-381) = ksw_u8 (:111-233) or
+ * ksw_i16 (:235-316) forward, then the same kernel on the reversed prefixes to find the start.
+ * The SSE2 kernels are restated lane by lane: a vector j of the striped layout holds the query
+ * positions j + l * slen (l = lane), the first pass carries F inside a lane only, the lazy-F loop
+ * (at most 16 sweeps, global early exit) completes H but not E.
+ * ============================================================================================== */
+namespace {
+const int KX_BYTE = 0x10000, KX_STOP = 0x20000, KX_SUBO = 0x40000, KX_START = 0x80000;
+struct KswR { int score, te, qe, score2, te2, tb, qb; };
+
+KswR ksw_striped(int size, int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat,
+                 int o_del, int e_del, int o_ins, int e_ins, int xtra)
+{
+    const int m = 5;
+    const int p = size == 1 ? 16 : 8;                         /* values per vector (ksw_qinit, :64) */
+    const int slen = (qlen + p - 1) / p, nlen = slen * p;
+    int shift = 127, mdiff = 0;
+    for (int a = 0; a < m * m; ++a) { if (mat[a] < shift) shift = mat[a]; if (mat[a] > mdiff) mdiff = mat[a]; }
+    const int qmax = mdiff;
+    shift = (256 - shift) & 0xff;                             /* uint8_t (:82) */
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    const int minsc = (xtra & KX_SUBO) ? xtra & 0xffff : 0x10000, endsc = (xtra & KX_STOP) ? xtra & 0xffff : 0x10000;
+    const int cap = size == 1 ? 255 : 32767;
+    auto sat0 = [](int v) { return v < 0 ? 0 : v; };
+    std::vector<int> H0(nlen + 1, 0), H1(nlen + 1, 0), E(nlen + 1, 0), Hmax(nlen + 1, 0), fl(p, 0), hh(p, 0);
+    std::vector<uint64_t> b;
+    KswR r = { 0, -1, -1, -1, -1, -1, -1 };
+    int gmax = 0, te = -1;
+    for (int i = 0; i < tlen; ++i) {
+        const int8_t *ma = mat + target[i] * m;
+        int rowmax = 0;
+        /* first pass: lane l walks its segment l*slen .. l*slen+slen-1 with its own F, starting at 0 */
+        for (int l = 0; l < p; ++l) {
+            int f = 0;
+            for (int j = 0; j < slen; ++j) {
+                const int k = l * slen + j;
+                const int sc = k >= qlen ? 0 : ma[query[k]];
+                int h = k == 0 ? 0 : H0[k - 1];
+                if (size == 1) { h = h + sc + shift; if (h > 255) h = 255; h = sat0(h - shift); }        /* adds_epu8 + subs_epu8 */
+                else { h = h + sc; if (h > cap) h = cap; if (h < -32768) h = -32768; }                  /* adds_epi16 */
+                int e = E[k];
+                if (e > h) h = e;
+                if (f > h) h = f;
+                if (h > rowmax) rowmax = h;
+                H1[k] = h;
+                e = sat0(e - e_del); { const int t = sat0(h - oe_del); if (t > e) e = t; }
+                E[k] = e;
+                f = sat0(f - e_ins); { const int t = sat0(h - oe_ins); if (t > f) f = t; }
+            }
+            fl[l] = f;
+        }
+        /* lazy F: shift F one lane up, sweep the vectors; stop as soon as no lane's F beats H - oe_ins (:172-186, :277-289) */
+        {
+            bool done = false;
+            for (int kk = 0; kk < 16 && !done; ++kk) {
+                for (int l = p - 1; l > 0; --l) fl[l] = fl[l - 1];
+                fl[0] = 0;
+                for (int j = 0; j < slen && !done; ++j) {
+                    bool any = false;
+                    for (int l = 0; l < p; ++l) {
+                        const int k = l * slen + j;
+                        int h = H1[k];
+                        if (fl[l] > h) h = fl[l];
+                        H1[k] = h;
+                        h = sat0(h - oe_ins);
+                        fl[l] = sat0(fl[l] - e_ins);
+                        if (fl[l] > h) any = true;
+                    }
+                    if (!any) done = true;
+                }
+            }
+        }
+        const int imax = rowmax;
+        if (imax >= minsc) {
+            if (b.empty() || (int32_t) b.back() + 1 != i) b.push_back((uint64_t) imax << 32 | (uint32_t) i);
+            else if ((int) (b.back() >> 32) < imax) b.back() = (uint64_t) imax << 32 | (uint32_t) i;
+        }
+        if (imax > gmax) {
+            gmax = imax; te = i;
+            for (int k = 0; k < nlen; ++k) Hmax[k] = H1[k];
+            if (size == 1 ? (gmax + shift >= 255 || gmax >= endsc) : (gmax >= endsc)) break;
+        }
+        H0.swap(H1);
+    }
+    r.score = size == 1 ? (gmax + shift < 255 ? gmax : 255) : gmax;
+    r.te = te;
+    if (size == 2 || r.score != 255) {
+        int mx = -1;
+        if (size == 2) r.qe = -1;
+        /* memory order of the vectors: element i is lane i % p of vector i / p -> query position i / p + (i % p) * slen */
+        for (int i = 0; i < nlen; ++i) {
+            const int pos = i / p + i % p * slen, v = Hmax[pos];
+            if (v > mx) { mx = v; r.qe = pos; }
+            else if (v == mx && pos < r.qe) r.qe = pos;
+        }
+        if (!b.empty()) {
+            const int d = (r.score + qmax - 1) / qmax, low = te - d, high = te + d;
+            for (size_t k = 0; k < b.size(); ++k) {
+                const int e = (int32_t) b[k];
+                if ((e < low || e > high) && (int) (b[k] >> 32) > r.score2) { r.score2 = (int) (b[k] >> 32); r.te2 = e; }
+            }
+        }
+    }
+    return r;
+}
+}  // namespace
+
+extern "C" void bm2o_ksw_align2(int32_t qlen, const uint8_t *query, int32_t tlen, const uint8_t *target, const int8_t *mat,
+                                int32_t o_del, int32_t e_del, int32_t o_ins, int32_t e_ins, int32_t xtra, int32_t *out)
+{
+    const int size = (xtra & KX_BYTE) ? 1 : 2;
+    KswR r = ksw_striped(size, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra);
+    if (!((xtra & KX_START) == 0 || ((xtra & KX_SUBO) && r.score < (xtra & 0xffff)))) {
+        /* the reversed prefixes (+1: qe / te point at the end itself); the target keeps its tail (:366-371) */
+        std::vector<uint8_t> q(query, query + r.qe + 1), t(target, target + tlen);
+        std::reverse(q.begin(), q.end()); std::reverse(t.begin(), t.begin() + r.te + 1);
+        KswR rr = ksw_striped(size, r.qe + 1, q.data(), tlen, t.data(), mat, o_del, e_del, o_ins, e_ins, KX_STOP | r.score);
+        if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
+    }
+    out[0] = r.score; out[1] = r.te; out[2] = r.qe; out[3] = r.score2; out[4] = r.te2; out[5] = r.tb; out[6] = r.qb;
+}

@@ -56,6 +56,14 @@ int bm2o_seed_chain_extend(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
 int bm2o_gen_cigar(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const bm2_cigar_req *reqs,
                    int64_t n, bm2_cigar_rec **recs, uint32_t **cigar, int64_t *n_ops, char **md, int64_t *n_md);
 
+/* Local alignment of mate rescue == ksw_align2 (src/ksw.cpp:324-381) over ksw_u8 / ksw_i16 (:111-323), the call of mem_matesw
+ * (src/bwamem_pair.cpp:189; SURVEY 8f item 1, groundwork for the next widening step).  The reference's kernels are striped
+ * (Farrar) with a lazy-F loop; the E of the next row is taken from the FIRST-pass H (F propagated inside a stripe lane only), so
+ * the result depends on the segmentation slen = ceil(qlen / 16 or 8): restated in scalar code with the same segmentation.
+ * out[7] = score, te, qe, score2, te2, tb, qb (kswr_t).  query/target are not modified. */
+void bm2o_ksw_align2(int32_t qlen, const uint8_t *query, int32_t tlen, const uint8_t *target, const int8_t *mat /*5x5*/,
+                     int32_t o_del, int32_t e_del, int32_t o_ins, int32_t e_ins, int32_t xtra, int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,11 @@
  *   requests.bin: int64 n; then per request int64 rb, re; int32 w, l_query; uint8 query[l_query]
  *   out.bin:      per request int32 score, n_cigar, nm, n_md; uint32 cigar[n_cigar]; char md[n_md]
  *                 (score = INT32_MIN when the reference returns without setting it)
+ *
+ * `ref_driver ksw <requests.bin> <out.bin>` calls the reference's own ksw_align2 (src/ksw.cpp:324, the local alignment of mate
+ * rescue) with the default scoring on every request:
+ *   requests.bin: int64 n; then per request int32 qlen, tlen, xtra; uint8 query[qlen]; uint8 target[tlen]
+ *   out.bin:      per request 7 int32: score, te, qe, score2, te2, tb, qb  (kswr_t)
  */
 #include <cstdio>
 #include <cstdlib>
@@ -51,6 +56,7 @@
 #include "main.h"
 #include "bwa.h"
 #include "bntseq.h"
+#include "ksw.h"
 #undef private
 #undef protected
 
@@ -316,8 +322,30 @@ static int cigar_mode(int argc, char *argv[]) {
     return 0;
 }
 
+static int ksw_mode(int argc, char *argv[]) {
+    if (argc < 4) { fprintf(stderr, "usage: ref_driver ksw <requests.bin> <out.bin>\n"); return 1; }
+    mem_opt_t *opt = mem_opt_init();
+    FILE *fi = fopen(argv[2], "rb"), *fo = fopen(argv[3], "wb");
+    if (!fi || !fo) return 1;
+    int64_t n = 0;
+    if (fread(&n, 8, 1, fi) != 1) return 1;
+    std::vector<uint8_t> q, t;
+    for (int64_t i = 0; i < n; ++i) {
+        int32_t h[3];
+        if (fread(h, 4, 3, fi) != 3) return 1;
+        q.resize((size_t) h[0] + 1); t.resize((size_t) h[1] + 1);
+        if ((h[0] && fread(q.data(), 1, (size_t) h[0], fi) != (size_t) h[0]) || (h[1] && fread(t.data(), 1, (size_t) h[1], fi) != (size_t) h[1])) return 1;
+        kswr_t r = ksw_align2(h[0], q.data(), h[1], t.data(), 5, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, h[2], 0);
+        int32_t o[7] = { r.score, r.te, r.qe, r.score2, r.te2, r.tb, r.qb };
+        fwrite(o, 4, 7, fo);
+    }
+    fclose(fi); fclose(fo); free(opt);
+    return 0;
+}
+
 int main(int argc, char *argv[]) {
     if (argc >= 2 && strcmp(argv[1], "cigar") == 0) return cigar_mode(argc, argv);
+    if (argc >= 2 && strcmp(argv[1], "ksw") == 0) return ksw_mode(argc, argv);
     const char *m = getenv("BM2_MODE");
     if (m) {
         if (!strcmp(m, "hotpath")) g_mode = M_HOTPATH;
