@@ -654,6 +654,7 @@ static int patch_reg(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const ui
 {
     int w, score = 0, q_s, r_s;
     double r;
+    if (query == 0) return 0;                                  /* mem_patch_reg: bns == 0 || pac == 0 || query == 0 (src/bwamem.cpp:179) */
     if (a->rb < x->l_pac && b->rb >= x->l_pac) return 0;
     if (a->qb >= b->qb || a->qe >= b->qe || a->re >= b->re) return 0;
     w = (int)((a->re - b->rb) - (a->qe - b->qb));
@@ -1281,4 +1282,143 @@ extern "C" void bm2o_ksw_align2(int32_t qlen, const uint8_t *query, int32_t tlen
         if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
     }
     out[0] = r.score; out[1] = r.te; out[2] = r.qe; out[3] = r.score2; out[4] = r.te2; out[5] = r.tb; out[6] = r.qb;
+}
+
+
+/* ================================================================================================
+ * Mate rescue around the local alignment: mem_pestat (src/bwamem_pair.cpp:88-148) and
+ * mem_matesw (:150-283, MATE_SORT == 0).
+ * ============================================================================================== */
+static int o_infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t *dist) {      /* mem_infer_dir (:57-65) */
+    const int r1 = (b1 >= l_pac), r2 = (b2 >= l_pac);
+    const int64_t p2 = r1 == r2 ? b2 : (l_pac << 1) - 1 - b2;
+    *dist = p2 > b1 ? p2 - b1 : b1 - p2;
+    return (r1 == r2 ? 0 : 1) ^ (p2 > b1 ? 0 : 3);
+}
+
+static int o_cal_sub(const bm2_mem_opt_t *opt, const bm2_alnreg_t *a, int n) {       /* cal_sub (:67-79) */
+    int j;
+    for (j = 1; j < n; ++j) {
+        const int b_max = a[j].qb > a[0].qb ? a[j].qb : a[0].qb;
+        const int e_min = a[j].qe < a[0].qe ? a[j].qe : a[0].qe;
+        if (e_min > b_max) {
+            const int min_l = a[j].qe - a[j].qb < a[0].qe - a[0].qb ? a[j].qe - a[j].qb : a[0].qe - a[0].qb;
+            if (e_min - b_max >= min_l * opt->mask_level) break;
+        }
+    }
+    return j < n ? a[j].score : opt->min_seed_len * opt->a;
+}
+
+/* lh[12] = low, high, failed of the four orientations; as[8] = avg, std */
+extern "C" void bm2o_pestat(const bm2_mem_opt_t *opt, int64_t l_pac, int32_t n_reads, const bm2_alnreg_t *regs, const int64_t *read_off,
+                            int32_t *lh, double *as)
+{
+    std::vector<uint64_t> isize[4];
+    for (int i = 0; i < n_reads >> 1; ++i) {
+        const bm2_alnreg_t *r0 = regs + read_off[i << 1 | 0], *r1 = regs + read_off[i << 1 | 1];
+        const int n0 = (int) (read_off[(i << 1 | 0) + 1] - read_off[i << 1 | 0]), n1 = (int) (read_off[(i << 1 | 1) + 1] - read_off[i << 1 | 1]);
+        if (n0 == 0 || n1 == 0) continue;
+        if (o_cal_sub(opt, r0, n0) > 0.8 * r0[0].score) continue;            /* MIN_RATIO */
+        if (o_cal_sub(opt, r1, n1) > 0.8 * r1[0].score) continue;
+        if (r0[0].rid != r1[0].rid) continue;
+        int64_t is;
+        const int dir = o_infer_dir(l_pac, r0[0].rb, r1[0].rb, &is);
+        if (is && is <= opt->max_ins) isize[dir].push_back((uint64_t) is);
+    }
+    for (int d = 0; d < 4; ++d) {
+        int32_t *o = lh + 3 * d; double *oa = as + 2 * d;
+        o[0] = o[1] = o[2] = 0; oa[0] = oa[1] = 0;
+        std::vector<uint64_t> &q = isize[d];
+        if (q.size() < 10) { o[2] = 1; continue; }                               /* MIN_DIR_CNT */
+        std::sort(q.begin(), q.end());                                           /* ks_introsort_64: plain keys, any sort */
+        const size_t n = q.size();
+        const int p25 = (int) q[(int) (.25 * n + .499)], p50 = (int) q[(int) (.50 * n + .499)], p75 = (int) q[(int) (.75 * n + .499)];
+        (void) p50;
+        int low = (int) (p25 - 2.0 * (p75 - p25) + .499);                        /* OUTLIER_BOUND */
+        if (low < 1) low = 1;
+        int high = (int) (p75 + 2.0 * (p75 - p25) + .499);
+        double avg = 0; size_t x = 0;
+        for (size_t i = 0; i < n; ++i) if (q[i] >= (uint64_t) low && q[i] <= (uint64_t) high) { avg += q[i]; ++x; }
+        avg /= x;
+        double sd = 0;
+        for (size_t i = 0; i < n; ++i) if (q[i] >= (uint64_t) low && q[i] <= (uint64_t) high) sd += (q[i] - avg) * (q[i] - avg);
+        sd = sqrt(sd / x);
+        low = (int) (p25 - 3.0 * (p75 - p25) + .499);                            /* MAPPING_BOUND */
+        high = (int) (p75 + 3.0 * (p75 - p25) + .499);
+        if (low > avg - 4.0 * sd) low = (int) (avg - 4.0 * sd + .499);            /* MAX_STDDEV */
+        if (high < avg + 4.0 * sd) high = (int) (avg + 4.0 * sd + .499);
+        if (low < 1) low = 1;
+        o[0] = low; o[1] = high; oa[0] = avg; oa[1] = sd;
+    }
+    size_t mx = 0;
+    for (int d = 0; d < 4; ++d) mx = mx > isize[d].size() ? mx : isize[d].size();
+    for (int d = 0; d < 4; ++d) if (lh[3 * d + 2] == 0 && isize[d].size() < mx * 0.05) lh[3 * d + 2] = 1;      /* MIN_DIR_RATIO */
+}
+
+/* mem_matesw: a = the anchor alignment of one read, ms = its mate's sequence, ma[0..*n_ma) the mate's regs (room for 4 more).
+ * pes_lh[12] = low, high, failed.  Returns n (number of orientations aligned). */
+extern "C" int bm2o_matesw(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const int32_t *pes_lh, const bm2_alnreg_t *a, int32_t l_ms,
+                           const uint8_t *ms, bm2_alnreg_t *ma, int32_t *n_ma)
+{
+    const int64_t l_pac = x->l_pac;
+    int skip[4], n = 0, nm = *n_ma;
+    for (int r = 0; r < 4; ++r) skip[r] = pes_lh[3 * r + 2] ? 1 : 0;
+    for (int i = 0; i < nm; ++i) {
+        int64_t dist;
+        const int r = o_infer_dir(l_pac, a->rb, ma[i].rb, &dist);
+        if (dist >= pes_lh[3 * r] && dist <= pes_lh[3 * r + 1]) skip[r] = 1;
+    }
+    if (skip[0] + skip[1] + skip[2] + skip[3] == 4) return 0;
+    for (int r = 0; r < 4; ++r) {
+        if (skip[r]) continue;
+        const int is_rev = (r >> 1 != (r & 1)), is_larger = !(r >> 1);
+        const int low = pes_lh[3 * r], high = pes_lh[3 * r + 1];
+        std::vector<uint8_t> seq(ms, ms + l_ms);
+        if (is_rev) for (int i = 0; i < l_ms; ++i) seq[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4;
+        int64_t rb, re;
+        if (!is_rev) {
+            rb = is_larger ? a->rb + low : a->rb - high;
+            re = (is_larger ? a->rb + high : a->rb - low) + l_ms;
+        } else {
+            rb = (is_larger ? a->rb + low : a->rb - high) - l_ms;
+            re = is_larger ? a->rb + high : a->rb - low;
+        }
+        if (rb < 0) rb = 0;
+        if (re > l_pac << 1) re = l_pac << 1;
+        int rid = -1;
+        if (rb < re) {                                                           /* bns_fetch_seq (src/bntseq.cpp:453-482) */
+            const int64_t mid = (rb + re) >> 1;
+            const int mrev = mid >= l_pac;
+            rid = pos2rid(x, depos(x, mid));
+            int64_t far_beg = x->ann_offset[rid], far_end = far_beg + x->ann_len[rid];
+            if (mrev) { const int64_t tmp = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - tmp; }
+            rb = rb > far_beg ? rb : far_beg;
+            re = re < far_end ? re : far_end;
+        }
+        if (a->rid == rid && re - rb >= opt->min_seed_len) {
+            const int xtra = KX_SUBO | KX_START | (l_ms * opt->a < 250 ? KX_BYTE : 0) | (opt->min_seed_len * opt->a);
+            int32_t al[7];
+            bm2o_ksw_align2(l_ms, seq.data(), (int32_t) (re - rb), x->ref_string + rb, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, xtra, al);
+            const int score = al[0], te = al[1], qe = al[2], score2 = al[3], tb = al[5], qb = al[6];
+            if (score >= opt->min_seed_len && qb >= 0) {
+                bm2_alnreg_t b; memset(&b, 0, sizeof(b));
+                b.rid = a->rid;
+                reg_set_is_alt(b, (a->n_comp_is_alt >> 30) & 3);
+                b.qb = is_rev ? l_ms - (qe + 1) : qb;
+                b.qe = is_rev ? l_ms - qb : qe + 1;
+                b.rb = is_rev ? (l_pac << 1) - (rb + te + 1) : rb + tb;
+                b.re = is_rev ? (l_pac << 1) - (rb + tb) : rb + te + 1;
+                b.score = score; b.csub = score2; b.secondary = -1;
+                b.seedcov = (int) ((b.re - b.rb < b.qe - b.qb ? b.re - b.rb : b.qe - b.qb) >> 1);
+                int i;
+                for (i = 0; i < nm; ++i) if (ma[i].score < b.score) break;       /* keep ma sorted by score (:233-238) */
+                for (int k = nm; k > i; --k) ma[k] = ma[k - 1];
+                ma[i] = b; ++nm;
+            }
+            ++n;
+        }
+        if (n) nm = sort_dedup_patch(x, opt, nullptr, nm, ma);
+    }
+    *n_ma = nm;
+    return n;
 }

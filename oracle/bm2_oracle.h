@@ -64,6 +64,12 @@ int bm2o_gen_cigar(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm
 void bm2o_ksw_align2(int32_t qlen, const uint8_t *query, int32_t tlen, const uint8_t *target, const int8_t *mat /*5x5*/,
                      int32_t o_del, int32_t e_del, int32_t o_ins, int32_t e_ins, int32_t xtra, int32_t *out);
 
+/* mem_pestat (src/bwamem_pair.cpp:88-148): lh[12] = low, high, failed of the orientations FF, FR, RF, RR; as[8] = avg, std. */
+void bm2o_pestat(const bm2_mem_opt_t *opt, int64_t l_pac, int32_t n_reads, const bm2_alnreg_t *regs, const int64_t *read_off, int32_t *lh, double *as);
+/* mem_matesw (src/bwamem_pair.cpp:150-283, MATE_SORT == 0): ma has room for *n_ma + 4 records. */
+int bm2o_matesw(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const int32_t *pes_lh, const bm2_alnreg_t *a, int32_t l_ms, const uint8_t *ms,
+                bm2_alnreg_t *ma, int32_t *n_ma);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@
  *   BM2_MODE=gpu_bsw  replace only the BSW calls by bm2_extend_pairs (config 2)
  *   BM2_LIB=<path to libbm2b200.so>       (gpu modes)
  *   BM2_DUMP_PREFIX=<p>   write <p>.smem.bin <p>.chains.bin <p>.regs.bin <p>.bsw.bin  (use -t 1)
+ *                         + <p>.pestat.bin (mem_pestat's result per chunk)
  *   BM2_STATS=<file>      JSON with wall seconds of the phases
  *
  * `ref_driver cigar <index prefix> <requests.bin> <out.bin>` calls the reference's own bwa_gen_cigar2 (src/bwa.cpp:260)
@@ -28,6 +29,12 @@
  * rescue) with the default scoring on every request:
  *   requests.bin: int64 n; then per request int32 qlen, tlen, xtra; uint8 query[qlen]; uint8 target[tlen]
  *   out.bin:      per request 7 int32: score, te, qe, score2, te2, tb, qb  (kswr_t)
+ *
+ * `ref_driver matesw <index prefix> <in.bin> <out.bin>` runs the rescue block of mem_sam_pe (src/bwamem_pair.cpp:378-412, MATE_SORT=0)
+ * with the reference's own mem_matesw (:150) on read pairs of a file (mem_matesw is called inside its own translation unit, so a
+ * link-time wrap cannot see it):
+ *   in.bin:  4 x (int32 low, high, failed); int64 n_pairs; per pair, for read 0 then read 1: int32 l_seq; uint8 seq[l_seq]; int32 n; mem_alnreg_t regs[n]
+ *   out.bin: per mem_matesw call: int32 pair, i, j, returned n, n_after; mem_alnreg_t regs[n_after] (the mate's regs after the call)
  */
 #include <cstdio>
 #include <cstdlib>
@@ -287,6 +294,17 @@ BSW_HOOK(_ZN16BandedPairWiseSW11getScores16EP10dnaSeqPairPhS2_iti, 16, uint16_t)
 BSW_HOOK(_ZN16BandedPairWiseSW10getScores8EP10dnaSeqPairPhS2_iti, 8, uint16_t)
 BSW_HOOK(_ZN16BandedPairWiseSW22scalarBandedSWAWrapperEP10dnaSeqPairPhS2_iii, 1, int)
 
+/* ---- mate rescue: mem_pestat (src/bwamem_pair.cpp:88) and mem_matesw (:150) wrapped at link time ---- */
+static FILE *f_pestat = 0;
+extern "C" void __real__Z10mem_pestatPK9mem_opt_tliPK12mem_alnreg_vP12mem_pestat_t(const mem_opt_t *, int64_t, int, const mem_alnreg_v *, mem_pestat_t *);
+extern "C" void __wrap__Z10mem_pestatPK9mem_opt_tliPK12mem_alnreg_vP12mem_pestat_t(const mem_opt_t *opt, int64_t l_pac, int n, const mem_alnreg_v *regs, mem_pestat_t *pes) {
+    __real__Z10mem_pestatPK9mem_opt_tliPK12mem_alnreg_vP12mem_pestat_t(opt, l_pac, n, regs, pes);
+    if (f_pestat) {
+        int32_t nn = n; fwrite(&nn, 4, 1, f_pestat);
+        for (int d = 0; d < 4; ++d) { int32_t v[3] = { pes[d].low, pes[d].high, pes[d].failed }; double w[2] = { pes[d].avg, pes[d].std }; fwrite(v, 4, 3, f_pestat); fwrite(w, 8, 2, f_pestat); }
+        fflush(f_pestat);
+    }
+}
 static int cigar_mode(int argc, char *argv[]) {
     if (argc < 5) { fprintf(stderr, "usage: ref_driver cigar <index prefix> <requests.bin> <out.bin>\n"); return 1; }
     bntseq_t *bns = bns_restore(argv[2]);
@@ -343,7 +361,54 @@ static int ksw_mode(int argc, char *argv[]) {
     return 0;
 }
 
+extern int mem_matesw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4], const mem_alnreg_t *a, int l_ms,
+                      const uint8_t *ms, mem_alnreg_v *ma);
+
+static int matesw_mode(int argc, char *argv[]) {
+    if (argc < 5) { fprintf(stderr, "usage: ref_driver matesw <index prefix> <in.bin> <out.bin>\n"); return 1; }
+    bntseq_t *bns = bns_restore(argv[2]);
+    if (!bns) return 1;
+    std::vector<uint8_t> pac((size_t) (bns->l_pac / 4 + 1));
+    if (fread(pac.data(), 1, pac.size(), bns->fp_pac) == 0) return 1;
+    mem_opt_t *opt = mem_opt_init();
+    FILE *fi = fopen(argv[3], "rb"), *fo = fopen(argv[4], "wb");
+    if (!fi || !fo) return 1;
+    mem_pestat_t pes[4]; memset(pes, 0, sizeof(pes));
+    for (int d = 0; d < 4; ++d) { int32_t v[3]; if (fread(v, 4, 3, fi) != 3) return 1; pes[d].low = v[0]; pes[d].high = v[1]; pes[d].failed = v[2]; }
+    int64_t np = 0;
+    if (fread(&np, 8, 1, fi) != 1) return 1;
+    for (int64_t pr = 0; pr < np; ++pr) {
+        std::vector<uint8_t> seq[2]; mem_alnreg_v a[2];
+        for (int i = 0; i < 2; ++i) {
+            int32_t l = 0, n = 0;
+            if (fread(&l, 4, 1, fi) != 1) return 1;
+            seq[i].resize((size_t) l + 1);
+            if (l && fread(seq[i].data(), 1, (size_t) l, fi) != (size_t) l) return 1;
+            seq[i].resize((size_t) l);
+            if (fread(&n, 4, 1, fi) != 1) return 1;
+            a[i].n = (size_t) n; a[i].m = (size_t) n + 8; a[i].a = (mem_alnreg_t *) calloc(a[i].m, sizeof(mem_alnreg_t));
+            if (n && fread(a[i].a, sizeof(mem_alnreg_t), (size_t) n, fi) != (size_t) n) return 1;
+        }
+        /* the rescue block of mem_sam_pe (src/bwamem_pair.cpp:378-412 with MATE_SORT == 0) */
+        mem_alnreg_v b[2]; kv_init(b[0]); kv_init(b[1]);
+        for (int i = 0; i < 2; ++i)
+            for (size_t j = 0; j < a[i].n; ++j)
+                if (a[i].a[j].score >= a[i].a[0].score - opt->pen_unpaired) kv_push(mem_alnreg_t, b[i], a[i].a[j]);
+        for (int i = 0; i < 2; ++i)
+            for (size_t j = 0; j < b[i].n && (int) j < opt->max_matesw; ++j) {
+                const int n = mem_matesw(opt, bns, pac.data(), pes, &b[i].a[j], (int) seq[!i].size(), seq[!i].data(), &a[!i]);
+                int32_t h[5] = { (int32_t) pr, i, (int32_t) j, n, (int32_t) a[!i].n };
+                fwrite(h, 4, 5, fo);
+                if (a[!i].n) fwrite(a[!i].a, sizeof(mem_alnreg_t), a[!i].n, fo);
+            }
+        free(b[0].a); free(b[1].a); free(a[0].a); free(a[1].a);
+    }
+    fclose(fi); fclose(fo); free(opt); bns_destroy(bns);
+    return 0;
+}
+
 int main(int argc, char *argv[]) {
+    if (argc >= 2 && strcmp(argv[1], "matesw") == 0) return matesw_mode(argc, argv);
     if (argc >= 2 && strcmp(argv[1], "cigar") == 0) return cigar_mode(argc, argv);
     if (argc >= 2 && strcmp(argv[1], "ksw") == 0) return ksw_mode(argc, argv);
     const char *m = getenv("BM2_MODE");
@@ -359,6 +424,7 @@ int main(int argc, char *argv[]) {
         f_chain = fopen((g_dump + ".chains.bin").c_str(), "wb");
         f_regs = fopen((g_dump + ".regs.bin").c_str(), "wb");
         f_bsw = fopen((g_dump + ".bsw.bin").c_str(), "wb");
+        f_pestat = fopen((g_dump + ".pestat.bin").c_str(), "wb");
     }
     /* rdtsc calibration as src/main.cpp:57-59, shortened */
     uint64_t tim = __rdtsc(); usleep(100000); proc_freq = (__rdtsc() - tim) * 10;
@@ -375,6 +441,6 @@ int main(int argc, char *argv[]) {
     int ret = main_mem(argc - 1, argv + 1);
     write_stats();
     if (g_ctx) p_destroy(g_ctx);
-    for (FILE *f : { f_smem, f_chain, f_regs, f_bsw }) if (f) fclose(f);
+    for (FILE *f : { f_smem, f_chain, f_regs, f_bsw, f_pestat }) if (f) fclose(f);
     return ret;
 }
