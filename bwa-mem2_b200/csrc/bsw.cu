@@ -17,6 +17,7 @@
 #include "bsw_pair.cuh"
 #include "bsw_col2.cuh"
 #include <cstdlib>
+#include <mutex>
 #include <cub/device/device_radix_sort.cuh>
 
 #define BSW_THREADS 128
@@ -700,6 +701,8 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     bsw_class_off_kernel<<<1, 32, 0, stream>>>(class_cnt, class_off);
 
     static bool attr_set = false;
+    static std::mutex attr_mu;                      // launches come from several host threads (sub-batch lanes, contexts)
+    std::unique_lock<std::mutex> attr_lock(attr_mu);
     if (!attr_set) {   // one function, several dynamic sizes: raise the limit once
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -710,6 +713,7 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
+    attr_lock.unlock();
     // Two columns of one job per packed instruction (bsw_col2.cuh) for the 8-bit-score classes; BM2_BSW_COL2=0 keeps the
     // one-cell-per-instruction kernel for them (A/B measurements, tests of both kernels).
     const char *col2_env = getenv("BM2_BSW_COL2");
@@ -777,7 +781,10 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
         else if (2 * prm.w + 2 <= 32 * 32)
             bsw_warp_kernel<32><<<wblocks, BSWW_WARPS * 32, 0, stream>>>(d_jobs, idx_out, class_off, d_out, d_tbase, d_qbase, prm, next_job, d_cells);
         else {
-        // very wide bands: state in global memory, one job per thread; the class size is needed on the host
+        // very wide bands: state in global memory, one job per thread; the class size is needed on the host.  The scratch is
+        // shared by all contexts of the process: one launch of this (rare) path at a time, held until the kernel has finished.
+        static std::mutex wide_mu;
+        std::lock_guard<std::mutex> wide_lock(wide_mu);
         int32_t h_off[2];
         BM2_CUDA_OK(cudaMemcpyAsync(h_off, class_off + BSW_NCLASS, 8, cudaMemcpyDeviceToHost, stream));
         BM2_CUDA_OK(cudaStreamSynchronize(stream));
@@ -801,6 +808,7 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
             int blocks = (nw + 63) / 64; if (blocks > 148 * 8) blocks = 148 * 8;
             bsw_wide_kernel<<<blocks, 64, 0, stream>>>(d_jobs, idx_out, class_off, d_out, d_tbase, d_qbase, prm, g_wide.state,
                                                        g_wide.state_off, d_cells);
+            BM2_CUDA_OK(cudaStreamSynchronize(stream));
         }
         }
     }
