@@ -1087,12 +1087,66 @@ static int o_global_align(int qlen, const uint8_t *query, int tlen, const uint8_
     return score;
 }
 
+/* bwa_gen_cigar2 for one alignment: returns false when rejected (score untouched, n_cigar = 0, NM = -1) */
+static bool gen_cigar_one(const bm2_index_desc *x, const bm2_mem_opt_t *opt, int w_, int l_query, const uint8_t *query, int64_t rb, int64_t re,
+                          int *score, std::vector<uint32_t> &cig, int *NM, std::string &md)
+{
+    const int64_t l_pac = x->l_pac;
+    cig.clear(); md.clear(); *NM = -1;
+    if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) return false;     /* src/bwa.cpp:272 */
+    if (re > (l_pac << 1) || rb < 0) return false;                                 /* bns_get_seq clips: rlen != re - rb, :274 */
+    const int64_t rlen = re - rb;
+    std::vector<uint8_t> rs(x->ref_string + rb, x->ref_string + re), qs(query, query + l_query);
+    const bool rev = rb >= l_pac;
+    if (rev) { std::reverse(rs.begin(), rs.end()); std::reverse(qs.begin(), qs.end()); }      /* :275-280 */
+    if (l_query == rlen && w_ == 0) {                                                          /* :281-290 */
+        cig.push_back((uint32_t) l_query << 4 | 0);
+        int sc = 0;
+        for (int i = 0; i < l_query; ++i) sc += opt->mat[rs[i] * 5 + qs[i]];
+        *score = sc;
+    } else {                                                                                    /* :291-304 */
+        int max_ins = (int)((double)(((l_query + 1) >> 1) * opt->mat[0] - opt->o_ins) / opt->e_ins + 1.);
+        int max_del = (int)((double)(((l_query + 1) >> 1) * opt->mat[0] - opt->o_del) / opt->e_del + 1.);
+        int max_gap = max_ins > max_del ? max_ins : max_del;
+        max_gap = max_gap > 1 ? max_gap : 1;
+        int diff = (int)(rlen - l_query); if (diff < 0) diff = -diff;
+        int w = (max_gap + diff + 1) >> 1;
+        w = w < w_ ? w : w_;
+        int min_w = diff + 3;
+        w = w > min_w ? w : min_w;
+        *score = o_global_align(l_query, qs.data(), (int) rlen, rs.data(), opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, w, cig);
+    }
+    /* NM and MD (:305-337) */
+    int xq = 0, y = 0, u = 0, n_mm = 0, n_gap = 0;
+    const char *int2base = rev ? "TGCAN" : "ACGTN";
+    const int nc = (int) cig.size();
+    for (int k = 0; k < nc; ++k) {
+        const int op = (int) (cig[k] & 0xf), len = (int) (cig[k] >> 4);
+        if (op == 0) {
+            for (int i = 0; i < len; ++i) {
+                if (qs[xq + i] != rs[y + i]) { md += std::to_string(u); md += int2base[rs[y + i]]; ++n_mm; u = 0; }
+                else ++u;
+            }
+            xq += len; y += len;
+        } else if (op == 2) {
+            if (k > 0 && k < nc - 1) {
+                md += std::to_string(u); md += '^';
+                for (int i = 0; i < len; ++i) md += int2base[rs[y + i]];
+                u = 0; n_gap += len;
+            }
+            y += len;
+        } else if (op == 1) { xq += len; n_gap += len; }
+    }
+    md += std::to_string(u);
+    *NM = n_mm + n_gap;
+    return true;
+}
+
 extern "C" int bm2o_gen_cigar(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const bm2_cigar_req *reqs,
                               int64_t n, bm2_cigar_rec **recs_out, uint32_t **cigar_out, int64_t *n_ops_out, char **md_out, int64_t *n_md_out)
 {
     std::vector<bm2_cigar_rec> recs((size_t) n);
     std::vector<uint32_t> all_ops; std::string all_md;
-    const int64_t l_pac = x->l_pac;
     for (int64_t r = 0; r < n; ++r) {
         const bm2_cigar_req &q = reqs[r];
         bm2_cigar_rec &o = recs[(size_t) r];
@@ -1100,56 +1154,9 @@ extern "C" int bm2o_gen_cigar(const bm2_index_desc *x, const bm2_mem_opt_t *opt,
         if (q.read < 0 || q.read >= reads->n_reads) return 1;
         const int64_t ro = reads->offsets[q.read], rl = reads->offsets[q.read + 1] - ro;
         if (q.qb < 0 || q.qe > rl) return 1;
-        const int l_query = q.qe - q.qb;
-        const int64_t rb = q.rb, re = q.re;
-        if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) continue;       /* src/bwa.cpp:272 */
-        if (re > (l_pac << 1) || rb < 0) continue;                                   /* bns_get_seq clips: rlen != re - rb, :274 */
-        const int64_t rlen = re - rb;
-        std::vector<uint8_t> rs(x->ref_string + rb, x->ref_string + re), qs(reads->codes + ro + q.qb, reads->codes + ro + q.qe);
-        const bool rev = rb >= l_pac;
-        if (rev) { std::reverse(rs.begin(), rs.end()); std::reverse(qs.begin(), qs.end()); }      /* :275-280 */
-        std::vector<uint32_t> cig;
-        if (l_query == rlen && q.w == 0) {                                                          /* :281-290 */
-            cig.push_back((uint32_t) l_query << 4 | 0);
-            int sc = 0;
-            for (int i = 0; i < l_query; ++i) sc += opt->mat[rs[i] * 5 + qs[i]];
-            o.score = sc;
-        } else {                                                                                    /* :291-304 */
-            int max_ins = (int)((double)(((l_query + 1) >> 1) * opt->mat[0] - opt->o_ins) / opt->e_ins + 1.);
-            int max_del = (int)((double)(((l_query + 1) >> 1) * opt->mat[0] - opt->o_del) / opt->e_del + 1.);
-            int max_gap = max_ins > max_del ? max_ins : max_del;
-            max_gap = max_gap > 1 ? max_gap : 1;
-            int diff = (int)(rlen - l_query); if (diff < 0) diff = -diff;
-            int w = (max_gap + diff + 1) >> 1;
-            w = w < q.w ? w : q.w;
-            int min_w = diff + 3;
-            w = w > min_w ? w : min_w;
-            o.score = o_global_align(l_query, qs.data(), (int) rlen, rs.data(), opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, w, cig);
-        }
-        /* NM and MD (:305-337) */
-        std::string md;
-        int xq = 0, y = 0, u = 0, n_mm = 0, n_gap = 0;
-        const char *int2base = rev ? "TGCAN" : "ACGTN";
-        const int nc = (int) cig.size();
-        for (int k = 0; k < nc; ++k) {
-            const int op = (int) (cig[k] & 0xf), len = (int) (cig[k] >> 4);
-            if (op == 0) {
-                for (int i = 0; i < len; ++i) {
-                    if (qs[xq + i] != rs[y + i]) { md += std::to_string(u); md += int2base[rs[y + i]]; ++n_mm; u = 0; }
-                    else ++u;
-                }
-                xq += len; y += len;
-            } else if (op == 2) {
-                if (k > 0 && k < nc - 1) {
-                    md += std::to_string(u); md += '^';
-                    for (int i = 0; i < len; ++i) md += int2base[rs[y + i]];
-                    u = 0; n_gap += len;
-                }
-                y += len;
-            } else if (op == 1) { xq += len; n_gap += len; }
-        }
-        md += std::to_string(u);
-        o.n_cigar = nc; o.nm = n_mm + n_gap; o.n_md = (int32_t) md.size() + 1;
+        std::vector<uint32_t> cig; std::string md; int score = INT32_MIN, nm = -1;
+        if (!gen_cigar_one(x, opt, q.w, q.qe - q.qb, reads->codes + ro + q.qb, q.rb, q.re, &score, cig, &nm, md)) continue;
+        o.score = score; o.n_cigar = (int32_t) cig.size(); o.nm = nm; o.n_md = (int32_t) md.size() + 1;
         all_ops.insert(all_ops.end(), cig.begin(), cig.end());
         all_md += md; all_md.push_back('\0');
     }
@@ -1421,4 +1428,195 @@ extern "C" int bm2o_matesw(const bm2_index_desc *x, const bm2_mem_opt_t *opt, co
     }
     *n_ma = nm;
     return n;
+}
+
+
+/* ================================================================================================
+ * SAM stage, single-end (groundwork): mem_mark_primary_se, mem_approx_mapq_se, mem_reg2aln and the
+ * record selection of mem_reg2sam.
+ * ============================================================================================== */
+static inline uint64_t o_hash_64(uint64_t key) {                 /* src/utils.h:117-128 */
+    key += ~(key << 32); key ^= (key >> 22); key += ~(key << 13); key ^= (key >> 8);
+    key += (key << 3); key ^= (key >> 15); key += ~(key << 27); key ^= (key >> 31);
+    return key;
+}
+static inline int reg_is_alt(const bm2_alnreg_t &a) { return (a.n_comp_is_alt >> 30) & 3; }
+
+static void mark_primary_core(const bm2_mem_opt_t *opt, int n, bm2_alnreg_t *a, std::vector<int> &z) {      /* :1392-1418 */
+    int tmp = opt->a + opt->b;
+    tmp = opt->o_del + opt->e_del > tmp ? opt->o_del + opt->e_del : tmp;
+    tmp = opt->o_ins + opt->e_ins > tmp ? opt->o_ins + opt->e_ins : tmp;
+    z.clear(); z.push_back(0);
+    for (int i = 1; i < n; ++i) {
+        size_t k;
+        for (k = 0; k < z.size(); ++k) {
+            const int j = z[k];
+            const int b_max = a[j].qb > a[i].qb ? a[j].qb : a[i].qb;
+            const int e_min = a[j].qe < a[i].qe ? a[j].qe : a[i].qe;
+            if (e_min > b_max) {
+                const int min_l = a[i].qe - a[i].qb < a[j].qe - a[j].qb ? a[i].qe - a[i].qb : a[j].qe - a[j].qb;
+                if (e_min - b_max >= min_l * opt->mask_level) {
+                    if (a[j].sub == 0) a[j].sub = a[i].score;
+                    if (a[j].score - a[i].score <= tmp && (reg_is_alt(a[j]) || !reg_is_alt(a[i]))) ++a[j].sub_n;
+                    break;
+                }
+            }
+        }
+        if (k == z.size()) z.push_back(i);
+        else a[i].secondary = z[k];
+    }
+}
+
+static int mark_primary_se(const bm2_mem_opt_t *opt, int n, bm2_alnreg_t *a, int64_t id) {                  /* :1420-1468 */
+    if (n == 0) return 0;
+    int n_pri = 0;
+    std::vector<int> z;
+    for (int i = 0; i < n; ++i) {
+        a[i].sub = a[i].alt_sc = 0; a[i].secondary = a[i].secondary_all = -1; a[i].hash = o_hash_64((uint64_t) (id + i));
+        if (!reg_is_alt(a[i])) ++n_pri;
+    }
+    ks_introsort(a, n, [](const bm2_alnreg_t &p, const bm2_alnreg_t &q) {                                    /* alnreg_hlt */
+        return p.score > q.score || (p.score == q.score && (reg_is_alt(p) < reg_is_alt(q) || (reg_is_alt(p) == reg_is_alt(q) && p.hash < q.hash)));
+    });
+    mark_primary_core(opt, n, a, z);
+    for (int i = 0; i < n; ++i) {
+        bm2_alnreg_t *p = &a[i];
+        p->secondary_all = i;
+        if (!reg_is_alt(*p) && p->secondary >= 0 && reg_is_alt(a[p->secondary])) p->alt_sc = a[p->secondary].score;
+    }
+    if (n_pri >= 0 && n_pri < n) {
+        z.assign((size_t) n, 0);
+        if (n_pri > 0) ks_introsort(a, n, [](const bm2_alnreg_t &p, const bm2_alnreg_t &q) {                 /* alnreg_hlt2 */
+            return reg_is_alt(p) < reg_is_alt(q) || (reg_is_alt(p) == reg_is_alt(q) && (p.score > q.score || (p.score == q.score && p.hash < q.hash)));
+        });
+        for (int i = 0; i < n; ++i) z[a[i].secondary_all] = i;
+        for (int i = 0; i < n; ++i) {
+            if (a[i].secondary >= 0) {
+                a[i].secondary_all = z[a[i].secondary];
+                if (reg_is_alt(a[i])) a[i].secondary = INT_MAX;
+            } else a[i].secondary_all = -1;
+        }
+        if (n_pri > 0) {
+            for (int i = 0; i < n_pri; ++i) { a[i].sub = 0; a[i].secondary = -1; }
+            mark_primary_core(opt, n_pri, a, z);
+        }
+    } else {
+        for (int i = 0; i < n; ++i) a[i].secondary_all = a[i].secondary;
+    }
+    return n_pri;
+}
+
+static int approx_mapq_se(const bm2_mem_opt_t *opt, const bm2_alnreg_t *a) {                                 /* :1470-1494 */
+    int mapq, l, sub = a->sub ? a->sub : opt->min_seed_len * opt->a;
+    double identity;
+    sub = a->csub > sub ? a->csub : sub;
+    if (sub >= a->score) return 0;
+    l = a->qe - a->qb > a->re - a->rb ? a->qe - a->qb : (int) (a->re - a->rb);
+    identity = 1. - (double) (l * opt->a - a->score) / (opt->a + opt->b) / l;
+    if (a->score == 0) mapq = 0;
+    else if (opt->mapQ_coef_len > 0) {
+        double tmp = l < opt->mapQ_coef_len ? 1. : opt->mapQ_coef_fac / log(l);
+        tmp *= identity * identity;
+        mapq = (int) (6.02 * (a->score - sub) / opt->a * tmp * tmp + .499);
+    } else {
+        mapq = (int) (30.0 * (1. - (double) sub / a->score) * log(a->seedcov) + .499);                      /* MEM_MAPQ_COEF */
+        mapq = identity < 0.95 ? (int) (mapq * identity * identity + .499) : mapq;
+    }
+    if (a->sub_n > 0) mapq -= (int) (4.343 * log(a->sub_n + 1) + .499);
+    if (mapq > 60) mapq = 60;
+    if (mapq < 0) mapq = 0;
+    mapq = (int) (mapq * (1. - a->frac_rep) + .499);
+    return mapq;
+}
+
+static inline int o_infer_bw(int l1, int l2, int score, int a, int q, int r) {                               /* :1811-1818 */
+    if (l1 == l2 && l1 * a - score < (q + r - a) << 1) return 0;
+    int w = (int) ((double) ((l1 < l2 ? l1 : l2) * a - score - q) / r + 2.);
+    const int d = l1 > l2 ? l1 - l2 : l2 - l1;
+    if (w < d) w = d;
+    return w;
+}
+
+struct OAln { int flag, rid, mapq, nm, score, sub, is_rev, is_alt, alt_sc; int64_t pos; std::vector<uint32_t> cigar; std::string md; };
+
+static OAln reg2aln(const bm2_index_desc *x, const bm2_mem_opt_t *opt, int l_query, const uint8_t *query, const bm2_alnreg_t *ar) {   /* :1732-1805 */
+    OAln a; a.flag = 0; a.rid = -1; a.mapq = 0; a.nm = 0; a.score = 0; a.sub = 0; a.is_rev = 0; a.is_alt = 0; a.alt_sc = 0; a.pos = -1;
+    if (ar == 0 || ar->rb < 0 || ar->re < 0) { a.flag |= 0x4; return a; }
+    const int qb = ar->qb, qe = ar->qe;
+    const int64_t rb = ar->rb, re = ar->re;
+    a.mapq = ar->secondary < 0 ? approx_mapq_se(opt, ar) : 0;
+    if (ar->secondary >= 0) a.flag |= 0x100;
+    int tmp = o_infer_bw(qe - qb, (int) (re - rb), ar->truesc, opt->a, opt->o_del, opt->e_del);
+    int w2 = o_infer_bw(qe - qb, (int) (re - rb), ar->truesc, opt->a, opt->o_ins, opt->e_ins);
+    w2 = w2 > tmp ? w2 : tmp;
+    if (w2 > opt->w) w2 = w2 < ar->w ? w2 : ar->w;
+    int i = 0, score = 0, NM = -1, last_sc = -(1 << 30);
+    do {
+        w2 = w2 < opt->w << 2 ? w2 : opt->w << 2;
+        gen_cigar_one(x, opt, w2, qe - qb, query + qb, rb, re, &score, a.cigar, &NM, a.md);
+        if (score == last_sc || w2 == opt->w << 2) break;
+        last_sc = score;
+        w2 <<= 1;
+    } while (++i < 3 && score < ar->truesc - opt->a);
+    a.nm = NM;
+    const int is_rev = (rb < x->l_pac ? rb : re - 1) >= x->l_pac;
+    int64_t pos = depos(x, rb < x->l_pac ? rb : re - 1);
+    a.is_rev = is_rev;
+    if (!a.cigar.empty()) {                                      /* squeeze out leading or trailing deletions */
+        if ((a.cigar[0] & 0xf) == 2) { pos += a.cigar[0] >> 4; a.cigar.erase(a.cigar.begin()); }
+        else if ((a.cigar.back() & 0xf) == 2) a.cigar.pop_back();
+    }
+    if (qb != 0 || qe != l_query) {
+        const int clip5 = is_rev ? l_query - qe : qb, clip3 = is_rev ? qb : l_query - qe;
+        if (clip5) a.cigar.insert(a.cigar.begin(), (uint32_t) clip5 << 4 | 3);
+        if (clip3) a.cigar.push_back((uint32_t) clip3 << 4 | 3);
+    }
+    a.rid = pos2rid(x, pos);
+    a.pos = pos - x->ann_offset[a.rid];
+    a.score = ar->score; a.sub = ar->sub > ar->csub ? ar->sub : ar->csub;
+    a.is_alt = reg_is_alt(*ar); a.alt_sc = ar->alt_sc;
+    return a;
+}
+
+extern "C" int bm2o_sam_se(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, bm2_alnreg_t *regs, const int64_t *read_off,
+                           int64_t id_base, bm2o_aln **alns_out, int64_t *n_alns, uint32_t **cigar_out, int64_t *n_ops_out, char **md_out, int64_t *n_md_out)
+{
+    std::vector<bm2o_aln> out; std::vector<uint32_t> ops; std::string mds;
+    auto push = [&](int read, const OAln &q) {
+        bm2o_aln o; o.read = read; o.flag = q.flag; o.rid = q.rid; o.mapq = q.mapq; o.nm = q.nm; o.score = q.score; o.sub = q.sub; o.is_rev = q.is_rev;
+        o.is_alt = q.is_alt; o.alt_sc = q.alt_sc; o.n_cigar = (int32_t) q.cigar.size(); o.n_md = (int32_t) q.md.size() + 1; o.pos = q.pos;
+        o.cigar_off = (int64_t) ops.size(); o.md_off = (int64_t) mds.size();
+        ops.insert(ops.end(), q.cigar.begin(), q.cigar.end()); mds += q.md; mds.push_back('\0');
+        out.push_back(o);
+    };
+    for (int r = 0; r < reads->n_reads; ++r) {
+        bm2_alnreg_t *a = regs + read_off[r];
+        const int n = (int) (read_off[r + 1] - read_off[r]);
+        const uint8_t *query = reads->codes + reads->offsets[r];
+        const int l_query = (int) (reads->offsets[r + 1] - reads->offsets[r]);
+        mark_primary_se(opt, n, a, id_base + r);
+        /* mem_reg2sam (:1521-1577), extra_flag = 0, no mate */
+        std::vector<OAln> aa;
+        int l = 0;
+        for (int k = 0; k < n; ++k) {
+            const bm2_alnreg_t *p = &a[k];
+            if (p->score < opt->T) continue;
+            if (p->secondary >= 0 && (reg_is_alt(*p) || !(opt->flag & 0x8))) continue;                       /* MEM_F_ALL */
+            if (p->secondary >= 0 && p->secondary < INT_MAX && p->score < a[p->secondary].score * opt->drop_ratio) continue;
+            OAln q = reg2aln(x, opt, l_query, query, p);
+            if (p->secondary >= 0) q.sub = -1;
+            if (l && p->secondary < 0) q.flag |= (opt->flag & 0x10) ? 0x10000 : 0x800;                       /* MEM_F_NO_MULTI */
+            if (!(opt->flag & 0x1000) && l && !reg_is_alt(*p) && q.mapq > aa[0].mapq) q.mapq = aa[0].mapq;    /* MEM_F_KEEP_SUPP_MAPQ */
+            aa.push_back(q);
+            ++l;
+        }
+        if (aa.empty()) push(r, reg2aln(x, opt, l_query, query, 0));
+        else for (const OAln &q : aa) push(r, q);
+    }
+    const size_t n = out.size();
+    *alns_out = (bm2o_aln *) malloc(sizeof(bm2o_aln) * (n + 1)); memcpy(*alns_out, out.data(), sizeof(bm2o_aln) * n);
+    *cigar_out = (uint32_t *) malloc(4 * (ops.size() + 1)); memcpy(*cigar_out, ops.data(), 4 * ops.size());
+    *md_out = (char *) malloc(mds.size() + 1); memcpy(*md_out, mds.data(), mds.size());
+    *n_alns = (int64_t) n; *n_ops_out = (int64_t) ops.size(); *n_md_out = (int64_t) mds.size();
+    return 0;
 }

@@ -70,6 +70,17 @@ void bm2o_pestat(const bm2_mem_opt_t *opt, int64_t l_pac, int32_t n_reads, const
 int bm2o_matesw(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const int32_t *pes_lh, const bm2_alnreg_t *a, int32_t l_ms, const uint8_t *ms,
                 bm2_alnreg_t *ma, int32_t *n_ma);
 
+/* Single-end SAM stage (worker_sam without MEM_F_PE, src/bwamem.cpp:1330-1336): mem_mark_primary_se (:1420-1468) on the read's regs
+ * (modified in place, id = id_base + read index), then the records mem_reg2sam (:1521-1577) writes - mem_reg2aln (:1732-1805) per kept
+ * region: MAPQ (mem_approx_mapq_se :1470-1494), CIGAR with clipping, NM, MD, POS.  One bm2o_aln per output line (an unmapped read
+ * gives one with rid = -1); cigar ops as len << 4 | op with op 3 = clip (printed S or H); md NUL-terminated. */
+typedef struct bm2o_aln {
+    int32_t read, flag, rid, mapq, nm, score, sub, is_rev, is_alt, alt_sc, n_cigar, n_md;
+    int64_t pos, cigar_off, md_off;
+} bm2o_aln;
+int bm2o_sam_se(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, bm2_alnreg_t *regs, const int64_t *read_off,
+                int64_t id_base, bm2o_aln **alns, int64_t *n_alns, uint32_t **cigar, int64_t *n_ops, char **md, int64_t *n_md);
+
 #ifdef __cplusplus
 }
 #endif
