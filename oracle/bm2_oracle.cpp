@@ -1620,3 +1620,256 @@ extern "C" int bm2o_sam_se(const bm2_index_desc *x, const bm2_mem_opt_t *opt, co
     *n_alns = (int64_t) n; *n_ops_out = (int64_t) ops.size(); *n_md_out = (int64_t) mds.size();
     return 0;
 }
+
+
+/* ================================================================================================
+ * SAM stage, paired-end: mem_pair (src/bwamem_pair.cpp:285-346), mem_sam_pe (:353-552), mem_reg2sam with a mate, and the
+ * columns of mem_aln2sam (src/bwamem.cpp:1592-1730).
+ * ============================================================================================== */
+namespace {
+struct P64 { uint64_t x, y; };
+inline bool p64_lt(const P64 &a, const P64 &b) { return a.x < b.x || (a.x == b.x && a.y < b.y); }
+inline int raw_mapq(int diff, int a) { return (int) (6.02 * diff / a + .499); }
+inline int get_rlen(const std::vector<uint32_t> &c) { int l = 0; for (uint32_t v : c) { const int op = v & 0xf; if (op == 0 || op == 2) l += v >> 4; } return l; }
+
+int o_mem_pair(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const int32_t *lh, const double *as, const std::vector<bm2_alnreg_t> a[2], int id,
+               int *sub, int *n_sub, int z[2], const int n_pri[2])
+{
+    std::vector<P64> v, u;
+    const int64_t l_pac = x->l_pac;
+    for (int r = 0; r < 2; ++r)
+        for (int i = 0; i < n_pri[r]; ++i) {
+            const bm2_alnreg_t *e = &a[r][i];
+            P64 key;
+            key.x = (uint64_t) (e->rb < l_pac ? e->rb : (l_pac << 1) - 1 - e->rb);
+            key.x = (uint64_t) e->rid << 32 | (key.x - (uint64_t) x->ann_offset[e->rid]);
+            key.y = (uint64_t) e->score << 32 | (uint64_t) (i << 2 | (e->rb >= l_pac) << 1 | r);
+            v.push_back(key);
+        }
+    std::sort(v.begin(), v.end(), p64_lt);
+    int y[4] = { -1, -1, -1, -1 };
+    for (int i = 0; i < (int) v.size(); ++i) {
+        for (int r = 0; r < 2; ++r) {
+            const int dir = r << 1 | (int) (v[i].y >> 1 & 1);
+            if (lh[3 * dir + 2]) continue;
+            const int which = r << 1 | (int) ((v[i].y & 1) ^ 1);
+            if (y[which] < 0) continue;
+            for (int k = y[which]; k >= 0; --k) {
+                if ((int) (v[k].y & 3) != which) continue;
+                const int64_t dist = (int64_t) v[i].x - (int64_t) v[k].x;
+                if (dist > lh[3 * dir + 1]) break;
+                if (dist < lh[3 * dir]) continue;
+                const double ns = (dist - as[2 * dir]) / as[2 * dir + 1];
+                int q = (int) ((v[i].y >> 32) + (v[k].y >> 32) + .721 * log(2. * erfc(fabs(ns) * M_SQRT1_2)) * opt->a + .499);
+                if (q < 0) q = 0;
+                P64 p;
+                p.y = (uint64_t) k << 32 | (uint64_t) i;
+                p.x = (uint64_t) q << 32 | (o_hash_64(p.y ^ (uint64_t) (int64_t) (id << 8)) & 0xffffffffU);
+                u.push_back(p);
+            }
+        }
+        y[v[i].y & 3] = i;
+    }
+    int ret;
+    if (!u.empty()) {
+        int tmp = opt->a + opt->b;
+        tmp = tmp > opt->o_del + opt->e_del ? tmp : opt->o_del + opt->e_del;
+        tmp = tmp > opt->o_ins + opt->e_ins ? tmp : opt->o_ins + opt->e_ins;
+        std::sort(u.begin(), u.end(), p64_lt);
+        const int i = (int) (u.back().y >> 32), k = (int) (u.back().y << 32 >> 32);
+        z[v[i].y & 1] = (int) (v[i].y << 32 >> 34);
+        z[v[k].y & 1] = (int) (v[k].y << 32 >> 34);
+        ret = (int) (u.back().x >> 32);
+        *sub = u.size() > 1 ? (int) (u[u.size() - 2].x >> 32) : 0;
+        *n_sub = 0;
+        for (long j = (long) u.size() - 2; j >= 0; --j) if (*sub - (int) (u[j].x >> 32) <= tmp) ++*n_sub;
+    } else { ret = 0; *sub = 0; *n_sub = 0; }
+    return ret;
+}
+
+/* the records mem_reg2sam keeps for one read (:1534-1560) */
+void reg2sam_list(const bm2_index_desc *x, const bm2_mem_opt_t *opt, int l_query, const uint8_t *query, const std::vector<bm2_alnreg_t> &a, int extra_flag,
+                  std::vector<OAln> &aa)
+{
+    aa.clear();
+    int l = 0;
+    for (size_t k = 0; k < a.size(); ++k) {
+        const bm2_alnreg_t *p = &a[k];
+        if (p->score < opt->T) continue;
+        if (p->secondary >= 0 && (reg_is_alt(*p) || !(opt->flag & 0x8))) continue;
+        if (p->secondary >= 0 && p->secondary < INT_MAX && p->score < a[p->secondary].score * opt->drop_ratio) continue;
+        OAln q = reg2aln(x, opt, l_query, query, p);
+        q.flag |= extra_flag;
+        if (p->secondary >= 0) q.sub = -1;
+        if (l && p->secondary < 0) q.flag |= (opt->flag & 0x10) ? 0x10000 : 0x800;
+        if (!(opt->flag & 0x1000) && l && !reg_is_alt(*p) && q.mapq > aa[0].mapq) q.mapq = aa[0].mapq;
+        aa.push_back(q);
+        ++l;
+    }
+    if (aa.empty()) { OAln t = reg2aln(x, opt, l_query, query, 0); t.flag |= extra_flag; aa.push_back(t); }
+}
+
+struct SamOut { std::vector<bm2o_samrec> recs; std::vector<uint32_t> ops; std::string mds; };
+
+/* the columns of mem_aln2sam for list[which] with mate m_ (may be null) */
+void aln2sam(const bm2_mem_opt_t *opt, int read, const std::vector<OAln> &list, int which, const OAln *m_, SamOut &o)
+{
+    OAln p = list[which], mt; const OAln *m = 0;
+    if (m_) { mt = *m_; m = &mt; }
+    p.flag |= m ? 0x1 : 0;
+    p.flag |= p.rid < 0 ? 0x4 : 0;
+    p.flag |= m && m->rid < 0 ? 0x8 : 0;
+    if (p.rid < 0 && m && m->rid >= 0) { p.rid = m->rid; p.pos = m->pos; p.is_rev = m->is_rev; p.cigar.clear(); }
+    if (m && m->rid < 0 && p.rid >= 0) { mt.rid = p.rid; mt.pos = p.pos; mt.is_rev = p.is_rev; mt.cigar.clear(); }
+    p.flag |= p.is_rev ? 0x10 : 0;
+    p.flag |= m && m->is_rev ? 0x20 : 0;
+    bm2o_samrec r; memset(&r, 0, sizeof(r));
+    r.read = read; r.flag = (p.flag & 0xffff) | (p.flag & 0x10000 ? 0x100 : 0);
+    r.rid = p.rid; r.pos = p.rid >= 0 ? p.pos + 1 : 0; r.mapq = p.rid >= 0 ? p.mapq : 0;
+    r.cigar_off = (int64_t) o.ops.size(); r.md_off = (int64_t) o.mds.size();
+    if (p.rid >= 0)
+        for (uint32_t v : p.cigar) {
+            int c = v & 0xf;
+            if (!(opt->flag & 0x200) && !p.is_alt && (c == 3 || c == 4)) c = which ? 4 : 3;
+            o.ops.push_back((v >> 4) << 4 | (uint32_t) c);
+        }
+    r.n_cigar = (int32_t) (o.ops.size() - (size_t) r.cigar_off);
+    r.rnext = -1; r.pnext = 0; r.tlen = 0;
+    if (m && m->rid >= 0) {
+        r.rnext = m->rid; r.pnext = m->pos + 1;
+        if (p.rid == m->rid) {
+            const int64_t p0 = p.pos + (p.is_rev ? get_rlen(p.cigar) - 1 : 0), p1 = m->pos + (m->is_rev ? get_rlen(m->cigar) - 1 : 0);
+            if (m->cigar.empty() || p.cigar.empty()) r.tlen = 0;
+            else r.tlen = -(p0 - p1 + (p0 > p1 ? 1 : p0 < p1 ? -1 : 0));
+        }
+    }
+    if (!p.cigar.empty()) { r.nm = p.nm; o.mds += p.md; }          /* NM / MD only with a cigar (p.n_cigar) */
+    o.mds.push_back('\0');
+    r.n_md = (int32_t) (o.mds.size() - (size_t) r.md_off);
+    r.score = p.score; r.sub = p.sub;
+    if (p.cigar.empty()) r.n_cigar = 0;
+    r.tlen_valid = 1;
+    o.recs.push_back(r);
+}
+}  // namespace
+
+extern "C" int bm2o_sam_pe(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off,
+                           const int32_t *lh, const double *as, int64_t id_base, bm2o_samrec **recs_out, int64_t *n_recs, uint32_t **cigar_out,
+                           int64_t *n_ops_out, char **md_out, int64_t *n_md_out)
+{
+    if (opt->flag & 0x800) return 2;                          /* MEM_F_PRIMARY5: not restated */
+    SamOut so;
+    for (int pr = 0; pr < reads->n_reads >> 1; ++pr) {
+        const int id = (int) (id_base + pr);
+        std::vector<bm2_alnreg_t> a[2];
+        const uint8_t *seq[2]; int l_seq[2];
+        for (int i = 0; i < 2; ++i) {
+            const int r = 2 * pr + i;
+            a[i].assign(regs + read_off[r], regs + read_off[r + 1]);
+            seq[i] = reads->codes + reads->offsets[r]; l_seq[i] = (int) (reads->offsets[r + 1] - reads->offsets[r]);
+        }
+        int extra_flag = 1, n_pri[2], z[2] = { 0, 0 }, o = 0, subo = 0, n_sub = 0;
+        if (!(opt->flag & 0x20)) {                            /* !MEM_F_NO_RESCUE: mate SW for the best alignments (:378-412) */
+            std::vector<bm2_alnreg_t> b[2];
+            for (int i = 0; i < 2; ++i)
+                for (size_t j = 0; j < a[i].size(); ++j)
+                    if (a[i][j].score >= a[i][0].score - opt->pen_unpaired) b[i].push_back(a[i][j]);
+            for (int i = 0; i < 2; ++i)
+                for (size_t j = 0; j < b[i].size() && (int) j < opt->max_matesw; ++j) {
+                    std::vector<bm2_alnreg_t> &ma = a[!i];
+                    int32_t nm = (int32_t) ma.size();
+                    ma.resize((size_t) nm + 4);
+                    bm2o_matesw(x, opt, lh, &b[i][j], l_seq[!i], seq[!i], ma.data(), &nm);
+                    ma.resize((size_t) nm);
+                }
+        }
+        n_pri[0] = mark_primary_se(opt, (int) a[0].size(), a[0].data(), (int64_t) id << 1 | 0);
+        n_pri[1] = mark_primary_se(opt, (int) a[1].size(), a[1].data(), (int64_t) id << 1 | 1);
+        bool paired = false;
+        std::vector<OAln> aa[2];
+        OAln h[2];
+        if (!(opt->flag & 0x4) && n_pri[0] && n_pri[1] && (o = o_mem_pair(x, opt, lh, as, a, id, &subo, &n_sub, z, n_pri)) > 0) {   /* !MEM_F_NOPAIRING */
+            int is_multi[2];
+            for (int i = 0; i < 2; ++i) {
+                int j;
+                for (j = 1; j < n_pri[i]; ++j) if (a[i][j].secondary < 0 && a[i][j].score >= opt->T) break;
+                is_multi[i] = j < n_pri[i] ? 1 : 0;
+            }
+            if (!(is_multi[0] || is_multi[1])) {
+                paired = true;
+                int q_pe, q_se[2];
+                const int score_un = a[0][0].score + a[1][0].score - opt->pen_unpaired;
+                subo = subo > score_un ? subo : score_un;
+                q_pe = raw_mapq(o - subo, opt->a);
+                if (n_sub > 0) q_pe -= (int) (4.343 * log(n_sub + 1) + .499);
+                if (q_pe < 0) q_pe = 0;
+                if (q_pe > 60) q_pe = 60;
+                q_pe = (int) (q_pe * (1. - .5 * (a[0][0].frac_rep + a[1][0].frac_rep)) + .499);
+                if (o > score_un) {
+                    bm2_alnreg_t *c[2] = { &a[0][z[0]], &a[1][z[1]] };
+                    for (int i = 0; i < 2; ++i) {
+                        if (c[i]->secondary >= 0) { c[i]->sub = a[i][c[i]->secondary].score; c[i]->secondary = -2; }
+                        q_se[i] = approx_mapq_se(opt, c[i]);
+                    }
+                    q_se[0] = q_se[0] > q_pe ? q_se[0] : q_pe < q_se[0] + 40 ? q_pe : q_se[0] + 40;
+                    q_se[1] = q_se[1] > q_pe ? q_se[1] : q_pe < q_se[1] + 40 ? q_pe : q_se[1] + 40;
+                    extra_flag |= 2;
+                    q_se[0] = q_se[0] < raw_mapq(c[0]->score - c[0]->csub, opt->a) ? q_se[0] : raw_mapq(c[0]->score - c[0]->csub, opt->a);
+                    q_se[1] = q_se[1] < raw_mapq(c[1]->score - c[1]->csub, opt->a) ? q_se[1] : raw_mapq(c[1]->score - c[1]->csub, opt->a);
+                } else {
+                    z[0] = z[1] = 0;
+                    q_se[0] = approx_mapq_se(opt, &a[0][0]);
+                    q_se[1] = approx_mapq_se(opt, &a[1][0]);
+                }
+                for (int i = 0; i < 2; ++i) {
+                    const int k = a[i][z[i]].secondary_all;
+                    if (k >= 0 && k < n_pri[i]) {
+                        for (size_t j = 0; j < a[i].size(); ++j)
+                            if (a[i][j].secondary_all == k || (int) j == k) a[i][j].secondary_all = z[i];
+                        a[i][z[i]].secondary_all = -1;
+                    }
+                }
+                for (int i = 0; i < 2; ++i) {
+                    h[i] = reg2aln(x, opt, l_seq[i], seq[i], &a[i][z[i]]);
+                    h[i].mapq = q_se[i];
+                    h[i].flag |= 0x40 << i | extra_flag;
+                    aa[i].push_back(h[i]);
+                    if (n_pri[i] < (int) a[i].size()) {
+                        const bm2_alnreg_t *p = &a[i][n_pri[i]];
+                        if (p->score < opt->T || p->secondary >= 0 || !reg_is_alt(*p)) continue;
+                        OAln g = reg2aln(x, opt, l_seq[i], seq[i], p);
+                        g.flag |= 0x800 | 0x40 << i | extra_flag;
+                        aa[i].push_back(g);
+                    }
+                }
+                for (int i = 0; i < 2; ++i)
+                    for (size_t k = 0; k < aa[i].size(); ++k) aln2sam(opt, 2 * pr + i, aa[i], (int) k, &h[!i], so);
+            }
+        }
+        if (!paired) {                                        /* no_pairing (:523-551) */
+            for (int i = 0; i < 2; ++i) {
+                int which = -1;
+                if (!a[i].empty()) {
+                    if (a[i][0].score >= opt->T) which = 0;
+                    else if (n_pri[i] < (int) a[i].size() && a[i][n_pri[i]].score >= opt->T) which = n_pri[i];
+                }
+                h[i] = reg2aln(x, opt, l_seq[i], seq[i], which >= 0 ? &a[i][which] : 0);
+            }
+            if (!(opt->flag & 0x4) && h[0].rid == h[1].rid && h[0].rid >= 0) {
+                int64_t dist;
+                const int d = o_infer_dir(x->l_pac, a[0][0].rb, a[1][0].rb, &dist);
+                if (!lh[3 * d + 2] && dist >= lh[3 * d] && dist <= lh[3 * d + 1]) extra_flag |= 2;
+            }
+            for (int i = 0; i < 2; ++i) {
+                reg2sam_list(x, opt, l_seq[i], seq[i], a[i], (i == 0 ? 0x41 : 0x81) | extra_flag, aa[i]);
+                for (size_t k = 0; k < aa[i].size(); ++k) aln2sam(opt, 2 * pr + i, aa[i], (int) k, &h[!i], so);
+            }
+        }
+    }
+    const size_t n = so.recs.size();
+    *recs_out = (bm2o_samrec *) malloc(sizeof(bm2o_samrec) * (n + 1)); memcpy(*recs_out, so.recs.data(), sizeof(bm2o_samrec) * n);
+    *cigar_out = (uint32_t *) malloc(4 * (so.ops.size() + 1)); memcpy(*cigar_out, so.ops.data(), 4 * so.ops.size());
+    *md_out = (char *) malloc(so.mds.size() + 1); memcpy(*md_out, so.mds.data(), so.mds.size());
+    *n_recs = (int64_t) n; *n_ops_out = (int64_t) so.ops.size(); *n_md_out = (int64_t) so.mds.size();
+    return 0;
+}

@@ -81,6 +81,19 @@ typedef struct bm2o_aln {
 int bm2o_sam_se(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, bm2_alnreg_t *regs, const int64_t *read_off,
                 int64_t id_base, bm2o_aln **alns, int64_t *n_alns, uint32_t **cigar, int64_t *n_ops, char **md, int64_t *n_md);
 
+/* Paired-end SAM stage == mem_sam_pe (src/bwamem_pair.cpp:353-552, MATE_SORT == 0) per read pair: mate rescue (mem_matesw), mem_mark_primary_se,
+ * mem_pair (:285-346), the paired / unpaired MAPQ logic, and the columns mem_aln2sam (src/bwamem.cpp:1592-1730) prints.  pes_lh[12] = low, high,
+ * failed; pes_as[8] = avg, std (mem_pestat's result for the chunk).  regs of pair p: reads 2p and 2p+1; modified in place is not visible to the
+ * caller (copies).  One bm2o_samrec per SAM line in output order; cigar ops are len << 4 | op with op an index into "MIDSH" as printed.
+ * Not restated: XA / SA / MC / pa tags, -5 (MEM_F_PRIMARY5), -C. */
+typedef struct bm2o_samrec {
+    int32_t read, flag, rid, mapq, rnext, tlen_valid, nm, score, sub, n_cigar, n_md, _pad;   /* rid / rnext: -1 = '*'; sub < 0: no XS; nm valid iff n_cigar */
+    int64_t pos, pnext, tlen, cigar_off, md_off;                                           /* pos / pnext 1-based as printed */
+} bm2o_samrec;
+int bm2o_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off,
+                const int32_t *pes_lh, const double *pes_as, int64_t id_base, bm2o_samrec **recs, int64_t *n_recs, uint32_t **cigar, int64_t *n_ops,
+                char **md, int64_t *n_md);
+
 #ifdef __cplusplus
 }
 #endif
