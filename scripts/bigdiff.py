@@ -38,6 +38,15 @@ def main():
     bad = ol.regs_equal_to_dump(regs, ro, rr, roff)
     e, eo = el.seed_chain_extend(idx, opt, codes, offs)
     t3 = time.time()
+    # SAM level: the oracle's mate rescue + pairing + MAPQ + CIGAR/NM/MD against the reference's SAM lines
+    import test_oracle_sam_pe as tp
+    opt2 = opt_from_cli(capi, args); opt2.flag |= 0x2
+    lh, as_ = tp._pestat(capi, idx, opt2, reads, regs, ro)
+    recs, cig, md = tp.oracle_sam_pe(capi, idx, opt2, codes, offs, regs, ro, lh, as_)
+    names = [l.split()[1] for i, l in enumerate(open(work + "/ref.fa.ann")) if i % 2 == 1]
+    got = tp.fields(recs, cig, md, names); want = tp.parse_sam(open(work + "/o.sam"))
+    sam_bad = sum(1 for g, w in zip(got, want) if g != w) + abs(len(got) - len(want))
+    print(f"SAM lines {len(want)}, differing {sam_bad}")
     print(f"{mbp} Mbp, {2 * pairs} reads, options {args}: {len(rr)} regs; reference {t1 - t0:.0f}s oracle {t2 - t1:.0f}s emulation {t3 - t2:.0f}s; "
           f"oracle vs reference: {len(bad)} differing reads {bad[:5]}; device logic == oracle: {e.tobytes() == regs.tobytes() and np.array_equal(eo, ro)}")
 
