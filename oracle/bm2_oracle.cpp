@@ -1537,7 +1537,7 @@ static inline int o_infer_bw(int l1, int l2, int score, int a, int q, int r) {  
     return w;
 }
 
-struct OAln { int flag, rid, mapq, nm, score, sub, is_rev, is_alt, alt_sc; int64_t pos; std::vector<uint32_t> cigar; std::string md; };
+struct OAln { int flag, rid, mapq, nm, score, sub, is_rev, is_alt, alt_sc; int64_t pos; std::vector<uint32_t> cigar; std::string md, XA; };
 
 static OAln reg2aln(const bm2_index_desc *x, const bm2_mem_opt_t *opt, int l_query, const uint8_t *query, const bm2_alnreg_t *ar) {   /* :1732-1805 */
     OAln a; a.flag = 0; a.rid = -1; a.mapq = 0; a.nm = 0; a.score = 0; a.sub = 0; a.is_rev = 0; a.is_alt = 0; a.alt_sc = 0; a.pos = -1;
@@ -1687,11 +1687,16 @@ int o_mem_pair(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const int32_t 
     return ret;
 }
 
+void gen_alt(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const char *const *names, int l_query, const uint8_t *query, const std::vector<bm2_alnreg_t> &a,
+             std::vector<std::string> &XA);
+
 /* the records mem_reg2sam keeps for one read (:1534-1560) */
 void reg2sam_list(const bm2_index_desc *x, const bm2_mem_opt_t *opt, int l_query, const uint8_t *query, const std::vector<bm2_alnreg_t> &a, int extra_flag,
-                  std::vector<OAln> &aa)
+                  std::vector<OAln> &aa, const char *const *names = 0)
 {
     aa.clear();
+    std::vector<std::string> XA;
+    if (names && !(opt->flag & 0x8)) gen_alt(x, opt, names, l_query, query, a, XA);
     int l = 0;
     for (size_t k = 0; k < a.size(); ++k) {
         const bm2_alnreg_t *p = &a[k];
@@ -1699,6 +1704,7 @@ void reg2sam_list(const bm2_index_desc *x, const bm2_mem_opt_t *opt, int l_query
         if (p->secondary >= 0 && (reg_is_alt(*p) || !(opt->flag & 0x8))) continue;
         if (p->secondary >= 0 && p->secondary < INT_MAX && p->score < a[p->secondary].score * opt->drop_ratio) continue;
         OAln q = reg2aln(x, opt, l_query, query, p);
+        if (!XA.empty()) q.XA = XA[k];
         q.flag |= extra_flag;
         if (p->secondary >= 0) q.sub = -1;
         if (l && p->secondary < 0) q.flag |= (opt->flag & 0x10) ? 0x10000 : 0x800;
@@ -1710,9 +1716,44 @@ void reg2sam_list(const bm2_index_desc *x, const bm2_mem_opt_t *opt, int l_query
 }
 
 struct SamOut { std::vector<bm2o_samrec> recs; std::vector<uint32_t> ops; std::string mds; };
+/* optional: the SAM text of every line after QNAME (names of the contigs, the read's codes and qualities) */
+struct TextCtx { const char *const *names; const uint8_t *seq; const char *qual; int l_seq; std::string *text; };
+
+/* mem_gen_alt (src/bwamem_extra.cpp:130-183): the XA string of every primary; call after mem_mark_primary_se */
+void gen_alt(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const char *const *names, int l_query, const uint8_t *query, const std::vector<bm2_alnreg_t> &a,
+             std::vector<std::string> &XA)
+{
+    const int n = (int) a.size();
+    XA.assign((size_t) n, std::string());
+    std::vector<int> cnt((size_t) n, 0); std::vector<char> has_alt((size_t) n, 0);
+    const double xa_drop = opt->XA_drop_ratio;             /* get_pri_idx takes the float option as a double (src/bwamem_extra.cpp:122) */
+    auto pri_idx = [&](int i) { const int k = a[i].secondary_all; return (k >= 0 && a[i].score >= a[k].score * xa_drop) ? k : -1; };
+    int tot = 0;
+    for (int i = 0; i < n; ++i) { const int r = pri_idx(i); if (r >= 0) { ++cnt[r]; ++tot; if (reg_is_alt(a[i])) has_alt[r] = 1; } }
+    if (tot == 0) return;
+    for (int i = 0; i < n; ++i) {
+        const int r = pri_idx(i);
+        if (r < 0) continue;
+        if (cnt[r] > opt->max_XA_hits_alt || (!has_alt[r] && cnt[r] > opt->max_XA_hits)) continue;
+        const OAln t = reg2aln(x, opt, l_query, query, &a[i]);
+        std::string e = names[t.rid]; e += ','; e += "+-"[t.is_rev]; e += std::to_string(t.pos + 1); e += ',';
+        for (uint32_t v : t.cigar) { e += std::to_string(v >> 4); e += "MIDSHN"[v & 0xf]; }
+        e += ','; e += std::to_string(t.nm); e += ';';
+        XA[r] += e;
+    }
+}
+
+void cigar_text(const bm2_mem_opt_t *opt, const OAln &p, int which, std::string &t) {               /* add_cigar (src/bwamem.cpp:1579-1590) */
+    if (p.cigar.empty()) { t += '*'; return; }
+    for (uint32_t v : p.cigar) {
+        int c = v & 0xf;
+        if (!(opt->flag & 0x200) && !p.is_alt && (c == 3 || c == 4)) c = which ? 4 : 3;
+        t += std::to_string(v >> 4); t += "MIDSH"[c];
+    }
+}
 
 /* the columns of mem_aln2sam for list[which] with mate m_ (may be null) */
-void aln2sam(const bm2_mem_opt_t *opt, int read, const std::vector<OAln> &list, int which, const OAln *m_, SamOut &o)
+void aln2sam(const bm2_mem_opt_t *opt, int read, const std::vector<OAln> &list, int which, const OAln *m_, SamOut &o, const TextCtx *tc = 0)
 {
     OAln p = list[which], mt; const OAln *m = 0;
     if (m_) { mt = *m_; m = &mt; }
@@ -1750,15 +1791,66 @@ void aln2sam(const bm2_mem_opt_t *opt, int read, const std::vector<OAln> &list, 
     if (p.cigar.empty()) r.n_cigar = 0;
     r.tlen_valid = 1;
     o.recs.push_back(r);
+    if (!tc) return;
+    /* the line after QNAME (src/bwamem.cpp:1614-1729) */
+    std::string &t = *tc->text;
+    t += std::to_string(r.flag); t += '\t';
+    if (p.rid >= 0) {
+        t += tc->names[p.rid]; t += '\t'; t += std::to_string(p.pos + 1); t += '\t'; t += std::to_string(p.mapq); t += '\t';
+        cigar_text(opt, p, which, t);
+    } else t += "*\t0\t0\t*";
+    t += '\t';
+    if (m && m->rid >= 0) {
+        if (p.rid == m->rid) t += '='; else t += tc->names[m->rid];
+        t += '\t'; t += std::to_string(m->pos + 1); t += '\t';
+        if (p.rid == m->rid) t += std::to_string(r.tlen); else t += '0';
+    } else t += "*\t0\t0";
+    t += '\t';
+    if (r.flag & 0x100) t += "*\t*";
+    else {
+        int qb = 0, qe = tc->l_seq;
+        const bool trim = !p.cigar.empty() && which && !(opt->flag & 0x200) && !p.is_alt;
+        auto is_clip = [](uint32_t v) { return (v & 0xf) == 3 || (v & 0xf) == 4; };
+        if (!p.is_rev) {
+            if (trim) { if (is_clip(p.cigar[0])) qb += p.cigar[0] >> 4; if (is_clip(p.cigar.back())) qe -= p.cigar.back() >> 4; }
+            for (int i = qb; i < qe; ++i) t += "ACGTN"[tc->seq[i]];
+            t += '\t';
+            if (tc->qual) t.append(tc->qual + qb, (size_t) (qe - qb)); else t += '*';
+        } else {
+            if (trim) { if (is_clip(p.cigar[0])) qe -= p.cigar[0] >> 4; if (is_clip(p.cigar.back())) qb += p.cigar.back() >> 4; }
+            for (int i = qe - 1; i >= qb; --i) t += "TGCAN"[tc->seq[i]];
+            t += '\t';
+            if (tc->qual) { for (int i = qe - 1; i >= qb; --i) t += tc->qual[i]; } else t += '*';
+        }
+    }
+    if (!p.cigar.empty()) { t += "\tNM:i:"; t += std::to_string(p.nm); t += "\tMD:Z:"; t += p.md; }
+    if (m && !m->cigar.empty()) { t += "\tMC:Z:"; cigar_text(opt, *m, which, t); }
+    if (p.score >= 0) { t += "\tAS:i:"; t += std::to_string(p.score); }
+    if (p.sub >= 0) { t += "\tXS:i:"; t += std::to_string(p.sub); }
+    if (!(p.flag & 0x100)) {
+        size_t i;
+        for (i = 0; i < list.size(); ++i) if ((int) i != which && !(list[i].flag & 0x100)) break;
+        if (i < list.size()) {
+            t += "\tSA:Z:";
+            for (i = 0; i < list.size(); ++i) {
+                const OAln &q = list[i];
+                if ((int) i == which || (q.flag & 0x100)) continue;
+                t += tc->names[q.rid]; t += ','; t += std::to_string(q.pos + 1); t += ','; t += "+-"[q.is_rev]; t += ',';
+                for (uint32_t v : q.cigar) { t += std::to_string(v >> 4); t += "MIDSH"[v & 0xf]; }
+                t += ','; t += std::to_string(q.mapq); t += ','; t += std::to_string(q.nm); t += ';';
+            }
+        }
+        if (p.alt_sc > 0) { char buf[64]; snprintf(buf, sizeof(buf), "\tpa:f:%.3f", (double) p.score / p.alt_sc); t += buf; }
+    }
+    if (!p.XA.empty()) { t += "\tXA:Z:"; t += p.XA; }
+    t += '\n';
 }
 }  // namespace
 
-extern "C" int bm2o_sam_pe(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off,
-                           const int32_t *lh, const double *as, int64_t id_base, bm2o_samrec **recs_out, int64_t *n_recs, uint32_t **cigar_out,
-                           int64_t *n_ops_out, char **md_out, int64_t *n_md_out)
+static int sam_pe_core(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off,
+                       const int32_t *lh, const double *as, int64_t id_base, const char *const *names, const char *quals, std::string *text, SamOut &so)
 {
     if (opt->flag & 0x800) return 2;                          /* MEM_F_PRIMARY5: not restated */
-    SamOut so;
     for (int pr = 0; pr < reads->n_reads >> 1; ++pr) {
         const int id = (int) (id_base + pr);
         std::vector<bm2_alnreg_t> a[2];
@@ -1829,21 +1921,27 @@ extern "C" int bm2o_sam_pe(const bm2_index_desc *x, const bm2_mem_opt_t *opt, co
                         a[i][z[i]].secondary_all = -1;
                     }
                 }
+                std::vector<std::string> XA[2];
+                if (names && !(opt->flag & 0x8)) for (int i = 0; i < 2; ++i) gen_alt(x, opt, names, l_seq[i], seq[i], a[i], XA[i]);
                 for (int i = 0; i < 2; ++i) {
                     h[i] = reg2aln(x, opt, l_seq[i], seq[i], &a[i][z[i]]);
                     h[i].mapq = q_se[i];
                     h[i].flag |= 0x40 << i | extra_flag;
+                    if (!XA[i].empty()) h[i].XA = XA[i][z[i]];
                     aa[i].push_back(h[i]);
                     if (n_pri[i] < (int) a[i].size()) {
                         const bm2_alnreg_t *p = &a[i][n_pri[i]];
                         if (p->score < opt->T || p->secondary >= 0 || !reg_is_alt(*p)) continue;
                         OAln g = reg2aln(x, opt, l_seq[i], seq[i], p);
                         g.flag |= 0x800 | 0x40 << i | extra_flag;
+                        if (!XA[i].empty()) g.XA = XA[i][n_pri[i]];
                         aa[i].push_back(g);
                     }
                 }
-                for (int i = 0; i < 2; ++i)
-                    for (size_t k = 0; k < aa[i].size(); ++k) aln2sam(opt, 2 * pr + i, aa[i], (int) k, &h[!i], so);
+                for (int i = 0; i < 2; ++i) {
+                    TextCtx tc = { names, seq[i], quals ? quals + reads->offsets[2 * pr + i] : 0, l_seq[i], text };
+                    for (size_t k = 0; k < aa[i].size(); ++k) aln2sam(opt, 2 * pr + i, aa[i], (int) k, &h[!i], so, text ? &tc : 0);
+                }
             }
         }
         if (!paired) {                                        /* no_pairing (:523-551) */
@@ -1861,15 +1959,40 @@ extern "C" int bm2o_sam_pe(const bm2_index_desc *x, const bm2_mem_opt_t *opt, co
                 if (!lh[3 * d + 2] && dist >= lh[3 * d] && dist <= lh[3 * d + 1]) extra_flag |= 2;
             }
             for (int i = 0; i < 2; ++i) {
-                reg2sam_list(x, opt, l_seq[i], seq[i], a[i], (i == 0 ? 0x41 : 0x81) | extra_flag, aa[i]);
-                for (size_t k = 0; k < aa[i].size(); ++k) aln2sam(opt, 2 * pr + i, aa[i], (int) k, &h[!i], so);
+                reg2sam_list(x, opt, l_seq[i], seq[i], a[i], (i == 0 ? 0x41 : 0x81) | extra_flag, aa[i], names);
+                TextCtx tc = { names, seq[i], quals ? quals + reads->offsets[2 * pr + i] : 0, l_seq[i], text };
+                for (size_t k = 0; k < aa[i].size(); ++k) aln2sam(opt, 2 * pr + i, aa[i], (int) k, &h[!i], so, text ? &tc : 0);
             }
         }
     }
+    return 0;
+}
+
+extern "C" int bm2o_sam_pe(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off,
+                           const int32_t *lh, const double *as, int64_t id_base, bm2o_samrec **recs_out, int64_t *n_recs, uint32_t **cigar_out,
+                           int64_t *n_ops_out, char **md_out, int64_t *n_md_out)
+{
+    SamOut so;
+    const int rc = sam_pe_core(x, opt, reads, regs, read_off, lh, as, id_base, 0, 0, 0, so);
+    if (rc) return rc;
     const size_t n = so.recs.size();
     *recs_out = (bm2o_samrec *) malloc(sizeof(bm2o_samrec) * (n + 1)); memcpy(*recs_out, so.recs.data(), sizeof(bm2o_samrec) * n);
     *cigar_out = (uint32_t *) malloc(4 * (so.ops.size() + 1)); memcpy(*cigar_out, so.ops.data(), 4 * so.ops.size());
     *md_out = (char *) malloc(so.mds.size() + 1); memcpy(*md_out, so.mds.data(), so.mds.size());
     *n_recs = (int64_t) n; *n_ops_out = (int64_t) so.ops.size(); *n_md_out = (int64_t) so.mds.size();
+    return 0;
+}
+
+
+/* The SAM text of mem_sam_pe for every pair: each line from the FLAG column on (QNAME and the header are the caller's), tags NM MD MC AS XS SA pa XA
+ * as mem_aln2sam writes them.  names: contig names; quals: qualities laid out like reads->codes (may be null: '*').  *text is malloc'd. */
+extern "C" int bm2o_sam_pe_text(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const char *quals, const char *const *names,
+                                const bm2_alnreg_t *regs, const int64_t *read_off, const int32_t *lh, const double *as, int64_t id_base, char **text, int64_t *len)
+{
+    SamOut so; std::string t;
+    const int rc = sam_pe_core(x, opt, reads, regs, read_off, lh, as, id_base, names, quals, &t, so);
+    if (rc) return rc;
+    *text = (char *) malloc(t.size() + 1); memcpy(*text, t.data(), t.size()); (*text)[t.size()] = 0;
+    *len = (int64_t) t.size();
     return 0;
 }

@@ -94,6 +94,11 @@ int bm2o_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_r
                 const int32_t *pes_lh, const double *pes_as, int64_t id_base, bm2o_samrec **recs, int64_t *n_recs, uint32_t **cigar, int64_t *n_ops,
                 char **md, int64_t *n_md);
 
+/* The same stage as SAM TEXT: every line of mem_sam_pe from the FLAG column on (tags NM MD MC AS XS SA pa XA as mem_aln2sam writes them, src/bwamem.cpp:1592-1730;
+ * XA by mem_gen_alt, src/bwamem_extra.cpp:130-183).  names: contig names; quals: qualities laid out like reads->codes, or NULL ('*'). */
+int bm2o_sam_pe_text(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const char *quals, const char *const *names,
+                     const bm2_alnreg_t *regs, const int64_t *read_off, const int32_t *pes_lh, const double *pes_as, int64_t id_base, char **text, int64_t *len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,7 +46,11 @@ def main():
     names = [l.split()[1] for i, l in enumerate(open(work + "/ref.fa.ann")) if i % 2 == 1]
     got = tp.fields(recs, cig, md, names); want = tp.parse_sam(open(work + "/o.sam"))
     sam_bad = sum(1 for g, w in zip(got, want) if g != w) + abs(len(got) - len(want))
-    print(f"SAM lines {len(want)}, differing {sam_bad}")
+    # ... and the complete text of every line after QNAME (SEQ / QUAL, all tags); write_fastq_fast writes quality 'I'
+    tgot = tp.oracle_sam_text(capi, idx, opt2, codes, offs, regs, ro, lh, as_, names)
+    twant = [ln.rstrip("\n").split("\t", 1)[1] for ln in open(work + "/o.sam") if not ln.startswith("@")]
+    text_bad = sum(1 for g, w in zip(tgot, twant) if g != w) + abs(len(tgot) - len(twant))
+    print(f"SAM lines {len(want)}, differing columns {sam_bad}, differing text {text_bad}, XA tags {sum('XA:Z:' in w for w in twant)}, SA tags {sum('SA:Z:' in w for w in twant)}")
     print(f"{mbp} Mbp, {2 * pairs} reads, options {args}: {len(rr)} regs; reference {t1 - t0:.0f}s oracle {t2 - t1:.0f}s emulation {t3 - t2:.0f}s; "
           f"oracle vs reference: {len(bad)} differing reads {bad[:5]}; device logic == oracle: {e.tobytes() == regs.tobytes() and np.array_equal(eo, ro)}")
 

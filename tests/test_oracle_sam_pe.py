@@ -120,3 +120,94 @@ def test_paired_end_sam_matches_the_live_reference(c0, golden_dir, args):
     lh, as_ = _pestat(capi, idx, opt, reads, regs, ro)
     recs, cig, md = oracle_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_)
     _compare(fields(recs, cig, md, names), parse_sam(open(os.path.join(work, "o.sam"))))
+
+
+def oracle_sam_text(capi, idx, opt, codes, offs, regs, ro, lh, as_, names, qual_char="I"):
+    codes = np.ascontiguousarray(codes, np.uint8); offs = np.ascontiguousarray(offs, np.int64)
+    regs = np.ascontiguousarray(regs); ro = np.ascontiguousarray(ro, np.int64)
+    lh = np.ascontiguousarray(lh, np.int32); as_ = np.ascontiguousarray(as_, np.float64)
+    rb = capi.ReadBatch(len(offs) - 1, codes.ctypes.data, offs.ctypes.data)
+    quals = (qual_char * len(codes)).encode()
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    text = C.c_void_p(); ln = C.c_int64()
+    L = ol.lib()
+    rc = L.bm2o_sam_pe_text(C.byref(idx.desc), C.byref(opt), C.byref(rb), C.c_char_p(quals), arr, regs.ctypes.data_as(C.c_void_p), ro.ctypes.data_as(C.c_void_p),
+                            lh.ctypes.data_as(C.c_void_p), as_.ctypes.data_as(C.c_void_p), C.c_int64(0), C.byref(text), C.byref(ln))
+    assert rc == 0
+    out = C.string_at(text, ln.value).decode()
+    L.bm2o_free(text)
+    return out.split("\n")[:-1]
+
+
+def test_paired_end_sam_text_is_byte_identical_to_the_reference_golden(c0, golden_dir):
+    """Every character of every SAM line after QNAME (all columns, SEQ / QUAL with hard clips, NM MD MC AS XS SA pa XA tags)."""
+    capi, idx, reads, codes, offs, names = c0
+    opt = capi.default_opt(); opt.flag |= 0x2
+    regs, ro, _, rc = ol.seed_chain_extend(idx, opt, codes, offs)
+    lh, as_ = _pestat(capi, idx, opt, reads, regs, ro)
+    got = oracle_sam_text(capi, idx, opt, codes, offs, regs, ro, lh, as_, names)
+    want = [ln.rstrip("\n").split("\t", 1)[1] for ln in open(golden_dir + "/c0.sam") if not ln.startswith("@")]
+    assert len(got) == len(want)
+    bad = [i for i in range(len(got)) if got[i] != want[i]]
+    assert not bad, (len(bad), [(got[i], want[i]) for i in bad[:2]])
+    assert sum("SA:Z:" in w for w in want) >= 6 and sum("MC:Z:" in w for w in want) > 900
+
+
+def test_sam_text_with_xa_and_alt_tags_matches_the_live_reference(pkg):
+    """A genome with 2-4 copy segmental duplications (XA tags) and ALT contigs (pa tag, ALT-aware primary marking): byte-identical text."""
+    if cu.refbin() is None:
+        pytest.skip("oracle/_ref not built")
+    capi = pkg.capi
+    rng = np.random.default_rng(12)
+    work = tempfile.mkdtemp(prefix="bm2_xa_")
+    ctgs = []
+    for c in range(3):
+        g = rng.integers(0, 4, 120_000).astype(np.uint8)
+        for _ in range(25):                                   # duplications: 500-bp segments, 1-3 extra copies, ~1 % divergence
+            L = 500; src = int(rng.integers(0, len(g) - L)); seg = g[src:src + L]
+            for _ in range(int(rng.integers(1, 4))):
+                cp = seg.copy(); mut = rng.random(L) < 0.01; cp[mut] = rng.integers(0, 4, int(mut.sum()))
+                dst = int(rng.integers(0, len(g) - L)); g[dst:dst + L] = cp
+        ctgs.append(g)
+    alt = ctgs[0][20_000:60_000].copy(); mut = rng.random(len(alt)) < 0.005; alt[mut] = rng.integers(0, 4, int(mut.sum()))
+    ctgs.append(alt)                                          # an ALT contig: a diverged copy of a stretch of the first one
+    names = ["c1", "c2", "c3", "c1_alt"]
+    with open(work + "/ref.fa", "w") as f:
+        for n, g in zip(names, ctgs):
+            f.write(f">{n}\n"); s = "".join("ACGT"[b] for b in g)
+            f.write("\n".join(s[i:i + 80] for i in range(0, len(s), 80)) + "\n")
+    with open(work + "/ref.fa.alt", "w") as f:
+        f.write("c1_alt\t0\tc1\t20001\t60\t40000M\t*\t0\t0\t*\t*\n")
+    bindir = os.path.dirname(cu.refbin())
+    subprocess.check_call([bindir + "/bwa-mem2", "index", work + "/ref.fa"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    genome = np.concatenate(ctgs[:3])
+    n_pairs = 1500; L = 151
+    reads = np.zeros((2 * n_pairs, L), np.uint8)
+    comp = np.array([3, 2, 1, 0, 4], np.uint8)
+    for p in range(n_pairs):
+        c = int(rng.integers(0, 4)); g = ctgs[c]            # also from the ALT contig: its reads make the primary-assembly hit the secondary (pa tag)
+        ins = int(rng.normal(400, 40)); ins = max(ins, L + 10)
+        st = int(rng.integers(0, len(g) - ins))
+        frag = g[st:st + ins].copy(); mut = rng.random(ins) < 0.01; frag[mut] = rng.integers(0, 4, int(mut.sum()))
+        r1 = frag[:L]; r2 = comp[frag[-L:][::-1]]
+        if rng.random() < 0.5: r1, r2 = r2, r1
+        reads[2 * p] = r1; reads[2 * p + 1] = r2
+    for k, name in ((0, "r1.fq"), (1, "r2.fq")):
+        with open(os.path.join(work, name), "w") as f:
+            for i, r in enumerate(reads[k::2]):
+                f.write(f"@p{i}\n{''.join('ACGTN'[c] for c in r)}\n+\n{'I' * L}\n")
+    env = dict(os.environ, BM2_DUMP_PREFIX=os.path.join(work, "d"))
+    with open(os.path.join(work, "o.sam"), "w") as f:
+        subprocess.check_call([cu.refbin(), "mem", "-t", "1", "-K", "100000000", work + "/ref.fa", work + "/r1.fq", work + "/r2.fq"], stdout=f, stderr=subprocess.DEVNULL, env=env)
+    want = [ln.rstrip("\n").split("\t", 1)[1] for ln in open(work + "/o.sam") if not ln.startswith("@")]
+    idx = capi.Index(work + "/ref.fa")
+    opt = capi.default_opt(); opt.flag |= 0x2
+    codes = reads.reshape(-1); offs = (np.arange(len(reads) + 1) * L).astype(np.int64)
+    regs, ro, _, rc = ol.seed_chain_extend(idx, opt, codes, offs)
+    lh, as_ = _pestat(capi, idx, opt, reads, regs, ro)
+    got = oracle_sam_text(capi, idx, opt, codes, offs, regs, ro, lh, as_, names)
+    assert len(got) == len(want)
+    bad = [i for i in range(len(got)) if got[i] != want[i]]
+    assert not bad, (len(bad), [(got[i], want[i]) for i in bad[:2]])
+    assert sum("XA:Z:" in w for w in want) > 30 and sum("pa:f:" in w for w in want) > 5, (sum("XA:Z:" in w for w in want), sum("pa:f:" in w for w in want))
+    idx.close()
