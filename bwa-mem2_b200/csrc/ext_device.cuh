@@ -292,6 +292,7 @@ BM2_HD int patch_reg_d(const ContigView &cv, const ExtParams &p, const uint8_t *
 {
     int w, score = 0, q_s, r_s;
     double r;
+    if (query == 0) return 0;                                   // mem_patch_reg without a query (mate rescue's dedup, src/bwamem.cpp:179)
     if (a->rb < cv.l_pac && b->rb >= cv.l_pac) return 0;
     if (a->qb >= b->qb || a->qe >= b->qe || a->re >= b->re) return 0;
     w = (int) ((a->re - b->rb) - (a->qe - b->qb));

@@ -90,3 +90,44 @@ def test_matesw_matches_reference(c0):
         n_calls += 1; n_sw += n
     print("mem_matesw calls", n_calls, "orientations aligned", n_sw, "regs added", n_added)
     assert n_calls > 500 and n_sw > 20 and n_added > 5, (n_calls, n_sw, n_added)
+
+
+def test_device_logic_of_the_rescue_block_matches_the_oracle(c0):
+    """bwa-mem2_b200/csrc/mate_device.cuh (matesw_d, mate_rescue_pair_d over ksw_device.cuh and the tail's sort_dedup_patch_d), compiled for
+    the host, against the oracle's chained mem_matesw calls (pinned to the reference by the test above)."""
+    capi, idx, opt, reads, regs, ro, pes, work, prefix = c0
+    d = os.path.join(ROOT, "tests", "host_emul")
+    so = os.path.join(d, "libmateemul.so")
+    srcs = [os.path.join(d, "mate_emul.cpp")] + [os.path.join(ROOT, "bwa-mem2_b200", "csrc", f) for f in ("mate_device.cuh", "ksw_device.cuh", "ext_device.cuh", "chain_device.cuh", "hd.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-I" + os.path.join(ROOT, "bwa-mem2_b200", "csrc"),
+                               "-I" + os.path.join(ROOT, "include"), srcs[0], "-o", so])
+    E = C.CDLL(so); E.emul_mate_rescue.restype = C.c_longlong
+    lh = np.array([v for dd in range(4) for v in pes[dd][:3]], np.int32)
+    codes = np.ascontiguousarray(reads.reshape(-1)); offs = (np.arange(len(reads) + 1) * reads.shape[1]).astype(np.int64)
+    rb = capi.ReadBatch(len(reads), codes.ctypes.data, offs.ctypes.data)
+    regs_c = np.ascontiguousarray(regs); ro_c = np.ascontiguousarray(ro, np.int64)
+    cap = len(regs) + 8 * len(reads) + 1024
+    out = np.zeros(cap, capi.REG_DT); out_off = np.zeros(len(reads) + 1, np.int64)
+    tot = E.emul_mate_rescue(C.byref(idx.desc), C.byref(opt), C.byref(rb), regs_c.ctypes.data_as(C.c_void_p), ro_c.ctypes.data_as(C.c_void_p),
+                             lh.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_int64(cap), out_off.ctypes.data_as(C.c_void_p))
+    assert tot > 1000, tot
+    # the oracle's chain for every pair
+    L = ol.lib(); n_sw = 0
+    for p in range(len(reads) // 2):
+        a = [regs[ro[2 * p]:ro[2 * p + 1]].copy(), regs[ro[2 * p + 1]:ro[2 * p + 2]].copy()]
+        b = [x[x["score"] >= x["score"][0] - opt.pen_unpaired].copy() if len(x) else x.copy() for x in a]
+        for i in (0, 1):
+            for j in range(min(len(b[i]), opt.max_matesw)):
+                anchor = np.ascontiguousarray(b[i][j:j + 1])
+                ma = np.zeros(len(a[1 - i]) + 4, capi.REG_DT); ma[:len(a[1 - i])] = a[1 - i]
+                n_ma = C.c_int32(len(a[1 - i])); ms = np.ascontiguousarray(reads[2 * p + (1 - i)])
+                n_sw += L.bm2o_matesw(C.byref(idx.desc), C.byref(opt), lh.ctypes.data_as(C.c_void_p), anchor.ctypes.data_as(C.c_void_p), C.c_int32(len(ms)),
+                                      ms.ctypes.data_as(C.c_void_p), ma.ctypes.data_as(C.c_void_p), C.byref(n_ma))
+                a[1 - i] = ma[:n_ma.value].copy()
+        for i in (0, 1):
+            got = out[out_off[2 * p + i]:out_off[2 * p + i + 1]]
+            assert len(got) == len(a[i]), (p, i, len(got), len(a[i]))
+            for fld in FIELDS:
+                assert np.array_equal(got[fld], a[i][fld]), (p, i, fld)
+    assert n_sw == tot
