@@ -1,0 +1,89 @@
+// sam_emul.cpp — TEST-ONLY host build of the SAM-stage device logic (bwa-mem2_b200/csrc/sam_device.cuh + mate_device.cuh): mate rescue,
+// primary marking, pairing, MAPQ, CIGAR / NM / MD and the SAM columns of every line of a batch of pairs, in the record layout of the
+// oracle's bm2o_sam_pe so that the two can be compared field by field.  The libm tables are filled here with the host's log / erfc, as a
+// host driver would.  Never part of the product.
+#include <vector>
+#include <string>
+#include <cmath>
+#include <cstring>
+#include "sam_device.cuh"
+#include "../../oracle/bm2_oracle.h"
+
+extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off,
+                           const int32_t *lh, const double *as, int64_t id_base, bm2o_samrec **recs_out, int64_t *n_recs, uint32_t **cigar_out,
+                           int64_t *n_ops_out, char **md_out, int64_t *n_md_out)
+{
+    ContigView cv; cv.l_pac = idx->l_pac; cv.n_seqs = idx->n_seqs; cv.ann_off = idx->ann_offset; cv.ann_len = idx->ann_len; cv.ann_alt = idx->ann_is_alt;
+    SamParams p;
+    p.ep.a = opt->a; p.ep.b = opt->b; p.ep.o_del = opt->o_del; p.ep.e_del = opt->e_del; p.ep.o_ins = opt->o_ins; p.ep.e_ins = opt->e_ins; p.ep.w = opt->w;
+    p.ep.pen_clip5 = opt->pen_clip5; p.ep.pen_clip3 = opt->pen_clip3; p.ep.max_chain_gap = opt->max_chain_gap; p.ep.mask_level_redun = opt->mask_level_redun;
+    memcpy(p.ep.mat, opt->mat, 25);
+    p.T = opt->T; p.flag = opt->flag; p.min_seed_len = opt->min_seed_len; p.pen_unpaired = opt->pen_unpaired; p.mask_level = opt->mask_level;
+    p.drop_ratio = opt->drop_ratio; p.mapQ_coef_len = opt->mapQ_coef_len; p.mapQ_coef_fac = opt->mapQ_coef_fac;
+    MatePes pes;
+    for (int d = 0; d < 4; ++d) { pes.low[d] = lh[3 * d]; pes.high[d] = lh[3 * d + 1]; pes.failed[d] = lh[3 * d + 2]; }
+    // host-filled libm tables
+    std::vector<double> logt(1 << 16); for (size_t k = 0; k < logt.size(); ++k) logt[k] = log((double) k);      /* log(0) = -inf, as the reference would compute */
+    std::vector<double> term[4];
+    SamTables tb; tb.log_tab = logt.data(); tb.n_log = (int) logt.size();
+    for (int d = 0; d < 4; ++d) {
+        tb.pair_lo[d] = pes.low[d]; tb.pair_hi[d] = pes.failed[d] ? pes.low[d] - 1 : pes.high[d];
+        for (int64_t dist = tb.pair_lo[d]; dist <= tb.pair_hi[d]; ++dist) {
+            const double ns = (dist - as[2 * d]) / as[2 * d + 1];
+            term[d].push_back(.721 * log(2. * erfc(fabs(ns) * M_SQRT1_2)) * opt->a);
+        }
+        tb.pair_term[d] = term[d].data();
+    }
+    std::vector<bm2o_samrec> out; std::vector<uint32_t> ops_all; std::string md_all;
+    int overflow = 0;
+    for (int pr = 0; pr < reads->n_reads >> 1; ++pr) {
+        const uint8_t *seq[2]; int l_seq[2], n[2]; int max_l = 0;
+        std::vector<bm2_alnreg_t> a[2], b[2];
+        for (int i = 0; i < 2; ++i) {
+            const int r = 2 * pr + i;
+            seq[i] = reads->codes + reads->offsets[r]; l_seq[i] = (int) (reads->offsets[r + 1] - reads->offsets[r]);
+            n[i] = (int) (read_off[r + 1] - read_off[r]);
+            if (l_seq[i] > max_l) max_l = l_seq[i];
+        }
+        for (int i = 0; i < 2; ++i) {
+            a[i].assign(regs + read_off[2 * pr + i], regs + read_off[2 * pr + i + 1]);
+            const int calls = n[!i] < opt->max_matesw ? n[!i] : opt->max_matesw;
+            a[i].resize((size_t) n[i] + 4 * (size_t) calls + 4);
+            b[i].resize((size_t) n[i] + 1);
+        }
+        const size_t nreg = a[0].size() + a[1].size();
+        std::vector<uint8_t> rev((size_t) max_l + 1), tmp((size_t) 1 << 16);
+        std::vector<int32_t> ksw((size_t) 3 * (max_l + 16)), bsc(256), bpos(256), idxv(nreg + 8), zv(nreg + 8), he((size_t) 2 * (max_l + 2));
+        std::vector<TailSortKey> keys(nreg + 8);
+        MateScratch ms = { rev.data(), tmp.data(), ksw.data(), bsc.data(), bpos.data(), 256, idxv.data(), keys.data() };
+        bm2_alnreg_t *ap[2] = { a[0].data(), a[1].data() }, *bp[2] = { b[0].data(), b[1].data() };
+        if (!(opt->flag & 0x20)) mate_rescue_pair_d(cv, p.ep, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, idx->ref_string, seq, l_seq, ap, n, bp, ms, &overflow);
+        // SAM stage
+        std::vector<SamP64> v(nreg + 4), u(4096);
+        std::vector<uint8_t> zbuf((size_t) (max_l + 8) * (size_t) (max_l + 4 * opt->w + 64));
+        std::vector<SamAln> aa0((size_t) n[0] + 4), aa1((size_t) n[1] + 4);
+        std::vector<uint32_t> cig_pool((size_t) (nreg + 8) * (size_t) (3 * max_l + 512)), opsv((size_t) 3 * max_l + 512);
+        std::vector<char> md_pool((size_t) (nreg + 8) * (size_t) (12 * max_l + 2048));
+        SamScratch sc;
+        sc.z = zv.data(); sc.idx = idxv.data(); sc.v = v.data(); sc.u = u.data(); sc.ucap = (int) u.size(); sc.he = he.data();
+        sc.zz.base = zbuf.data(); sc.zz.stride = 1; sc.aa[0] = aa0.data(); sc.aa[1] = aa1.data(); sc.aa_cap = (int) (n[0] > n[1] ? n[0] : n[1]) + 2;
+        sc.cig_pool = cig_pool.data(); sc.cig_cap = (long long) cig_pool.size(); sc.md_pool = md_pool.data(); sc.md_cap = (long long) md_pool.size(); sc.ops = opsv.data();
+        auto emit = [&](int i, int k, const SamRec &r, const uint32_t *ops, const char *md) {
+            bm2o_samrec o; memset(&o, 0, sizeof(o));
+            o.read = 2 * pr + i; o.flag = r.flag; o.rid = r.rid; o.mapq = r.mapq; o.rnext = r.rnext; o.tlen_valid = 1; o.nm = r.nm; o.score = r.score; o.sub = r.sub;
+            o.n_cigar = r.n_cigar; o.pos = r.pos; o.pnext = r.pnext; o.tlen = r.tlen; o.cigar_off = (int64_t) ops_all.size(); o.md_off = (int64_t) md_all.size();
+            ops_all.insert(ops_all.end(), ops, ops + r.n_cigar);
+            if (r.n_cigar) md_all += md;
+            md_all.push_back('\0');
+            o.n_md = (int32_t) (md_all.size() - (size_t) o.md_off);
+            out.push_back(o);
+        };
+        sam_pe_pair_d(p, tb, cv, pes, idx->ref_string, seq, l_seq, ap, n, (int) (id_base + pr), sc, emit, &overflow);
+    }
+    const size_t nr = out.size();
+    *recs_out = (bm2o_samrec *) malloc(sizeof(bm2o_samrec) * (nr + 1)); memcpy(*recs_out, out.data(), sizeof(bm2o_samrec) * nr);
+    *cigar_out = (uint32_t *) malloc(4 * (ops_all.size() + 1)); memcpy(*cigar_out, ops_all.data(), 4 * ops_all.size());
+    *md_out = (char *) malloc(md_all.size() + 1); memcpy(*md_out, md_all.data(), md_all.size());
+    *n_recs = (int64_t) nr; *n_ops_out = (int64_t) ops_all.size(); *n_md_out = (int64_t) md_all.size();
+    return overflow ? 3 : 0;
+}

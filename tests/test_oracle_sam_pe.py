@@ -211,3 +211,54 @@ def test_sam_text_with_xa_and_alt_tags_matches_the_live_reference(pkg):
     assert not bad, (len(bad), [(got[i], want[i]) for i in bad[:2]])
     assert sum("XA:Z:" in w for w in want) > 30 and sum("pa:f:" in w for w in want) > 5, (sum("XA:Z:" in w for w in want), sum("pa:f:" in w for w in want))
     idx.close()
+
+
+# ---- the SAM-stage device logic (sam_device.cuh + mate_device.cuh, compiled for the host) against the oracle -----------------------------
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_EMUL = None
+
+
+def _emul():
+    global _EMUL
+    if _EMUL is None:
+        ol.lib()
+        d = os.path.join(ROOT, "tests", "host_emul")
+        so = os.path.join(d, "libsamemul.so")
+        srcs = [os.path.join(d, "sam_emul.cpp")] + [os.path.join(ROOT, "bwa-mem2_b200", "csrc", f) for f in
+                                                     ("sam_device.cuh", "mate_device.cuh", "ksw_device.cuh", "cigar_device.cuh", "ext_device.cuh", "chain_device.cuh", "hd.h")]
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+            subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-I" + os.path.join(ROOT, "bwa-mem2_b200", "csrc"),
+                                   "-I" + os.path.join(ROOT, "include"), srcs[0], "-o", so])
+        _EMUL = C.CDLL(so)
+    return _EMUL
+
+
+def emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_):
+    codes = np.ascontiguousarray(codes, np.uint8); offs = np.ascontiguousarray(offs, np.int64)
+    regs = np.ascontiguousarray(regs); ro = np.ascontiguousarray(ro, np.int64)
+    lh = np.ascontiguousarray(lh, np.int32); as_ = np.ascontiguousarray(as_, np.float64)
+    rb = capi.ReadBatch(len(offs) - 1, codes.ctypes.data, offs.ctypes.data)
+    rc_ = C.c_void_p(); cg = C.c_void_p(); md = C.c_void_p(); nr = C.c_int64(); no = C.c_int64(); nm = C.c_int64()
+    rc = _emul().emul_sam_pe(C.byref(idx.desc), C.byref(opt), C.byref(rb), regs.ctypes.data_as(C.c_void_p), ro.ctypes.data_as(C.c_void_p),
+                             lh.ctypes.data_as(C.c_void_p), as_.ctypes.data_as(C.c_void_p), C.c_int64(0), C.byref(rc_), C.byref(nr), C.byref(cg), C.byref(no),
+                             C.byref(md), C.byref(nm))
+    assert rc == 0, rc
+    def arr(p, n, dt):
+        dt = np.dtype(dt)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(n, 1) * dt.itemsize,))[:n * dt.itemsize].view(dt).copy()
+    out = arr(rc_, nr.value, REC_DT), arr(cg, no.value, "<u4"), arr(md, nm.value, "u1")
+    for p in (rc_, cg, md):
+        ol.lib().bm2o_free(p)
+    return out
+
+
+@pytest.mark.parametrize("flags", [0, 0x8, 0x10, 0x4, 0x20, 0x200], ids=["default", "all", "no_multi", "no_pairing", "no_rescue", "softclip"])
+def test_sam_stage_device_logic_matches_oracle(c0, flags):
+    capi, idx, reads, codes, offs, names = c0
+    opt = capi.default_opt(); opt.flag |= 0x2 | flags
+    regs, ro, _, rc = ol.seed_chain_extend(idx, opt, codes, offs)
+    lh, as_ = _pestat(capi, idx, opt, reads, regs, ro)
+    want = oracle_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_)
+    got = emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_)
+    _compare(fields(*got, names), fields(*want, names))
+    assert len(got[0]) >= len(reads)
