@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""One-off differential run (CPU only, needs oracle/_ref): a larger synthetic data set than the committed fixtures, optional
+"""One-off differential run (usage: bigdiff.py <ref Mbp> <pairs> <seed> [--len=N] [mem options ...])
+One-off differential run (CPU only, needs oracle/_ref): a larger synthetic data set than the committed fixtures, optional
 `bwa-mem2 mem` options; the UNMODIFIED reference (regs dumped by ref_driver's link-time hooks) against the oracle and against the
 kernels' device logic (host emulation), every field of every alignment region.
 Usage: bigdiff.py <ref Mbp> <pairs> <seed> [mem options ...]"""
@@ -16,11 +17,14 @@ from test_option_surface_cpu import opt_from_cli
 
 def main():
     mbp, pairs, seed = float(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]); args = sys.argv[4:]
+    read_len = 151
+    if args and args[0].startswith("--len="):            # read length of the synthetic pairs (default 151)
+        read_len = int(args[0][6:]); args = args[1:]
     synth = importlib.import_module("bwa_mem2_b200.synth")
     work = tempfile.mkdtemp(prefix="bm2_big_")
     ctg = synth.make_reference(int(mbp * 1e6), seed=seed, n_contigs=5, repeat_frac=0.3)
     synth.write_fasta(work + "/ref.fa", ctg)
-    r1, r2 = synth.make_pairs_fast(ctg, pairs, seed=seed + 1)
+    r1, r2 = synth.make_pairs_fast(ctg, pairs, read_len=read_len, seed=seed + 1)
     synth.write_fastq_fast(work + "/r1.fq", r1); synth.write_fastq_fast(work + "/r2.fq", r2)
     bindir = os.path.dirname(cu.refbin())
     subprocess.check_call([bindir + "/bwa-mem2", "index", work + "/ref.fa"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
