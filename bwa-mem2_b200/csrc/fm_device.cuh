@@ -57,6 +57,9 @@ BM2_HD FmOcc4 fm_occ4(const FmIndexView &fm, int64_t pp) {
 // are the reference's l[a] exactly, with half the popcounts and 8-byte instead of 16-byte loads.
 BM2_HD FmIv fm_backward_ext(const FmIndexView &fm, const FmIv &in, int a) {
     const int64_t p1 = in.k, p2 = in.k + in.s;
+#if defined(BM2_TRACE_EXT) && !defined(__CUDA_ARCH__)
+    BM2_TRACE_EXT(p1, p2, in.s);                                  // access-locality studies (scripts/study_smem_locality.py)
+#endif
     const bm2_cp_occ *e1 = fm.cp_occ + (p1 >> 6), *e2 = fm.cp_occ + (p2 >> 6);
     const int b2 = a == 1 ? 0 : (a == 2 ? 3 : a);                  // the one other base that is needed
     const int y1 = (int) (p1 & 63), y2 = (int) (p2 & 63);
