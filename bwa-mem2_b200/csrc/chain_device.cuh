@@ -114,12 +114,76 @@ struct FltRec { int32_t beg, end, w, is_alt, first, kept; };   // what mem_chain
 struct ChainStripe {               // all arrays have >= n_slots entries, private to the read
     WSeed *seeds;
     WChain *chains;
-    int32_t *ord;                  // chain ids ordered by pos (the B-tree's in-order sequence)
+    int32_t *ord;                  // chain ids ordered by pos (the B-tree's in-order sequence); bits 28-31: the key's level in the tree
     int64_t *ordpos;               // pos of ord[i] (contiguous copy for the binary search)
     int32_t *srt;                  // filter: chain ids sorted by weight
     int32_t *kv;                   // filter: kept non-overlapping chains
     FltRec *flt;                   // filter: compact records by sorted position
 };
+
+
+// ---- the shape of the reference's chain tree ---------------------------------------------------------------------------------
+// The reference keeps the chains of a read in a B-tree keyed by pos (KBTREE_INIT(chn, ...), src/bwamem.cpp:40-41; src/kbtree.h)
+// and the tree accepts equal keys.  Which of several chains with the same pos kb_intervalp meets first, and next to which of them
+// kb_putp places a new one, depends on the shape of the tree; reads inside short tandem repeats produce such chains.  The shape is
+// kept without building nodes: the keys stay in ONE array in key order (ord / ordpos) and every key carries the level of the node
+// that holds it (0 = leaf).  A node of level h is then the run of level-h keys between two neighbouring keys of a higher level, its
+// children are the stretches between its keys, and splitting a full node is "raise the level of its median key by one".
+// Order t = 5 (at most 9 keys per node): kb_init(chn, KB_DEFAULT_SIZE + 8) with the 48-byte mem_chain_t
+// (src/kbtree.h:64, src/bwamem.cpp:845, src/bwamem.h:126-133).
+#define BM2_CHAIN_TREE_T 5
+BM2_HD int chain_ord_id(int32_t v) { return (int) (v & 0x0fffffff); }
+BM2_HD int chain_ord_lvl(int32_t v) { return (int) ((uint32_t) v >> 28); }
+
+// kb_intervalp (src/kbtree.h:158-175) when a key equal to k exists; q = first index with ordpos >= k (so ordpos[q] == k).
+// Walks from the root: in each node the first key >= k (src/kbtree.h:125-139); an equal one ends the search, else descend
+// into the child on its left.  Returns the index of the key met.
+BM2_HD int chain_tree_equal_d(const int32_t *ord, const int64_t *ordpos, int n, int height, int64_t k, int q) {
+    int lo = 0, hi = n;                                  // the subtree spans [lo, hi)
+    for (int h = height; h > 0; --h) {
+        int b = q; while (b < hi && chain_ord_lvl(ord[b]) != h) ++b;
+        if (b < hi && ordpos[b] == k) return b;
+        int a = q - 1; while (a >= lo && chain_ord_lvl(ord[a]) != h) --a;
+        lo = a + 1; hi = b;
+    }
+    return q;
+}
+
+// kb_putp (src/kbtree.h:181-235): splits every full node on the way down, returns the index at which the new key (level 0)
+// goes.  q = first index with ordpos >= k; height / root_n = level and key count of the root, updated here.
+BM2_HD int chain_tree_put_d(int32_t *ord, const int64_t *ordpos, int n, int &height, int &root_n, int64_t k, int q) {
+    const int full = 2 * BM2_CHAIN_TREE_T - 1;
+    if (root_n == full) {                                // new root above the old one: the old root's median moves up
+        int seen = 0, m = 0;
+        for (; m < n; ++m) if (chain_ord_lvl(ord[m]) == height && ++seen == BM2_CHAIN_TREE_T) break;
+        ++height;
+        ord[m] = (int32_t) ((uint32_t) chain_ord_id(ord[m]) | (uint32_t) height << 28);
+        root_n = 1;
+    }
+    int lo = 0, hi = n;
+    for (int h = height; h > 0; --h) {
+        const int qr = q > lo ? q : lo;                  // first index of the subtree with ordpos >= k (hi if none)
+        int b = qr; while (b < hi && chain_ord_lvl(ord[b]) != h) ++b;           // first key of this node >= k
+        int clo, chi;
+        if (b < hi && ordpos[b] == k) {                  // equal: the child on its RIGHT (src/kbtree.h:210)
+            clo = b + 1; chi = b + 1; while (chi < hi && chain_ord_lvl(ord[chi]) != h) ++chi;
+        } else {
+            int a = qr - 1; while (a >= lo && chain_ord_lvl(ord[a]) != h) --a;
+            clo = a + 1; chi = b;
+        }
+        int cnt = 0, m = -1;
+        for (int j = clo; j < chi; ++j) if (chain_ord_lvl(ord[j]) == h - 1 && ++cnt == BM2_CHAIN_TREE_T) m = j;
+        if (cnt == full) {                               // split the child: its median joins this node
+            ord[m] = (int32_t) ((uint32_t) chain_ord_id(ord[m]) | (uint32_t) h << 28);
+            if (h == height) ++root_n;
+            if (k > ordpos[m]) clo = m + 1; else chi = m;
+        }
+        lo = clo; hi = chi;
+    }
+    if (height == 0) ++root_n;
+    const int qr = q > lo ? (q < hi ? q : hi) : lo;
+    return (qr < hi && ordpos[qr] == k) ? qr + 1 : qr;   // leaf: after the first equal key, else before the first larger one
+}
 
 // test_and_merge (src/bwamem.cpp:357-399) on the cached first/last seed of the chain
 BM2_HD bool chain_test_and_merge(const ChainParams &p, int64_t l_pac, WChain &c, WSeed *seeds, int seed_id, int seed_rid) {
@@ -171,7 +235,7 @@ BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_sm
     l_rep += e - b;
     *frac_rep = (float) l_rep / l_seq;
 
-    int n_ch = 0, n_sd = 0, rid_hint = -1;
+    int n_ch = 0, n_sd = 0, rid_hint = -1, tree_h = 0, root_n = 0;
     int64_t slot = 0;
     for (int i = 0; i < n_smem; ++i) {
         const bm2_smem &sm = smems[i];
@@ -184,12 +248,13 @@ BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_sm
             const int sid = n_sd;
             WSeed &s = ws.seeds[sid]; s.rbeg = rbeg; s.qbeg = (int) sm.m; s.len = slen; s.next = -1; s.score = slen;
             int lower = -1;
+            int lo = 0;                           // first chain with pos >= rbeg
             if (n_ch) {
-                int lo = 0, hi = n_ch;            // first chain with pos >= rbeg
+                int hi = n_ch;
                 while (lo < hi) { int mid = (lo + hi) >> 1; if (ws.ordpos[mid] < rbeg) lo = mid + 1; else hi = mid; }
-                lower = (lo < n_ch && ws.ordpos[lo] == rbeg) ? lo : lo - 1;
+                lower = (lo < n_ch && ws.ordpos[lo] == rbeg) ? chain_tree_equal_d(ws.ord, ws.ordpos, n_ch, tree_h, rbeg, lo) : lo - 1;
                 if (lower >= 0) {
-                    WChain &lc = ws.chains[ws.ord[lower]];
+                    WChain &lc = ws.chains[chain_ord_id(ws.ord[lower])];
                     if (chain_test_and_merge(p, cv.l_pac, lc, ws.seeds, sid, rid)) {
                         if (lc.tail == sid) ++n_sd;      // appended: keeps its slot; contained: slot is reused
                         continue;
@@ -201,8 +266,9 @@ BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_sm
             c.pos = rbeg; c.first_rbeg = c.last_rbeg = rbeg; c.first_qbeg = c.last_qbeg = s.qbeg; c.last_len = slen;
             c.head = c.tail = sid; c.n = 1; c.rid = rid; c.is_alt = cv.ann_alt ? (cv.ann_alt[rid] != 0) : 0;
             c.w = 0; c.kept = 0; c.first = -1;
-            for (int k = n_ch; k > lower + 1; --k) { ws.ord[k] = ws.ord[k - 1]; ws.ordpos[k] = ws.ordpos[k - 1]; }
-            ws.ord[lower + 1] = n_ch; ws.ordpos[lower + 1] = rbeg;
+            const int at = chain_tree_put_d(ws.ord, ws.ordpos, n_ch, tree_h, root_n, rbeg, lo);
+            for (int k = n_ch; k > at; --k) { ws.ord[k] = ws.ord[k - 1]; ws.ordpos[k] = ws.ordpos[k - 1]; }
+            ws.ord[at] = n_ch; ws.ordpos[at] = rbeg;      // a new key is always a leaf key (level 0)
             ++n_ch;
         }
     }
@@ -211,11 +277,11 @@ BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_sm
     // ---- mem_chain_flt (src/bwamem.cpp:506-624) -------------------------------------------------------------
     int n = 0;
     for (int i = 0; i < n_ch; ++i) {
-        WChain &c = ws.chains[ws.ord[i]];
+        WChain &c = ws.chains[chain_ord_id(ws.ord[i])];
         c.first = -1; c.kept = 0; c.w = chain_weight_d(c, ws.seeds);
-        if (c.w >= p.min_chain_weight) ws.srt[n++] = ws.ord[i];
+        if (c.w >= p.min_chain_weight) ws.srt[n++] = chain_ord_id(ws.ord[i]);
     }
-    if (n == 0) ws.srt[n++] = ws.ord[0];     // reference quirk: range (0,1) is processed even when all were dropped
+    if (n == 0) ws.srt[n++] = chain_ord_id(ws.ord[0]);     // reference quirk: range (0,1) is processed even when all were dropped
     {
         const WChain *chs = ws.chains;
         ks_introsort_d(ws.srt, (long) n, [chs](int x, int y) { return chs[x].w > chs[y].w; });

@@ -449,9 +449,85 @@ static void chain_filter(const bm2_mem_opt_t *opt, std::vector<OChain> &a) {
     a.swap(out);
 }
 
-/* A4. chains of one read from its ordered SMEMs (mem_chain_seeds, src/bwamem.cpp:806-974).  The
- * B-tree is restated as an array ordered by pos; a new chain whose pos equals an existing one
- * is placed right after the first equal element (leaf insertion rule, src/kbtree.h:219-225). */
+/* The chain tree (KBTREE_INIT(chn, mem_chain_t, chain_cmp), src/bwamem.cpp:40-41; src/kbtree.h).  Keys with equal pos are
+ * legal in it, and which of them a lookup meets first -- and next to which of them a new one is placed -- depends on the
+ * shape of the tree, so the tree is restated for real: order t from kb_init's arithmetic (src/kbtree.h:64) with the 48-byte
+ * mem_chain_t (src/bwamem.h:126-133) and size KB_DEFAULT_SIZE + 8 = 520 (src/bwamem.cpp:845), top-down insertion that
+ * splits every full node on the way (src/kbtree.h:181-235), lookups as kb_intervalp (src/kbtree.h:158-175).
+ * Keys are indices into the chain pool. */
+struct ChainTree {
+    static const int T = (int) (((520 - 4 - 8) / (8 + 48) + 1) >> 1);          /* 5: at most 9 keys per node */
+    struct Node { bool internal; std::vector<int> key; std::vector<int> child; };
+    std::vector<Node> nodes; int root; long n_keys;
+    const std::vector<OChain> &pool;
+    explicit ChainTree(const std::vector<OChain> &pool_) : root(0), n_keys(0), pool(pool_) { nodes.push_back(Node{false, {}, {}}); }
+    /* __kb_getp_aux (src/kbtree.h:125-139): index of the first key >= pos if it is equal (*r = 0), else the index before it
+     * (*r = -1); the last index when every key is smaller (*r = 1); -1 for an empty node */
+    int slot(const Node &x, int64_t pos, int *r) const {
+        const int n = (int) x.key.size();
+        if (n == 0) return -1;
+        int b = 0, e = n;
+        while (b < e) { const int mid = (b + e) >> 1; if (pool[x.key[mid]].pos < pos) b = mid + 1; else e = mid; }
+        if (b == n) { *r = 1; return n - 1; }
+        *r = pos < pool[x.key[b]].pos ? -1 : 0;
+        return *r < 0 ? b - 1 : b;
+    }
+    /* kb_intervalp: the `lower` key (pool index) or -1 */
+    int lower(int64_t pos) const {
+        int low = -1, r = 0;
+        for (int x = root;;) {
+            const Node &nd = nodes[x];
+            const int i = slot(nd, pos, &r);
+            if (i >= 0 && r == 0) return nd.key[i];
+            if (i >= 0) low = nd.key[i];
+            if (!nd.internal) return low;
+            x = nd.child[i + 1];
+        }
+    }
+    /* __kb_split: child number i of x (full) gives its median key to x and its upper half to a new sibling */
+    void split(int x, int i) {
+        const int y = nodes[x].child[i];
+        Node z; z.internal = nodes[y].internal;
+        z.key.assign(nodes[y].key.begin() + T, nodes[y].key.end());
+        if (z.internal) z.child.assign(nodes[y].child.begin() + T, nodes[y].child.end());
+        const int median = nodes[y].key[T - 1];
+        nodes[y].key.resize(T - 1);
+        if (z.internal) nodes[y].child.resize(T);
+        nodes.push_back(z);
+        const int zi = (int) nodes.size() - 1;
+        nodes[x].child.insert(nodes[x].child.begin() + i + 1, zi);
+        nodes[x].key.insert(nodes[x].key.begin() + i, median);
+    }
+    /* kb_putp */
+    void put(int id) {
+        const int64_t pos = pool[id].pos;
+        ++n_keys;
+        if ((int) nodes[root].key.size() == 2 * T - 1) {
+            Node s; s.internal = true; s.child.push_back(root);
+            nodes.push_back(s);
+            root = (int) nodes.size() - 1;
+            split(root, 0);
+        }
+        int x = root, r = 0;
+        while (nodes[x].internal) {
+            int i = slot(nodes[x], pos, &r) + 1;
+            if ((int) nodes[nodes[x].child[i]].key.size() == 2 * T - 1) {
+                split(x, i);
+                if (pos > pool[nodes[x].key[i]].pos) ++i;
+            }
+            x = nodes[x].child[i];
+        }
+        const int i = slot(nodes[x], pos, &r);
+        nodes[x].key.insert(nodes[x].key.begin() + (i + 1), id);
+    }
+    void in_order(int x, std::vector<int> &out) const {
+        const Node &nd = nodes[x];
+        for (size_t i = 0; i < nd.key.size(); ++i) { if (nd.internal) in_order(nd.child[i], out); out.push_back(nd.key[i]); }
+        if (nd.internal) in_order(nd.child.back(), out);
+    }
+};
+
+/* A4. chains of one read from its ordered SMEMs (mem_chain_seeds, src/bwamem.cpp:806-974) */
 static void chain_read(const Fm &fm, const bm2_mem_opt_t *opt, const bm2_smem *sm, int64_t nsm, int l_seq, int seqid,
                        std::vector<OChain> &chains)
 {
@@ -464,6 +540,8 @@ static void chain_read(const Fm &fm, const bm2_mem_opt_t *opt, const bm2_smem *s
         else e = e > se ? e : se;
     }
     l_rep += e - b;
+    std::vector<OChain> pool;                    /* in creation order */
+    ChainTree tree(pool);
     for (int64_t i = 0; i < nsm; ++i) {
         const bm2_smem &p = sm[i];
         int slen = p.n + 1 - p.m;
@@ -474,22 +552,22 @@ static void chain_read(const Fm &fm, const bm2_mem_opt_t *opt, const bm2_smem *s
             int rid = intv2rid(x, s.rbeg, s.rbeg + s.len);
             if (rid < 0) continue;
             bool to_add = true;
-            long lower = -1;
-            if (!chains.empty()) {
-                /* first element with pos >= rbeg; equal -> lower = it, else the one before */
-                long lo = 0, hi = (long) chains.size();
-                while (lo < hi) { long mid = (lo + hi) >> 1; if (chains[mid].pos < s.rbeg) lo = mid + 1; else hi = mid; }
-                if (lo < (long) chains.size() && chains[lo].pos == s.rbeg) lower = lo; else lower = lo - 1;
-                if (lower >= 0 && test_and_merge(opt, x->l_pac, chains[lower], s, rid)) to_add = false;
+            if (tree.n_keys) {
+                const int lower = tree.lower(s.rbeg);
+                if (lower >= 0 && test_and_merge(opt, x->l_pac, pool[lower], s, rid)) to_add = false;
             }
             if (to_add) {
                 OChain c; c.pos = s.rbeg; c.rid = rid; c.seqid = seqid; c.is_alt = x->ann_is_alt ? !!x->ann_is_alt[rid] : 0;
                 c.w = 0; c.kept = 0; c.first = -1; c.frac_rep = 0; c.seeds.push_back(s);
-                chains.insert(chains.begin() + (lower + 1), c);
+                pool.push_back(c);
+                tree.put((int) pool.size() - 1);
             }
         }
     }
-    for (OChain &c : chains) c.frac_rep = (float) l_rep / l_seq;
+    std::vector<int> order;
+    tree.in_order(tree.root, order);
+    chains.clear(); chains.reserve(order.size());
+    for (int id : order) { chains.push_back(std::move(pool[id])); chains.back().frac_rep = (float) l_rep / l_seq; }
 }
 
 }  // namespace

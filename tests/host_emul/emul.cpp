@@ -223,4 +223,23 @@ int emul_seed_chain_extend(const bm2_index_desc *idx, const bm2_mem_opt_t *o, co
     *n_regs = (int64_t) out.size();
     return 0;
 }
+
+// the chain tree alone: keys in insertion order; lower[i] = id of the key kb_intervalp would return before key i is inserted
+// (-1: none), order[] = ids in key order at the end
+void bm2e_chain_tree(const int64_t *keys, int n, int32_t *lower, int32_t *order)
+{
+    std::vector<int32_t> ord(n + 1); std::vector<int64_t> ordpos(n + 1);
+    int height = 0, root_n = 0;
+    for (int m = 0; m < n; ++m) {
+        const int64_t k = keys[m];
+        int lo = 0, hi = m;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (ordpos[mid] < k) lo = mid + 1; else hi = mid; }
+        const int at_low = (lo < m && ordpos[lo] == k) ? chain_tree_equal_d(ord.data(), ordpos.data(), m, height, k, lo) : lo - 1;
+        lower[m] = at_low >= 0 ? chain_ord_id(ord[at_low]) : -1;
+        const int at = chain_tree_put_d(ord.data(), ordpos.data(), m, height, root_n, k, lo);
+        for (int j = m; j > at; --j) { ord[j] = ord[j - 1]; ordpos[j] = ordpos[j - 1]; }
+        ord[at] = m; ordpos[at] = k;
+    }
+    for (int m = 0; m < n; ++m) order[m] = chain_ord_id(ord[m]);
+}
 }
