@@ -298,6 +298,25 @@ BM2_HD void sam_aln2rec_d(const SamParams &prm, const SamAln &p_, int which, con
     r->score = p_.score; r->sub = p_.sub;
 }
 
+// mem_reorder_primary5 (src/bwamem.cpp:1496-1518), option -5: the primary with the smallest query start becomes record 0
+BM2_HD void sam_reorder_primary5_d(int T, int n, bm2_alnreg_t *a) {
+    int n_pri = 0, left_st = 0x7fffffff, left_k = -1;
+    for (int k = 0; k < n; ++k) if (a[k].secondary < 0 && !sam_is_alt_d(a[k]) && a[k].score >= T) ++n_pri;
+    if (n_pri <= 1) return;
+    for (int k = 0; k < n; ++k) {
+        const bm2_alnreg_t &q = a[k];
+        if (q.secondary >= 0 || sam_is_alt_d(q) || q.score < T) continue;
+        if (q.qb < left_st) { left_st = q.qb; left_k = k; }
+    }
+    if (left_k == 0) return;
+    { const bm2_alnreg_t t = a[0]; a[0] = a[left_k]; a[left_k] = t; }
+    for (int k = 1; k < n; ++k) {
+        bm2_alnreg_t &q = a[k];
+        if (q.secondary == 0) q.secondary = left_k; else if (q.secondary == left_k) q.secondary = 0;
+        if (q.secondary_all == 0) q.secondary_all = left_k; else if (q.secondary_all == left_k) q.secondary_all = 0;
+    }
+}
+
 // Scratch of one pair for the SAM stage.
 struct SamScratch {
     int32_t *z, *idx;              // max(n0, n1) + 4 ints each
@@ -328,6 +347,7 @@ BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigV
     int extra_flag = 1, n_pri[2], z[2] = { 0, 0 }, o = 0, subo = 0, n_sub = 0, n_aa[2] = { 0, 0 };
     n_pri[0] = sam_mark_primary_se_d(p, n[0], a[0], (int64_t) id << 1 | 0, sc.z, sc.idx);
     n_pri[1] = sam_mark_primary_se_d(p, n[1], a[1], (int64_t) id << 1 | 1, sc.z, sc.idx);
+    if (p.flag & 0x800) { sam_reorder_primary5_d(p.T, n[0], a[0]); sam_reorder_primary5_d(p.T, n[1], a[1]); }      // MEM_F_PRIMARY5 (src/bwamem_pair.cpp:420-423)
     bool paired = false;
     SamAln h[2];
     auto out_all = [&]() {

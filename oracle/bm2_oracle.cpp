@@ -1656,6 +1656,25 @@ static OAln reg2aln(const bm2_index_desc *x, const bm2_mem_opt_t *opt, int l_que
     return a;
 }
 
+/* mem_reorder_primary5 (src/bwamem.cpp:1496-1518), option -5: the primary with the smallest query start becomes record 0 */
+static void reorder_primary5(int T, int n, bm2_alnreg_t *a) {
+    int n_pri = 0, left_st = INT_MAX, left_k = -1;
+    for (int k = 0; k < n; ++k) if (a[k].secondary < 0 && !reg_is_alt(a[k]) && a[k].score >= T) ++n_pri;
+    if (n_pri <= 1) return;
+    for (int k = 0; k < n; ++k) {
+        const bm2_alnreg_t *p = &a[k];
+        if (p->secondary >= 0 || reg_is_alt(*p) || p->score < T) continue;
+        if (p->qb < left_st) { left_st = p->qb; left_k = k; }
+    }
+    if (left_k == 0) return;
+    std::swap(a[0], a[left_k]);
+    for (int k = 1; k < n; ++k) {
+        bm2_alnreg_t *p = &a[k];
+        if (p->secondary == 0) p->secondary = left_k; else if (p->secondary == left_k) p->secondary = 0;
+        if (p->secondary_all == 0) p->secondary_all = left_k; else if (p->secondary_all == left_k) p->secondary_all = 0;
+    }
+}
+
 extern "C" int bm2o_sam_se(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, bm2_alnreg_t *regs, const int64_t *read_off,
                            int64_t id_base, bm2o_aln **alns_out, int64_t *n_alns, uint32_t **cigar_out, int64_t *n_ops_out, char **md_out, int64_t *n_md_out)
 {
@@ -1673,6 +1692,7 @@ extern "C" int bm2o_sam_se(const bm2_index_desc *x, const bm2_mem_opt_t *opt, co
         const uint8_t *query = reads->codes + reads->offsets[r];
         const int l_query = (int) (reads->offsets[r + 1] - reads->offsets[r]);
         mark_primary_se(opt, n, a, id_base + r);
+        if (opt->flag & 0x800) reorder_primary5(opt->T, n, a);                                                /* MEM_F_PRIMARY5 (:1329) */
         /* mem_reg2sam (:1521-1577), extra_flag = 0, no mate */
         std::vector<OAln> aa;
         int l = 0;
@@ -1928,7 +1948,6 @@ void aln2sam(const bm2_mem_opt_t *opt, int read, const std::vector<OAln> &list, 
 static int sam_pe_core(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off,
                        const int32_t *lh, const double *as, int64_t id_base, const char *const *names, const char *quals, std::string *text, SamOut &so)
 {
-    if (opt->flag & 0x800) return 2;                          /* MEM_F_PRIMARY5: not restated */
     for (int pr = 0; pr < reads->n_reads >> 1; ++pr) {
         const int id = (int) (id_base + pr);
         std::vector<bm2_alnreg_t> a[2];
@@ -1955,6 +1974,10 @@ static int sam_pe_core(const bm2_index_desc *x, const bm2_mem_opt_t *opt, const 
         }
         n_pri[0] = mark_primary_se(opt, (int) a[0].size(), a[0].data(), (int64_t) id << 1 | 0);
         n_pri[1] = mark_primary_se(opt, (int) a[1].size(), a[1].data(), (int64_t) id << 1 | 1);
+        if (opt->flag & 0x800) {                                                                              /* MEM_F_PRIMARY5 (src/bwamem_pair.cpp:420-423) */
+            reorder_primary5(opt->T, (int) a[0].size(), a[0].data());
+            reorder_primary5(opt->T, (int) a[1].size(), a[1].data());
+        }
         bool paired = false;
         std::vector<OAln> aa[2];
         OAln h[2];

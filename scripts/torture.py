@@ -82,8 +82,14 @@ def main():
     tgot = tp.oracle_sam_text(capi, idx, opt2, codes, offs, regs, ro, lh, as_, names)
     twant = [ln.rstrip("\n").split("\t", 1)[1] for ln in open(work + "/o.sam") if not ln.startswith("@")]
     tbad = [i for i in range(min(len(tgot), len(twant))) if tgot[i] != twant[i]]
+    try:                                                       # the SAM stage's device logic (mate rescue, pairing, MAPQ, CIGAR / NM / MD) on the same input
+        tp._compare(tp.fields(*tp.emul_sam_pe(capi, idx, opt2, codes, offs, regs, ro, lh, as_), names),
+                    tp.fields(*tp.oracle_sam_pe(capi, idx, opt2, codes, offs, regs, ro, lh, as_), names))
+        sam_dev = "== oracle"
+    except AssertionError as ex:
+        sam_dev = "DIFFERS: " + str(ex)[:300]
     print(f"seed {seed} {args}: {len(reads)} reads, {len(rr)} regs (max per read {int(np.diff(roff).max())}); oracle vs reference: {len(bad)} differing reads {bad[:5]}; "
-          f"device logic == oracle: {e.tobytes() == regs.tobytes() and np.array_equal(eo, ro)}; SAM lines {len(twant)} vs {len(tgot)}, differing text {len(tbad)} {tbad[:3]}")
+          f"device logic == oracle: {e.tobytes() == regs.tobytes() and np.array_equal(eo, ro)}; SAM lines {len(twant)} vs {len(tgot)}, differing text {len(tbad)} {tbad[:3]}; SAM-stage device logic {sam_dev}")
     for i in tbad[:2]:
         g = tgot[i].split("\t"); w = twant[i].split("\t")
         for a, b in zip(g, w):

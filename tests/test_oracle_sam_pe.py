@@ -98,7 +98,8 @@ def test_paired_end_sam_matches_reference_golden(c0, golden_dir):
     assert (flags & 0x2).sum() > 800 and (flags & 0x800).sum() >= 3 and (flags & 0x4).sum() >= 5      # proper pairs, supplementary, unmapped
 
 
-@pytest.mark.parametrize("args", [["-a"], ["-M"], ["-P"], ["-S"], ["-Y", "-T", "40"], ["-U", "9"]], ids=["all", "no_multi", "no_pairing", "no_rescue", "softclip_T40", "U9"])
+@pytest.mark.parametrize("args", [["-a"], ["-M"], ["-P"], ["-S"], ["-Y", "-T", "40"], ["-U", "9"], ["-5"], ["-q"], ["-5", "-P", "-a"]],
+                         ids=["all", "no_multi", "no_pairing", "no_rescue", "softclip_T40", "U9", "primary5", "keep_supp_mapq", "primary5_P_a"])
 def test_paired_end_sam_matches_the_live_reference(c0, golden_dir, args):
     if cu.refbin() is None:
         pytest.skip("oracle/_ref not built")
@@ -112,7 +113,7 @@ def test_paired_end_sam_matches_the_live_reference(c0, golden_dir, args):
         subprocess.check_call([cu.refbin(), "mem", "-t", "1", "-K", "100000000"] + args + [golden_dir + "/c0_index/ref.fa", os.path.join(work, "r1.fq"),
                                os.path.join(work, "r2.fq")], stdout=f, stderr=subprocess.DEVNULL)
     opt = capi.default_opt(); opt.flag |= 0x2
-    for fl, bit in (("-a", 0x8), ("-M", 0x10), ("-P", 0x4), ("-S", 0x20), ("-Y", 0x200)):
+    for fl, bit in (("-a", 0x8), ("-M", 0x10), ("-P", 0x4), ("-S", 0x20), ("-Y", 0x200), ("-5", 0x1800), ("-q", 0x1000)):
         if fl in args: opt.flag |= bit
     if "-T" in args: opt.T = int(args[args.index("-T") + 1])
     if "-U" in args: opt.pen_unpaired = int(args[args.index("-U") + 1])
@@ -252,7 +253,7 @@ def emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_):
     return out
 
 
-@pytest.mark.parametrize("flags", [0, 0x8, 0x10, 0x4, 0x20, 0x200], ids=["default", "all", "no_multi", "no_pairing", "no_rescue", "softclip"])
+@pytest.mark.parametrize("flags", [0, 0x8, 0x10, 0x4, 0x20, 0x200, 0x1800, 0x1000, 0x1808], ids=["default", "all", "no_multi", "no_pairing", "no_rescue", "softclip", "primary5", "keep_supp_mapq", "primary5_all"])
 def test_sam_stage_device_logic_matches_oracle(c0, flags):
     capi, idx, reads, codes, offs, names = c0
     opt = capi.default_opt(); opt.flag |= 0x2 | flags

@@ -67,7 +67,7 @@ def parse_sam(path):
     return out
 
 
-@pytest.mark.parametrize("args", [[], ["-a"], ["-M"], ["-T", "50"], ["-Y"]], ids=["default", "all", "no_multi", "T50", "softclip"])
+@pytest.mark.parametrize("args", [[], ["-a"], ["-M"], ["-T", "50"], ["-Y"], ["-5"], ["-q"]], ids=["default", "all", "no_multi", "T50", "softclip", "primary5", "keep_supp_mapq"])
 def test_single_end_sam_matches_reference(pkg, golden_dir, args):
     if cu.refbin() is None:
         pytest.skip("oracle/_ref not built")
@@ -87,6 +87,8 @@ def test_single_end_sam_matches_reference(pkg, golden_dir, args):
     if "-a" in args: opt.flag |= 0x8
     if "-M" in args: opt.flag |= 0x10
     if "-Y" in args: opt.flag |= 0x200
+    if "-5" in args: opt.flag |= 0x1800                                      # MEM_F_PRIMARY5 | MEM_F_KEEP_SUPP_MAPQ (src/fastmap.cpp:673)
+    if "-q" in args: opt.flag |= 0x1000
     if "-T" in args: opt.T = int(args[args.index("-T") + 1])
     regs, ro, _, rc = ol.seed_chain_extend(idx, opt, codes, offs)
     assert rc == 0
