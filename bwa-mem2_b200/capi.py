@@ -43,6 +43,10 @@ CIGAR_REQ_DT = np.dtype([("rb", "<i8"), ("re", "<i8"), ("read", "<i4"), ("qb", "
 CIGAR_REC_DT = np.dtype([("score", "<i4"), ("n_cigar", "<i4"), ("nm", "<i4"), ("n_md", "<i4"), ("cigar_off", "<i8"), ("md_off", "<i8")])
 
 
+# seam 4, first piece (bm2_pestat): mem_pestat_t of the four orientations FF, FR, RF, RR
+PESTAT_DT = np.dtype([("low", "<i4"), ("high", "<i4"), ("failed", "<i4"), ("_pad", "<i4"), ("avg", "<f8"), ("std", "<f8")])
+
+
 class CigarResult(C.Structure):
     _fields_ = [("n", C.c_int64), ("recs", C.c_void_p), ("n_ops", C.c_int64), ("cigar", C.c_void_p), ("n_md", C.c_int64), ("md", C.c_void_p)]
 
@@ -66,7 +70,7 @@ class RegResult(C.Structure):
 
 EXPORTS = ["bm2_gather64_gbs", "bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
            "bm2_last_error", "bm2_extend_pairs", "bm2_extend_pairs_device", "bm2_collect_smems", "bm2_seed_chain",
-           "bm2_seed_chain_extend", "bm2_last_stage_ms", "bm2_gen_cigar"]
+           "bm2_seed_chain_extend", "bm2_last_stage_ms", "bm2_gen_cigar", "bm2_pestat"]
 
 _lib = None
 
@@ -100,6 +104,19 @@ def default_opt() -> MemOpt:
 
 class Bm2Error(RuntimeError):
     pass
+
+
+def pestat(opt, l_pac, regs, read_off):
+    """bm2_pestat: insert-size statistics of a chunk (reads 2i, 2i+1 are mates) from the regs of bm2_seed_chain_extend -> PESTAT_DT[4]."""
+    regs = np.ascontiguousarray(regs, REG_DT); read_off = np.ascontiguousarray(read_off, np.int64)
+    out = np.zeros(4, PESTAT_DT)
+    f = lib().bm2_pestat
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = f(C.addressof(opt), int(l_pac), len(read_off) - 1, regs.ctypes.data, read_off.ctypes.data, out.ctypes.data)
+    if rc:
+        raise Bm2Error(f"bm2_pestat failed ({rc})")
+    return out
 
 
 class Index:

@@ -66,7 +66,7 @@ BM2_HD KswRes ksw_pass_d(int size, int qlen, const uint8_t *query, int qstride, 
         }
         if (rowmax >= minsc) {
             if (n_b == 0 || bpos[n_b - 1] + 1 != i) {
-                if (n_b < bcap) { bsc[n_b] = rowmax; bpos[n_b] = i; ++n_b; } else *overflow = 1;
+                if (n_b < bcap) { bsc[n_b] = rowmax; bpos[n_b] = i; ++n_b; } else *overflow |= 32;            // BM2_OVF_KSW_LIST (sam_device.cuh)
             } else if (bsc[n_b - 1] < rowmax) { bsc[n_b - 1] = rowmax; bpos[n_b - 1] = i; }
         }
         if (rowmax > gmax) {

@@ -22,12 +22,19 @@ BM2_HD int mate_infer_dir_d(int64_t l_pac, int64_t b1, int64_t b2, int64_t *dist
 // scratch of one pair
 struct MateScratch {
     uint8_t *rev;            // l_ms bytes: the reverse complement of the mate
-    uint8_t *tmp;            // window bytes (ksw_align2's reversed target)
+    uint8_t *tmp; int tcap;  // tcap bytes, tcap >= mate_window_max_d(): ksw_align2's reversed target
     int32_t *ksw;            // 3 * (l_ms + 16) ints
-    int32_t *bsc, *bpos; int bcap;
+    int32_t *bsc, *bpos; int bcap;       // score2 candidates: rows of one window, neighbours merged -> bcap >= tcap / 2 + 1 never overflows
     int32_t *idx;            // regions + 4 ints
     TailSortKey *keys;       // regions + 4 keys
 };
+
+// longest window mem_matesw can ask for with these statistics and a mate of l_ms bases (:173-181): high - low + l_ms
+BM2_HD int mate_window_max_d(const MatePes &pes, int l_ms) {
+    int w = 0;
+    for (int r = 0; r < 4; ++r) if (!pes.failed[r] && pes.high[r] - pes.low[r] > w) w = pes.high[r] - pes.low[r];
+    return w + l_ms;
+}
 
 // mem_matesw: a = the anchor, ms = the mate's codes; ma[0..*n_ma) the mate's regions with room for 4 more.  Returns n.
 BM2_HD int matesw_d(const ContigView &cv, const ExtParams &ep, int min_seed_len, const MatePes &pes, const uint8_t *ref, const bm2_alnreg_t *a, int l_ms,
@@ -67,6 +74,7 @@ BM2_HD int matesw_d(const ContigView &cv, const ExtParams &ep, int min_seed_len,
             re = re < far_end ? re : far_end;
         }
         if (a->rid == rid && re - rb >= min_seed_len) {
+            if (re - rb > sc.tcap) { *overflow |= 64; continue; }             // BM2_OVF_WINDOW (sam_device.cuh): scratch sized for other statistics
             const int xtra = BM2_KSW_XSUBO | BM2_KSW_XSTART | (l_ms * ep.a < 250 ? BM2_KSW_XBYTE : 0) | (min_seed_len * ep.a);
             const KswRes al = ksw_align2_d(l_ms, seq, (int) (re - rb), ref + rb, ep.mat, ep.o_del, ep.e_del, ep.o_ins, ep.e_ins, xtra, sc.ksw, sc.bsc, sc.bpos,
                                            sc.bcap, sc.tmp, overflow);

@@ -12,6 +12,14 @@
 #include "mate_device.cuh"
 #include "cigar_device.cuh"
 
+// why a pair could not be finished with the scratch it was given (bits of *overflow; the driver grows that buffer and re-runs)
+#define BM2_OVF_LOG 1          // an argument of log() beyond the host-filled table
+#define BM2_OVF_PAIR_TERM 2    // an insert size outside the host-filled pairing-term table
+#define BM2_OVF_POOL 8         // CIGAR / MD storage of the records
+#define BM2_OVF_RECORDS 16     // records per read (aa_cap)
+#define BM2_OVF_KSW_LIST 32    // score2 candidates of one local alignment (bcap)
+#define BM2_OVF_WINDOW 64      // a rescue window longer than MateScratch::tcap
+
 struct SamParams {
     ExtParams ep;                 // a, b, gaps, w, mat
     int T, flag, min_seed_len, pen_unpaired;
@@ -123,17 +131,17 @@ BM2_HD int sam_mapq_se_d(const SamParams &p, const SamTables &tb, const bm2_alnr
     const double identity = 1. - (double) (l * p.ep.a - a->score) / (p.ep.a + p.ep.b) / l;
     if (a->score == 0) mapq = 0;
     else if (p.mapQ_coef_len > 0) {
-        if (l >= tb.n_log) { *overflow = 1; return 0; }
+        if (l >= tb.n_log) { *overflow |= BM2_OVF_LOG; return 0; }
         double tmp = l < p.mapQ_coef_len ? 1. : p.mapQ_coef_fac / tb.log_tab[l];
         tmp *= identity * identity;
         mapq = (int) (6.02 * (a->score - sub) / p.ep.a * tmp * tmp + .499);
     } else {
-        if (a->seedcov < 0 || a->seedcov >= tb.n_log) { *overflow = 1; return 0; }
+        if (a->seedcov < 0 || a->seedcov >= tb.n_log) { *overflow |= BM2_OVF_LOG; return 0; }
         mapq = (int) (30.0 * (1. - (double) sub / a->score) * tb.log_tab[a->seedcov] + .499);
         mapq = identity < 0.95 ? (int) (mapq * identity * identity + .499) : mapq;
     }
     if (a->sub_n > 0) {
-        if (a->sub_n + 1 >= tb.n_log) { *overflow = 1; return 0; }
+        if (a->sub_n + 1 >= tb.n_log) { *overflow |= BM2_OVF_LOG; return 0; }
         mapq -= (int) (4.343 * tb.log_tab[a->sub_n + 1] + .499);
     }
     if (mapq > 60) mapq = 60;
@@ -198,23 +206,12 @@ BM2_HD void sam_reg2aln_d(const SamParams &p, const SamTables &tb, const ContigV
 
 struct SamP64 { uint64_t x, y; };
 
-// mem_pair (src/bwamem_pair.cpp:285-346).  v: n_pri[0] + n_pri[1] entries, u: ucap entries.
-BM2_HD int sam_pair_d(const SamParams &p, const SamTables &tb, const ContigView &cv, const MatePes &pes, bm2_alnreg_t *const a[2], int id, int *sub, int *n_sub,
-                      int z[2], const int n_pri[2], SamP64 *v, SamP64 *u, int ucap, int *overflow)
-{
-    const int64_t l_pac = cv.l_pac;
-    int nv = 0, nu = 0;
-    for (int r = 0; r < 2; ++r)
-        for (int i = 0; i < n_pri[r]; ++i) {
-            const bm2_alnreg_t *e = &a[r][i];
-            SamP64 key;
-            key.x = (uint64_t) (e->rb < l_pac ? e->rb : (l_pac << 1) - 1 - e->rb);
-            key.x = (uint64_t) e->rid << 32 | (key.x - (uint64_t) cv.ann_off[e->rid]);
-            key.y = (uint64_t) e->score << 32 | (uint64_t) (i << 2 | (e->rb >= l_pac) << 1 | r);
-            v[nv++] = key;
-        }
-    auto lt = [](const SamP64 &s, const SamP64 &t) { return s.x < t.x || (s.x == t.x && s.y < t.y); };
-    ks_introsort_d(v, (long) nv, lt);
+// mem_pair (src/bwamem_pair.cpp:285-346).  v: n_pri[0] + n_pri[1] entries.  The reference collects every candidate pair in a growing
+// array `u`, sorts it and reads off the best entry, the score of the second best and the number of entries within a small score
+// distance of the second best.  A read pair inside a tandem repeat has 10^5 candidates, so nothing is stored here: the candidates
+// are enumerated twice (best two, then the count); the keys are the reference's, so the order - hash tie-break included - is too.
+template <class F>
+BM2_HD void sam_pair_enum_d(const SamTables &tb, const MatePes &pes, const SamP64 *v, int nv, int id, int *overflow, F &f) {
     int y[4] = { -1, -1, -1, -1 };
     for (int i = 0; i < nv; ++i) {
         for (int r = 0; r < 2; ++r) {
@@ -227,33 +224,62 @@ BM2_HD int sam_pair_d(const SamParams &p, const SamTables &tb, const ContigView 
                 const int64_t dist = (int64_t) v[i].x - (int64_t) v[k].x;
                 if (dist > pes.high[dir]) break;
                 if (dist < pes.low[dir]) continue;
-                if (dist < tb.pair_lo[dir] || dist > tb.pair_hi[dir]) { *overflow = 1; continue; }
+                if (dist < tb.pair_lo[dir] || dist > tb.pair_hi[dir]) { *overflow |= BM2_OVF_PAIR_TERM; continue; }
                 int q = (int) ((double) ((v[i].y >> 32) + (v[k].y >> 32)) + tb.pair_term[dir][dist - tb.pair_lo[dir]] + .499);
                 if (q < 0) q = 0;
-                if (nu >= ucap) { *overflow = 1; continue; }
                 SamP64 e;
                 e.y = (uint64_t) k << 32 | (uint64_t) i;
                 e.x = (uint64_t) q << 32 | (sam_hash64_d(e.y ^ (uint64_t) (int64_t) (id << 8)) & 0xffffffffU);
-                u[nu++] = e;
+                f(e);
             }
         }
         y[v[i].y & 3] = i;
     }
-    int ret;
-    if (nu) {
+}
+
+BM2_HD int sam_pair_d(const SamParams &p, const SamTables &tb, const ContigView &cv, const MatePes &pes, bm2_alnreg_t *const a[2], int id, int *sub, int *n_sub,
+                      int z[2], const int n_pri[2], SamP64 *v, int *overflow)
+{
+    const int64_t l_pac = cv.l_pac;
+    int nv = 0;
+    for (int r = 0; r < 2; ++r)
+        for (int i = 0; i < n_pri[r]; ++i) {
+            const bm2_alnreg_t *e = &a[r][i];
+            SamP64 key;
+            key.x = (uint64_t) (e->rb < l_pac ? e->rb : (l_pac << 1) - 1 - e->rb);
+            key.x = (uint64_t) e->rid << 32 | (key.x - (uint64_t) cv.ann_off[e->rid]);
+            key.y = (uint64_t) e->score << 32 | (uint64_t) (i << 2 | (e->rb >= l_pac) << 1 | r);
+            v[nv++] = key;
+        }
+    auto lt = [](const SamP64 &s, const SamP64 &t) { return s.x < t.x || (s.x == t.x && s.y < t.y); };
+    ks_introsort_d(v, (long) nv, lt);
+    long long nu = 0;
+    SamP64 best; best.x = 0; best.y = 0;
+    int second = 0;                                        // score of the second entry from the top of the sorted list
+    auto top2 = [&](const SamP64 &e) {
+        if (nu == 0 || lt(best, e)) { if (nu) second = (int) (best.x >> 32); best = e; }
+        else if (nu == 1 || (int) (e.x >> 32) > second) second = (int) (e.x >> 32);
+        ++nu;
+    };
+    sam_pair_enum_d(tb, pes, v, nv, id, overflow, top2);
+    *sub = 0; *n_sub = 0;
+    if (nu == 0) return 0;
+    const int i = (int) (best.y >> 32), k = (int) (best.y << 32 >> 32);
+    z[v[i].y & 1] = (int) (v[i].y << 32 >> 34);
+    z[v[k].y & 1] = (int) (v[k].y << 32 >> 34);
+    if (nu > 1) {
         int tmp = p.ep.a + p.ep.b;
         tmp = tmp > p.ep.o_del + p.ep.e_del ? tmp : p.ep.o_del + p.ep.e_del;
         tmp = tmp > p.ep.o_ins + p.ep.e_ins ? tmp : p.ep.o_ins + p.ep.e_ins;
-        ks_introsort_d(u, (long) nu, lt);
-        const int i = (int) (u[nu - 1].y >> 32), k = (int) (u[nu - 1].y << 32 >> 32);
-        z[v[i].y & 1] = (int) (v[i].y << 32 >> 34);
-        z[v[k].y & 1] = (int) (v[k].y << 32 >> 34);
-        ret = (int) (u[nu - 1].x >> 32);
-        *sub = nu > 1 ? (int) (u[nu - 2].x >> 32) : 0;
-        *n_sub = 0;
-        for (int j = nu - 2; j >= 0; --j) if (*sub - (int) (u[j].x >> 32) <= tmp) ++*n_sub;
-    } else { ret = 0; *sub = 0; *n_sub = 0; }
-    return ret;
+        *sub = second;
+        long long cnt = 0;                                 // entries below the top one with sub - score <= tmp
+        const int sb = second;
+        auto count = [&](const SamP64 &e) { if (sb - (int) (e.x >> 32) <= tmp) ++cnt; };
+        sam_pair_enum_d(tb, pes, v, nv, id, overflow, count);
+        if (sb - (int) (best.x >> 32) <= tmp) --cnt;       // the top entry itself
+        *n_sub = cnt > 0x7fffffff ? 0x7fffffff : (int) cnt;
+    }
+    return (int) (best.x >> 32);
 }
 
 BM2_HD int sam_rlen_d(const SamAln &a) { int l = 0; for (int k = 0; k < a.n_cigar; ++k) { const int op = a.cigar[k] & 0xf; if (op == 0 || op == 2) l += a.cigar[k] >> 4; } return l; }
@@ -320,7 +346,7 @@ BM2_HD void sam_reorder_primary5_d(int T, int n, bm2_alnreg_t *a) {
 // Scratch of one pair for the SAM stage.
 struct SamScratch {
     int32_t *z, *idx;              // max(n0, n1) + 4 ints each
-    SamP64 *v, *u; int ucap;       // n0 + n1 entries, ucap entries
+    SamP64 *v;                     // n0 + n1 entries
     int32_t *he; CigarZ zz;        // global alignment: 2 * (max read length + 1) ints; backtrack cells
     SamAln *aa[2]; int aa_cap;     // per read: records to print (regions + 2)
     uint32_t *cig_pool; long long cig_cap; char *md_pool; long long md_cap;      // storage of the records' CIGAR / MD
@@ -359,7 +385,7 @@ BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigV
             }
     };
     if (!(p.flag & 0x4) && n_pri[0] && n_pri[1] &&
-        (o = sam_pair_d(p, tb, cv, pes, a, id, &subo, &n_sub, z, n_pri, sc.v, sc.u, sc.ucap, overflow)) > 0) {
+        (o = sam_pair_d(p, tb, cv, pes, a, id, &subo, &n_sub, z, n_pri, sc.v, overflow)) > 0) {
         int is_multi[2];
         for (int i = 0; i < 2; ++i) {
             int j;
@@ -372,7 +398,7 @@ BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigV
             const int score_un = a[0][0].score + a[1][0].score - p.pen_unpaired;
             subo = subo > score_un ? subo : score_un;
             q_pe = sam_raw_mapq_d(o - subo, p.ep.a);
-            if (n_sub > 0) { if (n_sub + 1 >= tb.n_log) *overflow = 1; else q_pe -= (int) (4.343 * tb.log_tab[n_sub + 1] + .499); }
+            if (n_sub > 0) { if (n_sub + 1 >= tb.n_log) *overflow |= BM2_OVF_LOG; else q_pe -= (int) (4.343 * tb.log_tab[n_sub + 1] + .499); }
             if (q_pe < 0) q_pe = 0;
             if (q_pe > 60) q_pe = 60;
             q_pe = (int) (q_pe * (1. - .5 * (a[0][0].frac_rep + a[1][0].frac_rep)) + .499);
@@ -401,7 +427,7 @@ BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigV
                 }
             }
             for (int i = 0; i < 2; ++i) {
-                if (!sam_alloc_d(pl, l_seq[i], &a[i][z[i]], &h[i])) { *overflow = 1; return; }
+                if (!sam_alloc_d(pl, l_seq[i], &a[i][z[i]], &h[i])) { *overflow |= BM2_OVF_POOL; return; }
                 sam_reg2aln_d(p, tb, cv, ref, l_seq[i], seq[i], &a[i][z[i]], sc.he, sc.zz, &h[i], overflow);
                 h[i].mapq = q_se[i];
                 h[i].flag |= 0x40 << i | extra_flag;
@@ -410,7 +436,7 @@ BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigV
                     const bm2_alnreg_t *q = &a[i][n_pri[i]];
                     if (q->score < p.T || q->secondary >= 0 || !sam_is_alt_d(*q)) continue;
                     SamAln g;
-                    if (!sam_alloc_d(pl, l_seq[i], q, &g)) { *overflow = 1; return; }
+                    if (!sam_alloc_d(pl, l_seq[i], q, &g)) { *overflow |= BM2_OVF_POOL; return; }
                     sam_reg2aln_d(p, tb, cv, ref, l_seq[i], seq[i], q, sc.he, sc.zz, &g, overflow);
                     g.flag |= 0x800 | 0x40 << i | extra_flag;
                     sc.aa[i][n_aa[i]++] = g;
@@ -427,7 +453,7 @@ BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigV
             if (a[i][0].score >= p.T) which = 0;
             else if (n_pri[i] < n[i] && a[i][n_pri[i]].score >= p.T) which = n_pri[i];
         }
-        if (!sam_alloc_d(pl, l_seq[i], which >= 0 ? &a[i][which] : 0, &h[i])) { *overflow = 1; return; }
+        if (!sam_alloc_d(pl, l_seq[i], which >= 0 ? &a[i][which] : 0, &h[i])) { *overflow |= BM2_OVF_POOL; return; }
         sam_reg2aln_d(p, tb, cv, ref, l_seq[i], seq[i], which >= 0 ? &a[i][which] : 0, sc.he, sc.zz, &h[i], overflow);
     }
     if (!(p.flag & 0x4) && h[0].rid == h[1].rid && h[0].rid >= 0) {
@@ -443,9 +469,9 @@ BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigV
             if (q->score < p.T) continue;
             if (q->secondary >= 0 && (sam_is_alt_d(*q) || !(p.flag & 0x8))) continue;
             if (q->secondary >= 0 && q->secondary < 0x7fffffff && q->score < a[i][q->secondary].score * p.drop_ratio) continue;
-            if (n_aa[i] >= sc.aa_cap) { *overflow = 1; break; }
+            if (n_aa[i] >= sc.aa_cap) { *overflow |= BM2_OVF_RECORDS; break; }
             SamAln &t = sc.aa[i][n_aa[i]];
-            if (!sam_alloc_d(pl, l_seq[i], q, &t)) { *overflow = 1; return; }
+            if (!sam_alloc_d(pl, l_seq[i], q, &t)) { *overflow |= BM2_OVF_POOL; return; }
             sam_reg2aln_d(p, tb, cv, ref, l_seq[i], seq[i], q, sc.he, sc.zz, &t, overflow);
             t.flag |= ef;
             if (q->secondary >= 0) t.sub = -1;
@@ -455,7 +481,7 @@ BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigV
         }
         if (n_aa[i] == 0) {
             SamAln &t = sc.aa[i][0];
-            if (!sam_alloc_d(pl, l_seq[i], 0, &t)) { *overflow = 1; return; }
+            if (!sam_alloc_d(pl, l_seq[i], 0, &t)) { *overflow |= BM2_OVF_POOL; return; }
             sam_reg2aln_d(p, tb, cv, ref, l_seq[i], seq[i], 0, sc.he, sc.zz, &t, overflow);
             t.flag |= ef;
             n_aa[i] = 1;

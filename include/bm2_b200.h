@@ -244,6 +244,20 @@ typedef struct bm2_cigar_result {
 /* Needs a context created with an index.  Result arrays are owned by the context (valid until its next call). */
 int bm2_gen_cigar(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_cigar_req *reqs, int64_t n, bm2_cigar_result *out);
 
+/* ---- seam 4, first piece: insert-size statistics -------------------------------------------------------------------------
+ * Replaces mem_pestat (reference src/bwamem_pair.cpp:81-148), called once per chunk between the alignment regions (seam 2) and
+ * the SAM stage (src/bwamem.cpp:1368-1378).  Host code, as in the reference: one pass over the best region of every read; no
+ * context, no device.  regs / read_off: the output of bm2_seed_chain_extend for a chunk whose reads 2i, 2i+1 are mates.
+ * pes[d], d = FF, FR, RF, RR: mem_pestat_t (src/bwamem.h:162-166).  Returns 0; 1 on bad arguments; 2 where the reference
+ * asserts (no insert size inside the outlier bounds). */
+typedef struct bm2_pestat_t {
+    int32_t low, high;         /* proper-pair bounds of the insert size                      */
+    int32_t failed;            /* too few pairs of this orientation                          */
+    int32_t _pad;
+    double avg, std;
+} bm2_pestat_t;
+int bm2_pestat(const bm2_mem_opt_t *opt, int64_t l_pac, int32_t n_reads, const bm2_alnreg_t *regs, const int64_t *read_off, bm2_pestat_t pes[4]);
+
 #ifdef __cplusplus
 }
 #endif

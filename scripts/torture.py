@@ -2,7 +2,7 @@
 """One-off differential run on hostile input (CPU only, needs oracle/_ref): many tiny contigs, N runs, microsatellites and tandem repeats in the
 reference; reads of mixed lengths (25-251), homopolymers, dinucleotide repeats, N-rich reads, reads spanning contig ends.  The UNMODIFIED reference
 (regs dumped by ref_driver's hooks, SAM) against the oracle (regs, SAM text) and the kernels' device logic (host emulation).
-Usage: torture.py <seed> [mem options ...]"""
+Usage: torture.py <seed> [mem options ...]      (BM2_TORTURE_LONG=1: a tenth of the pairs are 0.8-3 kb reads, for mem_flt_chained_seeds)"""
 import os, subprocess, sys, tempfile
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -41,12 +41,13 @@ def main():
     ref = np.ctypeslib.as_array(C.cast(idx.desc.ref_string, C.POINTER(C.c_uint8)), shape=(2 * l_pac,))
     comp = np.array([3, 2, 1, 0, 4], np.uint8)
     reads = []
-    n_pairs = 4000
+    n_pairs = int(os.environ.get("BM2_TORTURE_PAIRS", "4000"))
     for p in range(n_pairs):
         L1 = int(rng.choice([25, 36, 50, 76, 101, 151, 151, 151, 200, 251])); L2 = int(rng.choice([25, 50, 76, 151, 151, 251]))
+        if os.environ.get("BM2_TORTURE_LONG") and p % 10 == 0: L1 = int(rng.integers(800, 3000)); L2 = int(rng.integers(800, 3000))
         kind = rng.random()
         if kind < 0.70:                                        # a fragment from the text (may span contig ends / N-filled holes)
-            ins = int(max(rng.normal(350, 60), max(L1, L2) + 5)); st = int(rng.integers(0, l_pac - ins))
+            ins = int(max(rng.normal(350, 60), max(L1, L2) + 5)); ins = min(ins, int(l_pac) - 10); st = int(rng.integers(0, l_pac - ins))
             frag = ref[st:st + ins].copy(); mut = rng.random(ins) < 0.015; frag[mut] = rng.integers(0, 4, int(mut.sum()))
             if rng.random() < 0.2:
                 q = int(rng.integers(5, ins - 5)); d = int(rng.integers(1, 12)); frag = np.concatenate([frag[:q], frag[q + d:]]) if rng.random() < .5 else np.concatenate([frag[:q], rng.integers(0, 4, d).astype(np.uint8), frag[q:]])
@@ -78,6 +79,9 @@ def main():
     class R:                                                   # _pestat only needs len(reads)
         def __len__(self): return len(reads)
     lh, as_ = tp._pestat(capi, idx, opt2, R(), regs, ro)
+    pp = capi.pestat(opt2, l_pac, regs, ro)                    # the product's host-side mem_pestat against the oracle's (pinned to the reference's dump)
+    pes_ok = all((int(pp[d]["low"]), int(pp[d]["high"]), int(pp[d]["failed"])) == tuple(int(v) for v in lh[3 * d:3 * d + 3]) and
+                 (pp[d]["failed"] or (pp[d]["avg"] == as_[2 * d] and pp[d]["std"] == as_[2 * d + 1])) for d in range(4))
     names = [l.split()[1] for i, l in enumerate(open(work + "/ref.fa.ann")) if i % 2 == 1]
     tgot = tp.oracle_sam_text(capi, idx, opt2, codes, offs, regs, ro, lh, as_, names)
     twant = [ln.rstrip("\n").split("\t", 1)[1] for ln in open(work + "/o.sam") if not ln.startswith("@")]
@@ -89,7 +93,7 @@ def main():
     except AssertionError as ex:
         sam_dev = "DIFFERS: " + str(ex)[:300]
     print(f"seed {seed} {args}: {len(reads)} reads, {len(rr)} regs (max per read {int(np.diff(roff).max())}); oracle vs reference: {len(bad)} differing reads {bad[:5]}; "
-          f"device logic == oracle: {e.tobytes() == regs.tobytes() and np.array_equal(eo, ro)}; SAM lines {len(twant)} vs {len(tgot)}, differing text {len(tbad)} {tbad[:3]}; SAM-stage device logic {sam_dev}")
+          f"device logic == oracle: {e.tobytes() == regs.tobytes() and np.array_equal(eo, ro)}; SAM lines {len(twant)} vs {len(tgot)}, differing text {len(tbad)} {tbad[:3]}; SAM-stage device logic {sam_dev}; bm2_pestat == oracle: {pes_ok}")
     for i in tbad[:2]:
         g = tgot[i].split("\t"); w = twant[i].split("\t")
         for a, b in zip(g, w):

@@ -34,10 +34,11 @@ extern "C" long long emul_mate_rescue(const bm2_index_desc *idx, const bm2_mem_o
             b[i].resize((size_t) n[i] + 1);
         }
         const size_t nreg = a[0].size() + a[1].size();
-        std::vector<uint8_t> rev((size_t) max_l + 1), tmp((size_t) 1 << 16);
-        std::vector<int32_t> ksw((size_t) 3 * (max_l + 16)), bsc(256), bpos(256), idxv(nreg + 8);
+        const int tcap = mate_window_max_d(pes, max_l) + 16;            // the driver sizes the window scratch from the statistics
+        std::vector<uint8_t> rev((size_t) max_l + 1), tmp((size_t) tcap);
+        std::vector<int32_t> ksw((size_t) 3 * (max_l + 16)), bsc((size_t) tcap / 2 + 2), bpos((size_t) tcap / 2 + 2), idxv(nreg + 8);
         std::vector<TailSortKey> keys(nreg + 8);
-        MateScratch sc = { rev.data(), tmp.data(), ksw.data(), bsc.data(), bpos.data(), 256, idxv.data(), keys.data() };
+        MateScratch sc = { rev.data(), tmp.data(), tcap, ksw.data(), bsc.data(), bpos.data(), tcap / 2 + 2, idxv.data(), keys.data() };
         bm2_alnreg_t *ap[2] = { a[0].data(), a[1].data() }, *bp[2] = { b[0].data(), b[1].data() };
         total += mate_rescue_pair_d(cv, ep, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, idx->ref_string, seq, l_seq, ap, n, bp, sc, &overflow);
         for (int i = 0; i < 2; ++i) {

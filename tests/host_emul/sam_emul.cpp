@@ -52,20 +52,21 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
             b[i].resize((size_t) n[i] + 1);
         }
         const size_t nreg = a[0].size() + a[1].size();
-        std::vector<uint8_t> rev((size_t) max_l + 1), tmp((size_t) 1 << 16);
-        std::vector<int32_t> ksw((size_t) 3 * (max_l + 16)), bsc(256), bpos(256), idxv(nreg + 8), zv(nreg + 8), he((size_t) 2 * (max_l + 2));
+        const int tcap = mate_window_max_d(pes, max_l) + 16;            // the driver sizes the window scratch from the statistics
+        std::vector<uint8_t> rev((size_t) max_l + 1), tmp((size_t) tcap);
+        std::vector<int32_t> ksw((size_t) 3 * (max_l + 16)), bsc((size_t) tcap / 2 + 2), bpos((size_t) tcap / 2 + 2), idxv(nreg + 8), zv(nreg + 8), he((size_t) 2 * (max_l + 2));
         std::vector<TailSortKey> keys(nreg + 8);
-        MateScratch ms = { rev.data(), tmp.data(), ksw.data(), bsc.data(), bpos.data(), 256, idxv.data(), keys.data() };
+        MateScratch ms = { rev.data(), tmp.data(), tcap, ksw.data(), bsc.data(), bpos.data(), tcap / 2 + 2, idxv.data(), keys.data() };
         bm2_alnreg_t *ap[2] = { a[0].data(), a[1].data() }, *bp[2] = { b[0].data(), b[1].data() };
         if (!(opt->flag & 0x20)) mate_rescue_pair_d(cv, p.ep, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, idx->ref_string, seq, l_seq, ap, n, bp, ms, &overflow);
         // SAM stage
-        std::vector<SamP64> v(nreg + 4), u(4096);
+        std::vector<SamP64> v(nreg + 4);
         std::vector<uint8_t> zbuf((size_t) (max_l + 8) * (size_t) (max_l + 4 * opt->w + 64));
         std::vector<SamAln> aa0((size_t) n[0] + 4), aa1((size_t) n[1] + 4);
         std::vector<uint32_t> cig_pool((size_t) (nreg + 8) * (size_t) (3 * max_l + 512)), opsv((size_t) 3 * max_l + 512);
         std::vector<char> md_pool((size_t) (nreg + 8) * (size_t) (12 * max_l + 2048));
         SamScratch sc;
-        sc.z = zv.data(); sc.idx = idxv.data(); sc.v = v.data(); sc.u = u.data(); sc.ucap = (int) u.size(); sc.he = he.data();
+        sc.z = zv.data(); sc.idx = idxv.data(); sc.v = v.data(); sc.he = he.data();
         sc.zz.base = zbuf.data(); sc.zz.stride = 1; sc.aa[0] = aa0.data(); sc.aa[1] = aa1.data(); sc.aa_cap = (int) (n[0] > n[1] ? n[0] : n[1]) + 2;
         sc.cig_pool = cig_pool.data(); sc.cig_cap = (long long) cig_pool.size(); sc.md_pool = md_pool.data(); sc.md_cap = (long long) md_pool.size(); sc.ops = opsv.data();
         auto emit = [&](int i, int k, const SamRec &r, const uint32_t *ops, const char *md) {
@@ -85,5 +86,5 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
     *cigar_out = (uint32_t *) malloc(4 * (ops_all.size() + 1)); memcpy(*cigar_out, ops_all.data(), 4 * ops_all.size());
     *md_out = (char *) malloc(md_all.size() + 1); memcpy(*md_out, md_all.data(), md_all.size());
     *n_recs = (int64_t) nr; *n_ops_out = (int64_t) ops_all.size(); *n_md_out = (int64_t) md_all.size();
-    return overflow ? 3 : 0;
+    return overflow ? 0x100 | overflow : 0;
 }

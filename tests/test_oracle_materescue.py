@@ -51,6 +51,20 @@ def test_pestat_matches_reference(c0):
     assert pes[1][2] == 0 and pes[1][0] > 0                                      # FR is the orientation of the data set
 
 
+def test_product_pestat_matches_reference(c0):
+    """bm2_pestat of the C ABI (host code of the product, bwa-mem2_b200/csrc/pestat.cpp) against the reference's mem_pestat dump."""
+    capi, idx, opt, reads, regs, ro, pes, work, prefix = c0
+    got = capi.pestat(opt, idx.desc.l_pac, regs, ro)
+    for d in range(4):
+        assert (int(got[d]["low"]), int(got[d]["high"]), int(got[d]["failed"])) == pes[d][:3], (d, got, pes)
+        assert got[d]["avg"] == pes[d][3] and got[d]["std"] == pes[d][4]          # bit-identical doubles (0 for a failed orientation)
+    # degenerate chunks: no reads, reads without regions
+    empty = capi.pestat(opt, idx.desc.l_pac, regs[:0], np.zeros(1, np.int64))
+    assert all(int(e["failed"]) == 1 for e in empty)
+    none = capi.pestat(opt, idx.desc.l_pac, regs[:0], np.zeros(9, np.int64))
+    assert all(int(e["failed"]) == 1 for e in none)
+
+
 def test_matesw_matches_reference(c0):
     capi, idx, opt, reads, regs, ro, pes, work, prefix = c0
     n_pairs = len(reads) // 2
