@@ -25,6 +25,7 @@ struct SamParams {
     int T, flag, min_seed_len, pen_unpaired;
     float mask_level, drop_ratio;
     float mapQ_coef_len; int mapQ_coef_fac;
+    float XA_drop_ratio; int max_XA_hits, max_XA_hits_alt;
 };
 struct SamTables {
     const double *log_tab; int n_log;          // log_tab[k] = log((double) k), k < n_log (k = 0 unused)
@@ -32,11 +33,14 @@ struct SamTables {
 };
 struct SamAln {                    // mem_aln_t subset
     int flag, rid, mapq, nm, score, sub, is_rev, is_alt, alt_sc, n_cigar, n_md;
+    int reg;                      // index of the region it was made from (the key of its XA entries), -1: none
     int64_t pos;
     uint32_t *cigar; char *md;    // storage provided by the caller: l_query + rlen + 4 ops, 2*l_query + 7*rlen + 16 bytes
 };
 struct SamRec {                    // the columns of one SAM line (bm2o_samrec without the offsets)
     int flag, rid, mapq, rnext, nm, score, sub, n_cigar, n_md;
+    int reg;                      // SamAln::reg
+    int alt_sc;                   // > 0: the pa tag is score / alt_sc (src/bwamem.cpp:1713-1714; not printed on 0x100 records)
     int64_t pos, pnext, tlen;
 };
 
@@ -162,7 +166,7 @@ BM2_HD int sam_infer_bw_d(int l1, int l2, int score, int a, int q, int r) {     
 BM2_HD void sam_reg2aln_d(const SamParams &p, const SamTables &tb, const ContigView &cv, const uint8_t *ref, int l_query, const uint8_t *query,
                           const bm2_alnreg_t *ar, int32_t *he, const CigarZ &z, SamAln *a, int *overflow)
 {
-    a->flag = 0; a->rid = -1; a->mapq = 0; a->nm = 0; a->score = 0; a->sub = 0; a->is_rev = 0; a->is_alt = 0; a->alt_sc = 0; a->n_cigar = 0; a->n_md = 0; a->pos = -1;
+    a->reg = -1; a->flag = 0; a->rid = -1; a->mapq = 0; a->nm = 0; a->score = 0; a->sub = 0; a->is_rev = 0; a->is_alt = 0; a->alt_sc = 0; a->n_cigar = 0; a->n_md = 0; a->pos = -1;
     if (ar == 0 || ar->rb < 0 || ar->re < 0) { a->flag |= 0x4; return; }
     const int qb = ar->qb, qe = ar->qe;
     const int64_t rb = ar->rb, re = ar->re;
@@ -321,7 +325,7 @@ BM2_HD void sam_aln2rec_d(const SamParams &prm, const SamAln &p_, int which, con
         }
     }
     r->nm = n_cigar ? p_.nm : 0; r->n_md = n_cigar ? p_.n_md : 1;
-    r->score = p_.score; r->sub = p_.sub;
+    r->score = p_.score; r->sub = p_.sub; r->reg = p_.reg; r->alt_sc = p_.alt_sc;
 }
 
 // mem_reorder_primary5 (src/bwamem.cpp:1496-1518), option -5: the primary with the smallest query start becomes record 0
@@ -340,6 +344,33 @@ BM2_HD void sam_reorder_primary5_d(int T, int n, bm2_alnreg_t *a) {
         bm2_alnreg_t &q = a[k];
         if (q.secondary == 0) q.secondary = left_k; else if (q.secondary == left_k) q.secondary = 0;
         if (q.secondary_all == 0) q.secondary_all = left_k; else if (q.secondary_all == left_k) q.secondary_all = 0;
+    }
+}
+
+// mem_gen_alt (src/bwamem_extra.cpp:130-183): the entries of the XA tags of one read, in the reference's order.  An entry belongs to
+// the region r = secondary_all of the hit it describes and is printed with every record made from region r (SamAln::reg).
+// emit(r, t): t.rid, t.is_rev, t.pos, t.cigar[0..n_cigar), t.nm are the fields of the entry; t's storage is reused by the next one.
+// cnt / has_alt: n ints each.  Call after mem_mark_primary_se (and after the paired path's secondary_all fix-up).
+template <class EmitXa>
+BM2_HD void sam_gen_alt_d(const SamParams &p, const SamTables &tb, const ContigView &cv, const uint8_t *ref, int l_query, const uint8_t *query,
+                          const bm2_alnreg_t *a, int n, int32_t *cnt, int32_t *has_alt, int32_t *he, const CigarZ &zz, SamAln &t, EmitXa &emit, int *overflow)
+{
+    const double drop = p.XA_drop_ratio;                  // get_pri_idx takes the float option as a double (src/bwamem_extra.cpp:122)
+    int tot = 0;
+    for (int i = 0; i < n; ++i) { cnt[i] = 0; has_alt[i] = 0; }
+    for (int i = 0; i < n; ++i) {
+        const int k = a[i].secondary_all;
+        if (k < 0 || !(a[i].score >= a[k].score * drop)) continue;
+        ++cnt[k]; ++tot;
+        if (sam_is_alt_d(a[i])) has_alt[k] = 1;
+    }
+    if (tot == 0) return;
+    for (int i = 0; i < n; ++i) {
+        const int r = a[i].secondary_all;
+        if (r < 0 || !(a[i].score >= a[r].score * drop)) continue;
+        if (cnt[r] > p.max_XA_hits_alt || (!has_alt[r] && cnt[r] > p.max_XA_hits)) continue;
+        sam_reg2aln_d(p, tb, cv, ref, l_query, query, &a[i], he, zz, &t, overflow);
+        emit(r, t);
     }
 }
 
@@ -363,11 +394,12 @@ BM2_HD bool sam_alloc_d(SamPool &pl, int l_query, const bm2_alnreg_t *ar, SamAln
 }
 
 // mem_sam_pe after the rescue block (src/bwamem_pair.cpp:414-552) for one pair whose regions a[i][0..n[i]) already went through mate
-// rescue.  emit(read_in_pair, record index, SamRec, printed ops, md pointer) is called once per SAM line in output order.
-template <class Emit>
+// rescue.  emit(read_in_pair, record index, SamRec, printed ops, md pointer) is called once per SAM line in output order;
+// emit_xa(read_in_pair, region, SamAln) once per XA entry (before the records; SamRec::reg of a record names its entries' region).
+template <class Emit, class EmitXa>
 BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigView &cv, const MatePes &pes, const uint8_t *ref,
                           const uint8_t *const seq[2], const int l_seq[2], bm2_alnreg_t *const a[2], const int n[2], int id, const SamScratch &sc,
-                          Emit &emit, int *overflow)
+                          Emit &emit, EmitXa &emit_xa, int *overflow)
 {
     SamPool pl = { sc.cig_pool, sc.cig_cap, 0, sc.md_pool, sc.md_cap, 0 };
     int extra_flag = 1, n_pri[2], z[2] = { 0, 0 }, o = 0, subo = 0, n_sub = 0, n_aa[2] = { 0, 0 };
@@ -377,6 +409,16 @@ BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigV
     bool paired = false;
     SamAln h[2];
     auto out_all = [&]() {
+        if (!(p.flag & 0x8))                                  // !MEM_F_ALL: XA entries (src/bwamem_pair.cpp:484-487, src/bwamem.cpp:1529-1530)
+            for (int i = 0; i < 2; ++i) {
+                if (n[i] == 0) continue;
+                bm2_alnreg_t widest; widest.rb = 0; widest.re = 0;
+                for (int k = 0; k < n[i]; ++k) if (a[i][k].re - a[i][k].rb > widest.re) widest.re = a[i][k].re - a[i][k].rb;
+                SamAln t;
+                if (!sam_alloc_d(pl, l_seq[i], &widest, &t)) { *overflow |= BM2_OVF_POOL; return; }
+                auto one = [&](int r, const SamAln &e) { emit_xa(i, r, e); };
+                sam_gen_alt_d(p, tb, cv, ref, l_seq[i], seq[i], a[i], n[i], sc.z, sc.idx, sc.he, sc.zz, t, one, overflow);
+            }
         for (int i = 0; i < 2; ++i)
             for (int k = 0; k < n_aa[i]; ++k) {
                 SamRec r;
@@ -429,7 +471,7 @@ BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigV
             for (int i = 0; i < 2; ++i) {
                 if (!sam_alloc_d(pl, l_seq[i], &a[i][z[i]], &h[i])) { *overflow |= BM2_OVF_POOL; return; }
                 sam_reg2aln_d(p, tb, cv, ref, l_seq[i], seq[i], &a[i][z[i]], sc.he, sc.zz, &h[i], overflow);
-                h[i].mapq = q_se[i];
+                h[i].mapq = q_se[i]; h[i].reg = z[i];
                 h[i].flag |= 0x40 << i | extra_flag;
                 sc.aa[i][n_aa[i]++] = h[i];
                 if (n_pri[i] < n[i]) {
@@ -438,7 +480,7 @@ BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigV
                     SamAln g;
                     if (!sam_alloc_d(pl, l_seq[i], q, &g)) { *overflow |= BM2_OVF_POOL; return; }
                     sam_reg2aln_d(p, tb, cv, ref, l_seq[i], seq[i], q, sc.he, sc.zz, &g, overflow);
-                    g.flag |= 0x800 | 0x40 << i | extra_flag;
+                    g.flag |= 0x800 | 0x40 << i | extra_flag; g.reg = n_pri[i];
                     sc.aa[i][n_aa[i]++] = g;
                 }
             }
@@ -473,7 +515,7 @@ BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigV
             SamAln &t = sc.aa[i][n_aa[i]];
             if (!sam_alloc_d(pl, l_seq[i], q, &t)) { *overflow |= BM2_OVF_POOL; return; }
             sam_reg2aln_d(p, tb, cv, ref, l_seq[i], seq[i], q, sc.he, sc.zz, &t, overflow);
-            t.flag |= ef;
+            t.flag |= ef; t.reg = k;
             if (q->secondary >= 0) t.sub = -1;
             if (l && q->secondary < 0) t.flag |= (p.flag & 0x10) ? 0x10000 : 0x800;
             if (!(p.flag & 0x1000) && l && !sam_is_alt_d(*q) && t.mapq > sc.aa[i][0].mapq) t.mapq = sc.aa[i][0].mapq;

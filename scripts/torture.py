@@ -87,9 +87,10 @@ def main():
     twant = [ln.rstrip("\n").split("\t", 1)[1] for ln in open(work + "/o.sam") if not ln.startswith("@")]
     tbad = [i for i in range(min(len(tgot), len(twant))) if tgot[i] != twant[i]]
     try:                                                       # the SAM stage's device logic (mate rescue, pairing, MAPQ, CIGAR / NM / MD) on the same input
-        tp._compare(tp.fields(*tp.emul_sam_pe(capi, idx, opt2, codes, offs, regs, ro, lh, as_), names),
-                    tp.fields(*tp.oracle_sam_pe(capi, idx, opt2, codes, offs, regs, ro, lh, as_), names))
-        sam_dev = "== oracle"
+        em = tp.emul_sam_pe(capi, idx, opt2, codes, offs, regs, ro, lh, as_, xa_names=names)
+        tp._compare(tp.fields(*em[:3], names), tp.fields(*tp.oracle_sam_pe(capi, idx, opt2, codes, offs, regs, ro, lh, as_), names))
+        assert em[3] == tp.xa_of_lines(twant), "XA entries differ from the reference's tags"
+        sam_dev = "== oracle, XA == reference"
     except AssertionError as ex:
         sam_dev = "DIFFERS: " + str(ex)[:300]
     print(f"seed {seed} {args}: {len(reads)} reads, {len(rr)} regs (max per read {int(np.diff(roff).max())}); oracle vs reference: {len(bad)} differing reads {bad[:5]}; "

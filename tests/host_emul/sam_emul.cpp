@@ -9,9 +9,13 @@
 #include "sam_device.cuh"
 #include "../../oracle/bm2_oracle.h"
 
+// one XA entry: printed with every record of `read` whose rec_reg equals `reg`
+struct EmXa { int32_t read, reg, rid, is_rev, nm, n_cigar; int64_t pos, cigar_off; };
+
 extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off,
                            const int32_t *lh, const double *as, int64_t id_base, bm2o_samrec **recs_out, int64_t *n_recs, uint32_t **cigar_out,
-                           int64_t *n_ops_out, char **md_out, int64_t *n_md_out)
+                           int64_t *n_ops_out, char **md_out, int64_t *n_md_out, int32_t **rec_reg_out, EmXa **xa_out, int64_t *n_xa_out, uint32_t **xa_cigar_out,
+                           int64_t *n_xa_ops_out)
 {
     ContigView cv; cv.l_pac = idx->l_pac; cv.n_seqs = idx->n_seqs; cv.ann_off = idx->ann_offset; cv.ann_len = idx->ann_len; cv.ann_alt = idx->ann_is_alt;
     SamParams p;
@@ -20,6 +24,7 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
     memcpy(p.ep.mat, opt->mat, 25);
     p.T = opt->T; p.flag = opt->flag; p.min_seed_len = opt->min_seed_len; p.pen_unpaired = opt->pen_unpaired; p.mask_level = opt->mask_level;
     p.drop_ratio = opt->drop_ratio; p.mapQ_coef_len = opt->mapQ_coef_len; p.mapQ_coef_fac = opt->mapQ_coef_fac;
+    p.XA_drop_ratio = opt->XA_drop_ratio; p.max_XA_hits = opt->max_XA_hits; p.max_XA_hits_alt = opt->max_XA_hits_alt;
     MatePes pes;
     for (int d = 0; d < 4; ++d) { pes.low[d] = lh[3 * d]; pes.high[d] = lh[3 * d + 1]; pes.failed[d] = lh[3 * d + 2]; }
     // host-filled libm tables
@@ -35,6 +40,7 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
         tb.pair_term[d] = term[d].data();
     }
     std::vector<bm2o_samrec> out; std::vector<uint32_t> ops_all; std::string md_all;
+    std::vector<int32_t> rec_reg; std::vector<EmXa> xa; std::vector<uint32_t> xa_ops;
     int overflow = 0;
     for (int pr = 0; pr < reads->n_reads >> 1; ++pr) {
         const uint8_t *seq[2]; int l_seq[2], n[2]; int max_l = 0;
@@ -71,20 +77,29 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
         sc.cig_pool = cig_pool.data(); sc.cig_cap = (long long) cig_pool.size(); sc.md_pool = md_pool.data(); sc.md_cap = (long long) md_pool.size(); sc.ops = opsv.data();
         auto emit = [&](int i, int k, const SamRec &r, const uint32_t *ops, const char *md) {
             bm2o_samrec o; memset(&o, 0, sizeof(o));
-            o.read = 2 * pr + i; o.flag = r.flag; o.rid = r.rid; o.mapq = r.mapq; o.rnext = r.rnext; o.tlen_valid = 1; o.nm = r.nm; o.score = r.score; o.sub = r.sub;
+            o.read = 2 * pr + i; o.flag = r.flag; o.rid = r.rid; o.mapq = r.mapq; o.rnext = r.rnext; o.tlen_valid = 1; o.nm = r.nm; o.score = r.score; o.sub = r.sub; o._pad = r.alt_sc;        /* _pad carries alt_sc (pa tag) in this test build */
             o.n_cigar = r.n_cigar; o.pos = r.pos; o.pnext = r.pnext; o.tlen = r.tlen; o.cigar_off = (int64_t) ops_all.size(); o.md_off = (int64_t) md_all.size();
             ops_all.insert(ops_all.end(), ops, ops + r.n_cigar);
             if (r.n_cigar) md_all += md;
             md_all.push_back('\0');
             o.n_md = (int32_t) (md_all.size() - (size_t) o.md_off);
-            out.push_back(o);
+            out.push_back(o); rec_reg.push_back(r.reg);
         };
-        sam_pe_pair_d(p, tb, cv, pes, idx->ref_string, seq, l_seq, ap, n, (int) (id_base + pr), sc, emit, &overflow);
+        auto emit_xa = [&](int i, int reg, const SamAln &t) {
+            EmXa e; e.read = 2 * pr + i; e.reg = reg; e.rid = t.rid; e.is_rev = t.is_rev; e.nm = t.nm; e.n_cigar = t.n_cigar; e.pos = t.pos; e.cigar_off = (int64_t) xa_ops.size();
+            xa_ops.insert(xa_ops.end(), t.cigar, t.cigar + t.n_cigar);
+            xa.push_back(e);
+        };
+        sam_pe_pair_d(p, tb, cv, pes, idx->ref_string, seq, l_seq, ap, n, (int) (id_base + pr), sc, emit, emit_xa, &overflow);
     }
     const size_t nr = out.size();
     *recs_out = (bm2o_samrec *) malloc(sizeof(bm2o_samrec) * (nr + 1)); memcpy(*recs_out, out.data(), sizeof(bm2o_samrec) * nr);
     *cigar_out = (uint32_t *) malloc(4 * (ops_all.size() + 1)); memcpy(*cigar_out, ops_all.data(), 4 * ops_all.size());
     *md_out = (char *) malloc(md_all.size() + 1); memcpy(*md_out, md_all.data(), md_all.size());
+    *rec_reg_out = (int32_t *) malloc(4 * (nr + 1)); memcpy(*rec_reg_out, rec_reg.data(), 4 * nr);
+    *xa_out = (EmXa *) malloc(sizeof(EmXa) * (xa.size() + 1)); memcpy(*xa_out, xa.data(), sizeof(EmXa) * xa.size());
+    *xa_cigar_out = (uint32_t *) malloc(4 * (xa_ops.size() + 1)); memcpy(*xa_cigar_out, xa_ops.data(), 4 * xa_ops.size());
+    *n_xa_out = (int64_t) xa.size(); *n_xa_ops_out = (int64_t) xa_ops.size();
     *n_recs = (int64_t) nr; *n_ops_out = (int64_t) ops_all.size(); *n_md_out = (int64_t) md_all.size();
     return overflow ? 0x100 | overflow : 0;
 }

@@ -211,6 +211,12 @@ def test_sam_text_with_xa_and_alt_tags_matches_the_live_reference(pkg):
     bad = [i for i in range(len(got)) if got[i] != want[i]]
     assert not bad, (len(bad), [(got[i], want[i]) for i in bad[:2]])
     assert sum("XA:Z:" in w for w in want) > 30 and sum("pa:f:" in w for w in want) > 5, (sum("XA:Z:" in w for w in want), sum("pa:f:" in w for w in want))
+    # the device logic's XA entries (sam_gen_alt_d) against the reference's XA tags, record by record
+    e_recs, e_cig, e_md, e_xa = emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_, xa_names=names)
+    assert e_xa == xa_of_lines(want)
+    pa_want = [([f for f in w.split("\t") if f.startswith("pa:f:")] or [""])[0] for w in want]
+    pa_got = [("pa:f:%.3f" % (float(r["score"]) / float(r["_pad"]))) if r["_pad"] > 0 and not (r["flag"] & 0x100) else "" for r in e_recs]
+    assert pa_got == pa_want                                         # SamRec::alt_sc
     idx.close()
 
 
@@ -234,22 +240,44 @@ def _emul():
     return _EMUL
 
 
-def emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_):
+XA_DT = np.dtype([("read", "<i4"), ("reg", "<i4"), ("rid", "<i4"), ("is_rev", "<i4"), ("nm", "<i4"), ("n_cigar", "<i4"), ("pos", "<i8"), ("cigar_off", "<i8")])
+
+
+def emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_, xa_names=None):
+    """-> (recs, cigar, md); with xa_names also the XA string of every record ('' for none), built from the device logic's XA entries."""
     codes = np.ascontiguousarray(codes, np.uint8); offs = np.ascontiguousarray(offs, np.int64)
     regs = np.ascontiguousarray(regs); ro = np.ascontiguousarray(ro, np.int64)
     lh = np.ascontiguousarray(lh, np.int32); as_ = np.ascontiguousarray(as_, np.float64)
     rb = capi.ReadBatch(len(offs) - 1, codes.ctypes.data, offs.ctypes.data)
     rc_ = C.c_void_p(); cg = C.c_void_p(); md = C.c_void_p(); nr = C.c_int64(); no = C.c_int64(); nm = C.c_int64()
+    rr = C.c_void_p(); xa = C.c_void_p(); nxa = C.c_int64(); xc = C.c_void_p(); nxc = C.c_int64()
     rc = _emul().emul_sam_pe(C.byref(idx.desc), C.byref(opt), C.byref(rb), regs.ctypes.data_as(C.c_void_p), ro.ctypes.data_as(C.c_void_p),
                              lh.ctypes.data_as(C.c_void_p), as_.ctypes.data_as(C.c_void_p), C.c_int64(0), C.byref(rc_), C.byref(nr), C.byref(cg), C.byref(no),
-                             C.byref(md), C.byref(nm))
+                             C.byref(md), C.byref(nm), C.byref(rr), C.byref(xa), C.byref(nxa), C.byref(xc), C.byref(nxc))
     assert rc == 0, rc
     def arr(p, n, dt):
         dt = np.dtype(dt)
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(n, 1) * dt.itemsize,))[:n * dt.itemsize].view(dt).copy()
     out = arr(rc_, nr.value, REC_DT), arr(cg, no.value, "<u4"), arr(md, nm.value, "u1")
-    for p in (rc_, cg, md):
+    rec_reg = arr(rr, nr.value, "<i4"); xas = arr(xa, nxa.value, XA_DT); xops = arr(xc, nxc.value, "<u4")
+    for p in (rc_, cg, md, rr, xa, xc):
         ol.lib().bm2o_free(p)
+    if xa_names is None:
+        return out
+    by_key = {}
+    for e in xas:                                                    # entries in emission order (src/bwamem_extra.cpp:153-176)
+        ops = xops[e["cigar_off"]:e["cigar_off"] + e["n_cigar"]]
+        txt = f"{xa_names[e['rid']]},{'+-'[e['is_rev']]}{e['pos'] + 1}," + "".join(f"{v >> 4}{'MIDSHN'[v & 15]}" for v in ops) + f",{e['nm']};"
+        by_key.setdefault((int(e["read"]), int(e["reg"])), []).append(txt)
+    strings = ["".join(by_key.get((int(r["read"]), int(g)), [])) if g >= 0 else "" for r, g in zip(out[0], rec_reg)]
+    return out + (strings,)
+
+
+def xa_of_lines(lines):
+    out = []
+    for ln in lines:
+        t = [f for f in ln.split("\t") if f.startswith("XA:Z:")]
+        out.append(t[0][5:] if t else "")
     return out
 
 
