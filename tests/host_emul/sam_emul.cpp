@@ -6,7 +6,7 @@
 #include <string>
 #include <cmath>
 #include <cstring>
-#include "sam_device.cuh"
+#include "sam_layout.cuh"
 #include "../../oracle/bm2_oracle.h"
 
 // one XA entry: printed with every record of `read` whose rec_reg equals `reg`
@@ -42,39 +42,31 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
     std::vector<bm2o_samrec> out; std::vector<uint32_t> ops_all; std::string md_all;
     std::vector<int32_t> rec_reg; std::vector<EmXa> xa; std::vector<uint32_t> xa_ops;
     int overflow = 0;
+    int layout_bad = 0;
     for (int pr = 0; pr < reads->n_reads >> 1; ++pr) {
-        const uint8_t *seq[2]; int l_seq[2], n[2]; int max_l = 0;
-        std::vector<bm2_alnreg_t> a[2], b[2];
+        const uint8_t *seq[2]; int l_seq[2], n[2];
+        SamPairShape shape;
         for (int i = 0; i < 2; ++i) {
             const int r = 2 * pr + i;
             seq[i] = reads->codes + reads->offsets[r]; l_seq[i] = (int) (reads->offsets[r + 1] - reads->offsets[r]);
             n[i] = (int) (read_off[r + 1] - read_off[r]);
-            if (l_seq[i] > max_l) max_l = l_seq[i];
+            shape.n[i] = n[i]; shape.l_seq[i] = l_seq[i]; shape.max_rlen[i] = 0; shape.sum_rlen[i] = 0;
+            for (int64_t k = read_off[r]; k < read_off[r + 1]; ++k) {
+                const long long rl = regs[k].re - regs[k].rb;
+                shape.sum_rlen[i] += rl; if (rl > shape.max_rlen[i]) shape.max_rlen[i] = rl;
+            }
         }
-        for (int i = 0; i < 2; ++i) {
-            a[i].assign(regs + read_off[2 * pr + i], regs + read_off[2 * pr + i + 1]);
-            const int calls = n[!i] < opt->max_matesw ? n[!i] : opt->max_matesw;
-            a[i].resize((size_t) n[i] + 4 * (size_t) calls + 4);
-            b[i].resize((size_t) n[i] + 1);
-        }
-        const size_t nreg = a[0].size() + a[1].size();
-        const int tcap = mate_window_max_d(pes, max_l) + 16;            // the driver sizes the window scratch from the statistics
-        std::vector<uint8_t> rev((size_t) max_l + 1), tmp((size_t) tcap);
-        std::vector<int32_t> ksw((size_t) 3 * (max_l + 16)), bsc((size_t) tcap / 2 + 2), bpos((size_t) tcap / 2 + 2), idxv(nreg + 8), zv(nreg + 8), he((size_t) 2 * (max_l + 2));
-        std::vector<TailSortKey> keys(nreg + 8);
-        MateScratch ms = { rev.data(), tmp.data(), tcap, ksw.data(), bsc.data(), bpos.data(), tcap / 2 + 2, idxv.data(), keys.data() };
-        bm2_alnreg_t *ap[2] = { a[0].data(), a[1].data() }, *bp[2] = { b[0].data(), b[1].data() };
-        if (!(opt->flag & 0x20)) mate_rescue_pair_d(cv, p.ep, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, idx->ref_string, seq, l_seq, ap, n, bp, ms, &overflow);
-        // SAM stage
-        std::vector<SamP64> v(nreg + 4);
-        std::vector<uint8_t> zbuf((size_t) (max_l + 8) * (size_t) (max_l + 4 * opt->w + 64));
-        std::vector<SamAln> aa0((size_t) n[0] + 4), aa1((size_t) n[1] + 4);
-        std::vector<uint32_t> cig_pool((size_t) (nreg + 8) * (size_t) (3 * max_l + 512)), opsv((size_t) 3 * max_l + 512);
-        std::vector<char> md_pool((size_t) (nreg + 8) * (size_t) (12 * max_l + 2048));
-        SamScratch sc;
-        sc.z = zv.data(); sc.idx = idxv.data(); sc.v = v.data(); sc.he = he.data();
-        sc.zz.base = zbuf.data(); sc.zz.stride = 1; sc.aa[0] = aa0.data(); sc.aa[1] = aa1.data(); sc.aa_cap = (int) (n[0] > n[1] ? n[0] : n[1]) + 2;
-        sc.cig_pool = cig_pool.data(); sc.cig_cap = (long long) cig_pool.size(); sc.md_pool = md_pool.data(); sc.md_cap = (long long) md_pool.size(); sc.ops = opsv.data();
+        // the arena a kernel would get: capacities from sam_layout.cuh, guard words between the pieces
+        const SamPairCaps caps = sam_pair_caps_d(shape, pes, opt->max_matesw, !(opt->flag & 0x20));
+        std::vector<uint8_t> arena(caps.scratch_bytes + 64);
+        SamArena ar;
+        sam_arena_carve_d(arena.data(), caps, 1, &ar);
+        for (int i = 0; i < 2; ++i) memcpy(ar.a[i], regs + read_off[2 * pr + i], sizeof(bm2_alnreg_t) * (size_t) n[i]);
+        bm2_alnreg_t *ap[2] = { ar.a[0], ar.a[1] }, *bp[2] = { ar.b[0], ar.b[1] };
+        if (!(opt->flag & 0x20)) mate_rescue_pair_d(cv, p.ep, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, idx->ref_string, seq, l_seq, ap, n, bp, ar.ms, &overflow);
+        if (n[0] > caps.acap[0] || n[1] > caps.acap[1]) layout_bad |= 1;
+        const SamScratch &sc = ar.sc;
+        long long pair_recs = 0, pair_xa = 0, pair_ops = 0, pair_md = 0;
         auto emit = [&](int i, int k, const SamRec &r, const uint32_t *ops, const char *md) {
             bm2o_samrec o; memset(&o, 0, sizeof(o));
             o.read = 2 * pr + i; o.flag = r.flag; o.rid = r.rid; o.mapq = r.mapq; o.rnext = r.rnext; o.tlen_valid = 1; o.nm = r.nm; o.score = r.score; o.sub = r.sub; o._pad = r.alt_sc;        /* _pad carries alt_sc (pa tag) in this test build */
@@ -83,14 +75,16 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
             if (r.n_cigar) md_all += md;
             md_all.push_back('\0');
             o.n_md = (int32_t) (md_all.size() - (size_t) o.md_off);
-            out.push_back(o); rec_reg.push_back(r.reg);
+            out.push_back(o); rec_reg.push_back(r.reg); ++pair_recs; pair_ops += r.n_cigar; pair_md += o.n_md;
         };
         auto emit_xa = [&](int i, int reg, const SamAln &t) {
             EmXa e; e.read = 2 * pr + i; e.reg = reg; e.rid = t.rid; e.is_rev = t.is_rev; e.nm = t.nm; e.n_cigar = t.n_cigar; e.pos = t.pos; e.cigar_off = (int64_t) xa_ops.size();
             xa_ops.insert(xa_ops.end(), t.cigar, t.cigar + t.n_cigar);
-            xa.push_back(e);
+            xa.push_back(e); ++pair_xa; pair_ops += t.n_cigar;
         };
         sam_pe_pair_d(p, tb, cv, pes, idx->ref_string, seq, l_seq, ap, n, (int) (id_base + pr), sc, emit, emit_xa, &overflow);
+        if (!sam_arena_guards_ok_d(ar)) layout_bad |= 2;
+        if (pair_recs > caps.recs_cap || pair_xa > caps.xa_cap || pair_ops > caps.out_ops || pair_md > caps.out_md) layout_bad |= 4;
     }
     const size_t nr = out.size();
     *recs_out = (bm2o_samrec *) malloc(sizeof(bm2o_samrec) * (nr + 1)); memcpy(*recs_out, out.data(), sizeof(bm2o_samrec) * nr);
@@ -101,5 +95,5 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
     *xa_cigar_out = (uint32_t *) malloc(4 * (xa_ops.size() + 1)); memcpy(*xa_cigar_out, xa_ops.data(), 4 * xa_ops.size());
     *n_xa_out = (int64_t) xa.size(); *n_xa_ops_out = (int64_t) xa_ops.size();
     *n_recs = (int64_t) nr; *n_ops_out = (int64_t) ops_all.size(); *n_md_out = (int64_t) md_all.size();
-    return overflow ? 0x100 | overflow : 0;
+    return layout_bad ? 0x1000 | layout_bad : overflow ? 0x100 | overflow : 0;
 }

@@ -232,7 +232,7 @@ def _emul():
         d = os.path.join(ROOT, "tests", "host_emul")
         so = os.path.join(d, "libsamemul.so")
         srcs = [os.path.join(d, "sam_emul.cpp")] + [os.path.join(ROOT, "bwa-mem2_b200", "csrc", f) for f in
-                                                     ("sam_device.cuh", "mate_device.cuh", "ksw_device.cuh", "cigar_device.cuh", "ext_device.cuh", "chain_device.cuh", "hd.h")]
+                                                     ("sam_layout.cuh", "sam_device.cuh", "mate_device.cuh", "ksw_device.cuh", "cigar_device.cuh", "ext_device.cuh", "chain_device.cuh", "hd.h")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-I" + os.path.join(ROOT, "bwa-mem2_b200", "csrc"),
                                    "-I" + os.path.join(ROOT, "include"), srcs[0], "-o", so])
