@@ -47,6 +47,18 @@ CIGAR_REC_DT = np.dtype([("score", "<i4"), ("n_cigar", "<i4"), ("nm", "<i4"), ("
 PESTAT_DT = np.dtype([("low", "<i4"), ("high", "<i4"), ("failed", "<i4"), ("_pad", "<i4"), ("avg", "<f8"), ("std", "<f8")])
 
 
+# seam 4 (bm2_sam_pe): one record per SAM line, XA entries; layouts of include/bm2_b200.h
+SAM_REC_DT = np.dtype([("read", "<i4"), ("flag", "<i4"), ("rid", "<i4"), ("rnext", "<i4"), ("mapq", "<i4"), ("nm", "<i4"), ("score", "<i4"), ("sub", "<i4"),
+                       ("alt_sc", "<i4"), ("reg", "<i4"), ("n_cigar", "<i4"), ("n_md", "<i4"), ("pos", "<i8"), ("pnext", "<i8"), ("tlen", "<i8"),
+                       ("cigar_off", "<i8"), ("md_off", "<i8")])
+SAM_XA_DT = np.dtype([("read", "<i4"), ("reg", "<i4"), ("rid", "<i4"), ("is_rev", "<i4"), ("nm", "<i4"), ("n_cigar", "<i4"), ("pos", "<i8"), ("cigar_off", "<i8")])
+
+
+class SamResult(C.Structure):
+    _fields_ = [("n_recs", C.c_int64), ("recs", C.c_void_p), ("n_xa", C.c_int64), ("xa", C.c_void_p), ("n_ops", C.c_int64), ("cigar", C.c_void_p),
+                ("n_md", C.c_int64), ("md", C.c_void_p)]
+
+
 class CigarResult(C.Structure):
     _fields_ = [("n", C.c_int64), ("recs", C.c_void_p), ("n_ops", C.c_int64), ("cigar", C.c_void_p), ("n_md", C.c_int64), ("md", C.c_void_p)]
 
@@ -70,7 +82,7 @@ class RegResult(C.Structure):
 
 EXPORTS = ["bm2_gather64_gbs", "bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
            "bm2_last_error", "bm2_extend_pairs", "bm2_extend_pairs_device", "bm2_collect_smems", "bm2_seed_chain",
-           "bm2_seed_chain_extend", "bm2_last_stage_ms", "bm2_gen_cigar", "bm2_pestat"]
+           "bm2_seed_chain_extend", "bm2_last_stage_ms", "bm2_gen_cigar", "bm2_pestat", "bm2_sam_pe"]
 
 _lib = None
 
@@ -229,6 +241,20 @@ class Context:
             dt = np.dtype(dt)
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * dt.itemsize,)).view(dt).copy() if n else np.zeros(0, dt)
         return arr(res.recs, res.n, CIGAR_REC_DT), arr(res.cigar, res.n_ops, "<u4"), arr(res.md, res.n_md, "u1")
+
+    def sam_pe(self, codes, offsets, regs, read_off, pes, id_base=0):
+        """bm2_sam_pe: the SAM stage of a batch of pairs -> (recs SAM_REC_DT, xa SAM_XA_DT, cigar uint32[], md bytes)."""
+        rb, keep = self._batch(codes, offsets)
+        regs = np.ascontiguousarray(regs, REG_DT); read_off = np.ascontiguousarray(read_off, np.int64); pes = np.ascontiguousarray(pes, PESTAT_DT)
+        res = SamResult()
+        f = lib().bm2_sam_pe
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        self._check(f(self._ctx, C.byref(rb), regs.ctypes.data_as(C.c_void_p), read_off.ctypes.data_as(C.c_void_p), pes.ctypes.data_as(C.c_void_p),
+                      int(id_base), C.byref(res)), "bm2_sam_pe")
+        def arr(p, n, dt):
+            dt = np.dtype(dt)
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * dt.itemsize,)).view(dt).copy() if n else np.zeros(0, dt)
+        return arr(res.recs, res.n_recs, SAM_REC_DT), arr(res.xa, res.n_xa, SAM_XA_DT), arr(res.cigar, res.n_ops, "<u4"), arr(res.md, res.n_md, "u1")
 
     def set_stream(self, cuda_stream_handle):
         lib().bm2_set_stream.argtypes = [C.c_void_p, C.c_void_p]

@@ -34,8 +34,8 @@ struct bm2_ctx {
     // seam 1
     DevBuf io_pairs, io_ref, io_qer, bsw_jobs, bsw_outs, bsw_scratch;
     // seam 2 (pipeline.cu)
-    DevBuf d[64];
-    HostBuf h[16];
+    DevBuf d[96];
+    HostBuf h[32];
     std::vector<cudaEvent_t> events;
     std::vector<const char *> stage_names;
     std::vector<float> stage_ms;

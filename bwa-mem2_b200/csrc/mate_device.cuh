@@ -79,7 +79,7 @@ BM2_HD int matesw_d(const ContigView &cv, const ExtParams &ep, int min_seed_len,
             const KswRes al = ksw_align2_d(l_ms, seq, (int) (re - rb), ref + rb, ep.mat, ep.o_del, ep.e_del, ep.o_ins, ep.e_ins, xtra, sc.ksw, sc.bsc, sc.bpos,
                                            sc.bcap, sc.tmp, overflow);
             if (al.score >= min_seed_len && al.qb >= 0) {
-                bm2_alnreg_t b; memset(&b, 0, sizeof(b));
+                alignas(16) bm2_alnreg_t b; memset(&b, 0, sizeof(b));          // reg_copy moves 16-byte words
                 b.rid = a->rid;
                 reg_set_is_alt_d(b, (a->n_comp_is_alt >> 30) & 3);
                 b.qb = is_rev ? l_ms - (al.qe + 1) : al.qb;

@@ -1,0 +1,264 @@
+// sam.cu — seam 4: the SAM stage of a chunk of read pairs (mate rescue, pairing / MAPQ, records).
+//
+// Replaces what worker_sam does per pair through mem_sam_pe (reference src/bwamem_pair.cpp:349-552) for all pairs of a chunk: the
+// per-pair logic is sam_pe_pair_d / mate_rescue_pair_d (sam_device.cuh, mate_device.cuh: checked on the host against the oracle and
+// the unmodified reference), one pair per thread; the scratch of a pair is an arena whose capacities follow from the pair's regions
+// and the insert-size statistics (sam_layout.cuh); the records, XA entries, operations and MD bytes go to worst-case stripes and are
+// compacted by a gather.  Pairs are processed in waves sized by a scratch budget.  The libm values the stage needs (log of small
+// integers, the insert-size term of mem_pair) are tabulated on the host with the host's libm, as the reference computes them.
+//
+// STATUS: first version, written after this round's GPU minutes were spent - compiled for sm_100a, not yet run on a GPU
+// (tests/test_zz_sam_gpu.py is its first run).  Correctness-first: thread-per-pair, no warp cooperation in the local alignment yet.
+#include "bm2_common.cuh"
+#include "bm2_ctx.h"
+#include "sam_layout.cuh"
+#include <vector>
+#include <cmath>
+#include <cstring>
+#include <string>
+
+namespace {
+enum { SB_CODES = 64, SB_OFFS, SB_REGS, SB_REGOFF, SB_DESC, SB_ARENA, SB_RECS_W, SB_XA_W, SB_OPS_W, SB_MD_W, SB_CNT, SB_FINAL, SB_LOG, SB_TERM,
+       SB_RECS, SB_XA, SB_OPS, SB_MD };
+enum { SH_RECS = 16, SH_XA, SH_OPS, SH_MD, SH_CNT, SH_STAGE };
+static_assert(SB_MD < 96, "bm2_ctx::d[] too small");
+
+struct PairDesc {                 // one pair of a wave
+    SamPairCaps caps;
+    int64_t arena_off;            // bytes into the wave's arena
+    int64_t rec_off, xa_off, ops_off, md_off;      // worst-case stripes of the wave
+    int32_t pair;                 // pair index in the batch
+};
+struct PairCount { int64_t recs, xa, ops, md; int32_t overflow, _pad; };
+struct PairFinal { int64_t recs, xa, ops, md; };   // compact offsets (inside the wave)
+
+__global__ void __launch_bounds__(64)
+sam_kernel(SamParams p, SamTables tb, ContigView cv, MatePes pes, int max_matesw, int rescue, const uint8_t *__restrict__ ref,
+           const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, const bm2_alnreg_t *__restrict__ regs, const int64_t *__restrict__ reg_off,
+           const PairDesc *__restrict__ desc, int n_pairs, int64_t id_base, uint8_t *arena, bm2_sam_rec *recs_w, bm2_sam_xa *xa_w, uint32_t *ops_w, char *md_w,
+           PairCount *cnt)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pairs) return;
+    const PairDesc d = desc[t];
+    SamArena ar;
+    sam_arena_carve_d(arena + d.arena_off, d.caps, 0, &ar);
+    const uint8_t *seq[2]; int l_seq[2], n[2];
+    for (int i = 0; i < 2; ++i) {
+        const int64_t r = 2LL * d.pair + i;
+        seq[i] = codes + offs[r]; l_seq[i] = (int) (offs[r + 1] - offs[r]);
+        n[i] = (int) (reg_off[r + 1] - reg_off[r]);
+        for (int k = 0; k < n[i]; ++k) reg_copy(&ar.a[i][k], &regs[reg_off[r] + k]);
+    }
+    int overflow = 0;
+    bm2_alnreg_t *ap[2] = { ar.a[0], ar.a[1] }, *bp[2] = { ar.b[0], ar.b[1] };
+    if (rescue) mate_rescue_pair_d(cv, p.ep, p.min_seed_len, p.pen_unpaired, max_matesw, pes, ref, seq, l_seq, ap, n, bp, ar.ms, &overflow);
+    PairCount c; c.recs = 0; c.xa = 0; c.ops = 0; c.md = 0; c.overflow = 0; c._pad = 0;
+    bm2_sam_rec *recs = recs_w + d.rec_off; bm2_sam_xa *xa = xa_w + d.xa_off; uint32_t *ops = ops_w + d.ops_off; char *md = md_w + d.md_off;
+    const SamPairCaps &cp = d.caps;
+    auto emit = [&](int i, int k, const SamRec &r, const uint32_t *rops, const char *rmd) {
+        const int nmd = r.n_cigar ? r.n_md : 1;
+        if (c.recs >= cp.recs_cap || c.ops + r.n_cigar > cp.out_ops || c.md + nmd > cp.out_md) { overflow |= BM2_OVF_RECORDS; return; }
+        bm2_sam_rec o;
+        o.read = 2 * d.pair + i; o.flag = r.flag; o.rid = r.rid; o.rnext = r.rnext; o.mapq = r.mapq; o.nm = r.nm; o.score = r.score; o.sub = r.sub;
+        o.alt_sc = r.alt_sc; o.reg = r.reg; o.n_cigar = r.n_cigar; o.n_md = nmd; o.pos = r.pos; o.pnext = r.pnext; o.tlen = r.tlen;
+        o.cigar_off = c.ops; o.md_off = c.md;
+        for (int j = 0; j < r.n_cigar; ++j) ops[c.ops + j] = rops[j];
+        if (r.n_cigar) { for (int j = 0; j < nmd; ++j) md[c.md + j] = rmd[j]; } else md[c.md] = 0;
+        recs[c.recs++] = o; c.ops += r.n_cigar; c.md += nmd;
+    };
+    auto emit_xa = [&](int i, int reg, const SamAln &e) {
+        if (c.xa >= cp.xa_cap || c.ops + e.n_cigar > cp.out_ops) { overflow |= BM2_OVF_RECORDS; return; }
+        bm2_sam_xa o;
+        o.read = 2 * d.pair + i; o.reg = reg; o.rid = e.rid; o.is_rev = e.is_rev; o.nm = e.nm; o.n_cigar = e.n_cigar; o.pos = e.pos; o.cigar_off = c.ops;
+        for (int j = 0; j < e.n_cigar; ++j) ops[c.ops + j] = e.cigar[j];
+        xa[c.xa++] = o; c.ops += e.n_cigar;
+    };
+    sam_pe_pair_d(p, tb, cv, pes, ref, seq, l_seq, ap, n, (int) (id_base + d.pair), ar.sc, emit, emit_xa, &overflow);
+    c.overflow = overflow;
+    cnt[t] = c;
+}
+
+// compaction of one wave: stripes -> dense arrays; offsets become offsets into the batch's result (base_* = what earlier waves produced)
+__global__ void sam_gather_kernel(const PairDesc *__restrict__ desc, const PairCount *__restrict__ cnt, const PairFinal *__restrict__ fin, int n_pairs,
+                                  const bm2_sam_rec *__restrict__ recs_w, const bm2_sam_xa *__restrict__ xa_w, const uint32_t *__restrict__ ops_w,
+                                  const char *__restrict__ md_w, int64_t base_ops, int64_t base_md, bm2_sam_rec *recs, bm2_sam_xa *xa, uint32_t *ops, char *md)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pairs) return;
+    const PairDesc d = desc[t]; const PairCount c = cnt[t]; const PairFinal f = fin[t];
+    for (int64_t k = 0; k < c.recs; ++k) {
+        bm2_sam_rec o = recs_w[d.rec_off + k];
+        o.cigar_off += base_ops + f.ops; o.md_off += base_md + f.md;
+        recs[f.recs + k] = o;
+    }
+    for (int64_t k = 0; k < c.xa; ++k) {
+        bm2_sam_xa o = xa_w[d.xa_off + k];
+        o.cigar_off += base_ops + f.ops;
+        xa[f.xa + k] = o;
+    }
+    for (int64_t k = 0; k < c.ops; ++k) ops[f.ops + k] = ops_w[d.ops_off + k];
+    for (int64_t k = 0; k < c.md; ++k) md[f.md + k] = md_w[d.md_off + k];
+}
+
+template <class T> T *P(bm2_ctx *ctx, int b) { return (T *) ctx->d[b].p; }
+
+// pinned host buffer that keeps its content when it grows
+int grow_host(bm2_ctx *ctx, HostBuf &b, size_t used, size_t need) {
+    bm2_ctx *ctx_for_error = ctx;
+    if (b.cap >= need) return 0;
+    void *np = nullptr;
+    const size_t want = need + need / 2 + 4096;
+    BM2_CUDA_OK(cudaMallocHost(&np, want));
+    if (used) memcpy(np, b.p, used);
+    if (b.p) BM2_CUDA_OK(cudaFreeHost(b.p));
+    b.p = np; b.cap = want;
+    return 0;
+}
+}  // namespace
+
+extern "C" int bm2_sam_pe(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off, const bm2_pestat_t pes4[4],
+                          int64_t id_base, bm2_sam_result *out)
+{
+    bm2_ctx *ctx_for_error = ctx;
+    if (!ctx || !reads || !out || !read_off || !pes4) { if (ctx) bm2_set_error(ctx, "bm2_sam_pe: bad arguments"); return 1; }
+    if (!ctx->idx.loaded) { bm2_set_error(ctx, "bm2_sam_pe needs a context created with an index"); return 1; }
+    const int nr = reads->n_reads;
+    if (nr < 0 || (nr & 1)) { bm2_set_error(ctx, "bm2_sam_pe: the batch must hold whole pairs (reads 2i, 2i+1)"); return 1; }
+    if (read_off[nr] > 0 && !regs) { bm2_set_error(ctx, "bm2_sam_pe: regs is NULL"); return 1; }
+    BM2_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    memset(out, 0, sizeof(*out));
+    if (grow_host(ctx, ctx->h[SH_RECS], 0, 64) || grow_host(ctx, ctx->h[SH_XA], 0, 64) || grow_host(ctx, ctx->h[SH_OPS], 0, 64) || grow_host(ctx, ctx->h[SH_MD], 0, 64)) return 1;
+    out->recs = (const bm2_sam_rec *) ctx->h[SH_RECS].p; out->xa = (const bm2_sam_xa *) ctx->h[SH_XA].p;
+    out->cigar = (const uint32_t *) ctx->h[SH_OPS].p; out->md = (const char *) ctx->h[SH_MD].p;
+    const int n_pairs_all = nr >> 1;
+    if (n_pairs_all == 0) return 0;
+    const bm2_mem_opt_t &o = ctx->opt;
+    if (o.e_del <= 0 || o.e_ins <= 0 || o.a <= 0) { bm2_set_error(ctx, "bm2_sam_pe: match score and gap extension penalties must be positive"); return 1; }
+
+    // ---- parameters and host-filled tables ----------------------------------------------------------------------------------
+    SamParams p;
+    p.ep.a = o.a; p.ep.b = o.b; p.ep.o_del = o.o_del; p.ep.e_del = o.e_del; p.ep.o_ins = o.o_ins; p.ep.e_ins = o.e_ins; p.ep.w = o.w;
+    p.ep.pen_clip5 = o.pen_clip5; p.ep.pen_clip3 = o.pen_clip3; p.ep.max_chain_gap = o.max_chain_gap; p.ep.mask_level_redun = o.mask_level_redun;
+    memcpy(p.ep.mat, o.mat, 25);
+    p.T = o.T; p.flag = o.flag; p.min_seed_len = o.min_seed_len; p.pen_unpaired = o.pen_unpaired; p.mask_level = o.mask_level; p.drop_ratio = o.drop_ratio;
+    p.mapQ_coef_len = o.mapQ_coef_len; p.mapQ_coef_fac = o.mapQ_coef_fac;
+    p.XA_drop_ratio = o.XA_drop_ratio; p.max_XA_hits = o.max_XA_hits; p.max_XA_hits_alt = o.max_XA_hits_alt;
+    MatePes pes;
+    for (int d = 0; d < 4; ++d) { pes.low[d] = pes4[d].low; pes.high[d] = pes4[d].high; pes.failed[d] = pes4[d].failed; }
+    const int n_log = 1 << 16;
+    std::vector<double> tab((size_t) n_log);
+    for (int k = 0; k < n_log; ++k) tab[(size_t) k] = log((double) k);
+    SamTables tb; tb.n_log = n_log;
+    size_t term_total = 0, term_at[4];
+    for (int d = 0; d < 4; ++d) {
+        tb.pair_lo[d] = pes.low[d]; tb.pair_hi[d] = pes.failed[d] ? (int64_t) pes.low[d] - 1 : pes.high[d];
+        term_at[d] = term_total;
+        if (tb.pair_hi[d] >= tb.pair_lo[d]) term_total += (size_t) (tb.pair_hi[d] - tb.pair_lo[d] + 1);
+    }
+    if (term_total > ((size_t) 1 << 28)) { bm2_set_error(ctx, "bm2_sam_pe: insert-size bounds span more than 2^28 values"); return 1; }
+    std::vector<double> term(term_total + 1);
+    for (int d = 0; d < 4; ++d)
+        for (int64_t dist = tb.pair_lo[d]; dist <= tb.pair_hi[d]; ++dist) {
+            const double ns = (dist - pes4[d].avg) / pes4[d].std;                 // src/bwamem_pair.cpp:320-322
+            term[term_at[d] + (size_t) (dist - tb.pair_lo[d])] = .721 * log(2. * erfc(fabs(ns) * M_SQRT1_2)) * o.a;
+        }
+    if (ctx->ensure(ctx->d[SB_LOG], tab.size() * 8) || ctx->ensure(ctx->d[SB_TERM], term.size() * 8)) return 1;
+    BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[SB_LOG].p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, st));
+    BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[SB_TERM].p, term.data(), term.size() * 8, cudaMemcpyHostToDevice, st));
+    tb.log_tab = P<double>(ctx, SB_LOG);
+    for (int d = 0; d < 4; ++d) tb.pair_term[d] = P<double>(ctx, SB_TERM) + term_at[d];
+    ContigView cv; cv.l_pac = ctx->idx.l_pac; cv.n_seqs = ctx->idx.n_seqs; cv.ann_off = ctx->idx.ann_off; cv.ann_len = ctx->idx.ann_len; cv.ann_alt = ctx->idx.ann_alt;
+    const int rescue = !(o.flag & 0x20);
+
+    // ---- inputs ------------------------------------------------------------------------------------------------------------
+    const int64_t total = reads->offsets[nr], n_regs = read_off[nr];
+    if (ctx->ensure(ctx->d[SB_CODES], (size_t) total + 16) || ctx->ensure(ctx->d[SB_OFFS], (size_t) (nr + 1) * 8) ||
+        ctx->ensure(ctx->d[SB_REGS], (size_t) (n_regs + 1) * sizeof(bm2_alnreg_t)) || ctx->ensure(ctx->d[SB_REGOFF], (size_t) (nr + 1) * 8)) return 1;
+    BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[SB_CODES].p, reads->codes, (size_t) total, cudaMemcpyHostToDevice, st));
+    BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[SB_OFFS].p, reads->offsets, (size_t) (nr + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_regs) BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[SB_REGS].p, regs, (size_t) n_regs * sizeof(bm2_alnreg_t), cudaMemcpyHostToDevice, st));
+    BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[SB_REGOFF].p, read_off, (size_t) (nr + 1) * 8, cudaMemcpyHostToDevice, st));
+
+    // ---- capacities of every pair; waves by budget ---------------------------------------------------------------------------
+    std::vector<PairDesc> desc((size_t) n_pairs_all);
+    for (int pr = 0; pr < n_pairs_all; ++pr) {
+        SamPairShape sh;
+        for (int i = 0; i < 2; ++i) {
+            const int r = 2 * pr + i;
+            const int64_t nn = read_off[r + 1] - read_off[r], ls = reads->offsets[r + 1] - reads->offsets[r];
+            if (nn < 0 || nn > (1 << 24) || ls < 0 || ls > (1 << 24)) { bm2_set_error(ctx, "bm2_sam_pe: a read with more than 2^24 bases or regions"); return 1; }
+            sh.n[i] = (int) nn; sh.l_seq[i] = (int) ls; sh.max_rlen[i] = 0; sh.sum_rlen[i] = 0;
+            for (int64_t k = read_off[r]; k < read_off[r + 1]; ++k) {
+                const long long rl = regs[k].re - regs[k].rb;
+                if (rl < 0 || rl > (1 << 24)) { bm2_set_error(ctx, "bm2_sam_pe: a region outside [0, 2^24) reference bases"); return 1; }
+                sh.sum_rlen[i] += rl; if (rl > sh.max_rlen[i]) sh.max_rlen[i] = rl;
+            }
+        }
+        desc[(size_t) pr].caps = sam_pair_caps_d(sh, pes, o.max_matesw, rescue != 0);
+        desc[(size_t) pr].pair = pr;
+    }
+    const size_t budget = (size_t) 12 << 30;                // scratch + stripes of one wave
+    size_t used[4] = { 0, 0, 0, 0 };                        // recs, xa, ops, md of the batch so far
+    for (int w0 = 0; w0 < n_pairs_all;) {
+        size_t arena = 0; int64_t nrec = 0, nxa = 0, nops = 0, nmd = 0; int w1 = w0;
+        while (w1 < n_pairs_all && w1 - w0 < (1 << 20)) {
+            PairDesc &d = desc[(size_t) w1];
+            const size_t add = d.caps.scratch_bytes + (size_t) d.caps.recs_cap * sizeof(bm2_sam_rec) + (size_t) d.caps.xa_cap * sizeof(bm2_sam_xa) +
+                               (size_t) d.caps.out_ops * 4 + (size_t) d.caps.out_md;
+            const size_t now = arena + (size_t) nrec * sizeof(bm2_sam_rec) + (size_t) nxa * sizeof(bm2_sam_xa) + (size_t) nops * 4 + (size_t) nmd;
+            if (w1 > w0 && now + add > budget) break;
+            if (add > ((size_t) 100 << 30)) { bm2_set_error(ctx, "bm2_sam_pe: one pair needs more than 100 GB of scratch"); return 1; }
+            d.arena_off = (int64_t) arena; d.rec_off = nrec; d.xa_off = nxa; d.ops_off = nops; d.md_off = nmd;
+            arena += sam_align16_d(d.caps.scratch_bytes); nrec += d.caps.recs_cap; nxa += d.caps.xa_cap; nops += d.caps.out_ops; nmd += d.caps.out_md;
+            ++w1;
+        }
+        const int np = w1 - w0;
+        if (ctx->ensure(ctx->d[SB_DESC], (size_t) np * sizeof(PairDesc)) || ctx->ensure(ctx->d[SB_ARENA], arena + 64) ||
+            ctx->ensure(ctx->d[SB_RECS_W], (size_t) (nrec + 1) * sizeof(bm2_sam_rec)) || ctx->ensure(ctx->d[SB_XA_W], (size_t) (nxa + 1) * sizeof(bm2_sam_xa)) ||
+            ctx->ensure(ctx->d[SB_OPS_W], (size_t) (nops + 4) * 4) || ctx->ensure(ctx->d[SB_MD_W], (size_t) nmd + 16) ||
+            ctx->ensure(ctx->d[SB_CNT], (size_t) np * sizeof(PairCount)) || ctx->ensure(ctx->d[SB_FINAL], (size_t) np * sizeof(PairFinal)) ||
+            ctx->ensure_host(ctx->h[SH_CNT], (size_t) np * (sizeof(PairCount) + sizeof(PairFinal)))) return 1;
+        BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[SB_DESC].p, desc.data() + w0, (size_t) np * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+        sam_kernel<<<(unsigned) ((np + 63) / 64), 64, 0, st>>>(p, tb, cv, pes, o.max_matesw, rescue, ctx->idx.ref, P<uint8_t>(ctx, SB_CODES), P<int64_t>(ctx, SB_OFFS),
+                                                              P<bm2_alnreg_t>(ctx, SB_REGS), P<int64_t>(ctx, SB_REGOFF), P<PairDesc>(ctx, SB_DESC), np, id_base,
+                                                              P<uint8_t>(ctx, SB_ARENA), P<bm2_sam_rec>(ctx, SB_RECS_W), P<bm2_sam_xa>(ctx, SB_XA_W),
+                                                              P<uint32_t>(ctx, SB_OPS_W), P<char>(ctx, SB_MD_W), P<PairCount>(ctx, SB_CNT));
+        BM2_CUDA_OK(cudaGetLastError());
+        PairCount *hc = (PairCount *) ctx->h[SH_CNT].p; PairFinal *hf = (PairFinal *) (hc + np);
+        BM2_CUDA_OK(cudaMemcpyAsync(hc, ctx->d[SB_CNT].p, (size_t) np * sizeof(PairCount), cudaMemcpyDeviceToHost, st));
+        BM2_CUDA_OK(cudaStreamSynchronize(st));
+        PairFinal run = { 0, 0, 0, 0 };
+        for (int k = 0; k < np; ++k) {
+            if (hc[k].overflow) {
+                bm2_set_error(ctx, "bm2_sam_pe: scratch of pair " + std::to_string(w0 + k) + " was too small (BM2_OVF bits " + std::to_string(hc[k].overflow) + ")");
+                return 1;
+            }
+            hf[k] = run;
+            run.recs += hc[k].recs; run.xa += hc[k].xa; run.ops += hc[k].ops; run.md += hc[k].md;
+        }
+        if (ctx->ensure(ctx->d[SB_RECS], (size_t) (run.recs + 1) * sizeof(bm2_sam_rec)) || ctx->ensure(ctx->d[SB_XA], (size_t) (run.xa + 1) * sizeof(bm2_sam_xa)) ||
+            ctx->ensure(ctx->d[SB_OPS], (size_t) (run.ops + 4) * 4) || ctx->ensure(ctx->d[SB_MD], (size_t) run.md + 16)) return 1;
+        BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[SB_FINAL].p, hf, (size_t) np * sizeof(PairFinal), cudaMemcpyHostToDevice, st));
+        sam_gather_kernel<<<(unsigned) ((np + 127) / 128), 128, 0, st>>>(P<PairDesc>(ctx, SB_DESC), P<PairCount>(ctx, SB_CNT), P<PairFinal>(ctx, SB_FINAL), np,
+                                                                        P<bm2_sam_rec>(ctx, SB_RECS_W), P<bm2_sam_xa>(ctx, SB_XA_W), P<uint32_t>(ctx, SB_OPS_W),
+                                                                        P<char>(ctx, SB_MD_W), (int64_t) (used[2] / 4), (int64_t) used[3], P<bm2_sam_rec>(ctx, SB_RECS),
+                                                                        P<bm2_sam_xa>(ctx, SB_XA), P<uint32_t>(ctx, SB_OPS), P<char>(ctx, SB_MD));
+        BM2_CUDA_OK(cudaGetLastError());
+        const size_t add[4] = { (size_t) run.recs * sizeof(bm2_sam_rec), (size_t) run.xa * sizeof(bm2_sam_xa), (size_t) run.ops * 4, (size_t) run.md };
+        const int hb[4] = { SH_RECS, SH_XA, SH_OPS, SH_MD }, db[4] = { SB_RECS, SB_XA, SB_OPS, SB_MD };
+        for (int k = 0; k < 4; ++k) {
+            if (grow_host(ctx, ctx->h[hb[k]], used[k], used[k] + add[k] + 64)) return 1;
+            if (add[k]) BM2_CUDA_OK(cudaMemcpyAsync((char *) ctx->h[hb[k]].p + used[k], ctx->d[db[k]].p, add[k], cudaMemcpyDeviceToHost, st));
+            used[k] += add[k];
+        }
+        BM2_CUDA_OK(cudaStreamSynchronize(st));
+        w0 = w1;
+    }
+    out->n_recs = (int64_t) (used[0] / sizeof(bm2_sam_rec)); out->recs = (const bm2_sam_rec *) ctx->h[SH_RECS].p;
+    out->n_xa = (int64_t) (used[1] / sizeof(bm2_sam_xa)); out->xa = (const bm2_sam_xa *) ctx->h[SH_XA].p;
+    out->n_ops = (int64_t) (used[2] / 4); out->cigar = (const uint32_t *) ctx->h[SH_OPS].p;
+    out->n_md = (int64_t) used[3]; out->md = (const char *) ctx->h[SH_MD].p;
+    return 0;
+}

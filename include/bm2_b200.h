@@ -258,6 +258,46 @@ typedef struct bm2_pestat_t {
 } bm2_pestat_t;
 int bm2_pestat(const bm2_mem_opt_t *opt, int64_t l_pac, int32_t n_reads, const bm2_alnreg_t *regs, const int64_t *read_off, bm2_pestat_t pes[4]);
 
+/* ---- seam 4: the SAM stage of a chunk of read pairs ----------------------------------------------------------------------
+ * Replaces, for all pairs of a chunk at once, what worker_sam does per pair through mem_sam_pe (reference
+ * src/bwamem_pair.cpp:349-552, MATE_SORT == 0): mate rescue (mem_matesw :150-283 over ksw_align2, src/ksw.cpp:324-381),
+ * mem_mark_primary_se (src/bwamem.cpp:1420-1468), -5 reordering, mem_pair (:285-346), the MAPQ logic, mem_reg2aln with its
+ * CIGAR / NM / MD (src/bwamem.cpp:1732-1805), the record selection of mem_reg2sam (:1521-1577), the columns of mem_aln2sam
+ * (:1592-1730) and the entries of the XA tags (mem_gen_alt, src/bwamem_extra.cpp:130-183).  What is left to the caller is text:
+ * QNAME, SEQ / QUAL (trimmed by the hard clips of the record's CIGAR), the tag syntax, SA and MC (columns of the read's other
+ * records / the mate's record), -C / -R / -V constants.
+ * regs / read_off: the output of bm2_seed_chain_extend for the same batch (reads 2i, 2i+1 are mates); pes: bm2_pestat or the
+ * -I values.  One bm2_sam_rec per SAM line, in output order (pair by pair, read 0 then read 1). */
+typedef struct bm2_sam_rec {
+    int32_t read;              /* read of the batch the line belongs to                                        */
+    int32_t flag;              /* FLAG as printed                                                              */
+    int32_t rid, rnext;        /* contig ids of RNAME / RNEXT, -1: '*'                                         */
+    int32_t mapq, nm;          /* nm valid iff n_cigar > 0                                                     */
+    int32_t score, sub;        /* AS (printed if >= 0), XS (printed if >= 0)                                   */
+    int32_t alt_sc;            /* > 0 and not a 0x100 record: pa:f: = score / alt_sc                           */
+    int32_t reg;               /* its XA tag = the bm2_sam_xa entries of this read with the same reg; -1: none */
+    int32_t n_cigar, n_md;     /* printed operations (len << 4 | index into "MIDSH"); MD bytes incl. the NUL   */
+    int64_t pos, pnext, tlen;  /* as printed (1-based; 0 where the column is 0)                                */
+    int64_t cigar_off, md_off; /* into bm2_sam_result::cigar / ::md                                            */
+} bm2_sam_rec;
+typedef struct bm2_sam_xa {    /* one entry of an XA tag: name(rid),[+-]pos,CIGAR,nm;                          */
+    int32_t read, reg;
+    int32_t rid, is_rev, nm, n_cigar;      /* operations: len << 4 | index into "MIDSHN"                       */
+    int64_t pos;               /* 0-based: printed as pos + 1                                                  */
+    int64_t cigar_off;
+} bm2_sam_xa;
+typedef struct bm2_sam_result {
+    int64_t n_recs; const bm2_sam_rec *recs;
+    int64_t n_xa; const bm2_sam_xa *xa;        /* in the order the reference appends them                      */
+    int64_t n_ops; const uint32_t *cigar;
+    int64_t n_md; const char *md;
+} bm2_sam_result;
+/* Needs a context created with an index; uses the context's mem_opt_t (flag bits -a -M -P -S -Y -5 -q included).
+ * Result arrays are owned by the context (valid until its next call).  id_base: number of pairs before this batch in the
+ * run (the reference's `id`, which seeds the tie-breaking hashes). */
+int bm2_sam_pe(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off, const bm2_pestat_t pes[4],
+               int64_t id_base, bm2_sam_result *out);
+
 #ifdef __cplusplus
 }
 #endif
