@@ -7,8 +7,8 @@
 // compacted by a gather.  Pairs are processed in waves sized by a scratch budget.  The libm values the stage needs (log of small
 // integers, the insert-size term of mem_pair) are tabulated on the host with the host's libm, as the reference computes them.
 //
-// STATUS: first version, written after this round's GPU minutes were spent - compiled for sm_100a, not yet run on a GPU
-// (tests/test_zz_sam_gpu.py is its first run).  Correctness-first: thread-per-pair, no warp cooperation in the local alignment yet.
+// STATUS: first version, parity-green on a B200 (tests/test_zz_sam_gpu.py, profiles/r1s_zz_tests_gpu.log), not yet timed or profiled.
+// Correctness-first: thread-per-pair, no warp cooperation in the local alignment yet.
 #include "bm2_common.cuh"
 #include "bm2_ctx.h"
 #include "sam_layout.cuh"

@@ -1,15 +1,14 @@
 """GPU parity of seam 4 (bm2_sam_pe: mate rescue, pairing, MAPQ, CIGAR / NM / MD, SAM records, XA entries) through the C ABI: every
 SAM column and the NM MD AS XS XA pa tags of every line of the UNMODIFIED reference's output on C0 (tests/golden/c0.sam), and the
 oracle on flag variants and on the tandem-repeat reads (hundreds of regions per read).
-sam.cu was written after this round's GPU minutes were spent: its first run on a B200 is the round-end run, hence the non-strict
-xfail marks (the per-pair logic it launches is checked on the host, tests/test_oracle_sam_pe.py; what is new is the launch, the arena
-layout on the device and the compaction).  Named to run last."""
+First run on a B200: profiles/r1s_zz_tests_gpu.log (8 passed).  The per-pair logic the kernel launches is also checked on the host
+(tests/test_oracle_sam_pe.py)."""
 import numpy as np
 import pytest
 import oracle_lib as ol
 import test_oracle_sam_pe as tp
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="sam.cu has not run on a GPU yet (written after the round's GPU budget was spent)")]
+pytestmark = pytest.mark.gpu
 
 
 def _xa_strings(recs, xa, cigar, names):
