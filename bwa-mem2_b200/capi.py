@@ -54,6 +54,11 @@ SAM_REC_DT = np.dtype([("read", "<i4"), ("flag", "<i4"), ("rid", "<i4"), ("rnext
 SAM_XA_DT = np.dtype([("read", "<i4"), ("reg", "<i4"), ("rid", "<i4"), ("is_rev", "<i4"), ("nm", "<i4"), ("n_cigar", "<i4"), ("pos", "<i8"), ("cigar_off", "<i8")])
 
 
+# finer seam under seam 4 (bm2_ksw_align2): request / result layouts of include/bm2_b200.h
+KSW_REQ_DT = np.dtype([("qoff", "<i8"), ("toff", "<i8"), ("qlen", "<i4"), ("tlen", "<i4"), ("xtra", "<i4"), ("_pad", "<i4")])
+KSW_RES_DT = np.dtype([("score", "<i4"), ("te", "<i4"), ("qe", "<i4"), ("score2", "<i4"), ("te2", "<i4"), ("tb", "<i4"), ("qb", "<i4"), ("_pad", "<i4")])
+
+
 class SamResult(C.Structure):
     _fields_ = [("n_recs", C.c_int64), ("recs", C.c_void_p), ("n_xa", C.c_int64), ("xa", C.c_void_p), ("n_ops", C.c_int64), ("cigar", C.c_void_p),
                 ("n_md", C.c_int64), ("md", C.c_void_p)]
@@ -82,7 +87,7 @@ class RegResult(C.Structure):
 
 EXPORTS = ["bm2_gather64_gbs", "bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
            "bm2_last_error", "bm2_extend_pairs", "bm2_extend_pairs_device", "bm2_collect_smems", "bm2_seed_chain",
-           "bm2_seed_chain_extend", "bm2_last_stage_ms", "bm2_gen_cigar", "bm2_pestat", "bm2_sam_pe"]
+           "bm2_seed_chain_extend", "bm2_last_stage_ms", "bm2_gen_cigar", "bm2_pestat", "bm2_sam_pe", "bm2_ksw_align2"]
 
 _lib = None
 
@@ -241,6 +246,18 @@ class Context:
             dt = np.dtype(dt)
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * dt.itemsize,)).view(dt).copy() if n else np.zeros(0, dt)
         return arr(res.recs, res.n, CIGAR_REC_DT), arr(res.cigar, res.n_ops, "<u4"), arr(res.md, res.n_md, "u1")
+
+    def ksw_align2(self, reqs):
+        """bm2_ksw_align2: reqs = [(query codes, window codes, xtra), ...] -> int32[n, 7] (score, te, qe, score2, te2, tb, qb)."""
+        seqs = np.concatenate([np.concatenate([np.asarray(q, np.uint8), np.asarray(t, np.uint8)]) for q, t, _ in reqs]) if reqs else np.zeros(0, np.uint8)
+        rq = np.zeros(len(reqs), KSW_REQ_DT); pos = 0
+        for i, (q, t, x) in enumerate(reqs):
+            rq[i] = (pos, pos + len(q), len(q), len(t), x, 0); pos += len(q) + len(t)
+        out = np.zeros(len(reqs), KSW_RES_DT)
+        f = lib().bm2_ksw_align2
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+        self._check(f(self._ctx, seqs.ctypes.data_as(C.c_void_p), len(seqs), rq.ctypes.data_as(C.c_void_p), len(rq), out.ctypes.data_as(C.c_void_p)), "bm2_ksw_align2")
+        return np.stack([out[k] for k in ("score", "te", "qe", "score2", "te2", "tb", "qb")], axis=1).astype(np.int32) if len(out) else np.zeros((0, 7), np.int32)
 
     def sam_pe(self, codes, offsets, regs, read_off, pes, id_base=0):
         """bm2_sam_pe: the SAM stage of a batch of pairs -> (recs SAM_REC_DT, xa SAM_XA_DT, cigar uint32[], md bytes)."""

@@ -1,0 +1,197 @@
+// ksw_warp.cuh — the local alignment of mate rescue, one WINDOW PER WARP (groundwork for the second version of seam 4: sam.cu still
+// runs ksw_device.cuh's one-thread sweep; nothing launches this yet).
+//
+// Same function as ksw_pass_d (ksw_device.cuh: the reference's striped ksw_u8 / ksw_i16, src/ksw.cpp:111-316, with its first-pass E /
+// row maximum and its padding).  There a row is one sequential sweep over the query with two insertion registers: F of the segment
+// (restarts at every segment start of the reference's striping) and the complete F.  Both are max-plus prefix scans over
+//     base[k] = max(H(i-1, k-1) + S, E(i, k))            (an opening from an F-derived H never beats extending that F, o_ins >= 0)
+//     F(k) = max(0, max over j < k of base[j] - o_ins - e_ins * (k - j))     (for the segment F: j inside k's segment)
+// so a row splits over the 32 lanes: lane l owns C = ceil(nlen / 32) neighbouring columns (H, E in registers), computes base[] and the
+// summary (decay, value) of its block, an exclusive warp scan of the summaries under
+//     (d1, v1) o (d2, v2) = (d1 + d2, max(v1 - d2, v2))         (a segment start inside a block makes its decay "infinite")
+// hands every lane the F values entering its block, and a second local pass finishes the cells.  The row maximum is a warp max.
+// Rows stay synchronous, so the reference's early stops, its score-2 list and the copy of the best row are as in the sweep.
+//
+// The per-lane phases are plain BM2_HD functions; tests/host_emul/ksw_warp_emul.cpp drives them with a loop over 32 lane states and
+// plain loops for the scan / reductions (tests/test_oracle_ksw.py: equal to the oracle and to the reference's golden vectors);
+// ksw_pass_warp_d drives the same phases with __shfl_sync.
+#pragma once
+#include "ksw_device.cuh"
+
+#define BM2_KSW_CMAX 16                          // columns per lane: queries up to 32 * 16 - 15 = 497 bases
+#define BM2_KSW_KILL (1 << 28)                   // decay of a block that holds a segment start
+
+struct KswLane {
+    int32_t H[BM2_KSW_CMAX], E[BM2_KSW_CMAX], Hbest[BM2_KSW_CMAX];     // completed H of the previous row, E, H of the best row
+    int32_t base[BM2_KSW_CMAX];
+    uint8_t q[BM2_KSW_CMAX];                     // query codes of the lane's columns (4 beyond qlen: their score is 0, see sc below)
+    int col0, ncol;                              // first column, columns owned (0 for lanes beyond nlen)
+};
+struct KswShape { int size, qlen, p, slen, nlen, C, shift; int oe_del, e_del, oe_ins, e_ins; };
+struct KswSummary { int d_seg, v_seg, d_full, v_full; };
+
+BM2_HD KswShape ksw_shape_d(int size, int qlen, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins) {
+    KswShape s; s.size = size; s.qlen = qlen; s.p = size == 1 ? 16 : 8;
+    s.slen = (qlen + s.p - 1) / s.p; s.nlen = s.slen * s.p; s.C = (s.nlen + 31) / 32;
+    int shift = 127;
+    for (int a = 0; a < 25; ++a) if (mat[a] < shift) shift = mat[a];
+    s.shift = (256 - shift) & 0xff;
+    s.oe_del = o_del + e_del; s.e_del = e_del; s.oe_ins = o_ins + e_ins; s.e_ins = e_ins;
+    return s;
+}
+
+BM2_HD void ksw_lane_init_d(const KswShape &s, int lane, const uint8_t *query, int qstride, KswLane &L) {
+    L.col0 = lane * s.C;
+    L.ncol = L.col0 >= s.nlen ? 0 : (s.nlen - L.col0 < s.C ? s.nlen - L.col0 : s.C);
+    for (int c = 0; c < L.ncol; ++c) {
+        const int k = L.col0 + c;
+        L.H[c] = 0; L.E[c] = 0; L.Hbest[c] = 0;
+        L.q[c] = k < s.qlen ? query[(long long) k * qstride] : 255;           // 255: padding column, substitution score 0
+    }
+}
+
+// phase A: base[] of the row and the block's scan summary.  diag_in = H(i-1) of the column left of the block (0 for lane 0).
+BM2_HD KswSummary ksw_lane_phase_a_d(const KswShape &s, const int8_t *ma, int diag_in, KswLane &L) {
+    KswSummary m; m.d_seg = 0; m.v_seg = 0; m.d_full = 0; m.v_full = 0;
+    int diag = L.col0 == 0 ? 0 : diag_in, fs = 0, ff = 0;
+    bool killed = false;
+    for (int c = 0; c < L.ncol; ++c) {
+        const int k = L.col0 + c;
+        if (k % s.slen == 0) { fs = 0; killed = true; }                        // a segment starts here: nothing from the left survives
+        const int sc = L.q[c] == 255 ? 0 : (int) ma[L.q[c]];
+        int h = diag; diag = L.H[c];
+        if (s.size == 1) { h = h + sc + s.shift; if (h > 255) h = 255; h -= s.shift; if (h < 0) h = 0; }
+        else { h = h + sc; if (h > 32767) h = 32767; }
+        const int e = L.E[c];
+        if (e > h) h = e;
+        L.base[c] = h;
+        const int open = h - s.oe_ins > 0 ? h - s.oe_ins : 0;
+        fs -= s.e_ins; if (fs < 0) fs = 0; if (open > fs) fs = open;
+        ff -= s.e_ins; if (ff < 0) ff = 0; if (open > ff) ff = open;
+    }
+    m.d_seg = killed ? BM2_KSW_KILL : L.ncol * s.e_ins; m.v_seg = fs;
+    m.d_full = L.ncol * s.e_ins; m.v_full = ff;
+    return m;
+}
+
+BM2_HD KswSummary ksw_summary_join_d(const KswSummary &a, const KswSummary &b) {          // a's block lies left of b's
+    KswSummary r;
+    r.d_seg = a.d_seg + b.d_seg > BM2_KSW_KILL ? BM2_KSW_KILL : a.d_seg + b.d_seg;
+    r.v_seg = a.v_seg - b.d_seg > b.v_seg ? a.v_seg - b.d_seg : b.v_seg;
+    r.d_full = a.d_full + b.d_full > BM2_KSW_KILL ? BM2_KSW_KILL : a.d_full + b.d_full;
+    r.v_full = a.v_full - b.d_full > b.v_full ? a.v_full - b.d_full : b.v_full;
+    return r;
+}
+
+// phase B: the cells of the row with the F values entering the block (in.v_seg / in.v_full of the exclusive scan).  Returns the
+// block's maximum of the first-pass H; leaves the completed H in L.H and the new E in L.E.
+BM2_HD int ksw_lane_phase_b_d(const KswShape &s, const KswSummary &in, KswLane &L) {
+    int fs = in.v_seg > 0 ? in.v_seg : 0, ff = in.v_full > 0 ? in.v_full : 0, rowmax = 0;
+    for (int c = 0; c < L.ncol; ++c) {
+        const int k = L.col0 + c;
+        if (k % s.slen == 0) fs = 0;
+        int h = L.base[c];
+        if (fs > h) h = fs;                                                      // first-pass H
+        if (h > rowmax) rowmax = h;
+        { int t = h - s.oe_del; if (t < 0) t = 0; int e = L.E[c] - s.e_del; if (e < 0) e = 0; L.E[c] = e > t ? e : t; }
+        const int open = h - s.oe_ins > 0 ? h - s.oe_ins : 0;
+        fs -= s.e_ins; if (fs < 0) fs = 0; if (open > fs) fs = open;
+        L.H[c] = ff > h ? ff : h;                                                // completed H
+        ff -= s.e_ins; if (ff < 0) ff = 0; if (open > ff) ff = open;
+    }
+    return rowmax;
+}
+
+// row bookkeeping shared by both drivers (every lane can run it redundantly; only lane 0's list writes matter)
+struct KswRowState { int gmax, te, n_b; bool stop; };
+BM2_HD void ksw_row_end_d(const KswShape &s, int i, int rowmax, int minsc, int endsc, KswRowState &st, int32_t *bsc, int32_t *bpos, int bcap, int *overflow, bool *took) {
+    *took = false;
+    if (rowmax >= minsc) {
+        if (st.n_b == 0 || bpos[st.n_b - 1] + 1 != i) {
+            if (st.n_b < bcap) { bsc[st.n_b] = rowmax; bpos[st.n_b] = i; ++st.n_b; } else *overflow |= 32;
+        } else if (bsc[st.n_b - 1] < rowmax) { bsc[st.n_b - 1] = rowmax; bpos[st.n_b - 1] = i; }
+    }
+    if (rowmax > st.gmax) {
+        st.gmax = rowmax; st.te = i; *took = true;
+        if (s.size == 1 ? (st.gmax + s.shift >= 255 || st.gmax >= endsc) : (st.gmax >= endsc)) st.stop = true;
+    }
+}
+
+#if defined(__CUDACC__)
+// One pass by a full warp (all 32 lanes call it with the same arguments).  bsc / bpos: the warp's score-2 list (global or shared).
+// rev_upto >= 0: the rows run over target[rev_upto], target[rev_upto - 1], ..., target[0], target[rev_upto + 1], ... (ksw_align2's second pass
+// reverses the prefix in place and still walks all tlen rows, src/ksw.cpp:366-371).
+__device__ inline KswRes ksw_pass_warp_d(int size, int qlen, const uint8_t *query, int qstride, int tlen, const uint8_t *target, int rev_upto, const int8_t *mat,
+                                         int o_del, int e_del, int o_ins, int e_ins, int xtra, int32_t *bsc, int32_t *bpos, int bcap, int *overflow)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const KswShape s = ksw_shape_d(size, qlen, mat, o_del, e_del, o_ins, e_ins);
+    int qmax = 0;
+    for (int a = 0; a < 25; ++a) if (mat[a] > qmax) qmax = mat[a];
+    const int minsc = (xtra & BM2_KSW_XSUBO) ? xtra & 0xffff : 0x10000, endsc = (xtra & BM2_KSW_XSTOP) ? xtra & 0xffff : 0x10000;
+    KswLane L;
+    ksw_lane_init_d(s, lane, query, qstride, L);
+    KswRowState st; st.gmax = 0; st.te = -1; st.n_b = 0; st.stop = false;
+    int ov = 0;
+    for (int i = 0; i < tlen && !st.stop; ++i) {
+        const int8_t *ma = mat + (int) target[i <= rev_upto ? rev_upto - i : i] * 5;
+        const int last = L.ncol ? L.H[L.ncol - 1] : 0;
+        const int diag_in = __shfl_up_sync(full, last, 1);
+        KswSummary m = ksw_lane_phase_a_d(s, ma, diag_in, L);
+        KswSummary inc = m;                                                      // inclusive scan (Hillis-Steele), then shift by one lane
+        for (int d = 1; d < 32; d <<= 1) {
+            KswSummary o;
+            o.d_seg = __shfl_up_sync(full, inc.d_seg, d); o.v_seg = __shfl_up_sync(full, inc.v_seg, d);
+            o.d_full = __shfl_up_sync(full, inc.d_full, d); o.v_full = __shfl_up_sync(full, inc.v_full, d);
+            if (lane >= d) inc = ksw_summary_join_d(o, inc);
+        }
+        KswSummary in;
+        in.d_seg = 0; in.d_full = 0;
+        in.v_seg = __shfl_up_sync(full, inc.v_seg, 1); in.v_full = __shfl_up_sync(full, inc.v_full, 1);
+        if (lane == 0) { in.v_seg = 0; in.v_full = 0; }
+        int rowmax = ksw_lane_phase_b_d(s, in, L);
+        for (int d = 16; d > 0; d >>= 1) { const int o = __shfl_xor_sync(full, rowmax, d); if (o > rowmax) rowmax = o; }
+        bool took;                                                               // all lanes keep the same row state; their list writes coincide
+        ksw_row_end_d(s, i, rowmax, minsc, endsc, st, bsc, bpos, bcap, &ov, &took);
+        if (took) for (int c = 0; c < L.ncol; ++c) L.Hbest[c] = L.H[c];
+        __syncwarp(full);
+    }
+    KswRes r; r.score = size == 1 ? (st.gmax + s.shift < 255 ? st.gmax : 255) : st.gmax; r.te = st.te; r.qe = -1; r.score2 = -1; r.te2 = -1; r.tb = -1; r.qb = -1;
+    if (size == 2 || r.score != 255) {
+        int mx = -1, pos = 0x7fffffff;
+        for (int c = 0; c < L.ncol; ++c) if (L.Hbest[c] > mx) { mx = L.Hbest[c]; pos = L.col0 + c; }
+        for (int d = 16; d > 0; d >>= 1) {
+            const int omx = __shfl_xor_sync(full, mx, d), opos = __shfl_xor_sync(full, pos, d);
+            if (omx > mx || (omx == mx && opos < pos)) { mx = omx; pos = opos; }
+        }
+        r.qe = pos;
+        if (st.n_b) {
+            const int dd = (r.score + qmax - 1) / qmax, low = st.te - dd, high = st.te + dd;
+            int s2 = -1, t2 = -1;
+            for (int k = lane; k < st.n_b; k += 32) if ((bpos[k] < low || bpos[k] > high) && bsc[k] > s2) { s2 = bsc[k]; t2 = bpos[k]; }
+            for (int d = 16; d > 0; d >>= 1) {                                       // first entry among equal scores, as the serial scan
+                const int os = __shfl_xor_sync(full, s2, d), ot = __shfl_xor_sync(full, t2, d);
+                if (os > s2 || (os == s2 && os >= 0 && ot < t2)) { s2 = os; t2 = ot; }
+            }
+            r.score2 = s2; r.te2 = t2;
+        }
+    }
+    if (lane == 0 && ov) *overflow |= ov;
+    return r;
+}
+
+// ksw_align2 (src/ksw.cpp:324-381) by a full warp: forward pass, then the reversed prefixes to find the start.
+__device__ inline KswRes ksw_align2_warp_d(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int o_del, int e_del, int o_ins,
+                                           int e_ins, int xtra, int32_t *bsc, int32_t *bpos, int bcap, int *overflow)
+{
+    const int size = (xtra & BM2_KSW_XBYTE) ? 1 : 2;
+    KswRes r = ksw_pass_warp_d(size, qlen, query, 1, tlen, target, -1, mat, o_del, e_del, o_ins, e_ins, xtra, bsc, bpos, bcap, overflow);
+    if ((xtra & BM2_KSW_XSTART) == 0 || ((xtra & BM2_KSW_XSUBO) && r.score < (xtra & 0xffff))) return r;
+    int ov2 = 0;
+    __syncwarp(0xffffffffu);
+    const KswRes rr = ksw_pass_warp_d(size, r.qe + 1, query + r.qe, -1, tlen, target, r.te, mat, o_del, e_del, o_ins, e_ins, BM2_KSW_XSTOP | r.score, bsc, bpos, bcap, &ov2);
+    if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
+    return r;
+}
+#endif

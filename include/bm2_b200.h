@@ -258,6 +258,15 @@ typedef struct bm2_pestat_t {
 } bm2_pestat_t;
 int bm2_pestat(const bm2_mem_opt_t *opt, int64_t l_pac, int32_t n_reads, const bm2_alnreg_t *regs, const int64_t *read_off, bm2_pestat_t pes[4]);
 
+/* ---- finer seam under seam 4: a batch of the local alignments of mate rescue -----------------------------------------------
+ * Replaces ksw_align2 (reference src/ksw.cpp:324-381: ksw_u8 / ksw_i16 forward, then the reversed prefixes for the start) as
+ * mem_matesw calls it (src/bwamem_pair.cpp:186-193).  seqs: codes 0-4; a request names its query and its reference window by
+ * offsets into seqs; xtra as the reference's (KSW_XBYTE 0x10000, KSW_XSTOP 0x20000, KSW_XSUBO 0x40000, KSW_XSTART 0x80000 |
+ * threshold).  Scoring from the context's mem_opt_t.  out: n results, caller's memory.  Queries up to 497 bases. */
+typedef struct bm2_ksw_req { int64_t qoff, toff; int32_t qlen, tlen; int32_t xtra, _pad; } bm2_ksw_req;
+typedef struct bm2_ksw_res { int32_t score, te, qe, score2, te2, tb, qb, _pad; } bm2_ksw_res;       /* kswr_t (src/ksw.h:45-50) */
+int bm2_ksw_align2(bm2_ctx *ctx, const uint8_t *seqs, int64_t n_seq_bytes, const bm2_ksw_req *reqs, int64_t n, bm2_ksw_res *out);
+
 /* ---- seam 4: the SAM stage of a chunk of read pairs ----------------------------------------------------------------------
  * Replaces, for all pairs of a chunk at once, what worker_sam does per pair through mem_sam_pe (reference
  * src/bwamem_pair.cpp:349-552, MATE_SORT == 0): mate rescue (mem_matesw :150-283 over ksw_align2, src/ksw.cpp:324-381),

@@ -1,0 +1,63 @@
+// ksw_warp_emul.cpp — TEST-ONLY host driver of the warp formulation of the mate-rescue local alignment (bwa-mem2_b200/csrc/ksw_warp.cuh):
+// the per-lane phases are the product's functions; the 32 lanes are a loop, the warp scan and the reductions plain loops in lane order.
+// Checked against the oracle / the reference's golden vectors by tests/test_oracle_ksw.py.  Never part of the product.
+#include <vector>
+#include <cstdint>
+#include "ksw_warp.cuh"
+
+static KswRes pass_lanes(int size, int qlen, const uint8_t *query, int qstride, int tlen, const uint8_t *target, int tstride, const int8_t *mat,
+                         int o_del, int e_del, int o_ins, int e_ins, int xtra, int32_t *bsc, int32_t *bpos, int bcap, int *overflow)
+{
+    const KswShape s = ksw_shape_d(size, qlen, mat, o_del, e_del, o_ins, e_ins);
+    int qmax = 0;
+    for (int a = 0; a < 25; ++a) if (mat[a] > qmax) qmax = mat[a];
+    const int minsc = (xtra & BM2_KSW_XSUBO) ? xtra & 0xffff : 0x10000, endsc = (xtra & BM2_KSW_XSTOP) ? xtra & 0xffff : 0x10000;
+    std::vector<KswLane> L(32);
+    for (int l = 0; l < 32; ++l) ksw_lane_init_d(s, l, query, qstride, L[l]);
+    KswRowState st; st.gmax = 0; st.te = -1; st.n_b = 0; st.stop = false;
+    for (int i = 0; i < tlen && !st.stop; ++i) {
+        const int8_t *ma = mat + (int) target[(long long) i * tstride] * 5;
+        int last[32];
+        for (int l = 0; l < 32; ++l) last[l] = L[l].ncol ? L[l].H[L[l].ncol - 1] : 0;
+        KswSummary m[32], in[32];
+        for (int l = 0; l < 32; ++l) m[l] = ksw_lane_phase_a_d(s, ma, l ? last[l - 1] : 0, L[l]);
+        KswSummary run; run.d_seg = 0; run.v_seg = 0; run.d_full = 0; run.v_full = 0;      // exclusive scan
+        for (int l = 0; l < 32; ++l) { in[l] = run; run = l == 0 ? m[0] : ksw_summary_join_d(run, m[l]); }
+        int rowmax = 0;
+        for (int l = 0; l < 32; ++l) { const int r = ksw_lane_phase_b_d(s, in[l], L[l]); if (r > rowmax) rowmax = r; }
+        bool took;
+        ksw_row_end_d(s, i, rowmax, minsc, endsc, st, bsc, bpos, bcap, overflow, &took);
+        if (took) for (int l = 0; l < 32; ++l) for (int c = 0; c < L[l].ncol; ++c) L[l].Hbest[c] = L[l].H[c];
+    }
+    KswRes r; r.score = size == 1 ? (st.gmax + s.shift < 255 ? st.gmax : 255) : st.gmax; r.te = st.te; r.qe = -1; r.score2 = -1; r.te2 = -1; r.tb = -1; r.qb = -1;
+    if (size == 2 || r.score != 255) {
+        int mx = -1;
+        for (int l = 0; l < 32; ++l) for (int c = 0; c < L[l].ncol; ++c) if (L[l].Hbest[c] > mx) { mx = L[l].Hbest[c]; r.qe = L[l].col0 + c; }
+        if (st.n_b) {
+            const int d = (r.score + qmax - 1) / qmax, low = st.te - d, high = st.te + d;
+            for (int k = 0; k < st.n_b; ++k) if ((bpos[k] < low || bpos[k] > high) && bsc[k] > r.score2) { r.score2 = bsc[k]; r.te2 = bpos[k]; }
+        }
+    }
+    return r;
+}
+
+extern "C" int emul_ksw_warp_align2(int32_t qlen, const uint8_t *query, int32_t tlen, const uint8_t *target, const int8_t *mat, int32_t o_del,
+                                    int32_t e_del, int32_t o_ins, int32_t e_ins, int32_t xtra, int32_t *out)
+{
+    if (qlen > 32 * BM2_KSW_CMAX - 15) return -1;
+    std::vector<int32_t> bsc((size_t) tlen / 2 + 2), bpos((size_t) tlen / 2 + 2);
+    std::vector<uint8_t> tmp((size_t) tlen + 1);
+    int overflow = 0;
+    const int size = (xtra & BM2_KSW_XBYTE) ? 1 : 2;
+    KswRes r = pass_lanes(size, qlen, query, 1, tlen, target, 1, mat, o_del, e_del, o_ins, e_ins, xtra, bsc.data(), bpos.data(), (int) bsc.size(), &overflow);
+    if (!((xtra & BM2_KSW_XSTART) == 0 || ((xtra & BM2_KSW_XSUBO) && r.score < (xtra & 0xffff)))) {          // ksw_align2's second pass (ksw_device.cuh)
+        for (int i = 0; i <= r.te; ++i) tmp[i] = target[r.te - i];
+        for (int i = r.te + 1; i < tlen; ++i) tmp[i] = target[i];
+        int ov2 = 0;
+        const KswRes rr = pass_lanes(size, r.qe + 1, query + r.qe, -1, tlen, tmp.data(), 1, mat, o_del, e_del, o_ins, e_ins, BM2_KSW_XSTOP | r.score, bsc.data(),
+                                     bpos.data(), (int) bsc.size(), &ov2);
+        if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
+    }
+    out[0] = r.score; out[1] = r.te; out[2] = r.qe; out[3] = r.score2; out[4] = r.te2; out[5] = r.tb; out[6] = r.qb;
+    return overflow;
+}

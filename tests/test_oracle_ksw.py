@@ -43,36 +43,41 @@ def _emul():
     if _EMUL is None:
         d = os.path.join(ROOT, "tests", "host_emul")
         so = os.path.join(d, "libkswemul.so")
-        srcs = [os.path.join(d, "ksw_emul.cpp")] + [os.path.join(ROOT, "bwa-mem2_b200", "csrc", f) for f in ("ksw_device.cuh", "hd.h")]
+        srcs = [os.path.join(d, f) for f in ("ksw_emul.cpp", "ksw_warp_emul.cpp")] + [os.path.join(ROOT, "bwa-mem2_b200", "csrc", f) for f in ("ksw_device.cuh", "ksw_warp.cuh", "hd.h")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-w", "-I" + os.path.join(ROOT, "bwa-mem2_b200", "csrc"),
-                                   "-I" + os.path.join(ROOT, "include"), srcs[0], "-o", so])
+                                   "-I" + os.path.join(ROOT, "include"), srcs[0], srcs[1], "-o", so])
         _EMUL = C.CDLL(so)
     return _EMUL
 
 
-def emul_ksw(reqs, opt):
+def emul_ksw(reqs, opt, warp=False):
+    """ksw_device.cuh's one-thread sweep, or (warp=True) ksw_warp.cuh's 32-lane formulation; queries beyond the latter's 497 bases fall back to the sweep."""
     L = _emul()
     out = np.zeros((len(reqs), 7), np.int32)
     mat = (C.c_int8 * 25)(*[opt.mat[i] for i in range(25)])
     for i, (q, t, x) in enumerate(reqs):
         q = np.ascontiguousarray(q); t = np.ascontiguousarray(t)
-        ov = L.emul_ksw_align2(C.c_int32(len(q)), q.ctypes.data_as(C.c_void_p), C.c_int32(len(t)), t.ctypes.data_as(C.c_void_p), mat,
+        f = L.emul_ksw_warp_align2 if warp and len(q) <= 497 else L.emul_ksw_align2
+        ov = f(C.c_int32(len(q)), q.ctypes.data_as(C.c_void_p), C.c_int32(len(t)), t.ctypes.data_as(C.c_void_p), mat,
                                C.c_int32(opt.o_del), C.c_int32(opt.e_del), C.c_int32(opt.o_ins), C.c_int32(opt.e_ins), C.c_int32(x),
                                out[i].ctypes.data_as(C.c_void_p))
         assert ov == 0
     return out
 
 
-def test_device_logic_matches_reference_golden(pkg, golden_dir):
+@pytest.mark.parametrize("warp", [False, True], ids=["thread_sweep", "warp_scan"])
+def test_device_logic_matches_reference_golden(pkg, golden_dir, warp):
     reqs, want = _golden(golden_dir)
-    assert np.array_equal(emul_ksw(reqs, pkg.capi.default_opt()), want)
+    assert np.array_equal(emul_ksw(reqs, pkg.capi.default_opt(), warp=warp), want)
 
 
 @pytest.mark.parametrize("seed,qlens,sc", [(21, (151, 100, 36), {}), (22, (249, 250, 300, 17), {}),
                                            (23, (151, 76), dict(o_del=1, e_del=1, o_ins=1, e_ins=1, b=1)),     # gap open == 0 after update: F ties
-                                           (24, (120, 260), dict(o_del=4, e_del=2, o_ins=5, e_ins=1, a=2, b=3))])
-def test_device_logic_matches_oracle(pkg, seed, qlens, sc):
+                                           (24, (120, 260), dict(o_del=4, e_del=2, o_ins=5, e_ins=1, a=2, b=3)),
+                                           (25, (497, 481, 33, 32, 31), {})])                                  # the warp formulation's longest query, lanes without columns
+@pytest.mark.parametrize("warp", [False, True], ids=["thread_sweep", "warp_scan"])
+def test_device_logic_matches_oracle(pkg, seed, qlens, sc, warp):
     o = pkg.capi.default_opt()
     for k, v in sc.items():
         setattr(o, k, v)
@@ -84,6 +89,6 @@ def test_device_logic_matches_oracle(pkg, seed, qlens, sc):
     reqs = ku.make_requests(np.random.default_rng(seed), 1000, qlens=qlens)
     reqs = [(q, t, ku.mate_xtra(len(q), a=o.a, min_seed_len=o.min_seed_len)) for q, t, _ in reqs]
     want = ku.oracle_ksw(reqs, o)
-    got = emul_ksw(reqs, o)
+    got = emul_ksw(reqs, o, warp=warp)
     bad = np.nonzero((got != want).any(1))[0]
     assert len(bad) == 0, (bad[:5], got[bad[:5]], want[bad[:5]])
