@@ -1,7 +1,7 @@
 """GPU parity of bm2_ksw_align2 (the local alignment of mate rescue, one window per warp: ksw.cu / ksw_warp.cuh) through the C ABI: the
 golden vectors made by the UNMODIFIED reference's ksw_align2 (tests/golden/ksw_c0.npz) and the oracle on fresh requests with other
 scoring.  ksw.cu was written after the round's GPU minutes were spent: non-strict xfail until it has run once (its arithmetic is
-checked on the host, tests/test_oracle_ksw.py[warp_scan]).  Named to run last."""
+checked on the host, tests/test_oracle_ksw.py[warp_scan]).  Named to run after every other file (a fault in a kernel that has never run must not take later tests with it)."""
 import numpy as np
 import pytest
 import ksw_util as ku
