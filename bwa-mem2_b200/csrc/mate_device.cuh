@@ -36,48 +36,72 @@ BM2_HD int mate_window_max_d(const MatePes &pes, int l_ms) {
     return w + l_ms;
 }
 
-// mem_matesw: a = the anchor, ms = the mate's codes; ma[0..*n_ma) the mate's regions with room for 4 more.  Returns n.
-BM2_HD int matesw_d(const ContigView &cv, const ExtParams &ep, int min_seed_len, const MatePes &pes, const uint8_t *ref, const bm2_alnreg_t *a, int l_ms,
-                    const uint8_t *ms, bm2_alnreg_t *ma, int *n_ma, const MateScratch &sc, int *overflow)
-{
+// The window of orientation r around anchor a for a mate of l_ms bases (src/bwamem_pair.cpp:168-185, bns_fetch_seq's clipping to the
+// contig of the window's middle, src/bntseq.cpp:453-482).  False: the reference does not align (other contig, window too short).
+BM2_HD bool mate_window_d(const ContigView &cv, int min_seed_len, const MatePes &pes, const bm2_alnreg_t *a, int l_ms, int r, int64_t *rb_, int64_t *re_, int *is_rev_) {
     const int64_t l_pac = cv.l_pac;
-    int skip[4], n = 0, nm = *n_ma;
+    const int is_rev = (r >> 1 != (r & 1)), is_larger = !(r >> 1);
+    int64_t rb, re;
+    if (!is_rev) {
+        rb = is_larger ? a->rb + pes.low[r] : a->rb - pes.high[r];
+        re = (is_larger ? a->rb + pes.high[r] : a->rb - pes.low[r]) + l_ms;
+    } else {
+        rb = (is_larger ? a->rb + pes.low[r] : a->rb - pes.high[r]) - l_ms;
+        re = is_larger ? a->rb + pes.high[r] : a->rb - pes.low[r];
+    }
+    if (rb < 0) rb = 0;
+    if (re > l_pac << 1) re = l_pac << 1;
+    int rid = -1;
+    if (rb < re) {
+        const int64_t mid = (rb + re) >> 1;
+        rid = bns_pos2rid_d(cv, bns_depos_d(cv, mid));
+        int64_t far_beg = cv.ann_off[rid], far_end = far_beg + cv.ann_len[rid];
+        if (mid >= l_pac) { const int64_t t = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - t; }
+        rb = rb > far_beg ? rb : far_beg;
+        re = re < far_end ? re : far_end;
+    }
+    *rb_ = rb; *re_ = re; *is_rev_ = is_rev;
+    return a->rid == rid && re - rb >= min_seed_len;
+}
+
+// which orientations mem_matesw would align for anchor a given the mate's regions ma[0..nm) (:159-166)
+BM2_HD int mate_skip_d(const ContigView &cv, const MatePes &pes, const bm2_alnreg_t *a, const bm2_alnreg_t *ma, int nm, int skip[4]) {
     for (int r = 0; r < 4; ++r) skip[r] = pes.failed[r] ? 1 : 0;
     for (int i = 0; i < nm; ++i) {
         int64_t dist;
-        const int r = mate_infer_dir_d(l_pac, a->rb, ma[i].rb, &dist);
+        const int r = mate_infer_dir_d(cv.l_pac, a->rb, ma[i].rb, &dist);
         if (dist >= pes.low[r] && dist <= pes.high[r]) skip[r] = 1;
     }
-    if (skip[0] + skip[1] + skip[2] + skip[3] == 4) return 0;
+    return skip[0] + skip[1] + skip[2] + skip[3];
+}
+
+// the local alignment computed in place (the provider of the one-thread version; a staged driver passes a table lookup instead)
+struct MateKswDirect {
+    const ExtParams *ep; const uint8_t *ref; const MateScratch *sc; int *overflow;
+    BM2_HD KswRes operator()(int /*anchor_read*/, int /*anchor*/, int /*r*/, int l_ms, const uint8_t *seq, int64_t rb, int64_t re, int xtra) const {
+        return ksw_align2_d(l_ms, seq, (int) (re - rb), ref + rb, ep->mat, ep->o_del, ep->e_del, ep->o_ins, ep->e_ins, xtra, sc->ksw, sc->bsc, sc->bpos, sc->bcap,
+                            sc->tmp, overflow);
+    }
+};
+
+// mem_matesw: a = the anchor (anchor j of read ai), ms = the mate's codes; ma[0..*n_ma) the mate's regions with room for 4 more.  Returns n.
+// ksw(ai, j, r, l_ms, seq, rb, re, xtra) supplies the local alignment of orientation r (seq = the mate, reverse-complemented in sc.rev if needed).
+template <class Ksw>
+BM2_HD int matesw_d(const ContigView &cv, const ExtParams &ep, int min_seed_len, const MatePes &pes, const uint8_t *ref, const bm2_alnreg_t *a, int l_ms,
+                    const uint8_t *ms, bm2_alnreg_t *ma, int *n_ma, const MateScratch &sc, int ai, int j, Ksw &ksw, int *overflow)
+{
+    const int64_t l_pac = cv.l_pac;
+    int skip[4], n = 0, nm = *n_ma;
+    if (mate_skip_d(cv, pes, a, ma, nm, skip) == 4) return 0;
     for (int r = 0; r < 4; ++r) {
         if (skip[r]) continue;
-        const int is_rev = (r >> 1 != (r & 1)), is_larger = !(r >> 1);
-        const uint8_t *seq = ms;
-        if (is_rev) { for (int i = 0; i < l_ms; ++i) sc.rev[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4; seq = sc.rev; }
-        int64_t rb, re;
-        if (!is_rev) {
-            rb = is_larger ? a->rb + pes.low[r] : a->rb - pes.high[r];
-            re = (is_larger ? a->rb + pes.high[r] : a->rb - pes.low[r]) + l_ms;
-        } else {
-            rb = (is_larger ? a->rb + pes.low[r] : a->rb - pes.high[r]) - l_ms;
-            re = is_larger ? a->rb + pes.high[r] : a->rb - pes.low[r];
-        }
-        if (rb < 0) rb = 0;
-        if (re > l_pac << 1) re = l_pac << 1;
-        int rid = -1;
-        if (rb < re) {                                           // bns_fetch_seq (src/bntseq.cpp:453-482): clip to the contig of the middle
-            const int64_t mid = (rb + re) >> 1;
-            rid = bns_pos2rid_d(cv, bns_depos_d(cv, mid));
-            int64_t far_beg = cv.ann_off[rid], far_end = far_beg + cv.ann_len[rid];
-            if (mid >= l_pac) { const int64_t t = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - t; }
-            rb = rb > far_beg ? rb : far_beg;
-            re = re < far_end ? re : far_end;
-        }
-        if (a->rid == rid && re - rb >= min_seed_len) {
+        int64_t rb, re; int is_rev;
+        if (mate_window_d(cv, min_seed_len, pes, a, l_ms, r, &rb, &re, &is_rev)) {
             if (re - rb > sc.tcap) { *overflow |= 64; continue; }             // BM2_OVF_WINDOW (sam_device.cuh): scratch sized for other statistics
+            const uint8_t *seq = ms;
+            if (is_rev) { for (int i = 0; i < l_ms; ++i) sc.rev[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4; seq = sc.rev; }
             const int xtra = BM2_KSW_XSUBO | BM2_KSW_XSTART | (l_ms * ep.a < 250 ? BM2_KSW_XBYTE : 0) | (min_seed_len * ep.a);
-            const KswRes al = ksw_align2_d(l_ms, seq, (int) (re - rb), ref + rb, ep.mat, ep.o_del, ep.e_del, ep.o_ins, ep.e_ins, xtra, sc.ksw, sc.bsc, sc.bpos,
-                                           sc.bcap, sc.tmp, overflow);
+            const KswRes al = ksw(ai, j, r, l_ms, seq, rb, re, xtra);
             if (al.score >= min_seed_len && al.qb >= 0) {
                 alignas(16) bm2_alnreg_t b; memset(&b, 0, sizeof(b));          // reg_copy moves 16-byte words
                 b.rid = a->rid;
@@ -103,9 +127,10 @@ BM2_HD int matesw_d(const ContigView &cv, const ExtParams &ep, int min_seed_len,
 
 // The rescue block of mem_sam_pe for one pair.  a[i] / n[i]: the regions of read i (capacity n[i] + 4 * max_matesw... the caller sizes it:
 // every mem_matesw call adds at most 4), seq / l_seq the reads; b0 / b1: scratch for the anchor copies (n[i] records each).
+template <class Ksw>
 BM2_HD int mate_rescue_pair_d(const ContigView &cv, const ExtParams &ep, int min_seed_len, int pen_unpaired, int max_matesw, const MatePes &pes,
                               const uint8_t *ref, const uint8_t *const seq[2], const int l_seq[2], bm2_alnreg_t *const a[2], int n[2],
-                              bm2_alnreg_t *const b[2], const MateScratch &sc, int *overflow)
+                              bm2_alnreg_t *const b[2], const MateScratch &sc, Ksw &ksw, int *overflow)
 {
     int nb[2] = { 0, 0 }, total = 0;
     for (int i = 0; i < 2; ++i)
@@ -113,6 +138,39 @@ BM2_HD int mate_rescue_pair_d(const ContigView &cv, const ExtParams &ep, int min
             if (a[i][j].score >= a[i][0].score - pen_unpaired) reg_copy(&b[i][nb[i]++], &a[i][j]);
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < nb[i] && j < max_matesw; ++j)
-            total += matesw_d(cv, ep, min_seed_len, pes, ref, &b[i][j], l_seq[!i], seq[!i], a[!i], &n[!i], sc, overflow);
+            total += matesw_d(cv, ep, min_seed_len, pes, ref, &b[i][j], l_seq[!i], seq[!i], a[!i], &n[!i], sc, i, j, ksw, overflow);
     return total;
+}
+
+BM2_HD int mate_rescue_pair_d(const ContigView &cv, const ExtParams &ep, int min_seed_len, int pen_unpaired, int max_matesw, const MatePes &pes,
+                              const uint8_t *ref, const uint8_t *const seq[2], const int l_seq[2], bm2_alnreg_t *const a[2], int n[2],
+                              bm2_alnreg_t *const b[2], const MateScratch &sc, int *overflow)
+{
+    MateKswDirect direct = { &ep, ref, &sc, overflow };
+    return mate_rescue_pair_d(cv, ep, min_seed_len, pen_unpaired, max_matesw, pes, ref, seq, l_seq, a, n, b, sc, direct, overflow);
+}
+
+// Staged form, first stage: the local alignments the rescue block of a pair CAN ask for, decided from the regions before any rescue.
+// A later call of the block sees the regions earlier calls added, which only turns more orientations off (a hit inside the proper window
+// is what switches an orientation off), except when the dedup that follows an insertion drops the hit that had switched it off - so the
+// second stage (mate_rescue_pair_d with a lookup) must still be able to compute a missing alignment itself.
+// emit(anchor_read, anchor, r, rb, re, is_rev): the mate is read !anchor_read.
+template <class EmitJob>
+BM2_HD void mate_jobs_pair_d(const ContigView &cv, int min_seed_len, int pen_unpaired, int max_matesw, const MatePes &pes, const int l_seq[2],
+                             const bm2_alnreg_t *const a[2], const int n[2], EmitJob &emit)
+{
+    for (int i = 0; i < 2; ++i) {
+        int nb = 0;
+        for (int j = 0; j < n[i] && nb < max_matesw; ++j) {
+            if (!(a[i][j].score >= a[i][0].score - pen_unpaired)) continue;
+            int skip[4];
+            if (mate_skip_d(cv, pes, &a[i][j], a[!i], n[!i], skip) < 4)
+                for (int r = 0; r < 4; ++r) {
+                    if (skip[r]) continue;
+                    int64_t rb, re; int is_rev;
+                    if (mate_window_d(cv, min_seed_len, pes, &a[i][j], l_seq[!i], r, &rb, &re, &is_rev)) emit(i, nb, r, rb, re, is_rev);
+                }
+            ++nb;
+        }
+    }
 }

@@ -9,6 +9,30 @@
 #include "sam_layout.cuh"
 #include "../../oracle/bm2_oracle.h"
 
+// ---- staged form of the rescue (the shape of the next kernel version): all local alignments a chunk can ask for are enumerated from the
+// regions before any rescue (mate_jobs_pair_d), computed as one batch - here by the warp formulation, ksw_warp.cuh through
+// ksw_warp_emul.cpp - and the per-pair block then looks its alignments up, computing one itself only if the batch does not hold it.
+extern "C" int emul_ksw_warp_align2(int32_t qlen, const uint8_t *query, int32_t tlen, const uint8_t *target, const int8_t *mat, int32_t o_del,
+                                    int32_t e_del, int32_t o_ins, int32_t e_ins, int32_t xtra, int32_t *out);
+#include <map>
+#include <tuple>
+static int g_staged = 0;
+static long long g_stage_stats[4];            // jobs in the batch, looked up, computed in place (not in the batch), windows that differed
+extern "C" void emul_sam_set_staged(int on) { g_staged = on; }
+extern "C" void emul_sam_stage_stats(long long *out) { for (int k = 0; k < 4; ++k) out[k] = g_stage_stats[k]; }
+struct StagedJob { int64_t rb, re; KswRes res; };
+typedef std::map<std::tuple<int, int, int, int>, StagedJob> JobTable;      // (pair, anchor read, anchor, orientation)
+struct MateKswLookup {
+    const JobTable *tab; int pair; MateKswDirect direct;
+    KswRes operator()(int ai, int j, int r, int l_ms, const uint8_t *seq, int64_t rb, int64_t re, int xtra) const {
+        auto it = tab->find(std::make_tuple(pair, ai, j, r));
+        if (it == tab->end()) { ++g_stage_stats[2]; return direct(ai, j, r, l_ms, seq, rb, re, xtra); }
+        if (it->second.rb != rb || it->second.re != re) { ++g_stage_stats[3]; return direct(ai, j, r, l_ms, seq, rb, re, xtra); }
+        ++g_stage_stats[1];
+        return it->second.res;
+    }
+};
+
 // one XA entry: printed with every record of `read` whose rec_reg equals `reg`
 struct EmXa { int32_t read, reg, rid, is_rev, nm, n_cigar; int64_t pos, cigar_off; };
 
@@ -43,6 +67,32 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
     std::vector<int32_t> rec_reg; std::vector<EmXa> xa; std::vector<uint32_t> xa_ops;
     int overflow = 0;
     int layout_bad = 0;
+    JobTable jobs;
+    for (int k = 0; k < 4; ++k) g_stage_stats[k] = 0;
+    if (g_staged && !(opt->flag & 0x20))
+        for (int pr = 0; pr < reads->n_reads >> 1; ++pr) {
+            const bm2_alnreg_t *a2[2]; int n2[2], l2[2]; const uint8_t *s2[2];
+            for (int i = 0; i < 2; ++i) {
+                const int r = 2 * pr + i;
+                a2[i] = regs + read_off[r]; n2[i] = (int) (read_off[r + 1] - read_off[r]);
+                s2[i] = reads->codes + reads->offsets[r]; l2[i] = (int) (reads->offsets[r + 1] - reads->offsets[r]);
+            }
+            auto emit_job = [&](int ai, int j, int r, int64_t rb, int64_t re, int is_rev) {
+                const int l_ms = l2[!ai];
+                std::vector<uint8_t> q(s2[!ai], s2[!ai] + l_ms);
+                if (is_rev) for (int k = 0; k < l_ms; ++k) q[l_ms - 1 - k] = s2[!ai][k] < 4 ? 3 - s2[!ai][k] : 4;
+                const int xtra = BM2_KSW_XSUBO | BM2_KSW_XSTART | (l_ms * opt->a < 250 ? BM2_KSW_XBYTE : 0) | (opt->min_seed_len * opt->a);
+                int32_t o7[7];
+                StagedJob sj; sj.rb = rb; sj.re = re;
+                if (l_ms <= 32 * 16 - 15) {
+                    emul_ksw_warp_align2(l_ms, q.data(), (int) (re - rb), idx->ref_string + rb, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, xtra, o7);
+                    sj.res.score = o7[0]; sj.res.te = o7[1]; sj.res.qe = o7[2]; sj.res.score2 = o7[3]; sj.res.te2 = o7[4]; sj.res.tb = o7[5]; sj.res.qb = o7[6];
+                    jobs[std::make_tuple(pr, ai, j, r)] = sj;
+                    ++g_stage_stats[0];
+                }
+            };
+            mate_jobs_pair_d(cv, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, l2, a2, n2, emit_job);
+        }
     for (int pr = 0; pr < reads->n_reads >> 1; ++pr) {
         const uint8_t *seq[2]; int l_seq[2], n[2];
         SamPairShape shape;
@@ -63,7 +113,12 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
         sam_arena_carve_d(arena.data(), caps, 1, &ar);
         for (int i = 0; i < 2; ++i) memcpy(ar.a[i], regs + read_off[2 * pr + i], sizeof(bm2_alnreg_t) * (size_t) n[i]);
         bm2_alnreg_t *ap[2] = { ar.a[0], ar.a[1] }, *bp[2] = { ar.b[0], ar.b[1] };
-        if (!(opt->flag & 0x20)) mate_rescue_pair_d(cv, p.ep, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, idx->ref_string, seq, l_seq, ap, n, bp, ar.ms, &overflow);
+        if (!(opt->flag & 0x20)) {
+            if (g_staged) {
+                MateKswLookup look = { &jobs, pr, { &p.ep, idx->ref_string, &ar.ms, &overflow } };
+                mate_rescue_pair_d(cv, p.ep, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, idx->ref_string, seq, l_seq, ap, n, bp, ar.ms, look, &overflow);
+            } else mate_rescue_pair_d(cv, p.ep, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, idx->ref_string, seq, l_seq, ap, n, bp, ar.ms, &overflow);
+        }
         if (n[0] > caps.acap[0] || n[1] > caps.acap[1]) layout_bad |= 1;
         const SamScratch &sc = ar.sc;
         long long pair_recs = 0, pair_xa = 0, pair_ops = 0, pair_md = 0;

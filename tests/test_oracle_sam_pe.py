@@ -232,10 +232,10 @@ def _emul():
         d = os.path.join(ROOT, "tests", "host_emul")
         so = os.path.join(d, "libsamemul.so")
         srcs = [os.path.join(d, "sam_emul.cpp")] + [os.path.join(ROOT, "bwa-mem2_b200", "csrc", f) for f in
-                                                     ("sam_layout.cuh", "sam_device.cuh", "mate_device.cuh", "ksw_device.cuh", "cigar_device.cuh", "ext_device.cuh", "chain_device.cuh", "hd.h")]
+                                                     ("../../tests/host_emul/ksw_warp_emul.cpp", "ksw_warp.cuh", "sam_layout.cuh", "sam_device.cuh", "mate_device.cuh", "ksw_device.cuh", "cigar_device.cuh", "ext_device.cuh", "chain_device.cuh", "hd.h")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-I" + os.path.join(ROOT, "bwa-mem2_b200", "csrc"),
-                                   "-I" + os.path.join(ROOT, "include"), srcs[0], "-o", so])
+                                   "-I" + os.path.join(ROOT, "include"), srcs[0], os.path.join(d, "ksw_warp_emul.cpp"), "-o", so])
         _EMUL = C.CDLL(so)
     return _EMUL
 
@@ -279,6 +279,27 @@ def xa_of_lines(lines):
         t = [f for f in ln.split("\t") if f.startswith("XA:Z:")]
         out.append(t[0][5:] if t else "")
     return out
+
+
+def test_staged_rescue_equals_the_per_pair_block(c0):
+    """The shape of the next kernel version: the rescue's local alignments enumerated from the regions before any rescue, computed as a
+    batch by the warp formulation (ksw_warp.cuh), looked up by the per-pair block.  Same records; the batch must hold what is asked for."""
+    capi, idx, reads, codes, offs, names = c0
+    opt = capi.default_opt(); opt.flag |= 0x2
+    regs, ro, _, rc = ol.seed_chain_extend(idx, opt, codes, offs)
+    lh, as_ = _pestat(capi, idx, opt, reads, regs, ro)
+    want = emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_)
+    L = _emul()
+    L.emul_sam_set_staged(1)
+    try:
+        got = emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_)
+        st = (C.c_longlong * 4)(); L.emul_sam_stage_stats(st)
+    finally:
+        L.emul_sam_set_staged(0)
+    _compare(fields(*got, names), fields(*want, names))
+    jobs, used, in_place, moved = [int(v) for v in st]
+    assert jobs > 50 and used > 50 and in_place == 0 and moved == 0, (jobs, used, in_place, moved)
+    assert used <= jobs
 
 
 @pytest.mark.parametrize("flags", [0, 0x8, 0x10, 0x4, 0x20, 0x200, 0x1800, 0x1000, 0x1808], ids=["default", "all", "no_multi", "no_pairing", "no_rescue", "softclip", "primary5", "keep_supp_mapq", "primary5_all"])
