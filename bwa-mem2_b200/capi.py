@@ -87,7 +87,7 @@ class RegResult(C.Structure):
 
 EXPORTS = ["bm2_gather64_gbs", "bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
            "bm2_last_error", "bm2_extend_pairs", "bm2_extend_pairs_device", "bm2_collect_smems", "bm2_seed_chain",
-           "bm2_seed_chain_extend", "bm2_last_stage_ms", "bm2_gen_cigar", "bm2_pestat", "bm2_sam_pe", "bm2_ksw_align2"]
+           "bm2_seed_chain_extend", "bm2_last_stage_ms", "bm2_gen_cigar", "bm2_pestat", "bm2_sam_pe", "bm2_sam_se", "bm2_ksw_align2"]
 
 _lib = None
 
@@ -258,6 +258,19 @@ class Context:
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         self._check(f(self._ctx, seqs.ctypes.data_as(C.c_void_p), len(seqs), rq.ctypes.data_as(C.c_void_p), len(rq), out.ctypes.data_as(C.c_void_p)), "bm2_ksw_align2")
         return np.stack([out[k] for k in ("score", "te", "qe", "score2", "te2", "tb", "qb")], axis=1).astype(np.int32) if len(out) else np.zeros((0, 7), np.int32)
+
+    def sam_se(self, codes, offsets, regs, read_off, id_base=0):
+        """bm2_sam_se: the SAM stage of a batch of single-end reads -> (recs SAM_REC_DT, xa SAM_XA_DT, cigar uint32[], md bytes)."""
+        rb, keep = self._batch(codes, offsets)
+        regs = np.ascontiguousarray(regs, REG_DT); read_off = np.ascontiguousarray(read_off, np.int64)
+        res = SamResult()
+        f = lib().bm2_sam_se
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        self._check(f(self._ctx, C.byref(rb), regs.ctypes.data_as(C.c_void_p), read_off.ctypes.data_as(C.c_void_p), int(id_base), C.byref(res)), "bm2_sam_se")
+        def arr(p, n, dt):
+            dt = np.dtype(dt)
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * dt.itemsize,)).view(dt).copy() if n else np.zeros(0, dt)
+        return arr(res.recs, res.n_recs, SAM_REC_DT), arr(res.xa, res.n_xa, SAM_XA_DT), arr(res.cigar, res.n_ops, "<u4"), arr(res.md, res.n_md, "u1")
 
     def sam_pe(self, codes, offsets, regs, read_off, pes, id_base=0):
         """bm2_sam_pe: the SAM stage of a batch of pairs -> (recs SAM_REC_DT, xa SAM_XA_DT, cigar uint32[], md bytes)."""

@@ -35,24 +35,25 @@ struct PairFinal { int64_t recs, xa, ops, md; };   // compact offsets (inside th
 __global__ void __launch_bounds__(64)
 sam_kernel(SamParams p, SamTables tb, ContigView cv, MatePes pes, int max_matesw, int rescue, const uint8_t *__restrict__ ref,
            const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, const bm2_alnreg_t *__restrict__ regs, const int64_t *__restrict__ reg_off,
-           const PairDesc *__restrict__ desc, int n_pairs, int64_t id_base, uint8_t *arena, bm2_sam_rec *recs_w, bm2_sam_xa *xa_w, uint32_t *ops_w, char *md_w,
-           PairCount *cnt)
+           const PairDesc *__restrict__ desc, int n_pairs, int paired, int64_t id_base, uint8_t *arena, bm2_sam_rec *recs_w, bm2_sam_xa *xa_w, uint32_t *ops_w,
+           char *md_w, PairCount *cnt)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_pairs) return;
     const PairDesc d = desc[t];
     SamArena ar;
     sam_arena_carve_d(arena + d.arena_off, d.caps, 0, &ar);
-    const uint8_t *seq[2]; int l_seq[2], n[2];
-    for (int i = 0; i < 2; ++i) {
-        const int64_t r = 2LL * d.pair + i;
+    const uint8_t *seq[2] = { codes, codes }; int l_seq[2] = { 0, 0 }, n[2] = { 0, 0 };
+    const int64_t read0 = paired ? 2LL * d.pair : d.pair;         // a unit is a pair (reads 2u, 2u+1) or, single-end, one read
+    for (int i = 0; i < (paired ? 2 : 1); ++i) {
+        const int64_t r = read0 + i;
         seq[i] = codes + offs[r]; l_seq[i] = (int) (offs[r + 1] - offs[r]);
         n[i] = (int) (reg_off[r + 1] - reg_off[r]);
         for (int k = 0; k < n[i]; ++k) reg_copy(&ar.a[i][k], &regs[reg_off[r] + k]);
     }
     int overflow = 0;
     bm2_alnreg_t *ap[2] = { ar.a[0], ar.a[1] }, *bp[2] = { ar.b[0], ar.b[1] };
-    if (rescue) mate_rescue_pair_d(cv, p.ep, p.min_seed_len, p.pen_unpaired, max_matesw, pes, ref, seq, l_seq, ap, n, bp, ar.ms, &overflow);
+    if (rescue && paired) mate_rescue_pair_d(cv, p.ep, p.min_seed_len, p.pen_unpaired, max_matesw, pes, ref, seq, l_seq, ap, n, bp, ar.ms, &overflow);
     PairCount c; c.recs = 0; c.xa = 0; c.ops = 0; c.md = 0; c.overflow = 0; c._pad = 0;
     bm2_sam_rec *recs = recs_w + d.rec_off; bm2_sam_xa *xa = xa_w + d.xa_off; uint32_t *ops = ops_w + d.ops_off; char *md = md_w + d.md_off;
     const SamPairCaps &cp = d.caps;
@@ -60,7 +61,7 @@ sam_kernel(SamParams p, SamTables tb, ContigView cv, MatePes pes, int max_matesw
         const int nmd = r.n_cigar ? r.n_md : 1;
         if (c.recs >= cp.recs_cap || c.ops + r.n_cigar > cp.out_ops || c.md + nmd > cp.out_md) { overflow |= BM2_OVF_RECORDS; return; }
         bm2_sam_rec o;
-        o.read = 2 * d.pair + i; o.flag = r.flag; o.rid = r.rid; o.rnext = r.rnext; o.mapq = r.mapq; o.nm = r.nm; o.score = r.score; o.sub = r.sub;
+        o.read = (int32_t) read0 + i; o.flag = r.flag; o.rid = r.rid; o.rnext = r.rnext; o.mapq = r.mapq; o.nm = r.nm; o.score = r.score; o.sub = r.sub;
         o.alt_sc = r.alt_sc; o.reg = r.reg; o.n_cigar = r.n_cigar; o.n_md = nmd; o.pos = r.pos; o.pnext = r.pnext; o.tlen = r.tlen;
         o.cigar_off = c.ops; o.md_off = c.md;
         for (int j = 0; j < r.n_cigar; ++j) ops[c.ops + j] = rops[j];
@@ -70,11 +71,12 @@ sam_kernel(SamParams p, SamTables tb, ContigView cv, MatePes pes, int max_matesw
     auto emit_xa = [&](int i, int reg, const SamAln &e) {
         if (c.xa >= cp.xa_cap || c.ops + e.n_cigar > cp.out_ops) { overflow |= BM2_OVF_RECORDS; return; }
         bm2_sam_xa o;
-        o.read = 2 * d.pair + i; o.reg = reg; o.rid = e.rid; o.is_rev = e.is_rev; o.nm = e.nm; o.n_cigar = e.n_cigar; o.pos = e.pos; o.cigar_off = c.ops;
+        o.read = (int32_t) read0 + i; o.reg = reg; o.rid = e.rid; o.is_rev = e.is_rev; o.nm = e.nm; o.n_cigar = e.n_cigar; o.pos = e.pos; o.cigar_off = c.ops;
         for (int j = 0; j < e.n_cigar; ++j) ops[c.ops + j] = e.cigar[j];
         xa[c.xa++] = o; c.ops += e.n_cigar;
     };
-    sam_pe_pair_d(p, tb, cv, pes, ref, seq, l_seq, ap, n, (int) (id_base + d.pair), ar.sc, emit, emit_xa, &overflow);
+    if (paired) sam_pe_pair_d(p, tb, cv, pes, ref, seq, l_seq, ap, n, (int) (id_base + d.pair), ar.sc, emit, emit_xa, &overflow);
+    else sam_se_read_d(p, tb, cv, ref, seq[0], l_seq[0], ar.a[0], n[0], id_base + d.pair, ar.sc, emit, emit_xa, &overflow);
     c.overflow = overflow;
     cnt[t] = c;
 }
@@ -117,14 +119,17 @@ int grow_host(bm2_ctx *ctx, HostBuf &b, size_t used, size_t need) {
 }
 }  // namespace
 
-extern "C" int bm2_sam_pe(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off, const bm2_pestat_t pes4[4],
-                          int64_t id_base, bm2_sam_result *out)
+namespace {
+// paired: units are pairs (pes4 given); single-end: units are reads (pes4 == nullptr: no orientation has statistics)
+int run_sam(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off, const bm2_pestat_t *pes4, int64_t id_base,
+            bm2_sam_result *out)
 {
     bm2_ctx *ctx_for_error = ctx;
-    if (!ctx || !reads || !out || !read_off || !pes4) { if (ctx) bm2_set_error(ctx, "bm2_sam_pe: bad arguments"); return 1; }
-    if (!ctx->idx.loaded) { bm2_set_error(ctx, "bm2_sam_pe needs a context created with an index"); return 1; }
+    const int paired = pes4 != nullptr;
+    if (!ctx || !reads || !out || !read_off) { if (ctx) bm2_set_error(ctx, "bm2_sam_pe / bm2_sam_se: bad arguments"); return 1; }
+    if (!ctx->idx.loaded) { bm2_set_error(ctx, "bm2_sam_pe / bm2_sam_se need a context created with an index"); return 1; }
     const int nr = reads->n_reads;
-    if (nr < 0 || (nr & 1)) { bm2_set_error(ctx, "bm2_sam_pe: the batch must hold whole pairs (reads 2i, 2i+1)"); return 1; }
+    if (nr < 0 || (paired && (nr & 1))) { bm2_set_error(ctx, "bm2_sam_pe: the batch must hold whole pairs (reads 2i, 2i+1)"); return 1; }
     if (read_off[nr] > 0 && !regs) { bm2_set_error(ctx, "bm2_sam_pe: regs is NULL"); return 1; }
     BM2_CUDA_OK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -132,7 +137,7 @@ extern "C" int bm2_sam_pe(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_a
     if (grow_host(ctx, ctx->h[SH_RECS], 0, 64) || grow_host(ctx, ctx->h[SH_XA], 0, 64) || grow_host(ctx, ctx->h[SH_OPS], 0, 64) || grow_host(ctx, ctx->h[SH_MD], 0, 64)) return 1;
     out->recs = (const bm2_sam_rec *) ctx->h[SH_RECS].p; out->xa = (const bm2_sam_xa *) ctx->h[SH_XA].p;
     out->cigar = (const uint32_t *) ctx->h[SH_OPS].p; out->md = (const char *) ctx->h[SH_MD].p;
-    const int n_pairs_all = nr >> 1;
+    const int n_pairs_all = paired ? nr >> 1 : nr;              // units
     if (n_pairs_all == 0) return 0;
     const bm2_mem_opt_t &o = ctx->opt;
     if (o.e_del <= 0 || o.e_ins <= 0 || o.a <= 0) { bm2_set_error(ctx, "bm2_sam_pe: match score and gap extension penalties must be positive"); return 1; }
@@ -146,7 +151,7 @@ extern "C" int bm2_sam_pe(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_a
     p.mapQ_coef_len = o.mapQ_coef_len; p.mapQ_coef_fac = o.mapQ_coef_fac;
     p.XA_drop_ratio = o.XA_drop_ratio; p.max_XA_hits = o.max_XA_hits; p.max_XA_hits_alt = o.max_XA_hits_alt;
     MatePes pes;
-    for (int d = 0; d < 4; ++d) { pes.low[d] = pes4[d].low; pes.high[d] = pes4[d].high; pes.failed[d] = pes4[d].failed; }
+    for (int d = 0; d < 4; ++d) { pes.low[d] = paired ? pes4[d].low : 0; pes.high[d] = paired ? pes4[d].high : 0; pes.failed[d] = paired ? pes4[d].failed : 1; }
     const int n_log = 1 << 16;
     std::vector<double> tab((size_t) n_log);
     for (int k = 0; k < n_log; ++k) tab[(size_t) k] = log((double) k);
@@ -170,7 +175,7 @@ extern "C" int bm2_sam_pe(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_a
     tb.log_tab = P<double>(ctx, SB_LOG);
     for (int d = 0; d < 4; ++d) tb.pair_term[d] = P<double>(ctx, SB_TERM) + term_at[d];
     ContigView cv; cv.l_pac = ctx->idx.l_pac; cv.n_seqs = ctx->idx.n_seqs; cv.ann_off = ctx->idx.ann_off; cv.ann_len = ctx->idx.ann_len; cv.ann_alt = ctx->idx.ann_alt;
-    const int rescue = !(o.flag & 0x20);
+    const int rescue = paired && !(o.flag & 0x20);
 
     // ---- inputs ------------------------------------------------------------------------------------------------------------
     const int64_t total = reads->offsets[nr], n_regs = read_off[nr];
@@ -186,15 +191,15 @@ extern "C" int bm2_sam_pe(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_a
     for (int pr = 0; pr < n_pairs_all; ++pr) {
         SamPairShape sh;
         for (int i = 0; i < 2; ++i) {
-            const int r = 2 * pr + i;
+            if (!paired && i == 1) { sam_shape_read_d(sh, 1, 0, regs, 0, o.w); break; }
+            const int r = paired ? 2 * pr + i : pr;
             const int64_t nn = read_off[r + 1] - read_off[r], ls = reads->offsets[r + 1] - reads->offsets[r];
-            if (nn < 0 || nn > (1 << 24) || ls < 0 || ls > (1 << 24)) { bm2_set_error(ctx, "bm2_sam_pe: a read with more than 2^24 bases or regions"); return 1; }
-            sh.n[i] = (int) nn; sh.l_seq[i] = (int) ls; sh.max_rlen[i] = 0; sh.sum_rlen[i] = 0;
+            if (nn < 0 || nn > (1 << 24) || ls < 0 || ls > (1 << 24)) { bm2_set_error(ctx, "bm2_sam_pe / bm2_sam_se: a read with more than 2^24 bases or regions"); return 1; }
             for (int64_t k = read_off[r]; k < read_off[r + 1]; ++k) {
                 const long long rl = regs[k].re - regs[k].rb;
-                if (rl < 0 || rl > (1 << 24)) { bm2_set_error(ctx, "bm2_sam_pe: a region outside [0, 2^24) reference bases"); return 1; }
-                sh.sum_rlen[i] += rl; if (rl > sh.max_rlen[i]) sh.max_rlen[i] = rl;
+                if (rl < 0 || rl > (1 << 24)) { bm2_set_error(ctx, "bm2_sam_pe / bm2_sam_se: a region outside [0, 2^24) reference bases"); return 1; }
             }
+            sam_shape_read_d(sh, i, (int) ls, regs + read_off[r], (int) nn, o.w);
         }
         desc[(size_t) pr].caps = sam_pair_caps_d(sh, pes, o.max_matesw, rescue != 0);
         desc[(size_t) pr].pair = pr;
@@ -222,7 +227,7 @@ extern "C" int bm2_sam_pe(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_a
             ctx->ensure_host(ctx->h[SH_CNT], (size_t) np * (sizeof(PairCount) + sizeof(PairFinal)))) return 1;
         BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[SB_DESC].p, desc.data() + w0, (size_t) np * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
         sam_kernel<<<(unsigned) ((np + 63) / 64), 64, 0, st>>>(p, tb, cv, pes, o.max_matesw, rescue, ctx->idx.ref, P<uint8_t>(ctx, SB_CODES), P<int64_t>(ctx, SB_OFFS),
-                                                              P<bm2_alnreg_t>(ctx, SB_REGS), P<int64_t>(ctx, SB_REGOFF), P<PairDesc>(ctx, SB_DESC), np, id_base,
+                                                              P<bm2_alnreg_t>(ctx, SB_REGS), P<int64_t>(ctx, SB_REGOFF), P<PairDesc>(ctx, SB_DESC), np, paired, id_base,
                                                               P<uint8_t>(ctx, SB_ARENA), P<bm2_sam_rec>(ctx, SB_RECS_W), P<bm2_sam_xa>(ctx, SB_XA_W),
                                                               P<uint32_t>(ctx, SB_OPS_W), P<char>(ctx, SB_MD_W), P<PairCount>(ctx, SB_CNT));
         BM2_CUDA_OK(cudaGetLastError());
@@ -261,4 +266,17 @@ extern "C" int bm2_sam_pe(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_a
     out->n_ops = (int64_t) (used[2] / 4); out->cigar = (const uint32_t *) ctx->h[SH_OPS].p;
     out->n_md = (int64_t) used[3]; out->md = (const char *) ctx->h[SH_MD].p;
     return 0;
+}
+}  // namespace
+
+extern "C" int bm2_sam_pe(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off, const bm2_pestat_t pes4[4],
+                          int64_t id_base, bm2_sam_result *out)
+{
+    if (!pes4) { if (ctx) bm2_set_error(ctx, "bm2_sam_pe: pes is NULL"); return 1; }
+    return run_sam(ctx, reads, regs, read_off, pes4, id_base, out);
+}
+
+extern "C" int bm2_sam_se(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off, int64_t id_base, bm2_sam_result *out)
+{
+    return run_sam(ctx, reads, regs, read_off, nullptr, id_base, out);
 }

@@ -531,3 +531,52 @@ BM2_HD void sam_pe_pair_d(const SamParams &p, const SamTables &tb, const ContigV
     }
     out_all();
 }
+
+// The single-end branch of worker_sam for one read (src/bwamem.cpp:1320-1334): mem_mark_primary_se, -5 reordering, then mem_reg2sam
+// (:1521-1577) without a mate.  a[0..n) the read's regions (modified: marking), id = the read's index in the run.
+// sc: z / idx n + 4 ints each, he, zz, aa[0] (aa_cap >= n + 1 records), pools, ops as for a pair.
+template <class Emit, class EmitXa>
+BM2_HD void sam_se_read_d(const SamParams &p, const SamTables &tb, const ContigView &cv, const uint8_t *ref, const uint8_t *seq, int l_seq, bm2_alnreg_t *a, int n,
+                          int64_t id, const SamScratch &sc, Emit &emit, EmitXa &emit_xa, int *overflow)
+{
+    SamPool pl = { sc.cig_pool, sc.cig_cap, 0, sc.md_pool, sc.md_cap, 0 };
+    sam_mark_primary_se_d(p, n, a, id, sc.z, sc.idx);
+    if (p.flag & 0x800) sam_reorder_primary5_d(p.T, n, a);
+    if (!(p.flag & 0x8) && n > 0) {                               // XA entries (mem_gen_alt inside mem_reg2sam, :1529-1530)
+        bm2_alnreg_t widest; widest.rb = 0; widest.re = 0;
+        for (int k = 0; k < n; ++k) if (a[k].re - a[k].rb > widest.re) widest.re = a[k].re - a[k].rb;
+        SamAln t;
+        if (!sam_alloc_d(pl, l_seq, &widest, &t)) { *overflow |= BM2_OVF_POOL; return; }
+        auto one = [&](int r, const SamAln &e) { emit_xa(0, r, e); };
+        sam_gen_alt_d(p, tb, cv, ref, l_seq, seq, a, n, sc.z, sc.idx, sc.he, sc.zz, t, one, overflow);
+    }
+    int n_aa = 0, l = 0;
+    SamAln *aa = sc.aa[0];
+    for (int k = 0; k < n; ++k) {
+        const bm2_alnreg_t *q = &a[k];
+        if (q->score < p.T) continue;
+        if (q->secondary >= 0 && (sam_is_alt_d(*q) || !(p.flag & 0x8))) continue;
+        if (q->secondary >= 0 && q->secondary < 0x7fffffff && q->score < a[q->secondary].score * p.drop_ratio) continue;
+        if (n_aa >= sc.aa_cap) { *overflow |= BM2_OVF_RECORDS; break; }
+        SamAln &t = aa[n_aa];
+        if (!sam_alloc_d(pl, l_seq, q, &t)) { *overflow |= BM2_OVF_POOL; return; }
+        sam_reg2aln_d(p, tb, cv, ref, l_seq, seq, q, sc.he, sc.zz, &t, overflow);
+        t.reg = k;
+        if (q->secondary >= 0) t.sub = -1;
+        if (l && q->secondary < 0) t.flag |= (p.flag & 0x10) ? 0x10000 : 0x800;
+        if (!(p.flag & 0x1000) && l && !sam_is_alt_d(*q) && t.mapq > aa[0].mapq) t.mapq = aa[0].mapq;
+        ++n_aa; ++l;
+    }
+    if (n_aa == 0) {
+        SamAln &t = aa[0];
+        if (!sam_alloc_d(pl, l_seq, 0, &t)) { *overflow |= BM2_OVF_POOL; return; }
+        sam_reg2aln_d(p, tb, cv, ref, l_seq, seq, 0, sc.he, sc.zz, &t, overflow);
+        n_aa = 1;
+    }
+    for (int k = 0; k < n_aa; ++k) {
+        SamRec r;
+        sam_aln2rec_d(p, aa[k], k, (const SamAln *) 0, &r, sc.ops);
+        emit(0, k, r, sc.ops, aa[k].n_cigar ? aa[k].md : "");
+    }
+}
+

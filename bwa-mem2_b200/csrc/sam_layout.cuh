@@ -14,7 +14,30 @@ struct SamPairShape {            // known before the launch (seam 2's output and
     int l_seq[2];
     long long max_rlen[2];       // widest region (re - rb) of each read, 0 if none
     long long sum_rlen[2];       // sum of (re - rb) over the regions of each read
+    long long max_zcells[2];     // largest backtrack matrix among the regions of each read (sam_reg_zcells_d)
 };
+
+// Backtrack cells mem_reg2aln can need for a region: ksw_global2 keeps min(l_query, 2w + 1) columns per reference base, and its band is
+// at most max(4 * opt->w, |rlen - l_query| + 3) (the doubling loop of src/bwamem.cpp:1762-1768 stops at opt->w << 2; src/bwa.cpp:292-300).
+BM2_HD long long sam_reg_zcells_d(int w_opt, const bm2_alnreg_t &r) {
+    const long long lq = r.qe - r.qb, rl = r.re - r.rb;
+    if (lq <= 0 || rl <= 0) return 0;
+    long long w = 4LL * w_opt, d = rl > lq ? rl - lq : lq - rl;
+    if (d + 3 > w) w = d + 3;
+    const long long ncol = lq < 2 * w + 1 ? lq : 2 * w + 1;
+    return ncol * rl;
+}
+
+// shape of read i of a pair from its regions (host side of the launch)
+BM2_HD void sam_shape_read_d(SamPairShape &s, int i, int l_seq, const bm2_alnreg_t *a, int n, int w_opt) {
+    s.n[i] = n; s.l_seq[i] = l_seq; s.max_rlen[i] = 0; s.sum_rlen[i] = 0; s.max_zcells[i] = 0;
+    for (int k = 0; k < n; ++k) {
+        const long long rl = a[k].re - a[k].rb, zc = sam_reg_zcells_d(w_opt, a[k]);
+        s.sum_rlen[i] += rl;
+        if (rl > s.max_rlen[i]) s.max_rlen[i] = rl;
+        if (zc > s.max_zcells[i]) s.max_zcells[i] = zc;
+    }
+}
 
 struct SamPairCaps {
     int acap[2];                 // regions of read i after rescue: every mem_matesw call adds at most one per orientation (:233-238),
@@ -27,7 +50,7 @@ struct SamPairCaps {
     int zi;                      // z / idx / keys entries: max(acap) + 4
     int nv;                      // pairing keys: acap[0] + acap[1] + 4
     int aa_cap;                  // records of one read: its regions + 2 (mem_reg2sam prints each region at most once, + the ALT / unmapped one)
-    long long zz_cells;          // backtrack matrix of one global alignment: columns <= l_query, rows = rlen
+    long long zz_cells;          // backtrack matrix of one global alignment (sam_reg_zcells_d; rescued regions: l_query x window)
     long long pool_ops, pool_md; // CIGAR / MD storage of all records of the pair + one XA entry at a time (sam_alloc_d's sizes)
     int ops_cap;                 // printed CIGAR of one record
     int recs_cap, xa_cap;        // output: records of the pair, XA entries of the pair (one per region at most)
@@ -59,7 +82,8 @@ BM2_HD SamPairCaps sam_pair_caps_d(const SamPairShape &s, const MatePes &pes, in
     c.zz_cells = 16; c.pool_ops = 0; c.pool_md = 0; c.ops_cap = 16; c.out_ops = 0; c.out_md = 0;
     for (int i = 0; i < 2; ++i) {
         const long long lq = s.l_seq[i], widest = c.rlen_cap[i];
-        if (lq * widest + 16 > c.zz_cells) c.zz_cells = lq * widest + 16;
+        if (s.max_zcells[i] + 16 > c.zz_cells) c.zz_cells = s.max_zcells[i] + 16;
+        if (resc[i] > 0 && lq * c.tcap + 16 > c.zz_cells) c.zz_cells = lq * c.tcap + 16;      // a rescued region: at most l_query columns, rows inside its window
         // every region printed once (its own rlen), rescued ones bounded by the window, + h[i], the ALT record, the unmapped record, one XA entry
         const long long extra = 4;
         const long long ops = s.n[i] * (lq + 4) + s.sum_rlen[i] + resc[i] * (lq + c.tcap + 4) + extra * (lq + widest + 4);

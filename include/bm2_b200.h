@@ -306,6 +306,9 @@ typedef struct bm2_sam_result {
  * run (the reference's `id`, which seeds the tie-breaking hashes). */
 int bm2_sam_pe(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off, const bm2_pestat_t pes[4],
                int64_t id_base, bm2_sam_result *out);
+/* The single-end branch of worker_sam (src/bwamem.cpp:1320-1334: mem_mark_primary_se, -5, mem_reg2sam without a mate) for a batch of reads;
+ * same records (no RNEXT / PNEXT / TLEN).  id_base: number of reads before this batch in the run. */
+int bm2_sam_se(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off, int64_t id_base, bm2_sam_result *out);
 
 #ifdef __cplusplus
 }

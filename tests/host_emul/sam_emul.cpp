@@ -100,11 +100,7 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
             const int r = 2 * pr + i;
             seq[i] = reads->codes + reads->offsets[r]; l_seq[i] = (int) (reads->offsets[r + 1] - reads->offsets[r]);
             n[i] = (int) (read_off[r + 1] - read_off[r]);
-            shape.n[i] = n[i]; shape.l_seq[i] = l_seq[i]; shape.max_rlen[i] = 0; shape.sum_rlen[i] = 0;
-            for (int64_t k = read_off[r]; k < read_off[r + 1]; ++k) {
-                const long long rl = regs[k].re - regs[k].rb;
-                shape.sum_rlen[i] += rl; if (rl > shape.max_rlen[i]) shape.max_rlen[i] = rl;
-            }
+            sam_shape_read_d(shape, i, l_seq[i], regs + read_off[r], n[i], opt->w);
         }
         // the arena a kernel would get: capacities from sam_layout.cuh, guard words between the pieces
         const SamPairCaps caps = sam_pair_caps_d(shape, pes, opt->max_matesw, !(opt->flag & 0x20));
@@ -140,6 +136,69 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
         sam_pe_pair_d(p, tb, cv, pes, idx->ref_string, seq, l_seq, ap, n, (int) (id_base + pr), sc, emit, emit_xa, &overflow);
         if (!sam_arena_guards_ok_d(ar)) layout_bad |= 2;
         if (pair_recs > caps.recs_cap || pair_xa > caps.xa_cap || pair_ops > caps.out_ops || pair_md > caps.out_md) layout_bad |= 4;
+    }
+    const size_t nr = out.size();
+    *recs_out = (bm2o_samrec *) malloc(sizeof(bm2o_samrec) * (nr + 1)); memcpy(*recs_out, out.data(), sizeof(bm2o_samrec) * nr);
+    *cigar_out = (uint32_t *) malloc(4 * (ops_all.size() + 1)); memcpy(*cigar_out, ops_all.data(), 4 * ops_all.size());
+    *md_out = (char *) malloc(md_all.size() + 1); memcpy(*md_out, md_all.data(), md_all.size());
+    *rec_reg_out = (int32_t *) malloc(4 * (nr + 1)); memcpy(*rec_reg_out, rec_reg.data(), 4 * nr);
+    *xa_out = (EmXa *) malloc(sizeof(EmXa) * (xa.size() + 1)); memcpy(*xa_out, xa.data(), sizeof(EmXa) * xa.size());
+    *xa_cigar_out = (uint32_t *) malloc(4 * (xa_ops.size() + 1)); memcpy(*xa_cigar_out, xa_ops.data(), 4 * xa_ops.size());
+    *n_xa_out = (int64_t) xa.size(); *n_xa_ops_out = (int64_t) xa_ops.size();
+    *n_recs = (int64_t) nr; *n_ops_out = (int64_t) ops_all.size(); *n_md_out = (int64_t) md_all.size();
+    return layout_bad ? 0x1000 | layout_bad : overflow ? 0x100 | overflow : 0;
+}
+
+// The single-end branch (sam_se_read_d) in the same record layout; one read per arena (shape: read 0 of a pair without a mate).
+extern "C" int emul_sam_se(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off,
+                           int64_t id_base, bm2o_samrec **recs_out, int64_t *n_recs, uint32_t **cigar_out, int64_t *n_ops_out, char **md_out, int64_t *n_md_out,
+                           int32_t **rec_reg_out, EmXa **xa_out, int64_t *n_xa_out, uint32_t **xa_cigar_out, int64_t *n_xa_ops_out)
+{
+    ContigView cv; cv.l_pac = idx->l_pac; cv.n_seqs = idx->n_seqs; cv.ann_off = idx->ann_offset; cv.ann_len = idx->ann_len; cv.ann_alt = idx->ann_is_alt;
+    SamParams p;
+    p.ep.a = opt->a; p.ep.b = opt->b; p.ep.o_del = opt->o_del; p.ep.e_del = opt->e_del; p.ep.o_ins = opt->o_ins; p.ep.e_ins = opt->e_ins; p.ep.w = opt->w;
+    p.ep.pen_clip5 = opt->pen_clip5; p.ep.pen_clip3 = opt->pen_clip3; p.ep.max_chain_gap = opt->max_chain_gap; p.ep.mask_level_redun = opt->mask_level_redun;
+    memcpy(p.ep.mat, opt->mat, 25);
+    p.T = opt->T; p.flag = opt->flag; p.min_seed_len = opt->min_seed_len; p.pen_unpaired = opt->pen_unpaired; p.mask_level = opt->mask_level;
+    p.drop_ratio = opt->drop_ratio; p.mapQ_coef_len = opt->mapQ_coef_len; p.mapQ_coef_fac = opt->mapQ_coef_fac;
+    p.XA_drop_ratio = opt->XA_drop_ratio; p.max_XA_hits = opt->max_XA_hits; p.max_XA_hits_alt = opt->max_XA_hits_alt;
+    MatePes pes; for (int d = 0; d < 4; ++d) { pes.low[d] = 0; pes.high[d] = 0; pes.failed[d] = 1; }
+    std::vector<double> logt(1 << 16); for (size_t k = 0; k < logt.size(); ++k) logt[k] = log((double) k);
+    SamTables tb; tb.log_tab = logt.data(); tb.n_log = (int) logt.size();
+    for (int d = 0; d < 4; ++d) { tb.pair_lo[d] = 0; tb.pair_hi[d] = -1; tb.pair_term[d] = 0; }
+    std::vector<bm2o_samrec> out; std::vector<uint32_t> ops_all; std::string md_all;
+    std::vector<int32_t> rec_reg; std::vector<EmXa> xa; std::vector<uint32_t> xa_ops;
+    int overflow = 0, layout_bad = 0;
+    for (int r = 0; r < reads->n_reads; ++r) {
+        const uint8_t *seq = reads->codes + reads->offsets[r]; const int l_seq = (int) (reads->offsets[r + 1] - reads->offsets[r]);
+        const int n = (int) (read_off[r + 1] - read_off[r]);
+        SamPairShape shape;
+        sam_shape_read_d(shape, 0, l_seq, regs + read_off[r], n, opt->w);
+        sam_shape_read_d(shape, 1, 0, regs, 0, opt->w);
+        const SamPairCaps caps = sam_pair_caps_d(shape, pes, opt->max_matesw, false);
+        std::vector<uint8_t> arena(caps.scratch_bytes + 64);
+        SamArena ar;
+        sam_arena_carve_d(arena.data(), caps, 1, &ar);
+        memcpy(ar.a[0], regs + read_off[r], sizeof(bm2_alnreg_t) * (size_t) n);
+        long long n_rec = 0, n_x = 0, n_o = 0, n_m = 0;
+        auto emit = [&](int, int, const SamRec &q, const uint32_t *ops, const char *md) {
+            bm2o_samrec o; memset(&o, 0, sizeof(o));
+            o.read = r; o.flag = q.flag; o.rid = q.rid; o.mapq = q.mapq; o.rnext = q.rnext; o.tlen_valid = 1; o.nm = q.nm; o.score = q.score; o.sub = q.sub; o._pad = q.alt_sc;
+            o.n_cigar = q.n_cigar; o.pos = q.pos; o.pnext = q.pnext; o.tlen = q.tlen; o.cigar_off = (int64_t) ops_all.size(); o.md_off = (int64_t) md_all.size();
+            ops_all.insert(ops_all.end(), ops, ops + q.n_cigar);
+            if (q.n_cigar) md_all += md;
+            md_all.push_back('\0');
+            o.n_md = (int32_t) (md_all.size() - (size_t) o.md_off);
+            out.push_back(o); rec_reg.push_back(q.reg); ++n_rec; n_o += q.n_cigar; n_m += o.n_md;
+        };
+        auto emit_xa = [&](int, int reg, const SamAln &t) {
+            EmXa e; e.read = r; e.reg = reg; e.rid = t.rid; e.is_rev = t.is_rev; e.nm = t.nm; e.n_cigar = t.n_cigar; e.pos = t.pos; e.cigar_off = (int64_t) xa_ops.size();
+            xa_ops.insert(xa_ops.end(), t.cigar, t.cigar + t.n_cigar);
+            xa.push_back(e); ++n_x; n_o += t.n_cigar;
+        };
+        sam_se_read_d(p, tb, cv, idx->ref_string, seq, l_seq, ar.a[0], n, id_base + r, ar.sc, emit, emit_xa, &overflow);
+        if (!sam_arena_guards_ok_d(ar)) layout_bad |= 2;
+        if (n_rec > caps.recs_cap || n_x > caps.xa_cap || n_o > caps.out_ops || n_m > caps.out_md) layout_bad |= 4;
     }
     const size_t nr = out.size();
     *recs_out = (bm2o_samrec *) malloc(sizeof(bm2o_samrec) * (nr + 1)); memcpy(*recs_out, out.data(), sizeof(bm2o_samrec) * nr);

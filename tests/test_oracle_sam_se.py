@@ -100,3 +100,67 @@ def test_single_end_sam_matches_reference(pkg, golden_dir, args):
     assert not bad, (len(bad), [(got[i], want[i]) for i in bad[:3]])
     assert sum(1 for w in want if w[1] & 0x800) >= 3 or "-M" in args or "-a" in args or "-T" in args
     idx.close()
+
+
+# ---- the single-end device logic (sam_se_read_d of sam_device.cuh, compiled for the host inside the bounded arenas) --------------------------
+def emul_sam_se(capi, idx, opt, codes, offs, regs, ro, id_base=0):
+    import test_oracle_sam_pe as tp
+    codes = np.ascontiguousarray(codes, np.uint8); offs = np.ascontiguousarray(offs, np.int64)
+    regs = np.ascontiguousarray(regs); ro = np.ascontiguousarray(ro, np.int64)
+    rb = capi.ReadBatch(len(offs) - 1, codes.ctypes.data, offs.ctypes.data)
+    rc_ = C.c_void_p(); cg = C.c_void_p(); md = C.c_void_p(); nr = C.c_int64(); no = C.c_int64(); nm = C.c_int64()
+    rr = C.c_void_p(); xa = C.c_void_p(); nxa = C.c_int64(); xc = C.c_void_p(); nxc = C.c_int64()
+    rc = tp._emul().emul_sam_se(C.byref(idx.desc), C.byref(opt), C.byref(rb), regs.ctypes.data_as(C.c_void_p), ro.ctypes.data_as(C.c_void_p), C.c_int64(id_base),
+                                C.byref(rc_), C.byref(nr), C.byref(cg), C.byref(no), C.byref(md), C.byref(nm), C.byref(rr), C.byref(xa), C.byref(nxa), C.byref(xc), C.byref(nxc))
+    assert rc == 0, rc
+    def arr(p, n, dt):
+        dt = np.dtype(dt)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(n, 1) * dt.itemsize,))[:n * dt.itemsize].view(dt).copy()
+    out = arr(rc_, nr.value, tp.REC_DT), arr(cg, no.value, "<u4"), arr(md, nm.value, "u1")
+    for p in (rc_, cg, md, rr, xa, xc):
+        ol.lib().bm2o_free(p)
+    return out
+
+
+def rec_fields(recs, cigar, md, names):
+    """The tuples of parse_sam from printed records (flags and clip letters already as printed)."""
+    out = []
+    for r in recs:
+        if r["rid"] < 0:
+            out.append((int(r["read"]), int(r["flag"]), "*", 0, 0, "*", None, None, None, None)); continue
+        cs = "".join(f"{int(o >> 4)}{'MIDSH'[int(o & 0xf)]}" for o in cigar[r["cigar_off"]:r["cigar_off"] + r["n_cigar"]])
+        out.append((int(r["read"]), int(r["flag"]), names[r["rid"]], int(r["pos"]), int(r["mapq"]), cs, int(r["nm"]),
+                    bytes(md[r["md_off"]:r["md_off"] + r["n_md"] - 1]).decode(), int(r["score"]), int(r["sub"]) if r["sub"] >= 0 else None))
+    return out
+
+
+@pytest.mark.parametrize("args", [[], ["-a"], ["-M"], ["-T", "50"], ["-Y"], ["-5"]], ids=["default", "all", "no_multi", "T50", "softclip", "primary5"])
+def test_single_end_device_logic_matches_reference(pkg, golden_dir, args):
+    if cu.refbin() is None:
+        pytest.skip("oracle/_ref not built")
+    capi = pkg.capi
+    idx = capi.Index(golden_dir + "/c0_index/ref.fa")
+    reads = np.load(golden_dir + "/c0_reads.npz")["reads"][0::2]
+    codes = reads.reshape(-1); offs = (np.arange(len(reads) + 1) * reads.shape[1]).astype(np.int64)
+    work = tempfile.mkdtemp(prefix="bm2_se_")
+    with open(os.path.join(work, "r1.fq"), "w") as f:
+        for i, r in enumerate(reads):
+            f.write(f"@p{i}\n{''.join('ACGTN'[c] for c in r)}\n+\n{'I' * len(r)}\n")
+    with open(os.path.join(work, "o.sam"), "w") as f:
+        subprocess.check_call([cu.refbin(), "mem", "-t", "1", "-K", "100000000"] + args + [golden_dir + "/c0_index/ref.fa", os.path.join(work, "r1.fq")],
+                              stdout=f, stderr=subprocess.DEVNULL)
+    want = parse_sam(os.path.join(work, "o.sam"))
+    opt = capi.default_opt()
+    if "-a" in args: opt.flag |= 0x8
+    if "-M" in args: opt.flag |= 0x10
+    if "-Y" in args: opt.flag |= 0x200
+    if "-5" in args: opt.flag |= 0x1800
+    if "-T" in args: opt.T = int(args[args.index("-T") + 1])
+    regs, ro, _, rc = ol.seed_chain_extend(idx, opt, codes, offs)
+    names = [l.split()[1] for i, l in enumerate(open(golden_dir + "/c0_index/ref.fa.ann")) if i % 2 == 1]
+    got = rec_fields(*emul_sam_se(capi, idx, opt, codes, offs, regs, ro), names)
+    assert len(got) == len(want), (len(got), len(want))
+    bad = [i for i in range(len(got)) if got[i] != want[i]]
+    assert not bad, (len(bad), [(got[i], want[i]) for i in bad[:3]])
+    idx.close()
+

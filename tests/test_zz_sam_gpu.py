@@ -87,3 +87,24 @@ def test_tandem_repeat_pairs_match_oracle(pkg, golden_dir):
     names = ["tr1", "tr2"]
     tp._compare(tp.fields(recs, cig, md, names), tp.fields(*want, names))
     idx.close()
+
+
+@pytest.mark.xfail(strict=False, reason="bm2_sam_se was added after the file's first GPU run (same kernel, single-end branch)")
+@pytest.mark.parametrize("flags", [0, 0x8, 0x1800], ids=["default", "all", "primary5"])
+def test_single_end_records_match_oracle(c0, flags):
+    """bm2_sam_se: the r1 reads of C0 as single-end reads, against the oracle's single-end SAM stage (pinned to the live reference by
+    tests/test_oracle_sam_se.py)."""
+    import test_oracle_sam_se as ts
+    capi, idx, reads, codes, offs, names = c0
+    r1 = reads[0::2]; codes1 = np.ascontiguousarray(r1.reshape(-1)); offs1 = (np.arange(len(r1) + 1) * r1.shape[1]).astype(np.int64)
+    opt = capi.default_opt(); opt.flag |= flags
+    ctx = capi.Context(0, index=idx, opt=opt)
+    try:
+        regs, ro = ctx.seed_chain_extend(codes1, offs1)
+        recs, xa, cig, md = ctx.sam_se(codes1, offs1, regs, ro)
+    finally:
+        ctx.close()
+    alns, ocig, omd = ts.oracle_sam_se(capi, idx, opt, codes1, offs1, regs, ro)
+    want = ts.sam_fields(alns, ocig, omd, names, soft_clip_all=False)
+    assert ts.rec_fields(recs, cig, md, names) == want
+
