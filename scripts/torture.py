@@ -91,6 +91,18 @@ def main():
         tp._compare(tp.fields(*em[:3], names), tp.fields(*tp.oracle_sam_pe(capi, idx, opt2, codes, offs, regs, ro, lh, as_), names))
         assert em[3] == tp.xa_of_lines(twant), "XA entries differ from the reference's tags"
         sam_dev = "== oracle, XA == reference"
+        import ctypes as C, test_oracle_sam_se as ts
+        L = tp._emul(); L.emul_sam_set_staged(1)                # the staged rescue: batch of local alignments (warp formulation) + lookup
+        try:
+            em2 = tp.emul_sam_pe(capi, idx, opt2, codes, offs, regs, ro, lh, as_)
+            st = (C.c_longlong * 4)(); L.emul_sam_stage_stats(st)
+        finally:
+            L.emul_sam_set_staged(0)
+        assert all(np.array_equal(x, y) for x, y in zip(em2, em[:3])), "staged rescue differs"
+        sam_dev += f"; staged rescue identical (batch {st[0]}, used {st[1]}, computed in place {st[2]}, window moved {st[3]})"
+        al, oc, om = ts.oracle_sam_se(capi, idx, opt, codes, offs, regs, ro)                      # every read as a single-end read
+        assert ts.rec_fields(*ts.emul_sam_se(capi, idx, opt, codes, offs, regs, ro), names) == ts.sam_fields(al, oc, om, names, soft_clip_all=bool(opt.flag & 0x200)), "single-end differs"
+        sam_dev += "; single-end device logic == oracle"
     except AssertionError as ex:
         sam_dev = "DIFFERS: " + str(ex)[:300]
     print(f"seed {seed} {args}: {len(reads)} reads, {len(rr)} regs (max per read {int(np.diff(roff).max())}); oracle vs reference: {len(bad)} differing reads {bad[:5]}; "
