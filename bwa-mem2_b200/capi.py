@@ -49,8 +49,8 @@ PESTAT_DT = np.dtype([("low", "<i4"), ("high", "<i4"), ("failed", "<i4"), ("_pad
 
 # seam 4 (bm2_sam_pe): one record per SAM line, XA entries; layouts of include/bm2_b200.h
 SAM_REC_DT = np.dtype([("read", "<i4"), ("flag", "<i4"), ("rid", "<i4"), ("rnext", "<i4"), ("mapq", "<i4"), ("nm", "<i4"), ("score", "<i4"), ("sub", "<i4"),
-                       ("alt_sc", "<i4"), ("reg", "<i4"), ("n_cigar", "<i4"), ("n_md", "<i4"), ("pos", "<i8"), ("pnext", "<i8"), ("tlen", "<i8"),
-                       ("cigar_off", "<i8"), ("md_off", "<i8")])
+                       ("alt_sc", "<i4"), ("reg", "<i4"), ("n_cigar", "<i4"), ("n_md", "<i4"), ("is_alt", "<i4"), ("n_mc", "<i4"),
+                       ("pos", "<i8"), ("pnext", "<i8"), ("tlen", "<i8"), ("cigar_off", "<i8"), ("md_off", "<i8")])
 SAM_XA_DT = np.dtype([("read", "<i4"), ("reg", "<i4"), ("rid", "<i4"), ("is_rev", "<i4"), ("nm", "<i4"), ("n_cigar", "<i4"), ("pos", "<i8"), ("cigar_off", "<i8")])
 
 

@@ -59,14 +59,15 @@ sam_kernel(SamParams p, SamTables tb, ContigView cv, MatePes pes, int max_matesw
     const SamPairCaps &cp = d.caps;
     auto emit = [&](int i, int k, const SamRec &r, const uint32_t *rops, const char *rmd) {
         const int nmd = r.n_cigar ? r.n_md : 1;
-        if (c.recs >= cp.recs_cap || c.ops + r.n_cigar > cp.out_ops || c.md + nmd > cp.out_md) { overflow |= BM2_OVF_RECORDS; return; }
+        const int nops = r.n_cigar + r.n_mc;
+        if (c.recs >= cp.recs_cap || c.ops + nops > cp.out_ops || c.md + nmd > cp.out_md) { overflow |= BM2_OVF_RECORDS; return; }
         bm2_sam_rec o;
         o.read = (int32_t) read0 + i; o.flag = r.flag; o.rid = r.rid; o.rnext = r.rnext; o.mapq = r.mapq; o.nm = r.nm; o.score = r.score; o.sub = r.sub;
-        o.alt_sc = r.alt_sc; o.reg = r.reg; o.n_cigar = r.n_cigar; o.n_md = nmd; o.pos = r.pos; o.pnext = r.pnext; o.tlen = r.tlen;
+        o.alt_sc = r.alt_sc; o.is_alt = r.is_alt; o.n_mc = r.n_mc; o.reg = r.reg; o.n_cigar = r.n_cigar; o.n_md = nmd; o.pos = r.pos; o.pnext = r.pnext; o.tlen = r.tlen;
         o.cigar_off = c.ops; o.md_off = c.md;
-        for (int j = 0; j < r.n_cigar; ++j) ops[c.ops + j] = rops[j];
+        for (int j = 0; j < nops; ++j) ops[c.ops + j] = rops[j];
         if (r.n_cigar) { for (int j = 0; j < nmd; ++j) md[c.md + j] = rmd[j]; } else md[c.md] = 0;
-        recs[c.recs++] = o; c.ops += r.n_cigar; c.md += nmd;
+        recs[c.recs++] = o; c.ops += nops; c.md += nmd;
     };
     auto emit_xa = [&](int i, int reg, const SamAln &e) {
         if (c.xa >= cp.xa_cap || c.ops + e.n_cigar > cp.out_ops) { overflow |= BM2_OVF_RECORDS; return; }

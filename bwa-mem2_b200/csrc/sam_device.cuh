@@ -41,6 +41,8 @@ struct SamRec {                    // the columns of one SAM line (bm2o_samrec w
     int flag, rid, mapq, rnext, nm, score, sub, n_cigar, n_md;
     int reg;                      // SamAln::reg
     int alt_sc;                   // > 0: the pa tag is score / alt_sc (src/bwamem.cpp:1713-1714; not printed on 0x100 records)
+    int is_alt;                   // the record's region lies on an ALT contig
+    int n_mc;                     // operations of the MC tag (the mate's CIGAR as this line prints it), stored after the record's own in ops[]
     int64_t pos, pnext, tlen;
 };
 
@@ -290,7 +292,7 @@ BM2_HD int sam_rlen_d(const SamAln &a) { int l = 0; for (int k = 0; k < a.n_ciga
 BM2_HD int sam_raw_mapq_d(int diff, int a) { return (int) (6.02 * diff / a + .499); }
 
 // The columns of mem_aln2sam (src/bwamem.cpp:1592-1640) for p (the which-th record of its read) with mate m (may be null).  The printed
-// CIGAR letters are returned in ops[0..rec->n_cigar) as len << 4 | index into "MIDSH".
+// CIGAR letters are returned in ops[0..rec->n_cigar) as len << 4 | index into "MIDSH", followed by the rec->n_mc operations of the MC tag.
 BM2_HD void sam_aln2rec_d(const SamParams &prm, const SamAln &p_, int which, const SamAln *m_, SamRec *r, uint32_t *ops)
 {
     int flag = p_.flag, rid = p_.rid, is_rev = p_.is_rev, n_cigar = p_.n_cigar; int64_t pos = p_.pos;
@@ -325,7 +327,14 @@ BM2_HD void sam_aln2rec_d(const SamParams &prm, const SamAln &p_, int which, con
         }
     }
     r->nm = n_cigar ? p_.nm : 0; r->n_md = n_cigar ? p_.n_md : 1;
-    r->score = p_.score; r->sub = p_.sub; r->reg = p_.reg; r->alt_sc = p_.alt_sc;
+    r->score = p_.score; r->sub = p_.sub; r->reg = p_.reg; r->alt_sc = p_.alt_sc; r->is_alt = p_.is_alt;
+    r->n_mc = 0;                                              // MC:Z: = add_cigar(opt, m, str, which) (src/bwamem.cpp:1686, :1579-1590)
+    if (m_ && m_ncig)
+        for (int k = 0; k < m_ncig; ++k) {
+            int c = m_->cigar[k] & 0xf;
+            if (!(prm.flag & 0x200) && !m_->is_alt && (c == 3 || c == 4)) c = which ? 4 : 3;
+            ops[r->n_cigar + r->n_mc++] = (m_->cigar[k] >> 4) << 4 | (uint32_t) c;
+        }
 }
 
 // mem_reorder_primary5 (src/bwamem.cpp:1496-1518), option -5: the primary with the smallest query start becomes record 0
@@ -381,7 +390,7 @@ struct SamScratch {
     int32_t *he; CigarZ zz;        // global alignment: 2 * (max read length + 1) ints; backtrack cells
     SamAln *aa[2]; int aa_cap;     // per read: records to print (regions + 2)
     uint32_t *cig_pool; long long cig_cap; char *md_pool; long long md_cap;      // storage of the records' CIGAR / MD
-    uint32_t *ops;                 // printed CIGAR of one record (longest record)
+    uint32_t *ops;                 // printed CIGAR of one record + its MC tag (longest record of each read)
 };
 
 struct SamPool { uint32_t *c; long long cc, cu; char *m; long long mc, mu; };

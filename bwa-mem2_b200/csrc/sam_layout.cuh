@@ -52,7 +52,7 @@ struct SamPairCaps {
     int aa_cap;                  // records of one read: its regions + 2 (mem_reg2sam prints each region at most once, + the ALT / unmapped one)
     long long zz_cells;          // backtrack matrix of one global alignment (sam_reg_zcells_d; rescued regions: l_query x window)
     long long pool_ops, pool_md; // CIGAR / MD storage of all records of the pair + one XA entry at a time (sam_alloc_d's sizes)
-    int ops_cap;                 // printed CIGAR of one record
+    int ops_cap;                 // printed CIGAR of one record + its MC tag
     int recs_cap, xa_cap;        // output: records of the pair, XA entries of the pair (one per region at most)
     long long out_ops, out_md;   // output: printed operations of records and XA entries, MD bytes
     size_t scratch_bytes;        // arena of the pair (pieces aligned to 16 bytes), outputs not included
@@ -91,8 +91,10 @@ BM2_HD SamPairCaps sam_pair_caps_d(const SamPairShape &s, const MatePes &pes, in
         c.pool_ops += ops; c.pool_md += md;
         // output: records as above; XA entries: each region at most once more
         c.out_ops += 2 * ops; c.out_md += md;
-        if (lq + widest + 4 > c.ops_cap) c.ops_cap = (int) (lq + widest + 4);
+        c.ops_cap += (int) (lq + widest + 4);                                 // a record's own CIGAR + the mate's (MC tag)
     }
+    // output: every record of read i also carries the MC operations (the CIGAR of the mate's record)
+    for (int i = 0; i < 2; ++i) c.out_ops += (long long) (c.acap[i] + 4) * (s.l_seq[!i] + c.rlen_cap[!i] + 4);
     c.recs_cap = c.acap[0] + c.acap[1] + 4;
     c.xa_cap = c.acap[0] + c.acap[1];
     size_t b = 0;

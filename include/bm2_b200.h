@@ -276,7 +276,9 @@ int bm2_ksw_align2(bm2_ctx *ctx, const uint8_t *seqs, int64_t n_seq_bytes, const
  * QNAME, SEQ / QUAL (trimmed by the hard clips of the record's CIGAR), the tag syntax, SA and MC (columns of the read's other
  * records / the mate's record), -C / -R / -V constants.
  * regs / read_off: the output of bm2_seed_chain_extend for the same batch (reads 2i, 2i+1 are mates); pes: bm2_pestat or the
- * -I values.  One bm2_sam_rec per SAM line, in output order (pair by pair, read 0 then read 1). */
+ * -I values.  One bm2_sam_rec per SAM line, in output order (pair by pair, read 0 then read 1).
+ * A record is a true secondary (SEQ / QUAL '*', no SA / pa tags) iff (flag & 0x100) && sub < 0; a -M supplementary has 0x100 and sub >= 0.
+ * tests/sam_text.py formats the reference's text from these records byte for byte (SEQ / QUAL with hard clips, NM MD MC AS XS SA pa XA). */
 typedef struct bm2_sam_rec {
     int32_t read;              /* read of the batch the line belongs to                                        */
     int32_t flag;              /* FLAG as printed                                                              */
@@ -286,6 +288,8 @@ typedef struct bm2_sam_rec {
     int32_t alt_sc;            /* > 0 and not a 0x100 record: pa:f: = score / alt_sc                           */
     int32_t reg;               /* its XA tag = the bm2_sam_xa entries of this read with the same reg; -1: none */
     int32_t n_cigar, n_md;     /* printed operations (len << 4 | index into "MIDSH"); MD bytes incl. the NUL   */
+    int32_t is_alt;            /* the hit lies on an ALT contig                                                */
+    int32_t n_mc;              /* MC tag: the n_mc operations after the record's own (cigar_off + n_cigar)     */
     int64_t pos, pnext, tlen;  /* as printed (1-based; 0 where the column is 0)                                */
     int64_t cigar_off, md_off; /* into bm2_sam_result::cigar / ::md                                            */
 } bm2_sam_rec;

@@ -98,7 +98,7 @@ def main():
             st = (C.c_longlong * 4)(); L.emul_sam_stage_stats(st)
         finally:
             L.emul_sam_set_staged(0)
-        assert all(np.array_equal(x, y) for x, y in zip(em2, em[:3])), "staged rescue differs"
+        assert all(np.array_equal(x, y) for x, y in zip(em2[:3], em[:3])), "staged rescue differs"
         sam_dev += f"; staged rescue identical (batch {st[0]}, used {st[1]}, computed in place {st[2]}, window moved {st[3]})"
         al, oc, om = ts.oracle_sam_se(capi, idx, opt, codes, offs, regs, ro)                      # every read as a single-end read
         assert ts.rec_fields(*ts.emul_sam_se(capi, idx, opt, codes, offs, regs, ro), names) == ts.sam_fields(al, oc, om, names, soft_clip_all=bool(opt.flag & 0x200)), "single-end differs"

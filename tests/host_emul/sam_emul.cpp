@@ -122,11 +122,11 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
             bm2o_samrec o; memset(&o, 0, sizeof(o));
             o.read = 2 * pr + i; o.flag = r.flag; o.rid = r.rid; o.mapq = r.mapq; o.rnext = r.rnext; o.tlen_valid = 1; o.nm = r.nm; o.score = r.score; o.sub = r.sub; o._pad = r.alt_sc;        /* _pad carries alt_sc (pa tag) in this test build */
             o.n_cigar = r.n_cigar; o.pos = r.pos; o.pnext = r.pnext; o.tlen = r.tlen; o.cigar_off = (int64_t) ops_all.size(); o.md_off = (int64_t) md_all.size();
-            ops_all.insert(ops_all.end(), ops, ops + r.n_cigar);
+            ops_all.insert(ops_all.end(), ops, ops + r.n_cigar + r.n_mc);          // the MC operations follow the record's own
             if (r.n_cigar) md_all += md;
             md_all.push_back('\0');
             o.n_md = (int32_t) (md_all.size() - (size_t) o.md_off);
-            out.push_back(o); rec_reg.push_back(r.reg); ++pair_recs; pair_ops += r.n_cigar; pair_md += o.n_md;
+            out.push_back(o); rec_reg.push_back(r.reg); rec_reg.push_back(r.is_alt); rec_reg.push_back(r.n_mc); ++pair_recs; pair_ops += r.n_cigar + r.n_mc; pair_md += o.n_md;
         };
         auto emit_xa = [&](int i, int reg, const SamAln &t) {
             EmXa e; e.read = 2 * pr + i; e.reg = reg; e.rid = t.rid; e.is_rev = t.is_rev; e.nm = t.nm; e.n_cigar = t.n_cigar; e.pos = t.pos; e.cigar_off = (int64_t) xa_ops.size();
@@ -141,7 +141,7 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
     *recs_out = (bm2o_samrec *) malloc(sizeof(bm2o_samrec) * (nr + 1)); memcpy(*recs_out, out.data(), sizeof(bm2o_samrec) * nr);
     *cigar_out = (uint32_t *) malloc(4 * (ops_all.size() + 1)); memcpy(*cigar_out, ops_all.data(), 4 * ops_all.size());
     *md_out = (char *) malloc(md_all.size() + 1); memcpy(*md_out, md_all.data(), md_all.size());
-    *rec_reg_out = (int32_t *) malloc(4 * (nr + 1)); memcpy(*rec_reg_out, rec_reg.data(), 4 * nr);
+    *rec_reg_out = (int32_t *) malloc(12 * (nr + 1)); memcpy(*rec_reg_out, rec_reg.data(), 12 * nr);        /* (reg, is_alt, n_mc) per record */
     *xa_out = (EmXa *) malloc(sizeof(EmXa) * (xa.size() + 1)); memcpy(*xa_out, xa.data(), sizeof(EmXa) * xa.size());
     *xa_cigar_out = (uint32_t *) malloc(4 * (xa_ops.size() + 1)); memcpy(*xa_cigar_out, xa_ops.data(), 4 * xa_ops.size());
     *n_xa_out = (int64_t) xa.size(); *n_xa_ops_out = (int64_t) xa_ops.size();
@@ -185,11 +185,11 @@ extern "C" int emul_sam_se(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
             bm2o_samrec o; memset(&o, 0, sizeof(o));
             o.read = r; o.flag = q.flag; o.rid = q.rid; o.mapq = q.mapq; o.rnext = q.rnext; o.tlen_valid = 1; o.nm = q.nm; o.score = q.score; o.sub = q.sub; o._pad = q.alt_sc;
             o.n_cigar = q.n_cigar; o.pos = q.pos; o.pnext = q.pnext; o.tlen = q.tlen; o.cigar_off = (int64_t) ops_all.size(); o.md_off = (int64_t) md_all.size();
-            ops_all.insert(ops_all.end(), ops, ops + q.n_cigar);
+            ops_all.insert(ops_all.end(), ops, ops + q.n_cigar + q.n_mc);
             if (q.n_cigar) md_all += md;
             md_all.push_back('\0');
             o.n_md = (int32_t) (md_all.size() - (size_t) o.md_off);
-            out.push_back(o); rec_reg.push_back(q.reg); ++n_rec; n_o += q.n_cigar; n_m += o.n_md;
+            out.push_back(o); rec_reg.push_back(q.reg); rec_reg.push_back(q.is_alt); rec_reg.push_back(q.n_mc); ++n_rec; n_o += q.n_cigar + q.n_mc; n_m += o.n_md;
         };
         auto emit_xa = [&](int, int reg, const SamAln &t) {
             EmXa e; e.read = r; e.reg = reg; e.rid = t.rid; e.is_rev = t.is_rev; e.nm = t.nm; e.n_cigar = t.n_cigar; e.pos = t.pos; e.cigar_off = (int64_t) xa_ops.size();
@@ -204,7 +204,7 @@ extern "C" int emul_sam_se(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
     *recs_out = (bm2o_samrec *) malloc(sizeof(bm2o_samrec) * (nr + 1)); memcpy(*recs_out, out.data(), sizeof(bm2o_samrec) * nr);
     *cigar_out = (uint32_t *) malloc(4 * (ops_all.size() + 1)); memcpy(*cigar_out, ops_all.data(), 4 * ops_all.size());
     *md_out = (char *) malloc(md_all.size() + 1); memcpy(*md_out, md_all.data(), md_all.size());
-    *rec_reg_out = (int32_t *) malloc(4 * (nr + 1)); memcpy(*rec_reg_out, rec_reg.data(), 4 * nr);
+    *rec_reg_out = (int32_t *) malloc(12 * (nr + 1)); memcpy(*rec_reg_out, rec_reg.data(), 12 * nr);        /* (reg, is_alt, n_mc) per record */
     *xa_out = (EmXa *) malloc(sizeof(EmXa) * (xa.size() + 1)); memcpy(*xa_out, xa.data(), sizeof(EmXa) * xa.size());
     *xa_cigar_out = (uint32_t *) malloc(4 * (xa_ops.size() + 1)); memcpy(*xa_cigar_out, xa_ops.data(), 4 * xa_ops.size());
     *n_xa_out = (int64_t) xa.size(); *n_xa_ops_out = (int64_t) xa_ops.size();

@@ -98,8 +98,8 @@ def test_paired_end_sam_matches_reference_golden(c0, golden_dir):
     assert (flags & 0x2).sum() > 800 and (flags & 0x800).sum() >= 3 and (flags & 0x4).sum() >= 5      # proper pairs, supplementary, unmapped
 
 
-@pytest.mark.parametrize("args", [["-a"], ["-M"], ["-P"], ["-S"], ["-Y", "-T", "40"], ["-U", "9"], ["-5"], ["-q"], ["-5", "-P", "-a"]],
-                         ids=["all", "no_multi", "no_pairing", "no_rescue", "softclip_T40", "U9", "primary5", "keep_supp_mapq", "primary5_P_a"])
+@pytest.mark.parametrize("args", [["-a"], ["-M"], ["-P"], ["-S"], ["-Y", "-T", "40"], ["-U", "9"], ["-5"], ["-q"], ["-5", "-P", "-a"], ["-a", "-M"]],
+                         ids=["all", "no_multi", "no_pairing", "no_rescue", "softclip_T40", "U9", "primary5", "keep_supp_mapq", "primary5_P_a", "all_no_multi"])
 def test_paired_end_sam_matches_the_live_reference(c0, golden_dir, args):
     if cu.refbin() is None:
         pytest.skip("oracle/_ref not built")
@@ -121,6 +121,13 @@ def test_paired_end_sam_matches_the_live_reference(c0, golden_dir, args):
     lh, as_ = _pestat(capi, idx, opt, reads, regs, ro)
     recs, cig, md = oracle_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_)
     _compare(fields(recs, cig, md, names), parse_sam(open(os.path.join(work, "o.sam"))))
+    # the device logic's records, formatted by tests/sam_text.py, against the reference's text (from FLAG on)
+    import sam_text
+    e_recs, e_cig, e_md, e_xa, e_aux = emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_, xa_names=names)
+    want = [ln.rstrip("\n").split("\t", 1)[1] for ln in open(os.path.join(work, "o.sam")) if not ln.startswith("@")]
+    got = sam_text.format_lines(e_recs, e_cig, e_md, e_xa, names, codes, offs, is_alt=e_aux[:, 1], n_mc=e_aux[:, 2])
+    bad = [i for i in range(len(want)) if got[i] != want[i]]
+    assert len(got) == len(want) and not bad, (len(bad), [(got[i], want[i]) for i in bad[:2]])
 
 
 def oracle_sam_text(capi, idx, opt, codes, offs, regs, ro, lh, as_, names, qual_char="I"):
@@ -212,8 +219,12 @@ def test_sam_text_with_xa_and_alt_tags_matches_the_live_reference(pkg):
     assert not bad, (len(bad), [(got[i], want[i]) for i in bad[:2]])
     assert sum("XA:Z:" in w for w in want) > 30 and sum("pa:f:" in w for w in want) > 5, (sum("XA:Z:" in w for w in want), sum("pa:f:" in w for w in want))
     # the device logic's XA entries (sam_gen_alt_d) against the reference's XA tags, record by record
-    e_recs, e_cig, e_md, e_xa = emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_, xa_names=names)
+    e_recs, e_cig, e_md, e_xa, e_aux = emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_, xa_names=names)
     assert e_xa == xa_of_lines(want)
+    import sam_text                                                  # ... and the whole text from the records: SEQ / QUAL, MC, SA, pa included
+    txt = sam_text.format_lines(e_recs, e_cig, e_md, e_xa, names, codes, offs, is_alt=e_aux[:, 1], n_mc=e_aux[:, 2])
+    bad = [i for i in range(len(want)) if txt[i] != want[i]]
+    assert not bad, (len(bad), [(txt[i], want[i]) for i in bad[:2]])
     pa_want = [([f for f in w.split("\t") if f.startswith("pa:f:")] or [""])[0] for w in want]
     pa_got = [("pa:f:%.3f" % (float(r["score"]) / float(r["_pad"]))) if r["_pad"] > 0 and not (r["flag"] & 0x100) else "" for r in e_recs]
     assert pa_got == pa_want                                         # SamRec::alt_sc
@@ -259,7 +270,8 @@ def emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_, xa_names=None):
         dt = np.dtype(dt)
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(n, 1) * dt.itemsize,))[:n * dt.itemsize].view(dt).copy()
     out = arr(rc_, nr.value, REC_DT), arr(cg, no.value, "<u4"), arr(md, nm.value, "u1")
-    rec_reg = arr(rr, nr.value, "<i4"); xas = arr(xa, nxa.value, XA_DT); xops = arr(xc, nxc.value, "<u4")
+    aux = arr(rr, 3 * nr.value, "<i4").reshape(-1, 3); xas = arr(xa, nxa.value, XA_DT); xops = arr(xc, nxc.value, "<u4")      # (reg, is_alt, n_mc) per record
+    rec_reg = aux[:, 0]
     for p in (rc_, cg, md, rr, xa, xc):
         ol.lib().bm2o_free(p)
     if xa_names is None:
@@ -270,7 +282,7 @@ def emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_, xa_names=None):
         txt = f"{xa_names[e['rid']]},{'+-'[e['is_rev']]}{e['pos'] + 1}," + "".join(f"{v >> 4}{'MIDSHN'[v & 15]}" for v in ops) + f",{e['nm']};"
         by_key.setdefault((int(e["read"]), int(e["reg"])), []).append(txt)
     strings = ["".join(by_key.get((int(r["read"]), int(g)), [])) if g >= 0 else "" for r, g in zip(out[0], rec_reg)]
-    return out + (strings,)
+    return out + (strings, aux)
 
 
 def xa_of_lines(lines):
@@ -300,6 +312,22 @@ def test_staged_rescue_equals_the_per_pair_block(c0):
     jobs, used, in_place, moved = [int(v) for v in st]
     assert jobs > 50 and used > 50 and in_place == 0 and moved == 0, (jobs, used, in_place, moved)
     assert used <= jobs
+
+
+def test_records_suffice_for_the_reference_text(c0, golden_dir):
+    """tests/golden/c0.sam byte for byte (from FLAG on) out of the device logic's records: the columns, SEQ / QUAL with hard clips, NM MD MC AS XS SA XA."""
+    import sam_text
+    capi, idx, reads, codes, offs, names = c0
+    opt = capi.default_opt(); opt.flag |= 0x2
+    regs, ro, _, rc = ol.seed_chain_extend(idx, opt, codes, offs)
+    lh, as_ = _pestat(capi, idx, opt, reads, regs, ro)
+    recs, cig, md, xa, aux = emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_, xa_names=names)
+    want = [ln.rstrip("\n").split("\t", 1)[1] for ln in open(golden_dir + "/c0.sam") if not ln.startswith("@")]
+    got = sam_text.format_lines(recs, cig, md, xa, names, codes, offs, is_alt=aux[:, 1], n_mc=aux[:, 2])
+    assert len(got) == len(want)
+    bad = [i for i in range(len(got)) if got[i] != want[i]]
+    assert not bad, (len(bad), [(got[i], want[i]) for i in bad[:2]])
+    assert sum("MC:Z:" in w for w in want) > 900 and sum("SA:Z:" in w for w in want) >= 6
 
 
 @pytest.mark.parametrize("flags", [0, 0x8, 0x10, 0x4, 0x20, 0x200, 0x1800, 0x1000, 0x1808], ids=["default", "all", "no_multi", "no_pairing", "no_rescue", "softclip", "primary5", "keep_supp_mapq", "primary5_all"])

@@ -44,6 +44,11 @@ def test_sam_records_match_reference_golden(c0, golden_dir):
     lines = [ln.rstrip("\n") for ln in open(golden_dir + "/c0.sam") if not ln.startswith("@")]
     tp._compare(tp.fields(recs, cig, md, names), tp.parse_sam(lines))
     assert _xa_strings(recs, xa, cig, names) == tp.xa_of_lines(lines)
+    import sam_text                                                  # the whole text (SEQ / QUAL, MC, SA ...) from the records
+    txt = sam_text.format_lines(recs, cig, md, _xa_strings(recs, xa, cig, names), names, codes, offs)
+    want = [ln.split("\t", 1)[1] for ln in lines]
+    bad = [i for i in range(len(want)) if txt[i] != want[i]]
+    assert not bad, (len(bad), [(txt[i], want[i]) for i in bad[:2]])
     pa_want = [([f for f in w.split("\t") if f.startswith("pa:f:")] or [""])[0] for w in lines]
     pa_got = [("pa:f:%.3f" % (float(r["score"]) / float(r["alt_sc"]))) if r["alt_sc"] > 0 and not (r["flag"] & 0x100) else "" for r in recs]
     assert pa_got == pa_want
