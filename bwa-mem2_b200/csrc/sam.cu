@@ -4,7 +4,8 @@
 // per-pair logic is sam_pe_pair_d / mate_rescue_pair_d (sam_device.cuh, mate_device.cuh: checked on the host against the oracle and
 // the unmodified reference), one pair per thread; the scratch of a pair is an arena whose capacities follow from the pair's regions
 // and the insert-size statistics (sam_layout.cuh); the records, XA entries, operations and MD bytes go to worst-case stripes and are
-// compacted by a gather.  Pairs are processed in waves sized by a scratch budget.  The libm values the stage needs (log of small
+// compacted by a gather.  Pairs are processed in waves sized by a scratch budget (worst-case capacities: ≈0.5 MB per typical pair, most of it the MD
+// and CIGAR pools - optimistic pools with a second wave for the pairs that overflow are the obvious next step).  The libm values the stage needs (log of small
 // integers, the insert-size term of mem_pair) are tabulated on the host with the host's libm, as the reference computes them.
 //
 // STATUS: first version, parity-green on a B200 (tests/test_zz_sam_gpu.py, profiles/r1s_zz_tests_gpu.log), not yet timed or profiled.
@@ -202,10 +203,10 @@ int run_sam(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs,
             }
             sam_shape_read_d(sh, i, (int) ls, regs + read_off[r], (int) nn, o.w);
         }
-        desc[(size_t) pr].caps = sam_pair_caps_d(sh, pes, o.max_matesw, rescue != 0);
+        desc[(size_t) pr].caps = sam_pair_caps_d(sh, pes, o.max_matesw, rescue != 0, o.a, o.e_del);
         desc[(size_t) pr].pair = pr;
     }
-    const size_t budget = (size_t) 12 << 30;                // scratch + stripes of one wave
+    const size_t budget = (size_t) 32 << 30;                // scratch + stripes of one wave (≈0.5 MB per pair of 151-bp reads with 8 regions each)
     size_t used[4] = { 0, 0, 0, 0 };                        // recs, xa, ops, md of the batch so far
     for (int w0 = 0; w0 < n_pairs_all;) {
         size_t arena = 0; int64_t nrec = 0, nxa = 0, nops = 0, nmd = 0; int w1 = w0;

@@ -40,7 +40,7 @@ BM2_HD void sam_shape_read_d(SamPairShape &s, int i, int l_seq, const bm2_alnreg
 }
 
 struct SamPairCaps {
-    int acap[2];                 // regions of read i after rescue: every mem_matesw call adds at most one per orientation (:233-238),
+    int acap[2];                 // regions of read i after rescue: every mem_matesw call adds at most one per orientation with statistics (:233-238),
                                  //   and at most min(n[!i], max_matesw) anchors of the other read call it (:398-407)
     int bcap[2];                 // anchor copies: n[i] + 1
     int max_l;                   // longer read
@@ -60,20 +60,29 @@ struct SamPairCaps {
 
 BM2_HD size_t sam_align16_d(size_t v) { return (v + 15) & ~(size_t) 15; }
 
-BM2_HD SamPairCaps sam_pair_caps_d(const SamPairShape &s, const MatePes &pes, int max_matesw, bool rescue)
+// a / e_del: match score and deletion extension penalty (mem_opt_t): a local alignment of positive score over l query bases spans fewer than
+// l + l * a / e_del reference bases (every deleted base costs at least e_del, the matches earn at most l * a).
+BM2_HD SamPairCaps sam_pair_caps_d(const SamPairShape &s, const MatePes &pes, int max_matesw, bool rescue, int a, int e_del)
 {
     SamPairCaps c;
     c.max_l = s.l_seq[0] > s.l_seq[1] ? s.l_seq[0] : s.l_seq[1];
     c.tcap = 16;
-    long long resc[2] = { 0, 0 };                                       // rescued regions read i can receive
+    long long resc[2] = { 0, 0 }, rlen_resc[2] = { 0, 0 };               // rescued regions read i can receive, and how wide one can be
+    int n_dirs = 0;
+    for (int r = 0; r < 4; ++r) n_dirs += pes.failed[r] ? 0 : 1;          // a call aligns at most one window per orientation that has statistics
     for (int i = 0; i < 2; ++i) {
         const int calls = !rescue ? 0 : (s.n[!i] < max_matesw ? s.n[!i] : max_matesw);
-        resc[i] = 4LL * calls;
+        resc[i] = (long long) n_dirs * calls;
         c.acap[i] = s.n[i] + (int) resc[i] + 4;
         c.bcap[i] = s.n[i] + 1;
         const int win = mate_window_max_d(pes, s.l_seq[i]) + 16;          // read i is the mate that gets aligned into the window
         c.rlen_cap[i] = s.max_rlen[i];
-        if (calls > 0) { if (win > c.tcap) c.tcap = win; if (win > c.rlen_cap[i]) c.rlen_cap[i] = win; }
+        if (resc[i] > 0) {
+            if (win > c.tcap) c.tcap = win;
+            const long long span = (long long) s.l_seq[i] + (long long) s.l_seq[i] * a / (e_del > 0 ? e_del : 1) + 2;
+            rlen_resc[i] = span < win ? span : win;
+            if (rlen_resc[i] > c.rlen_cap[i]) c.rlen_cap[i] = rlen_resc[i];
+        }
     }
     c.kcap = c.tcap / 2 + 2;
     c.zi = (c.acap[0] > c.acap[1] ? c.acap[0] : c.acap[1]) + 4;
@@ -83,11 +92,11 @@ BM2_HD SamPairCaps sam_pair_caps_d(const SamPairShape &s, const MatePes &pes, in
     for (int i = 0; i < 2; ++i) {
         const long long lq = s.l_seq[i], widest = c.rlen_cap[i];
         if (s.max_zcells[i] + 16 > c.zz_cells) c.zz_cells = s.max_zcells[i] + 16;
-        if (resc[i] > 0 && lq * c.tcap + 16 > c.zz_cells) c.zz_cells = lq * c.tcap + 16;      // a rescued region: at most l_query columns, rows inside its window
+        if (resc[i] > 0 && lq * rlen_resc[i] + 16 > c.zz_cells) c.zz_cells = lq * rlen_resc[i] + 16;      // a rescued region: at most l_query columns
         // every region printed once (its own rlen), rescued ones bounded by the window, + h[i], the ALT record, the unmapped record, one XA entry
         const long long extra = 4;
-        const long long ops = s.n[i] * (lq + 4) + s.sum_rlen[i] + resc[i] * (lq + c.tcap + 4) + extra * (lq + widest + 4);
-        const long long md = s.n[i] * (2 * lq + 16) + 7 * s.sum_rlen[i] + resc[i] * (2 * lq + 7LL * c.tcap + 16) + extra * (2 * lq + 7 * widest + 16);
+        const long long ops = s.n[i] * (lq + 4) + s.sum_rlen[i] + resc[i] * (lq + rlen_resc[i] + 4) + extra * (lq + widest + 4);
+        const long long md = s.n[i] * (2 * lq + 16) + 7 * s.sum_rlen[i] + resc[i] * (2 * lq + 7 * rlen_resc[i] + 16) + extra * (2 * lq + 7 * widest + 16);
         c.pool_ops += ops; c.pool_md += md;
         // output: records as above; XA entries: each region at most once more
         c.out_ops += 2 * ops; c.out_md += md;

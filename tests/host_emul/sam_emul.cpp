@@ -17,9 +17,11 @@ extern "C" int emul_ksw_warp_align2(int32_t qlen, const uint8_t *query, int32_t 
 #include <map>
 #include <tuple>
 static int g_staged = 0;
-static long long g_stage_stats[4];            // jobs in the batch, looked up, computed in place (not in the batch), windows that differed
+static long long g_stage_stats[8];            // jobs in the batch, looked up, computed in place (not in the batch), windows that differed;
+                                              // [4..6]: arena bytes, output-stripe bytes, units (pairs) of the last call
 extern "C" void emul_sam_set_staged(int on) { g_staged = on; }
 extern "C" void emul_sam_stage_stats(long long *out) { for (int k = 0; k < 4; ++k) out[k] = g_stage_stats[k]; }
+extern "C" void emul_sam_layout_stats(long long *out) { for (int k = 0; k < 3; ++k) out[k] = g_stage_stats[4 + k]; }
 struct StagedJob { int64_t rb, re; KswRes res; };
 typedef std::map<std::tuple<int, int, int, int>, StagedJob> JobTable;      // (pair, anchor read, anchor, orientation)
 struct MateKswLookup {
@@ -68,7 +70,7 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
     int overflow = 0;
     int layout_bad = 0;
     JobTable jobs;
-    for (int k = 0; k < 4; ++k) g_stage_stats[k] = 0;
+    for (int k = 0; k < 8; ++k) g_stage_stats[k] = 0;
     if (g_staged && !(opt->flag & 0x20))
         for (int pr = 0; pr < reads->n_reads >> 1; ++pr) {
             const bm2_alnreg_t *a2[2]; int n2[2], l2[2]; const uint8_t *s2[2];
@@ -103,7 +105,9 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
             sam_shape_read_d(shape, i, l_seq[i], regs + read_off[r], n[i], opt->w);
         }
         // the arena a kernel would get: capacities from sam_layout.cuh, guard words between the pieces
-        const SamPairCaps caps = sam_pair_caps_d(shape, pes, opt->max_matesw, !(opt->flag & 0x20));
+        const SamPairCaps caps = sam_pair_caps_d(shape, pes, opt->max_matesw, !(opt->flag & 0x20), opt->a, opt->e_del);
+        g_stage_stats[4] += (long long) caps.scratch_bytes; g_stage_stats[6] += 1;
+        g_stage_stats[5] += (long long) caps.recs_cap * 96 + (long long) caps.xa_cap * 40 + caps.out_ops * 4 + caps.out_md;
         std::vector<uint8_t> arena(caps.scratch_bytes + 64);
         SamArena ar;
         sam_arena_carve_d(arena.data(), caps, 1, &ar);
@@ -175,7 +179,7 @@ extern "C" int emul_sam_se(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
         SamPairShape shape;
         sam_shape_read_d(shape, 0, l_seq, regs + read_off[r], n, opt->w);
         sam_shape_read_d(shape, 1, 0, regs, 0, opt->w);
-        const SamPairCaps caps = sam_pair_caps_d(shape, pes, opt->max_matesw, false);
+        const SamPairCaps caps = sam_pair_caps_d(shape, pes, opt->max_matesw, false, opt->a, opt->e_del);
         std::vector<uint8_t> arena(caps.scratch_bytes + 64);
         SamArena ar;
         sam_arena_carve_d(arena.data(), caps, 1, &ar);
