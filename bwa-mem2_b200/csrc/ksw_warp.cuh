@@ -102,14 +102,16 @@ BM2_HD int ksw_lane_phase_b_d(const KswShape &s, const KswSummary &in, KswLane &
     return rowmax;
 }
 
-// row bookkeeping shared by both drivers (every lane can run it redundantly; only lane 0's list writes matter)
-struct KswRowState { int gmax, te, n_b; bool stop; };
-BM2_HD void ksw_row_end_d(const KswShape &s, int i, int rowmax, int minsc, int endsc, KswRowState &st, int32_t *bsc, int32_t *bpos, int bcap, int *overflow, bool *took) {
+// row bookkeeping shared by both drivers.  Every lane keeps the same row state; the last list entry lives in the state (registers), so no lane
+// reads the list while another may be writing it, and only the writer lane (lane 0 on the device) stores.
+struct KswRowState { int gmax, te, n_b, last_sc, last_pos; bool stop; };
+BM2_HD void ksw_row_end_d(const KswShape &s, int i, int rowmax, int minsc, int endsc, KswRowState &st, int32_t *bsc, int32_t *bpos, int bcap, int *overflow, bool *took,
+                          bool writer) {
     *took = false;
     if (rowmax >= minsc) {
-        if (st.n_b == 0 || bpos[st.n_b - 1] + 1 != i) {
-            if (st.n_b < bcap) { bsc[st.n_b] = rowmax; bpos[st.n_b] = i; ++st.n_b; } else *overflow |= 32;
-        } else if (bsc[st.n_b - 1] < rowmax) { bsc[st.n_b - 1] = rowmax; bpos[st.n_b - 1] = i; }
+        if (st.n_b == 0 || st.last_pos + 1 != i) {
+            if (st.n_b < bcap) { if (writer) { bsc[st.n_b] = rowmax; bpos[st.n_b] = i; } ++st.n_b; st.last_sc = rowmax; st.last_pos = i; } else *overflow |= 32;
+        } else if (st.last_sc < rowmax) { if (writer) { bsc[st.n_b - 1] = rowmax; bpos[st.n_b - 1] = i; } st.last_sc = rowmax; st.last_pos = i; }
     }
     if (rowmax > st.gmax) {
         st.gmax = rowmax; st.te = i; *took = true;
@@ -132,7 +134,7 @@ __device__ inline KswRes ksw_pass_warp_d(int size, int qlen, const uint8_t *quer
     const int minsc = (xtra & BM2_KSW_XSUBO) ? xtra & 0xffff : 0x10000, endsc = (xtra & BM2_KSW_XSTOP) ? xtra & 0xffff : 0x10000;
     KswLane L;
     ksw_lane_init_d(s, lane, query, qstride, L);
-    KswRowState st; st.gmax = 0; st.te = -1; st.n_b = 0; st.stop = false;
+    KswRowState st; st.gmax = 0; st.te = -1; st.n_b = 0; st.last_sc = 0; st.last_pos = -2; st.stop = false;
     int ov = 0;
     for (int i = 0; i < tlen && !st.stop; ++i) {
         const int8_t *ma = mat + (int) target[i <= rev_upto ? rev_upto - i : i] * 5;
@@ -152,8 +154,8 @@ __device__ inline KswRes ksw_pass_warp_d(int size, int qlen, const uint8_t *quer
         if (lane == 0) { in.v_seg = 0; in.v_full = 0; }
         int rowmax = ksw_lane_phase_b_d(s, in, L);
         for (int d = 16; d > 0; d >>= 1) { const int o = __shfl_xor_sync(full, rowmax, d); if (o > rowmax) rowmax = o; }
-        bool took;                                                               // all lanes keep the same row state; their list writes coincide
-        ksw_row_end_d(s, i, rowmax, minsc, endsc, st, bsc, bpos, bcap, &ov, &took);
+        bool took;                                                               // all lanes keep the same row state; lane 0 writes the list
+        ksw_row_end_d(s, i, rowmax, minsc, endsc, st, bsc, bpos, bcap, &ov, &took, lane == 0);
         if (took) for (int c = 0; c < L.ncol; ++c) L.Hbest[c] = L.H[c];
         __syncwarp(full);
     }

@@ -14,7 +14,7 @@ static KswRes pass_lanes(int size, int qlen, const uint8_t *query, int qstride, 
     const int minsc = (xtra & BM2_KSW_XSUBO) ? xtra & 0xffff : 0x10000, endsc = (xtra & BM2_KSW_XSTOP) ? xtra & 0xffff : 0x10000;
     std::vector<KswLane> L(32);
     for (int l = 0; l < 32; ++l) ksw_lane_init_d(s, l, query, qstride, L[l]);
-    KswRowState st; st.gmax = 0; st.te = -1; st.n_b = 0; st.stop = false;
+    KswRowState st; st.gmax = 0; st.te = -1; st.n_b = 0; st.last_sc = 0; st.last_pos = -2; st.stop = false;
     for (int i = 0; i < tlen && !st.stop; ++i) {
         const int8_t *ma = mat + (int) target[(long long) i * tstride] * 5;
         int last[32];
@@ -26,7 +26,7 @@ static KswRes pass_lanes(int size, int qlen, const uint8_t *query, int qstride, 
         int rowmax = 0;
         for (int l = 0; l < 32; ++l) { const int r = ksw_lane_phase_b_d(s, in[l], L[l]); if (r > rowmax) rowmax = r; }
         bool took;
-        ksw_row_end_d(s, i, rowmax, minsc, endsc, st, bsc, bpos, bcap, overflow, &took);
+        ksw_row_end_d(s, i, rowmax, minsc, endsc, st, bsc, bpos, bcap, overflow, &took, true);
         if (took) for (int l = 0; l < 32; ++l) for (int c = 0; c < L[l].ncol; ++c) L[l].Hbest[c] = L[l].H[c];
     }
     KswRes r; r.score = size == 1 ? (st.gmax + s.shift < 255 ? st.gmax : 255) : st.gmax; r.te = st.te; r.qe = -1; r.score2 = -1; r.te2 = -1; r.tb = -1; r.qb = -1;
