@@ -286,6 +286,19 @@ class Context:
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * dt.itemsize,)).view(dt).copy() if n else np.zeros(0, dt)
         return arr(res.recs, res.n_recs, SAM_REC_DT), arr(res.xa, res.n_xa, SAM_XA_DT), arr(res.cigar, res.n_ops, "<u4"), arr(res.md, res.n_md, "u1")
 
+    def set_sam_staged(self, on: int):
+        """bm2_set_sam_staged: 1 = the rescue's local alignments as a batch (one window per warp) before the per-pair kernel, 0 = inside it."""
+        lib().bm2_set_sam_staged.argtypes = [C.c_void_p, C.c_int]
+        self._check(lib().bm2_set_sam_staged(self._ctx, int(on)), "bm2_set_sam_staged")
+
+    def last_sam_stats(self):
+        """bm2_last_sam_stats -> dict: device ms of the last bm2_sam_pe / bm2_sam_se call (jobs, ksw, pairs, gather) and the rescue counters."""
+        ms = (C.c_double * 4)(); cnt = (C.c_ulonglong * 6)()
+        lib().bm2_last_sam_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        self._check(lib().bm2_last_sam_stats(self._ctx, ms, cnt, 4, 6), "bm2_last_sam_stats")
+        return {"ms": {"jobs": ms[0], "ksw": ms[1], "pairs": ms[2], "gather_and_copies": ms[3]}, "staged": int(cnt[0]), "jobs": int(cnt[1]),
+                "looked_up": int(cnt[2]), "in_place": int(cnt[3]), "window_moved": int(cnt[4]), "waves": int(cnt[5])}
+
     def set_stream(self, cuda_stream_handle):
         lib().bm2_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         self._check(lib().bm2_set_stream(self._ctx, cuda_stream_handle), "bm2_set_stream")

@@ -49,6 +49,12 @@ struct bm2_ctx {
     // ALU-bound extension stage, so that at any time DIFFERENT kinds of stages overlap instead of four copies of the same
     std::mutex tok_smem, tok_bsw;
     cudaEvent_t ev_entry = nullptr;
+    // seam 4 (sam.cu): staged rescue switch (-1: the BM2_SAM_STAGED environment variable decides, default off), events around the stage's
+    // kernels, and the last call's times (jobs, window alignments, pairs, gather; ms summed over waves) and counters
+    int sam_staged = -1;
+    cudaEvent_t sam_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double sam_ms[4] = {0, 0, 0, 0};
+    unsigned long long sam_counts[6] = {0, 0, 0, 0, 0, 0};        // staged, jobs, looked up, computed in place, of those: window moved, waves
 
     int ensure(DevBuf &b, size_t bytes);
     int ensure_host(HostBuf &b, size_t bytes);

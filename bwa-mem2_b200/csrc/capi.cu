@@ -152,6 +152,19 @@ extern "C" int bm2_set_sub_batches(bm2_ctx *ctx, int k, int min_reads) {
     return 0;
 }
 
+extern "C" int bm2_set_sam_staged(bm2_ctx *ctx, int on) {
+    if (!ctx || on < -1 || on > 1) { if (ctx) bm2_set_error(ctx, "bm2_set_sam_staged: on in {-1, 0, 1}"); return 1; }
+    ctx->sam_staged = on;
+    return 0;
+}
+
+extern "C" int bm2_last_sam_stats(const bm2_ctx *ctx, double *ms, unsigned long long *counts, int n_ms, int n_counts) {
+    if (!ctx || !ms || !counts || n_ms < 4 || n_counts < 6) return 1;
+    for (int k = 0; k < 4; ++k) ms[k] = ctx->sam_ms[k];
+    for (int k = 0; k < 6; ++k) counts[k] = ctx->sam_counts[k];
+    return 0;
+}
+
 extern "C" void bm2_destroy(bm2_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
@@ -159,6 +172,7 @@ extern "C" void bm2_destroy(bm2_ctx *ctx) {
     for (bm2_ctx *l : ctx->lanes) bm2_destroy(l);
     ctx->lanes.clear();
     if (ctx->ev_entry) cudaEventDestroy(ctx->ev_entry);
+    for (cudaEvent_t ev : ctx->sam_ev) if (ev) cudaEventDestroy(ev);
     bm2_free_index(ctx);
     for (DevBuf *b : ctx->all_dev()) if (b->p) cudaFree(b->p);
     for (HostBuf *b : ctx->all_host()) if (b->p) cudaFreeHost(b->p);

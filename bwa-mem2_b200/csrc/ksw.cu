@@ -28,7 +28,7 @@ ksw_warp_kernel(KswMat mat, int o_del, int e_del, int o_ins, int e_ins, const ui
         const int bcap = (int) ((list_off[r + 1] - list_off[r]) >> 1);
         int32_t *bsc = lists + list_off[r], *bpos = bsc + bcap;
         int overflow = 0;
-        const KswRes a = ksw_align2_warp_d(q.qlen, seqs + q.qoff, q.tlen, seqs + q.toff, mat.m, o_del, e_del, o_ins, e_ins, q.xtra, bsc, bpos, bcap, &overflow);
+        const KswRes a = ksw_align2_warp_d(q.qlen, seqs + q.qoff, 1, 0, q.tlen, seqs + q.toff, mat.m, o_del, e_del, o_ins, e_ins, q.xtra, bsc, bpos, bcap, &overflow);
         if (lane == 0) {
             bm2_ksw_res o; o.score = a.score; o.te = a.te; o.qe = a.qe; o.score2 = a.score2; o.te2 = a.te2; o.tb = a.tb; o.qb = a.qb; o._pad = 0;
             res[r] = o;

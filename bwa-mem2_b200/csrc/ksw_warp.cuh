@@ -40,13 +40,16 @@ BM2_HD KswShape ksw_shape_d(int size, int qlen, const int8_t *mat, int o_del, in
     return s;
 }
 
-BM2_HD void ksw_lane_init_d(const KswShape &s, int lane, const uint8_t *query, int qstride, KswLane &L) {
+// comp: the query is read complemented (with qstride < 0 from its last base: the reverse complement, without a copy)
+BM2_HD void ksw_lane_init_d(const KswShape &s, int lane, const uint8_t *query, int qstride, KswLane &L, int comp = 0) {
     L.col0 = lane * s.C;
     L.ncol = L.col0 >= s.nlen ? 0 : (s.nlen - L.col0 < s.C ? s.nlen - L.col0 : s.C);
     for (int c = 0; c < L.ncol; ++c) {
         const int k = L.col0 + c;
         L.H[c] = 0; L.E[c] = 0; L.Hbest[c] = 0;
-        L.q[c] = k < s.qlen ? query[(long long) k * qstride] : 255;           // 255: padding column, substitution score 0
+        uint8_t b = k < s.qlen ? query[(long long) k * qstride] : 255;        // 255: padding column, substitution score 0
+        if (comp && b != 255) b = b < 4 ? 3 - b : 4;
+        L.q[c] = b;
     }
 }
 
@@ -123,7 +126,7 @@ BM2_HD void ksw_row_end_d(const KswShape &s, int i, int rowmax, int minsc, int e
 // One pass by a full warp (all 32 lanes call it with the same arguments).  bsc / bpos: the warp's score-2 list (global or shared).
 // rev_upto >= 0: the rows run over target[rev_upto], target[rev_upto - 1], ..., target[0], target[rev_upto + 1], ... (ksw_align2's second pass
 // reverses the prefix in place and still walks all tlen rows, src/ksw.cpp:366-371).
-__device__ inline KswRes ksw_pass_warp_d(int size, int qlen, const uint8_t *query, int qstride, int tlen, const uint8_t *target, int rev_upto, const int8_t *mat,
+__device__ inline KswRes ksw_pass_warp_d(int size, int qlen, const uint8_t *query, int qstride, int comp, int tlen, const uint8_t *target, int rev_upto, const int8_t *mat,
                                          int o_del, int e_del, int o_ins, int e_ins, int xtra, int32_t *bsc, int32_t *bpos, int bcap, int *overflow)
 {
     const unsigned full = 0xffffffffu;
@@ -133,7 +136,7 @@ __device__ inline KswRes ksw_pass_warp_d(int size, int qlen, const uint8_t *quer
     for (int a = 0; a < 25; ++a) if (mat[a] > qmax) qmax = mat[a];
     const int minsc = (xtra & BM2_KSW_XSUBO) ? xtra & 0xffff : 0x10000, endsc = (xtra & BM2_KSW_XSTOP) ? xtra & 0xffff : 0x10000;
     KswLane L;
-    ksw_lane_init_d(s, lane, query, qstride, L);
+    ksw_lane_init_d(s, lane, query, qstride, L, comp);
     KswRowState st; st.gmax = 0; st.te = -1; st.n_b = 0; st.last_sc = 0; st.last_pos = -2; st.stop = false;
     int ov = 0;
     for (int i = 0; i < tlen && !st.stop; ++i) {
@@ -184,15 +187,16 @@ __device__ inline KswRes ksw_pass_warp_d(int size, int qlen, const uint8_t *quer
 }
 
 // ksw_align2 (src/ksw.cpp:324-381) by a full warp: forward pass, then the reversed prefixes to find the start.
-__device__ inline KswRes ksw_align2_warp_d(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int o_del, int e_del, int o_ins,
+// The query is query[0], query[qstride], ... (complemented if comp): (ms + l_ms - 1, -1, 1) is the reverse complement of ms.
+__device__ inline KswRes ksw_align2_warp_d(int qlen, const uint8_t *query, int qstride, int comp, int tlen, const uint8_t *target, const int8_t *mat, int o_del, int e_del, int o_ins,
                                            int e_ins, int xtra, int32_t *bsc, int32_t *bpos, int bcap, int *overflow)
 {
     const int size = (xtra & BM2_KSW_XBYTE) ? 1 : 2;
-    KswRes r = ksw_pass_warp_d(size, qlen, query, 1, tlen, target, -1, mat, o_del, e_del, o_ins, e_ins, xtra, bsc, bpos, bcap, overflow);
+    KswRes r = ksw_pass_warp_d(size, qlen, query, qstride, comp, tlen, target, -1, mat, o_del, e_del, o_ins, e_ins, xtra, bsc, bpos, bcap, overflow);
     if ((xtra & BM2_KSW_XSTART) == 0 || ((xtra & BM2_KSW_XSUBO) && r.score < (xtra & 0xffff))) return r;
     int ov2 = 0;
     __syncwarp(0xffffffffu);
-    const KswRes rr = ksw_pass_warp_d(size, r.qe + 1, query + r.qe, -1, tlen, target, r.te, mat, o_del, e_del, o_ins, e_ins, BM2_KSW_XSTOP | r.score, bsc, bpos, bcap, &ov2);
+    const KswRes rr = ksw_pass_warp_d(size, r.qe + 1, query + (long long) r.qe * qstride, -qstride, comp, tlen, target, r.te, mat, o_del, e_del, o_ins, e_ins, BM2_KSW_XSTOP | r.score, bsc, bpos, bcap, &ov2);
     if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
     return r;
 }

@@ -10,9 +10,18 @@
 //
 // STATUS: first version, parity-green on a B200 (tests/test_zz_sam_gpu.py, profiles/r1s_zz_tests_gpu.log), not yet timed or profiled.
 // Correctness-first: thread-per-pair, no warp cooperation in the local alignment yet.
+//
+// Staged rescue (bm2_set_sam_staged / BM2_SAM_STAGED=1; off by default until it has run on a GPU): the local alignments of the rescue - the
+// bulk of the stage's arithmetic - leave the per-pair thread.  sam_jobs_kernel lists, from the regions BEFORE any rescue, the windows the
+// rescue block of every pair can ask for (mate_jobs_pair_d); sam_ksw_jobs_kernel aligns them one window per warp (ksw_warp.cuh, the mate read
+// in place, reverse-complemented by addressing); the per-pair thread then looks its alignments up (MateKswTable) and computes one itself
+// only when the table does not hold it (a window that moved, a job that was not listed).  Same records either way - the host
+// emulation of exactly this split is tests/test_oracle_sam_pe.py::test_staged_rescue_equals_the_per_pair_block.
 #include "bm2_common.cuh"
 #include "bm2_ctx.h"
 #include "sam_layout.cuh"
+#include "ksw_warp.cuh"
+#include "mate_stage.cuh"
 #include <vector>
 #include <cmath>
 #include <cstring>
@@ -21,6 +30,8 @@
 namespace {
 enum { SB_CODES = 64, SB_OFFS, SB_REGS, SB_REGOFF, SB_DESC, SB_ARENA, SB_RECS_W, SB_XA_W, SB_OPS_W, SB_MD_W, SB_CNT, SB_FINAL, SB_LOG, SB_TERM,
        SB_RECS, SB_XA, SB_OPS, SB_MD };
+enum { SJ_PAIRJOBS = 90, SJ_JOBS, SJ_RES, SJ_LISTS, SJ_STATS };          // staged rescue (84-89 belong to ksw.cu)
+static_assert(SJ_STATS < 96, "bm2_ctx::d[] too small");
 enum { SH_RECS = 16, SH_XA, SH_OPS, SH_MD, SH_CNT, SH_STAGE };
 static_assert(SB_MD < 96, "bm2_ctx::d[] too small");
 
@@ -33,11 +44,72 @@ struct PairDesc {                 // one pair of a wave
 struct PairCount { int64_t recs, xa, ops, md; int32_t overflow, _pad; };
 struct PairFinal { int64_t recs, xa, ops, md; };   // compact offsets (inside the wave)
 
+// ---- staged rescue (mate_stage.cuh) ---------------------------------------------------------------------------------------------
+typedef MateStats SamStats;
+struct KswMat25 { int8_t m[25]; };
+static_assert(sizeof(MateJobRes) == sizeof(bm2_ksw_res), "job results have the layout of bm2_ksw_res");
+
+// stage 1: one pair per thread; the jobs of a pair are consecutive in `jobs` (reserved with one atomicAdd: their order between pairs does
+// not matter, the pair finds them through pj[])
+__global__ void __launch_bounds__(128)
+sam_jobs_kernel(ContigView cv, MatePes pes, int min_seed_len, int pen_unpaired, int max_matesw, const int64_t *__restrict__ offs,
+                const bm2_alnreg_t *__restrict__ regs, const int64_t *__restrict__ reg_off, const PairDesc *__restrict__ desc, int n_pairs,
+                MateJob *jobs, unsigned int job_cap, PairJobs *pj, SamStats *stats)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pairs) return;
+    const int pair = desc[t].pair;
+    const bm2_alnreg_t *a[2]; int n[2], l_seq[2];
+    for (int i = 0; i < 2; ++i) {
+        const int64_t r = 2LL * pair + i;
+        a[i] = regs + reg_off[r]; n[i] = (int) (reg_off[r + 1] - reg_off[r]); l_seq[i] = (int) (offs[r + 1] - offs[r]);
+    }
+    const int count = mate_jobs_list_d(cv, min_seed_len, pen_unpaired, max_matesw, pes, l_seq, a, n, pair, nullptr);
+    PairJobs mine; mine.begin = 0; mine.count = 0;
+    if (count) {
+        const unsigned int base = atomicAdd(&stats->n_jobs, (unsigned int) count);
+        if ((unsigned long long) base + (unsigned int) count <= job_cap) {         // always true with the host's bound; a pair left out computes in place
+            mine.begin = (int32_t) base; mine.count = count;
+            mate_jobs_list_d(cv, min_seed_len, pen_unpaired, max_matesw, pes, l_seq, a, n, pair, jobs + base);
+        }
+    }
+    pj[t] = mine;
+}
+
+// stage 2: one window per warp, grid-stride over the job count stage 1 left on the device (no host round trip in between).
+// lists: 2 * lcap ints per warp of the grid (the score-2 list of one window at a time).  res[k].valid = 1: computed.
+// With the host's bound every pair fits the table; if the bound had to be clamped, entries below job_cap that no pair wrote (stale bytes) are
+// never looked up - the range checks below only keep the warp inside the buffers for them.
+__global__ void __launch_bounds__(128)
+sam_ksw_jobs_kernel(KswMat25 mat, int a_match, int min_seed_len, int o_del, int e_del, int o_ins, int e_ins, const uint8_t *__restrict__ ref, int64_t ref_len,
+                    const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, int n_reads, const MateJob *__restrict__ jobs, const SamStats *stats,
+                    unsigned int job_cap, int32_t *lists, int lcap, MateJobRes *res)
+{
+    const unsigned int n = stats->n_jobs < job_cap ? stats->n_jobs : job_cap;
+    const unsigned int warps = gridDim.x * (blockDim.x >> 5), w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    int32_t *bsc = lists + (size_t) w * 2 * lcap, *bpos = bsc + lcap;
+    for (unsigned int k = w; k < n; k += warps) {
+        const MateJob jb = jobs[k];
+        MateJobRes o; o.score = 0; o.te = -1; o.qe = -1; o.score2 = -1; o.te2 = -1; o.tb = -1; o.qb = -1; o.valid = 0;
+        if (jb.pair >= 0 && 2LL * jb.pair + 1 < n_reads && jb.rb >= 0 && jb.re <= ref_len && jb.rb < jb.re) {
+            const MateJobQuery q = mate_job_query_d(jb, codes, offs, a_match, min_seed_len);
+            if (q.l_ms > 0 && q.l_ms <= 32 * BM2_KSW_CMAX - 15 && q.tlen / 2 + 2 <= lcap) {
+                int overflow = 0;
+                const KswRes al = ksw_align2_warp_d(q.l_ms, q.q, q.stride, q.comp, q.tlen, ref + jb.rb, mat.m, o_del, e_del, o_ins, e_ins, q.xtra, bsc, bpos, lcap, &overflow);
+                o.score = al.score; o.te = al.te; o.qe = al.qe; o.score2 = al.score2; o.te2 = al.te2; o.tb = al.tb; o.qb = al.qb; o.valid = overflow ? 0 : 1;
+            }
+        }
+        if (lane == 0) res[k] = o;
+        __syncwarp(0xffffffffu);
+    }
+}
+
 __global__ void __launch_bounds__(64)
 sam_kernel(SamParams p, SamTables tb, ContigView cv, MatePes pes, int max_matesw, int rescue, const uint8_t *__restrict__ ref,
            const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, const bm2_alnreg_t *__restrict__ regs, const int64_t *__restrict__ reg_off,
            const PairDesc *__restrict__ desc, int n_pairs, int paired, int64_t id_base, uint8_t *arena, bm2_sam_rec *recs_w, bm2_sam_xa *xa_w, uint32_t *ops_w,
-           char *md_w, PairCount *cnt)
+           char *md_w, PairCount *cnt, const PairJobs *__restrict__ pj, const MateJob *__restrict__ jobs, const MateJobRes *__restrict__ jres, SamStats *stats)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_pairs) return;
@@ -54,7 +126,13 @@ sam_kernel(SamParams p, SamTables tb, ContigView cv, MatePes pes, int max_matesw
     }
     int overflow = 0;
     bm2_alnreg_t *ap[2] = { ar.a[0], ar.a[1] }, *bp[2] = { ar.b[0], ar.b[1] };
-    if (rescue && paired) mate_rescue_pair_d(cv, p.ep, p.min_seed_len, p.pen_unpaired, max_matesw, pes, ref, seq, l_seq, ap, n, bp, ar.ms, &overflow);
+    if (rescue && paired) {
+        if (pj) {             // staged: the alignments were computed by sam_ksw_jobs_kernel
+            const PairJobs mine = pj[t];
+            MateKswTable look = { jobs + mine.begin, jres + mine.begin, mine.count, { &p.ep, ref, &ar.ms, &overflow }, stats };
+            mate_rescue_pair_d(cv, p.ep, p.min_seed_len, p.pen_unpaired, max_matesw, pes, ref, seq, l_seq, ap, n, bp, ar.ms, look, &overflow);
+        } else mate_rescue_pair_d(cv, p.ep, p.min_seed_len, p.pen_unpaired, max_matesw, pes, ref, seq, l_seq, ap, n, bp, ar.ms, &overflow);
+    }
     PairCount c; c.recs = 0; c.xa = 0; c.ops = 0; c.md = 0; c.overflow = 0; c._pad = 0;
     bm2_sam_rec *recs = recs_w + d.rec_off; bm2_sam_xa *xa = xa_w + d.xa_off; uint32_t *ops = ops_w + d.ops_off; char *md = md_w + d.md_off;
     const SamPairCaps &cp = d.caps;
@@ -178,6 +256,13 @@ int run_sam(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs,
     for (int d = 0; d < 4; ++d) tb.pair_term[d] = P<double>(ctx, SB_TERM) + term_at[d];
     ContigView cv; cv.l_pac = ctx->idx.l_pac; cv.n_seqs = ctx->idx.n_seqs; cv.ann_off = ctx->idx.ann_off; cv.ann_len = ctx->idx.ann_len; cv.ann_alt = ctx->idx.ann_alt;
     const int rescue = paired && !(o.flag & 0x20);
+    int staged = ctx->sam_staged;
+    if (staged < 0) { const char *e = getenv("BM2_SAM_STAGED"); staged = e && atoi(e) > 0; }
+    staged = staged && rescue;
+    for (double &v : ctx->sam_ms) v = 0;
+    for (unsigned long long &v : ctx->sam_counts) v = 0;
+    ctx->sam_counts[0] = (unsigned long long) staged;
+    for (cudaEvent_t &ev : ctx->sam_ev) if (!ev) BM2_CUDA_OK(cudaEventCreate(&ev));
 
     // ---- inputs ------------------------------------------------------------------------------------------------------------
     const int64_t total = reads->offsets[nr], n_regs = read_off[nr];
@@ -190,6 +275,8 @@ int run_sam(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs,
 
     // ---- capacities of every pair; waves by budget ---------------------------------------------------------------------------
     std::vector<PairDesc> desc((size_t) n_pairs_all);
+    int max_l = 1;
+    for (int r = 0; r < nr; ++r) { const int64_t ls = reads->offsets[r + 1] - reads->offsets[r]; if (ls > max_l && ls <= (1 << 24)) max_l = (int) ls; }
     for (int pr = 0; pr < n_pairs_all; ++pr) {
         SamPairShape sh;
         for (int i = 0; i < 2; ++i) {
@@ -228,11 +315,45 @@ int run_sam(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs,
             ctx->ensure(ctx->d[SB_CNT], (size_t) np * sizeof(PairCount)) || ctx->ensure(ctx->d[SB_FINAL], (size_t) np * sizeof(PairFinal)) ||
             ctx->ensure_host(ctx->h[SH_CNT], (size_t) np * (sizeof(PairCount) + sizeof(PairFinal)))) return 1;
         BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[SB_DESC].p, desc.data() + w0, (size_t) np * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+        if (ctx->ensure(ctx->d[SJ_STATS], 64)) return 1;
+        BM2_CUDA_OK(cudaMemsetAsync(ctx->d[SJ_STATS].p, 0, sizeof(SamStats), st));
+        BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[0], st));
+        if (staged) {
+            int64_t bound = 0;
+            for (int k = w0; k < w1; ++k) bound += mate_jobs_bound_d(read_off[2 * k + 1] - read_off[2 * k], read_off[2 * k + 2] - read_off[2 * k + 1], o.max_matesw);
+            if (bound > 0x7fffffff) bound = 0x7fffffff;                       // pairs beyond the table compute in place
+            const unsigned int job_cap = (unsigned int) bound;
+            // one score-2 list per warp of the alignment kernel's grid: rows of the longest window, neighbours merged
+            int lcap = mate_window_max_d(pes, max_l) / 2 + 2;
+            int ksw_blocks = ctx->n_sm * 8;
+            const size_t list_budget = (size_t) 1 << 30;
+            while (ksw_blocks > ctx->n_sm && (size_t) ksw_blocks * 4 * 2 * (size_t) lcap * 4 > list_budget) ksw_blocks >>= 1;
+            if ((size_t) ksw_blocks * 4 * 2 * (size_t) lcap * 4 > list_budget) lcap = (int) (list_budget / ((size_t) ksw_blocks * 4 * 2 * 4));   // longer windows: in place
+            if (ctx->ensure(ctx->d[SJ_PAIRJOBS], (size_t) np * sizeof(PairJobs)) || ctx->ensure(ctx->d[SJ_JOBS], ((size_t) job_cap + 1) * sizeof(MateJob)) ||
+                ctx->ensure(ctx->d[SJ_RES], ((size_t) job_cap + 1) * sizeof(MateJobRes)) ||
+                ctx->ensure(ctx->d[SJ_LISTS], (size_t) ksw_blocks * 4 * 2 * (size_t) lcap * 4 + 16)) return 1;
+            sam_jobs_kernel<<<(unsigned) ((np + 127) / 128), 128, 0, st>>>(cv, pes, o.min_seed_len, o.pen_unpaired, o.max_matesw, P<int64_t>(ctx, SB_OFFS),
+                                                                          P<bm2_alnreg_t>(ctx, SB_REGS), P<int64_t>(ctx, SB_REGOFF), P<PairDesc>(ctx, SB_DESC), np,
+                                                                          P<MateJob>(ctx, SJ_JOBS), job_cap, P<PairJobs>(ctx, SJ_PAIRJOBS), P<SamStats>(ctx, SJ_STATS));
+            BM2_CUDA_OK(cudaGetLastError());
+            BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[1], st));
+            KswMat25 m25; memcpy(m25.m, o.mat, 25);
+            sam_ksw_jobs_kernel<<<(unsigned) ksw_blocks, 128, 0, st>>>(m25, o.a, o.min_seed_len, o.o_del, o.e_del, o.o_ins, o.e_ins, ctx->idx.ref, 2 * ctx->idx.l_pac,
+                                                                      P<uint8_t>(ctx, SB_CODES), P<int64_t>(ctx, SB_OFFS), nr, P<MateJob>(ctx, SJ_JOBS),
+                                                                      P<SamStats>(ctx, SJ_STATS), job_cap, P<int32_t>(ctx, SJ_LISTS), lcap, P<MateJobRes>(ctx, SJ_RES));
+            BM2_CUDA_OK(cudaGetLastError());
+        } else BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[1], st));
+        BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[2], st));
         sam_kernel<<<(unsigned) ((np + 63) / 64), 64, 0, st>>>(p, tb, cv, pes, o.max_matesw, rescue, ctx->idx.ref, P<uint8_t>(ctx, SB_CODES), P<int64_t>(ctx, SB_OFFS),
                                                               P<bm2_alnreg_t>(ctx, SB_REGS), P<int64_t>(ctx, SB_REGOFF), P<PairDesc>(ctx, SB_DESC), np, paired, id_base,
                                                               P<uint8_t>(ctx, SB_ARENA), P<bm2_sam_rec>(ctx, SB_RECS_W), P<bm2_sam_xa>(ctx, SB_XA_W),
-                                                              P<uint32_t>(ctx, SB_OPS_W), P<char>(ctx, SB_MD_W), P<PairCount>(ctx, SB_CNT));
+                                                              P<uint32_t>(ctx, SB_OPS_W), P<char>(ctx, SB_MD_W), P<PairCount>(ctx, SB_CNT),
+                                                              staged ? P<PairJobs>(ctx, SJ_PAIRJOBS) : nullptr, P<MateJob>(ctx, SJ_JOBS), P<MateJobRes>(ctx, SJ_RES),
+                                                              P<SamStats>(ctx, SJ_STATS));
         BM2_CUDA_OK(cudaGetLastError());
+        BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[3], st));
+        SamStats wave_stats;
+        BM2_CUDA_OK(cudaMemcpyAsync(&wave_stats, ctx->d[SJ_STATS].p, sizeof(SamStats), cudaMemcpyDeviceToHost, st));
         PairCount *hc = (PairCount *) ctx->h[SH_CNT].p; PairFinal *hf = (PairFinal *) (hc + np);
         BM2_CUDA_OK(cudaMemcpyAsync(hc, ctx->d[SB_CNT].p, (size_t) np * sizeof(PairCount), cudaMemcpyDeviceToHost, st));
         BM2_CUDA_OK(cudaStreamSynchronize(st));
@@ -260,7 +381,11 @@ int run_sam(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs,
             if (add[k]) BM2_CUDA_OK(cudaMemcpyAsync((char *) ctx->h[hb[k]].p + used[k], ctx->d[db[k]].p, add[k], cudaMemcpyDeviceToHost, st));
             used[k] += add[k];
         }
+        BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[4], st));
         BM2_CUDA_OK(cudaStreamSynchronize(st));
+        for (int k = 0; k < 4; ++k) { float ms = 0; BM2_CUDA_OK(cudaEventElapsedTime(&ms, ctx->sam_ev[k], ctx->sam_ev[k + 1])); ctx->sam_ms[k] += ms; }
+        ctx->sam_counts[1] += wave_stats.n_jobs; ctx->sam_counts[2] += wave_stats.looked_up; ctx->sam_counts[3] += wave_stats.in_place;
+        ctx->sam_counts[4] += wave_stats.window_moved; ctx->sam_counts[5] += 1;
         w0 = w1;
     }
     out->n_recs = (int64_t) (used[0] / sizeof(bm2_sam_rec)); out->recs = (const bm2_sam_rec *) ctx->h[SH_RECS].p;

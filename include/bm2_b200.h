@@ -313,6 +313,16 @@ int bm2_sam_pe(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *re
 /* The single-end branch of worker_sam (src/bwamem.cpp:1320-1334: mem_mark_primary_se, -5, mem_reg2sam without a mate) for a batch of reads;
  * same records (no RNEXT / PNEXT / TLEN).  id_base: number of reads before this batch in the run. */
 int bm2_sam_se(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off, int64_t id_base, bm2_sam_result *out);
+/* Staged mate rescue inside bm2_sam_pe (same records, other kernels): the windows mem_matesw (src/bwamem_pair.cpp:150-283) can ask for are
+ * listed for all pairs of a wave from the regions before any rescue, aligned as one batch with one window per warp (the job shape of
+ * bm2_ksw_align2; the reference batches the same alignments across pairs in its kswv path, src/bwamem_pair.cpp:930-1248, src/kswv.cpp),
+ * and the per-pair logic looks them up - it still computes an alignment itself when an earlier rescue of the pair moved the window.
+ * on = 1 / 0; -1 (default) leaves the choice to the BM2_SAM_STAGED environment variable (unset: off, until the path has GPU numbers). */
+int bm2_set_sam_staged(bm2_ctx *ctx, int on);
+/* Device times and counters of the last bm2_sam_pe / bm2_sam_se call.  ms[0..3] (CUDA events, summed over waves): job listing, window
+ * alignments (both 0 when not staged), the per-pair kernel, the gather.  counts[0..5]: staged (0/1), jobs listed, alignments looked up,
+ * alignments computed in place by the per-pair kernel (staged mode only), of those the ones whose window had moved, waves.  n_ms >= 4, n_counts >= 6. */
+int bm2_last_sam_stats(const bm2_ctx *ctx, double *ms, unsigned long long *counts, int n_ms, int n_counts);
 
 #ifdef __cplusplus
 }

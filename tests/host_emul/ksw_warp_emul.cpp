@@ -5,7 +5,7 @@
 #include <cstdint>
 #include "ksw_warp.cuh"
 
-static KswRes pass_lanes(int size, int qlen, const uint8_t *query, int qstride, int tlen, const uint8_t *target, int tstride, const int8_t *mat,
+static KswRes pass_lanes(int size, int qlen, const uint8_t *query, int qstride, int comp, int tlen, const uint8_t *target, int tstride, const int8_t *mat,
                          int o_del, int e_del, int o_ins, int e_ins, int xtra, int32_t *bsc, int32_t *bpos, int bcap, int *overflow)
 {
     const KswShape s = ksw_shape_d(size, qlen, mat, o_del, e_del, o_ins, e_ins);
@@ -13,7 +13,7 @@ static KswRes pass_lanes(int size, int qlen, const uint8_t *query, int qstride, 
     for (int a = 0; a < 25; ++a) if (mat[a] > qmax) qmax = mat[a];
     const int minsc = (xtra & BM2_KSW_XSUBO) ? xtra & 0xffff : 0x10000, endsc = (xtra & BM2_KSW_XSTOP) ? xtra & 0xffff : 0x10000;
     std::vector<KswLane> L(32);
-    for (int l = 0; l < 32; ++l) ksw_lane_init_d(s, l, query, qstride, L[l]);
+    for (int l = 0; l < 32; ++l) ksw_lane_init_d(s, l, query, qstride, L[l], comp);
     KswRowState st; st.gmax = 0; st.te = -1; st.n_b = 0; st.last_sc = 0; st.last_pos = -2; st.stop = false;
     for (int i = 0; i < tlen && !st.stop; ++i) {
         const int8_t *ma = mat + (int) target[(long long) i * tstride] * 5;
@@ -41,23 +41,30 @@ static KswRes pass_lanes(int size, int qlen, const uint8_t *query, int qstride, 
     return r;
 }
 
-extern "C" int emul_ksw_warp_align2(int32_t qlen, const uint8_t *query, int32_t tlen, const uint8_t *target, const int8_t *mat, int32_t o_del,
-                                    int32_t e_del, int32_t o_ins, int32_t e_ins, int32_t xtra, int32_t *out)
+// the query is query[0], query[qstride], ... (complemented if comp), as ksw_align2_warp_d takes it
+extern "C" int emul_ksw_warp_align2_q(int32_t qlen, const uint8_t *query, int32_t qstride, int32_t comp, int32_t tlen, const uint8_t *target, const int8_t *mat,
+                                      int32_t o_del, int32_t e_del, int32_t o_ins, int32_t e_ins, int32_t xtra, int32_t *out)
 {
     if (qlen > 32 * BM2_KSW_CMAX - 15) return -1;
     std::vector<int32_t> bsc((size_t) tlen / 2 + 2), bpos((size_t) tlen / 2 + 2);
     std::vector<uint8_t> tmp((size_t) tlen + 1);
     int overflow = 0;
     const int size = (xtra & BM2_KSW_XBYTE) ? 1 : 2;
-    KswRes r = pass_lanes(size, qlen, query, 1, tlen, target, 1, mat, o_del, e_del, o_ins, e_ins, xtra, bsc.data(), bpos.data(), (int) bsc.size(), &overflow);
+    KswRes r = pass_lanes(size, qlen, query, qstride, comp, tlen, target, 1, mat, o_del, e_del, o_ins, e_ins, xtra, bsc.data(), bpos.data(), (int) bsc.size(), &overflow);
     if (!((xtra & BM2_KSW_XSTART) == 0 || ((xtra & BM2_KSW_XSUBO) && r.score < (xtra & 0xffff)))) {          // ksw_align2's second pass (ksw_device.cuh)
         for (int i = 0; i <= r.te; ++i) tmp[i] = target[r.te - i];
         for (int i = r.te + 1; i < tlen; ++i) tmp[i] = target[i];
         int ov2 = 0;
-        const KswRes rr = pass_lanes(size, r.qe + 1, query + r.qe, -1, tlen, tmp.data(), 1, mat, o_del, e_del, o_ins, e_ins, BM2_KSW_XSTOP | r.score, bsc.data(),
+        const KswRes rr = pass_lanes(size, r.qe + 1, query + (long long) r.qe * qstride, -qstride, comp, tlen, tmp.data(), 1, mat, o_del, e_del, o_ins, e_ins, BM2_KSW_XSTOP | r.score, bsc.data(),
                                      bpos.data(), (int) bsc.size(), &ov2);
         if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
     }
     out[0] = r.score; out[1] = r.te; out[2] = r.qe; out[3] = r.score2; out[4] = r.te2; out[5] = r.tb; out[6] = r.qb;
     return overflow;
+}
+
+extern "C" int emul_ksw_warp_align2(int32_t qlen, const uint8_t *query, int32_t tlen, const uint8_t *target, const int8_t *mat, int32_t o_del,
+                                    int32_t e_del, int32_t o_ins, int32_t e_ins, int32_t xtra, int32_t *out)
+{
+    return emul_ksw_warp_align2_q(qlen, query, 1, 0, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, out);
 }

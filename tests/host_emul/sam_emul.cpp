@@ -12,28 +12,15 @@
 // ---- staged form of the rescue (the shape of the next kernel version): all local alignments a chunk can ask for are enumerated from the
 // regions before any rescue (mate_jobs_pair_d), computed as one batch - here by the warp formulation, ksw_warp.cuh through
 // ksw_warp_emul.cpp - and the per-pair block then looks its alignments up, computing one itself only if the batch does not hold it.
-extern "C" int emul_ksw_warp_align2(int32_t qlen, const uint8_t *query, int32_t tlen, const uint8_t *target, const int8_t *mat, int32_t o_del,
-                                    int32_t e_del, int32_t o_ins, int32_t e_ins, int32_t xtra, int32_t *out);
-#include <map>
-#include <tuple>
+extern "C" int emul_ksw_warp_align2_q(int32_t qlen, const uint8_t *query, int32_t qstride, int32_t comp, int32_t tlen, const uint8_t *target, const int8_t *mat,
+                                      int32_t o_del, int32_t e_del, int32_t o_ins, int32_t e_ins, int32_t xtra, int32_t *out);
+#include "mate_stage.cuh"
 static int g_staged = 0;
 static long long g_stage_stats[8];            // jobs in the batch, looked up, computed in place (not in the batch), windows that differed;
                                               // [4..6]: arena bytes, output-stripe bytes, units (pairs) of the last call
 extern "C" void emul_sam_set_staged(int on) { g_staged = on; }
 extern "C" void emul_sam_stage_stats(long long *out) { for (int k = 0; k < 4; ++k) out[k] = g_stage_stats[k]; }
 extern "C" void emul_sam_layout_stats(long long *out) { for (int k = 0; k < 3; ++k) out[k] = g_stage_stats[4 + k]; }
-struct StagedJob { int64_t rb, re; KswRes res; };
-typedef std::map<std::tuple<int, int, int, int>, StagedJob> JobTable;      // (pair, anchor read, anchor, orientation)
-struct MateKswLookup {
-    const JobTable *tab; int pair; MateKswDirect direct;
-    KswRes operator()(int ai, int j, int r, int l_ms, const uint8_t *seq, int64_t rb, int64_t re, int xtra) const {
-        auto it = tab->find(std::make_tuple(pair, ai, j, r));
-        if (it == tab->end()) { ++g_stage_stats[2]; return direct(ai, j, r, l_ms, seq, rb, re, xtra); }
-        if (it->second.rb != rb || it->second.re != re) { ++g_stage_stats[3]; return direct(ai, j, r, l_ms, seq, rb, re, xtra); }
-        ++g_stage_stats[1];
-        return it->second.res;
-    }
-};
 
 // one XA entry: printed with every record of `read` whose rec_reg equals `reg`
 struct EmXa { int32_t read, reg, rid, is_rev, nm, n_cigar; int64_t pos, cigar_off; };
@@ -69,32 +56,38 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
     std::vector<int32_t> rec_reg; std::vector<EmXa> xa; std::vector<uint32_t> xa_ops;
     int overflow = 0;
     int layout_bad = 0;
-    JobTable jobs;
+    // the staged form as sam.cu runs it: the job table of the chunk (sam_jobs_kernel = mate_jobs_list_d per pair), the alignments of the
+    // table (sam_ksw_jobs_kernel = mate_job_query_d + the warp formulation), then the per-pair block with MateKswTable
+    std::vector<MateJob> jobs; std::vector<MateJobRes> jres; std::vector<PairJobs> pjobs((size_t) (reads->n_reads >> 1) + 1);
+    MateStats mstats = { 0, 0, 0, 0 };
     for (int k = 0; k < 8; ++k) g_stage_stats[k] = 0;
-    if (g_staged && !(opt->flag & 0x20))
+    if (g_staged && !(opt->flag & 0x20)) {
         for (int pr = 0; pr < reads->n_reads >> 1; ++pr) {
-            const bm2_alnreg_t *a2[2]; int n2[2], l2[2]; const uint8_t *s2[2];
+            const bm2_alnreg_t *a2[2]; int n2[2], l2[2];
             for (int i = 0; i < 2; ++i) {
                 const int r = 2 * pr + i;
                 a2[i] = regs + read_off[r]; n2[i] = (int) (read_off[r + 1] - read_off[r]);
-                s2[i] = reads->codes + reads->offsets[r]; l2[i] = (int) (reads->offsets[r + 1] - reads->offsets[r]);
+                l2[i] = (int) (reads->offsets[r + 1] - reads->offsets[r]);
             }
-            auto emit_job = [&](int ai, int j, int r, int64_t rb, int64_t re, int is_rev) {
-                const int l_ms = l2[!ai];
-                std::vector<uint8_t> q(s2[!ai], s2[!ai] + l_ms);
-                if (is_rev) for (int k = 0; k < l_ms; ++k) q[l_ms - 1 - k] = s2[!ai][k] < 4 ? 3 - s2[!ai][k] : 4;
-                const int xtra = BM2_KSW_XSUBO | BM2_KSW_XSTART | (l_ms * opt->a < 250 ? BM2_KSW_XBYTE : 0) | (opt->min_seed_len * opt->a);
-                int32_t o7[7];
-                StagedJob sj; sj.rb = rb; sj.re = re;
-                if (l_ms <= 32 * 16 - 15) {
-                    emul_ksw_warp_align2(l_ms, q.data(), (int) (re - rb), idx->ref_string + rb, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, xtra, o7);
-                    sj.res.score = o7[0]; sj.res.te = o7[1]; sj.res.qe = o7[2]; sj.res.score2 = o7[3]; sj.res.te2 = o7[4]; sj.res.tb = o7[5]; sj.res.qb = o7[6];
-                    jobs[std::make_tuple(pr, ai, j, r)] = sj;
-                    ++g_stage_stats[0];
-                }
-            };
-            mate_jobs_pair_d(cv, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, l2, a2, n2, emit_job);
+            const int count = mate_jobs_list_d(cv, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, l2, a2, n2, pr, nullptr);
+            if (count > mate_jobs_bound_d(n2[0], n2[1], opt->max_matesw)) layout_bad |= 8;
+            pjobs[(size_t) pr].begin = (int32_t) jobs.size(); pjobs[(size_t) pr].count = count;
+            jobs.resize(jobs.size() + (size_t) count);
+            mate_jobs_list_d(cv, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, l2, a2, n2, pr, jobs.data() + pjobs[(size_t) pr].begin);
         }
+        jres.resize(jobs.size() + 1);
+        for (size_t k = 0; k < jobs.size(); ++k) {
+            const MateJobQuery q = mate_job_query_d(jobs[k], reads->codes, reads->offsets, opt->a, opt->min_seed_len);
+            MateJobRes o; o.score = 0; o.te = -1; o.qe = -1; o.score2 = -1; o.te2 = -1; o.tb = -1; o.qb = -1; o.valid = 0;
+            if (q.l_ms <= 32 * 16 - 15) {
+                int32_t o7[7];
+                emul_ksw_warp_align2_q(q.l_ms, q.q, q.stride, q.comp, q.tlen, idx->ref_string + jobs[k].rb, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, q.xtra, o7);
+                o.score = o7[0]; o.te = o7[1]; o.qe = o7[2]; o.score2 = o7[3]; o.te2 = o7[4]; o.tb = o7[5]; o.qb = o7[6]; o.valid = 1;
+                ++g_stage_stats[0];
+            }
+            jres[k] = o;
+        }
+    }
     for (int pr = 0; pr < reads->n_reads >> 1; ++pr) {
         const uint8_t *seq[2]; int l_seq[2], n[2];
         SamPairShape shape;
@@ -115,7 +108,8 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
         bm2_alnreg_t *ap[2] = { ar.a[0], ar.a[1] }, *bp[2] = { ar.b[0], ar.b[1] };
         if (!(opt->flag & 0x20)) {
             if (g_staged) {
-                MateKswLookup look = { &jobs, pr, { &p.ep, idx->ref_string, &ar.ms, &overflow } };
+                MateKswTable look = { jobs.data() + pjobs[(size_t) pr].begin, jres.data() + pjobs[(size_t) pr].begin, pjobs[(size_t) pr].count,
+                                      { &p.ep, idx->ref_string, &ar.ms, &overflow }, &mstats };
                 mate_rescue_pair_d(cv, p.ep, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, idx->ref_string, seq, l_seq, ap, n, bp, ar.ms, look, &overflow);
             } else mate_rescue_pair_d(cv, p.ep, opt->min_seed_len, opt->pen_unpaired, opt->max_matesw, pes, idx->ref_string, seq, l_seq, ap, n, bp, ar.ms, &overflow);
         }
@@ -141,6 +135,7 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
         if (!sam_arena_guards_ok_d(ar)) layout_bad |= 2;
         if (pair_recs > caps.recs_cap || pair_xa > caps.xa_cap || pair_ops > caps.out_ops || pair_md > caps.out_md) layout_bad |= 4;
     }
+    g_stage_stats[1] = mstats.looked_up; g_stage_stats[2] = mstats.in_place; g_stage_stats[3] = mstats.window_moved;
     const size_t nr = out.size();
     *recs_out = (bm2o_samrec *) malloc(sizeof(bm2o_samrec) * (nr + 1)); memcpy(*recs_out, out.data(), sizeof(bm2o_samrec) * nr);
     *cigar_out = (uint32_t *) malloc(4 * (ops_all.size() + 1)); memcpy(*cigar_out, ops_all.data(), 4 * ops_all.size());
