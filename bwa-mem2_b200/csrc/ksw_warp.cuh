@@ -21,12 +21,28 @@
 #define BM2_KSW_CMAX 16                          // columns per lane: queries up to 32 * 16 - 15 = 497 bases
 #define BM2_KSW_KILL (1 << 28)                   // decay of a block that holds a segment start
 
-struct KswLane {
-    int32_t H[BM2_KSW_CMAX], E[BM2_KSW_CMAX], Hbest[BM2_KSW_CMAX];     // completed H of the previous row, E, H of the best row
-    int32_t base[BM2_KSW_CMAX];
-    uint8_t q[BM2_KSW_CMAX];                     // query codes of the lane's columns (4 beyond qlen: their score is 0, see sc below)
+// T = compile-time capacity of a lane (columns): every loop over the lane's columns is `for c < T, if c < ncol` fully unrolled, so the
+// lane's state stays in registers (a runtime trip count would put the arrays in local memory).  ksw_lane_width_d picks T from the shape.
+template <int T> struct KswLaneT {
+    int32_t H[T], E[T], Hbest[T];                // completed H of the previous row, E, H of the best row
+    int32_t base[T];
+    uint32_t prof[T];                            // query profile of the lane's columns: byte t = score of the column against target base t (0..3);
+    uint32_t profn[(T + 3) / 4];                 // byte c & 3 of word c >> 2 = score against target base 4 (N); padding columns (beyond qlen) score 0
     int col0, ncol;                              // first column, columns owned (0 for lanes beyond nlen)
+    int hlast;                                   // completed H of the lane's last column (the diagonal input of the next lane's next row)
 };
+typedef KswLaneT<BM2_KSW_CMAX> KswLane;
+#if defined(__CUDA_ARCH__)
+#define BM2_UNROLL _Pragma("unroll")
+#else
+#define BM2_UNROLL
+#endif
+// the lane capacities compiled: 151-bp reads need 5 columns per lane (160 padded columns), 250-bp reads 8
+BM2_HD int ksw_lane_width_d(int C) { return C <= 5 ? 5 : C <= 8 ? 8 : BM2_KSW_CMAX; }
+// does a query of qlen bases fit lanes of capacity tmax in either score class (16 or 8 columns per segment group)?
+BM2_HD bool ksw_lane_fits_d(int qlen, int tmax) { return qlen > 0 && ((qlen + 15) / 16 * 16 + 31) / 32 <= tmax && ((qlen + 7) / 8 * 8 + 31) / 32 <= tmax; }
+// the kernel instance (5, 8 or BM2_KSW_CMAX) for queries up to max_qlen bases; 0: too long for this formulation
+BM2_HD int ksw_kernel_width_d(int max_qlen) { return ksw_lane_fits_d(max_qlen, 5) ? 5 : ksw_lane_fits_d(max_qlen, 8) ? 8 : ksw_lane_fits_d(max_qlen, BM2_KSW_CMAX) ? BM2_KSW_CMAX : 0; }
 struct KswShape { int size, qlen, p, slen, nlen, C, shift; int oe_del, e_del, oe_ins, e_ins; };
 struct KswSummary { int d_seg, v_seg, d_full, v_full; };
 
@@ -41,27 +57,41 @@ BM2_HD KswShape ksw_shape_d(int size, int qlen, const int8_t *mat, int o_del, in
 }
 
 // comp: the query is read complemented (with qstride < 0 from its last base: the reverse complement, without a copy)
-BM2_HD void ksw_lane_init_d(const KswShape &s, int lane, const uint8_t *query, int qstride, KswLane &L, int comp = 0) {
+// mat is read here only (once per pass): the kernels stage it in shared memory, the rows then work from the profile registers
+template <int T>
+BM2_HD void ksw_lane_init_d(const KswShape &s, int lane, const uint8_t *query, int qstride, const int8_t *mat, KswLaneT<T> &L, int comp = 0) {
     L.col0 = lane * s.C;
     L.ncol = L.col0 >= s.nlen ? 0 : (s.nlen - L.col0 < s.C ? s.nlen - L.col0 : s.C);
-    for (int c = 0; c < L.ncol; ++c) {
+    L.hlast = 0;
+    BM2_UNROLL
+    for (int c = 0; c < T; ++c) {
+        L.H[c] = 0; L.E[c] = 0; L.Hbest[c] = 0; L.base[c] = 0; L.prof[c] = 0;
+        if ((c & 3) == 0) L.profn[c >> 2] = 0;
+        if (c >= L.ncol) continue;
         const int k = L.col0 + c;
-        L.H[c] = 0; L.E[c] = 0; L.Hbest[c] = 0;
-        uint8_t b = k < s.qlen ? query[(long long) k * qstride] : 255;        // 255: padding column, substitution score 0
-        if (comp && b != 255) b = b < 4 ? 3 - b : 4;
-        L.q[c] = b;
+        if (k >= s.qlen) continue;                                               // padding column, substitution score 0
+        int b = query[(long long) k * qstride];
+        if (b > 4) b = 4;
+        if (comp) b = b < 4 ? 3 - b : 4;
+        uint32_t w = 0;
+        for (int t = 0; t < 4; ++t) w |= (uint32_t) (uint8_t) mat[t * 5 + b] << (8 * t);
+        L.prof[c] = w;
+        L.profn[c >> 2] |= (uint32_t) (uint8_t) mat[20 + b] << (8 * (c & 3));
     }
 }
 
 // phase A: base[] of the row and the block's scan summary.  diag_in = H(i-1) of the column left of the block (0 for lane 0).
-BM2_HD KswSummary ksw_lane_phase_a_d(const KswShape &s, const int8_t *ma, int diag_in, KswLane &L) {
+template <int T>
+BM2_HD KswSummary ksw_lane_phase_a_d(const KswShape &s, int tbase, int diag_in, KswLaneT<T> &L) {      // tbase: the row's target code (0..4)
     KswSummary m; m.d_seg = 0; m.v_seg = 0; m.d_full = 0; m.v_full = 0;
     int diag = L.col0 == 0 ? 0 : diag_in, fs = 0, ff = 0;
     bool killed = false;
-    for (int c = 0; c < L.ncol; ++c) {
+    BM2_UNROLL
+    for (int c = 0; c < T; ++c) {
+        if (c >= L.ncol) continue;
         const int k = L.col0 + c;
         if (k % s.slen == 0) { fs = 0; killed = true; }                        // a segment starts here: nothing from the left survives
-        const int sc = L.q[c] == 255 ? 0 : (int) ma[L.q[c]];
+        const int sc = tbase < 4 ? (int) (int8_t) (L.prof[c] >> (8 * tbase)) : (int) (int8_t) (L.profn[c >> 2] >> (8 * (c & 3)));
         int h = diag; diag = L.H[c];
         if (s.size == 1) { h = h + sc + s.shift; if (h > 255) h = 255; h -= s.shift; if (h < 0) h = 0; }
         else { h = h + sc; if (h > 32767) h = 32767; }
@@ -88,9 +118,12 @@ BM2_HD KswSummary ksw_summary_join_d(const KswSummary &a, const KswSummary &b) {
 
 // phase B: the cells of the row with the F values entering the block (in.v_seg / in.v_full of the exclusive scan).  Returns the
 // block's maximum of the first-pass H; leaves the completed H in L.H and the new E in L.E.
-BM2_HD int ksw_lane_phase_b_d(const KswShape &s, const KswSummary &in, KswLane &L) {
-    int fs = in.v_seg > 0 ? in.v_seg : 0, ff = in.v_full > 0 ? in.v_full : 0, rowmax = 0;
-    for (int c = 0; c < L.ncol; ++c) {
+template <int T>
+BM2_HD int ksw_lane_phase_b_d(const KswShape &s, const KswSummary &in, KswLaneT<T> &L) {
+    int fs = in.v_seg > 0 ? in.v_seg : 0, ff = in.v_full > 0 ? in.v_full : 0, rowmax = 0, hl = 0;
+    BM2_UNROLL
+    for (int c = 0; c < T; ++c) {
+        if (c >= L.ncol) continue;
         const int k = L.col0 + c;
         if (k % s.slen == 0) fs = 0;
         int h = L.base[c];
@@ -99,9 +132,11 @@ BM2_HD int ksw_lane_phase_b_d(const KswShape &s, const KswSummary &in, KswLane &
         { int t = h - s.oe_del; if (t < 0) t = 0; int e = L.E[c] - s.e_del; if (e < 0) e = 0; L.E[c] = e > t ? e : t; }
         const int open = h - s.oe_ins > 0 ? h - s.oe_ins : 0;
         fs -= s.e_ins; if (fs < 0) fs = 0; if (open > fs) fs = open;
-        L.H[c] = ff > h ? ff : h;                                                // completed H
+        const int hc = ff > h ? ff : h;                                          // completed H
+        L.H[c] = hc; hl = hc;
         ff -= s.e_ins; if (ff < 0) ff = 0; if (open > ff) ff = open;
     }
+    L.hlast = hl;
     return rowmax;
 }
 
@@ -126,7 +161,8 @@ BM2_HD void ksw_row_end_d(const KswShape &s, int i, int rowmax, int minsc, int e
 // One pass by a full warp (all 32 lanes call it with the same arguments).  bsc / bpos: the warp's score-2 list (global or shared).
 // rev_upto >= 0: the rows run over target[rev_upto], target[rev_upto - 1], ..., target[0], target[rev_upto + 1], ... (ksw_align2's second pass
 // reverses the prefix in place and still walks all tlen rows, src/ksw.cpp:366-371).
-__device__ inline KswRes ksw_pass_warp_d(int size, int qlen, const uint8_t *query, int qstride, int comp, int tlen, const uint8_t *target, int rev_upto, const int8_t *mat,
+template <int T>
+__device__ __forceinline__ KswRes ksw_pass_warp_t(int size, int qlen, const uint8_t *query, int qstride, int comp, int tlen, const uint8_t *target, int rev_upto, const int8_t *mat,
                                          int o_del, int e_del, int o_ins, int e_ins, int xtra, int32_t *bsc, int32_t *bpos, int bcap, int *overflow)
 {
     const unsigned full = 0xffffffffu;
@@ -135,15 +171,14 @@ __device__ inline KswRes ksw_pass_warp_d(int size, int qlen, const uint8_t *quer
     int qmax = 0;
     for (int a = 0; a < 25; ++a) if (mat[a] > qmax) qmax = mat[a];
     const int minsc = (xtra & BM2_KSW_XSUBO) ? xtra & 0xffff : 0x10000, endsc = (xtra & BM2_KSW_XSTOP) ? xtra & 0xffff : 0x10000;
-    KswLane L;
-    ksw_lane_init_d(s, lane, query, qstride, L, comp);
+    KswLaneT<T> L;
+    ksw_lane_init_d(s, lane, query, qstride, mat, L, comp);
     KswRowState st; st.gmax = 0; st.te = -1; st.n_b = 0; st.last_sc = 0; st.last_pos = -2; st.stop = false;
     int ov = 0;
     for (int i = 0; i < tlen && !st.stop; ++i) {
-        const int8_t *ma = mat + (int) target[i <= rev_upto ? rev_upto - i : i] * 5;
-        const int last = L.ncol ? L.H[L.ncol - 1] : 0;
-        const int diag_in = __shfl_up_sync(full, last, 1);
-        KswSummary m = ksw_lane_phase_a_d(s, ma, diag_in, L);
+        const int tbase = target[i <= rev_upto ? rev_upto - i : i];
+        const int diag_in = __shfl_up_sync(full, L.hlast, 1);                    // H(i-1) of the left neighbour's last column
+        KswSummary m = ksw_lane_phase_a_d(s, tbase > 4 ? 4 : tbase, diag_in, L);
         KswSummary inc = m;                                                      // inclusive scan (Hillis-Steele), then shift by one lane
         for (int d = 1; d < 32; d <<= 1) {
             KswSummary o;
@@ -159,13 +194,17 @@ __device__ inline KswRes ksw_pass_warp_d(int size, int qlen, const uint8_t *quer
         for (int d = 16; d > 0; d >>= 1) { const int o = __shfl_xor_sync(full, rowmax, d); if (o > rowmax) rowmax = o; }
         bool took;                                                               // all lanes keep the same row state; lane 0 writes the list
         ksw_row_end_d(s, i, rowmax, minsc, endsc, st, bsc, bpos, bcap, &ov, &took, lane == 0);
-        if (took) for (int c = 0; c < L.ncol; ++c) L.Hbest[c] = L.H[c];
+        if (took) {
+            BM2_UNROLL
+            for (int c = 0; c < T; ++c) L.Hbest[c] = L.H[c];
+        }
         __syncwarp(full);
     }
     KswRes r; r.score = size == 1 ? (st.gmax + s.shift < 255 ? st.gmax : 255) : st.gmax; r.te = st.te; r.qe = -1; r.score2 = -1; r.te2 = -1; r.tb = -1; r.qb = -1;
     if (size == 2 || r.score != 255) {
         int mx = -1, pos = 0x7fffffff;
-        for (int c = 0; c < L.ncol; ++c) if (L.Hbest[c] > mx) { mx = L.Hbest[c]; pos = L.col0 + c; }
+        BM2_UNROLL
+        for (int c = 0; c < T; ++c) if (c < L.ncol && L.Hbest[c] > mx) { mx = L.Hbest[c]; pos = L.col0 + c; }
         for (int d = 16; d > 0; d >>= 1) {
             const int omx = __shfl_xor_sync(full, mx, d), opos = __shfl_xor_sync(full, pos, d);
             if (omx > mx || (omx == mx && opos < pos)) { mx = omx; pos = opos; }
@@ -186,17 +225,32 @@ __device__ inline KswRes ksw_pass_warp_d(int size, int qlen, const uint8_t *quer
     return r;
 }
 
+// TMAX: the largest lane capacity this kernel instance carries (its register budget); the caller guarantees ksw_lane_fits_d(qlen, TMAX)
+template <int TMAX>
+__device__ __forceinline__ KswRes ksw_pass_warp_d(int size, int qlen, const uint8_t *query, int qstride, int comp, int tlen, const uint8_t *target, int rev_upto,
+                                         const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins, int xtra, int32_t *bsc, int32_t *bpos, int bcap, int *overflow)
+{
+    const int p = size == 1 ? 16 : 8, nlen = (qlen + p - 1) / p * p;
+    const int w = ksw_lane_width_d((nlen + 31) / 32);                         // warp-uniform
+    if (TMAX > 8 && w > 8)
+        return ksw_pass_warp_t<(TMAX > 8) ? BM2_KSW_CMAX : 5>(size, qlen, query, qstride, comp, tlen, target, rev_upto, mat, o_del, e_del, o_ins, e_ins, xtra, bsc, bpos, bcap, overflow);
+    if (TMAX > 5 && w > 5)
+        return ksw_pass_warp_t<(TMAX > 5) ? 8 : 5>(size, qlen, query, qstride, comp, tlen, target, rev_upto, mat, o_del, e_del, o_ins, e_ins, xtra, bsc, bpos, bcap, overflow);
+    return ksw_pass_warp_t<5>(size, qlen, query, qstride, comp, tlen, target, rev_upto, mat, o_del, e_del, o_ins, e_ins, xtra, bsc, bpos, bcap, overflow);
+}
+
 // ksw_align2 (src/ksw.cpp:324-381) by a full warp: forward pass, then the reversed prefixes to find the start.
 // The query is query[0], query[qstride], ... (complemented if comp): (ms + l_ms - 1, -1, 1) is the reverse complement of ms.
-__device__ inline KswRes ksw_align2_warp_d(int qlen, const uint8_t *query, int qstride, int comp, int tlen, const uint8_t *target, const int8_t *mat, int o_del, int e_del, int o_ins,
+template <int TMAX>
+__device__ __forceinline__ KswRes ksw_align2_warp_d(int qlen, const uint8_t *query, int qstride, int comp, int tlen, const uint8_t *target, const int8_t *mat, int o_del, int e_del, int o_ins,
                                            int e_ins, int xtra, int32_t *bsc, int32_t *bpos, int bcap, int *overflow)
 {
     const int size = (xtra & BM2_KSW_XBYTE) ? 1 : 2;
-    KswRes r = ksw_pass_warp_d(size, qlen, query, qstride, comp, tlen, target, -1, mat, o_del, e_del, o_ins, e_ins, xtra, bsc, bpos, bcap, overflow);
+    KswRes r = ksw_pass_warp_d<TMAX>(size, qlen, query, qstride, comp, tlen, target, -1, mat, o_del, e_del, o_ins, e_ins, xtra, bsc, bpos, bcap, overflow);
     if ((xtra & BM2_KSW_XSTART) == 0 || ((xtra & BM2_KSW_XSUBO) && r.score < (xtra & 0xffff))) return r;
     int ov2 = 0;
     __syncwarp(0xffffffffu);
-    const KswRes rr = ksw_pass_warp_d(size, r.qe + 1, query + (long long) r.qe * qstride, -qstride, comp, tlen, target, r.te, mat, o_del, e_del, o_ins, e_ins, BM2_KSW_XSTOP | r.score, bsc, bpos, bcap, &ov2);
+    const KswRes rr = ksw_pass_warp_d<TMAX>(size, r.qe + 1, query + (long long) r.qe * qstride, -qstride, comp, tlen, target, r.te, mat, o_del, e_del, o_ins, e_ins, BM2_KSW_XSTOP | r.score, bsc, bpos, bcap, &ov2);
     if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
     return r;
 }

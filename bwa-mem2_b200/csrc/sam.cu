@@ -80,11 +80,15 @@ sam_jobs_kernel(ContigView cv, MatePes pes, int min_seed_len, int pen_unpaired, 
 // lists: 2 * lcap ints per warp of the grid (the score-2 list of one window at a time).  res[k].valid = 1: computed.
 // With the host's bound every pair fits the table; if the bound had to be clamped, entries below job_cap that no pair wrote (stale bytes) are
 // never looked up - the range checks below only keep the warp inside the buffers for them.
+template <int TMAX>
 __global__ void __launch_bounds__(128)
 sam_ksw_jobs_kernel(KswMat25 mat, int a_match, int min_seed_len, int o_del, int e_del, int o_ins, int e_ins, const uint8_t *__restrict__ ref, int64_t ref_len,
                     const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, int n_reads, const MateJob *__restrict__ jobs, const SamStats *stats,
                     unsigned int job_cap, int32_t *lists, int lcap, MateJobRes *res)
 {
+    __shared__ int8_t smat[32];                               // the passes index the matrix with data (profile set-up): shared, not a local copy
+    if (threadIdx.x < 25) smat[threadIdx.x] = mat.m[threadIdx.x];
+    __syncthreads();
     const unsigned int n = stats->n_jobs < job_cap ? stats->n_jobs : job_cap;
     const unsigned int warps = gridDim.x * (blockDim.x >> 5), w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -94,9 +98,9 @@ sam_ksw_jobs_kernel(KswMat25 mat, int a_match, int min_seed_len, int o_del, int 
         MateJobRes o; o.score = 0; o.te = -1; o.qe = -1; o.score2 = -1; o.te2 = -1; o.tb = -1; o.qb = -1; o.valid = 0;
         if (jb.pair >= 0 && 2LL * jb.pair + 1 < n_reads && jb.rb >= 0 && jb.re <= ref_len && jb.rb < jb.re) {
             const MateJobQuery q = mate_job_query_d(jb, codes, offs, a_match, min_seed_len);
-            if (q.l_ms > 0 && q.l_ms <= 32 * BM2_KSW_CMAX - 15 && q.tlen / 2 + 2 <= lcap) {
+            if (ksw_lane_fits_d(q.l_ms, TMAX) && q.tlen / 2 + 2 <= lcap) {
                 int overflow = 0;
-                const KswRes al = ksw_align2_warp_d(q.l_ms, q.q, q.stride, q.comp, q.tlen, ref + jb.rb, mat.m, o_del, e_del, o_ins, e_ins, q.xtra, bsc, bpos, lcap, &overflow);
+                const KswRes al = ksw_align2_warp_d<TMAX>(q.l_ms, q.q, q.stride, q.comp, q.tlen, ref + jb.rb, smat, o_del, e_del, o_ins, e_ins, q.xtra, bsc, bpos, lcap, &overflow);
                 o.score = al.score; o.te = al.te; o.qe = al.qe; o.score2 = al.score2; o.te2 = al.te2; o.tb = al.tb; o.qb = al.qb; o.valid = overflow ? 0 : 1;
             }
         }
@@ -338,9 +342,16 @@ int run_sam(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs,
             BM2_CUDA_OK(cudaGetLastError());
             BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[1], st));
             KswMat25 m25; memcpy(m25.m, o.mat, 25);
-            sam_ksw_jobs_kernel<<<(unsigned) ksw_blocks, 128, 0, st>>>(m25, o.a, o.min_seed_len, o.o_del, o.e_del, o.o_ins, o.e_ins, ctx->idx.ref, 2 * ctx->idx.l_pac,
-                                                                      P<uint8_t>(ctx, SB_CODES), P<int64_t>(ctx, SB_OFFS), nr, P<MateJob>(ctx, SJ_JOBS),
-                                                                      P<SamStats>(ctx, SJ_STATS), job_cap, P<int32_t>(ctx, SJ_LISTS), lcap, P<MateJobRes>(ctx, SJ_RES));
+            // the kernel instance whose lanes hold the longest read of the batch; longer reads than any instance holds are aligned in place
+#define BM2_SAM_KSW_LAUNCH(T) sam_ksw_jobs_kernel<T><<<(unsigned) ksw_blocks, 128, 0, st>>>(m25, o.a, o.min_seed_len, o.o_del, o.e_del, o.o_ins, o.e_ins, ctx->idx.ref, \
+                              2 * ctx->idx.l_pac, P<uint8_t>(ctx, SB_CODES), P<int64_t>(ctx, SB_OFFS), nr, P<MateJob>(ctx, SJ_JOBS), P<SamStats>(ctx, SJ_STATS), \
+                              job_cap, P<int32_t>(ctx, SJ_LISTS), lcap, P<MateJobRes>(ctx, SJ_RES))
+            switch (ksw_kernel_width_d(max_l)) {
+            case 5: BM2_SAM_KSW_LAUNCH(5); break;
+            case 8: BM2_SAM_KSW_LAUNCH(8); break;
+            default: BM2_SAM_KSW_LAUNCH(BM2_KSW_CMAX); break;
+            }
+#undef BM2_SAM_KSW_LAUNCH
             BM2_CUDA_OK(cudaGetLastError());
         } else BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[1], st));
         BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[2], st));

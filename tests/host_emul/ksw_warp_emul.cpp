@@ -5,22 +5,23 @@
 #include <cstdint>
 #include "ksw_warp.cuh"
 
-static KswRes pass_lanes(int size, int qlen, const uint8_t *query, int qstride, int comp, int tlen, const uint8_t *target, int tstride, const int8_t *mat,
+template <int T>
+static KswRes pass_lanes_t(int size, int qlen, const uint8_t *query, int qstride, int comp, int tlen, const uint8_t *target, int tstride, const int8_t *mat,
                          int o_del, int e_del, int o_ins, int e_ins, int xtra, int32_t *bsc, int32_t *bpos, int bcap, int *overflow)
 {
     const KswShape s = ksw_shape_d(size, qlen, mat, o_del, e_del, o_ins, e_ins);
     int qmax = 0;
     for (int a = 0; a < 25; ++a) if (mat[a] > qmax) qmax = mat[a];
     const int minsc = (xtra & BM2_KSW_XSUBO) ? xtra & 0xffff : 0x10000, endsc = (xtra & BM2_KSW_XSTOP) ? xtra & 0xffff : 0x10000;
-    std::vector<KswLane> L(32);
-    for (int l = 0; l < 32; ++l) ksw_lane_init_d(s, l, query, qstride, L[l], comp);
+    std::vector<KswLaneT<T>> L(32);
+    for (int l = 0; l < 32; ++l) ksw_lane_init_d(s, l, query, qstride, mat, L[l], comp);
     KswRowState st; st.gmax = 0; st.te = -1; st.n_b = 0; st.last_sc = 0; st.last_pos = -2; st.stop = false;
     for (int i = 0; i < tlen && !st.stop; ++i) {
-        const int8_t *ma = mat + (int) target[(long long) i * tstride] * 5;
+        const int tbase = target[(long long) i * tstride] > 4 ? 4 : target[(long long) i * tstride];
         int last[32];
-        for (int l = 0; l < 32; ++l) last[l] = L[l].ncol ? L[l].H[L[l].ncol - 1] : 0;
+        for (int l = 0; l < 32; ++l) last[l] = L[l].hlast;
         KswSummary m[32], in[32];
-        for (int l = 0; l < 32; ++l) m[l] = ksw_lane_phase_a_d(s, ma, l ? last[l - 1] : 0, L[l]);
+        for (int l = 0; l < 32; ++l) m[l] = ksw_lane_phase_a_d(s, tbase, l ? last[l - 1] : 0, L[l]);
         KswSummary run; run.d_seg = 0; run.v_seg = 0; run.d_full = 0; run.v_full = 0;      // exclusive scan
         for (int l = 0; l < 32; ++l) { in[l] = run; run = l == 0 ? m[0] : ksw_summary_join_d(run, m[l]); }
         int rowmax = 0;
@@ -39,6 +40,18 @@ static KswRes pass_lanes(int size, int qlen, const uint8_t *query, int qstride, 
         }
     }
     return r;
+}
+
+// the same choice of the lane capacity as ksw_pass_warp_d
+static KswRes pass_lanes(int size, int qlen, const uint8_t *query, int qstride, int comp, int tlen, const uint8_t *target, int tstride, const int8_t *mat,
+                         int o_del, int e_del, int o_ins, int e_ins, int xtra, int32_t *bsc, int32_t *bpos, int bcap, int *overflow)
+{
+    const int p = size == 1 ? 16 : 8, nlen = (qlen + p - 1) / p * p;
+    switch (ksw_lane_width_d((nlen + 31) / 32)) {
+    case 5: return pass_lanes_t<5>(size, qlen, query, qstride, comp, tlen, target, tstride, mat, o_del, e_del, o_ins, e_ins, xtra, bsc, bpos, bcap, overflow);
+    case 8: return pass_lanes_t<8>(size, qlen, query, qstride, comp, tlen, target, tstride, mat, o_del, e_del, o_ins, e_ins, xtra, bsc, bpos, bcap, overflow);
+    default: return pass_lanes_t<BM2_KSW_CMAX>(size, qlen, query, qstride, comp, tlen, target, tstride, mat, o_del, e_del, o_ins, e_ins, xtra, bsc, bpos, bcap, overflow);
+    }
 }
 
 // the query is query[0], query[qstride], ... (complemented if comp), as ksw_align2_warp_d takes it
