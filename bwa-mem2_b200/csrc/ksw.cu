@@ -62,6 +62,7 @@ extern "C" int bm2_ksw_align2(bm2_ctx *ctx, const uint8_t *seqs, int64_t n_seq_b
             bm2_set_error(ctx, "bm2_ksw_align2: a request outside the sequence buffer"); return 1;
         }
         if (q.qlen > 32 * BM2_KSW_CMAX - 15) { bm2_set_error(ctx, "bm2_ksw_align2: queries longer than 497 bases are not supported by this entry point yet"); return 1; }
+        if (!ksw_scan_ok_d(o.e_ins, q.qlen)) { bm2_set_error(ctx, "bm2_ksw_align2: gap extension penalty too large for this entry point (e_ins * qlen must stay below 2^20)"); return 1; }
         if (q.qlen > max_qlen) max_qlen = q.qlen;
         list_off[(size_t) r] = tot;
         tot += 2 * ((int64_t) q.tlen / 2 + 2);

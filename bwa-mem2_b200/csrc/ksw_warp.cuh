@@ -7,9 +7,12 @@
 //     base[k] = max(H(i-1, k-1) + S, E(i, k))            (an opening from an F-derived H never beats extending that F, o_ins >= 0)
 //     F(k) = max(0, max over j < k of base[j] - o_ins - e_ins * (k - j))     (for the segment F: j inside k's segment)
 // so a row splits over the 32 lanes: lane l owns C = ceil(nlen / 32) neighbouring columns (H, E in registers), computes base[] and the
-// summary (decay, value) of its block, an exclusive warp scan of the summaries under
-//     (d1, v1) o (d2, v2) = (d1 + d2, max(v1 - d2, v2))         (a segment start inside a block makes its decay "infinite")
-// hands every lane the F values entering its block, and a second local pass finishes the cells.  The row maximum is a warp max.
+// F values leaving its block (zero entering).  The decay between two blocks is e_ins per column and the columns are static, so with
+//     w_j = v_j + e_ins * (end column of block j)            F entering block l = max(0, max_{j<l} w_j - e_ins * col0_l)
+// the scan is a plain exclusive prefix MAXIMUM over the lanes (one shuffle + one max per step; no (decay, value) pairs).  The segment F only
+// sees lanes since the last segment start, and those are static too: keys w_j + BIG * (segment starts in columns [0, end of block j)) make
+// every lane of an older segment lose against any lane of the current one, so the same prefix maximum serves - two 32-bit scans per row.
+// A second local pass finishes the cells.  The row maximum is a warp max (redux.sync).
 // Rows stay synchronous, so the reference's early stops, its score-2 list and the copy of the best row are as in the sweep.
 //
 // The per-lane phases are plain BM2_HD functions; tests/host_emul/ksw_warp_emul.cpp drives them with a loop over 32 lane states and
@@ -19,7 +22,8 @@
 #include "ksw_device.cuh"
 
 #define BM2_KSW_CMAX 16                          // columns per lane: queries up to 32 * 16 - 15 = 497 bases
-#define BM2_KSW_KILL (1 << 28)                   // decay of a block that holds a segment start
+#define BM2_KSW_BIG (1 << 20)                    // segment offset of the scan keys: above any w (ksw_scan_ok_d)
+#define BM2_KSW_NONE (-(1 << 30))                // scan identity
 
 // T = compile-time capacity of a lane (columns): every loop over the lane's columns is `for c < T, if c < ncol` fully unrolled, so the
 // lane's state stays in registers (a runtime trip count would put the arrays in local memory).  ksw_lane_width_d picks T from the shape.
@@ -29,6 +33,8 @@ template <int T> struct KswLaneT {
     uint32_t prof[T];                            // query profile of the lane's columns: byte t = score of the column against target base t (0..3);
     uint32_t profn[(T + 3) / 4];                 // byte c & 3 of word c >> 2 = score against target base 4 (N); padding columns (beyond qlen) score 0
     int col0, ncol;                              // first column, columns owned (0 for lanes beyond nlen)
+    unsigned segmask;                            // bit c: column col0 + c starts a segment of the reference's striping
+    int endcol, seg_in, seg_end;                 // col0 + ncol; segment starts in columns [0, col0) and [0, endcol)
     int hlast;                                   // completed H of the lane's last column (the diagonal input of the next lane's next row)
 };
 typedef KswLaneT<BM2_KSW_CMAX> KswLane;
@@ -44,7 +50,9 @@ BM2_HD bool ksw_lane_fits_d(int qlen, int tmax) { return qlen > 0 && ((qlen + 15
 // the kernel instance (5, 8 or BM2_KSW_CMAX) for queries up to max_qlen bases; 0: too long for this formulation
 BM2_HD int ksw_kernel_width_d(int max_qlen) { return ksw_lane_fits_d(max_qlen, 5) ? 5 : ksw_lane_fits_d(max_qlen, 8) ? 8 : ksw_lane_fits_d(max_qlen, BM2_KSW_CMAX) ? BM2_KSW_CMAX : 0; }
 struct KswShape { int size, qlen, p, slen, nlen, C, shift; int oe_del, e_del, oe_ins, e_ins; };
-struct KswSummary { int d_seg, v_seg, d_full, v_full; };
+struct KswSummary { int v_seg, v_full; };        // F of the segment / complete F: leaving a block (phase A), scan keys, entering a block (phase B)
+// the scan keys stay below BM2_KSW_BIG: scores < 2^15 (both classes), decay e_ins per column
+BM2_HD bool ksw_scan_ok_d(int e_ins, int qlen) { return e_ins > 0 && (long long) e_ins * (qlen + 48) + 32768 < BM2_KSW_BIG; }
 
 BM2_HD KswShape ksw_shape_d(int size, int qlen, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins) {
     KswShape s; s.size = size; s.qlen = qlen; s.p = size == 1 ? 16 : 8;
@@ -62,13 +70,16 @@ template <int T>
 BM2_HD void ksw_lane_init_d(const KswShape &s, int lane, const uint8_t *query, int qstride, const int8_t *mat, KswLaneT<T> &L, int comp = 0) {
     L.col0 = lane * s.C;
     L.ncol = L.col0 >= s.nlen ? 0 : (s.nlen - L.col0 < s.C ? s.nlen - L.col0 : s.C);
-    L.hlast = 0;
+    L.hlast = 0; L.segmask = 0;
+    L.endcol = L.col0 + L.ncol;
+    L.seg_in = (L.col0 + s.slen - 1) / s.slen; L.seg_end = (L.endcol + s.slen - 1) / s.slen;
     BM2_UNROLL
     for (int c = 0; c < T; ++c) {
         L.H[c] = 0; L.E[c] = 0; L.Hbest[c] = 0; L.base[c] = 0; L.prof[c] = 0;
         if ((c & 3) == 0) L.profn[c >> 2] = 0;
         if (c >= L.ncol) continue;
         const int k = L.col0 + c;
+        if (k % s.slen == 0) L.segmask |= 1u << c;
         if (k >= s.qlen) continue;                                               // padding column, substitution score 0
         int b = query[(long long) k * qstride];
         if (b > 4) b = 4;
@@ -83,14 +94,12 @@ BM2_HD void ksw_lane_init_d(const KswShape &s, int lane, const uint8_t *query, i
 // phase A: base[] of the row and the block's scan summary.  diag_in = H(i-1) of the column left of the block (0 for lane 0).
 template <int T>
 BM2_HD KswSummary ksw_lane_phase_a_d(const KswShape &s, int tbase, int diag_in, KswLaneT<T> &L) {      // tbase: the row's target code (0..4)
-    KswSummary m; m.d_seg = 0; m.v_seg = 0; m.d_full = 0; m.v_full = 0;
+    KswSummary m;
     int diag = L.col0 == 0 ? 0 : diag_in, fs = 0, ff = 0;
-    bool killed = false;
     BM2_UNROLL
     for (int c = 0; c < T; ++c) {
         if (c >= L.ncol) continue;
-        const int k = L.col0 + c;
-        if (k % s.slen == 0) { fs = 0; killed = true; }                        // a segment starts here: nothing from the left survives
+        if ((L.segmask >> c) & 1) fs = 0;                                      // a segment starts here: nothing from the left survives
         const int sc = tbase < 4 ? (int) (int8_t) (L.prof[c] >> (8 * tbase)) : (int) (int8_t) (L.profn[c >> 2] >> (8 * (c & 3)));
         int h = diag; diag = L.H[c];
         if (s.size == 1) { h = h + sc + s.shift; if (h > 255) h = 255; h -= s.shift; if (h < 0) h = 0; }
@@ -102,18 +111,24 @@ BM2_HD KswSummary ksw_lane_phase_a_d(const KswShape &s, int tbase, int diag_in, 
         fs -= s.e_ins; if (fs < 0) fs = 0; if (open > fs) fs = open;
         ff -= s.e_ins; if (ff < 0) ff = 0; if (open > ff) ff = open;
     }
-    m.d_seg = killed ? BM2_KSW_KILL : L.ncol * s.e_ins; m.v_seg = fs;
-    m.d_full = L.ncol * s.e_ins; m.v_full = ff;
+    m.v_seg = fs; m.v_full = ff;
     return m;
 }
 
-BM2_HD KswSummary ksw_summary_join_d(const KswSummary &a, const KswSummary &b) {          // a's block lies left of b's
-    KswSummary r;
-    r.d_seg = a.d_seg + b.d_seg > BM2_KSW_KILL ? BM2_KSW_KILL : a.d_seg + b.d_seg;
-    r.v_seg = a.v_seg - b.d_seg > b.v_seg ? a.v_seg - b.d_seg : b.v_seg;
-    r.d_full = a.d_full + b.d_full > BM2_KSW_KILL ? BM2_KSW_KILL : a.d_full + b.d_full;
-    r.v_full = a.v_full - b.d_full > b.v_full ? a.v_full - b.d_full : b.v_full;
-    return r;
+// scan keys of a block (see the header) and the way back from the exclusive prefix maxima to the F values entering a block
+template <int T>
+BM2_HD KswSummary ksw_scan_keys_d(const KswShape &s, const KswLaneT<T> &L, const KswSummary &m) {
+    KswSummary k;
+    k.v_full = L.ncol ? m.v_full + s.e_ins * L.endcol : BM2_KSW_NONE;
+    k.v_seg = L.ncol ? m.v_seg + s.e_ins * L.endcol + BM2_KSW_BIG * L.seg_end : BM2_KSW_NONE;
+    return k;
+}
+template <int T>
+BM2_HD KswSummary ksw_scan_entering_d(const KswShape &s, const KswLaneT<T> &L, const KswSummary &pm) {      // pm: maxima over the lanes to the left
+    KswSummary in;
+    in.v_full = pm.v_full - s.e_ins * L.col0;
+    in.v_seg = pm.v_seg - BM2_KSW_BIG * L.seg_in - s.e_ins * L.col0;      // a lane of an older segment gives a negative value here: 0 after phase B's clamp
+    return in;
 }
 
 // phase B: the cells of the row with the F values entering the block (in.v_seg / in.v_full of the exclusive scan).  Returns the
@@ -124,8 +139,7 @@ BM2_HD int ksw_lane_phase_b_d(const KswShape &s, const KswSummary &in, KswLaneT<
     BM2_UNROLL
     for (int c = 0; c < T; ++c) {
         if (c >= L.ncol) continue;
-        const int k = L.col0 + c;
-        if (k % s.slen == 0) fs = 0;
+        if ((L.segmask >> c) & 1) fs = 0;
         int h = L.base[c];
         if (fs > h) h = fs;                                                      // first-pass H
         if (h > rowmax) rowmax = h;
@@ -179,19 +193,18 @@ __device__ __forceinline__ KswRes ksw_pass_warp_t(int size, int qlen, const uint
         const int tbase = target[i <= rev_upto ? rev_upto - i : i];
         const int diag_in = __shfl_up_sync(full, L.hlast, 1);                    // H(i-1) of the left neighbour's last column
         KswSummary m = ksw_lane_phase_a_d(s, tbase > 4 ? 4 : tbase, diag_in, L);
-        KswSummary inc = m;                                                      // inclusive scan (Hillis-Steele), then shift by one lane
+        const KswSummary key = ksw_scan_keys_d(s, L, m);
+        KswSummary pm;                                                           // exclusive prefix maxima: shift by one lane, then Hillis-Steele
+        pm.v_seg = __shfl_up_sync(full, key.v_seg, 1); pm.v_full = __shfl_up_sync(full, key.v_full, 1);
+        if (lane == 0) { pm.v_seg = BM2_KSW_NONE; pm.v_full = BM2_KSW_NONE; }
+        BM2_UNROLL
         for (int d = 1; d < 32; d <<= 1) {
-            KswSummary o;
-            o.d_seg = __shfl_up_sync(full, inc.d_seg, d); o.v_seg = __shfl_up_sync(full, inc.v_seg, d);
-            o.d_full = __shfl_up_sync(full, inc.d_full, d); o.v_full = __shfl_up_sync(full, inc.v_full, d);
-            if (lane >= d) inc = ksw_summary_join_d(o, inc);
+            const int os = __shfl_up_sync(full, pm.v_seg, d), of = __shfl_up_sync(full, pm.v_full, d);
+            if (lane >= d) { pm.v_seg = os > pm.v_seg ? os : pm.v_seg; pm.v_full = of > pm.v_full ? of : pm.v_full; }
         }
-        KswSummary in;
-        in.d_seg = 0; in.d_full = 0;
-        in.v_seg = __shfl_up_sync(full, inc.v_seg, 1); in.v_full = __shfl_up_sync(full, inc.v_full, 1);
-        if (lane == 0) { in.v_seg = 0; in.v_full = 0; }
+        const KswSummary in = ksw_scan_entering_d(s, L, pm);
         int rowmax = ksw_lane_phase_b_d(s, in, L);
-        for (int d = 16; d > 0; d >>= 1) { const int o = __shfl_xor_sync(full, rowmax, d); if (o > rowmax) rowmax = o; }
+        rowmax = __reduce_max_sync(full, rowmax);
         bool took;                                                               // all lanes keep the same row state; lane 0 writes the list
         ksw_row_end_d(s, i, rowmax, minsc, endsc, st, bsc, bpos, bcap, &ov, &took, lane == 0);
         if (took) {

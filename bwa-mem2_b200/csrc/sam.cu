@@ -98,7 +98,7 @@ sam_ksw_jobs_kernel(KswMat25 mat, int a_match, int min_seed_len, int o_del, int 
         MateJobRes o; o.score = 0; o.te = -1; o.qe = -1; o.score2 = -1; o.te2 = -1; o.tb = -1; o.qb = -1; o.valid = 0;
         if (jb.pair >= 0 && 2LL * jb.pair + 1 < n_reads && jb.rb >= 0 && jb.re <= ref_len && jb.rb < jb.re) {
             const MateJobQuery q = mate_job_query_d(jb, codes, offs, a_match, min_seed_len);
-            if (ksw_lane_fits_d(q.l_ms, TMAX) && q.tlen / 2 + 2 <= lcap) {
+            if (ksw_lane_fits_d(q.l_ms, TMAX) && ksw_scan_ok_d(e_ins, q.l_ms) && q.tlen / 2 + 2 <= lcap) {
                 int overflow = 0;
                 const KswRes al = ksw_align2_warp_d<TMAX>(q.l_ms, q.q, q.stride, q.comp, q.tlen, ref + jb.rb, smat, o_del, e_del, o_ins, e_ins, q.xtra, bsc, bpos, lcap, &overflow);
                 o.score = al.score; o.te = al.te; o.qe = al.qe; o.score2 = al.score2; o.te2 = al.te2; o.tb = al.tb; o.qb = al.qb; o.valid = overflow ? 0 : 1;

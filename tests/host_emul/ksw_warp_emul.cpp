@@ -22,8 +22,13 @@ static KswRes pass_lanes_t(int size, int qlen, const uint8_t *query, int qstride
         for (int l = 0; l < 32; ++l) last[l] = L[l].hlast;
         KswSummary m[32], in[32];
         for (int l = 0; l < 32; ++l) m[l] = ksw_lane_phase_a_d(s, tbase, l ? last[l - 1] : 0, L[l]);
-        KswSummary run; run.d_seg = 0; run.v_seg = 0; run.d_full = 0; run.v_full = 0;      // exclusive scan
-        for (int l = 0; l < 32; ++l) { in[l] = run; run = l == 0 ? m[0] : ksw_summary_join_d(run, m[l]); }
+        KswSummary run; run.v_seg = BM2_KSW_NONE; run.v_full = BM2_KSW_NONE;                  // exclusive prefix maxima of the scan keys, lane order
+        for (int l = 0; l < 32; ++l) {
+            in[l] = ksw_scan_entering_d(s, L[l], run);
+            const KswSummary key = ksw_scan_keys_d(s, L[l], m[l]);
+            if (key.v_seg > run.v_seg) run.v_seg = key.v_seg;
+            if (key.v_full > run.v_full) run.v_full = key.v_full;
+        }
         int rowmax = 0;
         for (int l = 0; l < 32; ++l) { const int r = ksw_lane_phase_b_d(s, in[l], L[l]); if (r > rowmax) rowmax = r; }
         bool took;
@@ -58,7 +63,7 @@ static KswRes pass_lanes(int size, int qlen, const uint8_t *query, int qstride, 
 extern "C" int emul_ksw_warp_align2_q(int32_t qlen, const uint8_t *query, int32_t qstride, int32_t comp, int32_t tlen, const uint8_t *target, const int8_t *mat,
                                       int32_t o_del, int32_t e_del, int32_t o_ins, int32_t e_ins, int32_t xtra, int32_t *out)
 {
-    if (qlen > 32 * BM2_KSW_CMAX - 15) return -1;
+    if (qlen > 32 * BM2_KSW_CMAX - 15 || !ksw_scan_ok_d(e_ins, qlen)) return -1;
     std::vector<int32_t> bsc((size_t) tlen / 2 + 2), bpos((size_t) tlen / 2 + 2);
     std::vector<uint8_t> tmp((size_t) tlen + 1);
     int overflow = 0;

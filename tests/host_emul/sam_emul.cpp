@@ -15,6 +15,7 @@
 extern "C" int emul_ksw_warp_align2_q(int32_t qlen, const uint8_t *query, int32_t qstride, int32_t comp, int32_t tlen, const uint8_t *target, const int8_t *mat,
                                       int32_t o_del, int32_t e_del, int32_t o_ins, int32_t e_ins, int32_t xtra, int32_t *out);
 #include "mate_stage.cuh"
+#include "ksw_warp.cuh"
 static int g_staged = 0;
 static long long g_stage_stats[8];            // jobs in the batch, looked up, computed in place (not in the batch), windows that differed;
                                               // [4..6]: arena bytes, output-stripe bytes, units (pairs) of the last call
@@ -79,7 +80,7 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
         for (size_t k = 0; k < jobs.size(); ++k) {
             const MateJobQuery q = mate_job_query_d(jobs[k], reads->codes, reads->offsets, opt->a, opt->min_seed_len);
             MateJobRes o; o.score = 0; o.te = -1; o.qe = -1; o.score2 = -1; o.te2 = -1; o.tb = -1; o.qb = -1; o.valid = 0;
-            if (q.l_ms <= 32 * 16 - 15) {
+            if (ksw_lane_fits_d(q.l_ms, BM2_KSW_CMAX) && ksw_scan_ok_d(opt->e_ins, q.l_ms)) {
                 int32_t o7[7];
                 emul_ksw_warp_align2_q(q.l_ms, q.q, q.stride, q.comp, q.tlen, idx->ref_string + jobs[k].rb, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, q.xtra, o7);
                 o.score = o7[0]; o.te = o7[1]; o.qe = o7[2]; o.score2 = o7[3]; o.te2 = o7[4]; o.tb = o7[5]; o.qb = o7[6]; o.valid = 1;
