@@ -1,0 +1,25 @@
+#!/bin/bash
+# First GPU call of round 2 (everything named here was written or changed after round 1's last GPU minute).
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/gpurun_r2_first.sh'
+# Order: the proven suite first, the never-run kernels last and in their own processes (a device fault there must not take the rest along);
+# every step writes its own log, summaries only in gpurun_out/ (64 MiB limit: .ncu-rep files stay in /tmp).
+mkdir -p gpurun_out
+export PYTHONDONTWRITEBYTECODE=1
+# 1. the whole GPU suite (xfail marks of the never-run files are non-strict: XPASS = they run)
+( timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider -rxX 2>&1 | tail -60 ) > gpurun_out/r2a_tests_gpu.log 2>&1
+# 2. the never-run kernels with their assertions live (--runxfail), one file per process
+( timeout 120 python -m pytest tests/test_zzz_ksw_gpu.py -q --runxfail -p no:cacheprovider 2>&1 | tail -40 ) > gpurun_out/r2a_ksw_first_run.log 2>&1
+( timeout 240 python -m pytest tests/test_zzz_sam_staged_gpu.py -q --runxfail -p no:cacheprovider 2>&1 | tail -40 ) > gpurun_out/r2a_sam_staged_first_run.log 2>&1
+( timeout 120 python -m pytest "tests/test_zz_sam_gpu.py::test_single_end_records_match_oracle" -q --runxfail -p no:cacheprovider 2>&1 | tail -30 ) > gpurun_out/r2a_sam_se_first_run.log 2>&1
+# 3. the headline line (the chain stage with the level-per-key tree has not been timed) and the SAM stage in both modes
+( timeout 600 python bench.py --steps 3 --warmup 3 2> gpurun_out/r2a_bench.err | tail -1 ) > gpurun_out/r2a_bench_3gbp_1gpu.json
+( timeout 600 python bench.py --workload sam --steps 2 --warmup 1 2> gpurun_out/r2a_bench_sam.err | tail -1 ) > gpurun_out/r2a_bench_sam.json
+# 4. launch list of the SAM stage: bench --workload sam runs the default mode, then the staged mode, in one process (per-launch times are
+#    cold-cache and serialised: shares, not absolutes)
+( timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'sam_|ksw_' -c 80 --csv --log-file gpurun_out/r2a_launches_sam.csv \
+    python bench.py --workload sam --steps 1 --warmup 1 > /tmp/ncu_sam_default.log 2>&1 )
+# 5. one full capture of the window-alignment kernel of the staged mode (summary only)
+( timeout 900 ncu --set full --clock-control none --import-source on -k regex:sam_ksw_jobs_kernel -c 1 -o /tmp/r2a_sam_ksw \
+    python bench.py --workload sam --steps 1 --warmup 1 > /tmp/ncu_sam_ksw.log 2>&1 ;
+  [ -f /tmp/r2a_sam_ksw.ncu-rep ] && python scripts/ncu_summary.py /tmp/r2a_sam_ksw.ncu-rep gpurun_out/r2a_sam_ksw_jobs.md 'sam_ksw_jobs_kernel (staged rescue, one window per warp)' ) > gpurun_out/r2a_ncu_sam_ksw.log 2>&1
+ls -la gpurun_out | tail -20
