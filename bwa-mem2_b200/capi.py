@@ -287,7 +287,7 @@ class Context:
         return arr(res.recs, res.n_recs, SAM_REC_DT), arr(res.xa, res.n_xa, SAM_XA_DT), arr(res.cigar, res.n_ops, "<u4"), arr(res.md, res.n_md, "u1")
 
     def set_sam_staged(self, on: int):
-        """bm2_set_sam_staged: 1 = the rescue's local alignments as a batch (one window per warp) before the per-pair kernel, 0 = inside it."""
+        """bm2_set_sam_staged: 1 / 2 = the rescue's local alignments as a batch (one window per warp / per thread) before the per-pair kernel, 0 = inside it."""
         lib().bm2_set_sam_staged.argtypes = [C.c_void_p, C.c_int]
         self._check(lib().bm2_set_sam_staged(self._ctx, int(on)), "bm2_set_sam_staged")
 

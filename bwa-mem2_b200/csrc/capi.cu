@@ -153,7 +153,7 @@ extern "C" int bm2_set_sub_batches(bm2_ctx *ctx, int k, int min_reads) {
 }
 
 extern "C" int bm2_set_sam_staged(bm2_ctx *ctx, int on) {
-    if (!ctx || on < -1 || on > 1) { if (ctx) bm2_set_error(ctx, "bm2_set_sam_staged: on in {-1, 0, 1}"); return 1; }
+    if (!ctx || on < -1 || on > 2) { if (ctx) bm2_set_error(ctx, "bm2_set_sam_staged: on in {-1, 0, 1, 2}"); return 1; }
     ctx->sam_staged = on;
     return 0;
 }

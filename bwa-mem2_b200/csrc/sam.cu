@@ -109,6 +109,39 @@ sam_ksw_jobs_kernel(KswMat25 mat, int a_match, int min_seed_len, int o_del, int 
     }
 }
 
+// stage 2, other formulation (staged mode 2): one window per THREAD over the same job table - the one-thread sweep of ksw_device.cuh (the arithmetic the
+// per-pair kernel runs, proven on the B200) with 32 windows of similar size per warp in lock step.  Per-thread scratch in global memory:
+// [3 * (max_l + 16) ints H / E / best row][lcap ints scores][lcap ints rows][tcap bytes reversed target][max_l + 1 bytes reverse complement].
+__global__ void __launch_bounds__(128)
+sam_ksw_jobs_thread_kernel(KswMat25 mat, int a_match, int min_seed_len, int o_del, int e_del, int o_ins, int e_ins, const uint8_t *__restrict__ ref, int64_t ref_len,
+                           const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, int n_reads, const MateJob *__restrict__ jobs, const SamStats *stats,
+                           unsigned int job_cap, uint8_t *scratch, size_t per_thread, int max_l, int lcap, int tcap, MateJobRes *res)
+{
+    __shared__ int8_t smat[32];
+    if (threadIdx.x < 25) smat[threadIdx.x] = mat.m[threadIdx.x];
+    __syncthreads();
+    const unsigned int n = stats->n_jobs < job_cap ? stats->n_jobs : job_cap;
+    const unsigned int T = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint8_t *mine = scratch + (size_t) t * per_thread;
+    int32_t *ksw = (int32_t *) mine, *bsc = ksw + 3 * (max_l + 16), *bpos = bsc + lcap;
+    uint8_t *tmp = (uint8_t *) (bpos + lcap), *rev = tmp + tcap;
+    for (unsigned int k = t; k < n; k += T) {
+        const MateJob jb = jobs[k];
+        MateJobRes o; o.score = 0; o.te = -1; o.qe = -1; o.score2 = -1; o.te2 = -1; o.tb = -1; o.qb = -1; o.valid = 0;
+        if (jb.pair >= 0 && 2LL * jb.pair + 1 < n_reads && jb.rb >= 0 && jb.re <= ref_len && jb.rb < jb.re) {
+            const MateJobQuery q = mate_job_query_d(jb, codes, offs, a_match, min_seed_len);
+            if (q.l_ms > 0 && q.l_ms <= max_l && q.tlen <= tcap && q.tlen / 2 + 2 <= lcap) {
+                const uint8_t *seq = q.q;
+                if (q.comp) { for (int i = 0; i < q.l_ms; ++i) { const uint8_t b = q.q[-i]; rev[i] = b < 4 ? 3 - b : 4; } seq = rev; }      // q.q = the mate's last base
+                int overflow = 0;
+                const KswRes al = ksw_align2_d(q.l_ms, seq, q.tlen, ref + jb.rb, smat, o_del, e_del, o_ins, e_ins, q.xtra, ksw, bsc, bpos, lcap, tmp, &overflow);
+                o.score = al.score; o.te = al.te; o.qe = al.qe; o.score2 = al.score2; o.te2 = al.te2; o.tb = al.tb; o.qb = al.qb; o.valid = overflow ? 0 : 1;
+            }
+        }
+        res[k] = o;
+    }
+}
+
 __global__ void __launch_bounds__(64)
 sam_kernel(SamParams p, SamTables tb, ContigView cv, MatePes pes, int max_matesw, int rescue, const uint8_t *__restrict__ ref,
            const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, const bm2_alnreg_t *__restrict__ regs, const int64_t *__restrict__ reg_off,
@@ -261,8 +294,8 @@ int run_sam(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs,
     ContigView cv; cv.l_pac = ctx->idx.l_pac; cv.n_seqs = ctx->idx.n_seqs; cv.ann_off = ctx->idx.ann_off; cv.ann_len = ctx->idx.ann_len; cv.ann_alt = ctx->idx.ann_alt;
     const int rescue = paired && !(o.flag & 0x20);
     int staged = ctx->sam_staged;
-    if (staged < 0) { const char *e = getenv("BM2_SAM_STAGED"); staged = e && atoi(e) > 0; }
-    staged = staged && rescue;
+    if (staged < 0) { const char *e = getenv("BM2_SAM_STAGED"); staged = e ? atoi(e) : 0; if (staged < 0 || staged > 2) staged = 0; }
+    if (!rescue) staged = 0;
     for (double &v : ctx->sam_ms) v = 0;
     for (unsigned long long &v : ctx->sam_counts) v = 0;
     ctx->sam_counts[0] = (unsigned long long) staged;
@@ -342,16 +375,27 @@ int run_sam(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs,
             BM2_CUDA_OK(cudaGetLastError());
             BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[1], st));
             KswMat25 m25; memcpy(m25.m, o.mat, 25);
-            // the kernel instance whose lanes hold the longest read of the batch; longer reads than any instance holds are aligned in place
+            if (staged == 2) {               // one window per thread: per-thread scratch instead of per-warp lists
+                const int tcap = mate_window_max_d(pes, max_l) + 16;
+                const size_t per_thread = sam_align16_d((size_t) 3 * (max_l + 16) * 4 + (size_t) 2 * lcap * 4 + (size_t) tcap + (size_t) max_l + 1);
+                int tblocks = ctx->n_sm * 8;
+                while (tblocks > ctx->n_sm && (size_t) tblocks * 128 * per_thread > ((size_t) 4 << 30)) tblocks >>= 1;
+                if (ctx->ensure(ctx->d[SJ_LISTS], (size_t) tblocks * 128 * per_thread + 16)) return 1;
+                sam_ksw_jobs_thread_kernel<<<(unsigned) tblocks, 128, 0, st>>>(m25, o.a, o.min_seed_len, o.o_del, o.e_del, o.o_ins, o.e_ins, ctx->idx.ref, 2 * ctx->idx.l_pac,
+                              P<uint8_t>(ctx, SB_CODES), P<int64_t>(ctx, SB_OFFS), nr, P<MateJob>(ctx, SJ_JOBS), P<SamStats>(ctx, SJ_STATS), job_cap,
+                              P<uint8_t>(ctx, SJ_LISTS), per_thread, max_l, lcap, tcap, P<MateJobRes>(ctx, SJ_RES));
+            } else {
+                // the kernel instance whose lanes hold the longest read of the batch; longer reads than any instance holds are aligned in place
 #define BM2_SAM_KSW_LAUNCH(T) sam_ksw_jobs_kernel<T><<<(unsigned) ksw_blocks, 128, 0, st>>>(m25, o.a, o.min_seed_len, o.o_del, o.e_del, o.o_ins, o.e_ins, ctx->idx.ref, \
-                              2 * ctx->idx.l_pac, P<uint8_t>(ctx, SB_CODES), P<int64_t>(ctx, SB_OFFS), nr, P<MateJob>(ctx, SJ_JOBS), P<SamStats>(ctx, SJ_STATS), \
-                              job_cap, P<int32_t>(ctx, SJ_LISTS), lcap, P<MateJobRes>(ctx, SJ_RES))
-            switch (ksw_kernel_width_d(max_l)) {
-            case 5: BM2_SAM_KSW_LAUNCH(5); break;
-            case 8: BM2_SAM_KSW_LAUNCH(8); break;
-            default: BM2_SAM_KSW_LAUNCH(BM2_KSW_CMAX); break;
-            }
+                                  2 * ctx->idx.l_pac, P<uint8_t>(ctx, SB_CODES), P<int64_t>(ctx, SB_OFFS), nr, P<MateJob>(ctx, SJ_JOBS), P<SamStats>(ctx, SJ_STATS), \
+                                  job_cap, P<int32_t>(ctx, SJ_LISTS), lcap, P<MateJobRes>(ctx, SJ_RES))
+                switch (ksw_kernel_width_d(max_l)) {
+                case 5: BM2_SAM_KSW_LAUNCH(5); break;
+                case 8: BM2_SAM_KSW_LAUNCH(8); break;
+                default: BM2_SAM_KSW_LAUNCH(BM2_KSW_CMAX); break;
+                }
 #undef BM2_SAM_KSW_LAUNCH
+            }
             BM2_CUDA_OK(cudaGetLastError());
         } else BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[1], st));
         BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[2], st));

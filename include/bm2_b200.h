@@ -317,10 +317,11 @@ int bm2_sam_se(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *re
  * listed for all pairs of a wave from the regions before any rescue, aligned as one batch with one window per warp (the job shape of
  * bm2_ksw_align2; the reference batches the same alignments across pairs in its kswv path, src/bwamem_pair.cpp:930-1248, src/kswv.cpp),
  * and the per-pair logic looks them up - it still computes an alignment itself when an earlier rescue of the pair moved the window.
- * on = 1 / 0; -1 (default) leaves the choice to the BM2_SAM_STAGED environment variable (unset: off, until the path has GPU numbers). */
+ * on = 0: off; 1: one window per warp (the row of a window split over 32 lanes); 2: one window per thread (the one-thread sweep of the per-pair
+ * logic, 32 windows per warp); -1 (default) leaves the choice to the BM2_SAM_STAGED environment variable (unset: off, until the path has GPU numbers). */
 int bm2_set_sam_staged(bm2_ctx *ctx, int on);
 /* Device times and counters of the last bm2_sam_pe / bm2_sam_se call.  ms[0..3] (CUDA events, summed over waves): job listing, window
- * alignments (both 0 when not staged), the per-pair kernel, the gather.  counts[0..5]: staged (0/1), jobs listed, alignments looked up,
+ * alignments (both 0 when not staged), the per-pair kernel, the gather.  counts[0..5]: staged mode (0/1/2), jobs listed, alignments looked up,
  * alignments computed in place by the per-pair kernel (staged mode only), of those the ones whose window had moved, waves.  n_ms >= 4, n_counts >= 6. */
 int bm2_last_sam_stats(const bm2_ctx *ctx, double *ms, unsigned long long *counts, int n_ms, int n_counts);
 

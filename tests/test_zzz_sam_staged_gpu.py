@@ -1,5 +1,5 @@
 """GPU parity of the STAGED mate rescue of bm2_sam_pe (bm2_set_sam_staged: sam_jobs_kernel lists the windows, sam_ksw_jobs_kernel aligns
-them one window per warp, the per-pair kernel looks them up): the same records as the unmodified reference's SAM on C0, as the default
+them one window per warp - or, mode 2, sam_ksw_jobs_thread_kernel one window per thread -, the per-pair kernel looks them up): the same records as the unmodified reference's SAM on C0, as the default
 mode on the flag variants, and as the oracle on the tandem-repeat pairs.  Written after the round's GPU minutes were spent: non-strict xfail until it
 has run once (the same split is checked on the host: tests/test_oracle_sam_pe.py::test_staged_rescue_equals_the_per_pair_block).
 Named to run after every other file - a fault in kernels that have never run must not take later tests with it."""
@@ -25,25 +25,30 @@ def _run(capi, idx, opt, codes, offs, staged, pes=None):
     return out, st, (regs, ro, pes)
 
 
-def test_staged_records_match_reference_golden(c0, golden_dir):
+MODES = pytest.mark.parametrize("mode", [1, 2], ids=["warp_per_window", "thread_per_window"])
+
+
+@MODES
+def test_staged_records_match_reference_golden(c0, golden_dir, mode):
     capi, idx, reads, codes, offs, names = c0
     opt = capi.default_opt(); opt.flag |= 0x2
-    (recs, xa, cig, md), st, _ = _run(capi, idx, opt, codes, offs, 1)
+    (recs, xa, cig, md), st, _ = _run(capi, idx, opt, codes, offs, mode)
     lines = [ln.rstrip("\n") for ln in open(golden_dir + "/c0.sam") if not ln.startswith("@")]
     tp._compare(tp.fields(recs, cig, md, names), tp.parse_sam(lines))
     assert _xa_strings(recs, xa, cig, names) == tp.xa_of_lines(lines)
     # the batch held what the pairs asked for (the host emulation of the same split: 0 in place on C0)
-    assert st["staged"] == 1 and st["jobs"] > 50 and st["looked_up"] > 50 and st["looked_up"] <= st["jobs"], st
+    assert st["staged"] == mode and st["jobs"] > 50 and st["looked_up"] > 50 and st["looked_up"] <= st["jobs"], st
     assert st["in_place"] == 0 and st["window_moved"] == 0, st
 
 
+@MODES
 @pytest.mark.parametrize("flags", [0x8, 0x10, 0x4, 0x200, 0x1800], ids=["all", "no_multi", "no_pairing", "softclip", "primary5"])
-def test_staged_equals_default_mode_with_flags(c0, flags):
+def test_staged_equals_default_mode_with_flags(c0, flags, mode):
     capi, idx, reads, codes, offs, names = c0
     opt = capi.default_opt(); opt.flag |= 0x2 | flags
     a, st_a, _ = _run(capi, idx, opt, codes, offs, 0)
-    b, st_b, _ = _run(capi, idx, opt, codes, offs, 1)
-    assert st_a["staged"] == 0 and st_a["jobs"] == 0 and st_b["staged"] == 1 and st_b["jobs"] > 0
+    b, st_b, _ = _run(capi, idx, opt, codes, offs, mode)
+    assert st_a["staged"] == 0 and st_a["jobs"] == 0 and st_b["staged"] == mode and st_b["jobs"] > 0
     for x, y in zip(a, b):
         assert x.dtype == y.dtype and x.tobytes() == y.tobytes()
 
@@ -58,7 +63,8 @@ def test_staged_no_rescue_flag_lists_nothing(c0):
         assert x.tobytes() == y.tobytes()
 
 
-def test_staged_tandem_repeat_pairs_match_oracle(pkg, golden_dir):
+@MODES
+def test_staged_tandem_repeat_pairs_match_oracle(pkg, golden_dir, mode):
     """Hundreds of regions per read, up to max_matesw anchors per read: long job lists per pair, windows that move after earlier rescues."""
     capi = pkg.capi
     idx = capi.Index(golden_dir + "/tandem_index/ref.fa")
@@ -68,12 +74,12 @@ def test_staged_tandem_repeat_pairs_match_oracle(pkg, golden_dir):
         pes = np.zeros(4, capi.PESTAT_DT)
         pes["failed"] = 1
         pes[1] = (100, 700, 0, 0, 400.0, 80.0)
-        (recs, xa, cig, md), st, (regs, ro, _) = _run(capi, idx, opt, codes, offs, 1, pes=pes)
+        (recs, xa, cig, md), st, (regs, ro, _) = _run(capi, idx, opt, codes, offs, mode, pes=pes)
         lh = np.array([v for d in range(4) for v in (pes[d]["low"], pes[d]["high"], pes[d]["failed"])], np.int32)
         as_ = np.array([v for d in range(4) for v in (pes[d]["avg"], pes[d]["std"])], np.float64)
         want = tp.oracle_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_)
         names = ["tr1", "tr2"]
         tp._compare(tp.fields(recs, cig, md, names), tp.fields(*want, names))
-        assert st["staged"] == 1
+        assert st["staged"] == mode
     finally:
         idx.close()
