@@ -1,5 +1,5 @@
-// ksw_warp.cuh — the local alignment of mate rescue, one WINDOW PER WARP (groundwork for the second version of seam 4: sam.cu still
-// runs ksw_device.cuh's one-thread sweep; nothing launches this yet).
+// ksw_warp.cuh — the local alignment of mate rescue, one WINDOW PER WARP.  Launched by ksw.cu (bm2_ksw_align2, a batch of requests) and by sam.cu's
+// staged rescue (sam_ksw_jobs_kernel); the per-pair kernel's own fallback stays ksw_device.cuh's one-thread sweep.
 //
 // Same function as ksw_pass_d (ksw_device.cuh: the reference's striped ksw_u8 / ksw_i16, src/ksw.cpp:111-316, with its first-pass E /
 // row maximum and its padding).  There a row is one sequential sweep over the query with two insertion registers: F of the segment

@@ -1,4 +1,4 @@
-// mate_device.cuh — mate rescue of ONE read pair (device logic, groundwork for SURVEY §8(f) item 1: no kernel launches this yet).
+// mate_device.cuh — mate rescue of ONE read pair (device logic of SURVEY §8(f) item 1; launched by sam.cu's per-pair kernel, staged form in mate_stage.cuh).
 //
 // Replaces the rescue block of mem_sam_pe (reference src/bwamem_pair.cpp:378-412, MATE_SORT == 0) and mem_matesw (:150-283):
 // for the best alignments of each read, align the mate inside the window the insert-size statistics predict (ksw_align2,

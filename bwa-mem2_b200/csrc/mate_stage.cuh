@@ -54,6 +54,15 @@ BM2_HD MateJobQuery mate_job_query_d(const MateJob &jb, const uint8_t *codes, co
     return o;
 }
 
+// one window by one thread (staged mode 2): the contiguous query ksw_align2_d wants (the reverse complement built in rev) and the one-thread sweep
+BM2_HD KswRes mate_job_align_thread_d(const MateJobQuery &q, const uint8_t *target, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
+                                      int32_t *ksw, int32_t *bsc, int32_t *bpos, int bcap, uint8_t *tmp, uint8_t *rev, int *overflow)
+{
+    const uint8_t *seq = q.q;
+    if (q.comp) { for (int i = 0; i < q.l_ms; ++i) { const uint8_t b = q.q[-i]; rev[i] = b < 4 ? 3 - b : 4; } seq = rev; }      // q.q = the mate's last base
+    return ksw_align2_d(q.l_ms, seq, q.tlen, target, mat, o_del, e_del, o_ins, e_ins, q.xtra, ksw, bsc, bpos, bcap, tmp, overflow);
+}
+
 // The provider of the local alignment for mate_rescue_pair_d in the staged form: the pair's slice of the job table, else the computation
 // in place (a window that moved because an earlier rescue of the pair changed the regions, a job that was not listed or not computed).
 struct MateKswTable {

@@ -131,10 +131,8 @@ sam_ksw_jobs_thread_kernel(KswMat25 mat, int a_match, int min_seed_len, int o_de
         if (jb.pair >= 0 && 2LL * jb.pair + 1 < n_reads && jb.rb >= 0 && jb.re <= ref_len && jb.rb < jb.re) {
             const MateJobQuery q = mate_job_query_d(jb, codes, offs, a_match, min_seed_len);
             if (q.l_ms > 0 && q.l_ms <= max_l && q.tlen <= tcap && q.tlen / 2 + 2 <= lcap) {
-                const uint8_t *seq = q.q;
-                if (q.comp) { for (int i = 0; i < q.l_ms; ++i) { const uint8_t b = q.q[-i]; rev[i] = b < 4 ? 3 - b : 4; } seq = rev; }      // q.q = the mate's last base
                 int overflow = 0;
-                const KswRes al = ksw_align2_d(q.l_ms, seq, q.tlen, ref + jb.rb, smat, o_del, e_del, o_ins, e_ins, q.xtra, ksw, bsc, bpos, lcap, tmp, &overflow);
+                const KswRes al = mate_job_align_thread_d(q, ref + jb.rb, smat, o_del, e_del, o_ins, e_ins, ksw, bsc, bpos, lcap, tmp, rev, &overflow);
                 o.score = al.score; o.te = al.te; o.qe = al.qe; o.score2 = al.score2; o.te2 = al.te2; o.tb = al.tb; o.qb = al.qb; o.valid = overflow ? 0 : 1;
             }
         }

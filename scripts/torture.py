@@ -92,14 +92,16 @@ def main():
         assert em[3] == tp.xa_of_lines(twant), "XA entries differ from the reference's tags"
         sam_dev = "== oracle, XA == reference"
         import ctypes as C, test_oracle_sam_se as ts
-        L = tp._emul(); L.emul_sam_set_staged(1)                # the staged rescue: batch of local alignments (warp formulation) + lookup
-        try:
-            em2 = tp.emul_sam_pe(capi, idx, opt2, codes, offs, regs, ro, lh, as_)
-            st = (C.c_longlong * 4)(); L.emul_sam_stage_stats(st)
-        finally:
-            L.emul_sam_set_staged(0)
-        assert all(np.array_equal(x, y) for x, y in zip(em2[:3], em[:3])), "staged rescue differs"
-        sam_dev += f"; staged rescue identical (batch {st[0]}, used {st[1]}, computed in place {st[2]}, window moved {st[3]})"
+        L = tp._emul()
+        for mode, what in ((1, "warp per window"), (2, "thread per window")):      # the staged rescue: job table + batch of local alignments + lookup
+            L.emul_sam_set_staged(mode)
+            try:
+                em2 = tp.emul_sam_pe(capi, idx, opt2, codes, offs, regs, ro, lh, as_)
+                st = (C.c_longlong * 4)(); L.emul_sam_stage_stats(st)
+            finally:
+                L.emul_sam_set_staged(0)
+            assert all(np.array_equal(x, y) for x, y in zip(em2[:3], em[:3])), "staged rescue differs"
+            sam_dev += f"; staged rescue ({what}) identical (batch {st[0]}, looked up {st[1]}, computed in place {st[2]}, of those window moved {st[3]})"
         al, oc, om = ts.oracle_sam_se(capi, idx, opt, codes, offs, regs, ro)                      # every read as a single-end read
         assert ts.rec_fields(*ts.emul_sam_se(capi, idx, opt, codes, offs, regs, ro), names) == ts.sam_fields(al, oc, om, names, soft_clip_all=bool(opt.flag & 0x200)), "single-end differs"
         sam_dev += "; single-end device logic == oracle"

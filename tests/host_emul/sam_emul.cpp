@@ -80,7 +80,16 @@ extern "C" int emul_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, 
         for (size_t k = 0; k < jobs.size(); ++k) {
             const MateJobQuery q = mate_job_query_d(jobs[k], reads->codes, reads->offsets, opt->a, opt->min_seed_len);
             MateJobRes o; o.score = 0; o.te = -1; o.qe = -1; o.score2 = -1; o.te2 = -1; o.tb = -1; o.qb = -1; o.valid = 0;
-            if (ksw_lane_fits_d(q.l_ms, BM2_KSW_CMAX) && ksw_scan_ok_d(opt->e_ins, q.l_ms)) {
+            if (g_staged == 2) {             // one window per thread (sam_ksw_jobs_thread_kernel): the same function, the same scratch shapes
+                const int lcap = q.tlen / 2 + 2;
+                std::vector<int32_t> ksw((size_t) 3 * (q.l_ms + 16)), bsc((size_t) lcap), bpos((size_t) lcap);
+                std::vector<uint8_t> tmp((size_t) q.tlen + 16), rev((size_t) q.l_ms + 1);
+                int ov = 0;
+                const KswRes al = mate_job_align_thread_d(q, idx->ref_string + jobs[k].rb, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, ksw.data(), bsc.data(),
+                                                          bpos.data(), lcap, tmp.data(), rev.data(), &ov);
+                o.score = al.score; o.te = al.te; o.qe = al.qe; o.score2 = al.score2; o.te2 = al.te2; o.tb = al.tb; o.qb = al.qb; o.valid = ov ? 0 : 1;
+                ++g_stage_stats[0];
+            } else if (ksw_lane_fits_d(q.l_ms, BM2_KSW_CMAX) && ksw_scan_ok_d(opt->e_ins, q.l_ms)) {
                 int32_t o7[7];
                 emul_ksw_warp_align2_q(q.l_ms, q.q, q.stride, q.comp, q.tlen, idx->ref_string + jobs[k].rb, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, q.xtra, o7);
                 o.score = o7[0]; o.te = o7[1]; o.qe = o7[2]; o.score2 = o7[3]; o.te2 = o7[4]; o.tb = o7[5]; o.qb = o7[6]; o.valid = 1;

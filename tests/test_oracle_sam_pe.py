@@ -293,7 +293,8 @@ def xa_of_lines(lines):
     return out
 
 
-def test_staged_rescue_equals_the_per_pair_block(c0):
+@pytest.mark.parametrize("mode", [1, 2], ids=["warp_per_window", "thread_per_window"])
+def test_staged_rescue_equals_the_per_pair_block(c0, mode):
     """The shape of the next kernel version: the rescue's local alignments enumerated from the regions before any rescue, computed as a
     batch by the warp formulation (ksw_warp.cuh), looked up by the per-pair block.  Same records; the batch must hold what is asked for."""
     capi, idx, reads, codes, offs, names = c0
@@ -302,7 +303,7 @@ def test_staged_rescue_equals_the_per_pair_block(c0):
     lh, as_ = _pestat(capi, idx, opt, reads, regs, ro)
     want = emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_)
     L = _emul()
-    L.emul_sam_set_staged(1)
+    L.emul_sam_set_staged(mode)
     try:
         got = emul_sam_pe(capi, idx, opt, codes, offs, regs, ro, lh, as_)
         st = (C.c_longlong * 4)(); L.emul_sam_stage_stats(st)
