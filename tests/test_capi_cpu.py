@@ -53,3 +53,14 @@ def test_no_cpu_fallback(pkg):
     with pytest.raises(pkg.capi.Bm2Error) as e:
         pkg.capi.Context(0)
     assert "no CPU fallback" in str(e.value)
+
+
+def test_sam_stage_switches_validate_their_arguments(pkg):
+    """bm2_set_sam_staged / bm2_last_sam_stats: host-only entries; without a context they return an error code, nothing runs."""
+    lib = pkg.capi.lib()
+    lib.bm2_set_sam_staged.argtypes = [C.c_void_p, C.c_int]
+    lib.bm2_last_sam_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    assert lib.bm2_set_sam_staged(None, 1) == 1
+    ms = (C.c_double * 4)(); cnt = (C.c_ulonglong * 6)()
+    assert lib.bm2_last_sam_stats(None, ms, cnt, 4, 6) == 1
+    assert {"bm2_set_sam_staged", "bm2_last_sam_stats"} <= set(pkg.capi.EXPORTS)
