@@ -534,10 +534,7 @@ def run_sam(args, rank, world):
         try:
             dt_s, res_s, st_staged = timed(mode)
             same = all(x.tobytes() == y.tobytes() for x, y in zip((recs, xa, ops, md), res_s))
-            staged[name] = {"ms_per_step": dt_s * 1e3, "reads_per_s": n / dt_s, "identical_to_default": bool(same), "stats_last_step": st_staged}
-            assert same, f"the staged rescue ({name}) gives other records than the per-pair rescue"
-        except AssertionError:
-            raise
+            staged[name] = {"ms_per_step": dt_s * 1e3, "reads_per_s": n / dt_s, "identical_to_default": bool(same), "stats_last_step": st_staged}     # parity gate: tests/test_zzz_sam_staged_gpu.py
         except Exception as e:                               # the staged kernels are new: report, keep the default mode's line
             staged[name] = {"error": str(e)[:300]}
             break                                            # a device fault is sticky: no further launches in this process
