@@ -39,9 +39,56 @@ def _refbin(name):
     return p
 
 
+def _cgroup_cpu_limit():
+    """CPU quota of this process's cgroup in cores (None = unlimited / unknown); v2 cpu.max, v1 cfs_quota/period."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / per
+    except Exception:
+        return None
+
+
 def host_threads():
+    """Threads for the reference arm: the cores this process may really use (affinity, cgroup quota), at most 128
+    (the reference's tprof[][] is 128 columns wide, src/macro.h LIM_C)."""
     n = len(os.sched_getaffinity(0))
-    return max(1, min(n, 128))      # reference tprof[][] is 128 columns wide (src/macro.h LIM_C)
+    q = _cgroup_cpu_limit()
+    if q is not None:
+        n = min(n, max(1, int(q + 0.5)))
+    return max(1, min(n, 128))
+
+
+def host_info(probe=True):
+    """What the CPU arm ran on: model, logical CPUs, affinity, cgroup quota, load, and the MEASURED parallel capacity
+    (oracle/libbm2oracle.so:bm2o_cpu_probe - rate of a fixed integer loop on n threads / rate on 1 thread)."""
+    info = {"cpu_model": None, "logical_cpus": os.cpu_count(), "affinity": len(os.sched_getaffinity(0)),
+            "cgroup_cpu_max": _cgroup_cpu_limit(), "threads_used": host_threads(), "isa": _isa()}
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                info["cpu_model"] = ln.split(":", 1)[1].strip(); break
+        info["loadavg_1min"] = float(open("/proc/loadavg").read().split()[0])
+    except Exception:
+        pass
+    if probe:
+        try:
+            import ctypes as C
+            L = C.CDLL(os.path.join(ROOT, "oracle", "libbm2oracle.so")); L.bm2o_cpu_probe.restype = C.c_double
+            r1 = L.bm2o_cpu_probe(1, C.c_double(0.25)); rn = L.bm2o_cpu_probe(info["threads_used"], C.c_double(0.5))
+            info["effective_cores"] = round(rn / r1, 1) if r1 > 0 else None
+            info["effective_cores_how"] = f"integer-loop rate on {info['threads_used']} threads / rate on 1 thread (0.5 s)"
+        except Exception as e:
+            info["effective_cores"] = None; info["effective_cores_how"] = f"probe failed: {e!r}"
+    return info
+
+
+METRIC_BSW = "paired 151bp reads/s (BSW extension only, seeds from the reference CPU path)"
+METRIC = "paired 151bp reads/s (seed+chain+extend hot path)"      # the SAME string in both arms: the driver compares them
 
 
 class ClockSampler:
@@ -210,7 +257,7 @@ def run_bsw(args, rank, world):
         # CPU baseline: the reference's own AVX-512 BSW calls timed by ref_driver on this host (1 thread)
         cpu = {"value": st["reads"] / st["t_bsw"], "unit": "reads/s", "cores": 1, "kind": "reference",
                "sample": f"{st['bsw_pairs']} extension jobs of {st['reads']} reads, reference getScores8/16 ({_isa()}), 1 thread"}
-        out = {"metric": "paired 151bp reads/s (BSW extension only, seeds from the reference CPU path)", "value": value,
+        out = {"metric": METRIC_BSW, "value": value,
                "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
                "config": {"workload": f"config[1]-like: BSW kernel only; {reads_per_step} reads/step/GPU = {n} extension jobs "
@@ -262,9 +309,11 @@ def prepare_pipeline_inputs(work, ref_bp, n_pairs, seed):
     return fa
 
 
-def reference_hotpath(work, fa, n_pairs_sample, threads, steps=1, warmup=0):
+def reference_hotpath(work, fa, n_pairs_sample, threads, steps=1, warmup=0, dump_regs=None):
     """reads/s of the unmodified reference's worker_bwt + worker_aln (ref_driver BM2_MODE=hotpath) on the first
-    n_pairs_sample pairs."""
+    n_pairs_sample pairs: ONE process (one index load), warmup + steps repetitions of the two kt_for phases inside it
+    (BM2_REPEAT), each timed alone.  dump_regs: file that receives the reference's regs of those reads (parity of the
+    bench workload against the reference itself).  -> (mean reads/s over the timed repetitions, per-repetition list, stats)."""
     r1 = os.path.join(work, "r1.fq"); r2 = os.path.join(work, "r2.fq")
     s1 = os.path.join(work, f"s1_{n_pairs_sample}.fq"); s2 = os.path.join(work, f"s2_{n_pairs_sample}.fq")
     if not os.path.exists(s1):
@@ -272,16 +321,29 @@ def reference_hotpath(work, fa, n_pairs_sample, threads, steps=1, warmup=0):
         for src, dst in ((r1, s1), (r2, s2)):
             with open(src, "rb") as f, open(dst, "wb") as o:
                 o.write(f.read(rec * n_pairs_sample))
-    vals = []
-    for i in range(warmup + steps):
-        stats = os.path.join(work, "stats_ref.json")
-        env = dict(os.environ, BM2_MODE="hotpath", BM2_STATS=stats)
-        subprocess.check_call([_refbin("ref_driver"), "mem", "-t", str(threads), "-K", "1000000000", fa, s1, s2],
-                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
-        st = json.load(open(stats))
-        if i >= warmup:
-            vals.append(st["reads"] / (st["t_bwt"] + st["t_aln"]))
-    return float(np.mean(vals)), st
+    stats = os.path.join(work, "stats_ref.json")
+    env = dict(os.environ, BM2_MODE="hotpath", BM2_STATS=stats, BM2_REPEAT=str(warmup + steps))
+    if dump_regs:
+        env["BM2_DUMP_REGS"] = dump_regs
+    subprocess.check_call([_refbin("ref_driver"), "mem", "-t", str(threads), "-K", "1000000000", fa, s1, s2],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
+    st = json.load(open(stats))
+    reps = st.get("rep_s") or [st["t_bwt"] + st["t_aln"]]
+    vals = [st["reads"] / t for t in reps[warmup:]]
+    return float(np.mean(vals)), vals, st
+
+
+def check_against_reference_dump(regs, ro, dump_path, n_reads):
+    """Every field of every alignment region of the first n_reads reads == the unmodified reference's own regs
+    (ref_driver BM2_DUMP_REGS).  Raises on a difference."""
+    import refdump, oracle_lib as ol
+    d_regs, d_off = refdump.read_regs(dump_path)
+    assert len(d_off) == n_reads + 1, f"reference dump holds {len(d_off) - 1} reads, expected {n_reads}"
+    bad = ol.regs_equal_to_dump(regs[:ro[n_reads]], ro[:n_reads + 1], d_regs, d_off)
+    if bad or len(d_regs) != ro[n_reads]:
+        raise AssertionError(f"bench workload: GPU regs differ from the unmodified reference on reads {bad[:10]} "
+                             f"({ro[n_reads]} vs {len(d_regs)} regs)")
+    return int(len(d_regs))
 
 
 def run_pipeline(args, rank, world):
@@ -293,18 +355,9 @@ def run_pipeline(args, rank, world):
     torch.cuda.set_device(dev)
     work = os.path.join(tempfile.gettempdir(), f"bm2_bench_pipe_{args.ref_mbp}_{args.pairs}")
     if rank == 0:
-        try:
-            prepare_pipeline_inputs(work, args.ref_mbp * 1_000_000, args.pairs, seed=21)
-        except Exception as e:      # never lose the bench line to input preparation: fall back to a reference-built 100 Mbp index
-            if args.ref_mbp <= 400:
-                raise
-            sys.stderr.write(f"[bench] preparing the {args.ref_mbp} Mbp inputs failed ({e!r}); falling back to 100 Mbp\n")
-            args.ref_mbp = 100
-            work = os.path.join(tempfile.gettempdir(), f"bm2_bench_pipe_{args.ref_mbp}_{args.pairs}")
-            prepare_pipeline_inputs(work, args.ref_mbp * 1_000_000, args.pairs, seed=21)
+        prepare_pipeline_inputs(work, args.ref_mbp * 1_000_000, args.pairs, seed=21)     # a failure here fails the bench (no smaller stand-in)
     if world > 1:
-        mb = torch.tensor([args.ref_mbp], device="cuda"); torch.distributed.broadcast(mb, 0); args.ref_mbp = int(mb.item())
-        work = os.path.join(tempfile.gettempdir(), f"bm2_bench_pipe_{args.ref_mbp}_{args.pairs}")
+        torch.distributed.barrier()
     fa = os.path.join(work, "ref.fa")
     reads = np.load(os.path.join(work, "reads.npy"))
     if rank:   # weak scaling: every rank aligns its own batch (a rotation of the same read set)
@@ -328,8 +381,10 @@ def run_pipeline(args, rank, world):
         assert np.array_equal(o_one, o_sub) and r_one.tobytes() == r_sub.tobytes(), "sub-batches in flight differ from the unsplit batch"
         del r_one, r_sub
     int_gops = ctx.int_pipe_gops()
-    gather_gbs = ctx.gather64_gbs()
-    gather_by_span = {f"{mb}MB": round(ctx.gather64_gbs(mb << 20), 1) for mb in (32, 256, 1024, 4096)}
+    # random-gather probes over the Occ table: request shape (64 B as 4 x 16 B loads / 32 B as one 256-bit load / 64 B as two) x
+    # requests in flight per thread, inside L2 (32 MB span) and over 4 GB: separates DRAM, request-rate and latency limits
+    gather_by_span = {f"{mb}MB_{nm}_mlp{k}": round(ctx.gather_probe(mb << 20, k, sh), 1)
+                      for mb in (32, 4096) for sh, nm in ((0, "64B_4x16"), (1, "32B_1x256"), (2, "64B_2x256")) for k in (1, 4, 8)}
     index_how = "built by the reference binary" if args.ref_mbp <= 400 else "built on the GPU by bwa_mem2_b200.index_build, byte-identical format"
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
@@ -399,15 +454,45 @@ def run_pipeline(args, rank, world):
         alg_bytes = cnt["n_ext"] * 128.0
         achieved = alg_bytes / (smem_ms * 1e-3) / 1e9 if smem_ms > 0 else 0.0
         bsw_ms = stage_acc.get("bsw_left", 0.0) + stage_acc.get("bsw_right", 0.0)
-        nt = host_threads()
+        # CPU arm + parity against the reference ITSELF: the unmodified reference's worker_bwt + worker_aln on the first
+        # sample of the same reads (all usable host threads, one process), its regs dumped and compared field by field
+        hi = host_info()
+        nt = hi["threads_used"]
         sample_pairs = min(args.pairs, 100_000)
-        cpu_v, cpu_st = reference_hotpath(work, fa, sample_pairs, nt)
-        out = {"metric": "paired 151bp reads/s (seed+chain+extend hot path: SMEM, SA lookup, chaining, BSW, post-filter)", "value": value,
+        dump = os.path.join(work, "ref_regs.bin")
+        cpu_v, cpu_vals, cpu_st = reference_hotpath(work, fa, sample_pairs, nt, steps=3, warmup=1, dump_regs=dump)
+        n_ref_regs = check_against_reference_dump(regs, ro, dump, 2 * sample_pairs)
+        os.remove(dump)
+        # roofline objects of the two big stages; `roofline` is the one that dominates the unsplit stage times
+        gcells = cnt["cells"] / (bsw_ms * 1e-3) / 1e9 if bsw_ms > 0 else 0.0
+        ceil = {"pack1_s32": int_gops / 14.0, "pack2_s16x2": 2 * int_gops / 14.0, "pack4_s8x4": 4 * int_gops / 14.0}
+        roof_bsw = {"bound": "int_alu", "achieved": gcells, "peak": ceil["pack2_s16x2"], "unit": "Gcell/s",
+                    "frac": gcells / ceil["pack2_s16x2"] if int_gops > 0 else None, "traffic": None,
+                    "kernel": "extension stage: bsw_col2_kernel launches of bsw_left + bsw_right (incl. job bucketing, fold, doubled-band retry)",
+                    "kernel_ms": bsw_ms, "ceilings_gcell_s": {k: round(v, 1) for k, v in ceil.items()},
+                    "frac_by_ceiling": {k: (gcells / v if v > 0 else None) for k, v in ceil.items()},
+                    "note": f"cells = banded DP cells counted by the kernels; ceilings = {int_gops:.0f} G two-input int32 op/s measured in-library "
+                            "(bm2_int_pipe_gops: dependent VIADDMNMX chains on all SMs) x pack / 14 ops per cell (SURVEY 8d).  peak/frac use pack 2: the "
+                            "kernel issues s16x2 DPX instructions; pack 4 (byte SIMD) is emulated on sm_100a (profiles/r1_study_packed_simd_sass.md) "
+                            "and is listed because north_star names it"}
+        roof_smem = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": _smem_traffic(args),
+                     "kernel": "SMEM stage: smem_fwd1_kernel + smem_bwd_kernel + smem_fwd2_kernel + smem_bwd_kernel (+ smem_pass3_kernel on a side stream)",
+                     "note": "algorithmic bytes = 128 B (two 64-B Occ checkpoints) x interval extensions counted by the kernels; peak = "
+                             + ("MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback of B200_PROFILING.md")
+                             + "; traffic = DRAM read+write bytes of those kernels per step from profiles/ (ncu), null when the workload differs",
+                     "extensions_per_read": cnt["n_ext"] / n, "kernel_ms": smem_ms,
+                     "random_64B_gather_gbs_by_span_and_mlp": gather_by_span}
+        timed_how = ("one extra pass of the same batch, unsplit (stage timed alone, CUDA events inside the library)" if args.sub_batches > 1
+                     else "timed steps")
+        roof_bsw["timed"] = roof_smem["timed"] = timed_how
+        dominant = "bsw" if bsw_ms >= smem_ms else "smem"
+        out = {"metric": METRIC, "value": value,
                "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/int16", "data": "synthetic",
-               "config": {"workload": f"config[2]-like: full GPU pipeline, {n} reads/step/GPU (2x151 bp pairs, 1% subs, 25% reads with an indel, "
-                                      f"1% garbage) vs {args.ref_mbp} Mbp synthetic reference (planted repeat families; index files "
-                                      f"{index_how})",
+               "config": {"workload": f"config[2]-like: full GPU pipeline (SMEM, SA lookup, chaining, BSW, post-filter), {n} reads/step/GPU "
+                                      f"(2x151 bp pairs, 1% subs, 25% reads with an indel, 1% garbage) vs {args.ref_mbp} Mbp synthetic reference "
+                                      f"(planted repeat families; index files {index_how})",
                           "l2": "256 MB flush between steps; FM-index %d MB" % (index.desc.reference_seq_len // 64 * 64 // 1_000_000),
                           "sub_batches_in_flight": args.sub_batches,
                           "regs_per_step": int(n_regs)},
@@ -415,28 +500,19 @@ def run_pipeline(args, rank, world):
                        "d2h_bytes_per_step": int(n_out * capi.REG_DT.itemsize + offs.nbytes)},
                # our own kernels per step and sub-batch (profiles/r1n_kernel_traffic_3gbp.md: 115 launches, 48 of them cub sort/scan)
                "gpu_launches": 67 * args.steps * max(1, args.sub_batches),
-               "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                            "traffic": _smem_traffic(args),
-                            "kernel": "SMEM stage: smem_fwd1_kernel + smem_bwd_kernel + smem_fwd2_kernel + smem_bwd_kernel (+ smem_pass3_kernel on a side stream)",
-                            "note": "algorithmic bytes = 128 B (two 64-B Occ checkpoints) x interval extensions counted by the kernels; peak = "
-                                    + ("MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback of B200_PROFILING.md")
-                                    + "; traffic = DRAM read+write bytes of those kernels per step from profiles/ (ncu), null when the workload differs",
-                            "extensions_per_read": cnt["n_ext"] / n, "kernel_ms": smem_ms,
-                            "random_64B_gather_gbs": gather_gbs, "random_64B_gather_gbs_by_span": gather_by_span, "frac_of_random_gather": achieved / gather_gbs if gather_gbs > 0 else None,
-                            "timed": "one extra pass of the same batch, unsplit (stage timed alone, CUDA events inside the library)" if args.sub_batches > 1
-                                     else "timed steps"},
-               "roofline_bsw": {"bound": "int-alu", "achieved": cnt["cells"] / (bsw_ms * 1e-3) / 1e9 if bsw_ms > 0 else None,
-                                "peak": int_gops / 14.0, "unit": "Gcell/s",
-                                "frac": (cnt["cells"] / (bsw_ms * 1e-3) / 1e9) / (int_gops / 14.0) if bsw_ms > 0 else None,
-                                "note": f"banded DP cells counted by the kernels / (bsw_left + bsw_right stage time); peak = {int_gops:.0f} G two-input "
-                                        "int32 op/s measured in-library (bm2_int_pipe_gops) / 14 ops per cell (SURVEY 8d)"},
+               "roofline": dict(roof_bsw if dominant == "bsw" else roof_smem, dominant_stage=dominant),
+               "roofline_bsw": roof_bsw, "roofline_smem": roof_smem,
                "stages_ms": {k: round(v, 3) for k, v in stage_acc.items()},
                "stages_ms_sum_over_sub_batches_in_timed_steps": {k: round(v, 3) for k, v in stage_split.items()},
-               "bsw": {"gcups": cnt["cells"] / (bsw_ms * 1e-3) / 1e9 if bsw_ms > 0 else None, "cells_per_step": int(cnt["cells"]),
+               "bsw": {"gcups": gcells, "cells_per_step": int(cnt["cells"]),
                        "retry_left": int(cnt["retry_left"]), "retry_right": int(cnt["retry_right"])},
+               "parity": {"vs": "unmodified reference (ref_driver regs dump of the CPU arm's run), every field of every alignment region",
+                          "reads": 2 * sample_pairs, "regs": n_ref_regs, "identical": True,
+                          "also": f"first {ns} reads against the oracle; sub-batch path == unsplit path on {nsb} reads"},
                "cpu_baseline": {"value": cpu_v, "unit": "reads/s", "cores": nt, "kind": "reference",
                                 "sample": f"first {2 * sample_pairs} reads of the same workload, worker_bwt+worker_aln of the unmodified reference "
-                                          f"({_isa()}), {nt} threads"},
+                                          f"({_isa()}), {nt} threads, one process, mean of {len(cpu_vals)} repetitions after 1 warm-up",
+                                "per_repetition": [round(v, 1) for v in cpu_vals], "host": hi},
                "clocks": clocks, "wall_s": wall}
     ctx.close(); index.close()
     return out
@@ -482,7 +558,7 @@ def run_cigar(args, rank, world):
                       "mean_ops": float(recs["n_cigar"].mean()), "with_indels": int((recs["n_cigar"] > 1).sum())},
            "e2e": {"value": len(reqs) / dt, "unit": "alignments/s", "h2d_bytes_per_step": int(codes.nbytes + offs.nbytes + reqs.nbytes),
                    "d2h_bytes_per_step": int(recs.nbytes + ops.nbytes + md.nbytes)},
-           "gpu_launches": 2 * st_default["waves"] * args.steps,
+           "gpu_launches": 4 * args.steps,            # cigar_kernel + two scans + gather per call
            "cpu_baseline": {"value": len(sample) / t_ref, "unit": "alignments/s", "cores": 1, "kind": "reference",
                             "sample": f"the reference's bwa_gen_cigar2 (ref_driver cigar) on the first {len(sample)} requests, one host thread, index load subtracted"}}
     ctx.close(); index.close()
@@ -556,19 +632,27 @@ def run_sam(args, rank, world):
 
 
 def run_reference_pipeline(args, rank, world):
+    """--impl reference: the unmodified reference's worker_bwt + worker_aln on the host cores, same metric / config as our arm.
+    Each step = the first `sample` pairs of the same 1 M-read workload (bounded: the whole run ends within minutes); one process,
+    one index load, warmup + steps repetitions timed one by one inside it."""
     if rank != 0:
         return None
     work = os.path.join(tempfile.gettempdir(), f"bm2_bench_pipe_{args.ref_mbp}_{args.pairs}")
     fa = prepare_pipeline_inputs(work, args.ref_mbp * 1_000_000, args.pairs, seed=21)
-    nt = host_threads()
-    v, st = reference_hotpath(work, fa, args.pairs, nt, steps=args.steps, warmup=args.warmup)
-    n = 2 * args.pairs
-    return {"impl": "reference", "metric": "paired 151bp reads/s (seed+chain+extend hot path)", "value": v, "unit": "reads/s", "n_gpus": world,
+    hi = host_info()
+    nt = hi["threads_used"]
+    sample_pairs = min(args.pairs, 100_000)
+    v, vals, st = reference_hotpath(work, fa, sample_pairs, nt, steps=args.steps, warmup=args.warmup)
+    n = 2 * sample_pairs
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64/int16", "data": "synthetic",
-            "config": {"workload": f"worker_bwt + worker_aln of the unmodified reference ({_isa()}) on {n} synthetic 2x151 reads vs {args.ref_mbp} Mbp "
-                                   f"synthetic reference (same inputs as the GPU arm)"},
-            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": nt, "kind": "reference", "sample": f"{n} reads per step, kt_for over {nt} threads"},
+            "config": {"workload": f"config[2]-like: worker_bwt + worker_aln of the unmodified reference ({_isa()}) on the first {n} reads per step of the "
+                                   f"GPU arm's workload ({2 * args.pairs} synthetic 2x151 reads vs {args.ref_mbp} Mbp synthetic reference, same index files)",
+                       "sample": f"{n} reads per step (bounded sample), {nt} threads"},
+            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": nt, "kind": "reference",
+                             "sample": f"{n} reads per step, kt_for over {nt} threads, one process, {len(vals)} timed repetitions",
+                             "per_repetition": [round(x, 1) for x in vals], "host": hi},
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
@@ -589,7 +673,7 @@ def run_reference(args, rank, world):
         if i >= args.warmup:
             vals.append(st["reads"] / (st["t_bwt"] + st["t_aln"]))
     v = float(np.mean(vals))
-    return {"impl": "reference", "metric": "paired 151bp reads/s", "value": v, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+    return {"impl": "reference", "metric": METRIC_BSW, "value": v, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * 2 * args.pairs / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16", "data": "synthetic",
             "config": {"workload": f"worker_bwt + worker_aln of the unmodified reference ({_isa()}) on {2 * args.pairs} synthetic 2x151 reads "

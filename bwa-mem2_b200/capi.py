@@ -85,7 +85,7 @@ class RegResult(C.Structure):
     _fields_ = [("n", C.c_int64), ("regs", C.c_void_p), ("read_off", C.c_void_p)]
 
 
-EXPORTS = ["bm2_set_sam_staged", "bm2_last_sam_stats", "bm2_gather64_gbs", "bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
+EXPORTS = ["bm2_gather_probe", "bm2_set_sam_staged", "bm2_last_sam_stats", "bm2_gather64_gbs", "bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
            "bm2_last_error", "bm2_extend_pairs", "bm2_extend_pairs_device", "bm2_collect_smems", "bm2_seed_chain",
            "bm2_seed_chain_extend", "bm2_last_stage_ms", "bm2_gen_cigar", "bm2_pestat", "bm2_sam_pe", "bm2_sam_se", "bm2_ksw_align2"]
 
@@ -307,6 +307,13 @@ class Context:
         v = C.c_double()
         lib().bm2_gather64_gbs.argtypes = [C.c_void_p, C.c_ulonglong, C.POINTER(C.c_double)]
         self._check(lib().bm2_gather64_gbs(self._ctx, int(span_bytes), C.byref(v)), "bm2_gather64_gbs")
+        return v.value
+
+    def gather_probe(self, span_bytes: int = 0, mlp: int = 4, shape: int = 0) -> float:
+        """bm2_gather_probe: GB/s of random requests over the Occ table (shape 0: 64 B as 4 x 16 B, 1: 32 B as one 256-bit load, 2: 64 B as two)."""
+        v = C.c_double()
+        lib().bm2_gather_probe.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        self._check(lib().bm2_gather_probe(self._ctx, int(span_bytes), int(mlp), int(shape), C.byref(v)), "bm2_gather_probe")
         return v.value
 
     def set_sub_batches(self, k: int, min_reads: int = 16384):

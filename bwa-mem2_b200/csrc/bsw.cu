@@ -670,7 +670,8 @@ size_t bsw_scratch_bytes(int n) {
 }
 
 struct BswWideScratch { int2 *state; long long *state_off; long long *total; size_t cap_words; size_t cap_jobs; };
-static BswWideScratch g_wide = {nullptr, nullptr, nullptr, 0, 0};
+#define BSW_MAX_DEV 64
+static BswWideScratch g_wide_dev[BSW_MAX_DEV];      // per device ordinal (a process may hold one context per GPU), zero-initialised
 
 int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const BswJob *d_jobs, BswOut *d_out, int n,
                             const uint8_t *d_tbase, const uint8_t *d_qbase, const BswParams &prm,
@@ -700,10 +701,15 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     BM2_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, idx_in, idx_out, n, 0, 32, stream));
     bsw_class_off_kernel<<<1, 32, 0, stream>>>(class_cnt, class_off);
 
-    static bool attr_set = false;
+    int dev = 0, n_sm = 148;
+    BM2_CUDA_OK(cudaGetDevice(&dev));
+    BM2_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    if (dev < 0 || dev >= BSW_MAX_DEV) { bm2_set_error(ctx_for_error, "bsw: device ordinal out of range"); return 1; }
+    static bool attr_set_dev[BSW_MAX_DEV];          // the attribute is per device: one flag per ordinal
     static std::mutex attr_mu;                      // launches come from several host threads (sub-batch lanes, contexts)
     std::unique_lock<std::mutex> attr_lock(attr_mu);
-    if (!attr_set) {   // one function, several dynamic sizes: raise the limit once
+    bool &attr_set = attr_set_dev[dev];
+    if (!attr_set) {   // one function, several dynamic sizes: raise the limit once per device
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_col2_kernel<BSW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -718,8 +724,6 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     // one-cell-per-instruction kernel for them (A/B measurements, tests of both kernels).
     const char *col2_env = getenv("BM2_BSW_COL2");
     const int col2_ok = (!(col2_env && col2_env[0] == '0') && c2_params_ok(prm)) ? 1 : 0;
-    int n_sm = 148;
-    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     // shared memory the persistent CTAs of one launch may occupy per SM: the rest stays free for the kernels of the other
     // sub-batches in flight (latency-bound SMEM / chain / tail kernels co-resident with the ALU-bound extension)
     size_t smem_budget = 227 * 1024;
@@ -785,6 +789,7 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
         // shared by all contexts of the process: one launch of this (rare) path at a time, held until the kernel has finished.
         static std::mutex wide_mu;
         std::lock_guard<std::mutex> wide_lock(wide_mu);
+        BswWideScratch &g_wide = g_wide_dev[dev];
         int32_t h_off[2];
         BM2_CUDA_OK(cudaMemcpyAsync(h_off, class_off + BSW_NCLASS, 8, cudaMemcpyDeviceToHost, stream));
         BM2_CUDA_OK(cudaStreamSynchronize(stream));
@@ -805,7 +810,7 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
                 BM2_CUDA_OK(cudaMalloc(&g_wide.state, (size_t) total * sizeof(int2)));
                 g_wide.cap_words = total;
             }
-            int blocks = (nw + 63) / 64; if (blocks > 148 * 8) blocks = 148 * 8;
+            int blocks = (nw + 63) / 64; if (blocks > n_sm * 8) blocks = n_sm * 8;
             bsw_wide_kernel<<<blocks, 64, 0, stream>>>(d_jobs, idx_out, class_off, d_out, d_tbase, d_qbase, prm, g_wide.state,
                                                        g_wide.state_off, d_cells);
             BM2_CUDA_OK(cudaStreamSynchronize(stream));

@@ -101,8 +101,8 @@ extern "C" int bm2_create(bm2_ctx **out, int device, const bm2_index_desc *idx, 
     BM2_CUDA_OK(cudaSetDevice(device));
     cudaDeviceProp prop;
     BM2_CUDA_OK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
-        bm2_set_error(nullptr, "bm2_create: device is not sm_100 (library is built for sm_100a only)");
+    if (prop.major != 10) {      // the library holds an sm_100a cubin only (arch-specific: no forward compatibility to sm_11x / sm_12x)
+        bm2_set_error(nullptr, "bm2_create: device is not sm_10x (library is built for sm_100a only)");
         return 2;
     }
     bm2_ctx *ctx = new bm2_ctx();
@@ -112,13 +112,13 @@ extern "C" int bm2_create(bm2_ctx **out, int device, const bm2_index_desc *idx, 
     if (const char *e = getenv("BM2_SUB_BATCHES")) { int k = atoi(e); if (k >= 1 && k <= 16) ctx->n_lanes = k; }
     ctx_for_error = ctx;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
-        bm2_set_error(nullptr, "bm2_create: cudaStreamCreate failed"); delete ctx; return 1;
+        bm2_set_error(nullptr, "bm2_create: cudaStreamCreate failed"); bm2_destroy(ctx); return 1;
     }
     ctx->stream = ctx->own_stream;
     if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-        bm2_set_error(nullptr, "bm2_create: side stream/events failed"); delete ctx; return 1;
+        bm2_set_error(nullptr, "bm2_create: side stream/events failed"); bm2_destroy(ctx); return 1;
     }
     if (idx) {
         if (bm2_upload_index(ctx, idx)) { bm2_set_error(nullptr, "bm2_create: " + ctx->err); bm2_destroy(ctx); return 1; }
@@ -185,8 +185,11 @@ extern "C" void bm2_destroy(bm2_ctx *ctx) {
 }
 
 extern "C" const char *bm2_last_error(const bm2_ctx *ctx) {
+    // the caller gets a per-thread copy: another thread setting a new message cannot invalidate the returned pointer
+    static thread_local std::string copy;
     std::lock_guard<std::mutex> lk(g_err_mu);
-    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+    copy = ctx ? ctx->err : g_create_error;
+    return copy.c_str();
 }
 
 static BswParams bsw_params_of(const bm2_ctx *ctx, int w, int end_bonus) {
@@ -357,5 +360,74 @@ extern "C" int bm2_gather64_gbs(bm2_ctx *ctx, unsigned long long span_bytes, dou
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *gbs = (double) blocks * threads * (double) iters * MLP * 64.0 / (best * 1e-3) / 1e9;
+    return 0;
+}
+
+// ---- gather probe with selectable request shape and memory-level parallelism ---------------------------------------------
+// shape 0: 64 B per request as four 16-B loads of one thread (the shape of bm2_gather64_gbs); shape 1: 32 B per request as ONE
+// 256-bit load (LDG.E.256: the half-checkpoint of the device Occ layout, fm_device.cuh); shape 2: 64 B per request as two 256-bit
+// loads.  `mlp` independent requests per thread are in flight (1, 2, 4 or 8).  Reports GB/s of requested bytes.
+__device__ __forceinline__ void ld256(const void *p, unsigned long long &a, unsigned long long &b, unsigned long long &c, unsigned long long &d) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+template <int MLP, int SHAPE>
+__global__ void __launch_bounds__(256) gather_probe_kernel(const char *__restrict__ tab, unsigned long long n_units, int iters, unsigned long long seed,
+                                                           unsigned *out) {
+    unsigned long long x = seed + (unsigned long long) (blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull;
+    unsigned long long acc = 0;
+    constexpr int UNIT = SHAPE == 1 ? 32 : 64;
+    for (int it = 0; it < iters; ++it) {
+        unsigned long long v[MLP][8];
+#pragma unroll
+        for (int m = 0; m < MLP; ++m) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            const unsigned long long e = (unsigned long long) (((unsigned __int128) x * n_units) >> 64);
+            const char *p = tab + e * UNIT;
+            if (SHAPE == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p) + q); v[m][2 * q] = ((unsigned long long) t.x << 32) | t.y; v[m][2 * q + 1] = ((unsigned long long) t.z << 32) | t.w; }
+            } else {
+                ld256(p, v[m][0], v[m][1], v[m][2], v[m][3]);
+                if (SHAPE == 2) ld256(p + 32, v[m][4], v[m][5], v[m][6], v[m][7]);
+                else { v[m][4] = v[m][5] = v[m][6] = v[m][7] = 0; }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MLP; ++m)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc += v[m][q];
+    }
+    if (acc == 0x12345678u) out[0] = (unsigned) acc;
+}
+
+extern "C" int bm2_gather_probe(bm2_ctx *ctx, unsigned long long span_bytes, int mlp, int shape, double *gbs) {
+    bm2_ctx *ctx_for_error = ctx;
+    if (!ctx || !gbs || shape < 0 || shape > 2) return 1;
+    if (!ctx->idx.loaded) { bm2_set_error(ctx, "bm2_gather_probe needs a context created with an index"); return 1; }
+    BM2_CUDA_OK(cudaSetDevice(ctx->device));
+    const unsigned long long unit = shape == 1 ? 32 : 64;
+    unsigned long long n_units = ((unsigned long long) (ctx->idx.N >> 6) + 1) * 64 / unit;
+    if (span_bytes && span_bytes / unit < n_units) n_units = span_bytes / unit ? span_bytes / unit : 1;
+    const int blocks = ctx->n_sm * 8, threads = 256, iters = 64;
+    if (ctx->ensure(ctx->bsw_outs, 256)) return 1;
+    cudaEvent_t e0, e1;
+    BM2_CUDA_OK(cudaEventCreate(&e0)); BM2_CUDA_OK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    const char *tab = (const char *) ctx->idx.cp_occ; unsigned *o = (unsigned *) ctx->bsw_outs.p;
+    for (int rep = 0; rep < 4; ++rep) {
+        BM2_CUDA_OK(cudaEventRecord(e0, ctx->stream));
+#define BM2_GP(M, S) gather_probe_kernel<M, S><<<blocks, threads, 0, ctx->stream>>>(tab, n_units, iters, 777 + rep, o)
+#define BM2_GPS(M) do { if (shape == 0) BM2_GP(M, 0); else if (shape == 1) BM2_GP(M, 1); else BM2_GP(M, 2); } while (0)
+        if (mlp <= 1) BM2_GPS(1); else if (mlp == 2) BM2_GPS(2); else if (mlp <= 4) BM2_GPS(4); else BM2_GPS(8);
+#undef BM2_GPS
+#undef BM2_GP
+        BM2_CUDA_OK(cudaEventRecord(e1, ctx->stream));
+        BM2_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0; BM2_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const int m_eff = mlp <= 1 ? 1 : mlp == 2 ? 2 : mlp <= 4 ? 4 : 8;
+    *gbs = (double) blocks * threads * (double) iters * m_eff * (double) unit / (best * 1e-3) / 1e9;
     return 0;
 }

@@ -2097,3 +2097,34 @@ extern "C" int bm2o_sam_pe_text(const bm2_index_desc *x, const bm2_mem_opt_t *op
     *len = (int64_t) t.size();
     return 0;
 }
+
+
+/* Host probe for bench.py's cpu_baseline leg (no reference counterpart): aggregate rate of a fixed integer loop on `nthreads`
+ * pthreads for `seconds`, in loop iterations per second.  rate(n) / rate(1) is the number of cores the box really gives `n`
+ * threads (cgroup quotas, shared hosts and SMT siblings do not show in sched_getaffinity). */
+#include <pthread.h>
+#include <time.h>
+struct ProbeArg { double seconds; volatile uint64_t iters; };
+static double probe_now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+static void *probe_thread(void *p) {
+    ProbeArg *a = (ProbeArg *) p;
+    const double t_end = probe_now() + a->seconds;
+    uint64_t x = 88172645463325252ULL, n = 0;
+    do {
+        for (int i = 0; i < 100000; ++i) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; }
+        n += 100000;
+    } while (probe_now() < t_end);
+    a->iters = n + (x == 0);
+    return 0;
+}
+extern "C" double bm2o_cpu_probe(int32_t nthreads, double seconds) {
+    if (nthreads < 1) nthreads = 1;
+    std::vector<ProbeArg> args((size_t) nthreads);
+    std::vector<pthread_t> th((size_t) nthreads);
+    const double t0 = probe_now();
+    for (int i = 0; i < nthreads; ++i) { args[i].seconds = seconds; args[i].iters = 0; pthread_create(&th[i], 0, probe_thread, &args[i]); }
+    uint64_t tot = 0;
+    for (int i = 0; i < nthreads; ++i) { pthread_join(th[i], 0); tot += args[i].iters; }
+    const double dt = probe_now() - t0;
+    return dt > 0 ? (double) tot / dt : 0.0;
+}

@@ -99,6 +99,9 @@ int bm2o_sam_pe(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_r
 int bm2o_sam_pe_text(const bm2_index_desc *idx, const bm2_mem_opt_t *opt, const bm2_read_batch *reads, const char *quals, const char *const *names,
                      const bm2_alnreg_t *regs, const int64_t *read_off, const int32_t *pes_lh, const double *pes_as, int64_t id_base, char **text, int64_t *len);
 
+/* bench.py's cpu_baseline leg: aggregate iterations/s of a fixed integer loop on `nthreads` pthreads (effective cores = rate(n)/rate(1)) */
+double bm2o_cpu_probe(int32_t nthreads, double seconds);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,7 +94,6 @@ def test_tandem_repeat_pairs_match_oracle(pkg, golden_dir):
     idx.close()
 
 
-@pytest.mark.xfail(strict=False, reason="bm2_sam_se was added after the file's first GPU run (same kernel, single-end branch)")
 @pytest.mark.parametrize("flags", [0, 0x8, 0x1800], ids=["default", "all", "primary5"])
 def test_single_end_records_match_oracle(c0, flags):
     """bm2_sam_se: the r1 reads of C0 as single-end reads, against the oracle's single-end SAM stage (pinned to the live reference by

@@ -7,7 +7,7 @@ import pytest
 import ksw_util as ku
 import test_oracle_ksw as tk
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="ksw.cu has not run on a GPU yet (written after the round's GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu]      # first B200 run: GPUTEST_r01 (passed); no xfail any more
 
 
 def test_golden_vectors_of_the_reference(pkg, golden_dir):
