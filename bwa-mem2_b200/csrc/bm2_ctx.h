@@ -13,6 +13,7 @@ struct DevIndex {                 // FM-index + reference resident in HBM (repli
     int64_t N = 0, l_pac = 0, sentinel = 0;
     int64_t count[5] = {0, 0, 0, 0, 0};
     const bm2_cp_occ *cp_occ = nullptr;
+    int occ_layout = 0;                    // FmIndexView::layout of the resident table (1 = half-checkpoint sectors, made at upload)
     const int8_t *sa_ms = nullptr;
     const uint32_t *sa_ls = nullptr;
     const uint8_t *ref = nullptr;          // 2*l_pac codes

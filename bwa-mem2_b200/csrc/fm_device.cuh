@@ -14,13 +14,26 @@
 #include "hd.h"
 #include "bm2_b200.h"
 
+// layout 0: the checkpoints as the index file holds them, {cp_count[4]; one_hot_bwt_str[4]} (CP_OCC, src/FMI_search.h:54-58).
+// layout 1 (device only, made in place at upload by occ_relayout_kernel, pipeline.cu): the same eight words ordered
+// {cnt0, cnt1, bits0, bits1 | cnt2, cnt3, bits2, bits3}: an interval extension by base a needs base a and ONE partner base, and the partner
+// is always in a's half ({0,1} or {2,3}, see fm_backward_ext), so one checkpoint costs ONE 32-byte sector fetched by ONE 256-bit load
+// (LDG.E.256) instead of both sectors of the 64-byte line through four 8-byte loads.
 struct FmIndexView {
     const bm2_cp_occ *cp_occ;
     const int8_t *sa_ms;
     const uint32_t *sa_ls;
     int64_t count[5];
     int64_t sentinel;
+    int layout = 0;
 };
+
+#if defined(__CUDA_ARCH__)
+// 32 bytes by one 256-bit load, read-only path, no L1 allocation (the checkpoints of a multi-GB table are never re-used from L1)
+BM2_D void fm_ld256(const void *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+#endif
 
 struct FmIv { int64_t k, l, s; };
 
@@ -38,6 +51,7 @@ BM2_HD FmOcc4 fm_occ4(const FmIndexView &fm, int64_t pp) {
 #if defined(__CUDA_ARCH__)
     const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(e);
     ulonglong2 c01 = __ldg(p), c23 = __ldg(p + 1), b01 = __ldg(p + 2), b23 = __ldg(p + 3);
+    if (fm.layout) { const ulonglong2 t = c23; c23 = b01; b01 = t; }          // {c01, b01, c23, b23} in memory
     uint64_t cnt[4] = {c01.x, c01.y, c23.x, c23.y}, bits[4] = {b01.x, b01.y, b23.x, b23.y};
 #else
     uint64_t cnt[4], bits[4];
@@ -64,6 +78,28 @@ BM2_HD FmIv fm_backward_ext(const FmIndexView &fm, const FmIv &in, int a) {
     const int b2 = a == 1 ? 0 : (a == 2 ? 3 : a);                  // the one other base that is needed
     const int y1 = (int) (p1 & 63), y2 = (int) (p2 & 63);
     const uint64_t m1 = y1 ? ~0ULL << (64 - y1) : 0ULL, m2 = y2 ? ~0ULL << (64 - y2) : 0ULL;
+#if defined(__CUDA_ARCH__)
+    if (fm.layout) {
+        // device layout: the half {2h, 2h+1} of a checkpoint is one 32-byte sector {cnt, cnt, bits, bits}; both ends of a small
+        // interval usually lie in the same checkpoint, then the second load is skipped
+        const int h = a >> 1, odd = a & 1;
+        const char *q1 = reinterpret_cast<const char *>(e1) + h * 32, *q2 = reinterpret_cast<const char *>(e2) + h * 32;
+        uint64_t c10, c11, b10, b11, c20, c21, b20, b21;
+        fm_ld256(q1, c10, c11, b10, b11);
+        if (q2 != q1) fm_ld256(q2, c20, c21, b20, b21);
+        else { c20 = c10; c21 = c11; b20 = b10; b21 = b11; }
+        const int64_t o10 = (int64_t) c10 + __popcll(b10 & m1), o11 = (int64_t) c11 + __popcll(b11 & m1);
+        const int64_t o20 = (int64_t) c20 + __popcll(b20 & m2), o21 = (int64_t) c21 + __popcll(b21 & m2);
+        const int64_t s0 = o20 - o10, s1 = o21 - o11;
+        const int64_t sa = odd ? s1 : s0, sb = odd ? s0 : s1;          // partner of base 1 is base 0, of base 2 is base 3
+        const int64_t sent = (in.k <= fm.sentinel && in.k + in.s > fm.sentinel) ? 1 : 0;
+        FmIv r;
+        r.k = fm_count(fm, a) + (odd ? o11 : o10);
+        r.s = sa;
+        r.l = a == 0 ? in.l + in.s - sa : a == 1 ? in.l + in.s - sb - sa : a == 2 ? in.l + sent + sb : in.l + sent;
+        return r;
+    }
+#endif
     const int64_t o1a = (int64_t) BM2_LDG64(&e1->cp_count[a]) + BM2_POPC64(BM2_LDG64(&e1->one_hot_bwt_str[a]) & m1);
     const int64_t o2a = (int64_t) BM2_LDG64(&e2->cp_count[a]) + BM2_POPC64(BM2_LDG64(&e2->one_hot_bwt_str[a]) & m2);
     const int64_t o1b = (int64_t) BM2_LDG64(&e1->cp_count[b2]) + BM2_POPC64(BM2_LDG64(&e1->one_hot_bwt_str[b2]) & m1);
@@ -86,6 +122,7 @@ BM2_HD int64_t fm_sa_of_row(const FmIndexView &fm, int64_t r, int *lf_steps) {
 #if defined(__CUDA_ARCH__)
         const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(e);
         ulonglong2 c01 = __ldg(p), c23 = __ldg(p + 1), b01 = __ldg(p + 2), b23 = __ldg(p + 3);
+        if (fm.layout) { const ulonglong2 t = c23; c23 = b01; b01 = t; }      // {c01, b01, c23, b23} in memory
         uint64_t cnt[4] = {c01.x, c01.y, c23.x, c23.y}, bits[4] = {b01.x, b01.y, b23.x, b23.y};
 #else
         uint64_t cnt[4], bits[4];

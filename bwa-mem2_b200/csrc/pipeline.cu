@@ -39,6 +39,16 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
 // ------------------------------------------------------------------------------------------------
 // index upload
 // ------------------------------------------------------------------------------------------------
+// The device layout of the Occ table (FmIndexView::layout 1, fm_device.cuh): words {c0,c1,c2,c3,b0,b1,b2,b3} of every 64-byte
+// checkpoint become {c0,c1,b0,b1,c2,c3,b2,b3}, in place, once per upload.  The index files and bm2_index_desc keep the reference's format.
+__global__ void occ_relayout_kernel(ulonglong2 *tab, size_t n_entries) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_entries) return;
+    ulonglong2 *e = tab + i * 4;
+    const ulonglong2 c23 = e[1], b01 = e[2];
+    e[1] = b01; e[2] = c23;
+}
+
 int bm2_upload_index(bm2_ctx *ctx, const bm2_index_desc *idx) {
     bm2_ctx *ctx_for_error = ctx;
     auto up = [&](const void *src, size_t bytes, const void **dst) -> int {
@@ -55,6 +65,15 @@ int bm2_upload_index(bm2_ctx *ctx, const bm2_index_desc *idx) {
     d.n_seqs = idx->n_seqs;
     size_t n_occ = (size_t) (d.N >> 6) + 1, n_sa = (size_t) (d.N >> 3) + 1;
     if (up(idx->cp_occ, n_occ * sizeof(bm2_cp_occ), (const void **) &d.cp_occ)) return 1;
+    {   // BM2_OCC_LAYOUT=0 keeps the file layout on the device (A/B measurements); default: half-checkpoint sectors
+        const char *e = getenv("BM2_OCC_LAYOUT");
+        d.occ_layout = (e && e[0] == '0') ? 0 : 1;
+        if (d.occ_layout) {
+            occ_relayout_kernel<<<(unsigned) ((n_occ + 255) / 256), 256>>>((ulonglong2 *) d.cp_occ, n_occ);
+            BM2_CUDA_OK(cudaGetLastError());
+            BM2_CUDA_OK(cudaDeviceSynchronize());
+        }
+    }
     if (up(idx->sa_ms_byte, n_sa, (const void **) &d.sa_ms)) return 1;
     if (up(idx->sa_ls_word, n_sa * 4, (const void **) &d.sa_ls)) return 1;
     if (up(idx->ref_string, (size_t) d.l_pac * 2, (const void **) &d.ref)) return 1;
@@ -620,7 +639,7 @@ struct Params { FmIndexView fm; ContigView cv; SmemParams sp; ChainParams cp; Ex
 Params make_params(const bm2_ctx *ctx) {
     Params v;
     const DevIndex &d = ctx->idx; const bm2_mem_opt_t &o = ctx->opt;
-    v.fm.cp_occ = d.cp_occ; v.fm.sa_ms = d.sa_ms; v.fm.sa_ls = d.sa_ls; v.fm.sentinel = d.sentinel;
+    v.fm.cp_occ = d.cp_occ; v.fm.layout = d.occ_layout; v.fm.sa_ms = d.sa_ms; v.fm.sa_ls = d.sa_ls; v.fm.sentinel = d.sentinel;
     for (int i = 0; i < 5; ++i) v.fm.count[i] = d.count[i];
     v.cv.l_pac = d.l_pac; v.cv.n_seqs = d.n_seqs; v.cv.ann_off = d.ann_off; v.cv.ann_len = d.ann_len; v.cv.ann_alt = d.ann_alt;
     v.sp.min_seed_len = o.min_seed_len; v.sp.split_len = (int) (o.min_seed_len * o.split_factor + .499);
