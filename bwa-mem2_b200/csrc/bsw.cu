@@ -339,10 +339,10 @@ bsw_thread_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ p
 // 256 query columns, i.e. every job of a 2x151 bp read.  Shared memory: state words {H, E} x 2 columns [pair][thread],
 // then the query as one PRMT selector byte per column, 4 columns per word [word][thread].
 // ---------------------------------------------------------------------------------------------
-template <int NTHR>                     // compile-time strides: the unrolled pair loop addresses columns as [base + immediate]
+template <int NTHR>                     // compile-time strides: the pair loop walks the columns with constant pointer increments
 struct Col2MemShared {
-    unsigned st_base, q_base;           // shared-window byte addresses of the thread's pair 0 / selector word 0
-    static constexpr unsigned stride = NTHR * 4u;
+    unsigned st_base, q_base;           // shared-window byte addresses of the thread's pair 0 (state words / 16-bit selector pairs)
+    static constexpr unsigned stride = NTHR * 4u, qstride = NTHR * 2u;
     __device__ __forceinline__ uint32_t ldw(int q) const {
         uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(st_base + (unsigned) q * stride)); return w;
     }
@@ -355,8 +355,8 @@ struct Col2MemShared {
     __device__ __forceinline__ void sth(int j, uint32_t v) const {
         asm volatile("st.shared.u16 [%0], %1;" :: "r"(st_base + (unsigned) (j >> 1) * stride + 2u * (unsigned) (j & 1)), "h"((uint16_t) v) : "memory");
     }
-    __device__ __forceinline__ uint32_t qsel(int k) const {
-        uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(q_base + (unsigned) k * stride)); return w;
+    __device__ __forceinline__ uint32_t sel16(int q) const {
+        uint16_t w; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w) : "r"(q_base + (unsigned) q * qstride)); return (uint32_t) w;
     }
 };
 
@@ -370,7 +370,7 @@ bsw_col2_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ per
     const int first = class_off[cls], last = class_off[cls + 1];
     Col2MemShared<NTHR> mem;
     mem.st_base = (unsigned) __cvta_generic_to_shared(sh) + threadIdx.x * 4u;
-    mem.q_base = mem.st_base + (unsigned) NP * NTHR * 4u;
+    mem.q_base = (unsigned) __cvta_generic_to_shared(sh) + (unsigned) NP * NTHR * 4u + threadIdx.x * 2u;
     const bool same_oe = p.o_del + p.e_del == p.o_ins + p.e_ins;
     unsigned long long ncell = 0;
     for (int blk = blockIdx.x; first + blk * NTHR < last; blk += gridDim.x) {      // persistent CTAs: long jobs first
@@ -379,15 +379,12 @@ bsw_col2_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ per
             const int id = perm[g];
             const BswJob job = jobs[id];
             const uint8_t *qp = qbase + job.qoff;
-            for (int k = 0; k < job.qlen; k += 4) {
-                uint32_t wv = 0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int jj = k + u;
-                    const int b = jj < job.qlen ? (int) qp[(long long) jj * job.qstride] : 4;
-                    wv |= c2_selector_byte(b) << (8 * u);
-                }
-                asm volatile("st.shared.u32 [%0], %1;" :: "r"(mem.q_base + (unsigned) (k >> 2) * (NTHR * 4u)), "r"(wv) : "memory");
+            // selector bytes of columns 2q, 2q+1 as one 16-bit word per pair, up to the pair that holds column qlen (read masked)
+            for (int k = 0; k <= job.qlen; k += 2) {
+                const int b0 = k < job.qlen ? (int) qp[(long long) k * job.qstride] : 4;
+                const int b1 = k + 1 < job.qlen ? (int) qp[(long long) (k + 1) * job.qstride] : 4;
+                const uint32_t wv = c2_selector_byte(b0) | (c2_selector_byte(b1) << 8);
+                asm volatile("st.shared.u16 [%0], %1;" :: "r"(mem.q_base + (unsigned) (k >> 1) * (NTHR * 2u)), "h"((uint16_t) wv) : "memory");
             }
             BswOut o;
             if (same_oe) bsw_col2_extend<true>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
@@ -747,8 +744,8 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
         if (nblk > cap_blk) nblk = cap_blk;
         if (col2_ok && !is16 && bound <= 256) {
             // two columns per packed instruction (bsw_col2.cuh): state 2 B per column in pair words, selectors 1 B per column
-            const int NP = (W + 1) / 2, NQ = (bound + 3) / 4;
-            const size_t smem2 = (size_t) (NP + NQ) * 4 * BSW_THREADS;
+            const int NP = (W + 1) / 2;                       // state words: pairs over columns 0 .. bound + 1; selectors: 2 B per pair
+            const size_t smem2 = (size_t) NP * 6 * BSW_THREADS;
             int cps = (int) (smem_budget / (smem2 + 1024)); if (cps < 1) cps = 1; if (cps > max_ctas) cps = max_ctas;
             int nb = (n + BSW_THREADS - 1) / BSW_THREADS; if (nb > n_sm * cps) nb = n_sm * cps;
             bsw_col2_kernel<BSW_THREADS><<<nb, BSW_THREADS, smem2, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, NP, d_cells);

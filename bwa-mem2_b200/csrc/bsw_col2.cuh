@@ -11,9 +11,9 @@
 // (bsw_pair.cuh) - the band, the exit row and the trip count are shared: the lanes of a warp diverge no more than in
 // the one-cell-per-instruction kernel.  Odd band edges are single cells (at most two per row).
 //
-// Per pair of cells: 1 LDS + 1 STS of the state {H_lo, E_lo, H_hi, E_hi} (4 x 8 bit), one PRMT for both substitution
-// scores (the per-column selector byte is precomputed from the query), 9-10 ALU-pipe + 12 FMA-pipe instructions
-// (the ALU pipe is the busier one: unpacking H, moving F between the halves and all packing are multiply-adds).
+// Per pair of cells: 1 LDS + 1 STS of the state {H_lo, E_lo, H_hi, E_hi} (4 x 8 bit), 1 LDS of the two selector bytes, one PRMT
+// for both substitution scores (the per-column selector byte is precomputed from the query), 10 ALU-pipe + 8 FMA-pipe instructions
+// (unpacking H, the row-maximum key and all packing are multiply-adds on the FMA pipe).
 //
 // Written as BM2_HD so that tests/host_emul/bsw_col2_emul.cpp runs the very same code on the CPU against the oracle.
 #pragma once
@@ -32,8 +32,21 @@ BM2_HD uint32_t c2_selector_byte(int qb) { const uint32_t q = qb > 4 ? 4u : (uin
 BM2_HD bool c2_params_ok(const BswParams &p) { return p2_params_ok(p); }
 
 // Mem: ldw/stw (state word of column pair p = columns 2p, 2p+1), ldh/sth (16-bit state {H, E << 8} of one column),
-// qsel(k) (selector bytes of columns 4k .. 4k+3).
+// sel16(p) (the two selector bytes of pair p: columns 2p, 2p+1).
 // SAME_OE: o_del + e_del == o_ins + e_ins (the default scoring), one packed add per pair less.
+//
+// Round 2: ONE control flow for all 32 lanes of a warp.  The row is the pairs pb = beg >> 1 .. pe = (end - 1) >> 1; a pair that
+// sticks out of the band on the left (odd beg) or on the right (odd end) is run like any other pair on a masked input word:
+//   * dead low half (column beg - 1): H and E read as 0, so M = E' = h = 0 and nothing flows into column beg (F enters as 0, the
+//     left neighbour's H is h1 = 0 because beg > 0); its state bytes are written back unchanged;
+//   * dead high half (column end): H and E read as 0, its stored state becomes {H(i, end - 1), 0} - exactly the reference's
+//     eh[end] = {h1, 0} (src/bandedSWA.cpp:203) - and its key is masked out of the row maximum.
+// Every lane therefore executes: masked first pair, the pair loop (trip counts differ, code does not), masked last pair.  (Round 1
+// ran odd edges as single 32-bit cells and the pair loop as quads with remainder blocks: five code paths per row that the lanes of
+// a warp took at different times - 24-26 of 32 lanes active per instruction.)
+// F crosses the halves with one multiply and one PRMT per pair: with U = {F(2q), F(2q)},
+//   f2 = max(U + {0, -e}, {0, t(2q)}, 0) = {F(2q), F(2q+1)},  fb = max(f2 + {-e, -e}, {t(2q), t(2q+1)}, 0) -> high half F(2q+2),
+// t = M - oe_ins (round 1: two multiplies up, a merge and a shift down per pair).
 template <bool SAME_OE, class Mem>
 BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, int qlen, int tlen, int h0, const BswParams &p,
                             BswOut &o, unsigned long long &cells)
@@ -41,6 +54,7 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
     const int oe_del = p.o_del + p.e_del, oe_ins = p.o_ins + p.e_ins, e_del = p.e_del, e_ins = p.e_ins;
     const uint32_t n_oe_del = ((uint32_t) (-oe_del) & 0xFFFFu) * 0x10001u, n_e_del = ((uint32_t) (-e_del) & 0xFFFFu) * 0x10001u;
     const uint32_t n_oe_ins = ((uint32_t) (-oe_ins) & 0xFFFFu) * 0x10001u, n_e_ins = ((uint32_t) (-e_ins) & 0xFFFFu) * 0x10001u;
+    const uint32_t n_e_ins_hi = n_e_ins & 0xFFFF0000u;                                       // {0, -e_ins}
     const uint32_t one = qlen >= 0 ? 1u : 0u;          // 1, opaque to the compiler: x * one + y stays a multiply-add (FMA pipe)
     // first row (bandedSWA.cpp:141-144): columns 0..qlen, E = 0
     {
@@ -71,90 +85,59 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
         if (beg < i - w) beg = i - w;
         if (end > i + w + 1) end = i + w + 1;
         if (end > qlen) end = qlen;
-        int h1;
+        int h1 = 0;
         if (beg == 0) { h1 = h0 - (p.o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
-        else h1 = 0;
         const int tb = tb_next;
         if (i + 1 < tlen) tb_next = (int) tptr[(long long) (i + 1) * tstride];
         const uint32_t tbl = p2_score_table(tb, p.a, p.b);
-        int f = 0, key1 = 0;
         uint32_t key2 = 0;
-        // one cell (odd band edges): plain 32-bit arithmetic
-        auto cell1 = [&](const int jj) {
-            const uint32_t v = mem.ldh(jj);
-            const int hd = (int) (v & 0xFFu);
-            int e = (int) (v >> 8);
-            const uint32_t qb = (mem.qsel(jj >> 2) >> (8 * (jj & 3))) & 0xFu;
-            const int s = (int) p2_prmt(tbl, 0xFFFFFFFFu, qb * 0x1111u + 0x8880u);
-            int M = hd ? hd + s : 0; if (M < 0) M = 0;
-            int h = M > e ? M : e; if (f > h) h = f;
-            int t = M - oe_del; if (t < 0) t = 0;
-            e -= e_del; if (t > e) e = t;
-            mem.sth(jj, (uint32_t) (h1 | (e << 8)));
-            t = M - oe_ins; if (t < 0) t = 0;
-            f -= e_ins; if (t > f) f = t;
-            h1 = h;
-            const int k = h * 256 + jj;
-            if (k > key1) key1 = k;
-        };
-        int j = beg;
-        if (j < end && (j & 1)) { cell1(j); ++j; }
-        {
-            int pp = j >> 1;
-            const int pe = end >> 1;
-            if (pp < pe) {
-                // F, H1: running F / H(i, j-1) of the next column in the LOW half (high half 0)
-                uint32_t F = (uint32_t) f, H1 = (uint32_t) h1, jj2 = (uint32_t) (2 * pp) * 0x10001u + 0x10000u;
-                auto pair = [&](const int q, const uint32_t sel) {
-                    const uint32_t wv = mem.ldw(q);
-                    const uint32_t e = p2_prmt(wv, 0u, 0x4341u);
-                    const uint32_t hd = p2_mad(e, 0xFFFFFF00u, wv);                          // wv - (e << 8) on the FMA pipe
-                    const uint32_t s = p2_prmt(tbl, 0xFFFFFFFFu, sel);                       // low 16 selector bits: columns 2q, 2q+1
-                    const uint32_t M = p2_addmin_relu(hd, s, p2_mad(hd, 128u, 0u));          // hd ? max(hd + s, 0) : 0   (s <= 127)
-                    const uint32_t td = p2_add(M, n_oe_del);
-                    const uint32_t en = p2_addmax_relu(e, n_e_del, td);
-                    const uint32_t ti = SAME_OE ? td : p2_add(M, n_oe_ins);
-                    // F(2q+1) = max(F(2q) - e_ins, M(2q) - oe_ins, 0) in the HIGH half: both operands moved up by multiplies
-                    const uint32_t fa = p2_addmax_relu(p2_mad(F, 65536u, 0u), n_e_ins, p2_mad(ti, 65536u, 0u));      // low half: 0
-                    const uint32_t f2 = p2_mad(F, one, fa);                                  // {F(2q), F(2q+1)}
-                    const uint32_t fb = p2_addmax_relu(f2, n_e_ins, ti);                     // high half: F(2q+2)
-                    const uint32_t h = p2_max3(M, e, f2);
-                    const uint32_t hs = p2_mad(h, 65536u, H1);                               // {H(i, 2q-1), H(i, 2q)}
-                    mem.stw(q, p2_mad(en, 256u, hs));
-                    F = c2_shr16(fb);
-                    H1 = c2_shr16(h);
-                    key2 = p2_maxu(key2, p2_mad(h, 256u, jj2));
-                    jj2 = p2_mad(one, 0x00020002u, jj2);
-                };
-                auto quad = [&](const int k) {                                              // columns 4k .. 4k+3
-                    const uint32_t sw = mem.qsel(k);
-                    pair(2 * k, sw);
-                    pair(2 * k + 1, c2_shr16(sw));
-                };
-                if (pp & 1) { pair(pp, c2_shr16(mem.qsel(pp >> 1))); ++pp; }
-                int k = pp >> 1;
-                const int ke = pe >> 1;
-                for (; k + 2 <= ke; k += 2) { quad(k); quad(k + 1); }
-                if (k < ke) { quad(k); ++k; }
-                pp = 2 * k;
-                if (pp < pe) pair(pp, mem.qsel(pp >> 1));
-                f = (int) F; h1 = (int) H1;
-                j = 2 * pe;
+        if (end > beg) {
+            const int pb = beg >> 1, pe = (end - 1) >> 1;
+            const uint32_t in_first = (beg & 1) ? 0xFFFF0000u : 0xFFFFFFFFu, in_last = (end & 1) ? 0x0000FFFFu : 0xFFFFFFFFu;
+            uint32_t U = 0;                                            // {F(2q), F(2q)}
+            uint32_t hp = (uint32_t) h1 << 16;                         // packed h of the pair to the left: its high half is H(i, 2q - 1)
+            uint32_t jj2 = (uint32_t) (2 * pb) * 0x10001u + 0x10000u;  // {2q, 2q + 1}
+            // the DP of one pair on the (masked) state word wv; returns the new state word
+            auto pair = [&](const uint32_t wv, const uint32_t sel, const uint32_t keymask) -> uint32_t {
+                const uint32_t e = p2_prmt(wv, 0u, 0x4341u);
+                const uint32_t hd = p2_mad(e, 0xFFFFFF00u, wv);                          // wv - (e << 8) on the FMA pipe
+                const uint32_t s = p2_prmt(tbl, 0xFFFFFFFFu, sel);                       // low 16 selector bits: columns 2q, 2q+1
+                const uint32_t M = p2_addmin_relu(hd, s, p2_mad(hd, 128u, 0u));          // hd ? max(hd + s, 0) : 0   (s <= 127)
+                const uint32_t td = p2_add(M, n_oe_del);
+                const uint32_t en = p2_addmax_relu(e, n_e_del, td);
+                const uint32_t ti = SAME_OE ? td : p2_add(M, n_oe_ins);
+                const uint32_t f2 = p2_addmax_relu(U, n_e_ins_hi, p2_mad(ti, 65536u, 0u));   // {F(2q), F(2q+1)}
+                const uint32_t fb = p2_addmax_relu(f2, n_e_ins, ti);                     // high half: F(2q+2)
+                U = p2_prmt(fb, fb, 0x3232u);
+                const uint32_t h = p2_max3(M, e, f2);
+                const uint32_t hs = p2_mad(h, 65536u, c2_shr16(hp));                     // {H(i, 2q-1), H(i, 2q)}
+                hp = h;
+                key2 = p2_maxu(key2, p2_mad(h, 256u, jj2) & keymask);
+                jj2 = p2_mad(one, 0x00020002u, jj2);
+                return p2_mad(en, 256u, hs);
+            };
+            {   // first pair (also the last one when the band is a single pair)
+                const bool only = pb == pe;
+                const uint32_t in_and = only ? (in_first & in_last) : in_first;
+                const uint32_t old = mem.ldw(pb);
+                const uint32_t nw = pair(old & in_and, mem.sel16(pb), only ? in_last : 0xFFFFFFFFu);
+                mem.stw(pb, (nw & in_first) | (old & ~in_first));
             }
+            if (pb < pe) {
+                for (int q = pb + 1; q < pe; ++q) mem.stw(q, pair(mem.ldw(q), mem.sel16(q), 0xFFFFFFFFu));     // (unrolled x4 by the compiler, remainder first)
+                mem.stw(pe, pair(mem.ldw(pe) & in_last, mem.sel16(pe), in_last));
+            }
+            h1 = (int) ((end & 1) ? (hp & 0xFFFFu) : (hp >> 16));      // H(i, end - 1)
+            ncell += (unsigned) (end - beg);
         }
-        if (j < end) { cell1(j); ++j; }
-        {
-            const int ka = (int) (key2 & 0xFFFFu), kb = (int) (key2 >> 16);
-            if (ka > key1) key1 = ka;
-            if (kb > key1) key1 = kb;
-        }
+        const int ka = (int) (key2 & 0xFFFFu), kb = (int) (key2 >> 16);
+        const int key1 = ka > kb ? ka : kb;
         const int m = key1 >> 8, mj = key1 & 0xFF;
-        if (end > beg) ncell += (unsigned) (end - beg);
 #ifdef BM2_COL2_TRACE
         BM2_COL2_TRACE(beg, end);                              // lane-utilisation studies (tests/host_emul/bsw_col2_emul.cpp)
 #endif
-        mem.sth(end, (uint32_t) h1);
-        if (j == qlen) {
+        if (!(end > beg && (end & 1))) mem.sth(end, (uint32_t) h1);     // (odd end: the masked last pair has written {h1, 0} there)
+        if ((end > beg ? end : beg) == qlen) {
             if (h1 >= gscore) best_ie = i;
             if (h1 > gscore) gscore = h1;
         }
@@ -169,9 +152,10 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
             const int pen = di > dj ? di - dj : dj - di;       // SIMD z-drop: no e_del/e_ins factor, no `zdrop > 0` guard (ZSCORE8/16)
             if (best - m - pen > qk.zthr) break;
         }
+        int j;
         for (j = beg; j < end && mem.ldh(j) == 0u; ++j) {}
         beg = j;
-        j = end;                                               // column `end` holds {h1, 0} (written above): no load for the usual case
+        j = end;                                               // column `end` holds {h1, 0}: no load for the usual case
         if (h1 == 0) for (--j; j >= beg && mem.ldh(j) == 0u; --j) {}
         end = j + 2 < qlen ? j + 2 : qlen;
     }

@@ -11,6 +11,12 @@ WANT = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu_pipe_pct"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu_pipe_pct"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma_pipe_pct"),
+    ("sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "fmaheavy_pipe_pct"),
+    ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "alu_cycles_pct"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma_cycles_pct"),
+    ("launch__occupancy_limit_shared_mem", "occ_limit_smem_blocks"), ("launch__occupancy_limit_registers", "occ_limit_regs_blocks"),
+    ("sm__maximum_warps_per_active_cycle_pct", "theoretical_occupancy_pct"),
     ("smsp__thread_inst_executed_per_inst_executed.ratio", "threads_per_inst"), ("smsp__inst_executed.sum", "warp_insts"),
     ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_scoreboard"),
     ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_scoreboard"),

@@ -15,7 +15,7 @@ struct HostCol2Mem {
     void stw(int p, uint32_t w) const { state[2 * p] = (uint16_t) (w & 0xFFFFu); state[2 * p + 1] = (uint16_t) (w >> 16); }
     uint32_t ldh(int j) const { return state[j]; }
     void sth(int j, uint32_t v) const { state[j] = (uint16_t) v; }
-    uint32_t qsel(int k) const { uint32_t w; memcpy(&w, selb + 4 * k, 4); return w; }
+    uint32_t sel16(int q) const { return (uint32_t) selb[2 * q] | ((uint32_t) selb[2 * q + 1] << 8); }
 };
 
 // out = 6 ints per job (score, tle, gtle, qle, gscore, max_off); returns the number of DP cells, -1 for unsupported scoring.
