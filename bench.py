@@ -631,6 +631,154 @@ def run_sam(args, rank, world):
     return out
 
 
+def prepare_longread_inputs(work, index, n_reads, read_len, seed=31):
+    """config 5 reads (10 kbp, 4 % substitutions, 3 % insertions, 3 % deletions) drawn from the bench genome on the GPU; cached in `work`."""
+    import ctypes as C
+    f = os.path.join(work, f"long_{n_reads}_{read_len}.npy")
+    if not os.path.exists(f):
+        import torch
+        load_package()
+        from bwa_mem2_b200 import synth
+        l_pac = int(index.desc.l_pac); ns = int(index.desc.n_seqs)
+        ref = np.ctypeslib.as_array(C.cast(index.desc.ref_string, C.POINTER(C.c_uint8)), shape=(l_pac,))
+        lens = np.ctypeslib.as_array(C.cast(index.desc.ann_len, C.POINTER(C.c_int32)), shape=(ns,)).astype(np.int64)
+        genome = torch.from_numpy(ref.copy())
+        if torch.cuda.is_available():
+            genome = genome.cuda()
+        reads = synth.make_long_reads_torch(genome, lens, n_reads, read_len, seed=seed)
+        del genome
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+        synth.write_fastq_fast(os.path.join(work, f"long_{n_reads}_{read_len}.fq"), reads, prefix=b"l")
+        np.save(f, reads)
+    return np.load(f)
+
+
+ONT2D_ARGS = ["-x", "ont2d"]
+
+
+def reference_longread(work, fa, n_reads, read_len, n_sample, threads, steps=1, warmup=0, dump_regs=None):
+    """reads/s of the unmodified reference's worker_bwt + worker_aln with -x ont2d on the first n_sample long reads (one process)."""
+    src = os.path.join(work, f"long_{n_reads}_{read_len}.fq"); dst = os.path.join(work, f"long_{n_reads}_{read_len}_s{n_sample}.fq")
+    if not os.path.exists(dst):
+        rec = os.path.getsize(src) // n_reads
+        with open(src, "rb") as f, open(dst, "wb") as o:
+            o.write(f.read(rec * n_sample))
+    stats = os.path.join(work, "stats_ref_long.json")
+    env = dict(os.environ, BM2_MODE="hotpath", BM2_STATS=stats, BM2_REPEAT=str(warmup + steps))
+    if dump_regs:
+        env["BM2_DUMP_REGS"] = dump_regs
+    subprocess.check_call([_refbin("ref_driver"), "mem"] + ONT2D_ARGS + ["-t", str(threads), "-K", "2000000000", fa, dst],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
+    st = json.load(open(stats))
+    reps = st.get("rep_s") or [st["t_bwt"] + st["t_aln"]]
+    vals = [st["reads"] / t for t in reps[warmup:]]
+    return float(np.mean(vals)), vals, st
+
+
+METRIC_LONG = "10 kbp reads/s (seed+chain+extend hot path, -x ont2d; config 5)"
+
+
+def run_longread(args, rank, world):
+    """BASELINE.json config 5: single-end 10 kbp reads with the ont2d preset (k14 W20 r10 A1 B1 O1 E1 L0, src/fastmap.cpp:812-826)
+    against the ~3 Gbp bench genome: mem_flt_chained_seeds (seed SW), wide-band extensions (bsw_warp_kernel), doubled-band retries.
+    reads/s device-timed and end to end, GCUPS of the extension stage, the reference beside it, parity against the reference's regs."""
+    import torch
+    pkg = load_package(); capi = pkg.capi
+    import longread_util as lu
+    dev = int(os.environ.get("LOCAL_RANK", 0)); torch.cuda.set_device(dev)
+    work = os.path.join(tempfile.gettempdir(), f"bm2_bench_pipe_{args.ref_mbp}_{args.pairs}")
+    fa = prepare_pipeline_inputs(work, args.ref_mbp * 1_000_000, args.pairs, seed=21)
+    index = capi.Index(fa)
+    n, L = args.long_reads, args.long_len
+    reads = prepare_longread_inputs(work, index, n, L)
+    codes = np.ascontiguousarray(reads.reshape(-1)); offs = np.arange(n + 1, dtype=np.int64) * L
+    opt = lu.ont2d_opt(capi)
+    ctx = capi.Context(dev, index=index, opt=opt)
+    int_gops = ctx.int_pipe_gops()
+    stream = torch.cuda.current_stream(); ctx.set_stream(stream.cuda_stream)
+    d_codes = torch.from_numpy(codes).cuda(); d_offs = torch.from_numpy(offs).cuda()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(max(1, args.warmup)):
+        ctx.seed_chain_extend_resident(codes, offs, d_codes.data_ptr(), d_offs.data_ptr(), False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev); sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_acc = {}
+    t0 = time.perf_counter()
+    for a, b in evs:
+        flush.fill_(1)
+        a.record(stream)
+        n_regs = ctx.seed_chain_extend_resident(codes, offs, d_codes.data_ptr(), d_offs.data_ptr(), False)
+        b.record(stream)
+        for k, v in ctx.stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / args.steps
+        cnt = ctx.counters()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ms_step = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    ctx.set_stream(None)
+    h_codes = torch.from_numpy(codes.copy()).pin_memory(); h_offs = torch.from_numpy(offs.copy()).pin_memory()
+    regs, ro = ctx.seed_chain_extend(h_codes.numpy(), h_offs.numpy(), copy=False)
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 2))
+    for _ in range(e2e_steps):
+        regs, ro = ctx.seed_chain_extend(h_codes.numpy(), h_offs.numpy(), copy=False)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    hi = host_info(); nt = hi["threads_used"]
+    ns = min(n, args.long_sample)
+    busy = min(nt, (ns + 511) // 512)        # kt_for hands out blocks of 512 reads (BATCH_SIZE, src/macro.h:48): threads that get work
+    dump = os.path.join(work, "ref_regs_long.bin")
+    cpu_v, cpu_vals, _ = reference_longread(work, fa, n, L, ns, nt, steps=1, warmup=0, dump_regs=dump)
+    n_ref_regs = check_against_reference_dump(regs, ro, dump, ns)
+    os.remove(dump)
+    bsw_ms = stage_acc.get("bsw_left", 0.0) + stage_acc.get("bsw_right", 0.0)
+    gcells = cnt["cells"] / (bsw_ms * 1e-3) / 1e9 if bsw_ms > 0 else 0.0
+    ceil = {"pack1_s32": int_gops / 14.0, "pack2_s16x2": 2 * int_gops / 14.0}
+    out = {"metric": METRIC_LONG, "value": n / (ms_step * 1e-3), "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/int32", "data": "synthetic",
+           "config": {"workload": f"config[4]: {n} single-end reads of {L} bp per step (4% subs, 3% ins, 3% del), -x ont2d, vs {args.ref_mbp} Mbp synthetic reference",
+                      "l2": "256 MB flush between steps", "regs_per_step": int(n_regs)},
+           "e2e": {"value": n / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(codes.nbytes + offs.nbytes),
+                   "d2h_bytes_per_step": int(len(regs) * capi.REG_DT.itemsize + offs.nbytes)},
+           "gpu_launches": 80 * args.steps,
+           "roofline": {"bound": "int_alu", "achieved": gcells, "peak": ceil["pack1_s32"], "unit": "Gcell/s", "frac": gcells / ceil["pack1_s32"] if int_gops else None,
+                        "traffic": None, "kernel": "extension stage (bsw_warp_kernel: one job per warp, 32-bit cells)", "kernel_ms": bsw_ms,
+                        "ceilings_gcell_s": {k: round(v, 1) for k, v in ceil.items()}},
+           "stages_ms": {k: round(v, 3) for k, v in stage_acc.items()},
+           "bsw": {"gcups": gcells, "cells_per_step": int(cnt["cells"]), "retry_left": int(cnt["retry_left"]), "retry_right": int(cnt["retry_right"])},
+           "parity": {"vs": "unmodified reference (ref_driver regs dump, -x ont2d), every field of every alignment region", "reads": ns, "regs": n_ref_regs,
+                      "identical": True},
+           "cpu_baseline": {"value": cpu_v, "unit": "reads/s", "cores": nt, "kind": "reference",
+                            "sample": f"first {ns} reads, worker_bwt+worker_aln of the unmodified reference ({_isa()}, -x ont2d), {nt} threads of which "
+                                      f"{busy} get work (kt_for deals blocks of 512 reads), one repetition",
+                            "threads_with_work": busy, "host": hi},
+           "clocks": clocks, "wall_s": wall}
+    ctx.close(); index.close()
+    return out
+
+
+def run_reference_longread(args, rank, world):
+    if rank != 0:
+        return None
+    pkg = load_package(); capi = pkg.capi
+    work = os.path.join(tempfile.gettempdir(), f"bm2_bench_pipe_{args.ref_mbp}_{args.pairs}")
+    fa = prepare_pipeline_inputs(work, args.ref_mbp * 1_000_000, args.pairs, seed=21)
+    index = capi.Index(fa)
+    prepare_longread_inputs(work, index, args.long_reads, args.long_len)
+    index.close()
+    hi = host_info(); nt = hi["threads_used"]
+    ns = min(args.long_reads, args.long_sample)
+    v, vals, st = reference_longread(work, fa, args.long_reads, args.long_len, ns, nt, steps=args.steps, warmup=args.warmup)
+    return {"impl": "reference", "metric": METRIC_LONG, "value": v, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * ns / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/int32", "data": "synthetic",
+            "config": {"workload": f"config[4]: first {ns} of {args.long_reads} single-end reads of {args.long_len} bp per step, -x ont2d, unmodified reference ({_isa()}), {nt} threads"},
+            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": nt, "kind": "reference", "sample": f"{ns} reads per step", "host": hi,
+                             "per_repetition": [round(x, 2) for x in vals]},
+            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def run_reference_pipeline(args, rank, world):
     """--impl reference: the unmodified reference's worker_bwt + worker_aln on the host cores, same metric / config as our arm.
     Each step = the first `sample` pairs of the same 1 M-read workload (bounded: the whole run ends within minutes); one process,
@@ -689,7 +837,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="pipeline", choices=["bsw", "pipeline", "cigar", "sam"])
+    ap.add_argument("--workload", default="pipeline", choices=["bsw", "pipeline", "cigar", "sam", "longread"])
+    ap.add_argument("--long-reads", type=int, default=2048, help="--workload longread: reads per step")
+    ap.add_argument("--long-len", type=int, default=10000)
+    ap.add_argument("--long-sample", type=int, default=2048, help="--workload longread: reads of the CPU arm / parity check (512 per busy thread)")
     ap.add_argument("--ref-mbp", type=int, default=3000)
     ap.add_argument("--pairs", type=int, default=500_000)
     ap.add_argument("--bsw-jobs", type=int, default=4_000_000)
@@ -697,7 +848,8 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
-        out = run_reference_pipeline(args, rank, world) if args.workload == "pipeline" else run_reference(args, rank, world)
+        out = (run_reference_pipeline(args, rank, world) if args.workload == "pipeline" else
+               run_reference_longread(args, rank, world) if args.workload == "longread" else run_reference(args, rank, world))
         if rank == 0:
             print(json.dumps(out))
         return
@@ -705,7 +857,8 @@ def main():
         import torch, torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         dist.init_process_group("nccl")
-    out = run_pipeline(args, rank, world) if args.workload == "pipeline" else (run_cigar(args, rank, world) if args.workload == "cigar" else run_sam(args, rank, world) if args.workload == "sam" else run_bsw(args, rank, world))
+    runner = {"pipeline": run_pipeline, "cigar": run_cigar, "sam": run_sam, "bsw": run_bsw, "longread": run_longread}[args.workload]
+    out = runner(args, rank, world)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

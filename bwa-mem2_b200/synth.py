@@ -302,3 +302,44 @@ def make_pairs_torch(genome, contig_lens, n_pairs: int, read_len: int = 151, see
     r1 = torch.where(gb[:, None], torch.randint(0, 4, r1.shape, dtype=torch.uint8, device=dev, generator=g), r1)
     r2 = torch.where(gb[:, None], torch.randint(0, 4, r2.shape, dtype=torch.uint8, device=dev, generator=g), r2)
     return r1.cpu().numpy(), r2.cpu().numpy()
+
+
+def make_long_reads_torch(genome, contig_lens, n_reads: int, read_len: int = 10000, seed: int = 3, sub: float = 0.04, ins: float = 0.03,
+                          dele: float = 0.03, block: int = 1024):
+    """make_long_reads on a torch device (multi-Gbp genomes; config 5: 10 kbp reads, 4 % substitutions, 3 % insertions, 3 % deletions).
+    Per template base: deleted with probability `dele`, else copied (substituted with probability `sub`); after it a random base is
+    inserted with probability `ins`.  The read is the first read_len emitted bases; half of the reads come from the reverse strand.
+    -> uint8 array (n_reads, read_len)."""
+    import torch
+    dev = genome.device
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    lens = torch.as_tensor(np.asarray(contig_lens, dtype=np.int64), device=dev)
+    starts = torch.cumsum(lens, 0) - lens
+    lt = int(read_len * 1.25) + 64
+    ok = lens > lt + 16
+    pr = torch.where(ok, lens.to(torch.float64), torch.zeros_like(lens, dtype=torch.float64))
+    out = np.empty((n_reads, read_len), np.uint8)
+    for b0 in range(0, n_reads, block):
+        n = min(block, n_reads - b0)
+        cid = torch.multinomial(pr / pr.sum(), n, replacement=True, generator=g)
+        pos = (torch.rand(n, device=dev, generator=g, dtype=torch.float64) * (lens[cid] - lt - 8).to(torch.float64)).to(torch.int64) + starts[cid]
+        ar = torch.arange(lt, device=dev)
+        fwd = genome[pos[:, None] + ar[None, :]]
+        rev = 3 - genome[(pos + lt - 1)[:, None] - ar[None, :]]
+        flip = torch.rand(n, device=dev, generator=g) < 0.5
+        t = torch.where(flip[:, None], rev, fwd)
+        u = torch.rand((n, lt), device=dev, generator=g)
+        is_del = u < dele
+        is_sub = (u >= dele) & (u < dele + sub)
+        has_ins = torch.rand((n, lt), device=dev, generator=g) < ins
+        base = torch.where(is_sub, (t + torch.randint(1, 4, t.shape, dtype=torch.uint8, device=dev, generator=g)) & 3, t)
+        rnd = torch.randint(0, 4, t.shape, dtype=torch.uint8, device=dev, generator=g)
+        emit = (~is_del).to(torch.int32) + has_ins.to(torch.int32)
+        cum = torch.cumsum(emit, 1)
+        j = torch.arange(read_len, device=dev, dtype=torch.int32)[None, :].expand(n, -1).contiguous()
+        src = torch.searchsorted(cum, j, right=True).clamp(max=lt - 1)                 # template base that emits output position j
+        k = j - (torch.gather(cum, 1, src) - torch.gather(emit, 1, src))                 # 0: first emitted base of that template position
+        first_is_copy = ~torch.gather(is_del, 1, src)
+        r = torch.where((k == 0) & first_is_copy, torch.gather(base, 1, src), torch.gather(rnd, 1, src))
+        out[b0:b0 + n] = r.cpu().numpy()
+    return out
