@@ -359,18 +359,36 @@ def run_pipeline(args, rank, world):
     if world > 1:
         torch.distributed.barrier()
     fa = os.path.join(work, "ref.fa")
-    reads = np.load(os.path.join(work, "reads.npy"))
-    if rank:   # weak scaling: every rank aligns its own batch (a rotation of the same read set)
-        reads = np.roll(reads, 2 * 1000 * rank, axis=0)
+    sa = None
+    startup = {}
+    if world > 1:
+        # the product's multi-GPU start-up (bwa_mem2_b200.shard): rank 0 reads the index files, the other ranks receive the four big
+        # arrays by ONE NCCL broadcast over NVLink and adopt them in place (bm2_create_resident); chunk c of the stream goes to rank c % N
+        import importlib
+        shard = importlib.import_module("bwa_mem2_b200.shard")
+        sa = shard.ShardedAligner(capi, fa, device=dev, keep_host_index=(rank == 0))
+        ctx = sa.ctx; index = sa.index
+        startup = {k: round(v, 3) for k, v in sa.startup.items()}
+        if rank == 0:
+            reads = np.load(os.path.join(work, "reads.npy"))
+        else:       # weak scaling over ONE stream of N x 1 M reads: this rank's chunk is its own reads, drawn from the resident reference
+            from bwa_mem2_b200 import synth
+            m = sa.meta
+            r1, r2 = synth.make_pairs_torch(sa.big[3][:m["l_pac"]], m["ann_len"], args.pairs, seed=22 + rank)
+            reads = np.empty((2 * args.pairs, r1.shape[1]), np.uint8); reads[0::2] = r1; reads[1::2] = r2
+            del r1, r2
+    else:
+        reads = np.load(os.path.join(work, "reads.npy"))
+        index = capi.Index(fa)
+        ctx = capi.Context(dev, index=index)
     n = reads.shape[0]
     codes = reads.reshape(-1); offs = (np.arange(n + 1, dtype=np.int64) * reads.shape[1])
-    index = capi.Index(fa)
-    ctx = capi.Context(dev, index=index)
     # parity of the bench workload itself: a slice against the oracle, every field of every reg
     ns = 4000
-    got, go = ctx.seed_chain_extend(codes[:ns * reads.shape[1]], offs[:ns + 1])
-    want, wo, _, rc = ol.seed_chain_extend(index, ctx.opt, codes[:ns * reads.shape[1]], offs[:ns + 1])
-    assert rc == 0 and np.array_equal(go, wo) and got.tobytes() == want.tobytes(), "bench workload differs from the oracle"
+    if index is not None:
+        got, go = ctx.seed_chain_extend(codes[:ns * reads.shape[1]], offs[:ns + 1])
+        want, wo, _, rc = ol.seed_chain_extend(index, ctx.opt, codes[:ns * reads.shape[1]], offs[:ns + 1])
+        assert rc == 0 and np.array_equal(go, wo) and got.tobytes() == want.tobytes(), "bench workload differs from the oracle"
     # ... and of the sub-batch path the timed steps use: the same reads split into sub-batches in flight give the same bytes
     nsb = min(n, 65536)
     if args.sub_batches > 1 and nsb >= 2 * 16384:
@@ -435,11 +453,20 @@ def run_pipeline(args, rank, world):
     regs, ro = ctx.seed_chain_extend(h_codes.numpy(), h_offs.numpy(), copy=False)
     n_out = len(regs)
     e2e_steps = max(1, min(args.steps, 3))
+    tab = torch.zeros((world, 4), dtype=torch.int64, device="cuda") if world > 1 else None
+    if world > 1:
+        torch.distributed.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for step_i in range(e2e_steps):
         regs, ro = ctx.seed_chain_extend(h_codes.numpy(), h_offs.numpy(), copy=False)
+        if world > 1:    # the ordering step of the sharded run: every rank learns (chunk id, owner, reads, regs) of the step's N chunks
+            mine = torch.tensor([step_i * world + rank, rank, n, len(regs)], dtype=torch.int64, device="cuda")
+            torch.distributed.all_gather_into_tensor(tab, mine)
+    if world > 1:
+        torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     if world > 1:
+        assert tab[:, 1].tolist() == list(range(world)) and int(tab[:, 2].sum()) == world * n
         t = torch.tensor([e2e_s], device="cuda"); torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_s = float(t.item())
     out = None
@@ -514,7 +541,15 @@ def run_pipeline(args, rank, world):
                                           f"({_isa()}), {nt} threads, one process, mean of {len(cpu_vals)} repetitions after 1 warm-up",
                                 "per_repetition": [round(v, 1) for v in cpu_vals], "host": hi},
                "clocks": clocks, "wall_s": wall}
-    ctx.close(); index.close()
+        if world > 1:
+            out["sharding"] = {"how": "bwa_mem2_b200.shard.ShardedAligner: one stream of N x %d reads, chunk c (= %d reads, -K %d) to rank c %% N; "
+                                      "different reads per rank; index read once on rank 0 and broadcast over NCCL (bm2_create_resident); results stay in "
+                                      "each rank's pinned buffers, the e2e region includes the chunk-table all_gather" % (n, n, n * reads.shape[1]),
+                               "startup_s_rank0": startup}
+    if sa is not None:
+        sa.close()
+    else:
+        ctx.close(); index.close()
     return out
 
 

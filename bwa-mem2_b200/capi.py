@@ -85,7 +85,7 @@ class RegResult(C.Structure):
     _fields_ = [("n", C.c_int64), ("regs", C.c_void_p), ("read_off", C.c_void_p)]
 
 
-EXPORTS = ["bm2_gather_probe", "bm2_set_sam_staged", "bm2_last_sam_stats", "bm2_gather64_gbs", "bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
+EXPORTS = ["bm2_create_resident", "bm2_gather_probe", "bm2_set_sam_staged", "bm2_last_sam_stats", "bm2_gather64_gbs", "bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
            "bm2_last_error", "bm2_extend_pairs", "bm2_extend_pairs_device", "bm2_collect_smems", "bm2_seed_chain",
            "bm2_seed_chain_extend", "bm2_last_stage_ms", "bm2_gen_cigar", "bm2_pestat", "bm2_sam_pe", "bm2_sam_se", "bm2_ksw_align2"]
 
@@ -162,16 +162,19 @@ class Index:
 class Context:
     """bm2_ctx wrapper; mirrors the reference seams (see include/bm2_b200.h)."""
 
-    def __init__(self, device: int = 0, index=None, opt: MemOpt | None = None):
+    def __init__(self, device: int = 0, index=None, opt: MemOpt | None = None, resident: bool = False):
+        """index: an Index (host arrays, uploaded by bm2_create) or an IndexDesc; resident=True: the four big arrays of the
+        descriptor are device pointers already in `device`'s memory (bm2_create_resident; the caller keeps them alive)."""
         self._ctx = C.c_void_p()
         self.opt = opt if opt is not None else default_opt()
         self._index = index
         idx_ptr = None
         if index is not None:
             idx_ptr = C.cast(C.byref(index.desc if isinstance(index, Index) else index), C.c_void_p)
-        rc = lib().bm2_create(C.byref(self._ctx), device, idx_ptr, C.cast(C.byref(self.opt), C.c_void_p))
+        f = lib().bm2_create_resident if resident else lib().bm2_create
+        rc = f(C.byref(self._ctx), device, idx_ptr, C.cast(C.byref(self.opt), C.c_void_p))
         if rc:
-            raise Bm2Error("bm2_create: " + lib().bm2_last_error(None).decode())
+            raise Bm2Error(("bm2_create_resident: " if resident else "bm2_create: ") + lib().bm2_last_error(None).decode())
 
     def close(self):
         if self._ctx:

@@ -68,10 +68,14 @@ __global__ void bsw_keys_kernel(const BswJob *jobs, int n, int a, int pair_ok, c
             for (int k = 0; k < j.qlen && !has_n; ++k) has_n = qp[(long long) k * j.qstride] > 3;
             if (!has_n) c = BSW_PAIR0 + (c >> 1);
         }
-        int t = j.tlen > 0x7FFFF ? 0x7FFFF : j.tlen;
-        // ascending sort => class ascending, target length descending (long jobs first), then qlen desc
-        int q = j.qlen > 0xFF ? 0xFF : j.qlen;
-        keys[i] = ((uint32_t) c << 27) | ((uint32_t) (0x7FFFF - t) << 8) | (uint32_t) (0xFF - q);   // c <= 21: 5 bits
+        // ascending sort => class ascending, then query length descending (long jobs first: the persistent CTAs take them first),
+        // then h0 descending, then target length: query length and h0 shape the band of every row, so the 32 jobs of a warp run rows of
+        // similar width (row-lockstep model on the reference's jobs, scripts/study_bsw_order.py: efficiency 0.92 against 0.85 for
+        // round 1's (target length, query length) key)
+        const int q = j.qlen > 0x3FF ? 0x3FF : j.qlen;
+        const int h = j.h0 < 0 ? 0 : (j.h0 > 0x3FF ? 0x3FF : j.h0);
+        const int t = (j.tlen >> 3) > 0x7F ? 0x7F : (j.tlen >> 3);
+        keys[i] = ((uint32_t) c << 27) | ((uint32_t) (0x3FF - q) << 17) | ((uint32_t) (0x3FF - h) << 7) | (uint32_t) (0x7F - t);   // c <= 21: 5 bits
         idx[i] = i;
         atomicAdd(&hist[c], 1);
     }

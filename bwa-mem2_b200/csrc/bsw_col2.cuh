@@ -116,16 +116,24 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
                 jj2 = p2_mad(one, 0x00020002u, jj2);
                 return p2_mad(en, 256u, hs);
             };
+            // The state word and the selectors of a pair are loaded one pair AHEAD of their use (the accesses are volatile asm, so the
+            // compiler keeps this order): the shared-memory latency of pair q + 1 runs under the arithmetic of pair q.
+            const bool only = pb == pe;
+            const uint32_t old = mem.ldw(pb), sel0 = mem.sel16(pb);
+            uint32_t wv = 0, sl = 0;
+            if (!only) { wv = mem.ldw(pb + 1); sl = mem.sel16(pb + 1); }
             {   // first pair (also the last one when the band is a single pair)
-                const bool only = pb == pe;
                 const uint32_t in_and = only ? (in_first & in_last) : in_first;
-                const uint32_t old = mem.ldw(pb);
-                const uint32_t nw = pair(old & in_and, mem.sel16(pb), only ? in_last : 0xFFFFFFFFu);
+                const uint32_t nw = pair(old & in_and, sel0, only ? in_last : 0xFFFFFFFFu);
                 mem.stw(pb, (nw & in_first) | (old & ~in_first));
             }
-            if (pb < pe) {
-                for (int q = pb + 1; q < pe; ++q) mem.stw(q, pair(mem.ldw(q), mem.sel16(q), 0xFFFFFFFFu));     // (unrolled x4 by the compiler, remainder first)
-                mem.stw(pe, pair(mem.ldw(pe) & in_last, mem.sel16(pe), in_last));
+            if (!only) {
+                for (int q = pb + 1; q < pe; ++q) {                       // (unrolled x4 by the compiler, remainder first)
+                    const uint32_t wn = mem.ldw(q + 1), sn = mem.sel16(q + 1);
+                    mem.stw(q, pair(wv, sl, 0xFFFFFFFFu));
+                    wv = wn; sl = sn;
+                }
+                mem.stw(pe, pair(wv & in_last, sl, in_last));
             }
             h1 = (int) ((end & 1) ? (hp & 0xFFFFu) : (hp >> 16));      // H(i, end - 1)
             ncell += (unsigned) (end - beg);

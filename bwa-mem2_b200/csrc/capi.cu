@@ -83,10 +83,17 @@ int bm2_ctx::ensure_host(HostBuf &b, size_t bytes) {
     return 0;
 }
 
-int bm2_upload_index(bm2_ctx *ctx, const bm2_index_desc *idx);   // pipeline.cu
+int bm2_upload_index(bm2_ctx *ctx, const bm2_index_desc *idx, int resident);   // pipeline.cu
 void bm2_free_index(bm2_ctx *ctx);
 
-extern "C" int bm2_create(bm2_ctx **out, int device, const bm2_index_desc *idx, const bm2_mem_opt_t *opt) {
+static int create_impl(bm2_ctx **out, int device, const bm2_index_desc *idx, const bm2_mem_opt_t *opt, int resident);
+extern "C" int bm2_create(bm2_ctx **out, int device, const bm2_index_desc *idx, const bm2_mem_opt_t *opt) { return create_impl(out, device, idx, opt, 0); }
+extern "C" int bm2_create_resident(bm2_ctx **out, int device, const bm2_index_desc *dev_idx, const bm2_mem_opt_t *opt) {
+    if (!dev_idx) { bm2_set_error(nullptr, "bm2_create_resident: dev_idx is NULL"); return 1; }
+    return create_impl(out, device, dev_idx, opt, 1);
+}
+
+static int create_impl(bm2_ctx **out, int device, const bm2_index_desc *idx, const bm2_mem_opt_t *opt, int resident) {
     bm2_ctx *ctx_for_error = nullptr;
     if (!out) { bm2_set_error(nullptr, "bm2_create: out is NULL"); return 1; }
     *out = nullptr;
@@ -121,7 +128,7 @@ extern "C" int bm2_create(bm2_ctx **out, int device, const bm2_index_desc *idx, 
         bm2_set_error(nullptr, "bm2_create: side stream/events failed"); bm2_destroy(ctx); return 1;
     }
     if (idx) {
-        if (bm2_upload_index(ctx, idx)) { bm2_set_error(nullptr, "bm2_create: " + ctx->err); bm2_destroy(ctx); return 1; }
+        if (bm2_upload_index(ctx, idx, resident)) { bm2_set_error(nullptr, "bm2_create: " + ctx->err); bm2_destroy(ctx); return 1; }
     }
     *out = ctx;
     return 0;

@@ -49,9 +49,11 @@ __global__ void occ_relayout_kernel(ulonglong2 *tab, size_t n_entries) {
     e[1] = b01; e[2] = c23;
 }
 
-int bm2_upload_index(bm2_ctx *ctx, const bm2_index_desc *idx) {
+// resident != 0: the four big arrays of `idx` are already in this device's memory (bm2_create_resident): adopted, not copied, not owned
+int bm2_upload_index(bm2_ctx *ctx, const bm2_index_desc *idx, int resident) {
     bm2_ctx *ctx_for_error = ctx;
-    auto up = [&](const void *src, size_t bytes, const void **dst) -> int {
+    auto up = [&](const void *src, size_t bytes, const void **dst, bool big) -> int {
+        if (big && resident) { *dst = src; return 0; }
         void *p = nullptr;
         BM2_CUDA_OK(cudaMalloc(&p, bytes ? bytes : 1));
         ctx->idx_allocs.push_back(p);
@@ -64,7 +66,7 @@ int bm2_upload_index(bm2_ctx *ctx, const bm2_index_desc *idx) {
     for (int i = 0; i < 5; ++i) d.count[i] = idx->count[i];
     d.n_seqs = idx->n_seqs;
     size_t n_occ = (size_t) (d.N >> 6) + 1, n_sa = (size_t) (d.N >> 3) + 1;
-    if (up(idx->cp_occ, n_occ * sizeof(bm2_cp_occ), (const void **) &d.cp_occ)) return 1;
+    if (up(idx->cp_occ, n_occ * sizeof(bm2_cp_occ), (const void **) &d.cp_occ, true)) return 1;
     {   // BM2_OCC_LAYOUT=0 keeps the file layout on the device (A/B measurements); default: half-checkpoint sectors
         const char *e = getenv("BM2_OCC_LAYOUT");
         d.occ_layout = (e && e[0] == '0') ? 0 : 1;
@@ -74,15 +76,15 @@ int bm2_upload_index(bm2_ctx *ctx, const bm2_index_desc *idx) {
             BM2_CUDA_OK(cudaDeviceSynchronize());
         }
     }
-    if (up(idx->sa_ms_byte, n_sa, (const void **) &d.sa_ms)) return 1;
-    if (up(idx->sa_ls_word, n_sa * 4, (const void **) &d.sa_ls)) return 1;
-    if (up(idx->ref_string, (size_t) d.l_pac * 2, (const void **) &d.ref)) return 1;
-    if (up(idx->ann_offset, (size_t) d.n_seqs * 8, (const void **) &d.ann_off)) return 1;
-    if (up(idx->ann_len, (size_t) d.n_seqs * 4, (const void **) &d.ann_len)) return 1;
+    if (up(idx->sa_ms_byte, n_sa, (const void **) &d.sa_ms, true)) return 1;
+    if (up(idx->sa_ls_word, n_sa * 4, (const void **) &d.sa_ls, true)) return 1;
+    if (up(idx->ref_string, (size_t) d.l_pac * 2, (const void **) &d.ref, true)) return 1;
+    if (up(idx->ann_offset, (size_t) d.n_seqs * 8, (const void **) &d.ann_off, false)) return 1;
+    if (up(idx->ann_len, (size_t) d.n_seqs * 4, (const void **) &d.ann_len, false)) return 1;
     std::vector<int32_t> zeros;
     const int32_t *alt = idx->ann_is_alt;
     if (!alt) { zeros.assign(d.n_seqs, 0); alt = zeros.data(); }
-    if (up(alt, (size_t) d.n_seqs * 4, (const void **) &d.ann_alt)) return 1;
+    if (up(alt, (size_t) d.n_seqs * 4, (const void **) &d.ann_alt, false)) return 1;
     d.loaded = true;
     return 0;
 }

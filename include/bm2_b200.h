@@ -90,6 +90,12 @@ void bm2_index_free(bm2_index_desc *idx);
 /* Create a device context on CUDA device `device`: uploads the index to HBM and fixes the
  * parameters.  `idx` may be NULL for a BSW-only context (bm2_extend_pairs). */
 int  bm2_create(bm2_ctx **out, int device, const bm2_index_desc *idx, const bm2_mem_opt_t *opt);
+/* The same for an index that is ALREADY in the memory of `device` (multi-GPU start-up, SURVEY 8e: one rank reads the index files, the
+ * others receive the four big arrays by one NCCL broadcast over NVLink instead of 8 x 16 GB of disk + PCIe traffic): `cp_occ`,
+ * `sa_ms_byte`, `sa_ls_word` and `ref_string` of `dev_idx` are DEVICE pointers (file layout, sizes as in bm2_index_desc), the small
+ * `ann_*` arrays HOST pointers.  The context does not own the four arrays: the caller keeps them alive until bm2_destroy and must not
+ * read `cp_occ` afterwards - it is permuted in place into the device layout (fm_device.cuh) unless BM2_OCC_LAYOUT=0. */
+int  bm2_create_resident(bm2_ctx **out, int device, const bm2_index_desc *dev_idx, const bm2_mem_opt_t *opt);
 void bm2_destroy(bm2_ctx *ctx);
 const char *bm2_last_error(const bm2_ctx *ctx);   /* ctx may be NULL: last create error */
 /* Launch on a caller-owned CUDA stream (cudaStream_t as void*), e.g. the caller's framework stream,

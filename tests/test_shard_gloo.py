@@ -1,6 +1,7 @@
-"""N>1 path on CPU: two gloo ranks shard the chunks of one read set (bwa_mem2_b200.shard), each runs the hot path
-(the CPU oracle stands in for the GPU here) on its own chunks with no data-path collective, rank 0 gathers; the
-result must equal the single-process result read for read."""
+"""N>1 path on CPU: two gloo ranks deal the chunks of one read stream (bwa_mem2_b200.shard.ShardedAligner), each runs the hot path on
+its own chunks with no data-path collective (the CPU oracle stands in for the GPU context here; tests/test_shard_gpu.py runs the same
+flow on the GPU with the broadcast index), rank 0 gathers in input order; the result must equal the single-process result read for
+read.  Also: chunk_bounds cuts the stream where the reference's bseq_read_orig does."""
 import os, sys
 import numpy as np
 import torch
@@ -22,20 +23,23 @@ def _worker(rank, world, port, golden_dir, out):
     idx = pkg.capi.Index(golden_dir + "/c0_index/ref.fa"); opt = pkg.capi.default_opt()
     reads = np.load(golden_dir + "/c0_reads.npz")["reads"]
     n, L = reads.shape
-    mine = []
-    for ci, (s, e) in shard.rank_chunks(n, 512, rank, world):
-        codes = reads[s:e].reshape(-1); offs = (np.arange(e - s + 1) * L).astype(np.int64)
-        regs, ro, _, rc = ol.seed_chain_extend(idx, opt, codes, offs)
-        mine.append((ci, s, regs.tobytes(), ro.tolist()))
-    gathered = [None] * world
-    dist.all_gather_object(gathered, mine)
-    cnt = torch.tensor([sum(len(m[3]) - 1 for m in mine)]); dist.all_reduce(cnt)     # the only collective: a counter
+    codes = reads.reshape(-1); offs = (np.arange(n + 1) * L).astype(np.int64)
+
+    def oracle(c, o):
+        regs, ro, _, rc = ol.seed_chain_extend(idx, opt, c, o)
+        assert rc == 0
+        return regs, ro
+    sa = shard.ShardedAligner(pkg.capi, golden_dir + "/c0_index/ref.fa", compute=oracle)
+    bounds = shard.chunk_bounds((n, L), 40_000, paired=True)           # 133 pairs per chunk: 4 chunks, not aligned to 512-read blocks
+    res = sa.align_chunks(codes, offs, bounds)
+    table = sa.chunk_table(res)
+    assert [t[0] for t in table] == list(range(len(bounds))) and all(t[1] == t[0] % world for t in table)
+    regs, ro = sa.gather_in_order(res, dst=0)
+    cnt = torch.tensor([sum(len(r[3]) - 1 for r in res)]); dist.all_reduce(cnt)     # the only data-path collective: a counter
     if rank == 0:
-        allc = sorted([c for g in gathered for c in g])
-        blob = b"".join(c[2] for c in allc)
-        counts = np.concatenate([np.diff(np.array(c[3])) for c in allc])
-        np.save(out + ".counts.npy", counts); open(out + ".regs.bin", "wb").write(blob)
         assert int(cnt.item()) == n
+        np.save(out + ".off.npy", ro); open(out + ".regs.bin", "wb").write(regs.tobytes())
+        np.save(out + ".bounds.npy", np.array(bounds))
     dist.barrier(); dist.destroy_process_group()
 
 
@@ -45,16 +49,33 @@ def test_two_rank_sharding_equals_single_process(pkg, golden_dir, tmp_path):
     mp.spawn(_worker, args=(2, 29571, golden_dir, out), nprocs=2, join=True)
     idx = pkg.capi.Index(golden_dir + "/c0_index/ref.fa"); opt = pkg.capi.default_opt()
     reads = np.load(golden_dir + "/c0_reads.npz")["reads"]
-    codes = reads.reshape(-1); offs = (np.arange(len(reads) + 1) * reads.shape[1]).astype(np.int64)
-    regs, ro, _, rc = ol.seed_chain_extend(idx, opt, codes, offs)
-    assert np.array_equal(np.load(out + ".counts.npy"), np.diff(ro))
-    assert open(out + ".regs.bin", "rb").read() == regs.tobytes()
+    n, L = reads.shape
+    # the single-process result, chunk by chunk as the reference would process the stream with the same -K
+    bounds = [tuple(b) for b in np.load(out + ".bounds.npy")]
+    assert len(bounds) == 4 and bounds[0] == (0, 266)
+    parts = []; counts = []
+    for s, e in bounds:
+        regs, ro, _, rc = ol.seed_chain_extend(idx, opt, reads[s:e].reshape(-1), (np.arange(e - s + 1) * L).astype(np.int64))
+        parts.append(regs.tobytes()); counts.append(np.diff(ro))
+    assert np.array_equal(np.diff(np.load(out + ".off.npy")), np.concatenate(counts))
+    assert open(out + ".regs.bin", "rb").read() == b"".join(parts)
 
 
-def test_chunk_ranges_are_block_aligned(pkg):
+def test_chunk_bounds_follow_the_reference_reader(pkg):
     import importlib
     shard = importlib.import_module("bwa_mem2_b200.shard")
-    r = shard.chunk_ranges(100_000, 33_000)
-    assert all(s % 512 == 0 for s, _ in r) and r[-1][1] == 100_000 and r[0] == (0, 33_280)
-    a = shard.rank_chunks(100_000, 33_000, 0, 2); b = shard.rank_chunks(100_000, 33_000, 1, 2)
-    assert sorted(a + b) == list(enumerate(r))
+    # uniform 151-bp pairs, -K 10 Mbp: ceil(1e7 / 302) = 33113 pairs per chunk (src/bwa.cpp:170-216)
+    b = shard.chunk_bounds((200_000, 151), 10_000_000, paired=True)
+    assert b[0] == (0, 66_226) and b[-1][1] == 200_000 and all(s % 2 == 0 for s, _ in b)
+    # ragged lengths: a chunk ends at the first even read count whose bases reach the task size
+    rng = np.random.default_rng(5)
+    lens = rng.integers(30, 300, 5000)
+    bb = shard.chunk_bounds(lens, 50_000, paired=True)
+    assert bb[0][0] == 0 and bb[-1][1] == 5000 and all(bb[i][1] == bb[i + 1][0] for i in range(len(bb) - 1))
+    for s, e in bb[:-1]:
+        tot = int(lens[s:e].sum())
+        assert (e - s) % 2 == 0 and tot >= 50_000 and int(lens[s:e - 2].sum()) < 50_000
+    assert shard.chunk_bounds((0, 151), 1000) == [] and shard.chunk_bounds((10, 100), 250, paired=False) == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert shard.task_size(10_000_000, 8) == 80_000_000 and shard.task_size(10_000_000, 8, fixed_k=123) == 123
+    r = shard.rank_chunks(bb, 1, 3)
+    assert [i for i, _ in r] == list(range(1, len(bb), 3))
