@@ -814,6 +814,87 @@ def run_reference_longread(args, rank, world):
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
+METRIC_SAM = "paired 151bp reads/s, FASTQ bytes in -> SAM text out (parse+encode, seed+chain+extend, pestat, SAM stage, formatting)"
+
+
+def reference_mem_full(work, fa, n_pairs_sample, threads, sam_out):
+    """The unmodified reference's whole mem path on the first pairs of the bench reads (ref_driver BM2_MODE=ref = bwa-mem2 mem with the phase
+    timers): reads/s over worker_bwt + worker_aln + worker_sam (FASTQ parsing, mem_pestat and the SAM write are NOT in its time)."""
+    r1 = os.path.join(work, "r1.fq"); r2 = os.path.join(work, "r2.fq")
+    s1 = os.path.join(work, f"s1_{n_pairs_sample}.fq"); s2 = os.path.join(work, f"s2_{n_pairs_sample}.fq")
+    if not os.path.exists(s1):
+        rec = os.path.getsize(r1) // (np.load(os.path.join(work, "reads.npy"), mmap_mode="r").shape[0] // 2)
+        for src, dst in ((r1, s1), (r2, s2)):
+            with open(src, "rb") as f, open(dst, "wb") as o:
+                o.write(f.read(rec * n_pairs_sample))
+    stats = os.path.join(work, "stats_ref_full.json")
+    env = dict(os.environ, BM2_MODE="ref", BM2_STATS=stats)
+    with open(sam_out, "w") as f:
+        subprocess.check_call([_refbin("ref_driver"), "mem", "-t", str(threads), "-K", "1000000000", fa, s1, s2], stdout=f, stderr=subprocess.DEVNULL, env=env)
+    st = json.load(open(stats))
+    return st["reads"] / (st["t_bwt"] + st["t_aln"] + st["t_sam"]), st, s1, s2
+
+
+def run_fastq2sam(args, rank, world):
+    """SURVEY 8f item 3 end to end: the raw bytes of two FASTQ files in host memory -> SAM text in host memory, through the C ABI:
+    bm2_fastq_encode (parse + encode on the GPU), bm2_seed_chain_extend_resident, bm2_pestat, bm2_sam_pe (staged rescue), bm2_sam_format
+    (host threads).  One chunk per step (the sample), wall clock.  Beside it the unmodified reference's mem on the same files and threads;
+    the two SAM texts must be byte-identical (header lines aside)."""
+    import torch
+    pkg = load_package(); capi = pkg.capi
+    dev = int(os.environ.get("LOCAL_RANK", 0)); torch.cuda.set_device(dev)
+    work = os.path.join(tempfile.gettempdir(), f"bm2_bench_pipe_{args.ref_mbp}_{args.pairs}")
+    fa = prepare_pipeline_inputs(work, args.ref_mbp * 1_000_000, args.pairs, seed=21)
+    hi = host_info(); nt = hi["threads_used"]
+    sample_pairs = min(args.pairs, args.sam_pairs)
+    ref_sam = os.path.join(work, "ref_full.sam")
+    cpu_v, cpu_st, s1, s2 = reference_mem_full(work, fa, sample_pairs, nt, ref_sam)
+    b1 = open(s1, "rb").read(); b2 = open(s2, "rb").read()
+    index = capi.Index(fa)
+    contigs = [l.split()[1] for i, l in enumerate(open(fa + ".ann")) if i % 2 == 1]
+    opt = capi.default_opt(); opt.flag |= 0x2
+    ctx = capi.Context(dev, index=index, opt=opt)
+    ctx.set_sam_staged(1)
+
+    def step():
+        t = [time.perf_counter()]
+        fq = ctx.fastq_encode(b1, b2); t.append(time.perf_counter())
+        regs, ro = ctx.seed_chain_extend_resident(fq["codes"], fq["offsets"], fq["d_codes"], fq["d_offsets"], True, return_arrays=True); t.append(time.perf_counter())
+        pes = capi.pestat(opt, index.desc.l_pac, regs, ro); t.append(time.perf_counter())
+        recs, xa, cig, md = ctx.sam_pe(fq["codes"], fq["offsets"], regs, ro, pes); t.append(time.perf_counter())
+        text = capi.sam_format(recs, xa, cig, md, fq["codes"], fq["offsets"], contigs, read_names=fq["names"], quals=fq["quals"], n_threads=nt); t.append(time.perf_counter())
+        return text, np.diff(t), fq["n_reads"]
+
+    for _ in range(max(1, args.warmup)):
+        text, _, n = step()
+    want = b"".join(ln for ln in open(ref_sam, "rb") if not ln.startswith(b"@"))
+    if text != want:
+        a_ = text.split(b"\n"); b_ = want.split(b"\n")
+        bad = [i for i in range(min(len(a_), len(b_))) if a_[i] != b_[i]][:3]
+        raise AssertionError(f"FASTQ -> SAM text differs from the unmodified reference: {len(a_)} vs {len(b_)} lines, first differing {[(a_[i][:200], b_[i][:200]) for i in bad]}")
+    os.remove(ref_sam)
+    torch.cuda.synchronize()
+    acc = np.zeros(5); t0 = time.perf_counter()
+    for _ in range(args.steps):
+        text, dt, n = step(); acc += dt
+    wall = (time.perf_counter() - t0) / args.steps
+    acc /= args.steps
+    out = {"metric": METRIC_SAM, "value": n / wall, "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/int16/f64", "data": "synthetic",
+           "config": {"workload": f"first {n} reads ({n // 2} pairs) of the default workload as FASTQ bytes ({len(b1) + len(b2)} B) -> {len(text)} B of SAM text, "
+                                  f"{args.ref_mbp} Mbp reference; one chunk per step, wall clock; python binding overheads (array copies, name list) included"},
+           "stage_s": dict(zip(["fastq_encode", "seed_chain_extend", "pestat", "sam_pe_staged", "sam_format"], [round(float(x), 4) for x in acc])),
+           "e2e": {"value": n / wall, "unit": "reads/s", "h2d_bytes_per_step": int(len(b1) + len(b2)), "d2h_bytes_per_step": int(len(text))},
+           "gpu_launches": 80 * args.steps,
+           "parity": {"vs": "SAM text of the unmodified reference (bwa-mem2 mem through ref_driver) on the same FASTQ files", "lines": int(text.count(b"\n")),
+                      "identical": True},
+           "cpu_baseline": {"value": cpu_v, "unit": "reads/s", "cores": nt, "kind": "reference",
+                            "sample": f"the same {n} reads, worker_bwt + worker_aln + worker_sam of the unmodified reference ({_isa()}), {nt} threads "
+                                      "(its FASTQ parsing, mem_pestat and SAM write are not in its time)", "host": hi}}
+    ctx.close(); index.close()
+    return out
+
+
 def run_reference_pipeline(args, rank, world):
     """--impl reference: the unmodified reference's worker_bwt + worker_aln on the host cores, same metric / config as our arm.
     Each step = the first `sample` pairs of the same 1 M-read workload (bounded: the whole run ends within minutes); one process,
@@ -872,7 +953,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="pipeline", choices=["bsw", "pipeline", "cigar", "sam", "longread"])
+    ap.add_argument("--workload", default="pipeline", choices=["bsw", "pipeline", "cigar", "sam", "longread", "fastq2sam"])
+    ap.add_argument("--sam-pairs", type=int, default=100_000, help="--workload fastq2sam: pairs per chunk")
     ap.add_argument("--long-reads", type=int, default=2048, help="--workload longread: reads per step")
     ap.add_argument("--long-len", type=int, default=10000)
     ap.add_argument("--long-sample", type=int, default=2048, help="--workload longread: reads of the CPU arm / parity check (512 per busy thread)")
@@ -892,7 +974,7 @@ def main():
         import torch, torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         dist.init_process_group("nccl")
-    runner = {"pipeline": run_pipeline, "cigar": run_cigar, "sam": run_sam, "bsw": run_bsw, "longread": run_longread}[args.workload]
+    runner = {"pipeline": run_pipeline, "cigar": run_cigar, "sam": run_sam, "bsw": run_bsw, "longread": run_longread, "fastq2sam": run_fastq2sam}[args.workload]
     out = runner(args, rank, world)
     if rank == 0:
         print(json.dumps(out))

@@ -68,6 +68,39 @@ class CigarResult(C.Structure):
     _fields_ = [("n", C.c_int64), ("recs", C.c_void_p), ("n_ops", C.c_int64), ("cigar", C.c_void_p), ("n_md", C.c_int64), ("md", C.c_void_p)]
 
 
+class SamTextIn(C.Structure):
+    _fields_ = [("res", C.c_void_p), ("reads", C.c_void_p), ("names", C.c_void_p), ("quals", C.c_void_p), ("contig_names", C.c_void_p)]
+
+
+class FastqBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("d_codes", C.c_void_p), ("d_offsets", C.c_void_p), ("codes", C.c_void_p), ("offsets", C.c_void_p),
+                ("quals", C.c_void_p), ("name_beg", C.c_void_p), ("name_len", C.c_void_p)]
+
+
+def sam_format(recs, xa, cigar, md, codes, offsets, contig_names, read_names=None, quals=None, n_threads=1) -> bytes:
+    """bm2_sam_format: the SAM text of a batch from the records of bm2_sam_pe / bm2_sam_se (one line per record, QNAME to the last tag)."""
+    recs = np.ascontiguousarray(recs, SAM_REC_DT); xa = np.ascontiguousarray(xa, SAM_XA_DT)
+    cigar = np.ascontiguousarray(cigar, np.uint32); md = np.ascontiguousarray(md, np.uint8)
+    codes = np.ascontiguousarray(codes, np.uint8); offsets = np.ascontiguousarray(offsets, np.int64)
+    res = SamResult(len(recs), recs.ctypes.data, len(xa), xa.ctypes.data, len(cigar), cigar.ctypes.data, len(md), md.ctypes.data)
+    rb = ReadBatch(len(offsets) - 1, codes.ctypes.data, offsets.ctypes.data)
+    cn = (C.c_char_p * len(contig_names))(*[s.encode() for s in contig_names])
+    rn = (C.c_char_p * len(read_names))(*[s.encode() if isinstance(s, str) else bytes(s) for s in read_names]) if read_names is not None else None
+    q = np.ascontiguousarray(np.frombuffer(quals, np.uint8) if isinstance(quals, (bytes, bytearray)) else quals, np.uint8) if quals is not None else None
+    tin = SamTextIn(C.cast(C.byref(res), C.c_void_p), C.cast(C.byref(rb), C.c_void_p), C.cast(rn, C.c_void_p) if rn is not None else None,
+                    q.ctypes.data if q is not None else None, C.cast(cn, C.c_void_p))
+    text = C.c_void_p(); n = C.c_int64()
+    f = lib().bm2_sam_format
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rc = f(C.byref(tin), int(n_threads), C.byref(text), C.byref(n))
+    if rc:
+        raise Bm2Error(f"bm2_sam_format failed ({rc})")
+    out = C.string_at(text, n.value)
+    lib().bm2_free.argtypes = [C.c_void_p]
+    lib().bm2_free(text)
+    return out
+
+
 class ReadBatch(C.Structure):
     _fields_ = [("n_reads", C.c_int32), ("codes", C.c_void_p), ("offsets", C.c_void_p)]
 
@@ -85,7 +118,7 @@ class RegResult(C.Structure):
     _fields_ = [("n", C.c_int64), ("regs", C.c_void_p), ("read_off", C.c_void_p)]
 
 
-EXPORTS = ["bm2_create_resident", "bm2_gather_probe", "bm2_set_sam_staged", "bm2_last_sam_stats", "bm2_gather64_gbs", "bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
+EXPORTS = ["bm2_fastq_encode", "bm2_sam_format", "bm2_free", "bm2_create_resident", "bm2_gather_probe", "bm2_set_sam_staged", "bm2_last_sam_stats", "bm2_gather64_gbs", "bm2_set_sub_batches", "bm2_seed_chain_extend_resident", "bm2_last_counters", "bm2_set_stream", "bm2_int_pipe_gops", "bm2_abi_version", "bm2_opt_init", "bm2_index_load", "bm2_index_free", "bm2_create", "bm2_destroy",
            "bm2_last_error", "bm2_extend_pairs", "bm2_extend_pairs_device", "bm2_collect_smems", "bm2_seed_chain",
            "bm2_seed_chain_extend", "bm2_last_stage_ms", "bm2_gen_cigar", "bm2_pestat", "bm2_sam_pe", "bm2_sam_se", "bm2_ksw_align2"]
 
@@ -288,6 +321,25 @@ class Context:
             dt = np.dtype(dt)
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * dt.itemsize,)).view(dt).copy() if n else np.zeros(0, dt)
         return arr(res.recs, res.n_recs, SAM_REC_DT), arr(res.xa, res.n_xa, SAM_XA_DT), arr(res.cigar, res.n_ops, "<u4"), arr(res.md, res.n_md, "u1")
+
+    def fastq_encode(self, buf1: bytes, buf2: bytes | None = None):
+        """bm2_fastq_encode: raw FASTQ bytes of a chunk (two files for pairs) -> dict(n_reads, codes, offsets, quals, names, d_codes, d_offsets);
+        the device pointers stay valid until the context's next call."""
+        b = FastqBatch()
+        f = lib().bm2_fastq_encode
+        f.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p]
+        self._check(f(self._ctx, buf1, len(buf1), buf2, len(buf2) if buf2 is not None else 0, C.byref(b)), "bm2_fastq_encode")
+        n = b.n_reads
+        offs = np.ctypeslib.as_array(C.cast(b.offsets, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
+        tot = int(offs[-1])
+        codes = np.ctypeslib.as_array(C.cast(b.codes, C.POINTER(C.c_uint8)), shape=(max(tot, 1),))[:tot].copy()
+        quals = np.ctypeslib.as_array(C.cast(b.quals, C.POINTER(C.c_uint8)), shape=(max(tot, 1),))[:tot].copy()
+        nb = np.ctypeslib.as_array(C.cast(b.name_beg, C.POINTER(C.c_int64)), shape=(max(n, 1),))[:n].copy()
+        nl = np.ctypeslib.as_array(C.cast(b.name_len, C.POINTER(C.c_int32)), shape=(max(n, 1),))[:n].copy()
+        bufs = (buf1, buf2 if buf2 is not None else buf1)
+        stride = 2 if buf2 is not None else 1
+        names = [bufs[r % stride][nb[r]:nb[r] + nl[r]] for r in range(n)]
+        return dict(n_reads=n, codes=codes, offsets=offs, quals=quals, names=names, d_codes=b.d_codes, d_offsets=b.d_offsets)
 
     def set_sam_staged(self, on: int):
         """bm2_set_sam_staged: 1 / 2 = the rescue's local alignments as a batch (one window per warp / per thread) before the per-pair kernel, 0 = inside it."""

@@ -35,8 +35,8 @@ struct bm2_ctx {
     // seam 1
     DevBuf io_pairs, io_ref, io_qer, bsw_jobs, bsw_outs, bsw_scratch;
     // seam 2 (pipeline.cu)
-    DevBuf d[96];
-    HostBuf h[32];
+    DevBuf d[128];         // slots: pipeline.cu 0-47, cigar.cu 48-63, sam.cu 64-83 + 90-95, ksw.cu 84-89, fastq.cu 100-111
+    HostBuf h[48];         // slots: pipeline.cu 0-7, cigar.cu 8-15, sam.cu 16-23, fastq.cu 24-31
     std::vector<cudaEvent_t> events;
     std::vector<const char *> stage_names;
     std::vector<float> stage_ms;

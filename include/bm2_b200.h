@@ -324,6 +324,36 @@ int bm2_sam_pe(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *re
 /* The single-end branch of worker_sam (src/bwamem.cpp:1320-1334: mem_mark_primary_se, -5, mem_reg2sam without a mate) for a batch of reads;
  * same records (no RNEXT / PNEXT / TLEN).  id_base: number of reads before this batch in the run. */
 int bm2_sam_se(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs, const int64_t *read_off, int64_t id_base, bm2_sam_result *out);
+/* ---- seam 0 (host I/O on the fast side): FASTQ bytes -> read batch ----------------------------------------------
+ * Replaces the parsing of bseq_read_orig (src/bwa.cpp:170-216 over kseq.h; name up to the first blank, trim_readno :62-66) and the base
+ * encoding at the head of mem_kernel1_core (src/bwamem.cpp:992-1000, nst_nt4_table).  buf1 / buf2: the raw bytes of a chunk of the two
+ * FASTQ files (buf2 NULL: single-end); the result interleaves them (reads 2i / 2i+1 from buf1 / buf2).  Parsing and encoding run on the
+ * GPU; the batch is left on the device for bm2_seed_chain_extend_resident and copied to pinned host memory for the SAM stage.
+ * Four-line records only; a chunk must stay below 2 GiB per buffer.  Arrays are owned by the context (valid until its next call). */
+typedef struct bm2_fastq_batch {
+    int32_t n_reads;
+    const uint8_t *d_codes; const int64_t *d_offsets;     /* DEVICE: codes 0-4 ('-' = 5 as nst_nt4_table), n_reads + 1 offsets */
+    const uint8_t *codes;   const int64_t *offsets;       /* HOST copies                                                      */
+    const char *quals;                                    /* HOST: qualities laid out like codes                              */
+    const int64_t *name_beg; const int32_t *name_len;     /* HOST: QNAME of read r = its buffer [name_beg[r], + name_len[r])  */
+} bm2_fastq_batch;
+int  bm2_fastq_encode(bm2_ctx *ctx, const char *buf1, int64_t n1, const char *buf2, int64_t n2, bm2_fastq_batch *out);
+
+/* ---- seam 5 (host I/O on the fast side): SAM text of a chunk --------------------------------------------------------
+ * The formatting half of mem_aln2sam (src/bwamem.cpp:1592-1730): QNAME, the tab-separated columns, SEQ / QUAL trimmed by the record's
+ * hard clips and reverse-complemented on the reverse strand, tags NM MD MC AS XS SA pa XA in the reference's order, one line per
+ * bm2_sam_rec, byte for byte what `bwa-mem2 mem` prints for the record (without the constant -C / -R / -V additions).  Host code on
+ * n_threads threads (read ranges).  *text is malloc'd (release with bm2_free), NUL-terminated, *len bytes. */
+typedef struct bm2_sam_text_in {
+    const bm2_sam_result *res;          /* records of bm2_sam_pe / bm2_sam_se for this batch                       */
+    const bm2_read_batch *reads;        /* the batch (codes 0-4, offsets): SEQ                                     */
+    const char *const *names;           /* QNAME per read (mates carry the same name); NULL: "r<index>"            */
+    const char *quals;                  /* qualities laid out like reads->codes (same offsets); NULL: '*'          */
+    const char *const *contig_names;    /* RNAME by contig id (bntann1_t::name)                                    */
+} bm2_sam_text_in;
+int  bm2_sam_format(const bm2_sam_text_in *in, int n_threads, char **text, int64_t *len);
+void bm2_free(void *p);
+
 /* Staged mate rescue inside bm2_sam_pe (same records, other kernels): the windows mem_matesw (src/bwamem_pair.cpp:150-283) can ask for are
  * listed for all pairs of a wave from the regions before any rescue, aligned as one batch with one window per warp (the job shape of
  * bm2_ksw_align2; the reference batches the same alignments across pairs in its kswv path, src/bwamem_pair.cpp:930-1248, src/kswv.cpp),
