@@ -713,7 +713,9 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     if (!attr_set) {   // one function, several dynamic sizes: raise the limit once per device
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_thread_kernel<SmemPacked8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        BM2_CUDA_OK(cudaFuncSetAttribute(bsw_col2_kernel<BSW_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BM2_CUDA_OK(cudaFuncSetAttribute(bsw_col2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BM2_CUDA_OK(cudaFuncSetAttribute(bsw_col2_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BM2_CUDA_OK(cudaFuncSetAttribute(bsw_col2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         BM2_CUDA_OK(cudaFuncSetAttribute(bsw_pair_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -749,10 +751,19 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
         if (col2_ok && !is16 && bound <= 256) {
             // two columns per packed instruction (bsw_col2.cuh): state 2 B per column in pair words, selectors 1 B per column
             const int NP = (W + 1) / 2;                       // state words: pairs over columns 0 .. bound + 1; selectors: 2 B per pair
-            const size_t smem2 = (size_t) NP * 6 * BSW_THREADS;
-            int cps = (int) (smem_budget / (smem2 + 1024)); if (cps < 1) cps = 1; if (cps > max_ctas) cps = max_ctas;
-            int nb = (n + BSW_THREADS - 1) / BSW_THREADS; if (nb > n_sm * cps) nb = n_sm * cps;
-            bsw_col2_kernel<BSW_THREADS><<<nb, BSW_THREADS, smem2, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, NP, d_cells);
+            // threads per CTA: the size that keeps the most threads resident per SM (shared memory is what limits this kernel's
+            // occupancy: 6 B per column pair and thread; 64- or 96-thread CTAs waste less of the 227 KB than 128-thread ones)
+            int nthr2 = 128, best_res = 0, best_cps = 1;
+            for (int t = 128; t >= 64; t -= 32) {
+                int cps = (int) (smem_budget / ((size_t) NP * 6 * t + 1024)); if (cps < 1) cps = 1; if (cps > max_ctas * (128 / t)) cps = max_ctas * (128 / t);
+                if (cps > 32) cps = 32;
+                if (cps * t > best_res) { best_res = cps * t; nthr2 = t; best_cps = cps; }
+            }
+            const size_t smem2 = (size_t) NP * 6 * nthr2;
+            int nb = (n + nthr2 - 1) / nthr2; if (nb > n_sm * best_cps) nb = n_sm * best_cps;
+#define BM2_COL2_LAUNCH(T) bsw_col2_kernel<T><<<nb, T, smem2, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, NP, d_cells)
+            if (nthr2 == 128) BM2_COL2_LAUNCH(128); else if (nthr2 == 96) BM2_COL2_LAUNCH(96); else BM2_COL2_LAUNCH(64);
+#undef BM2_COL2_LAUNCH
             continue;
         }
         if (is16) bsw_thread_kernel<SmemPacked><<<nblk, nthr, smem, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, W, d_cells);

@@ -91,6 +91,7 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
         if (i + 1 < tlen) tb_next = (int) tptr[(long long) (i + 1) * tstride];
         const uint32_t tbl = p2_score_table(tb, p.a, p.b);
         uint32_t key2 = 0;
+        uint32_t fw = 0, lw = 0;            // the state words just written for the first / last pair of the row (band shrink below)
         if (end > beg) {
             const int pb = beg >> 1, pe = (end - 1) >> 1;
             const uint32_t in_first = (beg & 1) ? 0xFFFF0000u : 0xFFFFFFFFu, in_last = (end & 1) ? 0x0000FFFFu : 0xFFFFFFFFu;
@@ -125,7 +126,8 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
             {   // first pair (also the last one when the band is a single pair)
                 const uint32_t in_and = only ? (in_first & in_last) : in_first;
                 const uint32_t nw = pair(old & in_and, sel0, only ? in_last : 0xFFFFFFFFu);
-                mem.stw(pb, (nw & in_first) | (old & ~in_first));
+                fw = lw = (nw & in_first) | (old & ~in_first);
+                mem.stw(pb, fw);
             }
             if (!only) {
                 for (int q = pb + 1; q < pe; ++q) {                       // (unrolled x4 by the compiler, remainder first)
@@ -133,7 +135,8 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
                     mem.stw(q, pair(wv, sl, 0xFFFFFFFFu));
                     wv = wn; sl = sn;
                 }
-                mem.stw(pe, pair(wv & in_last, sl, in_last));
+                lw = pair(wv & in_last, sl, in_last);
+                mem.stw(pe, lw);
             }
             h1 = (int) ((end & 1) ? (hp & 0xFFFFu) : (hp >> 16));      // H(i, end - 1)
             ncell += (unsigned) (end - beg);
@@ -160,11 +163,30 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
             const int pen = di > dj ? di - dj : dj - di;       // SIMD z-drop: no e_del/e_ins factor, no `zdrop > 0` guard (ZSCORE8/16)
             if (best - m - pen > qk.zthr) break;
         }
-        int j;
-        for (j = beg; j < end && mem.ldh(j) == 0u; ++j) {}
+        // Band shrink (src/bandedSWA.cpp:222-225): beg = first column of [beg, end) with a non-zero state, end = last one + 2.  The two
+        // columns at either edge are decided from the words just written (registers); shared memory is only scanned when both are zero
+        // (round 2: the scan loops - a load, a compare and a branch per step, 19 of 32 lanes - took 11 % of the kernel's samples).
+        int j = beg;                                           // (here end > beg: an empty row has m == 0 and left the loop above)
+        {
+            bool scan = false;
+            if (!(beg & 1)) {
+                if ((fw & 0xFFFFu) == 0u) { j = beg + 1; if (j < end && (fw >> 16) == 0u) { j = beg + 2; scan = true; } }
+            } else if ((fw >> 16) == 0u) { j = beg + 1; scan = true; }
+            if (scan) for (; j < end && mem.ldh(j) == 0u; ++j) {}
+        }
         beg = j;
-        j = end;                                               // column `end` holds {h1, 0}: no load for the usual case
-        if (h1 == 0) for (--j; j >= beg && mem.ldh(j) == 0u; --j) {}
+        j = end;                                               // column `end` holds {h1, 0}: nothing to look at in the usual case
+        if (h1 == 0) {
+            bool scan = false;
+            --j;
+            if (end & 1) {                                     // column end - 1 is the low half of the last word
+                if (j >= beg && (lw & 0xFFFFu) == 0u) { --j; scan = true; }
+            } else if (j >= beg && (lw >> 16) == 0u) {         // column end - 1 is its high half, end - 2 its low half
+                --j;
+                if (j >= beg && (lw & 0xFFFFu) == 0u) { --j; scan = true; }
+            }
+            if (scan) for (; j >= beg && mem.ldh(j) == 0u; --j) {}
+        }
         end = j + 2 < qlen ? j + 2 : qlen;
     }
     o.score = best; o.qle = best_j + 1; o.tle = best_i + 1; o.gtle = best_ie + 1; o.gscore = gscore; o.max_off = max_off;

@@ -386,18 +386,34 @@ BM2_HD int seed_sw_d(const ContigView &cv, const SwParams &p, const uint8_t *ref
     return local_sw_score_d(qe - qb, query + qb, (int) (re - rb), ref + rb, p);
 }
 
-// drops the seeds of the surviving chains whose local SW score is below min_hsp (computed on the host with the
-// reference's double arithmetic); seeds keep their order, survivors get score = SW score (or len*a when skipped)
-BM2_HD void chain_flt_seeds_d(const ContigView &cv, const SwParams &p, const uint8_t *ref, int l_query, const uint8_t *query,
-                              int min_hsp, const ChainStripe &ws, int n_kept)
-{
+// mem_flt_chained_seeds (src/bwamem.cpp:472-504) in three steps, so that a warp can share the local alignments of ONE read (long reads:
+// hundreds of seeds per read, each a <= 200 x 200 local alignment - the chain stage's whole cost for 10 kbp reads):
+//   list:  the seeds of the surviving chains, in chain order, into ws.ord (free after chain_read_d)        [one lane]
+//   score: s.score = seed_sw_d(...) for every listed seed, independent of each other                        [all lanes, strided]
+//   apply: drop the seeds whose score is below min_hsp (computed on the host with the reference's double arithmetic); seeds keep their
+//          order, survivors get score = SW score (or len * a when the alignment was skipped)                [one lane]
+BM2_HD int chain_flt_list_d(const ChainStripe &ws, int n_kept) {
+    int T = 0;
+    for (int k = 0; k < n_kept; ++k) {
+        const WChain &c = ws.chains[ws.srt[k]];
+        for (int t = 0, i = c.head; t < c.n; ++t, i = ws.seeds[i].next) ws.ord[T++] = i;
+    }
+    return T;
+}
+
+BM2_HD void chain_flt_score_d(const ContigView &cv, const SwParams &p, const uint8_t *ref, int l_query, const uint8_t *query, const ChainStripe &ws,
+                              int T, int first, int step) {
+    for (int t = first; t < T; t += step) { WSeed &s = ws.seeds[ws.ord[t]]; s.score = seed_sw_d(cv, p, ref, l_query, query, s); }
+}
+
+BM2_HD void chain_flt_apply_d(const SwParams &p, int min_hsp, const ChainStripe &ws, int n_kept) {
     for (int k = 0; k < n_kept; ++k) {
         WChain &c = ws.chains[ws.srt[k]];
         int prev = -1, kept = 0, i = c.head;
         for (int t = 0; t < c.n; ++t) {
             WSeed &s = ws.seeds[i];
             const int nxt = s.next;
-            const int sc = seed_sw_d(cv, p, ref, l_query, query, s);
+            const int sc = s.score;
             if (sc < 0 || sc >= min_hsp) {
                 s.score = sc < 0 ? s.len * p.a : sc;
                 if (prev < 0) c.head = i; else ws.seeds[prev].next = i;
@@ -408,6 +424,14 @@ BM2_HD void chain_flt_seeds_d(const ContigView &cv, const SwParams &p, const uin
         c.n = kept;
         if (prev >= 0) { ws.seeds[prev].next = -1; c.tail = prev; }
     }
+}
+
+BM2_HD void chain_flt_seeds_d(const ContigView &cv, const SwParams &p, const uint8_t *ref, int l_query, const uint8_t *query,
+                              int min_hsp, const ChainStripe &ws, int n_kept)
+{
+    const int T = chain_flt_list_d(ws, n_kept);
+    chain_flt_score_d(cv, p, ref, l_query, query, ws, T, 0, 1);
+    chain_flt_apply_d(p, min_hsp, ws, n_kept);
 }
 
 // Writes the surviving chains of one read contiguously (reference order) and counts the extension

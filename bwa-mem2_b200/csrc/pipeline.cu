@@ -361,15 +361,16 @@ chain_kernel(ContigView cv, ChainParams cp, const bm2_smem *__restrict__ sm, con
              const int32_t *__restrict__ min_hsp, int mode, int heavy_thr)
 {
     // mode 0: light reads, one per thread; mode 1: heavy reads (many seed occurrences: O(n^2) chain insertion and
-    // filtering), one per WARP with lane 0 working, taken from the list sorted by decreasing work
+    // filtering), one per WARP, taken from the list sorted by decreasing work: lane 0 runs the sequential chaining, ALL lanes share the
+    // local alignments of mem_flt_chained_seeds (long reads: hundreds of independent <= 200 x 200 alignments per read)
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (mode && (threadIdx.x & 31)) return;
+    const int lane = threadIdx.x & 31;
     const int stride = mode ? (gridDim.x * blockDim.x) >> 5 : gridDim.x * blockDim.x;
     for (int t = mode ? tid >> 5 : tid; t < n_reads; t += stride) {
     const int r = mode ? perm[t] : t;
     {
         const int64_t nslot = slot_off[read_smem_off[r + 1]] - slot_off[read_smem_off[r]];
-        if (mode) { if (nslot <= heavy_thr) break; }                  // perm is sorted by decreasing work
+        if (mode) { if (nslot <= heavy_thr) break; }                  // perm is sorted by decreasing work (warp-uniform)
         else if (nslot > heavy_thr) continue;
     }
     int nk = 0, ns = 0, nl = 0, nr = 0;
@@ -378,15 +379,29 @@ chain_kernel(ContigView cv, ChainParams cp, const bm2_smem *__restrict__ sm, con
     // reference quirk: a 512-read block whose SMEM total is exactly 1 yields no chain (src/bwamem.cpp:835)
     const int b0 = (r / 512) * 512, b1 = min(n_reads, b0 + 512);
     const bool skip = (read_smem_off[b1] - read_smem_off[b0]) <= 1;
+    const bool lead = !mode || lane == 0;
     if (se > sb && !skip && len >= cp.min_seed_len) {
         const int64_t base = slot_off[sb];
         ChainStripe ws = { b.wseed + base, b.wchain + base, b.ord + base, b.ordpos + base, b.srt + base, b.kv + base, b.flt + base };
         float frac = 0.f;
-        nk = chain_read_d(cv, cp, sm + sb, (int) (se - sb), sa + base, len, ws, &frac);
-        if (min_hsp && min_hsp[r] >= 0) chain_flt_seeds_d(cv, sw, ref, len, codes + offs[r], min_hsp[r], ws, nk);
-        chain_finalize_d(ws, nk, frac, r, len, b.fin_chain + base, b.fin_seed + base, &ns, &nl, &nr);
+        if (lead) nk = chain_read_d(cv, cp, sm + sb, (int) (se - sb), sa + base, len, ws, &frac);
+        const bool flt = min_hsp && min_hsp[r] >= 0;
+        if (!mode) {
+            if (flt) chain_flt_seeds_d(cv, sw, ref, len, codes + offs[r], min_hsp[r], ws, nk);
+        } else if (flt) {
+            nk = __shfl_sync(0xffffffffu, nk, 0);
+            int T = 0;
+            if (lane == 0) T = chain_flt_list_d(ws, nk);
+            T = __shfl_sync(0xffffffffu, T, 0);                      // (the shuffle also orders lane 0's writes before the others' reads)
+            __syncwarp();
+            chain_flt_score_d(cv, sw, ref, len, codes + offs[r], ws, T, lane, 32);
+            __syncwarp();
+            if (lane == 0) chain_flt_apply_d(sw, min_hsp[r], ws, nk);
+        }
+        if (lead) chain_finalize_d(ws, nk, frac, r, len, b.fin_chain + base, b.fin_seed + base, &ns, &nl, &nr);
     }
-    b.n_chain[r] = nk; b.n_seed[r] = ns; b.n_left[r] = nl; b.n_right[r] = nr;
+    if (lead) { b.n_chain[r] = nk; b.n_seed[r] = ns; b.n_left[r] = nl; b.n_right[r] = nr; }
+    if (mode) __syncwarp();
     }
 }
 

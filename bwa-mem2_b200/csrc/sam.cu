@@ -8,10 +8,10 @@
 // and CIGAR pools - optimistic pools with a second wave for the pairs that overflow are the obvious next step).  The libm values the stage needs (log of small
 // integers, the insert-size term of mem_pair) are tabulated on the host with the host's libm, as the reference computes them.
 //
-// STATUS: first version, parity-green on a B200 (tests/test_zz_sam_gpu.py, profiles/r1s_zz_tests_gpu.log), not yet timed or profiled.
-// Correctness-first: thread-per-pair, no warp cooperation in the local alignment yet.
+// STATUS: parity-green on a B200 in all three rescue modes; timed in round 2 (profiles/r2a_bench_sam.json): the per-pair kernel is the
+// bottleneck (128 ms per 100 k pairs next to 32 ms for the window alignments of the staged mode).
 //
-// Staged rescue (bm2_set_sam_staged / BM2_SAM_STAGED=1; off by default until it has run on a GPU): the local alignments of the rescue - the
+// Staged rescue (the default since round 2; bm2_set_sam_staged / BM2_SAM_STAGED select 0 = per-pair, 1 = warp per window, 2 = thread per window): the local alignments of the rescue - the
 // bulk of the stage's arithmetic - leave the per-pair thread.  sam_jobs_kernel lists, from the regions BEFORE any rescue, the windows the
 // rescue block of every pair can ask for (mate_jobs_pair_d); sam_ksw_jobs_kernel aligns them one window per warp (ksw_warp.cuh, the mate read
 // in place, reverse-complemented by addressing); the per-pair thread then looks its alignments up (MateKswTable) and computes one itself
@@ -292,7 +292,9 @@ int run_sam(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs,
     ContigView cv; cv.l_pac = ctx->idx.l_pac; cv.n_seqs = ctx->idx.n_seqs; cv.ann_off = ctx->idx.ann_off; cv.ann_len = ctx->idx.ann_len; cv.ann_alt = ctx->idx.ann_alt;
     const int rescue = paired && !(o.flag & 0x20);
     int staged = ctx->sam_staged;
-    if (staged < 0) { const char *e = getenv("BM2_SAM_STAGED"); staged = e ? atoi(e) : 0; if (staged < 0 || staged > 2) staged = 0; }
+    // default: staged, one window per warp - byte-identical records (tests/test_zzz_sam_staged_gpu.py) and 6x the per-pair mode on the 3 Gbp
+    // workload (profiles/r2a_bench_sam.json: 1.01 M against 0.17 M reads/s); BM2_SAM_STAGED / bm2_set_sam_staged select the other modes
+    if (staged < 0) { const char *e = getenv("BM2_SAM_STAGED"); staged = e ? atoi(e) : 1; if (staged < 0 || staged > 2) staged = 1; }
     if (!rescue) staged = 0;
     for (double &v : ctx->sam_ms) v = 0;
     for (unsigned long long &v : ctx->sam_counts) v = 0;
