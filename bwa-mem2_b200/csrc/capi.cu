@@ -407,9 +407,49 @@ __global__ void __launch_bounds__(256) gather_probe_kernel(const char *__restric
     if (acc == 0x12345678u) out[0] = (unsigned) acc;
 }
 
+// shape 3: the same 32-byte requests through the bulk-async (TMA) path: every thread owns MLP 32-byte shared-memory slots and ONE mbarrier,
+// announces the bytes (mbarrier.arrive.expect_tx), issues cp.async.bulk.shared::cluster.global per request and waits on the barrier's
+// phase - the "Occ blocks TMA-staged to shared memory" shape of the north star, per lane because every lane of the SMEM kernels extends
+// its own interval at its own random address (there is no tile to describe with a tensor map).
+template <int MLP>
+__global__ void __launch_bounds__(256) gather_probe_bulk_kernel(const char *__restrict__ tab, unsigned long long n_units, int iters, unsigned long long seed,
+                                                                unsigned *out) {
+    __shared__ __align__(32) unsigned long long slots[256][MLP][4];
+    __shared__ __align__(8) unsigned long long bars[256];
+    const unsigned bar = (unsigned) __cvta_generic_to_shared(&bars[threadIdx.x]);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    unsigned long long x = seed + (unsigned long long) (blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull;
+    unsigned long long acc = 0;
+    unsigned phase = 0;
+    for (int it = 0; it < iters; ++it) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(32u * MLP) : "memory");
+#pragma unroll
+        for (int m = 0; m < MLP; ++m) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            const unsigned long long e = (unsigned long long) (((unsigned __int128) x * n_units) >> 64);
+            const unsigned dst = (unsigned) __cvta_generic_to_shared(&slots[threadIdx.x][m][0]);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 32, [%2];"
+                         :: "r"(dst), "l"(tab + e * 32), "r"(bar) : "memory");
+        }
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+        }
+        phase ^= 1u;
+#pragma unroll
+        for (int m = 0; m < MLP; ++m)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc += slots[threadIdx.x][m][q];
+    }
+    if (acc == 0x12345678u) out[0] = (unsigned) acc;
+}
+
 extern "C" int bm2_gather_probe(bm2_ctx *ctx, unsigned long long span_bytes, int mlp, int shape, double *gbs) {
     bm2_ctx *ctx_for_error = ctx;
-    if (!ctx || !gbs || shape < 0 || shape > 2) return 1;
+    if (!ctx || !gbs || shape < 0 || shape > 3) return 1;
     if (!ctx->idx.loaded) { bm2_set_error(ctx, "bm2_gather_probe needs a context created with an index"); return 1; }
     BM2_CUDA_OK(cudaSetDevice(ctx->device));
     const unsigned long long unit = shape == 1 ? 32 : 64;
@@ -424,7 +464,8 @@ extern "C" int bm2_gather_probe(bm2_ctx *ctx, unsigned long long span_bytes, int
     for (int rep = 0; rep < 4; ++rep) {
         BM2_CUDA_OK(cudaEventRecord(e0, ctx->stream));
 #define BM2_GP(M, S) gather_probe_kernel<M, S><<<blocks, threads, 0, ctx->stream>>>(tab, n_units, iters, 777 + rep, o)
-#define BM2_GPS(M) do { if (shape == 0) BM2_GP(M, 0); else if (shape == 1) BM2_GP(M, 1); else BM2_GP(M, 2); } while (0)
+#define BM2_GPS(M) do { if (shape == 0) BM2_GP(M, 0); else if (shape == 1) BM2_GP(M, 1); else if (shape == 2) BM2_GP(M, 2); \
+                        else gather_probe_bulk_kernel<(M > 4 ? 4 : M)><<<blocks, threads, 0, ctx->stream>>>(tab, n_units, iters, 777 + rep, o); } while (0)
         if (mlp <= 1) BM2_GPS(1); else if (mlp == 2) BM2_GPS(2); else if (mlp <= 4) BM2_GPS(4); else BM2_GPS(8);
 #undef BM2_GPS
 #undef BM2_GP
@@ -434,7 +475,7 @@ extern "C" int bm2_gather_probe(bm2_ctx *ctx, unsigned long long span_bytes, int
         if (rep > 0 && ms < best) best = ms;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    const int m_eff = mlp <= 1 ? 1 : mlp == 2 ? 2 : mlp <= 4 ? 4 : 8;
+    const int m_eff = mlp <= 1 ? 1 : mlp == 2 ? 2 : mlp <= 4 ? 4 : (shape == 3 ? 4 : 8);      // (the bulk shape holds at most 4 slots per thread)
     *gbs = (double) blocks * threads * (double) iters * m_eff * (double) unit / (best * 1e-3) / 1e9;
     return 0;
 }
