@@ -754,7 +754,9 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
             // threads per CTA: the size that keeps the most threads resident per SM (shared memory is what limits this kernel's
             // occupancy: 6 B per column pair and thread; 64- or 96-thread CTAs waste less of the 227 KB than 128-thread ones)
             int nthr2 = 128, best_res = 0, best_cps = 1;
-            for (int t = 128; t >= 64; t -= 32) {
+            int t_lo = 64, t_hi = 128;
+            if (const char *e = getenv("BM2_BSW_NTHR")) { const int v = atoi(e); if (v == 64 || v == 96 || v == 128) t_lo = t_hi = v; }      // A/B measurements
+            for (int t = t_hi; t >= t_lo; t -= 32) {
                 int cps = (int) (smem_budget / ((size_t) NP * 6 * t + 1024)); if (cps < 1) cps = 1; if (cps > max_ctas * (128 / t)) cps = max_ctas * (128 / t);
                 if (cps > 32) cps = 32;
                 if (cps * t > best_res) { best_res = cps * t; nthr2 = t; best_cps = cps; }
