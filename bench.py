@@ -874,18 +874,37 @@ def run_fastq2sam(args, rank, world):
         a_ = text.split(b"\n"); b_ = want.split(b"\n")
         bad = [i for i in range(min(len(a_), len(b_))) if a_[i] != b_[i]][:3]
         raise AssertionError(f"FASTQ -> SAM text differs from the unmodified reference: {len(a_)} vs {len(b_)} lines, first differing {[(a_[i][:200], b_[i][:200]) for i in bad]}")
-    os.remove(ref_sam)
+    # ... and the same through the C++ host program over the C ABI (bwa-mem2_b200/bm2_mem: no python in the loop): its own chunk-loop clock
+    tool = os.path.join(ROOT, "bwa-mem2_b200", "bm2_mem")
+    tool_out = os.path.join(work, "bm2_mem.sam")
+    ctx.close(); ctx = None                       # (one context at a time on the GPU: the program uploads the index itself)
+    tool_stats = []
+    for _ in range(2):
+        pr = subprocess.run([tool, "-t", str(nt), "-K", "1000000000", "-o", tool_out, fa, s1, s2], capture_output=True, text=True, check=True)
+        tool_stats.append(json.loads(pr.stderr.strip().splitlines()[-1]))
+    got_tool = b"".join(ln for ln in open(tool_out, "rb") if not ln.startswith(b"@"))
+    assert got_tool == want, "bm2_mem's SAM differs from the unmodified reference"
+    os.remove(tool_out); os.remove(ref_sam)
+    ts = tool_stats[-1]
+    ctx = capi.Context(dev, index=index, opt=opt); ctx.set_sam_staged(1)
+    step()
     torch.cuda.synchronize()
     acc = np.zeros(5); t0 = time.perf_counter()
     for _ in range(args.steps):
         text, dt, n = step(); acc += dt
     wall = (time.perf_counter() - t0) / args.steps
     acc /= args.steps
+    wall_py = wall
+    wall = ts["loop_s"]                          # the headline of this workload is the C++ program's chunk loop (second of two runs)
     out = {"metric": METRIC_SAM, "value": n / wall, "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/int16/f64", "data": "synthetic",
            "config": {"workload": f"first {n} reads ({n // 2} pairs) of the default workload as FASTQ bytes ({len(b1) + len(b2)} B) -> {len(text)} B of SAM text, "
                                   f"{args.ref_mbp} Mbp reference; one chunk per step, wall clock; python binding overheads (array copies, name list) included"},
-           "stage_s": dict(zip(["fastq_encode", "seed_chain_extend", "pestat", "sam_pe_staged", "sam_format"], [round(float(x), 4) for x in acc])),
+           "how": "bwa-mem2_b200/bm2_mem (C++ over the C ABI): FASTQ files already read into host memory -> SAM bytes written to a file; "
+                  "the clock covers its chunk loop (parse+encode, align, pestat, SAM stage, format, fwrite), not the index load",
+           "stage_s": {k: ts[k] for k in ("fastq_encode_s", "seed_chain_extend_s", "pestat_s", "sam_stage_s", "sam_format_s", "write_s")},
+           "through_the_python_binding": {"reads_per_s": n / wall_py, "stage_s": dict(zip(["fastq_encode", "seed_chain_extend", "pestat", "sam_pe_staged", "sam_format"],
+                                                                                      [round(float(x), 4) for x in acc]))},
            "e2e": {"value": n / wall, "unit": "reads/s", "h2d_bytes_per_step": int(len(b1) + len(b2)), "d2h_bytes_per_step": int(len(text))},
            "gpu_launches": 80 * args.steps,
            "parity": {"vs": "SAM text of the unmodified reference (bwa-mem2 mem through ref_driver) on the same FASTQ files", "lines": int(text.count(b"\n")),

@@ -69,7 +69,8 @@ class CigarResult(C.Structure):
 
 
 class SamTextIn(C.Structure):
-    _fields_ = [("res", C.c_void_p), ("reads", C.c_void_p), ("names", C.c_void_p), ("quals", C.c_void_p), ("contig_names", C.c_void_p)]
+    _fields_ = [("res", C.c_void_p), ("reads", C.c_void_p), ("names", C.c_void_p), ("quals", C.c_void_p), ("contig_names", C.c_void_p),
+                ("name_buf", C.c_char_p * 2), ("name_beg", C.c_void_p), ("name_len", C.c_void_p)]
 
 
 class FastqBatch(C.Structure):
@@ -77,8 +78,9 @@ class FastqBatch(C.Structure):
                 ("quals", C.c_void_p), ("name_beg", C.c_void_p), ("name_len", C.c_void_p)]
 
 
-def sam_format(recs, xa, cigar, md, codes, offsets, contig_names, read_names=None, quals=None, n_threads=1) -> bytes:
-    """bm2_sam_format: the SAM text of a batch from the records of bm2_sam_pe / bm2_sam_se (one line per record, QNAME to the last tag)."""
+def sam_format(recs, xa, cigar, md, codes, offsets, contig_names, read_names=None, quals=None, n_threads=1, name_spans=None) -> bytes:
+    """bm2_sam_format: the SAM text of a batch from the records of bm2_sam_pe / bm2_sam_se (one line per record, QNAME to the last tag).
+    read_names: list of names, or name_spans = (buf1, buf2 or None, name_beg int64[], name_len int32[]) as bm2_fastq_encode returns them."""
     recs = np.ascontiguousarray(recs, SAM_REC_DT); xa = np.ascontiguousarray(xa, SAM_XA_DT)
     cigar = np.ascontiguousarray(cigar, np.uint32); md = np.ascontiguousarray(md, np.uint8)
     codes = np.ascontiguousarray(codes, np.uint8); offsets = np.ascontiguousarray(offsets, np.int64)
@@ -89,6 +91,11 @@ def sam_format(recs, xa, cigar, md, codes, offsets, contig_names, read_names=Non
     q = np.ascontiguousarray(np.frombuffer(quals, np.uint8) if isinstance(quals, (bytes, bytearray)) else quals, np.uint8) if quals is not None else None
     tin = SamTextIn(C.cast(C.byref(res), C.c_void_p), C.cast(C.byref(rb), C.c_void_p), C.cast(rn, C.c_void_p) if rn is not None else None,
                     q.ctypes.data if q is not None else None, C.cast(cn, C.c_void_p))
+    if name_spans is not None:
+        b1, b2, nbeg, nlen = name_spans
+        nbeg = np.ascontiguousarray(nbeg, np.int64); nlen = np.ascontiguousarray(nlen, np.int32)
+        tin.name_buf[0] = b1; tin.name_buf[1] = b2
+        tin.name_beg = nbeg.ctypes.data; tin.name_len = nlen.ctypes.data
     text = C.c_void_p(); n = C.c_int64()
     f = lib().bm2_sam_format
     f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -322,7 +329,7 @@ class Context:
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * dt.itemsize,)).view(dt).copy() if n else np.zeros(0, dt)
         return arr(res.recs, res.n_recs, SAM_REC_DT), arr(res.xa, res.n_xa, SAM_XA_DT), arr(res.cigar, res.n_ops, "<u4"), arr(res.md, res.n_md, "u1")
 
-    def fastq_encode(self, buf1: bytes, buf2: bytes | None = None):
+    def fastq_encode(self, buf1: bytes, buf2: bytes | None = None, want_names: bool = True):
         """bm2_fastq_encode: raw FASTQ bytes of a chunk (two files for pairs) -> dict(n_reads, codes, offsets, quals, names, d_codes, d_offsets);
         the device pointers stay valid until the context's next call."""
         b = FastqBatch()
@@ -338,8 +345,9 @@ class Context:
         nl = np.ctypeslib.as_array(C.cast(b.name_len, C.POINTER(C.c_int32)), shape=(max(n, 1),))[:n].copy()
         bufs = (buf1, buf2 if buf2 is not None else buf1)
         stride = 2 if buf2 is not None else 1
-        names = [bufs[r % stride][nb[r]:nb[r] + nl[r]] for r in range(n)]
-        return dict(n_reads=n, codes=codes, offsets=offs, quals=quals, names=names, d_codes=b.d_codes, d_offsets=b.d_offsets)
+        names = [bufs[r % stride][nb[r]:nb[r] + nl[r]] for r in range(n)] if want_names else None
+        return dict(n_reads=n, codes=codes, offsets=offs, quals=quals, names=names, d_codes=b.d_codes, d_offsets=b.d_offsets,
+                    name_spans=(buf1, buf2, nb, nl))
 
     def set_sam_staged(self, on: int):
         """bm2_set_sam_staged: 1 / 2 = the rescue's local alignments as a batch (one window per warp / per thread) before the per-pair kernel, 0 = inside it."""

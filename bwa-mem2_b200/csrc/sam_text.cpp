@@ -17,19 +17,30 @@
 
 namespace {
 
-struct Out {
-    std::string s;
-    void num(long long v) {
-        char b[24]; int n = 0;
-        unsigned long long u = v < 0 ? (unsigned long long) (-(v + 1)) + 1ULL : (unsigned long long) v;
-        do { b[n++] = (char) ('0' + u % 10); u /= 10; } while (u);
-        if (v < 0) s.push_back('-');
-        while (n) s.push_back(b[--n]);
+struct Out {            // append-only byte buffer: raw pointer writes, doubling growth (one std::string::push_back per character was the
+    char *p = nullptr;  // formatter's whole cost in the first version: 0.5 GB/s on 16 threads)
+    size_t n = 0, cap = 0;
+    ~Out() { free(p); }
+    void need(size_t k) {
+        if (n + k <= cap) return;
+        size_t c = cap ? cap : (size_t) 1 << 16;
+        while (c < n + k) c <<= 1;
+        p = (char *) realloc(p, c); cap = c;
     }
-    void str(const char *p) { s.append(p); }
-    void ch(char c) { s.push_back(c); }
-    void ops(const uint32_t *o, int n, const char *alphabet) {
-        for (int i = 0; i < n; ++i) { num((long long) (o[i] >> 4)); ch(alphabet[o[i] & 15]); }
+    void num(long long v) {
+        need(24);
+        char b[24]; int m = 0;
+        unsigned long long u = v < 0 ? (unsigned long long) (-(v + 1)) + 1ULL : (unsigned long long) v;
+        do { b[m++] = (char) ('0' + u % 10); u /= 10; } while (u);
+        if (v < 0) p[n++] = '-';
+        while (m) p[n++] = b[--m];
+    }
+    void bytes(const char *q, size_t k) { need(k); memcpy(p + n, q, k); n += k; }
+    void str(const char *q) { bytes(q, strlen(q)); }
+    void ch(char c) { need(1); p[n++] = c; }
+    void ops(const uint32_t *o, int k, const char *alphabet) {
+        need((size_t) k * 12 + 1);
+        for (int i = 0; i < k; ++i) { num((long long) (o[i] >> 4)); p[n++] = alphabet[o[i] & 15]; }
     }
 };
 
@@ -49,7 +60,7 @@ void format_read_range(Job &j) {
     const bm2_read_batch &rb = *in.reads;
     static const char comp[6] = { 'T', 'G', 'C', 'A', 'N', 'N' };
     static const char fwd[6] = { 'A', 'C', 'G', 'T', 'N', 'N' };
-    j.out.s.reserve((size_t) (j.r1 - j.r0) * 420);
+    j.out.need((size_t) (j.r1 - j.r0) * 440 + 1024);
     for (int64_t rd = j.r0; rd < j.r1; ++rd) {
         const int64_t k0 = j.first_rec_of_read[rd], k1 = j.first_rec_of_read[rd + 1];
         const int64_t so = rb.offsets[rd], l_seq = rb.offsets[rd + 1] - so;
@@ -60,7 +71,11 @@ void format_read_range(Job &j) {
             Out &o = j.out;
             const uint32_t *ops = res.cigar + r.cigar_off;
             // QNAME FLAG RNAME POS MAPQ CIGAR
-            if (in.names) o.str(in.names[rd]); else { o.ch('r'); o.num(rd); }
+            if (in.names) o.str(in.names[rd]);
+            else if (in.name_beg && in.name_len && in.name_buf[0]) {      // QNAME as a span of the caller's FASTQ buffer (bm2_fastq_batch)
+                const char *nb = (in.name_buf[1] && (rd & 1)) ? in.name_buf[1] : in.name_buf[0];
+                o.bytes(nb + in.name_beg[rd], (size_t) in.name_len[rd]);
+            } else { o.ch('r'); o.num(rd); }
             o.ch('\t'); o.num(r.flag); o.ch('\t');
             if (r.rid >= 0) {
                 o.str(in.contig_names[r.rid]); o.ch('\t'); o.num(r.pos); o.ch('\t'); o.num(r.mapq); o.ch('\t');
@@ -81,20 +96,24 @@ void format_read_range(Job &j) {
                 const bool rev = (r.flag & 0x10) != 0;
                 if (r.n_cigar && (ops[0] & 15) == 4) { if (rev) qe -= ops[0] >> 4; else qb += ops[0] >> 4; }
                 if (r.n_cigar && (ops[r.n_cigar - 1] & 15) == 4) { if (rev) qb += ops[r.n_cigar - 1] >> 4; else qe -= ops[r.n_cigar - 1] >> 4; }
+                const size_t L = (size_t) (qe > qb ? qe - qb : 0);
+                o.need(2 * L + 4);
+                char *w = o.p + o.n;
                 if (!rev) {
-                    for (int64_t i = qb; i < qe; ++i) o.ch(fwd[seq[i] > 5 ? 4 : seq[i]]);
-                    o.ch('\t');
-                    if (qual) o.s.append(qual + qb, (size_t) (qe - qb)); else o.ch('*');
+                    for (int64_t i = qb; i < qe; ++i) *w++ = fwd[seq[i] > 5 ? 4 : seq[i]];
+                    *w++ = '\t';
+                    if (qual) { memcpy(w, qual + qb, L); w += L; } else *w++ = '*';
                 } else {
-                    for (int64_t i = qe - 1; i >= qb; --i) o.ch(comp[seq[i] > 5 ? 4 : seq[i]]);
-                    o.ch('\t');
-                    if (qual) { for (int64_t i = qe - 1; i >= qb; --i) o.ch(qual[i]); } else o.ch('*');
+                    for (int64_t i = qe - 1; i >= qb; --i) *w++ = comp[seq[i] > 5 ? 4 : seq[i]];
+                    *w++ = '\t';
+                    if (qual) { for (int64_t i = qe - 1; i >= qb; --i) *w++ = qual[i]; } else *w++ = '*';
                 }
+                o.n = (size_t) (w - o.p);
             }
             // tags: NM MD MC AS XS SA pa XA
             if (r.n_cigar) {
                 o.str("\tNM:i:"); o.num(r.nm);
-                o.str("\tMD:Z:"); o.s.append(res.md + r.md_off, (size_t) (r.n_md > 0 ? r.n_md - 1 : 0));
+                o.str("\tMD:Z:"); o.bytes(res.md + r.md_off, (size_t) (r.n_md > 0 ? r.n_md - 1 : 0));
             }
             if (r.n_mc > 0) { o.str("\tMC:Z:"); o.ops(ops + r.n_cigar, r.n_mc, "MIDSH"); }
             if (r.score >= 0) { o.str("\tAS:i:"); o.num(r.score); }
@@ -164,11 +183,18 @@ extern "C" int bm2_sam_format(const bm2_sam_text_in *in, int n_threads, char **t
         for (auto &x : th) x.join();
     }
     size_t total = 0;
-    for (auto &j : jobs) total += j.out.s.size();
+    for (auto &j : jobs) total += j.out.n;
     char *buf = (char *) malloc(total + 1);
     if (!buf) return 3;
-    size_t pos = 0;
-    for (auto &j : jobs) { memcpy(buf + pos, j.out.s.data(), j.out.s.size()); pos += j.out.s.size(); }
+    {   // the pieces into one buffer, one thread per piece
+        std::vector<size_t> at((size_t) n_threads, 0);
+        for (int t = 1; t < n_threads; ++t) at[t] = at[t - 1] + jobs[t - 1].out.n;
+        std::vector<std::thread> th;
+        auto cp = [&](int t) { if (jobs[t].out.n) memcpy(buf + at[t], jobs[t].out.p, jobs[t].out.n); };
+        for (int t = 1; t < n_threads; ++t) th.emplace_back(cp, t);
+        cp(0);
+        for (auto &x : th) x.join();
+    }
     buf[total] = 0;
     *text = buf; *len = (int64_t) total;
     return 0;

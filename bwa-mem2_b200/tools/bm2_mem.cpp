@@ -1,0 +1,157 @@
+// bm2_mem — FASTQ in, SAM out, on the GPU path: the host side of `bwa-mem2 mem` for the seams of libbm2b200.so (C++, as the reference's host
+// code; only the C ABI of include/bm2_b200.h is used).
+//
+//   bm2_mem [-t threads] [-K chunk_bases] [-o out.sam] <index prefix> <reads_1.fq> [reads_2.fq]
+//
+// What the reference does in main_mem / process / ktp_worker (src/fastmap.cpp:616-1003, :280-349), with every step of a chunk behind a seam:
+//   chunk of the input            bseq_read_orig's rule (src/bwa.cpp:170-216): records until the base count reaches the task size
+//                                 (-K, else chunk_size x threads, src/fastmap.cpp:943-949), mates kept together
+//   bm2_fastq_encode              parsing + nst_nt4_table encoding on the GPU                         (kseq + src/bwamem.cpp:992-1000)
+//   bm2_seed_chain_extend_resident  worker_bwt + worker_aln                                           (src/bwamem.cpp:1359-1363)
+//   bm2_pestat                    mem_pestat                                                          (src/bwamem.cpp:1368-1378)
+//   bm2_sam_pe / bm2_sam_se       worker_sam's arithmetic                                             (src/bwamem.cpp:1262-1336)
+//   bm2_sam_format                mem_aln2sam's text                                                  (src/bwamem.cpp:1592-1730)
+// The SAM records equal `bwa-mem2 mem` with the same -K (tests/test_zz_fastq_sam_gpu.py); the header carries the same @SQ lines and
+// this program's own @PG line.  Plain (uncompressed) FASTQ with four-line records; the files are read whole.
+#include "bm2_b200.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static bool read_file(const char *path, std::vector<char> &buf) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END); const long n = ftell(f); fseek(f, 0, SEEK_SET);
+    buf.resize((size_t) n);
+    const bool ok = n == 0 || fread(buf.data(), 1, (size_t) n, f) == (size_t) n;
+    fclose(f);
+    return ok;
+}
+
+// end of the record that starts at p (four lines), and the length of its sequence line; nullptr at a truncated record
+static const char *next_record(const char *p, const char *end, int64_t *seq_len) {
+    const char *l[4]; const char *q = p;
+    for (int k = 0; k < 4; ++k) {
+        const char *e = (const char *) memchr(q, '\n', (size_t) (end - q));
+        if (!e) { if (k == 3 && q < end) { e = end; l[k] = e; q = end; break; } return nullptr; }
+        l[k] = e; q = e + 1;
+    }
+    const char *s0 = l[0] + 1;
+    int64_t n = l[1] - s0;
+    if (n > 0 && s0[n - 1] == '\r') --n;
+    *seq_len = n;
+    return q;
+}
+
+int main(int argc, char **argv) {
+    int threads = 1; long long fixed_k = 0; const char *out_path = nullptr;
+    int a = 1;
+    for (; a < argc && argv[a][0] == '-' && argv[a][1]; a += 2) {
+        if (a + 1 >= argc) break;
+        if (!strcmp(argv[a], "-t")) threads = atoi(argv[a + 1]);
+        else if (!strcmp(argv[a], "-K")) fixed_k = atoll(argv[a + 1]);
+        else if (!strcmp(argv[a], "-o")) out_path = argv[a + 1];
+        else { fprintf(stderr, "bm2_mem: unknown option %s\n", argv[a]); return 1; }
+    }
+    if (argc - a < 2) { fprintf(stderr, "usage: bm2_mem [-t threads] [-K chunk_bases] [-o out.sam] <index prefix> <reads_1.fq> [reads_2.fq]\n"); return 1; }
+    if (threads < 1) threads = 1;
+    const char *prefix = argv[a], *f1 = argv[a + 1], *f2 = argc - a >= 3 ? argv[a + 2] : nullptr;
+    const double t_start = now_s();
+    bm2_index_desc *idx = nullptr;
+    if (bm2_index_load(prefix, &idx)) { fprintf(stderr, "bm2_mem: cannot load the index %s\n", prefix); return 2; }
+    // contig names: <prefix>.ann (src/bntseq.cpp:73-110): "l_pac n_seqs seed", then per contig "gi name [anno]" and "offset len n_ambs"
+    std::vector<std::string> names; std::vector<long long> lens;
+    {
+        FILE *f = fopen((std::string(prefix) + ".ann").c_str(), "r");
+        if (!f) { fprintf(stderr, "bm2_mem: cannot open %s.ann\n", prefix); return 2; }
+        char line[65536];
+        if (!fgets(line, sizeof line, f)) return 2;
+        for (int i = 0; i < idx->n_seqs; ++i) {
+            char nm[4096]; long long gi, off, len; int amb;
+            if (!fgets(line, sizeof line, f) || sscanf(line, "%lld %4095s", &gi, nm) != 2) return 2;
+            if (!fgets(line, sizeof line, f) || sscanf(line, "%lld %lld %d", &off, &len, &amb) != 3) return 2;
+            names.push_back(nm); lens.push_back(len);
+        }
+        fclose(f);
+    }
+    std::vector<const char *> cnames; for (auto &s : names) cnames.push_back(s.c_str());
+    bm2_mem_opt_t opt; bm2_opt_init(&opt);
+    opt.n_threads = threads;
+    if (f2) opt.flag |= 0x2;                                   // MEM_F_PE
+    bm2_ctx *ctx = nullptr;
+    if (bm2_create(&ctx, 0, idx, &opt)) { fprintf(stderr, "bm2_mem: %s\n", bm2_last_error(nullptr)); return 3; }
+    const double t_index = now_s() - t_start;
+    std::vector<char> b1, b2;
+    if (!read_file(f1, b1) || (f2 && !read_file(f2, b2))) { fprintf(stderr, "bm2_mem: cannot read the FASTQ files\n"); return 2; }
+    FILE *out = out_path ? fopen(out_path, "wb") : stdout;
+    if (!out) { fprintf(stderr, "bm2_mem: cannot open %s\n", out_path); return 2; }
+    for (size_t i = 0; i < names.size(); ++i) fprintf(out, "@SQ\tSN:%s\tLN:%lld\n", names[i].c_str(), lens[i]);
+    fprintf(out, "@PG\tID:bm2_mem\tPN:bm2_mem\tVN:b200-r2\tCL:%s", argv[0]);
+    for (int i = 1; i < argc; ++i) fprintf(out, " %s", argv[i]);
+    fprintf(out, "\n");
+    const long long task = fixed_k > 0 ? fixed_k : (long long) opt.chunk_size * threads;
+    const char *p1 = b1.data(), *e1 = p1 + b1.size(), *p2 = b2.data(), *e2 = p2 + b2.size();
+    long long n_processed = 0, n_chunks = 0;
+    double t_enc = 0, t_aln = 0, t_pes = 0, t_sam = 0, t_fmt = 0, t_write = 0;
+    const double t_loop = now_s();
+    while (p1 < e1) {
+        // one chunk: records until the base count reaches the task size (src/bwa.cpp:204)
+        const char *c1 = p1, *c2 = p2; long long size = 0;
+        while (p1 < e1) {
+            int64_t sl = 0;
+            const char *q = next_record(p1, e1, &sl);
+            if (!q) { fprintf(stderr, "bm2_mem: truncated record in %s\n", f1); return 2; }
+            p1 = q; size += sl;
+            if (f2) {
+                if (p2 >= e2) { fprintf(stderr, "bm2_mem: the 2nd file has fewer sequences\n"); return 2; }
+                const char *r = next_record(p2, e2, &sl);
+                if (!r) { fprintf(stderr, "bm2_mem: truncated record in %s\n", f2); return 2; }
+                p2 = r; size += sl;
+            }
+            if (size >= task) break;
+        }
+        double t0 = now_s();
+        bm2_fastq_batch fq;
+        if (bm2_fastq_encode(ctx, c1, p1 - c1, f2 ? c2 : nullptr, f2 ? p2 - c2 : 0, &fq)) { fprintf(stderr, "bm2_mem: %s\n", bm2_last_error(ctx)); return 3; }
+        double t1 = now_s(); t_enc += t1 - t0;
+        bm2_read_batch rb = { fq.n_reads, fq.codes, fq.offsets };
+        bm2_reg_result rr;
+        if (bm2_seed_chain_extend_resident(ctx, &rb, fq.d_codes, fq.d_offsets, 1, &rr)) { fprintf(stderr, "bm2_mem: %s\n", bm2_last_error(ctx)); return 3; }
+        double t2 = now_s(); t_aln += t2 - t1;
+        bm2_sam_result sr;
+        if (f2) {
+            bm2_pestat_t pes[4];
+            if (bm2_pestat(&opt, idx->l_pac, fq.n_reads, rr.regs, rr.read_off, pes)) { fprintf(stderr, "bm2_mem: bm2_pestat failed\n"); return 3; }
+            double t3 = now_s(); t_pes += t3 - t2;
+            if (bm2_sam_pe(ctx, &rb, rr.regs, rr.read_off, pes, n_processed >> 1, &sr)) { fprintf(stderr, "bm2_mem: %s\n", bm2_last_error(ctx)); return 3; }
+            t_sam += now_s() - t3;
+        } else {
+            if (bm2_sam_se(ctx, &rb, rr.regs, rr.read_off, n_processed, &sr)) { fprintf(stderr, "bm2_mem: %s\n", bm2_last_error(ctx)); return 3; }
+            t_sam += now_s() - t2;
+        }
+        double t4 = now_s();
+        bm2_sam_text_in tin; memset(&tin, 0, sizeof tin);
+        tin.res = &sr; tin.reads = &rb; tin.quals = fq.quals; tin.contig_names = cnames.data();
+        tin.name_buf[0] = c1; tin.name_buf[1] = f2 ? c2 : nullptr; tin.name_beg = fq.name_beg; tin.name_len = fq.name_len;
+        char *text = nullptr; int64_t len = 0;
+        if (bm2_sam_format(&tin, threads, &text, &len)) { fprintf(stderr, "bm2_mem: bm2_sam_format failed\n"); return 3; }
+        double t5 = now_s(); t_fmt += t5 - t4;
+        fwrite(text, 1, (size_t) len, out);
+        bm2_free(text);
+        t_write += now_s() - t5;
+        n_processed += fq.n_reads; ++n_chunks;
+    }
+    if (f2 && p2 < e2) fprintf(stderr, "[W::bm2_mem] the 1st file has fewer sequences.\n");
+    const double loop_s = now_s() - t_loop;
+    if (out != stdout) fclose(out);
+    fprintf(stderr, "{\"reads\": %lld, \"chunks\": %lld, \"loop_s\": %.6f, \"index_and_context_s\": %.3f, \"fastq_encode_s\": %.6f, \"seed_chain_extend_s\": %.6f, "
+                    "\"pestat_s\": %.6f, \"sam_stage_s\": %.6f, \"sam_format_s\": %.6f, \"write_s\": %.6f}\n",
+            n_processed, n_chunks, loop_s, t_index, t_enc, t_aln, t_pes, t_sam, t_fmt, t_write);
+    bm2_destroy(ctx); bm2_index_free(idx);
+    return 0;
+}

@@ -351,6 +351,10 @@ typedef struct bm2_sam_text_in {
     const char *const *names;           /* QNAME per read (mates carry the same name); NULL: "r<index>"            */
     const char *quals;                  /* qualities laid out like reads->codes (same offsets); NULL: '*'          */
     const char *const *contig_names;    /* RNAME by contig id (bntann1_t::name)                                    */
+    /* names == NULL: QNAME of read r = name_buf[paired ? r & 1 : 0][name_beg[r], + name_len[r]) - the spans bm2_fastq_encode returns
+     * (name_buf[1] NULL: single-end); all NULL: "r<index>" */
+    const char *name_buf[2];
+    const int64_t *name_beg; const int32_t *name_len;
 } bm2_sam_text_in;
 int  bm2_sam_format(const bm2_sam_text_in *in, int n_threads, char **text, int64_t *len);
 void bm2_free(void *p);

@@ -80,3 +80,34 @@ def test_fastq_bytes_to_sam_text_equals_the_reference(pkg, golden_dir, staged):
     text = capi.sam_format(recs, xa, cig, md, fq["codes"], fq["offsets"], contigs, read_names=fq["names"], quals=fq["quals"], n_threads=3).decode()
     assert text == "".join(want)
     ctx.close(); idx.close()
+
+
+@pytest.mark.parametrize("K", [100_000_000, 40_000])
+def test_bm2_mem_program_prints_the_reference_sam(pkg, golden_dir, tmp_path, K):
+    """The C++ host program over the C ABI (bwa-mem2_b200/tools/bm2_mem.cpp): FASTQ files in, SAM file out, chunked by -K like the reference's
+    reader; against the unmodified reference run live with the same -K (several chunks: mem_pestat per chunk, id offsets across chunks)."""
+    import os, subprocess, importlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "bwa-mem2_b200", "bm2_mem")
+    isa = "avx512bw" if "avx512bw" in open("/proc/cpuinfo").read() else "avx2"
+    drv = os.path.join(root, "oracle", "_ref", isa, "ref_driver")
+    if not os.path.exists(tool) or not os.path.exists(drv):
+        pytest.skip("bm2_mem / oracle/_ref not built")
+    synth = importlib.import_module("bwa_mem2_b200.synth")
+    reads = np.load(golden_dir + "/c0_reads.npz")["reads"]
+    r1, r2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    synth.write_fastq(r1, reads[0::2], "p"); synth.write_fastq(r2, reads[1::2], "p")
+    prefix = golden_dir + "/c0_index/ref.fa"
+    out = str(tmp_path / "out.sam")
+    o = subprocess.run([tool, "-t", "4", "-K", str(K), "-o", out, prefix, r1, r2], capture_output=True, text=True, timeout=600)
+    assert o.returncode == 0, o.stderr[-2000:]
+    ref = subprocess.run([drv, "mem", "-t", "4", "-K", str(K), prefix, r1, r2], env=dict(os.environ, BM2_MODE="ref"), capture_output=True, text=True, timeout=600)
+    assert ref.returncode == 0
+    got = [l for l in open(out).read().splitlines() if not l.startswith("@PG")]
+    want = [l for l in ref.stdout.splitlines() if not l.startswith("@PG")]
+    assert len(got) == len(want) and len(got) > 1000
+    diff = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
+    assert diff == [], (len(diff), got[diff[0]], want[diff[0]])
+    import json
+    st = json.loads(o.stderr.strip().splitlines()[-1])
+    assert st["reads"] == len(reads) and st["chunks"] == (1 if K > 1_000_000 else 4)
