@@ -135,15 +135,78 @@ struct ChainStripe {               // all arrays have >= n_slots entries, privat
 BM2_HD int chain_ord_id(int32_t v) { return (int) (v & 0x0fffffff); }
 BM2_HD int chain_ord_lvl(int32_t v) { return (int) ((uint32_t) v >> 28); }
 
+// The scans of the level-per-key tree and the one-element shift of an insertion are O(keys); a read with thousands of chains (10 kbp reads:
+// every repeat hit opens a chain) spends its whole chaining time there when ONE thread runs them.  Coop abstracts them: ChainSolo = the plain
+// loops (one thread per read, and the host build), ChainWarp = the same searches by ballots over 32 keys at a time and the shift in blocks of
+// 32, for a warp whose 32 lanes all run chain_read_d on the same read with the same data (redundantly: every lane computes and writes the
+// same values, so no lane depends on another's store except inside these helpers, which synchronise).
+struct ChainSolo {
+    BM2_HD int find_up(const int32_t *ord, int from, int hi, int h) const { int b = from; while (b < hi && (int) ((uint32_t) ord[b] >> 28) != h) ++b; return b; }
+    BM2_HD int find_down(const int32_t *ord, int from, int lo, int h) const { int a = from; while (a >= lo && (int) ((uint32_t) ord[a] >> 28) != h) --a; return a; }
+    // number of keys of level lv in [clo, chi); *mth = index of the T-th of them (-1 if fewer)
+    BM2_HD int count_level(const int32_t *ord, int clo, int chi, int lv, int T, int *mth) const {
+        int cnt = 0, m = -1;
+        for (int j = clo; j < chi; ++j) if ((int) ((uint32_t) ord[j] >> 28) == lv && ++cnt == T) m = j;
+        *mth = m; return cnt;
+    }
+    BM2_HD void shift_up(int32_t *ord, int64_t *ordpos, int at, int n) const { for (int k = n; k > at; --k) { ord[k] = ord[k - 1]; ordpos[k] = ordpos[k - 1]; } }
+    BM2_HD void sync() const {}
+};
+#if defined(__CUDACC__)
+struct ChainWarp {
+    int lane;
+    BM2_D int find_up(const int32_t *ord, int from, int hi, int h) const {
+        for (int base = from; base < hi; base += 32) {
+            const int i = base + lane;
+            const unsigned m = __ballot_sync(0xffffffffu, i < hi && (int) ((uint32_t) ord[i] >> 28) == h);
+            if (m) return base + __ffs(m) - 1;
+        }
+        return hi;
+    }
+    BM2_D int find_down(const int32_t *ord, int from, int lo, int h) const {
+        for (int base = from; base >= lo; base -= 32) {
+            const int i = base - lane;
+            const unsigned m = __ballot_sync(0xffffffffu, i >= lo && (int) ((uint32_t) ord[i] >> 28) == h);
+            if (m) return base - (__ffs(m) - 1);
+        }
+        return lo - 1;
+    }
+    BM2_D int count_level(const int32_t *ord, int clo, int chi, int lv, int T, int *mth) const {
+        int cnt = 0, m = -1;
+        for (int base = clo; base < chi; base += 32) {
+            const int j = base + lane;
+            unsigned bm = __ballot_sync(0xffffffffu, j < chi && (int) ((uint32_t) ord[j] >> 28) == lv);
+            const int c = __popc(bm);
+            if (m < 0 && cnt + c >= T) { for (int s = 0; s < T - cnt - 1; ++s) bm &= bm - 1; m = base + __ffs(bm) - 1; }
+            cnt += c;
+        }
+        *mth = m; return cnt;
+    }
+    BM2_D void shift_up(int32_t *ord, int64_t *ordpos, int at, int n) const {       // [at, n) moves up by one, from the top, 32 keys per step
+        __syncwarp();
+        for (int top = n - 1; top >= at; top -= 32) {
+            const int k = top - lane;
+            int32_t vo = 0; int64_t vp = 0;
+            if (k >= at) { vo = ord[k]; vp = ordpos[k]; }
+            __syncwarp();
+            if (k >= at) { ord[k + 1] = vo; ordpos[k + 1] = vp; }
+            __syncwarp();
+        }
+    }
+    BM2_D void sync() const { __syncwarp(); }
+};
+#endif
+
 // kb_intervalp (src/kbtree.h:158-175) when a key equal to k exists; q = first index with ordpos >= k (so ordpos[q] == k).
 // Walks from the root: in each node the first key >= k (src/kbtree.h:125-139); an equal one ends the search, else descend
 // into the child on its left.  Returns the index of the key met.
-BM2_HD int chain_tree_equal_d(const int32_t *ord, const int64_t *ordpos, int n, int height, int64_t k, int q) {
+template <class Coop = ChainSolo>
+BM2_HD int chain_tree_equal_d(const int32_t *ord, const int64_t *ordpos, int n, int height, int64_t k, int q, const Coop &co = Coop()) {
     int lo = 0, hi = n;                                  // the subtree spans [lo, hi)
     for (int h = height; h > 0; --h) {
-        int b = q; while (b < hi && chain_ord_lvl(ord[b]) != h) ++b;
+        const int b = co.find_up(ord, q, hi, h);
         if (b < hi && ordpos[b] == k) return b;
-        int a = q - 1; while (a >= lo && chain_ord_lvl(ord[a]) != h) --a;
+        const int a = co.find_down(ord, q - 1, lo, h);
         lo = a + 1; hi = b;
     }
     return q;
@@ -151,30 +214,35 @@ BM2_HD int chain_tree_equal_d(const int32_t *ord, const int64_t *ordpos, int n, 
 
 // kb_putp (src/kbtree.h:181-235): splits every full node on the way down, returns the index at which the new key (level 0)
 // goes.  q = first index with ordpos >= k; height / root_n = level and key count of the root, updated here.
-BM2_HD int chain_tree_put_d(int32_t *ord, const int64_t *ordpos, int n, int &height, int &root_n, int64_t k, int q) {
+template <class Coop = ChainSolo>
+BM2_HD int chain_tree_put_d(int32_t *ord, const int64_t *ordpos, int n, int &height, int &root_n, int64_t k, int q, const Coop &co = Coop()) {
     const int full = 2 * BM2_CHAIN_TREE_T - 1;
     if (root_n == full) {                                // new root above the old one: the old root's median moves up
-        int seen = 0, m = 0;
-        for (; m < n; ++m) if (chain_ord_lvl(ord[m]) == height && ++seen == BM2_CHAIN_TREE_T) break;
+        int m = -1;
+        co.count_level(ord, 0, n, height, BM2_CHAIN_TREE_T, &m);
         ++height;
+        co.sync();
         ord[m] = (int32_t) ((uint32_t) chain_ord_id(ord[m]) | (uint32_t) height << 28);
+        co.sync();
         root_n = 1;
     }
     int lo = 0, hi = n;
     for (int h = height; h > 0; --h) {
         const int qr = q > lo ? q : lo;                  // first index of the subtree with ordpos >= k (hi if none)
-        int b = qr; while (b < hi && chain_ord_lvl(ord[b]) != h) ++b;           // first key of this node >= k
+        const int b = co.find_up(ord, qr, hi, h);        // first key of this node >= k
         int clo, chi;
         if (b < hi && ordpos[b] == k) {                  // equal: the child on its RIGHT (src/kbtree.h:210)
-            clo = b + 1; chi = b + 1; while (chi < hi && chain_ord_lvl(ord[chi]) != h) ++chi;
+            clo = b + 1; chi = co.find_up(ord, b + 1, hi, h);
         } else {
-            int a = qr - 1; while (a >= lo && chain_ord_lvl(ord[a]) != h) --a;
+            const int a = co.find_down(ord, qr - 1, lo, h);
             clo = a + 1; chi = b;
         }
-        int cnt = 0, m = -1;
-        for (int j = clo; j < chi; ++j) if (chain_ord_lvl(ord[j]) == h - 1 && ++cnt == BM2_CHAIN_TREE_T) m = j;
+        int m = -1;
+        const int cnt = co.count_level(ord, clo, chi, h - 1, BM2_CHAIN_TREE_T, &m);
         if (cnt == full) {                               // split the child: its median joins this node
+            co.sync();
             ord[m] = (int32_t) ((uint32_t) chain_ord_id(ord[m]) | (uint32_t) h << 28);
+            co.sync();
             if (h == height) ++root_n;
             if (k > ordpos[m]) clo = m + 1; else chi = m;
         }
@@ -222,8 +290,9 @@ BM2_HD int chain_weight_d(const WChain &c, const WSeed *seeds) {
 // reference positions of its sampled rows (count = min(s, max_occ)).  On return srt[0..n_kept) lists
 // the surviving chains in the reference's output order (weight-sorted, kept != 0); returns n_kept.
 // *frac_rep receives l_rep / l_seq.
+template <class Coop = ChainSolo>
 BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_smem *smems, int n_smem, const int64_t *sa,
-                        int l_seq, ChainStripe &ws, float *frac_rep)
+                        int l_seq, ChainStripe &ws, float *frac_rep, const Coop &co = Coop())
 {
     int b = 0, e = 0, l_rep = 0;
     for (int i = 0; i < n_smem; ++i) {
@@ -252,7 +321,7 @@ BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_sm
             if (n_ch) {
                 int hi = n_ch;
                 while (lo < hi) { int mid = (lo + hi) >> 1; if (ws.ordpos[mid] < rbeg) lo = mid + 1; else hi = mid; }
-                lower = (lo < n_ch && ws.ordpos[lo] == rbeg) ? chain_tree_equal_d(ws.ord, ws.ordpos, n_ch, tree_h, rbeg, lo) : lo - 1;
+                lower = (lo < n_ch && ws.ordpos[lo] == rbeg) ? chain_tree_equal_d(ws.ord, ws.ordpos, n_ch, tree_h, rbeg, lo, co) : lo - 1;
                 if (lower >= 0) {
                     WChain &lc = ws.chains[chain_ord_id(ws.ord[lower])];
                     if (chain_test_and_merge(p, cv.l_pac, lc, ws.seeds, sid, rid)) {
@@ -266,9 +335,10 @@ BM2_HD int chain_read_d(const ContigView &cv, const ChainParams &p, const bm2_sm
             c.pos = rbeg; c.first_rbeg = c.last_rbeg = rbeg; c.first_qbeg = c.last_qbeg = s.qbeg; c.last_len = slen;
             c.head = c.tail = sid; c.n = 1; c.rid = rid; c.is_alt = cv.ann_alt ? (cv.ann_alt[rid] != 0) : 0;
             c.w = 0; c.kept = 0; c.first = -1;
-            const int at = chain_tree_put_d(ws.ord, ws.ordpos, n_ch, tree_h, root_n, rbeg, lo);
-            for (int k = n_ch; k > at; --k) { ws.ord[k] = ws.ord[k - 1]; ws.ordpos[k] = ws.ordpos[k - 1]; }
+            const int at = chain_tree_put_d(ws.ord, ws.ordpos, n_ch, tree_h, root_n, rbeg, lo, co);
+            co.shift_up(ws.ord, ws.ordpos, at, n_ch);
             ws.ord[at] = n_ch; ws.ordpos[at] = rbeg;      // a new key is always a leaf key (level 0)
+            co.sync();
             ++n_ch;
         }
     }

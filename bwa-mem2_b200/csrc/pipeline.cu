@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(128)
 chain_kernel(ContigView cv, ChainParams cp, const bm2_smem *__restrict__ sm, const int64_t *__restrict__ read_smem_off,
              const int64_t *__restrict__ slot_off, const int64_t *__restrict__ sa, const int64_t *__restrict__ offs, int n_reads,
              const int32_t *__restrict__ perm, ChainBufs b, SwParams sw, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ codes,
-             const int32_t *__restrict__ min_hsp, int mode, int heavy_thr)
+             const int32_t *__restrict__ min_hsp, int mode, int heavy_thr, int coop_min)
 {
     // mode 0: light reads, one per thread; mode 1: heavy reads (many seed occurrences: O(n^2) chain insertion and
     // filtering), one per WARP, taken from the list sorted by decreasing work: lane 0 runs the sequential chaining, ALL lanes share the
@@ -384,7 +384,11 @@ chain_kernel(ContigView cv, ChainParams cp, const bm2_smem *__restrict__ sm, con
         const int64_t base = slot_off[sb];
         ChainStripe ws = { b.wseed + base, b.wchain + base, b.ord + base, b.ordpos + base, b.srt + base, b.kv + base, b.flt + base };
         float frac = 0.f;
-        if (lead) nk = chain_read_d(cv, cp, sm + sb, (int) (se - sb), sa + base, len, ws, &frac);
+        // reads with very many seed occurrences (long reads): all 32 lanes run the chaining on the same data and share its O(chains)
+        // scans and shifts (ChainWarp); otherwise one thread runs it
+        const bool coop = mode && (slot_off[se] - base) > coop_min;
+        if (coop) { ChainWarp cw = { lane }; nk = chain_read_d(cv, cp, sm + sb, (int) (se - sb), sa + base, len, ws, &frac, cw); __syncwarp(); }
+        else if (lead) nk = chain_read_d(cv, cp, sm + sb, (int) (se - sb), sa + base, len, ws, &frac);
         const bool flt = min_hsp && min_hsp[r] >= 0;
         if (!mode) {
             if (flt) chain_flt_seeds_d(cv, sw, ref, len, codes + offs[r], min_hsp[r], ws, nk);
@@ -920,14 +924,15 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     work_keys_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(P<int64_t>(ctx, B_READ_SMEM_OFF), P<int64_t>(ctx, B_SLOT_OFF), n, wk_in, wv_in);
     if (sort_work(ctx, wk_in, wk_out, wv_in, d_perm, n, true)) return 1;             // decreasing number of seed slots
     const int chain_heavy = 64;
+    const int chain_coop_min = env_int("BM2_CHAIN_COOP_MIN", 1024, 0, 1 << 30);      // seed occurrences from which a warp shares the chaining of a read
     chain_kernel<<<(n + 127) / 128, 128, 0, st>>>(pv.cv, pv.cp, P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_READ_SMEM_OFF),
                                                   P<int64_t>(ctx, B_SLOT_OFF), P<int64_t>(ctx, B_SA), d_offs, n, d_perm, cb, pv.sw, ctx->idx.ref, d_codes,
-                                                  any_flt ? P<int32_t>(ctx, B_MINHSP) : nullptr, 0, chain_heavy);
+                                                  any_flt ? P<int32_t>(ctx, B_MINHSP) : nullptr, 0, chain_heavy, chain_coop_min);
     {   // heavy reads: one warp each; the sorted list ends the grid early (warps whose read is light return at once)
         int heavy_warps = n < ctx->n_sm * 256 ? n : ctx->n_sm * 256;
         chain_kernel<<<(heavy_warps * 32 + 127) / 128, 128, 0, st>>>(pv.cv, pv.cp, P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_READ_SMEM_OFF),
                                                                       P<int64_t>(ctx, B_SLOT_OFF), P<int64_t>(ctx, B_SA), d_offs, n, d_perm, cb, pv.sw,
-                                                                      ctx->idx.ref, d_codes, any_flt ? P<int32_t>(ctx, B_MINHSP) : nullptr, 1, chain_heavy);
+                                                                      ctx->idx.ref, d_codes, any_flt ? P<int32_t>(ctx, B_MINHSP) : nullptr, 1, chain_heavy, chain_coop_min);
     }
 
     // ---- E. scans + compaction ------------------------------------------------------------------------------
