@@ -792,8 +792,8 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     if (wide_possible) {
         int *next_job = class_cnt + 48;                    // zeroed with class_cnt above
         const int wblocks = n_sm * 4;
-        if (2 * prm.w + 2 <= 32 * 7)
-            bsw_warp_kernel<7><<<wblocks, BSWW_WARPS * 32, 0, stream>>>(d_jobs, idx_out, class_off, d_out, d_tbase, d_qbase, prm, next_job, d_cells);
+        if (2 * prm.w + 2 <= 32 * 7)       // 72 registers, 7.4 KB of shared memory per CTA: seven CTAs of four warps fit an SM (the jobs come from a queue)
+            bsw_warp_kernel<7><<<n_sm * 7, BSWW_WARPS * 32, 0, stream>>>(d_jobs, idx_out, class_off, d_out, d_tbase, d_qbase, prm, next_job, d_cells);
         else if (2 * prm.w + 2 <= 32 * 13)
             bsw_warp_kernel<13><<<wblocks, BSWW_WARPS * 32, 0, stream>>>(d_jobs, idx_out, class_off, d_out, d_tbase, d_qbase, prm, next_job, d_cells);
         else if (2 * prm.w + 2 <= 32 * 32)
