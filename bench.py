@@ -874,16 +874,20 @@ def run_fastq2sam(args, rank, world):
         a_ = text.split(b"\n"); b_ = want.split(b"\n")
         bad = [i for i in range(min(len(a_), len(b_))) if a_[i] != b_[i]][:3]
         raise AssertionError(f"FASTQ -> SAM text differs from the unmodified reference: {len(a_)} vs {len(b_)} lines, first differing {[(a_[i][:200], b_[i][:200]) for i in bad]}")
-    # ... and the same through the C++ host program over the C ABI (bwa-mem2_b200/bm2_mem: no python in the loop): its own chunk-loop clock
+    # ... and the same through the C++ host program over the C ABI (bwa-mem2_b200/bm2_mem: no python in the loop) on the WHOLE read files,
+    # cut by -K into chunks of the sample's size: the first chunk pays the process's allocations, the later ones are the steady state
     tool = os.path.join(ROOT, "bwa-mem2_b200", "bm2_mem")
     tool_out = os.path.join(work, "bm2_mem.sam")
     ctx.close(); ctx = None                       # (one context at a time on the GPU: the program uploads the index itself)
-    tool_stats = []
-    for _ in range(2):
-        pr = subprocess.run([tool, "-t", str(nt), "-K", "1000000000", "-o", tool_out, fa, s1, s2], capture_output=True, text=True, check=True)
-        tool_stats.append(json.loads(pr.stderr.strip().splitlines()[-1]))
-    got_tool = b"".join(ln for ln in open(tool_out, "rb") if not ln.startswith(b"@"))
-    assert got_tool == want, "bm2_mem's SAM differs from the unmodified reference"
+    reads_all = np.load(os.path.join(work, "reads.npy"), mmap_mode="r")
+    L_read = int(reads_all.shape[1])
+    k_bases = 2 * sample_pairs * L_read
+    r1_all = os.path.join(work, "r1.fq"); r2_all = os.path.join(work, "r2.fq")
+    pr = subprocess.run([tool, "-t", str(nt), "-K", str(k_bases), "-o", tool_out, fa, r1_all, r2_all], capture_output=True, text=True, check=True)
+    tool_stats = [json.loads(pr.stderr.strip().splitlines()[-1])]
+    with open(tool_out, "rb") as f:
+        got_tool = b"".join(ln for _, ln in zip(range(len(want.splitlines()) + 64), f) if not ln.startswith(b"@"))
+    assert got_tool[:len(want)] == want, "bm2_mem's SAM (first chunk) differs from the unmodified reference"
     os.remove(tool_out); os.remove(ref_sam)
     ts = tool_stats[-1]
     ctx = capi.Context(dev, index=index, opt=opt); ctx.set_sam_staged(1)
@@ -895,13 +899,17 @@ def run_fastq2sam(args, rank, world):
     wall = (time.perf_counter() - t0) / args.steps
     acc /= args.steps
     wall_py = wall
-    wall = ts["loop_s"]                          # the headline of this workload is the C++ program's chunk loop (second of two runs)
+    n_first = ts["chunk_reads"][0]
+    steady_reads = ts["reads"] - n_first; steady_s = ts["loop_s"] - ts["chunk_s"][0]
+    n = steady_reads; wall = steady_s            # the headline of this workload: the C++ program's chunk loop after its first chunk
     out = {"metric": METRIC_SAM, "value": n / wall, "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/int16/f64", "data": "synthetic",
-           "config": {"workload": f"first {n} reads ({n // 2} pairs) of the default workload as FASTQ bytes ({len(b1) + len(b2)} B) -> {len(text)} B of SAM text, "
+           "config": {"workload": f"chunks of {2 * sample_pairs} reads ({sample_pairs} pairs) of the default workload as FASTQ bytes ({len(b1) + len(b2)} B per chunk) -> {len(text)} B of SAM text per chunk, "
                                   f"{args.ref_mbp} Mbp reference; one chunk per step, wall clock; python binding overheads (array copies, name list) included"},
-           "how": "bwa-mem2_b200/bm2_mem (C++ over the C ABI): FASTQ files already read into host memory -> SAM bytes written to a file; "
-                  "the clock covers its chunk loop (parse+encode, align, pestat, SAM stage, format, fwrite), not the index load",
+           "how": "bwa-mem2_b200/bm2_mem (C++ over the C ABI) on the whole read files (%d reads, %d chunks of -K %d bases): FASTQ files already read into "
+                  "host memory -> SAM bytes written to a file; the clock covers its chunk loop after the first chunk (parse+encode, align, pestat, SAM stage, "
+                  "format, fwrite); first chunk (allocations of a fresh process) %.3f s, whole loop %.3f s" % (ts["reads"], ts["chunks"], k_bases, ts["chunk_s"][0], ts["loop_s"]),
+           "chunk_s": ts["chunk_s"],
            "stage_s": {k: ts[k] for k in ("fastq_encode_s", "seed_chain_extend_s", "pestat_s", "sam_stage_s", "sam_format_s", "write_s")},
            "through_the_python_binding": {"reads_per_s": n / wall_py, "stage_s": dict(zip(["fastq_encode", "seed_chain_extend", "pestat", "sam_pe_staged", "sam_format"],
                                                                                       [round(float(x), 4) for x in acc]))},

@@ -368,7 +368,7 @@ template <int NTHR>
 __global__ void __launch_bounds__(NTHR)
 bsw_col2_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ perm, const int32_t *__restrict__ class_off,
                 int cls, BswOut *__restrict__ out, const uint8_t *__restrict__ tbase, const uint8_t *__restrict__ qbase,
-                BswParams p, int NP, unsigned long long *cells)
+                BswParams p, int NP, unsigned long long *cells, int reg_shrink)
 {
     extern __shared__ uint32_t sh[];
     const int first = class_off[cls], last = class_off[cls + 1];
@@ -391,7 +391,8 @@ bsw_col2_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ per
                 asm volatile("st.shared.u16 [%0], %1;" :: "r"(mem.q_base + (unsigned) (k >> 1) * (NTHR * 2u)), "h"((uint16_t) wv) : "memory");
             }
             BswOut o;
-            if (same_oe) bsw_col2_extend<true>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
+            if (same_oe && reg_shrink) bsw_col2_extend<true>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
+            else if (same_oe) bsw_col2_extend<true, Col2MemShared<NTHR>, false>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
             else bsw_col2_extend<false>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
             out[id] = o;
         }
@@ -753,8 +754,10 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
             const int NP = (W + 1) / 2;                       // state words: pairs over columns 0 .. bound + 1; selectors: 2 B per pair
             // threads per CTA: the size that keeps the most threads resident per SM (shared memory is what limits this kernel's
             // occupancy: 6 B per column pair and thread; 64- or 96-thread CTAs waste less of the 227 KB than 128-thread ones)
+            const char *rs_env = getenv("BM2_BSW_REGSHRINK");
+            const int reg_shrink = (rs_env && rs_env[0] == '0') ? 0 : 1;
             int nthr2 = 128, best_res = 0, best_cps = 1;
-            int t_lo = 64, t_hi = 128;
+            int t_lo = 128, t_hi = 128;           // measured (profiles/r2e_exp_knobs.log): 128-thread CTAs 50.1 ms, 96: 53.5, 64: 51.2, most-resident-threads choice 52.3
             if (const char *e = getenv("BM2_BSW_NTHR")) { const int v = atoi(e); if (v == 64 || v == 96 || v == 128) t_lo = t_hi = v; }      // A/B measurements
             for (int t = t_hi; t >= t_lo; t -= 32) {
                 int cps = (int) (smem_budget / ((size_t) NP * 6 * t + 1024)); if (cps < 1) cps = 1; if (cps > max_ctas * (128 / t)) cps = max_ctas * (128 / t);
@@ -763,7 +766,7 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
             }
             const size_t smem2 = (size_t) NP * 6 * nthr2;
             int nb = (n + nthr2 - 1) / nthr2; if (nb > n_sm * best_cps) nb = n_sm * best_cps;
-#define BM2_COL2_LAUNCH(T) bsw_col2_kernel<T><<<nb, T, smem2, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, NP, d_cells)
+#define BM2_COL2_LAUNCH(T) bsw_col2_kernel<T><<<nb, T, smem2, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, NP, d_cells, reg_shrink)
             if (nthr2 == 128) BM2_COL2_LAUNCH(128); else if (nthr2 == 96) BM2_COL2_LAUNCH(96); else BM2_COL2_LAUNCH(64);
 #undef BM2_COL2_LAUNCH
             continue;

@@ -452,7 +452,7 @@ extern "C" int bm2_gather_probe(bm2_ctx *ctx, unsigned long long span_bytes, int
     if (!ctx || !gbs || shape < 0 || shape > 3) return 1;
     if (!ctx->idx.loaded) { bm2_set_error(ctx, "bm2_gather_probe needs a context created with an index"); return 1; }
     BM2_CUDA_OK(cudaSetDevice(ctx->device));
-    const unsigned long long unit = shape == 1 ? 32 : 64;
+    const unsigned long long unit = (shape == 1 || shape == 3) ? 32 : 64;
     unsigned long long n_units = ((unsigned long long) (ctx->idx.N >> 6) + 1) * 64 / unit;
     if (span_bytes && span_bytes / unit < n_units) n_units = span_bytes / unit ? span_bytes / unit : 1;
     const int blocks = ctx->n_sm * 8, threads = 256, iters = 64;

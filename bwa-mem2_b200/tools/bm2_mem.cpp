@@ -98,6 +98,7 @@ int main(int argc, char **argv) {
     const char *p1 = b1.data(), *e1 = p1 + b1.size(), *p2 = b2.data(), *e2 = p2 + b2.size();
     long long n_processed = 0, n_chunks = 0;
     double t_enc = 0, t_aln = 0, t_pes = 0, t_sam = 0, t_fmt = 0, t_write = 0;
+    std::vector<double> chunk_s; std::vector<long long> chunk_reads;
     const double t_loop = now_s();
     while (p1 < e1) {
         // one chunk: records until the base count reaches the task size (src/bwa.cpp:204)
@@ -145,13 +146,18 @@ int main(int argc, char **argv) {
         bm2_free(text);
         t_write += now_s() - t5;
         n_processed += fq.n_reads; ++n_chunks;
+        chunk_s.push_back(now_s() - t0); chunk_reads.push_back(fq.n_reads);
     }
     if (f2 && p2 < e2) fprintf(stderr, "[W::bm2_mem] the 1st file has fewer sequences.\n");
     const double loop_s = now_s() - t_loop;
     if (out != stdout) fclose(out);
     fprintf(stderr, "{\"reads\": %lld, \"chunks\": %lld, \"loop_s\": %.6f, \"index_and_context_s\": %.3f, \"fastq_encode_s\": %.6f, \"seed_chain_extend_s\": %.6f, "
-                    "\"pestat_s\": %.6f, \"sam_stage_s\": %.6f, \"sam_format_s\": %.6f, \"write_s\": %.6f}\n",
+                    "\"pestat_s\": %.6f, \"sam_stage_s\": %.6f, \"sam_format_s\": %.6f, \"write_s\": %.6f, \"chunk_s\": [",
             n_processed, n_chunks, loop_s, t_index, t_enc, t_aln, t_pes, t_sam, t_fmt, t_write);
+    for (size_t i = 0; i < chunk_s.size(); ++i) fprintf(stderr, "%s%.6f", i ? ", " : "", chunk_s[i]);
+    fprintf(stderr, "], \"chunk_reads\": [");
+    for (size_t i = 0; i < chunk_reads.size(); ++i) fprintf(stderr, "%s%lld", i ? ", " : "", chunk_reads[i]);
+    fprintf(stderr, "]}\n");
     bm2_destroy(ctx); bm2_index_free(idx);
     return 0;
 }

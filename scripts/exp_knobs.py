@@ -8,28 +8,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package
 
-KNOBS = ("BM2_BSW_NTHR", "BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
+KNOBS = ("BM2_BSW_REGSHRINK", "BM2_CHAIN_COOP_MIN", "BM2_BSW_NTHR", "BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
 CONFIGS = [
     dict(name="default, sub 4", sub=4),
     dict(name="default, sub 1", sub=1),
-    dict(name="sub 1, bsw 128-thread CTAs", sub=1, BM2_BSW_NTHR="128"),
-    dict(name="sub 1, bsw 96-thread CTAs", sub=1, BM2_BSW_NTHR="96"),
-    dict(name="sub 1, bsw 64-thread CTAs", sub=1, BM2_BSW_NTHR="64"),
-    dict(name="sub 1, bsw 128-thread CTAs, smem 180 KB", sub=1, BM2_BSW_NTHR="128", BM2_BSW_SMEM_KB="180"),
-    dict(name="sub 4, bsw 128-thread CTAs", sub=4, BM2_BSW_NTHR="128"),
-    # round 2: does the extension kernel starve the SMEM kernels of shared memory?  (its persistent CTAs take all 227 KB of an SM by
-    # default; smem_fwd1 / pass3 / bwd need 10-16 KB per CTA and cannot start next to them)
-    dict(name="sub 4, bsw smem 200 KB", sub=4, BM2_BSW_SMEM_KB="200"),
-    dict(name="sub 4, bsw smem 180 KB", sub=4, BM2_BSW_SMEM_KB="180"),
-    dict(name="sub 4, bsw smem 160 KB", sub=4, BM2_BSW_SMEM_KB="160"),
-    dict(name="sub 4, bsw smem 128 KB", sub=4, BM2_BSW_SMEM_KB="128"),
-    dict(name="sub 4, bsw smem 180 KB, smem ctas 6", sub=4, BM2_BSW_SMEM_KB="180", BM2_SMEM_CTAS="6"),
-    dict(name="sub 4, bsw smem 160 KB, smem ctas 8", sub=4, BM2_BSW_SMEM_KB="160", BM2_SMEM_CTAS="8"),
-    dict(name="sub 2, bsw smem 180 KB, smem ctas 6", sub=2, BM2_BSW_SMEM_KB="180", BM2_SMEM_CTAS="6"),
-    dict(name="sub 3, bsw smem 180 KB, smem ctas 5", sub=3, BM2_BSW_SMEM_KB="180", BM2_SMEM_CTAS="5"),
-    dict(name="sub 6, bsw smem 180 KB, smem ctas 3", sub=6, BM2_BSW_SMEM_KB="180", BM2_SMEM_CTAS="3"),
-    dict(name="sub 8, bsw smem 160 KB, smem ctas 3", sub=8, BM2_BSW_SMEM_KB="160", BM2_SMEM_CTAS="3"),
-    dict(name="sub 4, bsw ctas <= 3", sub=4, BM2_BSW_MAX_CTAS="3"),
+    dict(name="sub 1, band shrink by scans (round 1)", sub=1, BM2_BSW_REGSHRINK="0"),
+    dict(name="sub 1, warp chaining from 64 seed slots", sub=1, BM2_CHAIN_COOP_MIN="64"),
+    dict(name="sub 1, warp chaining from 256 seed slots", sub=1, BM2_CHAIN_COOP_MIN="256"),
+    dict(name="sub 1, warp chaining off", sub=1, BM2_CHAIN_COOP_MIN="1000000000"),
+    dict(name="default, sub 1 (again)", sub=1),
+    dict(name="sub 4, band shrink by scans", sub=4, BM2_BSW_REGSHRINK="0"),
+    dict(name="sub 4, warp chaining from 64", sub=4, BM2_CHAIN_COOP_MIN="64"),
     dict(name="default, sub 4 (again)", sub=4),
 ]
 
@@ -75,7 +64,7 @@ def main():
     # parity of one knob setting against another on a slice (regs must be byte-identical whatever the knobs)
     ns = 65536
     outs = []
-    for env in (dict(BM2_BSW_COL2="0", BM2_STAGE_TOKENS="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5")):
+    for env in (dict(BM2_BSW_COL2="0", BM2_STAGE_TOKENS="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5"), dict(BM2_BSW_REGSHRINK="0", BM2_CHAIN_COOP_MIN="64")):
         for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update(env)
