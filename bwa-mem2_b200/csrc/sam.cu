@@ -23,6 +23,7 @@
 #include "ksw_warp.cuh"
 #include "mate_stage.cuh"
 #include <vector>
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -30,7 +31,7 @@
 namespace {
 enum { SB_CODES = 64, SB_OFFS, SB_REGS, SB_REGOFF, SB_DESC, SB_ARENA, SB_RECS_W, SB_XA_W, SB_OPS_W, SB_MD_W, SB_CNT, SB_FINAL, SB_LOG, SB_TERM,
        SB_RECS, SB_XA, SB_OPS, SB_MD };
-enum { SJ_PAIRJOBS = 90, SJ_JOBS, SJ_RES, SJ_LISTS, SJ_STATS };          // staged rescue (84-89 belong to ksw.cu)
+enum { SJ_PAIRJOBS = 90, SJ_JOBS, SJ_RES, SJ_LISTS, SJ_STATS, SB_ORDER };          // staged rescue (84-89 belong to ksw.cu); processing order
 static_assert(SJ_STATS < 96, "bm2_ctx::d[] too small");
 enum { SH_RECS = 16, SH_XA, SH_OPS, SH_MD, SH_CNT, SH_STAGE };
 static_assert(SB_MD < 96, "bm2_ctx::d[] too small");
@@ -144,10 +145,15 @@ __global__ void __launch_bounds__(64)
 sam_kernel(SamParams p, SamTables tb, ContigView cv, MatePes pes, int max_matesw, int rescue, const uint8_t *__restrict__ ref,
            const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs, const bm2_alnreg_t *__restrict__ regs, const int64_t *__restrict__ reg_off,
            const PairDesc *__restrict__ desc, int n_pairs, int paired, int64_t id_base, uint8_t *arena, bm2_sam_rec *recs_w, bm2_sam_xa *xa_w, uint32_t *ops_w,
-           char *md_w, PairCount *cnt, const PairJobs *__restrict__ pj, const MateJob *__restrict__ jobs, const MateJobRes *__restrict__ jres, SamStats *stats)
+           char *md_w, PairCount *cnt, const PairJobs *__restrict__ pj, const MateJob *__restrict__ jobs, const MateJobRes *__restrict__ jres, SamStats *stats,
+           const int32_t *__restrict__ order)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_pairs) return;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t0 >= n_pairs) return;
+    // order: the wave's pairs sorted by a work key (host): the 32 pairs of a warp run similar code - same number of regions, the same
+    // need for a gapped CIGAR - instead of waiting for the one pair that needs a banded DP.  Every per-pair slot is indexed by t, so the
+    // output (stripes, counts, the gather) does not depend on the order.
+    const int t = order ? order[t0] : t0;
     const PairDesc d = desc[t];
     SamArena ar;
     sam_arena_carve_d(arena + d.arena_off, d.caps, 0, &ar);
@@ -398,13 +404,39 @@ int run_sam(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs,
             }
             BM2_CUDA_OK(cudaGetLastError());
         } else BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[1], st));
+        {   // processing order of the per-pair kernel: pairs that need a gapped CIGAR (infer_bw > 0 for the best region of a read: a banded DP
+            // with backtrack) apart from those that do not, then by the number of regions (mark_primary / pairing are quadratic in it)
+            std::vector<std::pair<int, int32_t>> keyed((size_t) np);
+            for (int k = 0; k < np; ++k) {
+                const int pr = desc[(size_t) (w0 + k)].pair;
+                int gapped = 0; long long nreg = 0;
+                for (int i = 0; i < (paired ? 2 : 1); ++i) {
+                    const int r = paired ? 2 * pr + i : pr;
+                    const int64_t b = read_off[r], e = read_off[r + 1];
+                    nreg += e - b;
+                    for (int64_t q = b; q < e && q < b + 2; ++q) {
+                        const bm2_alnreg_t &a = regs[q];
+                        const int l1 = a.qe - a.qb, l2 = (int) (a.re - a.rb);
+                        if (sam_infer_bw_d(l1, l2, a.truesc, o.a, o.o_del, o.e_del) > 0 || sam_infer_bw_d(l1, l2, a.truesc, o.a, o.o_ins, o.e_ins) > 0) ++gapped;
+                    }
+                }
+                keyed[(size_t) k] = { gapped * 4096 + (int) (nreg > 4095 ? 4095 : nreg), (int32_t) k };
+            }
+            const char *env = getenv("BM2_SAM_ORDER");
+            if (!(env && env[0] == '0')) std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<int, int32_t> &x, const std::pair<int, int32_t> &y) { return x.first < y.first; });
+            std::vector<int32_t> order((size_t) np);
+            for (int k = 0; k < np; ++k) order[(size_t) k] = keyed[(size_t) k].second;
+            if (ctx->ensure(ctx->d[SB_ORDER], (size_t) np * 4 + 16)) return 1;
+            BM2_CUDA_OK(cudaMemcpyAsync(ctx->d[SB_ORDER].p, order.data(), (size_t) np * 4, cudaMemcpyHostToDevice, st));
+            BM2_CUDA_OK(cudaStreamSynchronize(st));              // (order is a local vector)
+        }
         BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[2], st));
         sam_kernel<<<(unsigned) ((np + 63) / 64), 64, 0, st>>>(p, tb, cv, pes, o.max_matesw, rescue, ctx->idx.ref, P<uint8_t>(ctx, SB_CODES), P<int64_t>(ctx, SB_OFFS),
                                                               P<bm2_alnreg_t>(ctx, SB_REGS), P<int64_t>(ctx, SB_REGOFF), P<PairDesc>(ctx, SB_DESC), np, paired, id_base,
                                                               P<uint8_t>(ctx, SB_ARENA), P<bm2_sam_rec>(ctx, SB_RECS_W), P<bm2_sam_xa>(ctx, SB_XA_W),
                                                               P<uint32_t>(ctx, SB_OPS_W), P<char>(ctx, SB_MD_W), P<PairCount>(ctx, SB_CNT),
                                                               staged ? P<PairJobs>(ctx, SJ_PAIRJOBS) : nullptr, P<MateJob>(ctx, SJ_JOBS), P<MateJobRes>(ctx, SJ_RES),
-                                                              P<SamStats>(ctx, SJ_STATS));
+                                                              P<SamStats>(ctx, SJ_STATS), P<int32_t>(ctx, SB_ORDER));
         BM2_CUDA_OK(cudaGetLastError());
         BM2_CUDA_OK(cudaEventRecord(ctx->sam_ev[3], st));
         SamStats wave_stats;
