@@ -403,8 +403,8 @@ def run_pipeline(args, rank, world):
     # requests in flight per thread, inside L2 (32 MB span) and over 4 GB: separates DRAM, request-rate and latency limits; the last shape is
     # the bulk-async (TMA) path: cp.async.bulk of 32 B into shared memory behind a per-thread mbarrier
     gather_by_span = {f"{mb}MB_{nm}_mlp{k}": round(ctx.gather_probe(mb << 20, k, sh), 1)
-                      for mb in (32, 4096) for sh, nm in ((0, "64B_4x16"), (1, "32B_1x256"), (2, "64B_2x256"), (3, "32B_bulk_async_tma")) for k in (1, 4, 8)
-                      if not (sh == 3 and k == 8)}
+                      for mb in (32, 4096) for sh, nm in ((0, "64B_4x16"), (1, "32B_1x256"), (2, "64B_2x256"), (3, "32B_bulk_async_tma"), (4, "32B_tma_plus_loads")) for k in (1, 4, 8)
+                      if not (sh >= 3 and k == 8)}
     index_how = "built by the reference binary" if args.ref_mbp <= 400 else "built on the GPU by bwa_mem2_b200.index_build, byte-identical format"
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)

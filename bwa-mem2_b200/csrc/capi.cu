@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(256) gather_probe_kernel(const char *__restric
 // announces the bytes (mbarrier.arrive.expect_tx), issues cp.async.bulk.shared::cluster.global per request and waits on the barrier's
 // phase - the "Occ blocks TMA-staged to shared memory" shape of the north star, per lane because every lane of the SMEM kernels extends
 // its own interval at its own random address (there is no tile to describe with a tensor map).
-template <int MLP>
+template <int MLP, bool MIXED>
 __global__ void __launch_bounds__(256) gather_probe_bulk_kernel(const char *__restrict__ tab, unsigned long long n_units, int iters, unsigned long long seed,
                                                                 unsigned *out) {
     __shared__ __align__(32) unsigned long long slots[256][MLP][4];
@@ -433,6 +433,17 @@ __global__ void __launch_bounds__(256) gather_probe_bulk_kernel(const char *__re
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 32, [%2];"
                          :: "r"(dst), "l"(tab + e * 32), "r"(bar) : "memory");
         }
+        if (MIXED) {          // shape 4: the same number of 256-bit loads in flight next to the bulk copies (do the two paths add up?)
+            unsigned long long v[MLP][4];
+#pragma unroll
+            for (int m = 0; m < MLP; ++m) {
+                x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+                const unsigned long long e = (unsigned long long) (((unsigned __int128) x * n_units) >> 64);
+                ld256(tab + e * 32, v[m][0], v[m][1], v[m][2], v[m][3]);
+            }
+#pragma unroll
+            for (int m = 0; m < MLP; ++m) acc += v[m][0] + v[m][1] + v[m][2] + v[m][3];
+        }
         unsigned done = 0;
         while (!done) {
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
@@ -449,10 +460,10 @@ __global__ void __launch_bounds__(256) gather_probe_bulk_kernel(const char *__re
 
 extern "C" int bm2_gather_probe(bm2_ctx *ctx, unsigned long long span_bytes, int mlp, int shape, double *gbs) {
     bm2_ctx *ctx_for_error = ctx;
-    if (!ctx || !gbs || shape < 0 || shape > 3) return 1;
+    if (!ctx || !gbs || shape < 0 || shape > 4) return 1;
     if (!ctx->idx.loaded) { bm2_set_error(ctx, "bm2_gather_probe needs a context created with an index"); return 1; }
     BM2_CUDA_OK(cudaSetDevice(ctx->device));
-    const unsigned long long unit = (shape == 1 || shape == 3) ? 32 : 64;
+    const unsigned long long unit = (shape == 1 || shape >= 3) ? 32 : 64;
     unsigned long long n_units = ((unsigned long long) (ctx->idx.N >> 6) + 1) * 64 / unit;
     if (span_bytes && span_bytes / unit < n_units) n_units = span_bytes / unit ? span_bytes / unit : 1;
     const int blocks = ctx->n_sm * 8, threads = 256, iters = 64;
@@ -465,7 +476,8 @@ extern "C" int bm2_gather_probe(bm2_ctx *ctx, unsigned long long span_bytes, int
         BM2_CUDA_OK(cudaEventRecord(e0, ctx->stream));
 #define BM2_GP(M, S) gather_probe_kernel<M, S><<<blocks, threads, 0, ctx->stream>>>(tab, n_units, iters, 777 + rep, o)
 #define BM2_GPS(M) do { if (shape == 0) BM2_GP(M, 0); else if (shape == 1) BM2_GP(M, 1); else if (shape == 2) BM2_GP(M, 2); \
-                        else gather_probe_bulk_kernel<(M > 4 ? 4 : M)><<<blocks, threads, 0, ctx->stream>>>(tab, n_units, iters, 777 + rep, o); } while (0)
+                        else if (shape == 3) gather_probe_bulk_kernel<(M > 4 ? 4 : M), false><<<blocks, threads, 0, ctx->stream>>>(tab, n_units, iters, 777 + rep, o); \
+                        else gather_probe_bulk_kernel<(M > 4 ? 4 : M), true><<<blocks, threads, 0, ctx->stream>>>(tab, n_units, iters, 777 + rep, o); } while (0)
         if (mlp <= 1) BM2_GPS(1); else if (mlp == 2) BM2_GPS(2); else if (mlp <= 4) BM2_GPS(4); else BM2_GPS(8);
 #undef BM2_GPS
 #undef BM2_GP
@@ -475,7 +487,8 @@ extern "C" int bm2_gather_probe(bm2_ctx *ctx, unsigned long long span_bytes, int
         if (rep > 0 && ms < best) best = ms;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    const int m_eff = mlp <= 1 ? 1 : mlp == 2 ? 2 : mlp <= 4 ? 4 : (shape == 3 ? 4 : 8);      // (the bulk shape holds at most 4 slots per thread)
+    int m_eff = mlp <= 1 ? 1 : mlp == 2 ? 2 : mlp <= 4 ? 4 : (shape >= 3 ? 4 : 8);      // (the bulk shapes hold at most 4 slots per thread)
+    if (shape == 4) m_eff *= 2;                                                          // mixed: as many loads as bulk copies
     *gbs = (double) blocks * threads * (double) iters * m_eff * (double) unit / (best * 1e-3) / 1e9;
     return 0;
 }

@@ -117,7 +117,7 @@ int  bm2_int_pipe_gops(bm2_ctx *ctx, double *gops_s32);
 int  bm2_gather64_gbs(bm2_ctx *ctx, unsigned long long span_bytes, double *gbs);
 /* The same probe with a selectable request shape and memory-level parallelism: shape 0 = 64 B as four 16-B loads of one thread,
  * 1 = 32 B as ONE 256-bit load (the half-checkpoint of the device Occ layout), 2 = 64 B as two 256-bit loads, 3 = 32 B by cp.async.bulk
- * into shared memory behind an mbarrier (the TMA path; at most 4 in flight per thread); `mlp` (1, 2, 4, 8)
+ * into shared memory behind an mbarrier (the TMA path; at most 4 in flight per thread), 4 = shape 3 and shape 1 together (mlp of each); `mlp` (1, 2, 4, 8)
  * independent requests in flight per thread.  GB/s of requested bytes.  Decides whether the SMEM stage is bound by DRAM, by the
  * load/store unit's request rate or by latency. */
 int  bm2_gather_probe(bm2_ctx *ctx, unsigned long long span_bytes, int mlp, int shape, double *gbs);
