@@ -516,6 +516,7 @@ bsw_warp_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ per
             if (w > max_del) w = max_del;
         }
         const int zthr = bsw_quirk(qlen, tlen, h0, p).zthr;      // (never the 8-bit class here: 16-bit threshold, no guard)
+        const bool packed_key = qlen < 65536 && (long long) h0 + (long long) (qlen < tlen ? qlen : tlen) * p.a < 32768;
         // the launcher guarantees 2*w+2 <= 32*CMAX for this instantiation
         int max_init = -1;
         int best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0;
@@ -584,12 +585,18 @@ bsw_warp_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ per
             if (n > 0) h1 = __shfl_sync(0xffffffffu, hlast, (n - 1) / c);
             if (lane == 0) { H[end % WCAP] = h1; E[end % WCAP] = 0; }
             ncell += (lane == 0 && n > 0) ? (unsigned) n : 0u;
-            // row maximum: largest h, among equals the largest column
+            // row maximum: largest h, among equals the largest column.  Scores below 2^15 and columns below 2^16 (every long-read job with the
+            // default scoring) pack into one key and one REDUX instruction; otherwise ten shuffles
             int m = lm, mj = lmj;
+            if (packed_key) {
+                const int kmax = __reduce_max_sync(0xffffffffu, lm < 0 ? -1 : ((lm << 16) | lmj));
+                m = kmax < 0 ? -1 : kmax >> 16; mj = kmax < 0 ? -1 : (kmax & 0xFFFF);
+            } else {
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                const int om = __shfl_xor_sync(0xffffffffu, m, d), oj = __shfl_xor_sync(0xffffffffu, mj, d);
-                if (om > m || (om == m && oj > mj)) { m = om; mj = oj; }
+                for (int d = 16; d > 0; d >>= 1) {
+                    const int om = __shfl_xor_sync(0xffffffffu, m, d), oj = __shfl_xor_sync(0xffffffffu, mj, d);
+                    if (om > m || (om == m && oj > mj)) { m = om; mj = oj; }
+                }
             }
             if (m < 0) { m = 0; mj = -1; }
             __syncwarp();
@@ -613,11 +620,8 @@ bsw_warp_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ per
             for (int j = beg + lane; j <= end; j += 32) {
                 if ((H[j % WCAP] | E[j % WCAP]) != 0) { if (j < end && j < fz) fz = j; if (j > lz) lz = j; }
             }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                fz = min(fz, __shfl_xor_sync(0xffffffffu, fz, d));
-                lz = max(lz, __shfl_xor_sync(0xffffffffu, lz, d));
-            }
+            fz = __reduce_min_sync(0xffffffffu, fz);
+            lz = __reduce_max_sync(0xffffffffu, lz);
             if (lz < fz) lz = fz - 1;                          // (all zero: cannot happen after m > 0; scalar semantics anyway)
             beg = fz;                                          // == end when the whole row is zero
             end = lz + 2 < qlen ? lz + 2 : qlen;
