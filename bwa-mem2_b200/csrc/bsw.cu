@@ -759,7 +759,9 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
             // threads per CTA: the size that keeps the most threads resident per SM (shared memory is what limits this kernel's
             // occupancy: 6 B per column pair and thread; 64- or 96-thread CTAs waste less of the 227 KB than 128-thread ones)
             const char *rs_env = getenv("BM2_BSW_REGSHRINK");
-            const int reg_shrink = (rs_env && rs_env[0] == '0') ? 0 : 1;
+            // band shrink decided from the two words just written instead of scanning shared memory: measured 2 % SLOWER (49.6 against 48.5 ms,
+            // profiles/r2g_exp_knobs.log: the extra branches cost more than the one or two loads they save) - off unless BM2_BSW_REGSHRINK=1
+            const int reg_shrink = (rs_env && rs_env[0] == '1') ? 1 : 0;
             int nthr2 = 128, best_res = 0, best_cps = 1;
             int t_lo = 128, t_hi = 128;           // measured (profiles/r2e_exp_knobs.log): 128-thread CTAs 50.1 ms, 96: 53.5, 64: 51.2, most-resident-threads choice 52.3
             if (const char *e = getenv("BM2_BSW_NTHR")) { const int v = atoi(e); if (v == 64 || v == 96 || v == 128) t_lo = t_hi = v; }      // A/B measurements

@@ -792,7 +792,9 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     // Measured (profiles/r1q_exp_smem_ctas.log, 1 M reads, 3 Gbp): unsplit batch 8 CTAs/SM: SMEM stage 47 ms against 55 ms with 10
     // and 50 ms with 6 (the stage sits on the random-access roofline of HBM: more searches in flight only thrash L2 / the DRAM
     // pages); four sub-batch lanes with 3-4 CTAs/SM each: 126.5-127.3 ms per step against 129.2-129.8 ms with 10.
-    const int smem_ctas = env_int("BM2_SMEM_CTAS", ctx->parent ? 4 : 8, 1, 16);
+    const int use_tokens = ctx->parent ? env_int("BM2_STAGE_TOKENS", 0, 0, 3) : 0;
+    // (with the SMEM token only one lane is in the SMEM stage at a time: it gets the unsplit batch's 8 CTAs per SM)
+    const int smem_ctas = env_int("BM2_SMEM_CTAS", (ctx->parent && !(use_tokens & 1)) ? 4 : 8, 1, 16);
     int blocks_a = (n + 127) / 128; int max_blocks_a = ctx->n_sm * smem_ctas;
     {   // per-thread forward scratch = stripe * 32 bytes: keep it under ~8 GB for long reads
         const size_t per_block = (size_t) 128 * stripe * sizeof(FmPrev);
@@ -814,7 +816,6 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     // BM2_STAGE_TOKENS: bit 0 = SMEM-stage token, bit 1 = extension-stage token (sub-batch lanes only).  Off by default:
     // measured SLOWER (149-160 ms against 138 ms per 1 M-read step, profiles/r1o_exp_stage_tokens.log) - taking turns in
     // a stage leaves the other lanes' host threads waiting at the token instead of queueing work.
-    const int use_tokens = ctx->parent ? env_int("BM2_STAGE_TOKENS", 0, 0, 3) : 0;
     StageToken tok_smem((use_tokens & 1) ? &ctx->parent->tok_smem : nullptr);
     for (int attempt = 0; attempt < 3; ++attempt) {
         if (ctx->ensure(ctx->d[B_SMEM_RAW], cap * sizeof(bm2_smem)) || ctx->ensure(ctx->d[B_POOL], pool_cap * sizeof(FmPrev)) ||

@@ -422,8 +422,12 @@ int run_sam(bm2_ctx *ctx, const bm2_read_batch *reads, const bm2_alnreg_t *regs,
                 }
                 keyed[(size_t) k] = { gapped * 4096 + (int) (nreg > 4095 ? 4095 : nreg), (int32_t) k };
             }
+            // Measured (profiles/r2g_bench_sam*.json, 100 k pairs): the sorted order is SLOWER, 185 against 125 ms - the kernel is bound by the
+            // latency of its per-thread global-memory DP rows and backtrack bytes (91 stall cycles per issue on long scoreboard, 3 % of the issue
+            // slots, profiles/r2g_sam_kernel_staged.md), and neighbouring pairs share cache lines of regs / reads that the sort scatters.  Off
+            // unless BM2_SAM_ORDER=1.
             const char *env = getenv("BM2_SAM_ORDER");
-            if (!(env && env[0] == '0')) std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<int, int32_t> &x, const std::pair<int, int32_t> &y) { return x.first < y.first; });
+            if (env && env[0] == '1') std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<int, int32_t> &x, const std::pair<int, int32_t> &y) { return x.first < y.first; });
             std::vector<int32_t> order((size_t) np);
             for (int k = 0; k < np; ++k) order[(size_t) k] = keyed[(size_t) k].second;
             if (ctx->ensure(ctx->d[SB_ORDER], (size_t) np * 4 + 16)) return 1;
