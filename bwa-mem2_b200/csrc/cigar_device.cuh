@@ -50,10 +50,10 @@ BM2_HD int global_align_d(int qlen, const uint8_t *qp, int qstride, int tlen, co
         const int tb = tp[(long long) i * tstride];
         h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : MINUS_INF;
         const long long zi = (long long) i * n_col;
-        for (j = beg; j < end; ++j) {
-            int32_t m = H[j], e = E[j];
-            H[j] = h1;
-            m += mat[tb * 5 + qp[(long long) j * qstride]];
+        // One cell: the recurrence of ksw_global2 on values already in registers.  hs = the value H[j] takes (the previous cell's h).
+        auto cell = [&](int32_t m, int32_t e, const int qb, int32_t &hs, int32_t &es) -> uint8_t {
+            hs = h1;
+            m += mat[tb * 5 + qb];
             uint8_t d = m >= e ? 0 : 1;
             int32_t h = m >= e ? m : e;
             d = h >= f ? d : 2;
@@ -63,11 +63,33 @@ BM2_HD int global_align_d(int qlen, const uint8_t *qp, int qstride, int tlen, co
             e -= e_del;
             d |= e > t ? 1 << 2 : 0;
             e = e > t ? e : t;
-            E[j] = e;
+            es = e;
             t = m - oe_ins;
             f -= e_ins;
             d |= f > t ? 2 << 4 : 0;
             f = f > t ? f : t;
+            return d;
+        };
+        // Four cells per trip with all their loads (H, E, query bases) issued before the first cell is computed: the loads of neighbouring
+        // cells do not depend on each other (only h1 and f run along the row, in registers), so a thread keeps 12 loads in flight instead of
+        // waiting for each in turn - the rows live in per-thread global memory and this loop was bound by their latency (round 2 profile of the
+        // SAM stage: 91 stall cycles per issued instruction, profiles/r2g_sam_kernel_staged.md).  Same arithmetic, same order.
+        for (j = beg; j + 4 <= end; j += 4) {
+            const int32_t m0 = H[j], m1 = H[j + 1], m2 = H[j + 2], m3 = H[j + 3];
+            const int32_t e0 = E[j], e1 = E[j + 1], e2 = E[j + 2], e3 = E[j + 3];
+            const int q0 = qp[(long long) j * qstride], q1 = qp[(long long) (j + 1) * qstride], q2 = qp[(long long) (j + 2) * qstride],
+                      q3 = qp[(long long) (j + 3) * qstride];
+            int32_t hs0, hs1, hs2, hs3, es0, es1, es2, es3;
+            const uint8_t d0 = cell(m0, e0, q0, hs0, es0), d1 = cell(m1, e1, q1, hs1, es1), d2 = cell(m2, e2, q2, hs2, es2), d3 = cell(m3, e3, q3, hs3, es3);
+            H[j] = hs0; H[j + 1] = hs1; H[j + 2] = hs2; H[j + 3] = hs3;
+            E[j] = es0; E[j + 1] = es1; E[j + 2] = es2; E[j + 3] = es3;
+            const long long zc = zi + (j - beg);
+            z.put(zc, d0); z.put(zc + 1, d1); z.put(zc + 2, d2); z.put(zc + 3, d3);
+        }
+        for (; j < end; ++j) {
+            int32_t hs, es;
+            const uint8_t d = cell(H[j], E[j], qp[(long long) j * qstride], hs, es);
+            H[j] = hs; E[j] = es;
             z.put(zi + (j - beg), d);
         }
         H[end] = h1; E[end] = MINUS_INF;
