@@ -1142,10 +1142,20 @@ static int run_regs(bm2_ctx *ctx, const bm2_read_batch *rb, const uint8_t *d_cod
     BM2_CUDA_OK(cudaEventRecord(ctx->ev_entry, ctx->stream));
     struct Job { int first = 0, n = 0; std::vector<int64_t> offs; bm2_read_batch rb; BatchState bs; int rc = 0; };
     std::vector<Job> jobs((size_t) K);
+    // cut points (multiples of 512 reads).  BM2_LANE_SKEW = s percent: lane k gets a share proportional to 100 + s * k instead of equal shares,
+    // so that the lanes - which start together - leave the SMEM stage at different times (experiment: do unequal lanes overlap unlike stages better?)
+    std::vector<int> cut((size_t) K + 1, 0);
+    {
+        const int skew = env_int("BM2_LANE_SKEW", 0, 0, 400);
+        double tot = 0; for (int k = 0; k < K; ++k) tot += 100.0 + (double) skew * k;
+        double acc = 0;
+        for (int k = 0; k < K; ++k) { cut[k] = (int) ((int64_t) ((double) n * acc / tot) / 512 * 512); acc += 100.0 + (double) skew * k; }
+        cut[K] = n;
+    }
     for (int k = 0; k < K; ++k) {
         Job &j = jobs[k];
-        j.first = (int) (((int64_t) n * k / K) / 512 * 512);
-        const int next = k + 1 < K ? (int) (((int64_t) n * (k + 1) / K) / 512 * 512) : n;
+        j.first = cut[k];
+        const int next = cut[k + 1];
         j.n = next - j.first;
         bm2_ctx *l = ctx->lanes[k];
         l->opt = ctx->opt;

@@ -8,18 +8,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package
 
-KNOBS = ("BM2_STAGE_TOKENS", "BM2_BSW_REGSHRINK", "BM2_CHAIN_COOP_MIN", "BM2_BSW_NTHR", "BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
+KNOBS = ("BM2_LANE_SKEW", "BM2_STAGE_TOKENS", "BM2_BSW_REGSHRINK", "BM2_CHAIN_COOP_MIN", "BM2_BSW_NTHR", "BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
 CONFIGS = [
     dict(name="default, sub 4", sub=4),
-    # the lanes start together and do equal work, so they run the same stage at the same time; the SMEM token staggers them: one lane in the
-    # (memory-bound) SMEM stage at a time, with the unsplit batch's 8 CTAs per SM, the others in their (ALU-bound) later stages
-    dict(name="sub 4, SMEM token", sub=4, BM2_STAGE_TOKENS="1"),
-    dict(name="sub 6, SMEM token", sub=6, BM2_STAGE_TOKENS="1"),
-    dict(name="sub 8, SMEM token", sub=8, BM2_STAGE_TOKENS="1"),
-    dict(name="sub 12, SMEM token", sub=12, BM2_STAGE_TOKENS="1"),
-    dict(name="sub 8, SMEM token, smem ctas 6", sub=8, BM2_STAGE_TOKENS="1", BM2_SMEM_CTAS="6"),
-    dict(name="sub 8, SMEM + BSW tokens", sub=8, BM2_STAGE_TOKENS="3"),
-    dict(name="sub 8, no token", sub=8),
+    dict(name="sub 4, lane skew 50", sub=4, BM2_LANE_SKEW="50"),
+    dict(name="sub 4, lane skew 100", sub=4, BM2_LANE_SKEW="100"),
+    dict(name="sub 4, lane skew 200", sub=4, BM2_LANE_SKEW="200"),
+    dict(name="sub 3, lane skew 100", sub=3, BM2_LANE_SKEW="100"),
+    dict(name="sub 6, lane skew 60", sub=6, BM2_LANE_SKEW="60"),
+    dict(name="sub 8, lane skew 40", sub=8, BM2_LANE_SKEW="40"),
     dict(name="default, sub 4 (again)", sub=4),
 ]
 
