@@ -30,6 +30,95 @@ BM2_HD void cigar_push_d(uint32_t *cigar, int &n, int op, int len) {
     else cigar[n - 1] += (uint32_t) len << 4;
 }
 
+// Forward pass of ksw_global2 with the band in REGISTERS (round 2).  The band of a global alignment is static (|i - j| <= w), so in the
+// coordinate k = j - (i - W) a column moves down by one index per row: cell k reads its column's {H, E} from slot k and writes the next
+// row's values into slot k - 1 - an in-place shift for free when the sweep runs over k ascending and every index is a compile-time constant
+// (the loops over k are fully unrolled, so the slots are registers; W = capacity, the run-time band w <= W is a predicate on k).  The query
+// bases of the window slide the same way, 4 bits per base in a few registers (one funnel shift per word and row, the new base enters at the
+// fixed slot 2W).  Same arithmetic and the same backtrack bytes at the same indices as the loop over memory rows below, which it replaces when
+// the band fits: no loads on the dependent path at all (the memory version spent 91 cycles per issued instruction waiting for its rows).
+// Requires w <= W and qlen <= tlen + w (then the last row reaches column qlen and H[qlen] is its h1).
+template <int W>
+BM2_HD int global_forward_reg_d(int qlen, const uint8_t *qp, int qstride, int tlen, const uint8_t *tp, int tstride, const int8_t *mat,
+                                int o_del, int e_del, int o_ins, int e_ins, int w, const CigarZ &z)
+{
+    const int MINUS_INF = -0x40000000;
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+    constexpr int NS = 2 * W + 2;                        // slots 0 .. 2W + 1
+    constexpr int NQ = (2 * W + 1 + 7) / 8;              // query window words (8 bases each)
+    int32_t Hb[NS], Eb[NS];
+    uint32_t qw[NQ];
+    // row-0 view: slot k <-> column j = k - W
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int j = k - W;
+        int32_t h = MINUS_INF;
+        if (j == 0) h = 0; else if (j >= 1 && j <= qlen && j <= w) h = -(o_ins + e_ins * j);
+        Hb[k] = h; Eb[k] = MINUS_INF;
+    }
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) qw[t] = 0;
+#pragma unroll
+    for (int k = 0; k <= 2 * W; ++k) {
+        const int j = k - W;
+        if (j >= 0 && j < qlen) qw[k >> 3] |= (uint32_t) (qp[(long long) j * qstride] > 4 ? 4 : qp[(long long) j * qstride]) << ((k & 7) * 4);
+    }
+    int32_t h1 = MINUS_INF;
+    for (int i = 0; i < tlen; ++i) {
+        int32_t f = MINUS_INF;
+        const int beg = i > w ? i - w : 0;
+        const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+        const int tb = tp[(long long) i * tstride];
+        h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : MINUS_INF;
+        const long long zrow = (long long) i * n_col - beg;          // z index of column j: zrow + j
+        const int ke = end - i + W;                                   // slot of column `end` in this row's view
+        // the five scores of this row's target base against query bases 0 .. 4
+        const int tb5 = (tb > 4 ? 4 : tb) * 5;
+        const int s0 = mat[tb5], s1 = mat[tb5 + 1], s2 = mat[tb5 + 2], s3 = mat[tb5 + 3], s4 = mat[tb5 + 4];
+#pragma unroll
+        for (int k = 0; k <= 2 * W; ++k) {
+            const int j = i - W + k;
+            if (j >= beg && j < end) {
+                int32_t m = Hb[k], e = Eb[k];
+                const int32_t hs = h1;
+                const uint32_t qb = (qw[k >> 3] >> ((k & 7) * 4)) & 15u;
+                m += qb == 0 ? s0 : qb == 1 ? s1 : qb == 2 ? s2 : qb == 3 ? s3 : s4;
+                uint8_t d = m >= e ? 0 : 1;
+                int32_t h = m >= e ? m : e;
+                d = h >= f ? d : 2;
+                h = h >= f ? h : f;
+                h1 = h;
+                int32_t t = m - oe_del;
+                e -= e_del;
+                d |= e > t ? 1 << 2 : 0;
+                e = e > t ? e : t;
+                t = m - oe_ins;
+                f -= e_ins;
+                d |= f > t ? 2 << 4 : 0;
+                f = f > t ? f : t;
+                z.put(zrow + j, d);
+                if (k > 0) { Hb[k - 1] = hs; Eb[k - 1] = e; }
+            }
+        }
+        // H[end] = h1; E[end] = MINUS_INF: column `end` sits in slot ke - 1 of the next row's view
+#pragma unroll
+        for (int k = 1; k < NS; ++k)
+            if (k == ke) { Hb[k - 1] = h1; Eb[k - 1] = MINUS_INF; }
+        // the query window slides by one base; column i + 1 + W enters at slot 2W
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) qw[t] = (qw[t] >> 4) | (t + 1 < NQ ? qw[t + 1] << 28 : 0u);
+        {
+            const int jn = i + 1 + W;
+            if (jn < qlen) {
+                const uint32_t c = qp[(long long) jn * qstride];
+                qw[(2 * W) >> 3] |= (c > 4 ? 4u : c) << (((2 * W) & 7) * 4);
+            }
+        }
+    }
+    return h1;                                            // = H[qlen]: the last row's band ends at column qlen
+}
+
 // ksw_global2 with backtrack (src/ksw.cpp:558-668).  he: 2*(qlen+1) ints; z: n_col*tlen cells, n_col = min(qlen, 2w+1);
 // cigar: room for qlen + tlen + 2 operations.  Returns the score; *n_cigar operations in cigar[].
 BM2_HD int global_align_d(int qlen, const uint8_t *qp, int qstride, int tlen, const uint8_t *tp, int tstride, const int8_t *mat,
@@ -38,9 +127,13 @@ BM2_HD int global_align_d(int qlen, const uint8_t *qp, int qstride, int tlen, co
     const int MINUS_INF = -0x40000000;
     const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
     const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+    int score_reg = 0;
+    const bool in_regs = w <= 16 && tlen > 0 && qlen <= tlen + w;
+    if (in_regs) score_reg = global_forward_reg_d<16>(qlen, qp, qstride, tlen, tp, tstride, mat, o_del, e_del, o_ins, e_ins, w, z);
     int32_t *H = he, *E = he + (qlen + 1);
-    H[0] = 0; E[0] = MINUS_INF;
     int j;
+    if (!in_regs) {
+    H[0] = 0; E[0] = MINUS_INF;
     for (j = 1; j <= qlen && j <= w; ++j) { H[j] = -(o_ins + e_ins * j); E[j] = MINUS_INF; }
     for (; j <= qlen; ++j) H[j] = E[j] = MINUS_INF;
     for (int i = 0; i < tlen; ++i) {
@@ -94,7 +187,8 @@ BM2_HD int global_align_d(int qlen, const uint8_t *qp, int qstride, int tlen, co
         }
         H[end] = h1; E[end] = MINUS_INF;
     }
-    const int score = H[qlen];
+    }
+    const int score = in_regs ? score_reg : H[qlen];
     // backtrack
     int n = 0, which = 0;
     int i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
