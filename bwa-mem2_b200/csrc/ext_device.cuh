@@ -238,18 +238,32 @@ BM2_HD int global_score_d(int qlen, const uint8_t *qp, int qstride, int tlen, co
         const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
         const int tb = tp[(long long) i * tstride];
         h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : MINUS_INF;
-        for (j = beg; j < end; ++j) {
-            int32_t m = H[j], e = E[j];
-            H[j] = h1;
-            m += mat[tb * 5 + qp[(long long) j * qstride]];
+        auto cell = [&](int32_t m, int32_t e, const int qb, int32_t &hs, int32_t &es) {
+            hs = h1;
+            m += mat[tb * 5 + qb];
             int32_t h = m >= e ? m : e;
             h = h >= f ? h : f;
             h1 = h;
             int32_t t = m - oe_del;
             e -= e_del; e = e > t ? e : t;
-            E[j] = e;
+            es = e;
             t = m - oe_ins;
             f -= e_ins; f = f > t ? f : t;
+        };
+        // four cells per trip, their loads first (the rows live in per-thread global memory: see global_align_d in cigar_device.cuh)
+        for (j = beg; j + 4 <= end; j += 4) {
+            const int32_t m0 = H[j], m1 = H[j + 1], m2 = H[j + 2], m3 = H[j + 3], e0 = E[j], e1 = E[j + 1], e2 = E[j + 2], e3 = E[j + 3];
+            const int q0 = qp[(long long) j * qstride], q1 = qp[(long long) (j + 1) * qstride], q2 = qp[(long long) (j + 2) * qstride],
+                      q3 = qp[(long long) (j + 3) * qstride];
+            int32_t hs0, hs1, hs2, hs3, es0, es1, es2, es3;
+            cell(m0, e0, q0, hs0, es0); cell(m1, e1, q1, hs1, es1); cell(m2, e2, q2, hs2, es2); cell(m3, e3, q3, hs3, es3);
+            H[j] = hs0; H[j + 1] = hs1; H[j + 2] = hs2; H[j + 3] = hs3;
+            E[j] = es0; E[j + 1] = es1; E[j + 2] = es2; E[j + 3] = es3;
+        }
+        for (; j < end; ++j) {
+            int32_t hs, es;
+            cell(H[j], E[j], qp[(long long) j * qstride], hs, es);
+            H[j] = hs; E[j] = es;
         }
         H[end] = h1; E[end] = MINUS_INF;
     }

@@ -26,6 +26,10 @@ struct FmIndexView {
     int64_t count[5];
     int64_t sentinel;
     int layout = 0;
+    // Reference text (2 * l_pac codes, forward || reverse complement) for the unique-interval shortcut of fm_forward; null = off (exact `l`
+    // values: the staged bm2_collect_smems entry and the host builds)
+    const uint8_t *text = nullptr;
+    int64_t text_len = 0;
 };
 
 #if defined(__CUDA_ARCH__)
@@ -114,7 +118,7 @@ BM2_HD FmIv fm_backward_ext(const FmIndexView &fm, const FmIv &in, int a) {
 }
 
 // SA of one BWT row: LF-walk to a sampled row (call_one_step; returns 0 on the sentinel, :1230-1233)
-BM2_HD int64_t fm_sa_of_row(const FmIndexView &fm, int64_t r, int *lf_steps) {
+BM2_HD int64_t fm_sa_of_row(const FmIndexView &fm, int64_t r, int *lf_steps, int64_t at_sentinel = 0) {
     int64_t steps = 0;
     while (r & 7) {
         const bm2_cp_occ *e = fm.cp_occ + (r >> 6);
@@ -129,7 +133,7 @@ BM2_HD int64_t fm_sa_of_row(const FmIndexView &fm, int64_t r, int *lf_steps) {
         for (int b = 0; b < 4; ++b) { cnt[b] = (uint64_t) e->cp_count[b]; bits[b] = e->one_hot_bwt_str[b]; }
 #endif
         int b = ((bits[0] >> y) & 1) ? 0 : ((bits[1] >> y) & 1) ? 1 : ((bits[2] >> y) & 1) ? 2 : ((bits[3] >> y) & 1) ? 3 : 4;
-        if (b == 4) { if (lf_steps) *lf_steps += (int) steps; return 0; }
+        if (b == 4) { if (lf_steps) *lf_steps += (int) steps; return at_sentinel; }
         const int yy = (int) (r & 63);
         const uint64_t mask = yy ? ~0ULL << (64 - yy) : 0ULL;
         uint64_t cb = b == 0 ? cnt[0] : b == 1 ? cnt[1] : b == 2 ? cnt[2] : cnt[3];
@@ -145,6 +149,10 @@ BM2_HD int64_t fm_sa_of_row(const FmIndexView &fm, int64_t r, int *lf_steps) {
 #endif
     return sa + steps;
 }
+
+// Text position of BWT row r (the true suffix-array value), or -1 when the LF walk meets the sentinel (fm_sa_of_row mirrors the
+// reference's quirk there and returns 0, which is not a position)
+BM2_HD int64_t fm_text_pos_of_row(const FmIndexView &fm, int64_t r) { return fm_sa_of_row(fm, r, nullptr, -1); }
 
 // One entry of the per-read interval list of the SMEM search (prevArray, src/FMI_search.cpp:510).
 struct FmPrev { int64_t k, l, s; int32_t m, n; };
@@ -222,6 +230,12 @@ BM2_HD void fm_forward(const FmIndexView &fm, const Q &q, int len, int x0, int m
     int x = x0, j = 0, next_x = 0, top = cap;
     bool searching = false;
     FmPrev cur; cur.k = cur.l = cur.s = 0; cur.m = cur.n = 0;
+    // Unique-interval shortcut (fm.text != null): once the interval of read[x..j) has ONE row, the next extensions only ask whether the text
+    // goes on like the read: s' = [T[SA[k] + (j - x)] == read[j]], k unchanged (no suffix of the interval sorts before the match), so the
+    // search reads the reference text (one sector per 32 bases) instead of one random Occ sector per base.  The interval of the reverse
+    // complement (l) is not maintained in that mode: nothing after SMEM collection reads it (src/bwamem.cpp uses k, s, m, n), but the staged
+    // entry bm2_collect_smems, whose callers see l, runs without the shortcut.  tpos: text position of read[x], -1 unknown, -2 do not try.
+    int64_t tpos = -1;
     for (;;) {
         bool need = false;
         int base = 0;
@@ -232,7 +246,7 @@ BM2_HD void fm_forward(const FmIndexView &fm, const Q &q, int len, int x0, int m
                 const int a = q(x);
                 if (a > 3) { if (single) return; x = next_x; continue; }
                 cur.m = x; cur.n = x; cur.k = fm_count(fm, a); cur.l = fm_count(fm, 3 - a); cur.s = fm_count(fm, a + 1) - cur.k;
-                top = cap; j = x + 1; searching = true;
+                top = cap; j = x + 1; searching = true; tpos = -1;
             }
             bool stop = j >= len;
             if (!stop) { next_x = j + 1; const int a = q(j); if (a > 3) stop = true; else { base = 3 - a; need = true; } }
@@ -244,8 +258,17 @@ BM2_HD void fm_forward(const FmIndexView &fm, const Q &q, int len, int x0, int m
             }
         }
         BM2_SYNCWARP();
-        FmIv req; req.k = cur.l; req.l = cur.k; req.s = cur.s;
-        const FmIv r = fm_backward_ext(fm, req, base);
+        FmIv r;
+        if (fm.text && cur.s == 1 && tpos == -1) tpos = len - j >= 16 ? fm_text_pos_of_row(fm, cur.k) : -2;      // (-1 from the walk = sentinel met: try no more)
+        if (fm.text && cur.s == 1 && tpos >= 0) {
+            const int64_t tp = tpos + (j - x);
+            r.s = (tp < fm.text_len && (int) fm.text[tp] == 3 - base) ? 1 : 0;
+            r.l = cur.k; r.k = cur.l;
+        } else {
+            if (tpos == -1 && fm.text && cur.s == 1) tpos = -2;
+            FmIv req; req.k = cur.l; req.l = cur.k; req.s = cur.s;
+            r = fm_backward_ext(fm, req, base);
+        }
         ++n_ext;
         if (r.s != cur.s) scratch[--top] = cur;
         if (r.s < min_intv) {

@@ -761,6 +761,9 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     }
     bs.max_len = max_len;
     Params pv = make_params(ctx);
+    // unique-interval shortcut of the forward SMEM passes (fm_device.cuh): on for the whole-path entries; the staged bm2_collect_smems entry,
+    // whose callers see the SMEMs' l values, runs the plain search (BM2_SMEM_TEXT=0 turns it off everywhere: A/B measurements)
+    if (upto != UPTO_SMEM && env_int("BM2_SMEM_TEXT", 1, 0, 1)) { pv.fm.text = ctx->idx.ref; pv.fm.text_len = 2 * ctx->idx.l_pac; }
     Stages sg = { ctx, ctx->events, ctx->stage_names };
     if (sg.mark("h2d")) return 1;
 

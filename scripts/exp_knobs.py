@@ -8,15 +8,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package
 
-KNOBS = ("BM2_LANE_SKEW", "BM2_STAGE_TOKENS", "BM2_BSW_REGSHRINK", "BM2_CHAIN_COOP_MIN", "BM2_BSW_NTHR", "BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
+KNOBS = ("BM2_SMEM_TEXT", "BM2_LANE_SKEW", "BM2_STAGE_TOKENS", "BM2_BSW_REGSHRINK", "BM2_CHAIN_COOP_MIN", "BM2_BSW_NTHR", "BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
 CONFIGS = [
+    dict(name="default (text shortcut on), sub 1", sub=1),
+    dict(name="text shortcut off, sub 1", sub=1, BM2_SMEM_TEXT="0"),
     dict(name="default, sub 4", sub=4),
-    dict(name="sub 4, lane skew 50", sub=4, BM2_LANE_SKEW="50"),
-    dict(name="sub 4, lane skew 100", sub=4, BM2_LANE_SKEW="100"),
-    dict(name="sub 4, lane skew 200", sub=4, BM2_LANE_SKEW="200"),
-    dict(name="sub 3, lane skew 100", sub=3, BM2_LANE_SKEW="100"),
-    dict(name="sub 6, lane skew 60", sub=6, BM2_LANE_SKEW="60"),
-    dict(name="sub 8, lane skew 40", sub=8, BM2_LANE_SKEW="40"),
+    dict(name="text shortcut off, sub 4", sub=4, BM2_SMEM_TEXT="0"),
+    dict(name="default, sub 1 (again)", sub=1),
     dict(name="default, sub 4 (again)", sub=4),
 ]
 
@@ -62,7 +60,7 @@ def main():
     # parity of one knob setting against another on a slice (regs must be byte-identical whatever the knobs)
     ns = 65536
     outs = []
-    for env in (dict(BM2_BSW_COL2="0", BM2_STAGE_TOKENS="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5"), dict(BM2_BSW_REGSHRINK="0", BM2_CHAIN_COOP_MIN="64")):
+    for env in (dict(BM2_BSW_COL2="0", BM2_STAGE_TOKENS="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5"), dict(BM2_BSW_REGSHRINK="1", BM2_CHAIN_COOP_MIN="64"), dict(BM2_SMEM_TEXT="0")):
         for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update(env)

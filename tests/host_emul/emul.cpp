@@ -20,6 +20,9 @@ static long long g_gs_calls = 0, g_gs_cells = 0;      // statistics of the score
 #include "ext_device.cuh"
 #include "../../oracle/bm2_oracle.h"
 
+static int g_smem_text = 0;      // emul_set_smem_text: the unique-interval shortcut of fm_forward (fm.text) in the host runs
+extern "C" void emul_set_smem_text(int on) { g_smem_text = on; }
+
 namespace {
 struct Views { FmIndexView fm; ContigView cv; SmemParams sp; ChainParams cp; ExtParams ep; SwParams sw; const bm2_index_desc *idx; const bm2_mem_opt_t *opt; };
 
@@ -36,6 +39,7 @@ Views make_views(const bm2_index_desc *idx, const bm2_mem_opt_t *o) {
     v.ep.pen_clip5 = o->pen_clip5; v.ep.pen_clip3 = o->pen_clip3; v.ep.max_chain_gap = o->max_chain_gap; v.ep.mask_level_redun = o->mask_level_redun;
     memcpy(v.ep.mat, o->mat, 25);
     v.sw.a = o->a; v.sw.o_del = o->o_del; v.sw.e_del = o->e_del; v.sw.o_ins = o->o_ins; v.sw.e_ins = o->e_ins; memcpy(v.sw.mat, o->mat, 25);
+    if (g_smem_text || getenv("BM2_EMUL_SMEM_TEXT")) { v.fm.text = idx->ref_string; v.fm.text_len = 2 * idx->l_pac; }      // (the env form: a whole test run with the shortcut on)
     v.idx = idx; v.opt = o;
     return v;
 }

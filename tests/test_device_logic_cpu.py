@@ -63,3 +63,28 @@ def test_ragged_and_degenerate_reads(pkg, golden_dir):
         assert np.array_equal(regs[f], want[f]), f
     assert ro[1] == 0 and ro[2] == 0 and ro[3] == 0     # nothing for empty / too short / all-N reads
     idx.close()
+
+
+def test_unique_interval_text_shortcut_changes_only_l(pkg, golden_dir):
+    """fm_forward with the reference text (the whole-path entries' setting): a one-row interval is extended by comparing the text with the read
+    instead of by Occ lookups.  Every SMEM must keep rid, m, n, k, s (l is not maintained in that mode and not read by anything downstream), the
+    search must make the same number of extensions, and the alignment regions of the whole path must stay the oracle's."""
+    import emul_lib as el, oracle_lib as ol
+    capi = pkg.capi
+    idx = capi.Index(golden_dir + "/c0_index/ref.fa"); opt = capi.default_opt()
+    reads = np.load(golden_dir + "/c0_reads.npz")["reads"]
+    codes = reads.reshape(-1); offs = (np.arange(len(reads) + 1) * reads.shape[1]).astype(np.int64)
+    base = el.collect_smems(idx, opt, codes, offs)
+    el.lib().emul_set_smem_text(1)
+    try:
+        fast = el.collect_smems(idx, opt, codes, offs)
+        regs, ro = el.seed_chain_extend(idx, opt, codes, offs)
+    finally:
+        el.lib().emul_set_smem_text(0)
+    sm0, n0 = base[0], base[-1]; sm1, n1 = fast[0], fast[-1]
+    assert len(sm0) == len(sm1) and n0 == n1
+    for f in ("rid", "m", "n", "k", "s"):
+        assert np.array_equal(sm0[f], sm1[f]), f
+    assert (sm0["l"] != sm1["l"]).sum() > 100                      # the shortcut really ran
+    want, wo, _, rc = ol.seed_chain_extend(idx, opt, codes, offs)
+    assert rc == 0 and np.array_equal(ro, wo) and regs.tobytes() == want.tobytes()
