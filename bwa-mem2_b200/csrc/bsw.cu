@@ -368,7 +368,7 @@ template <int NTHR>
 __global__ void __launch_bounds__(NTHR)
 bsw_col2_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ perm, const int32_t *__restrict__ class_off,
                 int cls, BswOut *__restrict__ out, const uint8_t *__restrict__ tbase, const uint8_t *__restrict__ qbase,
-                BswParams p, int NP, unsigned long long *cells, int reg_shrink)
+                BswParams p, int NP, unsigned long long *cells, int reg_shrink, int *next_job)
 {
     extern __shared__ uint32_t sh[];
     const int first = class_off[cls], last = class_off[cls + 1];
@@ -377,8 +377,22 @@ bsw_col2_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ per
     mem.q_base = (unsigned) __cvta_generic_to_shared(sh) + (unsigned) NP * NTHR * 4u + threadIdx.x * 2u;
     const bool same_oe = p.o_del + p.e_del == p.o_ins + p.e_ins;
     unsigned long long ncell = 0;
-    for (int blk = blockIdx.x; first + blk * NTHR < last; blk += gridDim.x) {      // persistent CTAs: long jobs first
-        const int g = first + blk * NTHR + threadIdx.x;
+    // Persistent warps, long jobs first.  next_job != nullptr: every WARP takes the next 32 jobs of the sorted class from a counter when it
+    // is done with its own (the warps of a CTA never synchronise), so that the launch ends within one short job of the last fetch instead of
+    // with the CTAs that the static round-robin happened to give the longer blocks (ncu r2c: 22.4 % of the warp slots active against 25 %
+    // resident = a tenth of every launch was its tail).  nullptr: the static order (BM2_BSW_DYN=0, A/B measurements).
+    const int lane = threadIdx.x & 31;
+    for (int blk = blockIdx.x; ; blk += gridDim.x) {
+        int g;
+        if (next_job) {
+            int b = 0;
+            if (lane == 0) b = atomicAdd(next_job, 32);
+            g = first + __shfl_sync(0xffffffffu, b, 0) + lane;
+            if (g - lane >= last) break;
+        } else {
+            if (first + blk * NTHR >= last) break;
+            g = first + blk * NTHR + threadIdx.x;
+        }
         if (g < last) {
             const int id = perm[g];
             const BswJob job = jobs[id];
@@ -762,6 +776,8 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
             // band shrink decided from the two words just written instead of scanning shared memory: measured 2 % SLOWER (49.6 against 48.5 ms,
             // profiles/r2g_exp_knobs.log: the extra branches cost more than the one or two loads they save) - off unless BM2_BSW_REGSHRINK=1
             const int reg_shrink = (rs_env && rs_env[0] == '1') ? 1 : 0;
+            const char *dyn_env = getenv("BM2_BSW_DYN");
+            const int dyn = (dyn_env && dyn_env[0] == '0') ? 0 : 1;           // per-warp job counters: class_cnt[24 + c], zeroed with class_cnt above
             int nthr2 = 128, best_res = 0, best_cps = 1;
             int t_lo = 128, t_hi = 128;           // measured (profiles/r2e_exp_knobs.log): 128-thread CTAs 50.1 ms, 96: 53.5, 64: 51.2, most-resident-threads choice 52.3
             if (const char *e = getenv("BM2_BSW_NTHR")) { const int v = atoi(e); if (v == 64 || v == 96 || v == 128) t_lo = t_hi = v; }      // A/B measurements
@@ -772,7 +788,7 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
             }
             const size_t smem2 = (size_t) NP * 6 * nthr2;
             int nb = (n + nthr2 - 1) / nthr2; if (nb > n_sm * best_cps) nb = n_sm * best_cps;
-#define BM2_COL2_LAUNCH(T) bsw_col2_kernel<T><<<nb, T, smem2, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, NP, d_cells, reg_shrink)
+#define BM2_COL2_LAUNCH(T) bsw_col2_kernel<T><<<nb, T, smem2, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, NP, d_cells, reg_shrink, dyn ? class_cnt + 24 + c : nullptr)
             if (nthr2 == 128) BM2_COL2_LAUNCH(128); else if (nthr2 == 96) BM2_COL2_LAUNCH(96); else BM2_COL2_LAUNCH(64);
 #undef BM2_COL2_LAUNCH
             continue;

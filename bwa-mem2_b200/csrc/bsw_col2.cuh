@@ -12,7 +12,7 @@
 // the one-cell-per-instruction kernel.  Odd band edges are single cells (at most two per row).
 //
 // Per pair of cells: 1 LDS + 1 STS of the state {H_lo, E_lo, H_hi, E_hi} (4 x 8 bit), 1 LDS of the two selector bytes, one PRMT
-// for both substitution scores (the per-column selector byte is precomputed from the query), 10 ALU-pipe + 8 FMA-pipe instructions
+// for both substitution scores (the per-column selector byte is precomputed from the query), 10 ALU-pipe + 7 FMA-pipe instructions
 // (unpacking H, the row-maximum key and all packing are multiply-adds on the FMA pipe).
 //
 // Written as BM2_HD so that tests/host_emul/bsw_col2_emul.cpp runs the very same code on the CPU against the oracle.
@@ -55,7 +55,7 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
     const uint32_t n_oe_del = ((uint32_t) (-oe_del) & 0xFFFFu) * 0x10001u, n_e_del = ((uint32_t) (-e_del) & 0xFFFFu) * 0x10001u;
     const uint32_t n_oe_ins = ((uint32_t) (-oe_ins) & 0xFFFFu) * 0x10001u, n_e_ins = ((uint32_t) (-e_ins) & 0xFFFFu) * 0x10001u;
     const uint32_t n_e_ins_hi = n_e_ins & 0xFFFF0000u;                                       // {0, -e_ins}
-    const uint32_t one = qlen >= 0 ? 1u : 0u;          // 1, opaque to the compiler: x * one + y stays a multiply-add (FMA pipe)
+    const uint32_t k256 = qlen >= 0 ? 256u : 0u;       // 256, opaque to the compiler: h * k256 + c stays a multiply-add (FMA pipe), not an LEA (ALU pipe)
     // first row (bandedSWA.cpp:141-144): columns 0..qlen, E = 0
     {
         int h = h0;
@@ -90,14 +90,16 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
         const int tb = tb_next;
         if (i + 1 < tlen) tb_next = (int) tptr[(long long) (i + 1) * tstride];
         const uint32_t tbl = p2_score_table(tb, p.a, p.b);
-        uint32_t key2 = 0;
+        // Row maximum with its column, per half: key = H << 8 | c, c = 0xFF at the pair that set it and one less for every pair after it (ONE
+        // packed add-max per pair: the running key minus one against the pair's {H << 8 | 0xFF}; an equal H further right wins, as in the
+        // reference's row scan).  The column is pe - (0xFF - c) afterwards.  c never wraps: a row has at most 129 pairs.
+        uint32_t key2 = 0x00FF00FFu;
         uint32_t fw = 0, lw = 0;            // the state words just written for the first / last pair of the row (band shrink below)
         if (end > beg) {
             const int pb = beg >> 1, pe = (end - 1) >> 1;
             const uint32_t in_first = (beg & 1) ? 0xFFFF0000u : 0xFFFFFFFFu, in_last = (end & 1) ? 0x0000FFFFu : 0xFFFFFFFFu;
             uint32_t U = 0;                                            // {F(2q), F(2q)}
             uint32_t hp = (uint32_t) h1 << 16;                         // packed h of the pair to the left: its high half is H(i, 2q - 1)
-            uint32_t jj2 = (uint32_t) (2 * pb) * 0x10001u + 0x10000u;  // {2q, 2q + 1}
             // the DP of one pair on the (masked) state word wv; returns the new state word
             auto pair = [&](const uint32_t wv, const uint32_t sel, const uint32_t keymask) -> uint32_t {
                 const uint32_t e = p2_prmt(wv, 0u, 0x4341u);
@@ -113,8 +115,7 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
                 const uint32_t h = p2_max3(M, e, f2);
                 const uint32_t hs = p2_mad(h, 65536u, c2_shr16(hp));                     // {H(i, 2q-1), H(i, 2q)}
                 hp = h;
-                key2 = p2_maxu(key2, p2_mad(h, 256u, jj2) & keymask);
-                jj2 = p2_mad(one, 0x00020002u, jj2);
+                key2 = p2_addmaxu(key2, 0xFFFFFFFFu, p2_mad(h, k256, 0x00FF00FFu) & keymask);   // {H << 8 | 0xFF - pairs since}: see below
                 return p2_mad(en, 256u, hs);
             };
             // The state word and the selectors of a pair are loaded one pair AHEAD of their use (the accesses are volatile asm, so the
@@ -141,9 +142,15 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
             h1 = (int) ((end & 1) ? (hp & 0xFFFFu) : (hp >> 16));      // H(i, end - 1)
             ncell += (unsigned) (end - beg);
         }
-        const int ka = (int) (key2 & 0xFFFFu), kb = (int) (key2 >> 16);
-        const int key1 = ka > kb ? ka : kb;
-        const int m = key1 >> 8, mj = key1 & 0xFF;
+        int m = 0, mj = 0;
+        if (end > beg) {
+            const int pe = (end - 1) >> 1;
+            const int ka = (int) (key2 & 0xFFFFu), kb = (int) (key2 >> 16);
+            const int ja = 2 * (pe - (0xFF - (ka & 0xFF))), jb = 2 * (pe - (0xFF - (kb & 0xFF))) + 1;
+            const int ha = ka >> 8, hb = kb >> 8;
+            const bool hi = hb > ha || (hb == ha && jb > ja);
+            m = hi ? hb : ha; mj = hi ? jb : ja;
+        }
 #ifdef BM2_COL2_TRACE
         BM2_COL2_TRACE(beg, end);                              // lane-utilisation studies (tests/host_emul/bsw_col2_emul.cpp)
 #endif

@@ -19,6 +19,7 @@ BM2_D uint32_t p2_addmin_relu(uint32_t a, uint32_t b, uint32_t c) { return __via
 BM2_D uint32_t p2_addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); }   // max(a + b, c, 0)
 BM2_D uint32_t p2_max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 BM2_D uint32_t p2_maxu(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+BM2_D uint32_t p2_addmaxu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_u16x2(a, b, c); }               // max(a + b mod 2^16, c), unsigned halves
 BM2_D uint32_t p2_add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 // a * b + c as ONE multiply-add on the FMA pipe (the compiler would turn constant multiplies into ALU-pipe shift/mask pairs)
 BM2_D uint32_t p2_mad(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
@@ -54,6 +55,10 @@ inline uint32_t p2_max3(uint32_t a, uint32_t b, uint32_t c) {
 inline uint32_t p2_maxu(uint32_t a, uint32_t b) {
     const uint32_t lo = (a & 0xFFFF) > (b & 0xFFFF) ? (a & 0xFFFF) : (b & 0xFFFF), hi = (a >> 16) > (b >> 16) ? (a >> 16) : (b >> 16);
     return lo | (hi << 16);
+}
+inline uint32_t p2_addmaxu(uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t lo = (a + b) & 0xFFFFu, hi = ((a >> 16) + (b >> 16)) & 0xFFFFu, cl = c & 0xFFFFu, ch = c >> 16;
+    return (lo > cl ? lo : cl) | ((hi > ch ? hi : ch) << 16);
 }
 inline uint32_t p2_add(uint32_t a, uint32_t b) { return ((a + b) & 0xFFFF) | ((((a >> 16) + (b >> 16)) & 0xFFFF) << 16); }
 #endif

@@ -153,6 +153,19 @@ bm2_ctx *bm2_make_lane(bm2_ctx *parent) {
     return c;
 }
 
+extern "C" int bm2_create_sibling(bm2_ctx **out, bm2_ctx *ctx) {
+    if (!out || !ctx) { bm2_set_error(ctx, "bm2_create_sibling: NULL argument"); return 1; }
+    *out = nullptr;
+    if (ctx->parent) { bm2_set_error(ctx, "bm2_create_sibling: not on a sub-batch lane"); return 1; }
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { bm2_set_error(ctx, "bm2_create_sibling: cudaSetDevice failed"); return 1; }
+    bm2_ctx *c = bm2_make_lane(ctx);           // own streams, events and buffers; the index by reference (idx_allocs empty: never freed here)
+    if (!c) return 1;
+    c->parent = nullptr;                       // a full context of its own: its own sub-batch lanes, its own error text
+    c->n_lanes = ctx->n_lanes; c->lane_min_reads = ctx->lane_min_reads; c->sam_staged = ctx->sam_staged;
+    *out = c;
+    return 0;
+}
+
 extern "C" int bm2_set_sub_batches(bm2_ctx *ctx, int k, int min_reads) {
     if (!ctx || k < 1 || k > 16 || min_reads < 512) { if (ctx) bm2_set_error(ctx, "bm2_set_sub_batches: k in 1..16, min_reads >= 512"); return 1; }
     ctx->n_lanes = k; ctx->lane_min_reads = min_reads;

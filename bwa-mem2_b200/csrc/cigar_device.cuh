@@ -38,6 +38,12 @@ BM2_HD void cigar_push_d(uint32_t *cigar, int &n, int op, int len) {
 // fixed slot 2W).  Same arithmetic and the same backtrack bytes at the same indices as the loop over memory rows below, which it replaces when
 // the band fits: no loads on the dependent path at all (the memory version spent 91 cycles per issued instruction waiting for its rows).
 // Requires w <= W and qlen <= tlen + w (then the last row reaches column qlen and H[qlen] is its h1).
+// MEASURED SLOWER inside sam_kernel and cigar_kernel (profiles/r2j_*: 168 registers per thread, 2 x 34 slots of unrolled code per row; the SAM
+// stage's per-pair kernel 29.9 -> 43.7 ms, bm2_gen_cigar 4.13 -> 3.28 M alignments/s against the memory rows with hoisted loads below), so it is
+// compiled out unless BM2_CIGAR_REG_BAND=1 is defined (it passed the CIGAR / SAM parity tests on the GPU: profiles/r2j_tests.log).
+#ifndef BM2_CIGAR_REG_BAND
+#define BM2_CIGAR_REG_BAND 0
+#endif
 template <int W>
 BM2_HD int global_forward_reg_d(int qlen, const uint8_t *qp, int qstride, int tlen, const uint8_t *tp, int tstride, const int8_t *mat,
                                 int o_del, int e_del, int o_ins, int e_ins, int w, const CigarZ &z)
@@ -128,7 +134,7 @@ BM2_HD int global_align_d(int qlen, const uint8_t *qp, int qstride, int tlen, co
     const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
     const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
     int score_reg = 0;
-    const bool in_regs = w <= 16 && tlen > 0 && qlen <= tlen + w;
+    const bool in_regs = BM2_CIGAR_REG_BAND && w <= 16 && tlen > 0 && qlen <= tlen + w;
     if (in_regs) score_reg = global_forward_reg_d<16>(qlen, qp, qstride, tlen, tp, tstride, mat, o_del, e_del, o_ins, e_ins, w, z);
     int32_t *H = he, *E = he + (qlen + 1);
     int j;

@@ -96,6 +96,10 @@ int  bm2_create(bm2_ctx **out, int device, const bm2_index_desc *idx, const bm2_
  * `ann_*` arrays HOST pointers.  The context does not own the four arrays: the caller keeps them alive until bm2_destroy and must not
  * read `cp_occ` afterwards - it is permuted in place into the device layout (fm_device.cuh) unless BM2_OCC_LAYOUT=0. */
 int  bm2_create_resident(bm2_ctx **out, int device, const bm2_index_desc *dev_idx, const bm2_mem_opt_t *opt);
+/* A second context on the same device that uses `ctx`'s index in place (no second copy in HBM), with its own streams and buffers and a copy of
+ * `ctx`'s parameters: one context per host worker thread, the way the reference runs two chunks at a time in kt_pipeline (src/fastmap.cpp:
+ * 952-1003, src/kthread.cpp:122-176) - a context serves one call at a time, two contexts serve two.  `ctx` must outlive the sibling. */
+int  bm2_create_sibling(bm2_ctx **out, bm2_ctx *ctx);
 void bm2_destroy(bm2_ctx *ctx);
 const char *bm2_last_error(const bm2_ctx *ctx);   /* ctx may be NULL: last create error */
 /* Launch on a caller-owned CUDA stream (cudaStream_t as void*), e.g. the caller's framework stream,

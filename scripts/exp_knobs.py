@@ -8,13 +8,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package
 
-KNOBS = ("BM2_SMEM_TEXT", "BM2_LANE_SKEW", "BM2_STAGE_TOKENS", "BM2_BSW_REGSHRINK", "BM2_CHAIN_COOP_MIN", "BM2_BSW_NTHR", "BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
+KNOBS = ("BM2_BSW_DYN", "BM2_SMEM_TEXT", "BM2_LANE_SKEW", "BM2_STAGE_TOKENS", "BM2_BSW_REGSHRINK", "BM2_CHAIN_COOP_MIN", "BM2_BSW_NTHR", "BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
 CONFIGS = [
-    dict(name="default (text shortcut on), sub 1", sub=1),
+    dict(name="default, sub 1", sub=1),
     dict(name="text shortcut off, sub 1", sub=1, BM2_SMEM_TEXT="0"),
+    dict(name="static BSW job order, sub 1", sub=1, BM2_BSW_DYN="0"),
+    dict(name="chain coop from 64 slots, sub 1", sub=1, BM2_CHAIN_COOP_MIN="64"),
+    dict(name="chain coop from 256 slots, sub 1", sub=1, BM2_CHAIN_COOP_MIN="256"),
+    dict(name="default, sub 1 (again)", sub=1),
     dict(name="default, sub 4", sub=4),
     dict(name="text shortcut off, sub 4", sub=4, BM2_SMEM_TEXT="0"),
-    dict(name="default, sub 1 (again)", sub=1),
+    dict(name="static BSW job order, sub 4", sub=4, BM2_BSW_DYN="0"),
+    dict(name="chain coop from 64 slots, sub 4", sub=4, BM2_CHAIN_COOP_MIN="64"),
     dict(name="default, sub 4 (again)", sub=4),
 ]
 
@@ -60,7 +65,7 @@ def main():
     # parity of one knob setting against another on a slice (regs must be byte-identical whatever the knobs)
     ns = 65536
     outs = []
-    for env in (dict(BM2_BSW_COL2="0", BM2_STAGE_TOKENS="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5"), dict(BM2_BSW_REGSHRINK="1", BM2_CHAIN_COOP_MIN="64"), dict(BM2_SMEM_TEXT="0")):
+    for env in (dict(BM2_BSW_COL2="0", BM2_STAGE_TOKENS="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5"), dict(BM2_BSW_REGSHRINK="1", BM2_CHAIN_COOP_MIN="64"), dict(BM2_SMEM_TEXT="0", BM2_BSW_DYN="0")):
         for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update(env)

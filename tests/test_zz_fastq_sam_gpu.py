@@ -82,10 +82,11 @@ def test_fastq_bytes_to_sam_text_equals_the_reference(pkg, golden_dir, staged):
     ctx.close(); idx.close()
 
 
-@pytest.mark.parametrize("K", [100_000_000, 40_000])
-def test_bm2_mem_program_prints_the_reference_sam(pkg, golden_dir, tmp_path, K):
+@pytest.mark.parametrize("K,workers", [(100_000_000, 2), (40_000, 1), (40_000, 2), (15_000, 3)])
+def test_bm2_mem_program_prints_the_reference_sam(pkg, golden_dir, tmp_path, K, workers):
     """The C++ host program over the C ABI (bwa-mem2_b200/tools/bm2_mem.cpp): FASTQ files in, SAM file out, chunked by -K like the reference's
-    reader; against the unmodified reference run live with the same -K (several chunks: mem_pestat per chunk, id offsets across chunks)."""
+    reader; against the unmodified reference run live with the same -K (several chunks: mem_pestat per chunk, id offsets across chunks).
+    -p workers: chunks in flight at a time, each on its own context (bm2_create_sibling), output in chunk order."""
     import os, subprocess, importlib
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     tool = os.path.join(root, "bwa-mem2_b200", "bm2_mem")
@@ -99,7 +100,7 @@ def test_bm2_mem_program_prints_the_reference_sam(pkg, golden_dir, tmp_path, K):
     synth.write_fastq(r1, reads[0::2], "p"); synth.write_fastq(r2, reads[1::2], "p")
     prefix = golden_dir + "/c0_index/ref.fa"
     out = str(tmp_path / "out.sam")
-    o = subprocess.run([tool, "-t", "4", "-K", str(K), "-o", out, prefix, r1, r2], capture_output=True, text=True, timeout=600)
+    o = subprocess.run([tool, "-t", "4", "-K", str(K), "-p", str(workers), "-o", out, prefix, r1, r2], capture_output=True, text=True, timeout=600)
     assert o.returncode == 0, o.stderr[-2000:]
     ref = subprocess.run([drv, "mem", "-t", "4", "-K", str(K), prefix, r1, r2], env=dict(os.environ, BM2_MODE="ref"), capture_output=True, text=True, timeout=600)
     assert ref.returncode == 0
@@ -110,4 +111,6 @@ def test_bm2_mem_program_prints_the_reference_sam(pkg, golden_dir, tmp_path, K):
     assert diff == [], (len(diff), got[diff[0]], want[diff[0]])
     import json
     st = json.loads(o.stderr.strip().splitlines()[-1])
-    assert st["reads"] == len(reads) and st["chunks"] == (1 if K > 1_000_000 else 4)
+    assert st["reads"] == len(reads) and st["workers"] == workers and st["chunks"] == (1 if K > 1_000_000 else 4 if K == 40_000 else st["chunks"])
+    assert K != 15_000 or st["chunks"] > 8
+    assert st["chunk_done_s"] == sorted(st["chunk_done_s"]) and sum(st["chunk_reads"]) == len(reads)
