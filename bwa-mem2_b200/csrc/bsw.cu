@@ -21,14 +21,17 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #define BSW_THREADS 128
-#define BSW_NBOUND 8
-#define BSW_NCLASS 16          // class = 2 * bound index + (needs 16-bit state); class 16 = wide (warp / global-state kernels)
-#define BSW_NPAIR 5            // pair classes 17..21: two jobs per thread in packed 16-bit halves (bsw_pair.cuh), bounds 32..160
+#define BSW_NBOUND 12
+#define BSW_NCLASS 24          // class = 2 * bound index + (needs 16-bit state); class 24 = wide (warp / global-state kernels)
+#define BSW_NPAIR 5            // pair classes 25..29: two jobs per thread in packed 16-bit halves (bsw_pair.cuh), bounds 32..96
 #define BSW_PAIR0 (BSW_NCLASS + 1)
 #define BSW_NALL (BSW_PAIR0 + BSW_NPAIR)
-// upper query-length bound of each class (state words = bound + 2)
-__constant__ int c_class_bound[BSW_NBOUND] = {32, 64, 96, 128, 160, 256, 512, 1024};
-static const int h_class_bound[BSW_NBOUND] = {32, 64, 96, 128, 160, 256, 512, 1024};
+// Upper query-length bound of each class (state words = bound + 2).  The shared memory of a launch is sized by its bound and decides how many
+// CTAs (4 warps each) an SM holds - the column-pair kernel needs 6 B per column pair and thread - so every bound up to 256 is the LARGEST query
+// length that still fits k CTAs of 128 threads into 227 KB: k = 16, 11, 8, 7, 6, 5, 4, 3, 2.  (Round 2: with the bounds 32, 64, ... 160 the right
+// extensions of 129..132 columns of a 151 bp read ran in the 160-column class at 3 CTAs per SM and took as long as the whole 128-column class.)
+__constant__ int c_class_bound[BSW_NBOUND] = {32, 48, 70, 80, 96, 116, 146, 196, 256, 384, 512, 1024};
+static const int h_class_bound[BSW_NBOUND] = {32, 48, 70, 80, 96, 116, 146, 196, 256, 384, 512, 1024};
 
 struct BswSortScratch {
     uint32_t *keys_in, *keys_out;
@@ -75,7 +78,7 @@ __global__ void bsw_keys_kernel(const BswJob *jobs, int n, int a, int pair_ok, c
         const int q = j.qlen > 0x3FF ? 0x3FF : j.qlen;
         const int h = j.h0 < 0 ? 0 : (j.h0 > 0x3FF ? 0x3FF : j.h0);
         const int t = (j.tlen >> 3) > 0x7F ? 0x7F : (j.tlen >> 3);
-        keys[i] = ((uint32_t) c << 27) | ((uint32_t) (0x3FF - q) << 17) | ((uint32_t) (0x3FF - h) << 7) | (uint32_t) (0x7F - t);   // c <= 21: 5 bits
+        keys[i] = ((uint32_t) c << 27) | ((uint32_t) (0x3FF - q) << 17) | ((uint32_t) (0x3FF - h) << 7) | (uint32_t) (0x7F - t);   // c <= 29: 5 bits
         idx[i] = i;
         atomicAdd(&hist[c], 1);
     }
@@ -686,7 +689,7 @@ size_t bsw_scratch_bytes(int n) {
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint32_t *) nullptr, (uint32_t *) nullptr, (int32_t *) nullptr,
                                     (int32_t *) nullptr, n > 0 ? n : 1);
     size_t per = ((size_t) (n > 0 ? n : 1) * 4 + 255) / 256 * 256;
-    return 4 * per + 256 * 2 + ((cub_bytes + 255) / 256 * 256) + 256;
+    return 4 * per + 512 + 256 + ((cub_bytes + 255) / 256 * 256) + 256;
 }
 
 struct BswWideScratch { int2 *state; long long *state_off; long long *total; size_t cap_words; size_t cap_jobs; };
@@ -705,13 +708,13 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
     uint32_t *keys_out = (uint32_t *) s; s += per;
     int32_t *idx_in = (int32_t *) s; s += per;
     int32_t *idx_out = (int32_t *) s; s += per;
-    int32_t *class_cnt = (int32_t *) s; s += 256;
+    int32_t *class_cnt = (int32_t *) s; s += 512;       // [0, BSW_NALL) job counts; 48: job queue of the warp kernel; 64 + c: job queue of class c
     int32_t *class_off = (int32_t *) s; s += 256;
     void *cub_tmp = s;
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys_in, keys_out, idx_in, idx_out, n);
 
-    BM2_CUDA_OK(cudaMemsetAsync(class_cnt, 0, 256, stream));
+    BM2_CUDA_OK(cudaMemsetAsync(class_cnt, 0, 512, stream));
     // Two-jobs-per-thread kernel (bsw_pair.cuh): bit-exact, but measured SLOWER than the thread-per-job kernel on B200
     // (115 vs 89 ms per 1 M reads: the lanes of a warp spend the pre/post column segments of their pairs apart,
     // profiles/r1k_bsw_pair_3gbp.md), so it is off unless BM2_BSW_PAIR=1 asks for it (experiments, tests).
@@ -777,7 +780,7 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
             // profiles/r2g_exp_knobs.log: the extra branches cost more than the one or two loads they save) - off unless BM2_BSW_REGSHRINK=1
             const int reg_shrink = (rs_env && rs_env[0] == '1') ? 1 : 0;
             const char *dyn_env = getenv("BM2_BSW_DYN");
-            const int dyn = (dyn_env && dyn_env[0] == '0') ? 0 : 1;           // per-warp job counters: class_cnt[24 + c], zeroed with class_cnt above
+            const int dyn = (dyn_env && dyn_env[0] == '0') ? 0 : 1;           // per-warp job counters: class_cnt[64 + c], zeroed with class_cnt above
             int nthr2 = 128, best_res = 0, best_cps = 1;
             int t_lo = 128, t_hi = 128;           // measured (profiles/r2e_exp_knobs.log): 128-thread CTAs 50.1 ms, 96: 53.5, 64: 51.2, most-resident-threads choice 52.3
             if (const char *e = getenv("BM2_BSW_NTHR")) { const int v = atoi(e); if (v == 64 || v == 96 || v == 128) t_lo = t_hi = v; }      // A/B measurements
@@ -788,7 +791,7 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
             }
             const size_t smem2 = (size_t) NP * 6 * nthr2;
             int nb = (n + nthr2 - 1) / nthr2; if (nb > n_sm * best_cps) nb = n_sm * best_cps;
-#define BM2_COL2_LAUNCH(T) bsw_col2_kernel<T><<<nb, T, smem2, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, NP, d_cells, reg_shrink, dyn ? class_cnt + 24 + c : nullptr)
+#define BM2_COL2_LAUNCH(T) bsw_col2_kernel<T><<<nb, T, smem2, stream>>>(d_jobs, idx_out, class_off, c, d_out, d_tbase, d_qbase, prm, NP, d_cells, reg_shrink, dyn ? class_cnt + 64 + c : nullptr)
             if (nthr2 == 128) BM2_COL2_LAUNCH(128); else if (nthr2 == 96) BM2_COL2_LAUNCH(96); else BM2_COL2_LAUNCH(64);
 #undef BM2_COL2_LAUNCH
             continue;
