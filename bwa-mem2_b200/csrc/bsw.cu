@@ -408,7 +408,8 @@ bsw_col2_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ per
                 asm volatile("st.shared.u16 [%0], %1;" :: "r"(mem.q_base + (unsigned) (k >> 1) * (NTHR * 2u)), "h"((uint16_t) wv) : "memory");
             }
             BswOut o;
-            if (same_oe && reg_shrink) bsw_col2_extend<true>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
+            if (same_oe && reg_shrink == 1) bsw_col2_extend<true>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
+            else if (same_oe && reg_shrink == 2) bsw_col2_extend<true, Col2MemShared<NTHR>, false, 8>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
             else if (same_oe) bsw_col2_extend<true, Col2MemShared<NTHR>, false>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
             else bsw_col2_extend<false>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
             out[id] = o;
@@ -778,7 +779,8 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
             const char *rs_env = getenv("BM2_BSW_REGSHRINK");
             // band shrink decided from the two words just written instead of scanning shared memory: measured 2 % SLOWER (49.6 against 48.5 ms,
             // profiles/r2g_exp_knobs.log: the extra branches cost more than the one or two loads they save) - off unless BM2_BSW_REGSHRINK=1
-            const int reg_shrink = (rs_env && rs_env[0] == '1') ? 1 : 0;
+            int reg_shrink = (rs_env && rs_env[0] == '1') ? 1 : 0;
+            if (const char *e = getenv("BM2_BSW_UNROLL8")) { if (e[0] == '1') reg_shrink = 2; }      // the pair loop unrolled x8 instead of x4 (A/B)
             const char *dyn_env = getenv("BM2_BSW_DYN");
             const int dyn = (dyn_env && dyn_env[0] == '0') ? 0 : 1;           // per-warp job counters: class_cnt[64 + c], zeroed with class_cnt above
             int nthr2 = 128, best_res = 0, best_cps = 1;

@@ -47,7 +47,7 @@ BM2_HD bool c2_params_ok(const BswParams &p) { return p2_params_ok(p); }
 // F crosses the halves with one multiply and one PRMT per pair: with U = {F(2q), F(2q)},
 //   f2 = max(U + {0, -e}, {0, t(2q)}, 0) = {F(2q), F(2q+1)},  fb = max(f2 + {-e, -e}, {t(2q), t(2q+1)}, 0) -> high half F(2q+2),
 // t = M - oe_ins (round 1: two multiplies up, a merge and a shift down per pair).
-template <bool SAME_OE, class Mem, bool REG_SHRINK = true>
+template <bool SAME_OE, class Mem, bool REG_SHRINK = true, int UNR = 4>
 BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, int qlen, int tlen, int h0, const BswParams &p,
                             BswOut &o, unsigned long long &cells)
 {
@@ -131,7 +131,10 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
                 mem.stw(pb, fw);
             }
             if (!only) {
-                for (int q = pb + 1; q < pe; ++q) {                       // (unrolled x4 by the compiler, remainder first)
+#if defined(__CUDA_ARCH__)
+#pragma unroll UNR
+#endif
+                for (int q = pb + 1; q < pe; ++q) {                       // (unrolled x UNR, remainder first)
                     const uint32_t wn = mem.ldw(q + 1), sn = mem.sel16(q + 1);
                     mem.stw(q, pair(wv, sl, 0xFFFFFFFFu));
                     wv = wn; sl = sn;

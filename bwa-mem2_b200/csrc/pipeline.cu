@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(128)
 chain_kernel(ContigView cv, ChainParams cp, const bm2_smem *__restrict__ sm, const int64_t *__restrict__ read_smem_off,
              const int64_t *__restrict__ slot_off, const int64_t *__restrict__ sa, const int64_t *__restrict__ offs, int n_reads,
              const int32_t *__restrict__ perm, ChainBufs b, SwParams sw, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ codes,
-             const int32_t *__restrict__ min_hsp, int mode, int heavy_thr, int coop_min)
+             const int32_t *__restrict__ min_hsp, int mode, int heavy_thr, int coop_min, int light_sorted)
 {
     // mode 0: light reads, one per thread; mode 1: heavy reads (many seed occurrences: O(n^2) chain insertion and
     // filtering), one per WARP, taken from the list sorted by decreasing work: lane 0 runs the sequential chaining, ALL lanes share the
@@ -368,7 +368,8 @@ chain_kernel(ContigView cv, ChainParams cp, const bm2_smem *__restrict__ sm, con
     const int lane = threadIdx.x & 31;
     const int stride = mode ? (gridDim.x * blockDim.x) >> 5 : gridDim.x * blockDim.x;
     for (int t = mode ? tid >> 5 : tid; t < n_reads; t += stride) {
-    const int r = mode ? perm[t] : t;
+    // (mode 0 with light_sorted: the light reads in work order too, so that the 32 reads of a warp have similar numbers of seed occurrences)
+    const int r = (mode || light_sorted) ? perm[t] : t;
     {
         const int64_t nslot = slot_off[read_smem_off[r + 1]] - slot_off[read_smem_off[r]];
         if (mode) { if (nslot <= heavy_thr) break; }                  // perm is sorted by decreasing work (warp-uniform)
@@ -565,23 +566,20 @@ __global__ void __launch_bounds__(128)
 tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs,
             const bm2_chain *__restrict__ chains, const bm2_seed *__restrict__ seeds, const int64_t *__restrict__ chain_off,
             const int64_t *__restrict__ reg_off, int n_reads, bm2_alnreg_t *regs, const int32_t *reg_seed, int32_t *srt2_all, int32_t *he_all,
-            int he_stride, const int32_t *__restrict__ perm, PfBox *box_all, int32_t *n_final, int mode, int heavy_thr, int cap)
+            int he_stride, const int32_t *__restrict__ perm, PfBox *box_all, int32_t *n_final, int mode, int heavy_thr, int light_sorted)
 {
     // Heavy reads (many regs: O(regs^2) post-filter, sorts, patch DP) would serialise with the 31 other reads of their
     // warp (ncu: 1.9 active lanes per instruction), so they get a WARP each (mode 1: reads in decreasing-work order; the
     // post-filter scan runs on all lanes, the rest on lane 0); light reads run one per thread (mode 0).
-    // Round 2: a heavy read of at most `cap` regs is worked on in SHARED memory - its records (112 B each), the sort keys and the index array
-    // of the two introsorts: the warp copies them in and out with coalesced 16-byte accesses, and lane 0's sequential passes (compactions,
-    // sorts, the in-place permutations, the dedup scan: one dependent global-memory round trip per record before, ncu r2i: 60 % of the heavy
-    // pass's samples at 1 active lane) run at shared-memory latency.  Reads with more regs than `cap` keep the global-memory path.
-    extern __shared__ uint4 tail_sh[];
+    // (Round 2 measured the heavy reads in SHARED memory - records, sort keys and index array copied in and out by the warp: no faster at the
+    // same number of resident warps, 8.2 against 8.3 ms, and slower with fewer, 11.1 ms at 2 CTAs per SM, profiles/r2l_exp_knobs.log: the
+    // records of one read stay in L1 between lane 0's passes, so the sequential part is bound by its instructions, not by memory latency.)
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     int32_t *he = he_all + (size_t) (mode ? tid >> 5 : tid) * he_stride;
     const int unit = mode ? tid >> 5 : tid, nunit = mode ? nthr >> 5 : nthr;
-    char *wbase = reinterpret_cast<char *>(tail_sh) + (size_t) (threadIdx.x >> 5) * ((size_t) cap * 132);
     for (int t = unit; t < n_reads; t += nunit) {
-        const int r = mode ? perm[t] : t;
+        const int r = (mode || light_sorted) ? perm[t] : t;      // (the light reads in work order too: similar reads share a warp)
         const int64_t c0 = chain_off[r], c1 = chain_off[r + 1], g0 = reg_off[r];
         const int n_reg = (int) (reg_off[r + 1] - g0);
         if (mode) { if (n_reg <= heavy_thr) break; }       // perm is sorted by decreasing n_reg
@@ -589,26 +587,7 @@ tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const 
         int m = 0;
         if (c1 > c0) {
             const int l_query = (int) (offs[r + 1] - offs[r]);
-            if (mode && n_reg <= cap) {
-                bm2_alnreg_t *sregs = reinterpret_cast<bm2_alnreg_t *>(wbase);
-                TailSortKey *skeys = reinterpret_cast<TailSortKey *>(wbase + (size_t) cap * 112);
-                int32_t *sidx = reinterpret_cast<int32_t *>(wbase + (size_t) cap * 128);
-                {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(regs + g0); uint4 *dst = reinterpret_cast<uint4 *>(sregs);
-                    for (int k = lane; k < n_reg * 7; k += 32) dst[k] = src[k];
-                }
-                __syncwarp();
-                ext_postfilter_read_warp(ep, chains + c0, (int) (c1 - c0), seeds, l_query, sregs, n_reg, reg_seed + g0, sidx, box_all + g0);
-                __syncwarp();
-                if (lane == 0) m = ext_tail_read_d(cv, ep, ref, codes + offs[r], sregs, n_reg, he, sidx, skeys);
-                m = __shfl_sync(0xffffffffu, m, 0);
-                __syncwarp();
-                {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(sregs); uint4 *dst = reinterpret_cast<uint4 *>(regs + g0);
-                    for (int k = lane; k < m * 7; k += 32) dst[k] = src[k];
-                }
-                __syncwarp();
-            } else if (mode) {
+            if (mode) {
                 ext_postfilter_read_warp(ep, chains + c0, (int) (c1 - c0), seeds, l_query, regs + g0, n_reg, reg_seed + g0, srt2_all + g0, box_all + g0);
                 __syncwarp();
                 if (lane == 0) m = ext_tail_read_d(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he, srt2_all + g0, reinterpret_cast<TailSortKey *>(box_all + g0));
@@ -954,16 +933,17 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     int32_t *wv_in = (int32_t *) ((char *) ctx->d[B_PERM].p + 2 * al((size_t) n * 4)), *d_perm = (int32_t *) ((char *) ctx->d[B_PERM].p + 3 * al((size_t) n * 4));
     work_keys_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(P<int64_t>(ctx, B_READ_SMEM_OFF), P<int64_t>(ctx, B_SLOT_OFF), n, wk_in, wv_in);
     if (sort_work(ctx, wk_in, wk_out, wv_in, d_perm, n, true)) return 1;             // decreasing number of seed slots
+    const int light_sorted = env_int("BM2_LIGHT_SORTED", 1, 0, 1);              // light reads of the chain and tail kernels in work order (0: input order, A/B)
     const int chain_heavy = env_int("BM2_CHAIN_HEAVY", 64, 1, 1 << 30);          // seed occurrences from which a read gets a warp
     const int chain_coop_min = env_int("BM2_CHAIN_COOP_MIN", 1024, 0, 1 << 30);      // seed occurrences from which a warp shares the chaining of a read
     chain_kernel<<<(n + 127) / 128, 128, 0, st>>>(pv.cv, pv.cp, P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_READ_SMEM_OFF),
                                                   P<int64_t>(ctx, B_SLOT_OFF), P<int64_t>(ctx, B_SA), d_offs, n, d_perm, cb, pv.sw, ctx->idx.ref, d_codes,
-                                                  any_flt ? P<int32_t>(ctx, B_MINHSP) : nullptr, 0, chain_heavy, chain_coop_min);
+                                                  any_flt ? P<int32_t>(ctx, B_MINHSP) : nullptr, 0, chain_heavy, chain_coop_min, light_sorted);
     {   // heavy reads: one warp each; the sorted list ends the grid early (warps whose read is light return at once)
         int heavy_warps = n < ctx->n_sm * 256 ? n : ctx->n_sm * 256;
         chain_kernel<<<(heavy_warps * 32 + 127) / 128, 128, 0, st>>>(pv.cv, pv.cp, P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_READ_SMEM_OFF),
                                                                       P<int64_t>(ctx, B_SLOT_OFF), P<int64_t>(ctx, B_SA), d_offs, n, d_perm, cb, pv.sw,
-                                                                      ctx->idx.ref, d_codes, any_flt ? P<int32_t>(ctx, B_MINHSP) : nullptr, 1, chain_heavy, chain_coop_min);
+                                                                      ctx->idx.ref, d_codes, any_flt ? P<int32_t>(ctx, B_MINHSP) : nullptr, 1, chain_heavy, chain_coop_min, 0);
     }
 
     // ---- E. scans + compaction ------------------------------------------------------------------------------
@@ -1061,29 +1041,12 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     const int he_stride = 2 * (max_len + 2);
     if (ctx->ensure(ctx->d[B_NW], (size_t) blocks_i * 128 * he_stride * 4)) return 1;
     const int heavy_thr = env_int("BM2_TAIL_HEAVY", 24, 1, 1 << 20);            // regs from which a read gets a warp
-    // regs of a heavy read that are worked on in shared memory (132 B each: record, sort key, index); 0 = the global-memory path (A/B)
-    const int tail_cap = env_int("BM2_TAIL_SMEM_REGS", 192, 0, 400) & ~3;      // (multiple of 4: the per-warp areas stay 16-byte aligned)
     work_keys_off_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_reg_off, n, wk_in, wv_in);
     if (sort_work(ctx, wk_in, wk_out, wv_in, d_perm, n, true)) return 1;          // decreasing number of regs
     tail_kernel<<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
-                                          d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, 0, heavy_thr, 0);
-    {
-        const size_t sh_bytes = (size_t) 4 * tail_cap * 132;
-        int blocks_h = blocks_i;
-        if (tail_cap > 0) {
-            static std::mutex attr_mu; static bool attr_done[64] = {};
-            std::lock_guard<std::mutex> lk(attr_mu);
-            if (!attr_done[ctx->device & 63]) {
-                BM2_CUDA_OK(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                attr_done[ctx->device & 63] = true;
-            }
-            const int per_sm = (int) ((227 * 1024) / (sh_bytes + 1024));
-            const int cap_blocks = ctx->n_sm * (per_sm < 1 ? 1 : per_sm > 8 ? 8 : per_sm);
-            if (blocks_h > cap_blocks) blocks_h = cap_blocks;
-        }
-        tail_kernel<<<blocks_h, 128, sh_bytes, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
-                                                     d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, 1, heavy_thr, tail_cap);
-    }
+                                          d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, 0, heavy_thr, light_sorted);
+    tail_kernel<<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
+                                          d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, 1, heavy_thr, 0);
 
     // ---- J. output ---------------------------------------------------------------------------------------
     if (sg.mark("output")) return 1;
