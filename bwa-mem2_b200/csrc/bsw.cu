@@ -409,8 +409,9 @@ bsw_col2_kernel(const BswJob *__restrict__ jobs, const int32_t *__restrict__ per
             }
             BswOut o;
             if (same_oe && reg_shrink == 1) bsw_col2_extend<true>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
-            else if (same_oe && reg_shrink == 2) bsw_col2_extend<true, Col2MemShared<NTHR>, false, 8>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
-            else if (same_oe) bsw_col2_extend<true, Col2MemShared<NTHR>, false>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
+            else if (same_oe && reg_shrink == 2) bsw_col2_extend<true, Col2MemShared<NTHR>, 0, 8>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
+            else if (same_oe && reg_shrink == 3) bsw_col2_extend<true, Col2MemShared<NTHR>, 2>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
+            else if (same_oe) bsw_col2_extend<true, Col2MemShared<NTHR>, 0>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
             else bsw_col2_extend<false>(mem, tbase + job.toff, (int) job.tstride, job.qlen, job.tlen, job.h0, p, o, ncell);
             out[id] = o;
         }
@@ -781,6 +782,7 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
             // profiles/r2g_exp_knobs.log: the extra branches cost more than the one or two loads they save) - off unless BM2_BSW_REGSHRINK=1
             int reg_shrink = (rs_env && rs_env[0] == '1') ? 1 : 0;
             if (const char *e = getenv("BM2_BSW_UNROLL8")) { if (e[0] == '1') reg_shrink = 2; }      // the pair loop unrolled x8 instead of x4 (A/B)
+            if (rs_env && rs_env[0] == '2') reg_shrink = 3;                                            // edge columns from registers, then the scans (A/B)
             const char *dyn_env = getenv("BM2_BSW_DYN");
             const int dyn = (dyn_env && dyn_env[0] == '0') ? 0 : 1;           // per-warp job counters: class_cnt[64 + c], zeroed with class_cnt above
             int nthr2 = 128, best_res = 0, best_cps = 1;

@@ -47,7 +47,7 @@ BM2_HD bool c2_params_ok(const BswParams &p) { return p2_params_ok(p); }
 // F crosses the halves with one multiply and one PRMT per pair: with U = {F(2q), F(2q)},
 //   f2 = max(U + {0, -e}, {0, t(2q)}, 0) = {F(2q), F(2q+1)},  fb = max(f2 + {-e, -e}, {t(2q), t(2q+1)}, 0) -> high half F(2q+2),
 // t = M - oe_ins (round 1: two multiplies up, a merge and a shift down per pair).
-template <bool SAME_OE, class Mem, bool REG_SHRINK = true, int UNR = 4>
+template <bool SAME_OE, class Mem, int REG_SHRINK = 1, int UNR = 4>
 BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, int qlen, int tlen, int h0, const BswParams &p,
                             BswOut &o, unsigned long long &cells)
 {
@@ -177,6 +177,19 @@ BM2_HD void bsw_col2_extend(const Mem &mem, const uint8_t *tptr, int tstride, in
         // columns at either edge are decided from the words just written (registers); shared memory is only scanned when both are zero
         // (round 2: the scan loops - a load, a compare and a branch per step, 19 of 32 lanes - took 11 % of the kernel's samples).
         int j = beg;                                           // (here end > beg: an empty row has m == 0 and left the loop above)
+        if (REG_SHRINK == 2) {                                 // the column at either edge from the words just written, then the scans
+            const uint32_t f16 = (beg & 1) ? fw >> 16 : fw & 0xFFFFu;
+            if (f16 == 0u) for (++j; j < end && mem.ldh(j) == 0u; ++j) {}
+            beg = j;
+            j = end;
+            if (h1 == 0) {
+                const uint32_t l16 = (end & 1) ? lw & 0xFFFFu : lw >> 16;
+                --j;
+                if (j >= beg && l16 == 0u) for (--j; j >= beg && mem.ldh(j) == 0u; --j) {}
+            }
+            end = j + 2 < qlen ? j + 2 : qlen;
+            continue;
+        }
         if (!REG_SHRINK) {                                     // round 1's scans (A/B measurements: BM2_BSW_REGSHRINK=0)
             for (; j < end && mem.ldh(j) == 0u; ++j) {}
             beg = j;

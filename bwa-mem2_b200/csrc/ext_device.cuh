@@ -343,23 +343,10 @@ BM2_HD void permute_regs_d(bm2_alnreg_t *a, int32_t *idx, int n) {
     }
 }
 
-// mem_sort_dedup_patch (src/bwamem.cpp:292-353) on the regs of one read; he: 2*(l_query+1) ints; idx: n ints.
-// The two ks_introsort calls run on an index array (same comparisons, same swaps => same permutation as sorting
-// the records) and the records are permuted once.
-// keys: n entries of 16 bytes; the comparators read these compact copies of the sort fields instead of the 112-byte records.
-struct TailSortKey { int64_t r; int32_t score, qb; };
-BM2_HD int sort_dedup_patch_d(const ContigView &cv, const ExtParams &p, const uint8_t *ref, const uint8_t *query, int n,
-                              bm2_alnreg_t *a, int32_t *he, int32_t *idx, TailSortKey *keys)
+// the dedup / patch scan of mem_sort_dedup_patch (src/bwamem.cpp:302-333) over the regs sorted by `re` (n_comp already 1)
+BM2_HD void sort_dedup_scan_d(const ContigView &cv, const ExtParams &p, const uint8_t *ref, const uint8_t *query, int n, bm2_alnreg_t *a, int32_t *he)
 {
-    int m, i, j;
-    if (n <= 1) return n;
-    for (i = 0; i < n; ++i) { idx[i] = i; keys[i].r = a[i].re; }
-    {
-        const TailSortKey *rk = keys;
-        ks_introsort_d(idx, (long) n, [rk](int x, int y) { return rk[x].r < rk[y].r; });
-    }
-    permute_regs_d(a, idx, n);
-    for (i = 0; i < n; ++i) reg_set_n_comp_d(a[i], 1);
+    int i, j;
     for (i = 1; i < n; ++i) {
         bm2_alnreg_t *pp = &a[i];
         if (pp->rid != a[i - 1].rid || pp->rb >= a[i - 1].re + p.max_chain_gap) continue;
@@ -387,6 +374,26 @@ BM2_HD int sort_dedup_patch_d(const ContigView &cv, const ExtParams &p, const ui
             }
         }
     }
+}
+
+// mem_sort_dedup_patch (src/bwamem.cpp:292-353) on the regs of one read; he: 2*(l_query+1) ints; idx: n ints.
+// The two ks_introsort calls run on an index array (same comparisons, same swaps => same permutation as sorting
+// the records) and the records are permuted once.
+// keys: n entries of 16 bytes; the comparators read these compact copies of the sort fields instead of the 112-byte records.
+struct TailSortKey { int64_t r; int32_t score, qb; };
+BM2_HD int sort_dedup_patch_d(const ContigView &cv, const ExtParams &p, const uint8_t *ref, const uint8_t *query, int n,
+                              bm2_alnreg_t *a, int32_t *he, int32_t *idx, TailSortKey *keys)
+{
+    int m, i, j;
+    if (n <= 1) return n;
+    for (i = 0; i < n; ++i) { idx[i] = i; keys[i].r = a[i].re; }
+    {
+        const TailSortKey *rk = keys;
+        ks_introsort_d(idx, (long) n, [rk](int x, int y) { return rk[x].r < rk[y].r; });
+    }
+    permute_regs_d(a, idx, n);
+    for (i = 0; i < n; ++i) reg_set_n_comp_d(a[i], 1);
+    sort_dedup_scan_d(cv, p, ref, query, n, a, he);
     for (i = 0, m = 0; i < n; ++i)
         if (a[i].qe > a[i].qb) { if (m != i) reg_copy(&a[m++], &a[i]); else ++m; }
     n = m;

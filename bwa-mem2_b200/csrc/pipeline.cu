@@ -561,12 +561,117 @@ __device__ void ext_postfilter_read_warp(const ExtParams &p, const bm2_chain *ch
     }
 }
 
+// ---- the tail of one heavy read by a whole warp ---------------------------------------------------------------------------------
+// Same result as ext_tail_read_d (ext_device.cuh; src/bwamem.cpp:1141-1169 + mem_sort_dedup_patch, :292-353).  The passes that touch every record
+// once - the three compactions, the key arrays of the two sorts, the two in-place permutations, n_comp = 1, the equal-neighbour test, the ALT
+// marks - run on all lanes (ncu r2i: they were 36 % of the heavy pass's samples with ONE lane active); the two introsorts and the
+// dedup / patch scan, whose steps depend on each other, stay on lane 0.
+
+// keep the records with qe > qb, in order, in place; returns the count.  A block of 32 records is read completely before any of it is written,
+// and a record only moves towards the front.
+__device__ int tail_compact_warp(bm2_alnreg_t *a, int n, int lane) {
+    int m = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        uint4 v[7];
+        bool keep = false;
+        if (i < n) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(a + i);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) v[k] = s4[k];
+            keep = a[i].qe > a[i].qb;
+        }
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) {
+            const int d = m + __popc(km & ((1u << lane) - 1u));
+            if (d != i) {
+                uint4 *d4 = reinterpret_cast<uint4 *>(a + d);
+#pragma unroll
+                for (int k = 0; k < 7; ++k) d4[k] = v[k];
+            }
+        }
+        m += __popc(km);
+        __syncwarp();
+    }
+    return m;
+}
+
+// a[i] <- a[idx[i]] in place (permute_regs_d's cycle walk, every lane walking the same cycle); lanes 0..6 move one 16-byte word of the
+// record each, the displaced first record of a cycle waits in their registers; idx is destroyed
+__device__ void tail_permute_warp(bm2_alnreg_t *a, int32_t *idx, int n, int lane) {
+    for (int i = 0; i < n; ++i) {
+        const int first = idx[i];
+        if (first < 0 || first == i) continue;
+        uint4 tmp = make_uint4(0, 0, 0, 0);
+        if (lane < 7) tmp = reinterpret_cast<const uint4 *>(a + i)[lane];
+        int j = i;
+        for (;;) {
+            const int src = idx[j];
+            __syncwarp();
+            if (lane == 0) idx[j] = -1;
+            if (src == i) { if (lane < 7) reinterpret_cast<uint4 *>(a + j)[lane] = tmp; break; }
+            if (lane < 7) reinterpret_cast<uint4 *>(a + j)[lane] = reinterpret_cast<const uint4 *>(a + src)[lane];
+            j = src;
+        }
+        __syncwarp();
+    }
+}
+
+__device__ int ext_tail_read_warp(const ContigView &cv, const ExtParams &p, const uint8_t *ref, const uint8_t *query, bm2_alnreg_t *a, int n_reg,
+                                  int32_t *he, int32_t *idx, TailSortKey *keys)
+{
+    const int lane = threadIdx.x & 31;
+    int n = tail_compact_warp(a, n_reg, lane);
+    if (n > 1) {
+        for (int i = lane; i < n; i += 32) { idx[i] = i; keys[i].r = a[i].re; }
+        __syncwarp();
+        if (lane == 0) {
+            const TailSortKey *rk = keys;
+            ks_introsort_d(idx, (long) n, [rk](int x, int y) { return rk[x].r < rk[y].r; });
+        }
+        __syncwarp();
+        tail_permute_warp(a, idx, n, lane);
+        for (int i = lane; i < n; i += 32) reg_set_n_comp_d(a[i], 1);
+        __syncwarp();
+        if (lane == 0) sort_dedup_scan_d(cv, p, ref, query, n, a, he);
+        __syncwarp();
+        n = tail_compact_warp(a, n, lane);
+        for (int i = lane; i < n; i += 32) { idx[i] = i; keys[i].r = a[i].rb; keys[i].score = a[i].score; keys[i].qb = a[i].qb; }
+        __syncwarp();
+        if (lane == 0) {
+            const TailSortKey *rk = keys;
+            ks_introsort_d(idx, (long) n, [rk](int xi, int yi) {
+                const TailSortKey x = rk[xi], y = rk[yi];
+                return x.score > y.score || (x.score == y.score && (x.r < y.r || (x.r == y.r && x.qb < y.qb)));
+            });
+        }
+        __syncwarp();
+        tail_permute_warp(a, idx, n, lane);
+        // equal neighbours (score, rb, qb): the test reads fields the marking does not change, so all pairs are independent
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const bool dup = i >= 1 && i < n && a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb;
+            __syncwarp();
+            if (dup) a[i].qe = a[i].qb;
+        }
+        __syncwarp();
+        // (the reference's last compaction starts at index 1: a[0] stays whatever its qe is)
+        if (n > 1) n = 1 + tail_compact_warp(a + 1, n - 1, lane);
+    }
+    for (int i = lane; i < n; i += 32)
+        if (a[i].rid >= 0 && cv.ann_alt && cv.ann_alt[a[i].rid]) reg_set_is_alt_d(a[i], 1);
+    __syncwarp();
+    return n;
+}
+
 // I. one read per thread (grid-stride: the NW scratch `he` is per thread)
-__global__ void __launch_bounds__(128)
+template <int mode>             // separate instances: the warp-per-read code (more registers) must not cost the per-thread pass its occupancy (96)
+__global__ void __launch_bounds__(128, mode ? 4 : 1)
 tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs,
             const bm2_chain *__restrict__ chains, const bm2_seed *__restrict__ seeds, const int64_t *__restrict__ chain_off,
             const int64_t *__restrict__ reg_off, int n_reads, bm2_alnreg_t *regs, const int32_t *reg_seed, int32_t *srt2_all, int32_t *he_all,
-            int he_stride, const int32_t *__restrict__ perm, PfBox *box_all, int32_t *n_final, int mode, int heavy_thr, int light_sorted)
+            int he_stride, const int32_t *__restrict__ perm, PfBox *box_all, int32_t *n_final, int heavy_thr, int light_sorted, int coop_tail)
 {
     // Heavy reads (many regs: O(regs^2) post-filter, sorts, patch DP) would serialise with the 31 other reads of their
     // warp (ncu: 1.9 active lanes per instruction), so they get a WARP each (mode 1: reads in decreasing-work order; the
@@ -590,7 +695,8 @@ tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const 
             if (mode) {
                 ext_postfilter_read_warp(ep, chains + c0, (int) (c1 - c0), seeds, l_query, regs + g0, n_reg, reg_seed + g0, srt2_all + g0, box_all + g0);
                 __syncwarp();
-                if (lane == 0) m = ext_tail_read_d(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he, srt2_all + g0, reinterpret_cast<TailSortKey *>(box_all + g0));
+                if (coop_tail) m = ext_tail_read_warp(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he, srt2_all + g0, reinterpret_cast<TailSortKey *>(box_all + g0));
+                else if (lane == 0) m = ext_tail_read_d(cv, ep, ref, codes + offs[r], regs + g0, n_reg, he, srt2_all + g0, reinterpret_cast<TailSortKey *>(box_all + g0));
                 __syncwarp();
             } else {
                 ext_postfilter_read_d(ep, chains + c0, (int) (c1 - c0), seeds, l_query, regs + g0, n_reg, reg_seed + g0, srt2_all + g0, box_all + g0);
@@ -1043,10 +1149,10 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     const int heavy_thr = env_int("BM2_TAIL_HEAVY", 24, 1, 1 << 20);            // regs from which a read gets a warp
     work_keys_off_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_reg_off, n, wk_in, wv_in);
     if (sort_work(ctx, wk_in, wk_out, wv_in, d_perm, n, true)) return 1;          // decreasing number of regs
-    tail_kernel<<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
-                                          d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, 0, heavy_thr, light_sorted);
-    tail_kernel<<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
-                                          d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, 1, heavy_thr, 0);
+    tail_kernel<0><<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
+                                             d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, heavy_thr, light_sorted, 0);
+    tail_kernel<1><<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
+                                             d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, heavy_thr, 0, env_int("BM2_TAIL_COOP", 1, 0, 1));
 
     // ---- J. output ---------------------------------------------------------------------------------------
     if (sg.mark("output")) return 1;

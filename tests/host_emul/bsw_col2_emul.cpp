@@ -53,8 +53,13 @@ extern "C" long long col2_extend_trace(int n, const int64_t *qoff, const int64_t
         HostCol2Mem mem{state.data(), sel.data()};
         BswOut o;
         tr.clear(); g_trace = rows ? &tr : nullptr;
-        if (p.o_del + p.e_del == p.o_ins + p.e_ins && !(k & 1)) bsw_col2_extend<true>(mem, tbuf + toff[k], tstride[k], qlen[k], tlen[k], h0[k], p, o, cells);
-        else bsw_col2_extend<false>(mem, tbuf + toff[k], tstride[k], qlen[k], tlen[k], h0[k], p, o, cells);      // (odd jobs: the general form also under equal penalties)
+        // every instance the kernel compiles, by job index: the three band-shrink forms under equal penalties (0 = scans, the product's
+        // default; 1, 2 = edge columns from registers first) and the general form (also under equal penalties)
+        const bool same = p.o_del + p.e_del == p.o_ins + p.e_ins;
+        if (same && (k & 3) == 0) bsw_col2_extend<true, HostCol2Mem, 0>(mem, tbuf + toff[k], tstride[k], qlen[k], tlen[k], h0[k], p, o, cells);
+        else if (same && (k & 3) == 1) bsw_col2_extend<true, HostCol2Mem, 1>(mem, tbuf + toff[k], tstride[k], qlen[k], tlen[k], h0[k], p, o, cells);
+        else if (same && (k & 3) == 2) bsw_col2_extend<true, HostCol2Mem, 2>(mem, tbuf + toff[k], tstride[k], qlen[k], tlen[k], h0[k], p, o, cells);
+        else bsw_col2_extend<false>(mem, tbuf + toff[k], tstride[k], qlen[k], tlen[k], h0[k], p, o, cells);
         g_trace = nullptr;
         if (rows) {
             rows[k] = (int32_t) (tr.size() / 2);

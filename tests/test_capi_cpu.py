@@ -64,3 +64,13 @@ def test_sam_stage_switches_validate_their_arguments(pkg):
     ms = (C.c_double * 4)(); cnt = (C.c_ulonglong * 6)()
     assert lib.bm2_last_sam_stats(None, ms, cnt, 4, 6) == 1
     assert {"bm2_set_sam_staged", "bm2_last_sam_stats"} <= set(pkg.capi.EXPORTS)
+
+
+def test_sibling_context_needs_a_parent(pkg):
+    """bm2_create_sibling (a second context on the parent's index, one per host worker of bm2_mem): NULL arguments are an error code, not a crash."""
+    lib = pkg.capi.lib()
+    lib.bm2_create_sibling.argtypes = [C.POINTER(C.c_void_p), C.c_void_p]
+    out = C.c_void_p(123)
+    assert lib.bm2_create_sibling(C.byref(out), None) == 1
+    assert lib.bm2_create_sibling(None, None) == 1
+    assert "bm2_create_sibling" in pkg.capi.EXPORTS
