@@ -1039,7 +1039,9 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     int32_t *wv_in = (int32_t *) ((char *) ctx->d[B_PERM].p + 2 * al((size_t) n * 4)), *d_perm = (int32_t *) ((char *) ctx->d[B_PERM].p + 3 * al((size_t) n * 4));
     work_keys_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(P<int64_t>(ctx, B_READ_SMEM_OFF), P<int64_t>(ctx, B_SLOT_OFF), n, wk_in, wv_in);
     if (sort_work(ctx, wk_in, wk_out, wv_in, d_perm, n, true)) return 1;             // decreasing number of seed slots
-    const int light_sorted = env_int("BM2_LIGHT_SORTED", 1, 0, 1);              // light reads of the chain and tail kernels in work order (0: input order, A/B)
+    // light reads of the chain and tail kernels in work order instead of input order: measured no better (chain 13.4 against 12.8 ms, tail equal,
+    // profiles/r2m_exp_knobs.log: neighbouring reads share cache lines of the per-read arrays), so off unless BM2_LIGHT_SORTED=1
+    const int light_sorted = env_int("BM2_LIGHT_SORTED", 0, 0, 1);
     const int chain_heavy = env_int("BM2_CHAIN_HEAVY", 64, 1, 1 << 30);          // seed occurrences from which a read gets a warp
     const int chain_coop_min = env_int("BM2_CHAIN_COOP_MIN", 1024, 0, 1 << 30);      // seed occurrences from which a warp shares the chaining of a read
     chain_kernel<<<(n + 127) / 128, 128, 0, st>>>(pv.cv, pv.cp, P<bm2_smem>(ctx, B_SMEM), P<int64_t>(ctx, B_READ_SMEM_OFF),
