@@ -19,6 +19,10 @@ CONFIGS = [
     dict(name="heavy tail reads: lane 0 only, sub 4", sub=4, BM2_TAIL_COOP="0"),
     dict(name="band shrink: edge columns from registers, sub 4", sub=4, BM2_BSW_REGSHRINK="2"),
     dict(name="default, sub 4 (again)", sub=4),
+    dict(name="end to end (host buffers), sub 4", sub=4, e2e=True),
+    dict(name="end to end (host buffers), sub 6", sub=6, e2e=True),
+    dict(name="end to end (host buffers), sub 8", sub=8, e2e=True),
+    dict(name="end to end (host buffers), sub 4 (again)", sub=4, e2e=True),
 ]
 
 
@@ -36,6 +40,7 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     d_codes = torch.from_numpy(codes).cuda(); d_offs = torch.from_numpy(offs).cuda()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    h_codes = torch.from_numpy(codes.copy()).pin_memory(); h_offs = torch.from_numpy(offs.copy()).pin_memory()      # the e2e leg's pinned inputs
     results = []
     ref_bytes = None
     for cfg in CONFIGS:
@@ -45,11 +50,22 @@ def main():
             if k.startswith("BM2_"):
                 os.environ[k] = v
         ctx.set_sub_batches(cfg["sub"])
-        ctx.seed_chain_extend_resident(codes, offs, d_codes.data_ptr(), d_offs.data_ptr(), False)      # warm-up / buffer growth
+        e2e = bool(cfg.get("e2e"))          # host buffers in, regs out to host memory (wall clock), as bench.py's e2e leg
+        ctx.set_stream(None if e2e else stream.cuda_stream)
+        if e2e:
+            ctx.seed_chain_extend(h_codes.numpy(), h_offs.numpy(), copy=False)
+        else:
+            ctx.seed_chain_extend_resident(codes, offs, d_codes.data_ptr(), d_offs.data_ptr(), False)      # warm-up / buffer growth
         torch.cuda.synchronize()
         ms = []
         for _ in range(steps):
             flush.fill_(1)
+            torch.cuda.synchronize()
+            if e2e:
+                t0 = time.perf_counter()
+                n_regs = ctx.seed_chain_extend(codes, offs, copy=False)
+                ms.append((time.perf_counter() - t0) * 1e3)
+                continue
             a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
             a.record(stream)
             n_regs = ctx.seed_chain_extend_resident(codes, offs, d_codes.data_ptr(), d_offs.data_ptr(), False)

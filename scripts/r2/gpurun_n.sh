@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 export PYTHONDONTWRITEBYTECODE=1
 W=/tmp/bm2_bench_pipe_3000_500000
 ( timeout 1500 python bench.py --steps 3 --warmup 3 2> gpurun_out/r2n_bench.err | tail -1 ) > gpurun_out/r2n_bench_3gbp_1gpu.json
-( timeout 900 python scripts/exp_knobs.py $W 3 2>&1 | tail -12 ) > gpurun_out/r2n_exp_knobs.log
+( timeout 900 python scripts/exp_knobs.py $W 3 2>&1 | tail -16 ) > gpurun_out/r2n_exp_knobs.log
 ( timeout 1800 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -5 ) > gpurun_out/r2n_tests.log 2>&1
 ( timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ) > gpurun_out/r2n_smoke.log
 ( timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2> gpurun_out/r2n_bench_ref.err | tail -1 ) > gpurun_out/r2n_bench_reference_arm.json
