@@ -777,12 +777,14 @@ int bsw_launch_with_scratch(bm2_ctx *ctx_for_error, cudaStream_t stream, const B
             const int NP = (W + 1) / 2;                       // state words: pairs over columns 0 .. bound + 1; selectors: 2 B per pair
             // threads per CTA: the size that keeps the most threads resident per SM (shared memory is what limits this kernel's
             // occupancy: 6 B per column pair and thread; 64- or 96-thread CTAs waste less of the 227 KB than 128-thread ones)
+            // Band shrink of a row (first / last column with a non-zero state): 0 = scans over shared memory; 1 = the two columns at either edge
+            // from the words just written, then the scans: measured 2 % SLOWER than 0 (profiles/r2g_exp_knobs.log: the extra branches cost more
+            // than the loads they save); 2 (default) = only the ONE column at either edge from registers, then the scans: 42.0 against 42.4 ms
+            // (profiles/r2n_exp_knobs.log).  BM2_BSW_REGSHRINK selects (A/B); BM2_BSW_UNROLL8=1: the scans with the pair loop unrolled x8 (no gain).
             const char *rs_env = getenv("BM2_BSW_REGSHRINK");
-            // band shrink decided from the two words just written instead of scanning shared memory: measured 2 % SLOWER (49.6 against 48.5 ms,
-            // profiles/r2g_exp_knobs.log: the extra branches cost more than the one or two loads they save) - off unless BM2_BSW_REGSHRINK=1
-            int reg_shrink = (rs_env && rs_env[0] == '1') ? 1 : 0;
-            if (const char *e = getenv("BM2_BSW_UNROLL8")) { if (e[0] == '1') reg_shrink = 2; }      // the pair loop unrolled x8 instead of x4 (A/B)
-            if (rs_env && rs_env[0] == '2') reg_shrink = 3;                                            // edge columns from registers, then the scans (A/B)
+            int reg_shrink = 3;
+            if (rs_env && rs_env[0] == '0') reg_shrink = 0; else if (rs_env && rs_env[0] == '1') reg_shrink = 1;
+            if (const char *e = getenv("BM2_BSW_UNROLL8")) { if (e[0] == '1') reg_shrink = 2; }
             const char *dyn_env = getenv("BM2_BSW_DYN");
             const int dyn = (dyn_env && dyn_env[0] == '0') ? 0 : 1;           // per-warp job counters: class_cnt[64 + c], zeroed with class_cnt above
             int nthr2 = 128, best_res = 0, best_cps = 1;

@@ -76,7 +76,7 @@ def main():
     # parity of one knob setting against another on a slice (regs must be byte-identical whatever the knobs)
     ns = 65536
     outs = []
-    for env in (dict(BM2_BSW_COL2="0", BM2_STAGE_TOKENS="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5"), dict(BM2_BSW_REGSHRINK="1", BM2_CHAIN_COOP_MIN="64"), dict(BM2_SMEM_TEXT="0", BM2_BSW_DYN="0", BM2_LIGHT_SORTED="1", BM2_TAIL_COOP="0"), dict(BM2_TAIL_HEAVY="2", BM2_CHAIN_HEAVY="16", BM2_BSW_UNROLL8="1"), dict(BM2_BSW_REGSHRINK="2")):
+    for env in (dict(BM2_BSW_COL2="0", BM2_STAGE_TOKENS="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5"), dict(BM2_BSW_REGSHRINK="1", BM2_CHAIN_COOP_MIN="64"), dict(BM2_SMEM_TEXT="0", BM2_BSW_DYN="0", BM2_LIGHT_SORTED="1", BM2_TAIL_COOP="0"), dict(BM2_TAIL_HEAVY="2", BM2_CHAIN_HEAVY="16", BM2_BSW_UNROLL8="1"), dict(BM2_BSW_REGSHRINK="0", BM2_D2H_WAVES="2")):
         for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update(env)
