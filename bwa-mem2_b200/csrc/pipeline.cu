@@ -1314,14 +1314,17 @@ static int run_regs(bm2_ctx *ctx, const bm2_read_batch *rb, const uint8_t *d_cod
         std::mutex mu; std::condition_variable cv;
         std::vector<int64_t> nout((size_t) S, -1);
         bool failed = false;
-        std::vector<cudaEvent_t> copied((size_t) K, nullptr);       // last device -> host copy of every lane (a growing output buffer waits for them)
-        std::vector<char> copied_set((size_t) K, 0);
-        for (int k = 0; k < K; ++k) if (cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming) != cudaSuccess) { bm2_set_error(ctx, "sub-batches: event creation failed"); return 1; }
+        // two events per lane, one per output buffer: the last device -> host copy out of it (a growing host buffer waits for all of them)
+        std::vector<cudaEvent_t> copied((size_t) 2 * K, nullptr);
+        std::vector<char> copied_set((size_t) 2 * K, 0);
+        for (int k = 0; k < 2 * K; ++k) if (cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming) != cudaSuccess) { bm2_set_error(ctx, "sub-batches: event creation failed"); return 1; }
+        for (int k = 0; k < K; ++k)
+            if (!ctx->lanes[k]->copy_stream && cudaStreamCreateWithFlags(&ctx->lanes[k]->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { bm2_set_error(ctx, "sub-batches: stream creation failed"); return 1; }
         int wave_rc = 0;
         auto grow = [&](size_t need_regs, size_t keep_regs, size_t hint_regs) -> int {      // (mu held)
             HostBuf &hb = ctx->h[H_OUT_REGS];
             if (hb.cap >= need_regs * sizeof(bm2_alnreg_t)) return 0;
-            for (int k = 0; k < K; ++k) if (copied_set[k] && cudaEventSynchronize(copied[k]) != cudaSuccess) return 1;
+            for (int k = 0; k < 2 * K; ++k) if (copied_set[k] && cudaEventSynchronize(copied[k]) != cudaSuccess) return 1;
             const size_t want = (need_regs > hint_regs ? need_regs : hint_regs) * sizeof(bm2_alnreg_t);
             void *np = nullptr;
             if (cudaMallocHost(&np, want + want / 8 + 256) != cudaSuccess) return 1;
@@ -1334,6 +1337,9 @@ static int run_regs(bm2_ctx *ctx, const bm2_read_batch *rb, const uint8_t *d_cod
             cudaSetDevice(ctx->device);
             for (int s = lane; s < S; s += K) {
                 { std::lock_guard<std::mutex> lk(mu); if (failed) return; }
+                // the output buffer this sub-batch writes was copied from two sub-batches (of this lane) ago: that copy is long over
+                const int slot = 2 * lane + ((s / K) & 1);
+                if (copied_set[slot] && cudaEventSynchronize(copied[slot]) != cudaSuccess) { std::lock_guard<std::mutex> lk(mu); failed = true; wave_rc = 1; cv.notify_all(); return; }
                 run_sub(s, lane);
                 Job &j = jobs[s];
                 bm2_ctx *l = ctx->lanes[lane];
@@ -1351,10 +1357,13 @@ static int run_regs(bm2_ctx *ctx, const bm2_read_batch *rb, const uint8_t *d_cod
                     const size_t hint = (size_t) ((double) (pos + j.bs.n_out) * (double) n / (double) (j.first + j.n) * 1.05) + 1024;
                     if (grow((size_t) (pos + j.bs.n_out) + 1, (size_t) pos, hint)) { failed = true; wave_rc = 1; cv.notify_all(); return; }
                     bm2_alnreg_t *dst = (bm2_alnreg_t *) ctx->h[H_OUT_REGS].p + pos;
-                    if (cudaMemcpyAsync(dst, l->d[B_OUT].p, (size_t) j.bs.n_out * sizeof(bm2_alnreg_t), cudaMemcpyDeviceToHost, l->stream) != cudaSuccess ||
-                        cudaEventRecord(copied[lane], l->stream) != cudaSuccess) { failed = true; wave_rc = 1; cv.notify_all(); return; }
-                    copied_set[lane] = 1;
+                    // the copy runs on the lane's COPY stream (the sub-batch's kernels are done: run_pipeline ends with a synchronise), and the
+                    // lane's next sub-batch writes the lane's other output buffer - so the lane goes on computing under its own copy
+                    if (cudaMemcpyAsync(dst, l->d[B_OUT].p, (size_t) j.bs.n_out * sizeof(bm2_alnreg_t), cudaMemcpyDeviceToHost, l->copy_stream) != cudaSuccess) { failed = true; wave_rc = 1; cv.notify_all(); return; }
                 }
+                if (cudaEventRecord(copied[slot], l->copy_stream) != cudaSuccess) { failed = true; wave_rc = 1; cv.notify_all(); return; }
+                copied_set[slot] = 1;
+                std::swap(l->d[B_OUT], l->out_alt);
             }
         };
         {
@@ -1363,8 +1372,8 @@ static int run_regs(bm2_ctx *ctx, const bm2_read_batch *rb, const uint8_t *d_cod
             lane_work(0);
             for (auto &t : th) t.join();
         }
-        for (int k = 0; k < K; ++k) cudaStreamSynchronize(ctx->lanes[k]->stream);
-        for (int k = 0; k < K; ++k) cudaEventDestroy(copied[k]);
+        for (int k = 0; k < K; ++k) { cudaStreamSynchronize(ctx->lanes[k]->stream); cudaStreamSynchronize(ctx->lanes[k]->copy_stream); }
+        for (int k = 0; k < 2 * K; ++k) cudaEventDestroy(copied[k]);
         for (int s = 0; s < S; ++s)
             if (jobs[s].rc) { bm2_set_error(ctx, "sub-batch " + std::to_string(s) + ": " + ctx->lanes[s % K]->err); return 1; }
         if (wave_rc || failed) { bm2_set_error(ctx, "sub-batches: output copy failed"); return 1; }

@@ -60,7 +60,7 @@ def main():
             torch.cuda.synchronize()
             if e2e:
                 t0 = time.perf_counter()
-                n_regs = ctx.seed_chain_extend(codes, offs, copy=False)
+                n_regs = len(ctx.seed_chain_extend(h_codes.numpy(), h_offs.numpy(), copy=False)[0])
                 ms.append((time.perf_counter() - t0) * 1e3)
                 continue
             a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
