@@ -50,9 +50,6 @@ struct bm2_ctx {
     // ALU-bound extension stage, so that at any time DIFFERENT kinds of stages overlap instead of four copies of the same
     std::mutex tok_smem, tok_bsw;
     cudaEvent_t ev_entry = nullptr;
-    // a lane's second output buffer and its copy stream (run_regs in waves: the regs of sub-batch s travel to the host while s + K is computed)
-    DevBuf out_alt;
-    cudaStream_t copy_stream = nullptr;
     // seam 4 (sam.cu): staged rescue switch (-1: the BM2_SAM_STAGED environment variable decides, default off), events around the stage's
     // kernels, and the last call's times (jobs, window alignments, pairs, gather; ms summed over waves) and counters
     int sam_staged = -1;
@@ -63,7 +60,7 @@ struct bm2_ctx {
     int ensure(DevBuf &b, size_t bytes);
     int ensure_host(HostBuf &b, size_t bytes);
     std::vector<DevBuf *> all_dev() {
-        std::vector<DevBuf *> v = {&io_pairs, &io_ref, &io_qer, &bsw_jobs, &bsw_outs, &bsw_scratch, &out_alt};
+        std::vector<DevBuf *> v = {&io_pairs, &io_ref, &io_qer, &bsw_jobs, &bsw_outs, &bsw_scratch};
         for (auto &x : d) v.push_back(&x);
         return v;
     }

@@ -199,7 +199,6 @@ extern "C" void bm2_destroy(bm2_ctx *ctx) {
     for (cudaEvent_t ev : ctx->events) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
-    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;

@@ -25,7 +25,6 @@
 #include <cub/device/device_scan.cuh>
 #include <vector>
 #include <mutex>
-#include <condition_variable>
 #include <thread>
 #include <string>
 #include <cstring>
@@ -1260,132 +1259,41 @@ static int run_regs(bm2_ctx *ctx, const bm2_read_batch *rb, const uint8_t *d_cod
     // the sub-batches start after whatever the caller queued on the context's stream (its inputs, its start event)
     BM2_CUDA_OK(cudaEventRecord(ctx->ev_entry, ctx->stream));
     struct Job { int first = 0, n = 0; std::vector<int64_t> offs; bm2_read_batch rb; BatchState bs; int rc = 0; };
-    // Waves (BM2_D2H_WAVES = W > 1, only when the regs go back to the host): the batch is cut into K * W sub-batches and every lane runs W of
-    // them one after the other; a sub-batch's regs start their way to the host as soon as it and its predecessors are done, under the
-    // kernels of the sub-batches still running on the other lanes - with W = 1 every device -> host copy waits for the slowest lane and
-    // nothing is left to overlap it (387 MB per 1 M reads: the gap between the resident and the end-to-end number).
-    int W = copy_out ? env_int("BM2_D2H_WAVES", 1, 1, 8) : 1;
-    while (W > 1 && (int64_t) n < (int64_t) K * W * ctx->lane_min_reads) --W;
-    const int S = K * W;
-    std::vector<Job> jobs((size_t) S);
+    // (Round 2 also ran every lane over several smaller sub-batches in a row, each sub-batch's regs copied to the host on a copy stream under
+    // the kernels of the following ones - the device -> host copies at the end of the step, 387 MB per 1 M reads, are the gap between the
+    // resident and the end-to-end number.  Bit-identical and SLOWER end to end: 111.3 ms with 2 x 4 sub-batches, 119.4 with 3 x 4, against
+    // 108.5 with 4, profiles/r2p_exp_knobs.log - eight 125 k-read sub-batches lose more in the kernels than the hidden copies give back.)
+    std::vector<Job> jobs((size_t) K);
     // cut points (multiples of 512 reads).  BM2_LANE_SKEW = s percent: lane k gets a share proportional to 100 + s * k instead of equal shares,
     // so that the lanes - which start together - leave the SMEM stage at different times (experiment: do unequal lanes overlap unlike stages better?)
-    std::vector<int> cut((size_t) S + 1, 0);
+    std::vector<int> cut((size_t) K + 1, 0);
     {
-        const int skew = W > 1 ? 0 : env_int("BM2_LANE_SKEW", 0, 0, 400);
-        double tot = 0; for (int k = 0; k < S; ++k) tot += 100.0 + (double) skew * k;
+        const int skew = env_int("BM2_LANE_SKEW", 0, 0, 400);
+        double tot = 0; for (int k = 0; k < K; ++k) tot += 100.0 + (double) skew * k;
         double acc = 0;
-        for (int k = 0; k < S; ++k) { cut[k] = (int) ((int64_t) ((double) n * acc / tot) / 512 * 512); acc += 100.0 + (double) skew * k; }
-        cut[S] = n;
+        for (int k = 0; k < K; ++k) { cut[k] = (int) ((int64_t) ((double) n * acc / tot) / 512 * 512); acc += 100.0 + (double) skew * k; }
+        cut[K] = n;
     }
-    for (int k = 0; k < S; ++k) { jobs[k].first = cut[k]; jobs[k].n = cut[k + 1] - cut[k]; }
     for (int k = 0; k < K; ++k) {
+        Job &j = jobs[k];
+        j.first = cut[k];
+        const int next = cut[k + 1];
+        j.n = next - j.first;
         bm2_ctx *l = ctx->lanes[k];
         l->opt = ctx->opt;
         BM2_CUDA_OK(cudaStreamWaitEvent(l->stream, ctx->ev_entry, 0));
     }
-    // bookkeeping over the sub-batches: stage times are summed (GPU time per stage; the stages of different sub-batches overlap, so they
-    // no longer add up to the wall time), counters are totals
-    std::mutex acc_mu;
-    std::vector<float> acc_ms; std::vector<const char *> acc_names;
-    unsigned long long acc_ext = 0, acc_lf = 0, acc_cells = 0; int64_t acc_retry[2] = {0, 0};
-    auto account = [&](const bm2_ctx *l) {
-        std::lock_guard<std::mutex> lk(acc_mu);
-        if (acc_ms.empty()) { acc_names = l->stage_names; acc_ms.assign(l->stage_ms.size(), 0.f); }
-        for (size_t i = 0; i < acc_ms.size() && i < l->stage_ms.size(); ++i) acc_ms[i] += l->stage_ms[i];
-        acc_ext += l->last_n_ext; acc_lf += l->last_n_lf; acc_cells += l->last_cells;
-        acc_retry[0] += l->last_n_retry[0]; acc_retry[1] += l->last_n_retry[1];
-    };
-    auto run_sub = [&](int s, int lane) {
-        Job &j = jobs[s];
-        bm2_ctx *l = ctx->lanes[lane];
+    auto work = [&](int k) {
+        Job &j = jobs[k];
+        bm2_ctx *l = ctx->lanes[k];
         const int64_t base = rb->offsets[j.first];
         j.offs.resize((size_t) j.n + 1);
         for (int i = 0; i <= j.n; ++i) j.offs[i] = rb->offsets[j.first + i] - base;
         j.rb.n_reads = j.n; j.rb.codes = rb->codes ? rb->codes + base : nullptr; j.rb.offsets = j.offs.data();
         // (the device offsets of a resident batch mirror the host offsets: the sub-batch's codes start at `base`)
         j.rc = run_pipeline(l, &j.rb, UPTO_REGS, j.bs, d_codes ? d_codes + base : nullptr, nullptr, false);
-        if (!j.rc) { finish_stage_times(l); account(l); }
+        if (!j.rc) finish_stage_times(l);
     };
-    if (ctx->ensure_host(ctx->h[H_OUT_OFF], (size_t) (n + 1) * 8)) return 1;
-    int64_t *off = (int64_t *) ctx->h[H_OUT_OFF].p;
-    if (W > 1) {
-        // ---- waves: the order of the output is the order of the sub-batches; a sub-batch knows its place when its predecessors know their sizes
-        std::mutex mu; std::condition_variable cv;
-        std::vector<int64_t> nout((size_t) S, -1);
-        bool failed = false;
-        // two events per lane, one per output buffer: the last device -> host copy out of it (a growing host buffer waits for all of them)
-        std::vector<cudaEvent_t> copied((size_t) 2 * K, nullptr);
-        std::vector<char> copied_set((size_t) 2 * K, 0);
-        for (int k = 0; k < 2 * K; ++k) if (cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming) != cudaSuccess) { bm2_set_error(ctx, "sub-batches: event creation failed"); return 1; }
-        for (int k = 0; k < K; ++k)
-            if (!ctx->lanes[k]->copy_stream && cudaStreamCreateWithFlags(&ctx->lanes[k]->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { bm2_set_error(ctx, "sub-batches: stream creation failed"); return 1; }
-        int wave_rc = 0;
-        auto grow = [&](size_t need_regs, size_t keep_regs, size_t hint_regs) -> int {      // (mu held)
-            HostBuf &hb = ctx->h[H_OUT_REGS];
-            if (hb.cap >= need_regs * sizeof(bm2_alnreg_t)) return 0;
-            for (int k = 0; k < 2 * K; ++k) if (copied_set[k] && cudaEventSynchronize(copied[k]) != cudaSuccess) return 1;
-            const size_t want = (need_regs > hint_regs ? need_regs : hint_regs) * sizeof(bm2_alnreg_t);
-            void *np = nullptr;
-            if (cudaMallocHost(&np, want + want / 8 + 256) != cudaSuccess) return 1;
-            if (hb.p && keep_regs) memcpy(np, hb.p, keep_regs * sizeof(bm2_alnreg_t));
-            if (hb.p) cudaFreeHost(hb.p);
-            hb.p = np; hb.cap = want + want / 8 + 256;
-            return 0;
-        };
-        auto lane_work = [&](int lane) {
-            cudaSetDevice(ctx->device);
-            for (int s = lane; s < S; s += K) {
-                { std::lock_guard<std::mutex> lk(mu); if (failed) return; }
-                // the output buffer this sub-batch writes was copied from two sub-batches (of this lane) ago: that copy is long over
-                const int slot = 2 * lane + ((s / K) & 1);
-                if (copied_set[slot] && cudaEventSynchronize(copied[slot]) != cudaSuccess) { std::lock_guard<std::mutex> lk(mu); failed = true; wave_rc = 1; cv.notify_all(); return; }
-                run_sub(s, lane);
-                Job &j = jobs[s];
-                bm2_ctx *l = ctx->lanes[lane];
-                std::unique_lock<std::mutex> lk(mu);
-                if (j.rc) { failed = true; nout[s] = 0; cv.notify_all(); return; }
-                nout[s] = j.bs.n_out;
-                cv.notify_all();
-                cv.wait(lk, [&] { if (failed) return true; for (int q = 0; q < s; ++q) if (nout[q] < 0) return false; return true; });
-                if (failed) return;
-                int64_t pos = 0; for (int q = 0; q < s; ++q) pos += nout[q];
-                const int64_t *lo = (const int64_t *) l->h[H_OUT_OFF].p;
-                for (int i = 0; i < j.n; ++i) off[j.first + i] = lo[i] + pos;
-                if (j.bs.n_out) {
-                    // room for this sub-batch; when the buffer has to grow, for the whole batch at the rate seen so far
-                    const size_t hint = (size_t) ((double) (pos + j.bs.n_out) * (double) n / (double) (j.first + j.n) * 1.05) + 1024;
-                    if (grow((size_t) (pos + j.bs.n_out) + 1, (size_t) pos, hint)) { failed = true; wave_rc = 1; cv.notify_all(); return; }
-                    bm2_alnreg_t *dst = (bm2_alnreg_t *) ctx->h[H_OUT_REGS].p + pos;
-                    // the copy runs on the lane's COPY stream (the sub-batch's kernels are done: run_pipeline ends with a synchronise), and the
-                    // lane's next sub-batch writes the lane's other output buffer - so the lane goes on computing under its own copy
-                    if (cudaMemcpyAsync(dst, l->d[B_OUT].p, (size_t) j.bs.n_out * sizeof(bm2_alnreg_t), cudaMemcpyDeviceToHost, l->copy_stream) != cudaSuccess) { failed = true; wave_rc = 1; cv.notify_all(); return; }
-                }
-                if (cudaEventRecord(copied[slot], l->copy_stream) != cudaSuccess) { failed = true; wave_rc = 1; cv.notify_all(); return; }
-                copied_set[slot] = 1;
-                std::swap(l->d[B_OUT], l->out_alt);
-            }
-        };
-        {
-            std::vector<std::thread> th;
-            for (int k = 1; k < K; ++k) th.emplace_back(lane_work, k);
-            lane_work(0);
-            for (auto &t : th) t.join();
-        }
-        for (int k = 0; k < K; ++k) { cudaStreamSynchronize(ctx->lanes[k]->stream); cudaStreamSynchronize(ctx->lanes[k]->copy_stream); }
-        for (int k = 0; k < 2 * K; ++k) cudaEventDestroy(copied[k]);
-        for (int s = 0; s < S; ++s)
-            if (jobs[s].rc) { bm2_set_error(ctx, "sub-batch " + std::to_string(s) + ": " + ctx->lanes[s % K]->err); return 1; }
-        if (wave_rc || failed) { bm2_set_error(ctx, "sub-batches: output copy failed"); return 1; }
-        int64_t n_out = 0; for (int s = 0; s < S; ++s) n_out += jobs[s].bs.n_out;
-        if (n_out == 0 && ctx->ensure_host(ctx->h[H_OUT_REGS], sizeof(bm2_alnreg_t))) return 1;
-        off[n] = n_out;
-        ctx->stage_names = acc_names; ctx->stage_ms = acc_ms;
-        ctx->last_n_ext = acc_ext; ctx->last_n_lf = acc_lf; ctx->last_cells = acc_cells; ctx->last_n_retry[0] = acc_retry[0]; ctx->last_n_retry[1] = acc_retry[1];
-        out->n = n_out; out->regs = (const bm2_alnreg_t *) ctx->h[H_OUT_REGS].p; out->read_off = off;
-        return 0;
-    }
-    auto work = [&](int k) { run_sub(k, k); };
     if (getenv("BM2_SUB_BATCHES_SERIAL")) {        // debugging aid: the same split, one sub-batch after the other
         for (int k = 0; k < K; ++k) work(k);
     } else {
@@ -1399,7 +1307,8 @@ static int run_regs(bm2_ctx *ctx, const bm2_read_batch *rb, const uint8_t *d_cod
     // gather: per-read offsets on the host, regs device -> the context's pinned buffer, one copy per lane on its own stream
     int64_t n_out = 0;
     for (int k = 0; k < K; ++k) n_out += jobs[k].bs.n_out;
-    if (ctx->ensure_host(ctx->h[H_OUT_REGS], (size_t) (n_out + 1) * sizeof(bm2_alnreg_t))) return 1;
+    if (ctx->ensure_host(ctx->h[H_OUT_OFF], (size_t) (n + 1) * 8) || ctx->ensure_host(ctx->h[H_OUT_REGS], (size_t) (n_out + 1) * sizeof(bm2_alnreg_t))) return 1;
+    int64_t *off = (int64_t *) ctx->h[H_OUT_OFF].p;
     bm2_alnreg_t *regs = (bm2_alnreg_t *) ctx->h[H_OUT_REGS].p;
     int64_t pos = 0;
     for (int k = 0; k < K; ++k) {
@@ -1413,8 +1322,17 @@ static int run_regs(bm2_ctx *ctx, const bm2_read_batch *rb, const uint8_t *d_cod
     }
     off[n] = n_out;
     for (int k = 0; k < K; ++k) BM2_CUDA_OK(cudaStreamSynchronize(ctx->lanes[k]->stream));
-    ctx->stage_names = acc_names; ctx->stage_ms = acc_ms;
-    ctx->last_n_ext = acc_ext; ctx->last_n_lf = acc_lf; ctx->last_cells = acc_cells; ctx->last_n_retry[0] = acc_retry[0]; ctx->last_n_retry[1] = acc_retry[1];
+    // bookkeeping: stage times are summed over the sub-batches (GPU time per stage; the stages of different
+    // sub-batches overlap, so they no longer add up to the wall time), counters are totals
+    ctx->stage_names = ctx->lanes[0]->stage_names;
+    ctx->stage_ms.assign(ctx->lanes[0]->stage_ms.size(), 0.f);
+    ctx->last_n_ext = ctx->last_n_lf = ctx->last_cells = 0; ctx->last_n_retry[0] = ctx->last_n_retry[1] = 0;
+    for (int k = 0; k < K; ++k) {
+        const bm2_ctx *l = ctx->lanes[k];
+        for (size_t i = 0; i < ctx->stage_ms.size() && i < l->stage_ms.size(); ++i) ctx->stage_ms[i] += l->stage_ms[i];
+        ctx->last_n_ext += l->last_n_ext; ctx->last_n_lf += l->last_n_lf; ctx->last_cells += l->last_cells;
+        ctx->last_n_retry[0] += l->last_n_retry[0]; ctx->last_n_retry[1] += l->last_n_retry[1];
+    }
     out->n = n_out; out->regs = copy_out ? regs : nullptr; out->read_off = off;
     return 0;
 }

@@ -8,17 +8,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package
 
-KNOBS = ("BM2_D2H_WAVES", "BM2_TAIL_COOP", "BM2_LIGHT_SORTED", "BM2_BSW_UNROLL8", "BM2_TAIL_HEAVY", "BM2_CHAIN_HEAVY", "BM2_BSW_DYN", "BM2_SMEM_TEXT", "BM2_LANE_SKEW", "BM2_STAGE_TOKENS", "BM2_BSW_REGSHRINK", "BM2_CHAIN_COOP_MIN", "BM2_BSW_NTHR", "BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
+KNOBS = ("BM2_TAIL_COOP", "BM2_LIGHT_SORTED", "BM2_BSW_UNROLL8", "BM2_TAIL_HEAVY", "BM2_CHAIN_HEAVY", "BM2_BSW_DYN", "BM2_SMEM_TEXT", "BM2_LANE_SKEW", "BM2_STAGE_TOKENS", "BM2_BSW_REGSHRINK", "BM2_CHAIN_COOP_MIN", "BM2_BSW_NTHR", "BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
 CONFIGS = [
     dict(name="default, sub 4", sub=4),
+    dict(name="default, sub 1", sub=1),
     dict(name="end to end (host buffers), sub 4", sub=4, e2e=True),
-    dict(name="end to end, sub 4, 2 waves", sub=4, e2e=True, BM2_D2H_WAVES="2"),
-    dict(name="end to end, sub 4, 3 waves", sub=4, e2e=True, BM2_D2H_WAVES="3"),
-    dict(name="end to end, sub 3, 3 waves", sub=3, e2e=True, BM2_D2H_WAVES="3"),
-    dict(name="end to end, sub 2, 4 waves", sub=2, e2e=True, BM2_D2H_WAVES="4"),
-    dict(name="end to end, sub 6, 2 waves", sub=6, e2e=True, BM2_D2H_WAVES="2"),
-    dict(name="end to end (host buffers), sub 4 (again)", sub=4, e2e=True),
-    dict(name="end to end, sub 4, 2 waves (again)", sub=4, e2e=True, BM2_D2H_WAVES="2"),
+    dict(name="end to end (host buffers), sub 6", sub=6, e2e=True),
     dict(name="default, sub 4 (again)", sub=4),
 ]
 
@@ -76,7 +71,7 @@ def main():
     # parity of one knob setting against another on a slice (regs must be byte-identical whatever the knobs)
     ns = 65536
     outs = []
-    for env in (dict(BM2_BSW_COL2="0", BM2_STAGE_TOKENS="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5"), dict(BM2_BSW_REGSHRINK="1", BM2_CHAIN_COOP_MIN="64"), dict(BM2_SMEM_TEXT="0", BM2_BSW_DYN="0", BM2_LIGHT_SORTED="1", BM2_TAIL_COOP="0"), dict(BM2_TAIL_HEAVY="2", BM2_CHAIN_HEAVY="16", BM2_BSW_UNROLL8="1"), dict(BM2_BSW_REGSHRINK="0", BM2_D2H_WAVES="2")):
+    for env in (dict(BM2_BSW_COL2="0", BM2_STAGE_TOKENS="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5"), dict(BM2_BSW_REGSHRINK="1", BM2_CHAIN_COOP_MIN="64"), dict(BM2_SMEM_TEXT="0", BM2_BSW_DYN="0", BM2_LIGHT_SORTED="1", BM2_TAIL_COOP="0"), dict(BM2_TAIL_HEAVY="2", BM2_CHAIN_HEAVY="16", BM2_BSW_UNROLL8="1"), dict(BM2_BSW_REGSHRINK="0")):
         for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update(env)

@@ -142,24 +142,6 @@ def test_second_dataset_against_oracle(pkg):
         ctx.set_sub_batches(k, 512)
         regs3, ro3 = ctx.seed_chain_extend(codes, offs)
         assert regs.tobytes() == regs3.tobytes() and np.array_equal(ro, ro3), k
-    # waves (BM2_D2H_WAVES): 2 lanes x 2 / 3 x 3 sub-batches, every lane several sub-batches in a row, the regs of a sub-batch copied to their
-    # place in the output as soon as its predecessors are done; a fresh context too (its output buffer grows while copies are in flight)
-    try:
-        for k, w in ((2, 2), (3, 3), (2, 5)):
-            os.environ["BM2_D2H_WAVES"] = str(w)
-            ctx.set_sub_batches(k, 512)
-            regs5, ro5 = ctx.seed_chain_extend(codes, offs)
-            assert regs.tobytes() == regs5.tobytes() and np.array_equal(ro, ro5), (k, w)
-        ctx_w = pkg.capi.Context(0, index=idx)
-        ctx_w.set_sub_batches(2, 512)
-        regs6, ro6 = ctx_w.seed_chain_extend(codes, offs)
-        assert regs.tobytes() == regs6.tobytes() and np.array_equal(ro, ro6)
-        regs6, ro6 = ctx_w.seed_chain_extend(codes[:151 * 2048], offs[:2049])
-        n6 = int(ro[2048])
-        assert regs[:n6].tobytes() == regs6.tobytes() and np.array_equal(ro[:2049], ro6)
-        ctx_w.close()
-    finally:
-        os.environ.pop("BM2_D2H_WAVES", None)
     d_codes = torch.from_numpy(codes).cuda(); d_offs = torch.from_numpy(offs).cuda()
     torch.cuda.synchronize()
     regs4, ro4 = ctx.seed_chain_extend_resident(codes, offs, d_codes.data_ptr(), d_offs.data_ptr(), True, return_arrays=True)
