@@ -12,7 +12,13 @@ KNOBS = ("BM2_TAIL_COOP", "BM2_LIGHT_SORTED", "BM2_BSW_UNROLL8", "BM2_TAIL_HEAVY
 CONFIGS = [
     dict(name="default, sub 4", sub=4),
     dict(name="default, sub 1", sub=1),
+    dict(name="sub 4, SMEM kernels 6 CTAs per SM", sub=4, BM2_SMEM_CTAS="6"),
+    dict(name="sub 4, SMEM kernels 10 CTAs per SM", sub=4, BM2_SMEM_CTAS="10"),
+    dict(name="sub 3", sub=3),
+    dict(name="sub 5", sub=5),
     dict(name="end to end (host buffers), sub 4", sub=4, e2e=True),
+    dict(name="end to end (host buffers), sub 3", sub=3, e2e=True),
+    dict(name="end to end (host buffers), sub 5", sub=5, e2e=True),
     dict(name="end to end (host buffers), sub 6", sub=6, e2e=True),
     dict(name="default, sub 4 (again)", sub=4),
 ]
