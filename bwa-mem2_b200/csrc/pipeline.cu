@@ -24,6 +24,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <vector>
+#include <algorithm>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -503,35 +504,49 @@ __device__ void ext_postfilter_read_warp(const ExtParams &p, const bm2_chain *ch
         for (int k = n - 1; k >= 0; --k) {
             const bm2_seed s = cs[srt2[k]];
             int v = 0;
-            for (int i0 = 0; i0 < n_reg && v < lim; i0 += 32) {
-                const int i = i0 + lane;
-                int kind = 0;                                   // 0 skipped, 1 counted, 2 hit
-                if (i < n_reg) {
-                    const PfBox q = box[i];
-                    if (!(q.qb == -1 && q.qe == -1)) {
-                        kind = 1;
-                        if (!(s.rbeg < q.rb || s.rbeg + s.len > q.re || s.qbeg < q.qb || s.qbeg + s.len > q.qe) &&
-                            !(s.len - q.seedlen0 > .1 * l_query)) {
-                            int64_t rd; int qd, w, max_gap;
-                            qd = s.qbeg - q.qb; rd = s.rbeg - q.rb;
-                            max_gap = cal_max_gap_d(p, qd < rd ? qd : (int) rd);
-                            w = max_gap < q.w ? max_gap : q.w;
-                            if (qd - rd < w && rd - qd < w) kind = 2;
-                            else {
-                                qd = q.qe - (s.qbeg + s.len); rd = q.re - (s.rbeg + s.len);
+            // The boxes of FOUR 32-box steps are classified before the first of them is resolved (the loads and tests of a lane's four boxes
+            // overlap; a read inside a high-copy repeat has thousands of regs and its scan - O(regs) per seed, one dependent shared-nothing
+            // load -> test -> ballot chain per step - is the critical path of the whole kernel); the resolution keeps the sequential loop's
+            // order: step by step, stopping at the first step whose count reaches lim or whose first hit still lies below it.
+            bool hit = false;
+            for (int i0 = 0; i0 < n_reg && v < lim && !hit; i0 += 128) {
+                int kind[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int i = i0 + 32 * g + lane;
+                    int kd = 0;                                 // 0 skipped, 1 counted, 2 hit
+                    if (i < n_reg) {
+                        const PfBox q = box[i];
+                        if (!(q.qb == -1 && q.qe == -1)) {
+                            kd = 1;
+                            if (!(s.rbeg < q.rb || s.rbeg + s.len > q.re || s.qbeg < q.qb || s.qbeg + s.len > q.qe) &&
+                                !(s.len - q.seedlen0 > .1 * l_query)) {
+                                int64_t rd; int qd, w, max_gap;
+                                qd = s.qbeg - q.qb; rd = s.rbeg - q.rb;
                                 max_gap = cal_max_gap_d(p, qd < rd ? qd : (int) rd);
                                 w = max_gap < q.w ? max_gap : q.w;
-                                if (qd - rd < w && rd - qd < w) kind = 2;
+                                if (qd - rd < w && rd - qd < w) kd = 2;
+                                else {
+                                    qd = q.qe - (s.qbeg + s.len); rd = q.re - (s.rbeg + s.len);
+                                    max_gap = cal_max_gap_d(p, qd < rd ? qd : (int) rd);
+                                    w = max_gap < q.w ? max_gap : q.w;
+                                    if (qd - rd < w && rd - qd < w) kd = 2;
+                                }
                             }
                         }
                     }
+                    kind[g] = kd;
                 }
-                const unsigned cm = __ballot_sync(0xFFFFFFFFu, kind == 1), hm = __ballot_sync(0xFFFFFFFFu, kind == 2);
-                if (hm) {
-                    const int at = v + __popc(cm & ((1u << (__ffs(hm) - 1)) - 1u));
-                    if (at < lim) { v = at; break; }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const unsigned cm = __ballot_sync(0xFFFFFFFFu, kind[g] == 1), hm = __ballot_sync(0xFFFFFFFFu, kind[g] == 2);
+                    if (hit || v >= lim || i0 + 32 * g >= n_reg) continue;       // (warp-uniform: the ballots above are taken by all lanes)
+                    if (hm) {
+                        const int at = v + __popc(cm & ((1u << (__ffs(hm) - 1)) - 1u));
+                        if (at < lim) { v = at; hit = true; continue; }
+                    }
+                    v += __popc(cm);
                 }
-                v += __popc(cm);
             }
             if (v < lim) {
                 int vv;
@@ -1151,6 +1166,19 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     const int heavy_thr = env_int("BM2_TAIL_HEAVY", 24, 1, 1 << 20);            // regs from which a read gets a warp
     work_keys_off_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_reg_off, n, wk_in, wv_in);
     if (sort_work(ctx, wk_in, wk_out, wv_in, d_perm, n, true)) return 1;          // decreasing number of regs
+    if (getenv("BM2_DEBUG_NREG")) {     // the heaviest reads of the batch (their tail is the critical path of the warp-per-read kernel): stderr
+        std::vector<int64_t> ho((size_t) n + 1);
+        BM2_CUDA_OK(cudaMemcpyAsync(ho.data(), d_reg_off, (size_t) (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+        BM2_CUDA_OK(cudaStreamSynchronize(st));
+        std::vector<int64_t> cntv((size_t) n);
+        for (int i = 0; i < n; ++i) cntv[i] = ho[i + 1] - ho[i];
+        std::sort(cntv.begin(), cntv.end(), [](int64_t a, int64_t b) { return a > b; });
+        long long c24 = 0, c256 = 0, c1024 = 0; double sq = 0;
+        for (int i = 0; i < n; ++i) { c24 += cntv[i] > 24; c256 += cntv[i] > 256; c1024 += cntv[i] > 1024; if (cntv[i] > 24) sq += (double) cntv[i] * (double) cntv[i]; }
+        fprintf(stderr, "[bm2 debug] regs before the tail: reads %d, > 24: %lld, > 256: %lld, > 1024: %lld, sum of squares over the heavy reads %.3g; heaviest:", n, c24, c256, c1024, sq);
+        for (int i = 0; i < 8 && i < n; ++i) fprintf(stderr, " %lld", (long long) cntv[i]);
+        fprintf(stderr, "\n");
+    }
     tail_kernel<0><<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
                                              d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, heavy_thr, light_sorted, 0);
     tail_kernel<1><<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,

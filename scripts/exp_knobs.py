@@ -10,16 +10,9 @@ from __graft_entry__ import load_package
 
 KNOBS = ("BM2_TAIL_COOP", "BM2_LIGHT_SORTED", "BM2_BSW_UNROLL8", "BM2_TAIL_HEAVY", "BM2_CHAIN_HEAVY", "BM2_BSW_DYN", "BM2_SMEM_TEXT", "BM2_LANE_SKEW", "BM2_STAGE_TOKENS", "BM2_BSW_REGSHRINK", "BM2_CHAIN_COOP_MIN", "BM2_BSW_NTHR", "BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
 CONFIGS = [
-    dict(name="default, sub 4", sub=4),
     dict(name="default, sub 1", sub=1),
-    dict(name="sub 4, SMEM kernels 6 CTAs per SM", sub=4, BM2_SMEM_CTAS="6"),
-    dict(name="sub 4, SMEM kernels 10 CTAs per SM", sub=4, BM2_SMEM_CTAS="10"),
-    dict(name="sub 3", sub=3),
-    dict(name="sub 5", sub=5),
-    dict(name="end to end (host buffers), sub 4", sub=4, e2e=True),
-    dict(name="end to end (host buffers), sub 3", sub=3, e2e=True),
-    dict(name="end to end (host buffers), sub 5", sub=5, e2e=True),
-    dict(name="end to end (host buffers), sub 6", sub=6, e2e=True),
+    dict(name="default, sub 4", sub=4),
+    dict(name="default, sub 1 (again)", sub=1),
     dict(name="default, sub 4 (again)", sub=4),
 ]
 
