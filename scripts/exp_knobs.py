@@ -26,6 +26,9 @@ def main():
     pkg = load_package(); capi = pkg.capi
     work = sys.argv[1]
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    if not os.path.exists(os.path.join(work, "reads.npy")):      # same inputs as bench.py's default workload
+        import bench
+        bench.prepare_pipeline_inputs(work, 3_000_000_000, 500_000, seed=21)
     reads = np.load(os.path.join(work, "reads.npy"))
     n, L = reads.shape
     codes = reads.reshape(-1); offs = np.arange(n + 1, dtype=np.int64) * L
