@@ -682,7 +682,9 @@ __device__ int ext_tail_read_warp(const ContigView &cv, const ExtParams &p, cons
 
 // I. one read per thread (grid-stride: the NW scratch `he` is per thread)
 template <int mode>             // separate instances: the warp-per-read code (more registers) must not cost the per-thread pass its occupancy (96)
-__global__ void __launch_bounds__(128, mode == 2 ? 8 : mode == 3 ? 6 : mode ? 4 : 1)      // (modes 2, 3: mode 1's code at 64 / 80 registers: A/B of occupancy against spills)
+// (mode 1 at 4 CTAs per SM = 128 registers.  Compiled for 6 / 8 CTAs - 80 / 64 registers, 350-470 B of spills - it was no faster: 13.0 / 13.4 against
+// 12.6 ms, profiles/r2t_exp_knobs.log: more resident warps do not help this kernel.)
+__global__ void __launch_bounds__(128, mode ? 4 : 1)
 tail_kernel(ContigView cv, ExtParams ep, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ codes, const int64_t *__restrict__ offs,
             const bm2_chain *__restrict__ chains, const bm2_seed *__restrict__ seeds, const int64_t *__restrict__ chain_off,
             const int64_t *__restrict__ reg_off, int n_reads, bm2_alnreg_t *regs, const int32_t *reg_seed, int32_t *srt2_all, int32_t *he_all,
@@ -1181,14 +1183,8 @@ int run_pipeline(bm2_ctx *ctx, const bm2_read_batch *rb, UpTo upto, BatchState &
     }
     tail_kernel<0><<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
                                              d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, heavy_thr, light_sorted, 0);
-    {
-        const int occ = env_int("BM2_TAIL_OCC", 4, 4, 8);                      // resident CTAs per SM the warp-per-read instance is compiled for
-        const int coop = env_int("BM2_TAIL_COOP", 1, 0, 1);
-#define BM2_TAIL_HEAVY_LAUNCH(M) tail_kernel<M><<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), \
-            d_chain_off, d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, heavy_thr, 0, coop)
-        if (occ >= 8) BM2_TAIL_HEAVY_LAUNCH(2); else if (occ >= 6) BM2_TAIL_HEAVY_LAUNCH(3); else BM2_TAIL_HEAVY_LAUNCH(1);
-#undef BM2_TAIL_HEAVY_LAUNCH
-    }
+    tail_kernel<1><<<blocks_i, 128, 0, st>>>(pv.cv, pv.ep, ctx->idx.ref, d_codes, d_offs, P<bm2_chain>(ctx, B_CHAINS), P<bm2_seed>(ctx, B_SEEDS), d_chain_off,
+                                             d_reg_off, n, d_regs, d_reg_seed, d_srt2, P<int32_t>(ctx, B_NW), he_stride, d_perm, d_box, d_nfinal, heavy_thr, 0, env_int("BM2_TAIL_COOP", 1, 0, 1));
 
     // ---- J. output ---------------------------------------------------------------------------------------
     if (sg.mark("output")) return 1;

@@ -8,15 +8,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package
 
-KNOBS = ("BM2_TAIL_OCC", "BM2_TAIL_COOP", "BM2_LIGHT_SORTED", "BM2_BSW_UNROLL8", "BM2_TAIL_HEAVY", "BM2_CHAIN_HEAVY", "BM2_BSW_DYN", "BM2_SMEM_TEXT", "BM2_LANE_SKEW", "BM2_STAGE_TOKENS", "BM2_BSW_REGSHRINK", "BM2_CHAIN_COOP_MIN", "BM2_BSW_NTHR", "BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
+KNOBS = ("BM2_TAIL_COOP", "BM2_LIGHT_SORTED", "BM2_BSW_UNROLL8", "BM2_TAIL_HEAVY", "BM2_CHAIN_HEAVY", "BM2_BSW_DYN", "BM2_SMEM_TEXT", "BM2_LANE_SKEW", "BM2_STAGE_TOKENS", "BM2_BSW_REGSHRINK", "BM2_CHAIN_COOP_MIN", "BM2_BSW_NTHR", "BM2_BSW_COL2", "BM2_BSW_SMEM_KB", "BM2_BSW_MAX_CTAS", "BM2_SMEM_CTAS", "BM2_SMEM_P3_CTAS", "BM2_STAGE_TOKENS")
 CONFIGS = [
-    dict(name="default (tail warp kernel for 4 CTAs per SM), sub 1", sub=1),
-    dict(name="tail warp kernel for 6 CTAs per SM, sub 1", sub=1, BM2_TAIL_OCC="6"),
-    dict(name="tail warp kernel for 8 CTAs per SM, sub 1", sub=1, BM2_TAIL_OCC="8"),
-    dict(name="default, sub 1 (again)", sub=1),
+    dict(name="default, sub 1", sub=1),
     dict(name="default, sub 4", sub=4),
-    dict(name="tail warp kernel for 6 CTAs per SM, sub 4", sub=4, BM2_TAIL_OCC="6"),
-    dict(name="tail warp kernel for 8 CTAs per SM, sub 4", sub=4, BM2_TAIL_OCC="8"),
+    dict(name="default, sub 1 (again)", sub=1),
     dict(name="default, sub 4 (again)", sub=4),
 ]
 
@@ -77,7 +73,7 @@ def main():
     # parity of one knob setting against another on a slice (regs must be byte-identical whatever the knobs)
     ns = 65536
     outs = []
-    for env in (dict(BM2_BSW_COL2="0", BM2_STAGE_TOKENS="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5"), dict(BM2_BSW_REGSHRINK="1", BM2_CHAIN_COOP_MIN="64"), dict(BM2_SMEM_TEXT="0", BM2_BSW_DYN="0", BM2_LIGHT_SORTED="1", BM2_TAIL_COOP="0"), dict(BM2_TAIL_HEAVY="2", BM2_CHAIN_HEAVY="16", BM2_BSW_UNROLL8="1"), dict(BM2_BSW_REGSHRINK="0", BM2_TAIL_OCC="8"), dict(BM2_TAIL_OCC="6")):
+    for env in (dict(BM2_BSW_COL2="0", BM2_STAGE_TOKENS="0"), dict(), dict(BM2_BSW_MAX_CTAS="3", BM2_SMEM_CTAS="5"), dict(BM2_BSW_REGSHRINK="1", BM2_CHAIN_COOP_MIN="64"), dict(BM2_SMEM_TEXT="0", BM2_BSW_DYN="0", BM2_LIGHT_SORTED="1", BM2_TAIL_COOP="0"), dict(BM2_TAIL_HEAVY="2", BM2_CHAIN_HEAVY="16", BM2_BSW_UNROLL8="1"), dict(BM2_BSW_REGSHRINK="0")):
         for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update(env)
