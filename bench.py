@@ -519,12 +519,9 @@ def run_pipeline(args, rank, world):
         out = {"metric": METRIC, "value": value,
                "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/int16", "data": "synthetic",
-               "config": {"workload": f"config[2]-like: full GPU pipeline (SMEM, SA lookup, chaining, BSW, post-filter), {n} reads/step/GPU "
-                                      f"(2x151 bp pairs, 1% subs, 25% reads with an indel, 1% garbage) vs {args.ref_mbp} Mbp synthetic reference "
-                                      f"(planted repeat families; index files {index_how})",
-                          "l2": "256 MB flush between steps; FM-index %d MB" % (index.desc.reference_seq_len // 64 * 64 // 1_000_000),
-                          "sub_batches_in_flight": args.sub_batches,
-                          "regs_per_step": int(n_regs)},
+               "config": pipeline_config(args),          # the same object in the reference arm's line
+               "config_detail": {"index_files": index_how, "l2": "256 MB flush between steps; FM-index %d MB" % (index.desc.reference_seq_len // 64 * 64 // 1_000_000),
+                                 "sub_batches_in_flight": args.sub_batches, "regs_per_step": int(n_regs)},
                "e2e": {"value": world * n / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(codes.nbytes + offs.nbytes),
                        "d2h_bytes_per_step": int(n_out * capi.REG_DT.itemsize + offs.nbytes)},
                # our own kernels per step and sub-batch (profiles/r1n_kernel_traffic_3gbp.md: 115 launches, 48 of them cub sort/scan)
@@ -942,6 +939,13 @@ def run_fastq2sam(args, rank, world):
     return out
 
 
+def pipeline_config(args):
+    """`config` of the default workload, identical in both arms' lines (the driver compares them)."""
+    return {"workload": f"config[2]-like: seed+chain+extend hot path (SMEM, SA lookup, chaining, BSW, post-filter), {2 * args.pairs} reads/step/GPU "
+                        f"(2x151 bp pairs, 1% subs, 25% reads with an indel, 1% garbage) vs {args.ref_mbp} Mbp synthetic reference (planted repeat families), "
+                        "L2 flushed between steps (256 MB)"}
+
+
 def run_reference_pipeline(args, rank, world):
     """--impl reference: the unmodified reference's worker_bwt + worker_aln on the host cores, same metric / config as our arm.
     Each step = the first `sample` pairs of the same 1 M-read workload (bounded: the whole run ends within minutes); one process,
@@ -958,9 +962,9 @@ def run_reference_pipeline(args, rank, world):
     return {"impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64/int16", "data": "synthetic",
-            "config": {"workload": f"config[2]-like: worker_bwt + worker_aln of the unmodified reference ({_isa()}) on the first {n} reads per step of the "
-                                   f"GPU arm's workload ({2 * args.pairs} synthetic 2x151 reads vs {args.ref_mbp} Mbp synthetic reference, same index files)",
-                       "sample": f"{n} reads per step (bounded sample), {nt} threads"},
+            "config": pipeline_config(args),            # the GPU arm's config; what this arm ran of it: config_detail / cpu_baseline.sample
+            "config_detail": {"how": f"worker_bwt + worker_aln of the unmodified reference ({_isa()}) on the first {n} reads per step of that workload "
+                                     f"(bounded sample), {nt} threads, same index files"},
             "cpu_baseline": {"value": v, "unit": "reads/s", "cores": nt, "kind": "reference",
                              "sample": f"{n} reads per step, kt_for over {nt} threads, one process, {len(vals)} timed repetitions",
                              "per_repetition": [round(x, 1) for x in vals], "host": hi},
