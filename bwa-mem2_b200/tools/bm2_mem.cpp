@@ -16,7 +16,7 @@
 // (bm2_create_sibling: one index in HBM) and take whole chunks off a queue; the GPU interleaves the kernels of the two chunks, the host side of
 // one (pestat, formatting, fwrite) runs under the GPU stages of the other, and the output is written strictly in chunk order.
 // The SAM records equal `bwa-mem2 mem` with the same -K (tests/test_zz_fastq_sam_gpu.py); the header carries the same @SQ lines and
-// this program's own @PG line.  Plain (uncompressed) FASTQ with four-line records; the files are read whole.
+// this program's own @PG line.  FASTQ with four-line records, plain or gzip; the files are read whole.
 #include "bm2_b200.h"
 #include <chrono>
 #include <condition_variable>
@@ -28,12 +28,36 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <zlib.h>
 
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// the whole file into memory; gzip files (magic 1f 8b) through zlib, as the reference reads its input through zlib (gzdopen + kseq, src/fastmap.cpp:
+// 905-907, :933-935) - gzread also passes plain files through, but the plain path below needs no copy loop
 static bool read_file(const char *path, std::vector<char> &buf) {
     FILE *f = fopen(path, "rb");
     if (!f) return false;
+    unsigned char magic[2] = {0, 0};
+    const size_t got = fread(magic, 1, 2, f);
+    if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+        fclose(f);
+        gzFile g = gzopen(path, "rb");
+        if (!g) return false;
+        gzbuffer(g, 1 << 20);
+        size_t n = 0;
+        buf.resize((size_t) 64 << 20);
+        for (;;) {
+            if (buf.size() - n < ((size_t) 16 << 20)) buf.resize(buf.size() * 2);
+            const size_t want = buf.size() - n < ((size_t) 1 << 30) ? buf.size() - n : ((size_t) 1 << 30);
+            const int r = gzread(g, buf.data() + n, (unsigned) want);
+            if (r < 0) { gzclose(g); return false; }
+            if (r == 0) break;
+            n += (size_t) r;
+        }
+        gzclose(g);
+        buf.resize(n);
+        return true;
+    }
     fseek(f, 0, SEEK_END); const long n = ftell(f); fseek(f, 0, SEEK_SET);
     buf.resize((size_t) n);
     const bool ok = n == 0 || fread(buf.data(), 1, (size_t) n, f) == (size_t) n;

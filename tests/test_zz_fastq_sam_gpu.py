@@ -82,8 +82,8 @@ def test_fastq_bytes_to_sam_text_equals_the_reference(pkg, golden_dir, staged):
     ctx.close(); idx.close()
 
 
-@pytest.mark.parametrize("K,workers", [(100_000_000, 2), (40_000, 1), (40_000, 2), (15_000, 3)])
-def test_bm2_mem_program_prints_the_reference_sam(pkg, golden_dir, tmp_path, K, workers):
+@pytest.mark.parametrize("K,workers,gz", [(100_000_000, 2, False), (40_000, 1, False), (40_000, 2, True), (15_000, 3, False)])
+def test_bm2_mem_program_prints_the_reference_sam(pkg, golden_dir, tmp_path, K, workers, gz):
     """The C++ host program over the C ABI (bwa-mem2_b200/tools/bm2_mem.cpp): FASTQ files in, SAM file out, chunked by -K like the reference's
     reader; against the unmodified reference run live with the same -K (several chunks: mem_pestat per chunk, id offsets across chunks).
     -p workers: chunks in flight at a time, each on its own context (bm2_create_sibling), output in chunk order."""
@@ -98,6 +98,12 @@ def test_bm2_mem_program_prints_the_reference_sam(pkg, golden_dir, tmp_path, K, 
     reads = np.load(golden_dir + "/c0_reads.npz")["reads"]
     r1, r2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
     synth.write_fastq(r1, reads[0::2], "p"); synth.write_fastq(r2, reads[1::2], "p")
+    if gz:          # gzip input, as real read files come (both programs read it through zlib)
+        import gzip, shutil
+        for pth in (r1, r2):
+            with open(pth, "rb") as fi, gzip.open(pth + ".gz", "wb", compresslevel=1) as fo:
+                shutil.copyfileobj(fi, fo)
+        r1, r2 = r1 + ".gz", r2 + ".gz"
     prefix = golden_dir + "/c0_index/ref.fa"
     out = str(tmp_path / "out.sam")
     o = subprocess.run([tool, "-t", "4", "-K", str(K), "-p", str(workers), "-o", out, prefix, r1, r2], capture_output=True, text=True, timeout=600)
